@@ -1,0 +1,134 @@
+"""ctypes binding of libhoigen_b200.so (the C ABI declared in include/hoigen_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises. Torch is used only to
+obtain device pointers and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+from ._build import LIB_PATH
+
+ACT_NONE, ACT_QUICKGELU, ACT_RELU = 0, 1, 2
+
+
+class HoigenError(RuntimeError):
+    pass
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("lda", C.c_int32), ("ldw", C.c_int32),
+        ("bias", C.c_void_p), ("colscale", C.c_void_p),
+        ("act", C.c_int32),
+        ("residual", C.c_void_p), ("ld_res", C.c_int32),
+        ("out_f32", C.c_void_p), ("ld_f32", C.c_int32),
+        ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int32),
+        ("block_n", C.c_int32),
+    ]
+
+
+_lib = None
+_inited_devices = set()
+
+
+def lib_path() -> Path:
+    return Path(os.environ.get("HOIGEN_B200_LIB", str(LIB_PATH)))
+
+
+def load() -> C.CDLL:
+    """dlopen the C-ABI library (no CUDA call is made here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not path.exists():
+        raise HoigenError(
+            f"{path} not found: build it with `python -m hoigen_b200._build` (or __graft_entry__.build()). "
+            "hoigen_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(str(path))
+    lib.hoigen_abi_version.restype = C.c_int
+    lib.hoigen_last_error.restype = C.c_char_p
+    lib.hoigen_init.argtypes = [C.c_int]
+    for name, sig in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = sig
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().hoigen_last_error().decode(errors="replace")
+        raise HoigenError(f"{what} failed (status {rc}): {msg}")
+
+
+def init(device: torch.device | int | None = None) -> C.CDLL:
+    lib = load()
+    if not torch.cuda.is_available():
+        raise HoigenError("hoigen_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _inited_devices:
+        check(lib.hoigen_init(idx), "hoigen_init")
+        _inited_devices.add(idx)
+    return lib
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t: torch.Tensor | None) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+# name -> argtypes; populated below, one entry per symbol in include/hoigen_b200.h
+_SIGNATURES: dict[str, list] = {
+    "hoigen_gemm_bf16": [C.POINTER(GemmParams), C.c_void_p],
+    "hoigen_debug_gemm_simt": [C.POINTER(GemmParams), C.c_void_p],
+}
+
+EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", *_SIGNATURES.keys()]
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act=ACT_NONE, residual=None,
+              out_f32=None, out_bf16=None, block_n: int = 0, simt: bool = False) -> None:
+    """out = epi(a[M,K] @ w[N,K]^T); see hoigen_gemm_bf16 in include/hoigen_b200.h."""
+    lib = init(a.device)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    p = GemmParams()
+    p.a, p.w = a.data_ptr(), w.data_ptr()
+    p.M, p.N, p.K = M, N, K
+    p.lda, p.ldw = a.stride(0), w.stride(0)
+    for name, t in (("bias", bias), ("colscale", colscale)):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.numel() == N and t.is_contiguous()
+            setattr(p, name, t.data_ptr())
+    p.act = act
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(1) == 1
+        p.residual, p.ld_res = residual.data_ptr(), residual.stride(0)
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32 and out_f32.stride(1) == 1 and out_f32.shape[0] >= M
+        p.out_f32, p.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out_bf16 is not None:
+        assert out_bf16.dtype == torch.bfloat16 and out_bf16.stride(1) == 1 and out_bf16.shape[0] >= M
+        p.out_bf16, p.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    p.block_n = block_n
+    fn = lib.hoigen_debug_gemm_simt if simt else lib.hoigen_gemm_bf16
+    check(fn(C.byref(p), stream_ptr()), "hoigen_gemm_bf16")

@@ -1,0 +1,142 @@
+#include "common.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+namespace hoigen {
+
+static thread_local char g_err[512] = "";
+static int g_num_sms = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int resolve_driver() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return 0;
+}
+
+struct TmapKey {
+  uint64_t v[10];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 10; ++i) {
+      h ^= k.v[i];
+      h *= 1099511628211ull;
+    }
+    return size_t(h);
+  }
+};
+// CUtensorMap must stay at a stable 64-byte aligned address: heap-allocate each entry.
+static std::unordered_map<TmapKey, CUtensorMap*, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+
+static const CUtensorMap* get_tmap(int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides,
+                                   const uint32_t* box) {
+  if (resolve_driver() != 0) return nullptr;
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.v[0] = reinterpret_cast<uint64_t>(ptr);
+  key.v[1] = uint64_t(rank);
+  for (int i = 0; i < rank; ++i) {
+    key.v[2 + i] = dims[i];
+    key.v[5 + i] = (uint64_t(box[i]) << 40) ^ (i > 0 ? strides[i - 1] : 0);
+  }
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) return it->second;
+  CUtensorMap* m = nullptr;
+  if (posix_memalign(reinterpret_cast<void**>(&m), 64, sizeof(CUtensorMap)) != 0) {
+    set_error("posix_memalign failed");
+    return nullptr;
+  }
+  cuuint64_t gdims[3];
+  cuuint64_t gstrides[2];
+  cuuint32_t gbox[3];
+  cuuint32_t estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    if (i > 0) gstrides[i - 1] = strides[i - 1];
+  }
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), const_cast<void*>(ptr), gdims,
+                        gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d ptr %p dims [%llu,%llu,%llu] stride1 %llu box [%u,%u,%u]",
+              int(r), rank, ptr, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides[0] : 0),
+              box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+    free(m);
+    return nullptr;
+  }
+  g_tmaps.emplace(key, m);
+  return m;
+}
+
+const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                                    uint32_t box0, uint32_t box1) {
+  uint64_t dims[2] = {dim0, dim1};
+  uint64_t strides[1] = {stride1_bytes};
+  uint32_t box[2] = {box0, box1};
+  return get_tmap(2, ptr, dims, strides, box);
+}
+
+const CUtensorMap* get_tmap_3d_bf16(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                                    uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
+                                    uint32_t box1, uint32_t box2) {
+  uint64_t dims[3] = {dim0, dim1, dim2};
+  uint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  uint32_t box[3] = {box0, box1, box2};
+  return get_tmap(3, ptr, dims, strides, box);
+}
+
+}  // namespace hoigen
+
+extern "C" {
+
+int hoigen_abi_version(void) { return HOIGEN_ABI_VERSION; }
+
+const char* hoigen_last_error(void) { return hoigen::g_err; }
+
+int hoigen_init(int device) {
+  cudaDeviceProp prop;
+  HOIGEN_CHECK_CUDA(cudaSetDevice(device));
+  HOIGEN_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    hoigen::set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                      prop.minor);
+    return HOIGEN_ERR_ARCH;
+  }
+  hoigen::g_num_sms = prop.multiProcessorCount;
+  if (hoigen::resolve_driver() != 0) return HOIGEN_ERR_CUDA;
+  return HOIGEN_OK;
+}
+
+}  // extern "C"

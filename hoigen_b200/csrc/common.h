@@ -1,0 +1,43 @@
+// Host-side plumbing shared by the C-ABI translation units: error reporting, driver entry points,
+// TMA tensor-map construction (cached).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hoigen_b200.h"
+
+namespace hoigen {
+
+void set_error(const char* fmt, ...);
+int num_sms();
+
+// 2-D / 3-D bf16 row-major tensor maps with 128-byte swizzle. dims/box innermost-first, strides in
+// BYTES for dims 1.. (dim 0 is contiguous).  Returns nullptr (and sets the error) on failure.
+const CUtensorMap* get_tmap_2d_bf16(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                                    uint32_t box0, uint32_t box1);
+const CUtensorMap* get_tmap_3d_bf16(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                                    uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
+                                    uint32_t box1, uint32_t box2);
+
+#define HOIGEN_CHECK_ARG(cond, ...)        \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::hoigen::set_error(__VA_ARGS__);    \
+      return HOIGEN_ERR_INVALID;           \
+    }                                      \
+  } while (0)
+
+#define HOIGEN_CHECK_CUDA(expr)                                                              \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::hoigen::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return HOIGEN_ERR_CUDA;                                                                \
+    }                                                                                        \
+  } while (0)
+
+#define HOIGEN_CHECK_LAUNCH() HOIGEN_CHECK_CUDA(cudaGetLastError())
+
+}  // namespace hoigen

@@ -1,0 +1,390 @@
+// TMA-fed tcgen05/TMEM bf16 GEMM with fused epilogue (bias / QuickGELU / ReLU / column scale /
+// fp32 residual add / dual fp32+bf16 store).  out = epi(A[M,K] @ W[N,K]^T).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0    : TMA producer   (A tile 128x64, W tile BNx64, 128B swizzle, STAGES-deep mbarrier ring)
+//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accum in TMEM)
+//   warps 2-5 : epilogue       (tcgen05.ld 32 lanes x 32 columns -> registers -> global)
+// Two TMEM accumulator stages (2*BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Replaces the cuBLAS SGEMMs the reference dispatches from CLIP_models_adapter_prior2.py:443-445 (in/out
+// proj), :428-432 (c_fc/c_proj), :184/:201 (adapter down/up), :491 (conv1 as GEMM), :505 (@ proj) and
+// upt_tip_cache_model_free_finetune_distill3.py:1156-1163 (cache / text GEMMs).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace hoigen {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;
+  const float* colscale;
+  int act;
+  const float* residual;
+  int ld_res;
+  float* out_f32;
+  int ld_f32;
+  __nv_bfloat16* out_bf16;
+  int ld_bf16;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (power of two >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == HOIGEN_ACT_QUICKGELU) {
+    // x * sigmoid(1.702 x)   (CLIP_models_adapter_prior2.py:420)
+    return v / (1.0f + __expf(-1.702f * v));
+  } else if (act == HOIGEN_ACT_RELU) {
+    return fmaxf(v, 0.0f);
+  }
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte alignment
+  uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * Cfg::STAGE_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem base slot
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8u * STAGES;
+  const uint32_t bar_tfull = bar_full + 16u * STAGES;
+  const uint32_t bar_tempty = bar_tfull + 16u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (g.M + BM - 1) / BM;
+  const int num_n = (g.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8u * a, 1);
+      mbar_init(bar_tempty + 8u * a, 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+          const uint32_t a_dst = tiles_addr + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+          const uint32_t full = bar_full + 8u * stage;
+          mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
+          tma_load_2d(a_dst, &tmA, full, kb * BK, m_blk * BM);
+          tma_load_2d(b_dst, &tmB, full, kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(bar_full + 8u * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = tiles_addr + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_sdesc_sw128(a_addr + k * (UMMA_K * 2));
+            const uint64_t bdesc = make_sdesc_sw128(b_addr + k * (UMMA_K * 2));
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(bar_empty + 8u * stage);  // frees this smem stage once the MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(bar_tfull + 8u * acc);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(bar_tfull + 8u * acc, acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < g.M;
+      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= g.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + uint32_t(c * 32), r);
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full_chunk = (col0 + 32 <= g.N);
+        if (g.bias) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
+          }
+        }
+        if (g.act != HOIGEN_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
+        }
+        if (g.colscale) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(g.colscale + col0 + j));
+              v[j] *= b.x; v[j + 1] *= b.y; v[j + 2] *= b.z; v[j + 3] *= b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.N) v[j] *= __ldg(g.colscale + col0 + j);
+          }
+        }
+        if (row_ok) {
+          if (g.residual) {
+            const float* rp = g.residual + size_t(row) * g.ld_res + col0;
+            if (full_chunk && (g.ld_res & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(rp + j);
+                v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < g.N) v[j] += rp[j];
+            }
+          }
+          if (g.out_f32) {
+            float* op = g.out_f32 + size_t(row) * g.ld_f32 + col0;
+            if (full_chunk && (g.ld_f32 & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < g.N) op[j] = v[j];
+            }
+          }
+          if (g.out_bf16) {
+            __nv_bfloat16* op = g.out_bf16 + size_t(row) * g.ld_bf16 + col0;
+            if (full_chunk && (g.ld_bf16 & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                pk.x = pack_bf16x2(v[j], v[j + 1]);
+                pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(op + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < g.N) op[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// test-only SIMT cross-check
+// ---------------------------------------------------------------------------------------------
+__global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ w, int lda,
+                                 int ldw, GemmArgs g) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= g.N || m >= g.M) return;
+  float acc = 0.f;
+  for (int k = 0; k < g.K; ++k)
+    acc = fmaf(__bfloat162float(a[size_t(m) * lda + k]), __bfloat162float(w[size_t(n) * ldw + k]), acc);
+  if (g.bias) acc += g.bias[n];
+  acc = apply_act(acc, g.act);
+  if (g.colscale) acc *= g.colscale[n];
+  if (g.residual) acc += g.residual[size_t(m) * g.ld_res + n];
+  if (g.out_f32) g.out_f32[size_t(m) * g.ld_f32 + n] = acc;
+  if (g.out_bf16) g.out_bf16[size_t(m) * g.ld_bf16 + n] = __float2bfloat16_rn(acc);
+}
+
+static int validate(const hoigen_gemm_params* p) {
+  HOIGEN_CHECK_ARG(p != nullptr, "gemm: null params");
+  HOIGEN_CHECK_ARG(p->a && p->w, "gemm: null operand");
+  HOIGEN_CHECK_ARG(p->M > 0 && p->N > 0 && p->K > 0, "gemm: bad shape M=%d N=%d K=%d", p->M, p->N, p->K);
+  HOIGEN_CHECK_ARG(p->lda >= p->K && p->ldw >= p->K, "gemm: lda/ldw < K");
+  HOIGEN_CHECK_ARG((p->lda % 8) == 0 && (p->ldw % 8) == 0, "gemm: lda/ldw must be multiples of 8 (got %d, %d)",
+                   p->lda, p->ldw);
+  HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w) & 15) == 0,
+                   "gemm: operands must be 16-byte aligned");
+  HOIGEN_CHECK_ARG(p->out_f32 || p->out_bf16, "gemm: no output");
+  HOIGEN_CHECK_ARG(!p->out_f32 || p->ld_f32 >= p->N, "gemm: ld_f32 < N");
+  HOIGEN_CHECK_ARG(!p->out_bf16 || p->ld_bf16 >= p->N, "gemm: ld_bf16 < N");
+  HOIGEN_CHECK_ARG(!p->residual || p->ld_res >= p->N, "gemm: ld_res < N");
+  HOIGEN_CHECK_ARG(p->act >= 0 && p->act <= 2, "gemm: bad act %d", p->act);
+  HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->colscale) & 15) == 0,
+                   "gemm: bias/colscale must be 16-byte aligned");
+  HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->residual) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->out_f32) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(p->out_bf16) & 15) == 0,
+                   "gemm: residual/outputs must be 16-byte aligned");
+  return HOIGEN_OK;
+}
+
+static GemmArgs to_args(const hoigen_gemm_params* p) {
+  GemmArgs g;
+  g.M = p->M; g.N = p->N; g.K = p->K;
+  g.bias = p->bias; g.colscale = p->colscale; g.act = p->act;
+  g.residual = p->residual; g.ld_res = p->ld_res;
+  g.out_f32 = p->out_f32; g.ld_f32 = p->ld_f32;
+  g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16); g.ld_bf16 = p->ld_bf16;
+  return g;
+}
+
+// tiles-per-SM rounds x relative tile cost; smaller is better.
+static int choose_block_n(int M, int N) {
+  const int sms = num_sms();
+  const int num_m = (M + BM - 1) / BM;
+  int best = 256;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && N <= bn / 2) continue;  // do not pad N by 2x or more
+    const int tiles = num_m * ((N + bn - 1) / bn);
+    const int rounds = (tiles + sms - 1) / sms;
+    // narrower tiles re-read A more often and amortise the pipeline fill worse
+    const double tile_cost = double(bn) + 24.0;
+    const double cost = rounds * tile_cost;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int BN>
+static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
+  if (!ta) return HOIGEN_ERR_CUDA;
+  const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN);
+  if (!tb) return HOIGEN_ERR_CUDA;
+  const int num_tiles = ((p->M + BM - 1) / BM) * ((p->N + BN - 1) / BN);
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, to_args(p));
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+}  // namespace hoigen
+
+extern "C" {
+
+int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream) {
+  using namespace hoigen;
+  int rc = validate(p);
+  if (rc != HOIGEN_OK) return rc;
+  int bn = p->block_n;
+  if (bn == 0) bn = choose_block_n(p->M, p->N);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch_gemm<256>(p, s);
+    case 128: return launch_gemm<128>(p, s);
+    case 64: return launch_gemm<64>(p, s);
+    default: set_error("gemm: block_n must be 0/64/128/256 (got %d)", bn); return HOIGEN_ERR_INVALID;
+  }
+}
+
+int hoigen_debug_gemm_simt(const hoigen_gemm_params* p, hoigen_stream_t stream) {
+  using namespace hoigen;
+  int rc = validate(p);
+  if (rc != HOIGEN_OK) return rc;
+  dim3 grid((p->N + 127) / 128, p->M);
+  gemm_simt_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(p->a), reinterpret_cast<const __nv_bfloat16*>(p->w), p->lda, p->ldw,
+      to_args(p));
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+}  // extern "C"
