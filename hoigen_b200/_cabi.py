@@ -93,13 +93,78 @@ def ptr(t: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
-# name -> argtypes; populated below, one entry per symbol in include/hoigen_b200.h
+class AdapterMidWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "linear1_w", "linear1_b", "linear2_w", "linear2_b",
+        "norm2_w", "norm2_b", "norm3_w", "norm3_b")]
+
+
+ENCODER_WEIGHT_FIELDS = (
+    "conv_w", "class_embedding", "positional_embedding", "ln_pre_w", "ln_pre_b", "ln_post_w", "ln_post_b", "proj_t",
+    "ln1_w", "ln1_b", "ln2_w", "ln2_b", "qkv_w", "qkv_b", "out_w", "out_b", "fc_w", "fc_b", "proj_w", "proj_b",
+    "ad_down_w", "ad_down_b", "ad_up_w", "ad_up_b", "ad_scale", "ad_in_proj_w", "ad_in_proj_b", "ad_out_proj_w",
+    "ad_out_proj_b", "ad_linear1_w", "ad_linear1_b", "ad_linear2_w", "ad_linear2_b", "ad_norm2_w", "ad_norm2_b",
+    "ad_norm3_w", "ad_norm3_b")
+
+
+class EncoderWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ENCODER_WEIGHT_FIELDS]
+
+
+ENCODER_BUFFER_FIELDS = ("patches", "patch_emb", "x", "xb", "h", "qkv", "attn", "mlp", "adapter_d", "adapter_t",
+                         "adapter_kv", "tokens_out")
+
+
+class EncoderBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ENCODER_BUFFER_FIELDS]
+
+
+class ScoreWeights(C.Structure):
+    _fields_ = [
+        ("num_classes", C.c_int32), ("cache_rows", C.c_int32),
+        ("cache_keys", C.c_void_p * 3), ("bias_term", C.c_void_p * 3), ("label_t", C.c_void_p * 3),
+        ("colscale", C.c_void_p * 3),
+        ("global_keys", C.c_void_p), ("global_bias_term", C.c_void_p), ("colscale_global", C.c_void_p),
+        ("dino_keys", C.c_void_p), ("dino_bias_term", C.c_void_p), ("colscale_dino", C.c_void_p),
+        ("text_w", C.c_void_p), ("colscale_text", C.c_void_p),
+    ]
+
+
+SCORE_BUFFER_FIELDS = ("pair_feat_bf16", "phi", "phi_img", "g_bf16", "d_bf16", "img_logits", "logits")
+
+
+class ScoreBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in SCORE_BUFFER_FIELDS]
+
+
+_P, _I, _F, _L = C.c_void_p, C.c_int32, C.c_float, C.c_int64
+
+# name -> argtypes, one entry per symbol in include/hoigen_b200.h
 _SIGNATURES: dict[str, list] = {
-    "hoigen_gemm_bf16": [C.POINTER(GemmParams), C.c_void_p],
-    "hoigen_debug_gemm_simt": [C.POINTER(GemmParams), C.c_void_p],
+    "hoigen_gemm_bf16": [C.POINTER(GemmParams), _P],
+    "hoigen_debug_gemm_simt": [C.POINTER(GemmParams), _P],
+    "hoigen_patchify_bf16": [_P, _P, _I, _P],
+    "hoigen_embed_lnpre": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "hoigen_layernorm768": [_P, _P, _P, _P, _P, _I, _P],
+    "hoigen_adapter_kv": [_P, _P, _P, _P, _I, _I, _P],
+    "hoigen_adapter_mid": [_P, _P, _P, C.POINTER(AdapterMidWeights), _P, _I, _I, _P],
+    "hoigen_attention": [_P, _P, _I, _P],
+    "hoigen_encoder_forward": [C.POINTER(EncoderWeights), C.POINTER(EncoderBuffers), _P, _P, _P, _I, _I, _I, _P],
+    "hoigen_prior_tokens": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P],
+    "hoigen_roi_pair_features": [_P, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P],
+    "hoigen_rows_to_bf16": [_P, _L, _I, _I, _I, _P, _P],
+    "hoigen_broadcast_image_logits": [_P, _P, _I, _I, _I, _P, _P],
+    "hoigen_score_pairs": [C.POINTER(ScoreWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
+    "hoigen_emit_triplets": [_P, _I, _P, _P, _P, _P, _I, _I, _P, _I, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
 }
 
 EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", *_SIGNATURES.keys()]
+
+
+def call(name: str, *args) -> None:
+    """Invoke a C-ABI entry point on the current stream (the stream pointer is appended) and raise on error."""
+    lib = load()
+    check(getattr(lib, name)(*args, stream_ptr()), name)
 
 
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act=ACT_NONE, residual=None,

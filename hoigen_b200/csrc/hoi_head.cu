@@ -1,0 +1,490 @@
+// HOI head kernels (HBM / latency bound, fp32): prior-token MLP, RoIAlign(7x7, adaptive, aligned) + mean over the
+// 14x14 patch-token grid for single and union boxes, pairwise human/object/union feature assembly with L2
+// normalisation, per-image logit broadcast, and prior-score + ordered triplet emission.
+//
+// Reference (U = upt_tip_cache_model_free_finetune_distill3.py):
+//   get_prior U:1445-1495, compute_roi_embeddings U:981-1057 (torchvision.ops.roi_align call sites U:1028-1029),
+//   compute_prior_scores U:806-833, postprocessing U:1408-1427.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace hoigen {
+
+constexpr int FEAT = 512;
+constexpr int TOK = 197;
+constexpr int G14 = 14;
+constexpr int POOL = 7;
+
+__device__ __forceinline__ float warp_sum_h(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prior tokens: [score, box/(w,h,w,h), object_embedding[label]] (517) -> 128 -> 128 -> 64 (ReLU between)
+// one block per image, 128 threads; thread o owns output feature o for every token of the image.
+// Padding tokens (t >= n_b) are MLP(0) constants and mask = 1 (U:1448-1450, 1469, 1495).
+// weights are passed TRANSPOSED (in, out) so that the per-thread reads are coalesced.
+// ------------------------------------------------------------------------------------------------
+constexpr int PRIOR_IN = 517;
+constexpr int PRIOR_MAXTOK = 32;
+
+__global__ void __launch_bounds__(128)
+prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ labels,
+                    const int* __restrict__ box_off, const float* __restrict__ obj_emb, const float* __restrict__ w0t,
+                    const float* __restrict__ b0, const float* __restrict__ w1t, const float* __restrict__ b1,
+                    const float* __restrict__ w2t, const float* __restrict__ b2, float img_w, float img_h, int n_max,
+                    float* __restrict__ prior, uint8_t* __restrict__ mask) {
+  extern __shared__ float sm[];
+  float* xin = sm;                                // [n_max][520]
+  float* h1 = xin + PRIOR_MAXTOK * 520;           // [n_max][128]
+  float* h2 = h1 + PRIOR_MAXTOK * 128;            // [n_max][128]
+  const int b = blockIdx.x;
+  const int o = threadIdx.x;
+  const int base = box_off[b];
+  const int n = box_off[b + 1] - base;
+  for (int i = threadIdx.x; i < n_max * 520; i += 128) {
+    const int t = i / 520, c = i % 520;
+    float v = 0.f;
+    if (t < n && c < PRIOR_IN) {
+      if (c == 0) v = scores[base + t];
+      else if (c < 5) v = boxes[(base + t) * 4 + (c - 1)] / ((c & 1) ? img_w : img_h);  // x1/w, y1/h, x2/w, y2/h
+      else v = __ldg(obj_emb + labels[base + t] * FEAT + (c - 5));
+    }
+    xin[i] = v;
+  }
+  for (int t = threadIdx.x; t < n_max; t += 128) mask[b * n_max + t] = t < n ? 0 : 1;
+  __syncthreads();
+  float acc[PRIOR_MAXTOK];
+  // layer 0
+  {
+    const float bias = b0[o];
+#pragma unroll
+    for (int t = 0; t < PRIOR_MAXTOK; ++t) acc[t] = bias;
+    for (int k = 0; k < PRIOR_IN; ++k) {
+      const float w = __ldg(w0t + k * 128 + o);
+#pragma unroll
+      for (int t = 0; t < PRIOR_MAXTOK; ++t)
+        if (t < n_max) acc[t] = fmaf(w, xin[t * 520 + k], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < PRIOR_MAXTOK; ++t)
+      if (t < n_max) h1[t * 128 + o] = fmaxf(acc[t], 0.f);
+  }
+  __syncthreads();
+  {
+    const float bias = b1[o];
+#pragma unroll
+    for (int t = 0; t < PRIOR_MAXTOK; ++t) acc[t] = bias;
+    for (int k = 0; k < 128; ++k) {
+      const float w = __ldg(w1t + k * 128 + o);
+#pragma unroll
+      for (int t = 0; t < PRIOR_MAXTOK; ++t)
+        if (t < n_max) acc[t] = fmaf(w, h1[t * 128 + k], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < PRIOR_MAXTOK; ++t)
+      if (t < n_max) h2[t * 128 + o] = fmaxf(acc[t], 0.f);
+  }
+  __syncthreads();
+  if (o < 64) {
+    const float bias = b2[o];
+#pragma unroll
+    for (int t = 0; t < PRIOR_MAXTOK; ++t) acc[t] = bias;
+    for (int k = 0; k < 128; ++k) {
+      const float w = __ldg(w2t + k * 64 + o);
+#pragma unroll
+      for (int t = 0; t < PRIOR_MAXTOK; ++t)
+        if (t < n_max) acc[t] = fmaf(w, h2[t * 128 + k], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < PRIOR_MAXTOK; ++t)
+      if (t < n_max) prior[(size_t(b) * n_max + t) * 64 + o] = acc[t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoIAlign + mean.  Because the 7x7xg^2 sampling lattice is a product lattice and bilinear weights factorise,
+//   mean_bins(RoIAlign(F, box))[c] = (1 / (49 * count)) * sum_y sum_x Wy[y] * Wx[x] * F[y][x][c]
+// with per-axis weights Wy / Wx accumulated over the 7*g samples of that axis (out-of-range samples,
+// coordinate < -1 or > 14, contribute zero exactly as in torchvision's kernel).
+// grid = (B, 4): a CTA stages a 128-channel slice of one image's 14x14x512 token map in shared memory (coalesced
+// float4 loads) and produces that slice for every single box and every union box of the image; one warp per box,
+// lane = 4 channels.
+// ------------------------------------------------------------------------------------------------
+constexpr int ROI_THREADS = 256;
+constexpr int ROI_SLICE = 128;
+constexpr int ROI_SMEM_BYTES = 196 * ROI_SLICE * 4;
+
+__device__ __forceinline__ float axis_weight(int t, float start, float bin, int g) {
+  float w = 0.f;
+  const float gf = float(g);
+  for (int p = 0; p < POOL; ++p) {
+    for (int i = 0; i < g; ++i) {
+      float c = start + float(p) * bin + (float(i) + 0.5f) * bin / gf;
+      if (c < -1.0f || c > float(G14)) continue;
+      c = fmaxf(c, 0.f);
+      int lo = int(c), hi;
+      if (lo >= G14 - 1) { lo = hi = G14 - 1; c = float(lo); } else { hi = lo + 1; }
+      const float l = c - float(lo);
+      if (t == lo) w += 1.0f - l;
+      if (t == hi) w += l;
+    }
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(ROI_THREADS)
+roi_features_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const float* __restrict__ boxes,
+                    const int* __restrict__ box_off, const int* __restrict__ n_human, const int* __restrict__ pair_off,
+                    float spatial_scale, float* __restrict__ single_feat /* (Ntot,512) */,
+                    float* __restrict__ union_feat /* (Ktot,512) */) {
+  extern __shared__ float4 fs4[];  // [196][32] float4
+  const int b = blockIdx.x, slice = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(tokens + (size_t(b) * TOK + 1) * FEAT + slice * ROI_SLICE);
+  for (int i = threadIdx.x; i < 196 * 32; i += ROI_THREADS) fs4[i] = __ldg(src + (i >> 5) * (FEAT / 4) + (i & 31));
+  __syncthreads();
+  const int bbase = box_off[b];
+  const int n = box_off[b + 1] - bbase;
+  const int nh = n_human[b];
+  const int pbase = pair_off[b];
+  const int K = pair_off[b + 1] - pbase;
+  for (int job = warp; job < n + K; job += ROI_THREADS / 32) {
+    float x1, y1, x2, y2;
+    float* dst;
+    if (job < n) {
+      const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + job);
+      x1 = bx.x; y1 = bx.y; x2 = bx.z; y2 = bx.w;
+      dst = single_feat + size_t(bbase + job) * FEAT;
+    } else {
+      const int i = job - n;
+      const int px = i / (n - 1), r = i % (n - 1);
+      const int py = r < px ? r : r + 1;           // row-major enumeration of (x, y != x), x < n_h  (U:1007-1012)
+      const float4 bh = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + px);
+      const float4 bo = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + py);
+      x1 = fminf(bh.x, bo.x); y1 = fminf(bh.y, bo.y); x2 = fmaxf(bh.z, bo.z); y2 = fmaxf(bh.w, bo.w);  // U:1021-1023
+      dst = union_feat + size_t(pbase + i) * FEAT;
+    }
+    (void)nh;
+    const float sx = x1 * spatial_scale - 0.5f, sy = y1 * spatial_scale - 0.5f;
+    const float ex = x2 * spatial_scale - 0.5f, ey = y2 * spatial_scale - 0.5f;
+    const float rw = ex - sx, rh = ey - sy;
+    const float bw = rw / float(POOL), bh_ = rh / float(POOL);
+    const int gw = int(ceilf(rw / float(POOL))), gh = int(ceilf(rh / float(POOL)));
+    const float count = float(max(gh * gw, 1));
+    // lanes 0..13 hold Wy[lane], lanes 16..29 hold Wx[lane-16]
+    float wl = 0.f;
+    if (lane < G14) wl = axis_weight(lane, sy, bh_, gh);
+    else if (lane >= 16 && lane < 16 + G14) wl = axis_weight(lane - 16, sx, bw, gw);
+    const unsigned nzy = __ballot_sync(0xffffffffu, lane < G14 && wl != 0.f);
+    const unsigned nzx = __ballot_sync(0xffffffffu, lane >= 16 && lane < 16 + G14 && wl != 0.f) >> 16;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nzy && nzx) {
+      const int ylo = __ffs(nzy) - 1, yhi = 31 - __clz(nzy);
+      const int xlo = __ffs(nzx) - 1, xhi = 31 - __clz(nzx);
+      for (int y = ylo; y <= yhi; ++y) {
+        const float wy = __shfl_sync(0xffffffffu, wl, y);
+        float4 rowacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int x = xlo; x <= xhi; ++x) {
+          const float wx = __shfl_sync(0xffffffffu, wl, 16 + x);
+          const float4 f = fs4[(y * G14 + x) * 32 + lane];
+          rowacc.x = fmaf(wx, f.x, rowacc.x); rowacc.y = fmaf(wx, f.y, rowacc.y);
+          rowacc.z = fmaf(wx, f.z, rowacc.z); rowacc.w = fmaf(wx, f.w, rowacc.w);
+        }
+        acc.x = fmaf(wy, rowacc.x, acc.x); acc.y = fmaf(wy, rowacc.y, acc.y);
+        acc.z = fmaf(wy, rowacc.z, acc.z); acc.w = fmaf(wy, rowacc.w, acc.w);
+      }
+    }
+    const float inv = 1.0f / (count * float(POOL * POOL));
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    reinterpret_cast<float4*>(dst + slice * ROI_SLICE)[lane] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair assembly: f_H[i] = single[x_i]/|.|, f_O[i] = single[y_i]/|.|, f_U[i] = union[i]/|.|   (U:1044-1050)
+// one warp per pair; outputs bf16 (GEMM operands) and optionally fp32. out layout: [3][Ktot][512] (H, O, U).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_image(const int* __restrict__ off, int nimg, int idx) {
+  int lo = 0, hi = nimg;  // off[lo] <= idx < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= idx) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+pair_assemble_kernel(const float* __restrict__ single_feat, const float* __restrict__ union_feat,
+                     const int* __restrict__ box_off, const int* __restrict__ pair_off, int nimg, int ktot,
+                     __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= ktot) return;
+  const int b = find_image(pair_off, nimg, warp);
+  const int n = box_off[b + 1] - box_off[b];
+  const int i = warp - pair_off[b];
+  const int px = i / (n - 1), r = i % (n - 1);
+  const int py = r < px ? r : r + 1;
+  const float* srcs[3] = {single_feat + size_t(box_off[b] + px) * FEAT, single_feat + size_t(box_off[b] + py) * FEAT,
+                          union_feat + size_t(warp) * FEAT};
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    float4 v[4];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = reinterpret_cast<const float4*>(srcs[s])[lane + 32 * j];
+      ss += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+    }
+    const float nrm = sqrtf(warp_sum_h(ss));  // 0 -> x/0 = NaN, as in the reference
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 y = make_float4(v[j].x / nrm, v[j].y / nrm, v[j].z / nrm, v[j].w / nrm);
+      const size_t o = (size_t(s) * ktot + warp) * FEAT;
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + o)[lane + 32 * j] = y;
+      uint2 pk;
+      pk.x = pack_bf16x2(y.x, y.y);
+      pk.y = pack_bf16x2(y.z, y.w);
+      reinterpret_cast<uint2*>(out_bf16 + o)[lane + 32 * j] = pk;
+    }
+  }
+}
+
+// rows of `in` (ld_in floats apart) -> L2-normalised (optional) bf16 rows (cols wide); one warp per row.
+__global__ void __launch_bounds__(256)
+rows_to_bf16_kernel(const float* __restrict__ in, long ld_in, int rows, int cols, int normalize,
+                    __nv_bfloat16* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* src = in + size_t(warp) * ld_in;
+  float ss = 0.f;
+  for (int c = lane; c < cols; c += 32) ss += src[c] * src[c];
+  const float nrm = normalize ? sqrtf(warp_sum_h(ss)) : 1.0f;
+  for (int c = lane; c < cols; c += 32) out[size_t(warp) * cols + c] = __float2bfloat16_rn(src[c] / nrm);
+}
+
+// logits[i][:] = img_logits[image(i)][:]   (the per-image global-CLIP + DINO cache terms, U:1115, U:1138)
+__global__ void broadcast_rows_kernel(const float* __restrict__ img_logits, const int* __restrict__ pair_off, int nimg,
+                                      int ktot, int C, float* __restrict__ logits) {
+  const long total = long(ktot) * C;
+  for (long e = blockIdx.x * long(blockDim.x) + threadIdx.x; e < total; e += long(gridDim.x) * blockDim.x) {
+    const int i = int(e / C), c = int(e % C);
+    const int b = find_image(pair_off, nimg, i);
+    logits[e] = img_logits[size_t(b) * C + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prior scores + ordered triplet emission  (U:806-833, U:1408-1427)
+//   pr_i = score[x_i]^lambda * score[y_i]^lambda for every class c in table[label[y_i]] (bitmask rows), else 0
+//   emit (i, c) in row-major order wherever pr != 0: score = sigmoid(logit[i,c]) * pr, label = c,
+//   pairing = (x_i, y_i), object = label[y_i].  Compiled WITHOUT fast-math: denormal products stay non-zero.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pair_count_kernel(const float* __restrict__ scores, const int64_t* __restrict__ labels, const int* __restrict__ box_off,
+                  const int* __restrict__ pair_off, int nimg, int ktot, const uint32_t* __restrict__ table_bits,
+                  int words, float lambda, int* __restrict__ counts, float* __restrict__ pr_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ktot) return;
+  const int b = find_image(pair_off, nimg, i);
+  const int base = box_off[b];
+  const int n = box_off[b + 1] - base;
+  const int li = i - pair_off[b];
+  const int px = li / (n - 1), r = li % (n - 1);
+  const int py = r < px ? r : r + 1;
+  const float sh = powf(scores[base + px], lambda);
+  const float so = powf(scores[base + py], lambda);
+  const float pr = sh * so;
+  int cnt = 0;
+  if (pr != 0.f) {
+    const uint32_t* bits = table_bits + size_t(labels[base + py]) * words;
+    for (int w = 0; w < words; ++w) cnt += __popc(bits[w]);
+  }
+  counts[i] = cnt;
+  pr_out[i] = pr;
+}
+
+// single-block exclusive scan of counts[0..n) -> offsets[0..n], plus per-image offsets.
+__global__ void __launch_bounds__(1024)
+scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ offsets, const int* __restrict__ pair_off,
+            int nimg, int* __restrict__ img_off) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int idx = base + threadIdx.x;
+    const int v = idx < n ? counts[idx] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int prefix = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + x - v;
+    if (idx < n) offsets[idx] = prefix;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = prefix + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = carry;
+  __syncthreads();
+  for (int b = threadIdx.x; b <= nimg; b += 1024) img_off[b] = (pair_off[b] < n) ? offsets[pair_off[b]] : carry;
+}
+
+__global__ void __launch_bounds__(256)
+emit_kernel(const float* __restrict__ logits, int C, const float* __restrict__ pr_in, const int* __restrict__ offsets,
+            const int64_t* __restrict__ labels, const int* __restrict__ box_off, const int* __restrict__ pair_off,
+            const int* __restrict__ img_off, int nimg, int ktot, const uint32_t* __restrict__ table_bits, int words,
+            long capacity, float* __restrict__ out_scores, int64_t* __restrict__ out_labels,
+            int64_t* __restrict__ out_objects, int64_t* __restrict__ out_pairing) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= ktot) return;
+  const float pr = pr_in[i];
+  if (pr == 0.f) return;
+  const int b = find_image(pair_off, nimg, i);
+  const int base = box_off[b];
+  const int n = box_off[b + 1] - base;
+  const int li = i - pair_off[b];
+  const int px = li / (n - 1), r = li % (n - 1);
+  const int py = r < px ? r : r + 1;
+  const int64_t obj = labels[base + py];
+  const uint32_t* bits = table_bits + size_t(obj) * words;
+  int pos = offsets[i];
+  // per-image pairing block: [2][M_b] at 2*img_off[b]
+  const long ioff = img_off[b];
+  const long mb = long(img_off[b + 1]) - ioff;
+  for (int w = 0; w < words; ++w) {
+    const uint32_t m = bits[w];
+    const int c = w * 32 + lane;
+    if ((m >> lane) & 1u) {
+      const long p = long(pos) + __popc(m & ((1u << lane) - 1u));
+      if (p < capacity) {
+        const float x = logits[size_t(i) * C + c];
+        out_scores[p] = (1.0f / (1.0f + expf(-x))) * pr;
+        out_labels[p] = c;
+        out_objects[p] = obj;
+        const long j = p - ioff;
+        out_pairing[2 * ioff + j] = px;
+        out_pairing[2 * ioff + mb + j] = py;
+      }
+    }
+    pos += __popc(m);
+  }
+}
+
+}  // namespace hoigen
+
+extern "C" {
+
+int hoigen_prior_tokens(const float* boxes, const float* scores, const int64_t* labels, const int32_t* box_off,
+                        const float* obj_emb, const float* w0t, const float* b0, const float* w1t, const float* b1,
+                        const float* w2t, const float* b2, float img_w, float img_h, int32_t batch, int32_t n_max,
+                        float* prior, uint8_t* mask, hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(boxes && scores && labels && box_off && obj_emb && prior && mask && batch > 0, "prior_tokens: bad arguments");
+  HOIGEN_CHECK_ARG(n_max > 0 && n_max <= PRIOR_MAXTOK, "prior_tokens: n_max must be in [1,%d] (got %d)", PRIOR_MAXTOK, n_max);
+  const int smem = (PRIOR_MAXTOK * 520 + 2 * PRIOR_MAXTOK * 128) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(prior_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  prior_tokens_kernel<<<batch, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      boxes, scores, labels, box_off, obj_emb, w0t, b0, w1t, b1, w2t, b2, img_w, img_h, n_max, prior, mask);
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int32_t* box_off, const int32_t* n_human,
+                             const int32_t* pair_off, int32_t batch, int32_t ktot, float spatial_scale,
+                             float* single_feat, float* union_feat, void* pair_feat_bf16, float* pair_feat_f32,
+                             hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(tokens && boxes && box_off && n_human && pair_off && single_feat && union_feat && pair_feat_bf16,
+                   "roi_pair_features: null argument");
+  HOIGEN_CHECK_ARG(batch > 0 && ktot >= 0, "roi_pair_features: bad sizes");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(roi_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROI_SMEM_BYTES));
+    attr_set = true;
+  }
+  roi_features_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES, s>>>(
+      tokens, boxes, box_off, n_human, pair_off, spatial_scale, single_feat, union_feat);
+  HOIGEN_CHECK_LAUNCH();
+  if (ktot > 0) {
+    pair_assemble_kernel<<<(ktot * 32 + 255) / 256, 256, 0, s>>>(single_feat, union_feat, box_off, pair_off, batch, ktot,
+                                                                 reinterpret_cast<__nv_bfloat16*>(pair_feat_bf16), pair_feat_f32);
+    HOIGEN_CHECK_LAUNCH();
+  }
+  return HOIGEN_OK;
+}
+
+int hoigen_rows_to_bf16(const float* in, int64_t ld_in, int32_t rows, int32_t cols, int32_t normalize, void* out,
+                        hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(in && out && rows > 0 && cols > 0, "rows_to_bf16: bad arguments");
+  rows_to_bf16_kernel<<<(rows * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, rows, cols, normalize, reinterpret_cast<__nv_bfloat16*>(out));
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+int hoigen_broadcast_image_logits(const float* img_logits, const int32_t* pair_off, int32_t batch, int32_t ktot,
+                                  int32_t num_classes, float* logits, hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(img_logits && pair_off && logits && batch > 0 && num_classes > 0, "broadcast_image_logits: bad arguments");
+  if (ktot == 0) return HOIGEN_OK;
+  const long total = long(ktot) * num_classes;
+  const int blocks = int(min(long(num_sms()) * 8, (total + 255) / 256));
+  broadcast_rows_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img_logits, pair_off, batch, ktot,
+                                                                                      num_classes, logits);
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+int hoigen_emit_triplets(const float* logits, int32_t num_classes, const float* scores, const int64_t* labels,
+                         const int32_t* box_off, const int32_t* pair_off, int32_t batch, int32_t ktot,
+                         const uint32_t* table_bits, int32_t table_words, float hyper_lambda, int32_t* work_counts,
+                         int32_t* work_offsets, float* work_pr, int64_t capacity, float* out_scores,
+                         int64_t* out_labels, int64_t* out_objects, int64_t* out_pairing, int32_t* img_off,
+                         hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(logits && scores && labels && box_off && pair_off && table_bits && work_counts && work_offsets &&
+                       work_pr && out_scores && out_labels && out_objects && out_pairing && img_off,
+                   "emit_triplets: null argument");
+  HOIGEN_CHECK_ARG(batch > 0 && ktot >= 0 && num_classes > 0 && table_words * 32 >= num_classes, "emit_triplets: bad sizes");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (ktot > 0) {
+    pair_count_kernel<<<(ktot + 255) / 256, 256, 0, s>>>(scores, labels, box_off, pair_off, batch, ktot, table_bits,
+                                                         table_words, hyper_lambda, work_counts, work_pr);
+    HOIGEN_CHECK_LAUNCH();
+  }
+  scan_kernel<<<1, 1024, 0, s>>>(work_counts, ktot, work_offsets, pair_off, batch, img_off);
+  HOIGEN_CHECK_LAUNCH();
+  if (ktot > 0) {
+    emit_kernel<<<(ktot * 32 + 255) / 256, 256, 0, s>>>(logits, num_classes, work_pr, work_offsets, labels, box_off, pair_off,
+                                                        img_off, batch, ktot, table_bits, table_words, long(capacity),
+                                                        out_scores, out_labels, out_objects, out_pairing);
+    HOIGEN_CHECK_LAUNCH();
+  }
+  return HOIGEN_OK;
+}
+
+}  // extern "C"

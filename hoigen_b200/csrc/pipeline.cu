@@ -1,0 +1,129 @@
+// Host-side drivers that chain the kernels of one stage into ONE C-ABI call per batch (the Python caller would
+// otherwise pay ~120 ctypes round trips per encoder forward):
+//   hoigen_encoder_forward : VisionTransformer.forward(x, prior)      CLIP_models_adapter_prior2.py:489-506
+//   hoigen_score_pairs     : cache-model + text logits                upt_..._distill3.py:1111-1186
+#include "common.h"
+
+namespace hoigen {
+
+static int gemm(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias, int act,
+                const float* colscale, const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_bf16,
+                int ld_bf16, cudaStream_t s) {
+  hoigen_gemm_params p;
+  p.a = a; p.w = w; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw;
+  p.bias = bias; p.colscale = colscale; p.act = act;
+  p.residual = residual; p.ld_res = ld_res;
+  p.out_f32 = out_f32; p.ld_f32 = ld_f32;
+  p.out_bf16 = out_bf16; p.ld_bf16 = ld_bf16;
+  p.block_n = 0;
+  return hoigen_gemm_bf16(&p, s);
+}
+
+#define HOIGEN_TRY(expr)          \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != HOIGEN_OK) return _rc; \
+  } while (0)
+
+}  // namespace hoigen
+
+extern "C" {
+
+int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder_buffers* buf, const float* images,
+                           const float* prior, const uint8_t* mask, int32_t batch, int32_t n_max, int32_t num_layers,
+                           hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(w && buf && images && prior && mask, "encoder_forward: null argument");
+  HOIGEN_CHECK_ARG(batch > 0 && num_layers >= 0 && num_layers <= 12, "encoder_forward: bad batch/layers");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int D = 768, T = 197, M = batch * T;
+  // ---- patch embedding (conv1 as GEMM) + cls/pos + ln_pre -------------------------------------------------
+  HOIGEN_TRY(hoigen_patchify_bf16(images, buf->patches, batch, s));
+  HOIGEN_TRY(gemm(buf->patches, D, w->conv_w, D, batch * 196, D, D, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                  buf->patch_emb, D, nullptr, 0, s));
+  HOIGEN_TRY(hoigen_embed_lnpre(buf->patch_emb, w->class_embedding, w->positional_embedding, w->ln_pre_w, w->ln_pre_b,
+                                buf->x, buf->xb, batch, s));
+  // ---- adapter K/V of the prior tokens, all layers at once ------------------------------------------------
+  HOIGEN_TRY(hoigen_adapter_kv(prior, w->ad_in_proj_w, w->ad_in_proj_b, buf->adapter_kv, batch * n_max, 12, s));
+
+  for (int l = 0; l < num_layers; ++l) {
+    const size_t o768 = size_t(l) * D, o64 = size_t(l) * 64;
+    // (1) adapter: down-proj + ReLU (tensor cores) -> bottleneck body (SIMT) -> up-proj * scale + residual
+    HOIGEN_TRY(gemm(buf->xb, D, (const uint16_t*)w->ad_down_w + size_t(l) * 64 * D, D, M, 64, D, w->ad_down_b + o64,
+                    HOIGEN_ACT_RELU, nullptr, nullptr, 0, buf->adapter_d, 64, nullptr, 0, s));
+    hoigen_adapter_mid_weights mw;
+    mw.in_proj_w = w->ad_in_proj_w + size_t(l) * 192 * 64; mw.in_proj_b = w->ad_in_proj_b + size_t(l) * 192;
+    mw.out_proj_w = w->ad_out_proj_w + size_t(l) * 64 * 64; mw.out_proj_b = w->ad_out_proj_b + o64;
+    mw.linear1_w = w->ad_linear1_w + size_t(l) * 128 * 64; mw.linear1_b = w->ad_linear1_b + size_t(l) * 128;
+    mw.linear2_w = w->ad_linear2_w + size_t(l) * 64 * 128; mw.linear2_b = w->ad_linear2_b + o64;
+    mw.norm2_w = w->ad_norm2_w + o64; mw.norm2_b = w->ad_norm2_b + o64;
+    mw.norm3_w = w->ad_norm3_w + o64; mw.norm3_b = w->ad_norm3_b + o64;
+    HOIGEN_TRY(hoigen_adapter_mid(buf->adapter_d, buf->adapter_kv + size_t(l) * batch * n_max * 128, mask, &mw,
+                                  buf->adapter_t, batch, n_max, s));
+    HOIGEN_TRY(gemm(buf->adapter_t, 64, (const uint16_t*)w->ad_up_w + size_t(l) * D * 64, 64, M, D, 64,
+                    w->ad_up_b + o768, HOIGEN_ACT_NONE, w->ad_scale + o768, buf->x, D, buf->x, D, nullptr, 0, s));
+    // (2) x += out_proj(attention(ln_1(x)))
+    HOIGEN_TRY(hoigen_layernorm768(buf->x, w->ln1_w + o768, w->ln1_b + o768, nullptr, buf->h, M, s));
+    HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->qkv_w + size_t(l) * 3 * D * D, D, M, 3 * D, D,
+                    w->qkv_b + size_t(l) * 3 * D, HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->qkv, 3 * D, s));
+    HOIGEN_TRY(hoigen_attention(buf->qkv, buf->attn, batch, s));
+    HOIGEN_TRY(gemm(buf->attn, D, (const uint16_t*)w->out_w + size_t(l) * D * D, D, M, D, D, w->out_b + o768,
+                    HOIGEN_ACT_NONE, nullptr, buf->x, D, buf->x, D, nullptr, 0, s));
+    // (3) x += c_proj(quickgelu(c_fc(ln_2(x))))  (the c_proj epilogue also emits the bf16 copy the next adapter reads)
+    HOIGEN_TRY(hoigen_layernorm768(buf->x, w->ln2_w + o768, w->ln2_b + o768, nullptr, buf->h, M, s));
+    HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->fc_w + size_t(l) * 4 * D * D, D, M, 4 * D, D,
+                    w->fc_b + size_t(l) * 4 * D, HOIGEN_ACT_QUICKGELU, nullptr, nullptr, 0, nullptr, 0, buf->mlp, 4 * D, s));
+    HOIGEN_TRY(gemm(buf->mlp, 4 * D, (const uint16_t*)w->proj_w + size_t(l) * D * 4 * D, 4 * D, M, D, 4 * D,
+                    w->proj_b + o768, HOIGEN_ACT_NONE, nullptr, buf->x, D, buf->x, D, buf->xb, D, s));
+  }
+  // ---- ln_post on ALL tokens, @ proj (768 -> 512) ----------------------------------------------------------
+  HOIGEN_TRY(hoigen_layernorm768(buf->x, w->ln_post_w, w->ln_post_b, nullptr, buf->h, M, s));
+  HOIGEN_TRY(gemm(buf->h, D, w->proj_t, D, M, 512, D, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0, buf->tokens_out, 512,
+                  nullptr, 0, s));
+  return HOIGEN_OK;
+}
+
+int hoigen_score_pairs(const hoigen_score_weights* w, const hoigen_score_buffers* buf, const float* tokens,
+                       const float* dino_feats, const int32_t* pair_off, int32_t batch, int32_t ktot,
+                       hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(w && buf && tokens && pair_off, "score_pairs: null argument");
+  HOIGEN_CHECK_ARG(batch > 0 && ktot >= 0, "score_pairs: bad sizes");
+  HOIGEN_CHECK_ARG(w->num_classes > 0 && w->cache_rows > 0 && (w->cache_rows % 8) == 0,
+                   "score_pairs: cache_rows must be a positive multiple of 8 (got %d)", w->cache_rows);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int C = w->num_classes, N = w->cache_rows;
+  // The affinity is LINEAR in the reference (phi = f W^T + b, no exp: U:1156-1158), so the bias is carried exactly
+  // in fp32 through the second GEMM's epilogue: ((f W^T + b) Y)/s = (f W^T) Y / s + (b Y)/s, bias_term = b Y.
+  // ---- per-image terms: global-CLIP cache (U:1133-1138) and DINO cache (U:1112-1115) -------------------------
+  // g = feat_global / |feat_global|  (U:960) = token row 0 of each image
+  HOIGEN_TRY(hoigen_rows_to_bf16(tokens, 197L * 512, batch, 512, 1, buf->g_bf16, s));
+  HOIGEN_TRY(gemm(buf->g_bf16, 512, w->global_keys, 512, batch, N, 512, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                  nullptr, 0, buf->phi_img, N, s));
+  HOIGEN_TRY(gemm(buf->phi_img, N, w->label_t[2], N, batch, C, N, w->global_bias_term, HOIGEN_ACT_NONE, w->colscale_global,
+                  nullptr, 0, buf->img_logits, C, nullptr, 0, s));
+  if (dino_feats) {
+    HOIGEN_CHECK_ARG(w->dino_keys != nullptr, "score_pairs: dino features given but no dino cache");
+    HOIGEN_TRY(hoigen_rows_to_bf16(dino_feats, 2048, batch, 2048, 0, buf->d_bf16, s));
+    HOIGEN_TRY(gemm(buf->d_bf16, 2048, w->dino_keys, 2048, batch, N, 2048, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                    nullptr, 0, buf->phi_img, N, s));
+    HOIGEN_TRY(gemm(buf->phi_img, N, w->label_t[2], N, batch, C, N, w->dino_bias_term, HOIGEN_ACT_NONE, w->colscale_dino,
+                    buf->img_logits, C, buf->img_logits, C, nullptr, 0, s));
+  }
+  if (ktot == 0) return HOIGEN_OK;
+  HOIGEN_TRY(hoigen_broadcast_image_logits(buf->img_logits, pair_off, batch, ktot, C, buf->logits, s));
+  // ---- pair terms: three cache branches (H, O, U) + text classifier, accumulated in place ---------------------
+  for (int x = 0; x < 3; ++x) {
+    const uint16_t* f = (const uint16_t*)buf->pair_feat_bf16 + size_t(x) * ktot * 512;
+    HOIGEN_TRY(gemm(f, 512, w->cache_keys[x], 512, ktot, N, 512, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                    nullptr, 0, buf->phi, N, s));
+    HOIGEN_TRY(gemm(buf->phi, N, w->label_t[x], N, ktot, C, N, w->bias_term[x], HOIGEN_ACT_NONE, w->colscale[x], buf->logits, C,
+                    buf->logits, C, nullptr, 0, s));
+  }
+  const uint16_t* fu = (const uint16_t*)buf->pair_feat_bf16 + size_t(2) * ktot * 512;
+  HOIGEN_TRY(gemm(fu, 512, w->text_w, 512, ktot, C, 512, nullptr, HOIGEN_ACT_NONE, w->colscale_text, buf->logits, C,
+                  buf->logits, C, nullptr, 0, s));
+  return HOIGEN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,427 @@
+"""B200 HOI detector behind the reference's `UPT` surface.
+
+Mirrors upt_tip_cache_model_free_finetune_distill3.py: `UPT.forward(images, targets=None)` (U:1543, eval branch),
+`prepare_region_proposals` (U:1361), `recover_boxes`, the parameter / attribute names of SURVEY.md Appendix B
+(so reference checkpoints load and `net.module.num_classes`, `.object_class_to_target_class` keep working), and
+the detection dicts of U:1421-1425.  From the region proposals onward everything runs in sm_100a kernels through
+the C ABI: get_prior -> VisionTransformer(x, prior) -> RoIAlign / pair assembly -> cache + text logits ->
+prior scores + ordered triplet emission.  There is NO PyTorch fallback for those stages.
+
+Out of scope (delegated to injected stock modules, exactly as the reference composes them): the DETR proposal
+network (`detector`, `postprocessor`) and the DINO ResNet-50 (`dino_model`) — SURVEY.md §8 rows a8 / f3.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _cabi
+from .encoder import MAX_PRIOR_TOKENS, TOKENS, VisionTransformer, _ParamBag, _linear_params
+
+
+class _NestedTensor:
+    """Minimal stand-in for detr.util.misc.NestedTensor (tensors + padding mask), U:1592-1593."""
+
+    def __init__(self, tensors, mask):
+        self.tensors, self.mask = tensors, mask
+
+    def decompose(self):
+        return self.tensors, self.mask
+
+    def to(self, device):
+        return _NestedTensor(self.tensors.to(device), self.mask.to(device) if self.mask is not None else None)
+
+
+def nested_tensor_from_tensor_list(tensor_list: Sequence[torch.Tensor]) -> _NestedTensor:
+    """Zero-pad (C,H,W) images to the batch maximum; mask is True on padding (detr/util/misc.py:307 semantics)."""
+    c = tensor_list[0].shape[0]
+    h = max(t.shape[1] for t in tensor_list)
+    w = max(t.shape[2] for t in tensor_list)
+    out = tensor_list[0].new_zeros((len(tensor_list), c, h, w))
+    mask = torch.ones((len(tensor_list), h, w), dtype=torch.bool, device=out.device)
+    for i, t in enumerate(tensor_list):
+        out[i, :, : t.shape[1], : t.shape[2]].copy_(t)
+        mask[i, : t.shape[1], : t.shape[2]] = False
+    return _NestedTensor(out, mask)
+
+
+class _ClipHead(nn.Module):
+    """Holds `image_encoder` under the reference's name `clip_head.image_encoder` (CustomCLIP, U:208-217)."""
+
+    def __init__(self, image_encoder: VisionTransformer):
+        super().__init__()
+        self.image_encoder = image_encoder
+
+
+class _PriorMLP(_ParamBag):
+    """Parameter layout of MLP(517,128,64,3) (U:40-52): layers.{0,1,2}.{weight,bias}."""
+
+    def __init__(self, in_dim: int = 517, hidden: int = 128, out_dim: int = 64):
+        super().__init__()
+        dims = [in_dim, hidden, hidden, out_dim]
+        self.layers = nn.ModuleList([_linear_params(dims[i + 1], dims[i]) for i in range(3)])
+
+
+class UPT(nn.Module):
+    """Eval-mode drop-in for the reference UPT (cache_model='gen_feat', logits_type='HO+U+T', prior_type='cbe',
+    prior_method=0, use_insadapter=True — the configuration main_tip_finetune.py hard-sets, M:393-396,444-445)."""
+
+    def __init__(self, num_classes: int, cache_rows: int, *, detector: Optional[nn.Module] = None,
+                 postprocessor: Optional[nn.Module] = None, dino_model: Optional[nn.Module] = None,
+                 clip_head: Optional[nn.Module] = None, human_idx: int = 0, box_score_thresh: float = 0.2,
+                 min_instances: int = 3, max_instances: int = 15, hyper_lambda: float = 2.8,
+                 object_class_to_target_class: Optional[List[List[int]]] = None, dino: bool = True,
+                 clip_global: bool = True, dataset: str = "hicodet"):
+        super().__init__()
+        C_, N = num_classes, cache_rows
+        self.detector, self.postprocessor, self.dino_model = detector, postprocessor, dino_model
+        self.clip_head = clip_head if clip_head is not None else _ClipHead(VisionTransformer())
+        self.num_classes, self.human_idx = num_classes, human_idx
+        self.box_score_thresh, self.min_instances, self.max_instances = box_score_thresh, min_instances, max_instances
+        self.hyper_lambda = hyper_lambda
+        self.object_class_to_target_class = object_class_to_target_class
+        self.dino, self.clip_global, self.dataset = dino, clip_global, dataset
+        self.visual_output_dim = 512
+        self.priors_initial_dim = 517
+        self.logits_type, self.cache_model, self.prior_type, self.prior_method = "HO+U+T", "gen_feat", "cbe", 0
+        self.use_insadapter = True
+        ls = math.log(1 / 0.07)
+        P = lambda *shape: nn.Parameter(torch.zeros(*shape))
+        if dino:
+            self.dino_cache = P(2048, N)
+            self.dino_cache_bias = nn.Parameter(-torch.ones(N))
+            self.dino_cache_logit = nn.Parameter(torch.ones([]) * ls)
+        if clip_global:
+            self.clip_cache_logit = nn.Parameter(torch.ones([]) * ls)
+            self.global_cache = P(512, N)
+            self.global_cache_bias = nn.Parameter(-torch.ones(N))
+        for X in ("U", "H", "O"):
+            setattr(self, f"gen_adapter_{X}_weight", P(N, 512))
+            setattr(self, f"gen_adapter_{X}_bias", nn.Parameter(-torch.ones(N)))
+            setattr(self, f"gen_label_{X}", nn.Parameter(torch.zeros(N, C_), requires_grad=False))
+            setattr(self, f"gen_logit_scale_{X}", nn.Parameter(torch.ones([]) * ls))
+        self.adapter_union_weight = P(C_, 512)
+        self.logit_scale_text = nn.Parameter(torch.ones([]) * ls)
+        self.priors_downproj = _PriorMLP()
+        # plain attributes, re-derived from the labels unless given (U:397-405, 436, 450)
+        self.sample_lens_H = self.sample_lens_O = self.sample_lens_U = None
+        self.dino_sample_len = self.global_sample_len = None
+        self.object_embedding = torch.zeros(80, 512)
+        self.origin_text_embeddings = None
+        self._packed = None
+        self._ws: Dict[str, torch.Tensor] = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
+
+    # ------------------------------------------------------------------------------------------------------
+    # construction helpers
+    # ------------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_state(cls, enc_state: Dict[str, torch.Tensor], head, **kw) -> "UPT":
+        """Build from a `clip_head.image_encoder.*` state dict + a HeadState (hoigen_b200.synthetic)."""
+        N = head.tensors["gen_adapter_U_weight"].shape[0]
+        m = cls(head.num_classes, N, object_class_to_target_class=head.object_class_to_target_class,
+                human_idx=head.hyper["human_idx"], box_score_thresh=head.hyper["box_score_thresh"],
+                min_instances=head.hyper["min_instances"], max_instances=head.hyper["max_instances"],
+                hyper_lambda=head.hyper["hyper_lambda"], **kw)
+        missing, unexpected = m.load_state_dict({**enc_state, **head.tensors}, strict=False)
+        assert not unexpected, unexpected
+        # only the unused prior=None adapter branch may be missing
+        assert all(".adaptermlp.mhsa." in k or ".norm1." in k for k in missing), missing
+        for k, v in head.attrs.items():
+            setattr(m, k, v.clone())
+        return m.eval()
+
+    @classmethod
+    def from_reference(cls, ref: nn.Module) -> "UPT":
+        """Wrap an already-built reference UPT (after build_detector + load_state_dict, M:865-880): keeps its DETR,
+        postprocessor, DINO model and text tower objects, re-hosts the visual tower and every hot-path parameter."""
+        sd = ref.state_dict()
+        N = sd["gen_adapter_U_weight"].shape[0]
+        ref_clip = ref.clip_head
+        m = cls(ref.num_classes, N, detector=ref.detector, postprocessor=ref.postprocessor,
+                dino_model=getattr(ref, "dino_model", None), human_idx=ref.human_idx,
+                box_score_thresh=ref.box_score_thresh, min_instances=ref.min_instances,
+                max_instances=ref.max_instances, hyper_lambda=ref.hyper_lambda,
+                object_class_to_target_class=ref.object_class_to_target_class, dino=bool(ref.dino),
+                clip_global=bool(ref.clip_global), dataset=ref.dataset)
+        vt = VisionTransformer()
+        vt.load_state_dict(ref_clip.image_encoder.state_dict(), strict=True)
+        ref_clip.image_encoder = vt          # text tower / prompt learner stay the reference's own modules
+        m.clip_head = ref_clip
+        own = {k: v for k, v in sd.items() if not k.startswith(("detector.", "clip_head.", "dino_model."))}
+        missing, unexpected = m.load_state_dict(own, strict=False)
+        assert not unexpected, unexpected
+        for k in ("sample_lens_H", "sample_lens_O", "sample_lens_U", "dino_sample_len", "global_sample_len",
+                  "object_embedding", "origin_text_embeddings"):
+            if hasattr(ref, k):
+                setattr(m, k, getattr(ref, k))
+        if getattr(ref, "zs_type", None) == "rare_first":
+            m.object_class_to_target_class = ref.object_to_verb   # U:821-822
+        return m.eval()
+
+    def invalidate_packed(self) -> None:
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_packed()
+        self._ws = {}
+        out = super()._apply(fn, *a, **k)
+        for name in ("sample_lens_H", "sample_lens_O", "sample_lens_U", "dino_sample_len", "global_sample_len",
+                     "object_embedding"):
+            t = getattr(self, name, None)
+            if isinstance(t, torch.Tensor):
+                setattr(self, name, fn(t))
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
+    # weight packing for the scoring / prior / emit kernels (build-time, not timed)
+    # ------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def pack_weights(self):
+        dev = self.adapter_union_weight.device
+        C_, N0 = self.num_classes, self.gen_adapter_U_weight.shape[0]
+        N = (N0 + 7) // 8 * 8   # TMA row strides are multiples of 16 bytes: pad the cache with all-zero rows (no effect)
+        padr = lambda t: torch.nn.functional.pad(t, (0, 0, 0, N - N0)) if N != N0 else t      # rows
+        padc = lambda t: torch.nn.functional.pad(t, (0, N - N0)) if N != N0 else t            # columns
+        bf = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        p: Dict[str, torch.Tensor] = {}
+        sw = _cabi.ScoreWeights()
+        sw.num_classes, sw.cache_rows = C_, N
+
+        def lens(name, label):
+            t = getattr(self, name, None)
+            return f32(t) if t is not None else f32(label.sum(0))
+
+        for i, X in enumerate(("H", "O", "U")):
+            W, b, Y = (getattr(self, f"gen_adapter_{X}_weight"), getattr(self, f"gen_adapter_{X}_bias"),
+                       getattr(self, f"gen_label_{X}"))
+            s = lens(f"sample_lens_{X}", Y)
+            p[f"keys_{X}"] = bf(padr(W.detach()))
+            p[f"bias_term_{X}"] = f32(b.float() @ Y.float())                       # (b Y), exact fp32 carrier of the bias
+            p[f"label_t_{X}"] = bf(padc(Y.detach().t()))                           # 0/1 -> exact in bf16
+            p[f"colscale_{X}"] = f32(getattr(self, f"gen_logit_scale_{X}").float() / s)
+            sw.cache_keys[i], sw.bias_term[i] = p[f"keys_{X}"].data_ptr(), p[f"bias_term_{X}"].data_ptr()
+            sw.label_t[i], sw.colscale[i] = p[f"label_t_{X}"].data_ptr(), p[f"colscale_{X}"].data_ptr()
+        Yu = self.gen_label_U.float()                                              # dino/global cache values (U:432,442)
+        if self.clip_global:
+            p["global_keys"] = bf(padr(self.global_cache.detach().t()))
+            p["global_bias_term"] = f32(self.global_cache_bias.float() @ Yu)
+            p["colscale_global"] = f32(self.clip_cache_logit.float() / lens("global_sample_len", Yu))
+        else:  # branch absent: zero keys contribute nothing
+            p["global_keys"] = torch.zeros(N, 512, device=dev, dtype=torch.bfloat16)
+            p["global_bias_term"] = torch.zeros(C_, device=dev)
+            p["colscale_global"] = torch.zeros(C_, device=dev)
+        sw.global_keys, sw.global_bias_term = p["global_keys"].data_ptr(), p["global_bias_term"].data_ptr()
+        sw.colscale_global = p["colscale_global"].data_ptr()
+        if self.dino:
+            p["dino_keys"] = bf(padr(self.dino_cache.detach().t()))
+            p["dino_bias_term"] = f32(self.dino_cache_bias.float() @ Yu)
+            p["colscale_dino"] = f32(self.dino_cache_logit.float() / lens("dino_sample_len", Yu))
+            sw.dino_keys, sw.dino_bias_term = p["dino_keys"].data_ptr(), p["dino_bias_term"].data_ptr()
+            sw.colscale_dino = p["colscale_dino"].data_ptr()
+        p["text_w"] = bf(self.adapter_union_weight)
+        p["colscale_text"] = f32(self.logit_scale_text.float().expand(C_))
+        sw.text_w, sw.colscale_text = p["text_w"].data_ptr(), p["colscale_text"].data_ptr()
+        # prior MLP, transposed to (in,out)
+        for i, lyr in enumerate(self.priors_downproj.layers):
+            p[f"prior_w{i}t"] = f32(lyr.weight.t())
+            p[f"prior_b{i}"] = f32(lyr.bias)
+        p["object_embedding"] = f32(self.object_embedding)
+        # object class -> target classes bitmask (80 x words)
+        import numpy as np
+        words = (C_ + 31) // 32
+        bits = np.zeros((len(self.object_class_to_target_class), words), dtype=np.uint32)
+        for o, tars in enumerate(self.object_class_to_target_class):
+            for t in tars:
+                bits[o, t // 32] |= np.uint32(1 << (t % 32))
+        p["table_bits"] = torch.from_numpy(bits.view(np.int32)).to(dev)
+        p["table_words"] = words
+        p["max_row_len"] = max((len(set(t)) for t in self.object_class_to_target_class), default=0)
+        self._packed = (p, sw)
+        return self._packed
+
+    # ------------------------------------------------------------------------------------------------------
+    # proposals (torch, as in the reference: U:1361-1406) — upstream of the accelerated path
+    # ------------------------------------------------------------------------------------------------------
+    def prepare_region_proposals(self, results: Sequence[dict]) -> List[dict]:
+        from torchvision.ops.boxes import batched_nms
+        region_props = []
+        for res in results:
+            sc, lb, bx = res["scores"], res["labels"], res["boxes"]
+            keep = batched_nms(bx, sc, lb, 0.5)
+            sc, lb, bx = sc[keep].view(-1), lb[keep].view(-1), bx[keep].view(-1, 4)
+            keep = torch.nonzero(sc >= self.box_score_thresh).squeeze(1)
+            is_human = lb == self.human_idx
+            hum = torch.nonzero(is_human).squeeze(1)
+            obj = torch.nonzero(is_human == 0).squeeze(1)
+            n_human = int(is_human[keep].sum())
+            n_object = len(keep) - n_human
+
+            def select(n_kept, pool, kept_mask):
+                if n_kept < self.min_instances:
+                    return pool[sc[pool].argsort(descending=True)[: self.min_instances]]
+                if n_kept > self.max_instances:
+                    return pool[sc[pool].argsort(descending=True)[: self.max_instances]]
+                return keep[torch.nonzero(kept_mask).squeeze(1)]
+
+            keep_h = select(n_human, hum, is_human[keep])
+            keep_o = select(n_object, obj, is_human[keep] == 0)
+            k = torch.cat([keep_h, keep_o])
+            # n_human is known on the host here for free; it spares the hot path a device sync
+            region_props.append(dict(boxes=bx[k], scores=sc[k], labels=lb[k], n_human=int(keep_h.numel())))
+        return region_props
+
+    def recover_boxes(self, boxes: torch.Tensor, size: torch.Tensor) -> torch.Tensor:
+        """cxcywh in [0,1] -> xyxy pixels (U:1269-1274)."""
+        cx, cy, w, h = boxes.unbind(-1)
+        b = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+        hh, ww = size
+        return b * torch.stack([ww, hh, ww, hh])
+
+    # ------------------------------------------------------------------------------------------------------
+    # the accelerated path: region proposals -> detections
+    # ------------------------------------------------------------------------------------------------------
+    def _buf(self, name: str, numel: int, dtype: torch.dtype, device) -> torch.Tensor:
+        t = self._ws.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype or t.device != device:
+            t = torch.empty(max(numel, 1), device=device, dtype=dtype)
+            self._ws[name] = t
+        return t
+
+    @torch.no_grad()
+    def forward_from_proposals(self, images_clip: torch.Tensor, region_props: Sequence[dict],
+                               dino_image_features: Optional[torch.Tensor] = None, *,
+                               return_intermediates: bool = False):
+        """(B,3,224,224) CLIP images + region proposals (+ L2-normalised DINO features) -> List[dict] as U:1421-1425.
+
+        Equivalent to U:1609-1663 with `prepare_region_proposals` outputs as input (humans lead each image)."""
+        dev = images_clip.device
+        _cabi.init(dev)
+        if self._packed is None:
+            self.pack_weights()
+        p, sw = self._packed
+        B = len(region_props)
+        Cn = self.num_classes
+        img_h, img_w = int(images_clip.shape[-2]), int(images_clip.shape[-1])
+        # ---- layout (host): CSR offsets of boxes and pairs -------------------------------------------------
+        n_list = [int(rp["boxes"].shape[0]) for rp in region_props]
+        if all("n_human" in rp for rp in region_props):
+            nh_list = [int(rp["n_human"]) for rp in region_props]
+        else:  # one batched device->host read instead of the reference's per-image syncs (U:985-998)
+            counts = torch.stack([(rp["labels"] == self.human_idx).sum() for rp in region_props]).cpu()
+            nh_list = [int(v) for v in counts]
+        n_max = max(n_list)
+        if n_max > MAX_PRIOR_TOKENS:
+            raise ValueError(f"at most {MAX_PRIOR_TOKENS} boxes per image are supported (got {n_max}); the reference caps "
+                             f"at 2*max_instances = {2 * self.max_instances}")
+        k_list = [(nh * (n - 1) if (nh > 0 and n > 1) else 0) for n, nh in zip(n_list, nh_list)]
+        box_off = [0]
+        pair_off = [0]
+        for n, k in zip(n_list, k_list):
+            box_off.append(box_off[-1] + n)
+            pair_off.append(pair_off[-1] + k)
+        ntot, ktot = box_off[-1], pair_off[-1]
+        layout = torch.tensor(box_off + pair_off + nh_list, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        d_box_off, d_pair_off, d_nh = layout[: B + 1], layout[B + 1: 2 * B + 2], layout[2 * B + 2:]
+        boxes = torch.cat([rp["boxes"] for rp in region_props]).float().contiguous()
+        scores = torch.cat([rp["scores"] for rp in region_props]).float().contiguous()
+        labels = torch.cat([rp["labels"] for rp in region_props]).to(torch.int64).contiguous()
+
+        # ---- a3: prior tokens --------------------------------------------------------------------------------
+        prior = self._buf("prior", B * n_max * 64, torch.float32, dev)[: B * n_max * 64].view(B, n_max, 64)
+        mask = self._buf("mask", B * n_max, torch.uint8, dev)[: B * n_max].view(B, n_max)
+        _cabi.call("hoigen_prior_tokens", boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), d_box_off.data_ptr(),
+                   p["object_embedding"].data_ptr(), p["prior_w0t"].data_ptr(), p["prior_b0"].data_ptr(),
+                   p["prior_w1t"].data_ptr(), p["prior_b1"].data_ptr(), p["prior_w2t"].data_ptr(), p["prior_b2"].data_ptr(),
+                   float(img_w), float(img_h), B, n_max, prior.data_ptr(), mask.data_ptr())
+        # ---- a4-a7: encoder ------------------------------------------------------------------------------------
+        tokens = self.clip_head.image_encoder.encode_tokens(images_clip, prior, mask)
+        # ---- a8: DINO features are an input of this path (stock module, as in the reference U:1616-1618) ---------
+        if self.dino and dino_image_features is None:
+            if self.dino_model is None:
+                raise ValueError("dino=True needs `dino_image_features` or a `dino_model`")
+            dino_image_features = self.dino_model(images_clip)
+            dino_image_features = dino_image_features / dino_image_features.norm(dim=-1, keepdim=True)
+        dino_ptr = dino_image_features.float().contiguous() if self.dino else None
+
+        if ktot == 0:
+            return None  # U:1660-1662: no image produced logits
+        # ---- a9: RoIAlign + pair assembly --------------------------------------------------------------------------
+        single = self._buf("single", ntot * 512, torch.float32, dev)
+        union = self._buf("union", ktot * 512, torch.float32, dev)
+        pf_bf16 = self._buf("pair_bf16", 3 * ktot * 512, torch.bfloat16, dev)
+        pf_f32 = self._buf("pair_f32", 3 * ktot * 512, torch.float32, dev) if return_intermediates else None
+        spatial_scale = 1.0 / (img_h / 14.0)                                          # U:1027
+        _cabi.call("hoigen_roi_pair_features", tokens.data_ptr(), boxes.data_ptr(), d_box_off.data_ptr(), d_nh.data_ptr(),
+                   d_pair_off.data_ptr(), B, ktot, float(spatial_scale), single.data_ptr(), union.data_ptr(),
+                   pf_bf16.data_ptr(), pf_f32.data_ptr() if pf_f32 is not None else None)
+        # ---- a10: cache + text logits --------------------------------------------------------------------------------
+        N = sw.cache_rows
+        logits = self._buf("logits", ktot * Cn, torch.float32, dev)
+        sb = _cabi.ScoreBuffers()
+        sb.pair_feat_bf16 = pf_bf16.data_ptr()
+        sb.phi = self._buf("phi", ktot * N, torch.bfloat16, dev).data_ptr()
+        sb.phi_img = self._buf("phi_img", B * N, torch.bfloat16, dev).data_ptr()
+        sb.g_bf16 = self._buf("g_bf16", B * 512, torch.bfloat16, dev).data_ptr()
+        sb.d_bf16 = self._buf("d_bf16", B * 2048, torch.bfloat16, dev).data_ptr()
+        sb.img_logits = self._buf("img_logits", B * Cn, torch.float32, dev).data_ptr()
+        sb.logits = logits.data_ptr()
+        _cabi.call("hoigen_score_pairs", C.byref(sw), C.byref(sb), tokens.data_ptr(),
+                   dino_ptr.data_ptr() if dino_ptr is not None else None, d_pair_off.data_ptr(), B, ktot)
+        # ---- a11-a12: prior scores + ordered triplet emission ----------------------------------------------------------
+        cap = ktot * p["max_row_len"]
+        out_scores = torch.empty(max(cap, 1), device=dev, dtype=torch.float32)
+        out_labels = torch.empty(max(cap, 1), device=dev, dtype=torch.int64)
+        out_objects = torch.empty(max(cap, 1), device=dev, dtype=torch.int64)
+        out_pairing = torch.empty(max(2 * cap, 2), device=dev, dtype=torch.int64)
+        img_off = torch.empty(B + 1, device=dev, dtype=torch.int32)
+        _cabi.call("hoigen_emit_triplets", logits.data_ptr(), Cn, scores.data_ptr(), labels.data_ptr(), d_box_off.data_ptr(),
+                   d_pair_off.data_ptr(), B, ktot, p["table_bits"].data_ptr(), p["table_words"], float(self.hyper_lambda),
+                   self._buf("emit_counts", ktot, torch.int32, dev).data_ptr(),
+                   self._buf("emit_offsets", ktot + 1, torch.int32, dev).data_ptr(),
+                   self._buf("emit_pr", ktot, torch.float32, dev).data_ptr(), cap, out_scores.data_ptr(),
+                   out_labels.data_ptr(), out_objects.data_ptr(), out_pairing.data_ptr(), img_off.data_ptr())
+        # ---- the single device->host read of the path: per-image triplet offsets --------------------------------------
+        offs = img_off.cpu().tolist()
+        sizes = torch.tensor([[img_h, img_w]] * B, device=dev, dtype=torch.int64)
+        detections = []
+        for b in range(B):
+            s, e = offs[b], offs[b + 1]
+            detections.append(dict(
+                boxes=region_props[b]["boxes"],
+                pairing=out_pairing[2 * s: 2 * e].view(2, e - s),
+                scores=out_scores[s:e], labels=out_labels[s:e], objects=out_objects[s:e], size=sizes[b]))
+        if return_intermediates:
+            inter = dict(prior=prior, mask=mask.bool(), tokens=tokens.view(B, TOKENS, 512),
+                         logits=[logits[: ktot * Cn].view(ktot, Cn)[pair_off[b]: pair_off[b + 1]] for b in range(B)],
+                         pair_feats=pf_f32[: 3 * ktot * 512].view(3, ktot, 512), pair_off=pair_off, box_off=box_off)
+            return detections, inter
+        return detections
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward(self, images: List, targets: Optional[List[dict]] = None):
+        """U:1543-1664, eval branch. images: List[(img_detr (3,H,W), img_clip (3,224,224))]."""
+        if self.training:
+            raise NotImplementedError("hoigen_b200 accelerates the eval forward; train with the reference module")
+        images_orig = [im[0].float() for im in images]
+        images_clip = [im[1] for im in images]
+        device = images_clip[0].device
+        image_sizes = torch.as_tensor([im.size()[-2:] for im in images_clip], device=device)
+        if self.detector is None or self.postprocessor is None:
+            raise ValueError("UPT.forward needs the injected `detector` and `postprocessor` (U:303-304); "
+                             "use forward_from_proposals for precomputed region proposals")
+        nested = nested_tensor_from_tensor_list(images_orig)
+        features, pos = self.detector.backbone(nested)
+        src, mask = features[-1].decompose()
+        hs, _ = self.detector.transformer(self.detector.input_proj(src), mask, self.detector.query_embed.weight, pos[-1])
+        outputs_class = self.detector.class_embed(hs)
+        outputs_coord = self.detector.bbox_embed(hs).sigmoid()
+        results = self.postprocessor({"pred_logits": outputs_class[-1], "pred_boxes": outputs_coord[-1]}, image_sizes)
+        region_props = self.prepare_region_proposals(results)
+        clip = nested_tensor_from_tensor_list(images_clip).tensors
+        return self.forward_from_proposals(clip, region_props)

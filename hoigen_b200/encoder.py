@@ -1,0 +1,235 @@
+"""B200 visual encoder behind the reference's `VisionTransformer.forward(x, prior)` surface.
+
+Mirrors CLIP_models_adapter_prior2.py:463-506 (VisionTransformer), :423-459 (ResidualAttentionBlock) and
+:134-203 (Adapter): same constructor arguments, same parameter names/shapes (so `load_state_dict` of a reference
+checkpoint works unchanged), same return value `(feat_global (B,512), feat_local (B,512,14,14) view)`.
+The arithmetic runs in hand-written sm_100a kernels through the C ABI (hoigen_encoder_forward); there is no
+PyTorch fallback — on a machine without the CUDA library `forward` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _cabi
+
+TOKENS = 197
+MAX_PRIOR_TOKENS = 32
+
+
+class _ParamBag(nn.Module):
+    """A module that only holds parameters (keeps the reference's dotted state_dict names)."""
+
+
+def _linear_params(out_f: int, in_f: int) -> nn.Module:
+    m = _ParamBag()
+    m.weight = nn.Parameter(torch.empty(out_f, in_f))
+    m.bias = nn.Parameter(torch.empty(out_f))
+    return m
+
+
+def _ln_params(dim: int) -> nn.Module:
+    m = _ParamBag()
+    m.weight = nn.Parameter(torch.ones(dim))
+    m.bias = nn.Parameter(torch.zeros(dim))
+    return m
+
+
+def _mha_params(dim: int) -> nn.Module:
+    m = _ParamBag()
+    m.in_proj_weight = nn.Parameter(torch.empty(3 * dim, dim))
+    m.in_proj_bias = nn.Parameter(torch.empty(3 * dim))
+    m.out_proj = _linear_params(dim, dim)
+    return m
+
+
+def _decoder_layer_params(dim: int, ff: int) -> nn.Module:
+    """TransformerDecoderLayer parameter set (C:27-44): multihead_attn, linear1/2, norm1/2/3."""
+    m = _ParamBag()
+    m.multihead_attn = _mha_params(dim)
+    m.linear1 = _linear_params(ff, dim)
+    m.linear2 = _linear_params(dim, ff)
+    m.norm1, m.norm2, m.norm3 = _ln_params(dim), _ln_params(dim), _ln_params(dim)
+    return m
+
+
+class Adapter(_ParamBag):
+    """Parameter layout of C:134-181 (bottleneck 64, 2-head decoder layer(s), learnable per-channel scale)."""
+
+    def __init__(self, d_model: int = 768, bottleneck: int = 64, adapter_num_layers: int = 1):
+        super().__init__()
+        if adapter_num_layers != 1:
+            raise NotImplementedError("hoigen_b200 implements adapter_num_layers == 1 (the reference default, M:1139)")
+        self.scale = nn.Parameter(torch.ones(d_model) * 1e-9)
+        self.down_proj = _linear_params(bottleneck, d_model)
+        self.up_proj = _linear_params(d_model, bottleneck)
+        self.mhsa_layers = nn.ModuleList([_decoder_layer_params(bottleneck, 2 * bottleneck)])
+        self.mhsa = _decoder_layer_params(bottleneck, 2 * bottleneck)  # only used when prior is None (not on this path)
+
+
+class ResidualAttentionBlock(_ParamBag):
+    def __init__(self, d_model: int, adapter: bool, adapter_num_layers: int = 1):
+        super().__init__()
+        self.attn = _mha_params(d_model)
+        self.ln_1 = _ln_params(d_model)
+        self.mlp = _ParamBag()
+        self.mlp.c_fc = _linear_params(4 * d_model, d_model)
+        self.mlp.c_proj = _linear_params(d_model, 4 * d_model)
+        self.ln_2 = _ln_params(d_model)
+        if adapter:
+            self.adaptermlp = Adapter(d_model, 64, adapter_num_layers)
+        self.adapter = adapter
+
+
+class Transformer(_ParamBag):
+    def __init__(self, width: int, layers: int, adapter: bool, adapter_layers: List[int], adapter_num_layers: int):
+        super().__init__()
+        self.width, self.layers = width, layers
+        self.resblocks = nn.ModuleList(
+            [ResidualAttentionBlock(width, adapter and (i in adapter_layers), adapter_num_layers) for i in range(layers)])
+
+
+class VisionTransformer(nn.Module):
+    """Drop-in for C:VisionTransformer (ViT-B/16, 224^2, adapter in every block)."""
+
+    def __init__(self, input_resolution: int = 224, patch_size: int = 16, width: int = 768, layers: int = 12,
+                 heads: int = 12, output_dim: int = 512, use_adapter: bool = True,
+                 adapter_layers: Optional[List[int]] = None, adapter_num_layers: int = 1):
+        super().__init__()
+        if (input_resolution, patch_size, width, layers, heads, output_dim) != (224, 16, 768, 12, 12, 512):
+            raise NotImplementedError("hoigen_b200 kernels are specialised for CLIP ViT-B/16 @224 (768 wide, 12x12, 512 out)")
+        adapter_layers = list(range(24)) if adapter_layers is None else adapter_layers
+        if not use_adapter or any(i not in adapter_layers for i in range(layers)):
+            raise NotImplementedError("hoigen_b200 implements use_insadapter=True with adapter_pos='all' (M:1099,1144)")
+        self.input_resolution, self.output_dim, self.patch_size = input_resolution, output_dim, patch_size
+        self.conv1 = _ParamBag()
+        self.conv1.weight = nn.Parameter(torch.empty(width, 3, patch_size, patch_size))
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = _ln_params(width)
+        self.transformer = Transformer(width, layers, use_adapter, adapter_layers, adapter_num_layers)
+        self.ln_post = _ln_params(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._packed: Optional[Dict[str, torch.Tensor]] = None
+        self._packed_struct = None
+        self._ws_cache: Dict[Tuple[int, int], Tuple[Dict[str, torch.Tensor], object]] = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
+
+    # ------------------------------------------------------------------------------------------------------
+    def invalidate_packed(self) -> None:
+        """Call after mutating parameters in place; load_state_dict / .to() do it automatically."""
+        self._packed = None
+        self._packed_struct = None
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_packed()
+        self._ws_cache = {}
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def pack_weights(self) -> Dict[str, torch.Tensor]:
+        """Re-pack the reference parameters for the kernels: GEMM operands bf16 [N,K] stacked over layers,
+        vectors fp32; conv1 flattened to (768, 3*16*16); proj transposed to (512,768)."""
+        dev = self.proj.device
+        blocks = self.transformer.resblocks
+        bf = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        st = lambda get: torch.stack([get(b).detach() for b in blocks])
+        dl = lambda b: b.adaptermlp.mhsa_layers[0]
+        p = {
+            "conv_w": bf(self.conv1.weight.reshape(768, -1)),
+            "class_embedding": f32(self.class_embedding),
+            "positional_embedding": f32(self.positional_embedding),
+            "ln_pre_w": f32(self.ln_pre.weight), "ln_pre_b": f32(self.ln_pre.bias),
+            "ln_post_w": f32(self.ln_post.weight), "ln_post_b": f32(self.ln_post.bias),
+            "proj_t": bf(self.proj.t()),
+            "ln1_w": f32(st(lambda b: b.ln_1.weight)), "ln1_b": f32(st(lambda b: b.ln_1.bias)),
+            "ln2_w": f32(st(lambda b: b.ln_2.weight)), "ln2_b": f32(st(lambda b: b.ln_2.bias)),
+            "qkv_w": bf(st(lambda b: b.attn.in_proj_weight)), "qkv_b": f32(st(lambda b: b.attn.in_proj_bias)),
+            "out_w": bf(st(lambda b: b.attn.out_proj.weight)), "out_b": f32(st(lambda b: b.attn.out_proj.bias)),
+            "fc_w": bf(st(lambda b: b.mlp.c_fc.weight)), "fc_b": f32(st(lambda b: b.mlp.c_fc.bias)),
+            "proj_w": bf(st(lambda b: b.mlp.c_proj.weight)), "proj_b": f32(st(lambda b: b.mlp.c_proj.bias)),
+            "ad_down_w": bf(st(lambda b: b.adaptermlp.down_proj.weight)),
+            "ad_down_b": f32(st(lambda b: b.adaptermlp.down_proj.bias)),
+            "ad_up_w": bf(st(lambda b: b.adaptermlp.up_proj.weight)),
+            "ad_up_b": f32(st(lambda b: b.adaptermlp.up_proj.bias)),
+            "ad_scale": f32(st(lambda b: b.adaptermlp.scale)),
+            "ad_in_proj_w": f32(st(lambda b: dl(b).multihead_attn.in_proj_weight)),
+            "ad_in_proj_b": f32(st(lambda b: dl(b).multihead_attn.in_proj_bias)),
+            "ad_out_proj_w": f32(st(lambda b: dl(b).multihead_attn.out_proj.weight)),
+            "ad_out_proj_b": f32(st(lambda b: dl(b).multihead_attn.out_proj.bias)),
+            "ad_linear1_w": f32(st(lambda b: dl(b).linear1.weight)), "ad_linear1_b": f32(st(lambda b: dl(b).linear1.bias)),
+            "ad_linear2_w": f32(st(lambda b: dl(b).linear2.weight)), "ad_linear2_b": f32(st(lambda b: dl(b).linear2.bias)),
+            "ad_norm2_w": f32(st(lambda b: dl(b).norm2.weight)), "ad_norm2_b": f32(st(lambda b: dl(b).norm2.bias)),
+            "ad_norm3_w": f32(st(lambda b: dl(b).norm3.weight)), "ad_norm3_b": f32(st(lambda b: dl(b).norm3.bias)),
+        }
+        assert set(p) == set(_cabi.ENCODER_WEIGHT_FIELDS)
+        s = _cabi.EncoderWeights()
+        for k, v in p.items():
+            setattr(s, k, v.data_ptr())
+        self._packed, self._packed_struct = p, s
+        return p
+
+    def _workspace(self, batch: int, n_max: int):
+        key = (batch, n_max)
+        if key not in self._ws_cache:
+            dev = self.proj.device
+            M = batch * TOKENS
+            e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
+            bf, f32 = torch.bfloat16, torch.float32
+            b = {
+                "patches": e((batch * 196, 768), bf), "patch_emb": e((batch * 196, 768), f32),
+                "x": e((M, 768), f32), "xb": e((M, 768), bf), "h": e((M, 768), bf), "qkv": e((M, 2304), bf),
+                "attn": e((M, 768), bf), "mlp": e((M, 3072), bf), "adapter_d": e((M, 64), f32),
+                "adapter_t": e((M, 64), bf), "adapter_kv": e((12, batch * n_max, 128), f32),
+                "tokens_out": e((M, 512), f32),
+            }
+            s = _cabi.EncoderBuffers()
+            for k, v in b.items():
+                setattr(s, k, v.data_ptr())
+            if len(self._ws_cache) > 4:
+                self._ws_cache.clear()
+            self._ws_cache[key] = (b, s)
+        return self._ws_cache[key]
+
+    # ------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_tokens(self, x: torch.Tensor, prior: torch.Tensor, mask: torch.Tensor, num_layers: int = 12,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-> (B*197, 512) fp32 = ln_post(all tokens) @ proj; row b*197 is feat_global[b], the next 196 rows are the
+        14x14 grid of feat_local[b] in token-major (channel-contiguous) layout — exactly the physical layout the
+        reference's permuted view has (C:506)."""
+        _cabi.init(x.device)
+        if self.training:
+            raise NotImplementedError("hoigen_b200 implements the eval forward only")
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != (3, 224, 224):
+            raise ValueError(f"expected (B,3,224,224) images, got {tuple(x.shape)}")
+        n_max = prior.shape[1]
+        if n_max > MAX_PRIOR_TOKENS:
+            raise ValueError(f"at most {MAX_PRIOR_TOKENS} prior tokens per image are supported (got {n_max})")
+        if self._packed is None:
+            self.pack_weights()
+        x = x.contiguous().float()
+        prior = prior.contiguous().float()
+        mask_u8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous().to(torch.uint8)
+        bufs, bstruct = self._workspace(B, n_max)
+        _cabi.call("hoigen_encoder_forward", C.byref(self._packed_struct), C.byref(bstruct), x.data_ptr(),
+                   prior.data_ptr(), mask_u8.data_ptr(), B, n_max, num_layers)
+        return bufs["tokens_out"]
+
+    def forward(self, x: torch.Tensor, prior=None):
+        """C:489-506: returns (x[:,0,:], x[:,1:,:].view(B,14,14,512).permute(0,3,1,2))."""
+        if prior is None:
+            raise NotImplementedError(
+                "VisionTransformer.forward(x, prior=None) (self-attention adapter branch, C:194-199) is only used at "
+                "cache-construction time (utils.py:21) and is outside the accelerated path")
+        ctx, mask = prior
+        # the kernels write into a reused workspace: hand the caller its own copy
+        y = self.encode_tokens(x, ctx, mask).clone().view(x.shape[0], TOKENS, self.output_dim)
+        g = self.input_resolution // self.patch_size
+        return y[:, 0, :], y[:, 1:, :].view(x.shape[0], g, g, -1).permute(0, 3, 1, 2)

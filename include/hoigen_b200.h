@@ -75,6 +75,156 @@ HOIGEN_API int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t str
 /* Test-only SIMT cross-check of the same contract (never used by the product path). */
 HOIGEN_API int hoigen_debug_gemm_simt(const hoigen_gemm_params* p, hoigen_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Encoder row kernels (memory bound).  tokens = rows b*197+t of (B*197, 768) fp32 residual stream.
+ * ---------------------------------------------------------------------------------------------- */
+/* images (B,3,224,224) fp32 -> patches (B*196, 768) bf16, column = c*256+ky*16+kx: im2col of conv1, C:491 */
+HOIGEN_API int hoigen_patchify_bf16(const float* images, void* patches_bf16, int32_t batch, hoigen_stream_t stream);
+/* x[b,t] = ln_pre((t==0 ? class_embedding : patch_emb[b,t-1]) + positional_embedding[t])   C:494-496 */
+HOIGEN_API int hoigen_embed_lnpre(const float* patch_emb, const float* class_embedding, const float* positional_embedding,
+                                  const float* gamma, const float* beta, float* x_f32, void* x_bf16, int32_t batch,
+                                  hoigen_stream_t stream);
+/* LayerNorm over 768 columns, fp32 statistics, eps 1e-5 (C:409-415) -> bf16 and/or fp32 */
+HOIGEN_API int hoigen_layernorm768(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
+                                   int32_t rows, hoigen_stream_t stream);
+/* Adapter cross-attention K/V of the prior tokens for all layers: kv[l][tok][0:64]=K, [64:128]=V  (C:63-66).
+ * in_proj_w (layers,192,64) rows [q;k;v], in_proj_b (layers,192); prior (tokens,64). */
+HOIGEN_API int hoigen_adapter_kv(const float* prior, const float* in_proj_w, const float* in_proj_b, float* kv,
+                                 int32_t tokens, int32_t layers, hoigen_stream_t stream);
+
+typedef struct {
+  const float* in_proj_w;  /* (192,64) rows [q;k;v]   multihead_attn.in_proj_weight */
+  const float* in_proj_b;  /* (192) */
+  const float* out_proj_w; /* (64,64) */
+  const float* out_proj_b; /* (64) */
+  const float* linear1_w;  /* (128,64) */
+  const float* linear1_b;  /* (128) */
+  const float* linear2_w;  /* (64,128) */
+  const float* linear2_b;  /* (64) */
+  const float* norm2_w; const float* norm2_b; const float* norm3_w; const float* norm3_b; /* (64) */
+} hoigen_adapter_mid_weights;
+/* Adapter bottleneck body for one layer, Adapter.forward C:186-200 / forward_post C:51-72:
+ * d = relu(down_proj(x)) (B*197,64) fp32 -> LN3(t + FFN(t)), t = LN2(d + MHA_2h(d, prior, mask)) -> bf16 (B*197,64).
+ * kv_layer (B*n_max,128) from hoigen_adapter_kv; mask (B,n_max) uint8, 1 = padding. n_max <= 32. */
+HOIGEN_API int hoigen_adapter_mid(const float* d, const float* kv_layer, const uint8_t* mask,
+                                  const hoigen_adapter_mid_weights* w, void* out_bf16, int32_t batch, int32_t n_max,
+                                  hoigen_stream_t stream);
+/* 12-head attention over 197 tokens (tcgen05): qkv bf16 (B*197, 2304) = [q|k|v] -> out bf16 (B*197, 768). C:443-445 */
+HOIGEN_API int hoigen_attention(const void* qkv_bf16, void* out_bf16, int32_t batch, hoigen_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole visual encoder = VisionTransformer.forward(x, prior), C:489-506.  One call per batch.
+ * Weights are the reference parameters re-packed once at build time (bf16 GEMM operands, fp32 vectors),
+ * stacked over the 12 layers; see hoigen_b200/encoder.py::pack_encoder_weights for the exact mapping.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* conv_w;                 /* bf16 (768, 768)      conv1.weight.view(768,-1) */
+  const float* class_embedding;       /* (768) */
+  const float* positional_embedding;  /* (197,768) */
+  const float* ln_pre_w; const float* ln_pre_b; const float* ln_post_w; const float* ln_post_b; /* (768) */
+  const void* proj_t;                 /* bf16 (512, 768)      proj^T */
+  const float* ln1_w; const float* ln1_b; const float* ln2_w; const float* ln2_b;  /* (12,768) */
+  const void* qkv_w; const float* qkv_b;     /* bf16 (12,2304,768), (12,2304)   attn.in_proj_* */
+  const void* out_w; const float* out_b;     /* bf16 (12,768,768),  (12,768)    attn.out_proj.* */
+  const void* fc_w; const float* fc_b;       /* bf16 (12,3072,768), (12,3072)   mlp.c_fc.* */
+  const void* proj_w; const float* proj_b;   /* bf16 (12,768,3072), (12,768)    mlp.c_proj.* */
+  const void* ad_down_w; const float* ad_down_b;  /* bf16 (12,64,768), (12,64)  adaptermlp.down_proj.* */
+  const void* ad_up_w; const float* ad_up_b;      /* bf16 (12,768,64), (12,768) adaptermlp.up_proj.* */
+  const float* ad_scale;                          /* (12,768)                   adaptermlp.scale */
+  const float* ad_in_proj_w; const float* ad_in_proj_b;    /* (12,192,64), (12,192)  mhsa_layers.0.multihead_attn */
+  const float* ad_out_proj_w; const float* ad_out_proj_b;  /* (12,64,64), (12,64) */
+  const float* ad_linear1_w; const float* ad_linear1_b;    /* (12,128,64), (12,128) */
+  const float* ad_linear2_w; const float* ad_linear2_b;    /* (12,64,128), (12,64) */
+  const float* ad_norm2_w; const float* ad_norm2_b; const float* ad_norm3_w; const float* ad_norm3_b; /* (12,64) */
+} hoigen_encoder_weights;
+
+typedef struct {            /* caller-owned workspace, M = B*197 */
+  void* patches;            /* bf16 (B*196, 768) */
+  float* patch_emb;         /* f32  (B*196, 768) */
+  float* x;                 /* f32  (M, 768)   residual stream */
+  void* xb;                 /* bf16 (M, 768)   bf16 copy of x (adapter down-proj operand) */
+  void* h;                  /* bf16 (M, 768)   LayerNorm output */
+  void* qkv;                /* bf16 (M, 2304) */
+  void* attn;               /* bf16 (M, 768) */
+  void* mlp;                /* bf16 (M, 3072) */
+  float* adapter_d;         /* f32  (M, 64) */
+  void* adapter_t;          /* bf16 (M, 64) */
+  float* adapter_kv;        /* f32  (12, B*n_max, 128) */
+  float* tokens_out;        /* f32  (M, 512)   OUTPUT: ln_post(x) @ proj for all tokens; row b*197 = feat_global[b],
+                                               rows b*197+1.. = feat_local[b] token-major (C:503-506) */
+} hoigen_encoder_buffers;
+
+/* prior (B,n_max,64) fp32 and mask (B,n_max) uint8 (1 = padding) as produced by hoigen_prior_tokens. */
+HOIGEN_API int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder_buffers* buf,
+                                      const float* images, const float* prior, const uint8_t* mask, int32_t batch,
+                                      int32_t n_max, int32_t num_layers, hoigen_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * HOI head.  Boxes/scores/labels of all images are concatenated; box_off (B+1) and pair_off (B+1) are CSR
+ * offsets (pairs per image K_b = n_h*(n_b-1), or 0 when n_h == 0 or n_b <= 1; humans lead: U:988-1016).
+ * ---------------------------------------------------------------------------------------------- */
+/* get_prior U:1445-1495 (prior_type 'cbe', prior_method 0) incl. the 517->128->128->64 MLP (U:40-52, U:520).
+ * w*t are the Linear weights TRANSPOSED to (in,out). Outputs prior (B,n_max,64), mask (B,n_max) 1=padding. */
+HOIGEN_API int hoigen_prior_tokens(const float* boxes, const float* scores, const int64_t* labels, const int32_t* box_off,
+                                   const float* object_embedding, const float* w0t, const float* b0, const float* w1t,
+                                   const float* b1, const float* w2t, const float* b2, float img_w, float img_h,
+                                   int32_t batch, int32_t n_max, float* prior, uint8_t* mask, hoigen_stream_t stream);
+/* compute_roi_embeddings geometry U:981-1057: RoIAlign(7x7, sampling_ratio=-1, aligned=True)+mean of every single
+ * box and every union box on the 14x14 token grid (torchvision.ops.roi_align call sites U:1028-1029), then
+ * f_H = single[x]/|.|, f_O = single[y]/|.|, f_U = union/|.|  -> pair_feat [3][Ktot][512] (H,O,U) bf16 (+fp32). */
+HOIGEN_API int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int32_t* box_off,
+                                        const int32_t* n_human, const int32_t* pair_off, int32_t batch, int32_t ktot,
+                                        float spatial_scale, float* single_feat, float* union_feat,
+                                        void* pair_feat_bf16, float* pair_feat_f32, hoigen_stream_t stream);
+HOIGEN_API int hoigen_rows_to_bf16(const float* in, int64_t ld_in, int32_t rows, int32_t cols, int32_t normalize,
+                                   void* out_bf16, hoigen_stream_t stream);
+HOIGEN_API int hoigen_broadcast_image_logits(const float* img_logits, const int32_t* pair_off, int32_t batch,
+                                             int32_t ktot, int32_t num_classes, float* logits, hoigen_stream_t stream);
+
+typedef struct {                   /* scoring weights, packed once at build time (U:1156-1163, 1112-1115, 1133-1138) */
+  int32_t num_classes;             /* C */
+  int32_t cache_rows;              /* N (multiple of 8) */
+  const void* cache_keys[3];       /* bf16 (N,512)   gen_adapter_{H,O,U}_weight            order: H, O, U */
+  const float* bias_term[3];       /* f32 (C)        gen_adapter_X_bias @ gen_label_X */
+  const void* label_t[3];          /* bf16 (C,N)     gen_label_X^T (multi-hot, exact in bf16) */
+  const float* colscale[3];        /* f32 (C)        gen_logit_scale_X / sample_lens_X */
+  const void* global_keys;         /* bf16 (N,512)   global_cache^T */
+  const float* global_bias_term;   /* f32 (C)        global_cache_bias @ gen_label_U */
+  const float* colscale_global;    /* f32 (C)        clip_cache_logit / global_sample_len */
+  const void* dino_keys;           /* bf16 (N,2048)  dino_cache^T, or NULL */
+  const float* dino_bias_term;     /* f32 (C) */
+  const float* colscale_dino;      /* f32 (C)        dino_cache_logit / dino_sample_len */
+  const void* text_w;              /* bf16 (C,512)   adapter_union_weight */
+  const float* colscale_text;      /* f32 (C)        logit_scale_text broadcast */
+} hoigen_score_weights;
+
+typedef struct {                   /* caller-owned workspace */
+  const void* pair_feat_bf16;      /* bf16 [3][Ktot][512] from hoigen_roi_pair_features */
+  void* phi;                       /* bf16 (Ktot, N) */
+  void* phi_img;                   /* bf16 (B, N) */
+  void* g_bf16;                    /* bf16 (B, 512) */
+  void* d_bf16;                    /* bf16 (B, 2048) */
+  float* img_logits;               /* f32 (B, C) */
+  float* logits;                   /* f32 (Ktot, C)   OUTPUT */
+} hoigen_score_buffers;
+
+/* logits = sum_X scale_X * ((f_X W_X^T + b_X) Y_X)/s_X + scale_T f_U T^T + per-image global/DINO cache terms.
+ * tokens = encoder output (B*197,512); dino_feats (B,2048) L2-normalised fp32 or NULL. */
+HOIGEN_API int hoigen_score_pairs(const hoigen_score_weights* w, const hoigen_score_buffers* buf, const float* tokens,
+                                  const float* dino_feats, const int32_t* pair_off, int32_t batch, int32_t ktot,
+                                  hoigen_stream_t stream);
+
+/* compute_prior_scores U:806-833 + postprocessing U:1408-1427, whole batch, reference (row-major) order.
+ * table_bits (80, table_words) uint32 bitmask of object_class_to_target_class. Outputs are packed over images:
+ * scores/labels/objects [Mtot]; pairing holds, per image b, a contiguous [2][M_b] block at 2*img_off[b];
+ * img_off (B+1) int32 triplet offsets. capacity = allocated Mtot; entries beyond it are dropped (check img_off[B]). */
+HOIGEN_API int hoigen_emit_triplets(const float* logits, int32_t num_classes, const float* scores, const int64_t* labels,
+                                    const int32_t* box_off, const int32_t* pair_off, int32_t batch, int32_t ktot,
+                                    const uint32_t* table_bits, int32_t table_words, float hyper_lambda,
+                                    int32_t* work_counts, int32_t* work_offsets, float* work_pr, int64_t capacity,
+                                    float* out_scores, int64_t* out_labels, int64_t* out_objects, int64_t* out_pairing,
+                                    int32_t* img_off, hoigen_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

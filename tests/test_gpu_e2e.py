@@ -1,0 +1,238 @@
+"""End-to-end GPU parity through the reference-facing surface (UPT.forward_from_proposals / UPT.forward) against
+(a) the committed outputs of the UNMODIFIED reference (tests/golden/*.npz, made by oracle/make_golden.py) and
+(b) the oracle restatement on fresh seeded inputs.
+
+Bars (BASELINE.json north_star): pair enumeration, pairing, labels, objects and triplet order BIT-EXACT;
+logits max-abs <= 1e-2 (bf16 tensor-core path); scores within the matching relative tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-2          # north_star: bf16 max-abs <= 1e-2
+SCORE_RTOL = 1.5e-2       # d(sigmoid(l) * pr) / score <= |dl|
+
+
+def _props_to(props, dev):
+    return [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in p.items()} for p in props]
+
+
+def _build(num_classes, N, dev, max_instances=15):
+    from hoigen_b200 import synthetic as S
+    from hoigen_b200.detector import UPT
+    enc = S.make_encoder_state(0)
+    head = S.make_head_state(num_classes, N, seed=2, max_instances=max_instances)
+    return UPT.from_state(enc, head).to(dev), enc, head
+
+
+def _oob_props(props):
+    g = torch.Generator().manual_seed(4242)
+    for p in props:
+        n = p["boxes"].shape[0]
+        shift = (torch.rand(n, 2, generator=g) - 0.5) * 260.0
+        p["boxes"] = p["boxes"] + torch.cat([shift, shift], dim=1)
+        p["boxes"][0] = torch.tensor([-40.0, -30.0, 20.0, 260.0])
+        p["boxes"][-1] = torch.tensor([100.0, 180.0, 330.0, 300.0])
+    return props
+
+
+CASES = {
+    "hico117_b2": dict(num_classes=117, B=2, n_h=8, n_o=8, N=256, ragged=False, oob=False),
+    "hico117_ragged_b3": dict(num_classes=117, B=3, n_h=6, n_o=7, N=234, ragged=True, oob=False),
+    "hico117_oob_b1": dict(num_classes=117, B=1, n_h=4, n_o=5, N=128, ragged=False, oob=True),
+    "vcoco24_b2": dict(num_classes=24, B=2, n_h=16, n_o=16, N=96, ragged=False, oob=False, max_instances=16),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_matches_reference_golden(cuda_device, name):
+    from hoigen_b200 import synthetic as S
+    c = CASES[name]
+    gold = np.load(f"tests/golden/{name}.npz")
+    m, enc, head = _build(c["num_classes"], c["N"], cuda_device, c.get("max_instances", 15))
+    props = S.make_region_props(c["B"], c["n_h"], c["n_o"], ragged=c["ragged"])
+    if c["oob"]:
+        props = _oob_props(props)
+    imgs = S.make_images(c["B"], seed=1).to(cuda_device)
+    dino = S.make_dino_features(c["B"]).to(cuda_device)
+    dets, inter = m.forward_from_proposals(imgs, _props_to(props, cuda_device), dino, return_intermediates=True)
+    assert len(dets) == c["B"]
+    worst_logit = 0.0
+    for b, d in enumerate(dets):
+        assert d["pairing"].dtype == torch.int64 and d["labels"].dtype == torch.int64 and d["objects"].dtype == torch.int64
+        assert np.array_equal(d["pairing"].cpu().numpy(), gold[f"pairing_{b}"]), "pairing not bit-exact"
+        assert np.array_equal(d["labels"].cpu().numpy(), gold[f"labels_{b}"]), "labels not bit-exact"
+        assert np.array_equal(d["objects"].cpu().numpy(), gold[f"objects_{b}"]), "objects not bit-exact"
+        assert np.array_equal(d["boxes"].cpu().numpy(), gold[f"boxes_{b}"])
+        lg, ref = inter["logits"][b].cpu().numpy(), gold[f"logits_{b}"]
+        assert np.array_equal(np.isnan(lg), np.isnan(ref)), "NaN pattern differs"
+        err = np.nanmax(np.abs(lg - ref)) if np.isfinite(ref).any() else 0.0
+        worst_logit = max(worst_logit, float(err))
+        sc, sref = d["scores"].cpu().numpy(), gold[f"scores_{b}"]
+        assert np.array_equal(np.isnan(sc), np.isnan(sref))
+        ok = np.isfinite(sref)
+        assert np.all(np.abs(sc[ok] - sref[ok]) <= SCORE_RTOL * np.abs(sref[ok]) + 1e-30)
+    print(f"{name}: logits max-abs err vs reference {worst_logit:.3e}")
+    assert worst_logit <= LOGIT_TOL, worst_logit
+
+
+def test_matches_oracle_fresh_inputs(cuda_device):
+    """Fresh seeds (not in the fixtures), N=4096 cache, B=4 ragged: the bench configuration's shapes."""
+    from hoigen_b200 import synthetic as S
+    from oracle import hoi_forward_ref as O
+    m, enc, head = _build(117, 4096, cuda_device)
+    B = 4
+    props = S.make_region_props(B, ragged=True)
+    imgs = S.make_images(B, seed=77)
+    dino = S.make_dino_features(B, seed=78)
+    o_dets, o_int = O.hoi_forward(imgs, props, dino, enc, head, return_intermediates=True)
+    dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                           return_intermediates=True)
+    for b in range(B):
+        for k in ("pairing", "labels", "objects"):
+            assert torch.equal(dets[b][k].cpu(), o_dets[b][k]), k
+        err = (inter["logits"][b].cpu() - o_int["logits"][b]).abs().max().item()
+        assert err <= LOGIT_TOL, err
+        rel = ((dets[b]["scores"].cpu() - o_dets[b]["scores"]).abs() / o_dets[b]["scores"].abs().clamp_min(1e-30)).max().item()
+        assert rel <= SCORE_RTOL, rel
+    feat_err = (inter["tokens"].cpu() - o_int["tokens"]).abs().max().item()
+    print(f"N=4096: tokens max-abs {feat_err:.3e}")
+
+
+def test_scoring_stage_given_identical_features(cuda_device):
+    """a10 alone: feed the oracle's fp32 features, compare logits. bf16 operands (keys, features) with fp32
+    accumulation and an exact fp32 bias carrier: max-abs <= 3e-3."""
+    import ctypes as C
+    from hoigen_b200 import _cabi, synthetic as S
+    from oracle import hoi_forward_ref as O
+    m, enc, head = _build(117, 4096, cuda_device)
+    p, sw = m.pack_weights()
+    g = torch.Generator().manual_seed(31)
+    B, K = 3, 50
+    f = torch.randn(3, B * K, 512, generator=g)
+    f = f / f.norm(dim=-1, keepdim=True)
+    tokens = torch.randn(B * 197, 512, generator=g)
+    dino = S.make_dino_features(B, seed=32)
+    dev = cuda_device
+    pair_off = torch.tensor([0, K, 2 * K, 3 * K], dtype=torch.int32, device=dev)
+    ktot, Cn, N = B * K, 117, 4096
+    bufs = dict(pair=f.bfloat16().to(dev).contiguous(), phi=torch.empty(ktot, N, device=dev, dtype=torch.bfloat16),
+                phi_img=torch.empty(B, N, device=dev, dtype=torch.bfloat16), g=torch.empty(B, 512, device=dev, dtype=torch.bfloat16),
+                d=torch.empty(B, 2048, device=dev, dtype=torch.bfloat16), img=torch.empty(B, Cn, device=dev),
+                logits=torch.empty(ktot, Cn, device=dev))
+    sb = _cabi.ScoreBuffers()
+    sb.pair_feat_bf16, sb.phi, sb.phi_img = bufs["pair"].data_ptr(), bufs["phi"].data_ptr(), bufs["phi_img"].data_ptr()
+    sb.g_bf16, sb.d_bf16, sb.img_logits, sb.logits = bufs["g"].data_ptr(), bufs["d"].data_ptr(), bufs["img"].data_ptr(), bufs["logits"].data_ptr()
+    tk, dn = tokens.to(dev).contiguous(), dino.to(dev).contiguous()
+    _cabi.call("hoigen_score_pairs", C.byref(sw), C.byref(sb), tk.data_ptr(), dn.data_ptr(), pair_off.data_ptr(), B, ktot)
+    got = bufs["logits"].cpu()
+    worst = 0.0
+    for b in range(B):
+        gb = tokens[b * 197] / tokens[b * 197].norm()
+        sl = slice(b * K, (b + 1) * K)
+        ref = O.scoring_logits(f[0, sl], f[1, sl], f[2, sl], gb, dino[b], head.tensors, head.attrs)
+        worst = max(worst, (got[sl] - ref).abs().max().item())
+    print(f"scoring stage max-abs {worst:.3e}")
+    assert worst <= 3e-3, worst
+
+
+def test_emit_stage_exact_order_and_denormals(cuda_device):
+    """a11-a12 alone on fp32 logits: indices bit-exact, scores to 1e-6 relative; zero scores drop the pair, denormal
+    products survive (no flush-to-zero), an image with no human yields an empty detection."""
+    from hoigen_b200 import _cabi, synthetic as S
+    from oracle import hoi_forward_ref as O
+    head = S.make_head_state(117, 64)
+    from hoigen_b200.detector import UPT
+    m = UPT(117, 64, object_class_to_target_class=head.object_class_to_target_class).to(cuda_device)
+    p, _ = m.pack_weights()
+    props = S.make_region_props(4, 5, 6, ragged=True)
+    props[1]["scores"][0] = 0.0                       # pr == 0 for every pair of human 0 -> nothing emitted
+    props[2]["scores"][:] = 1e-8                      # (1e-8)^2.8 * (1e-8)^2.8 = 1.6e-45: fp32 denormal, must survive
+    props[3]["labels"][:] = 5                         # no human at all
+    dev = cuda_device
+    n_list = [q["boxes"].shape[0] for q in props]
+    nh_list = [int((q["labels"] == 0).sum()) for q in props]
+    k_list = [(nh * (n - 1) if nh > 0 and n > 1 else 0) for n, nh in zip(n_list, nh_list)]
+    box_off = np.concatenate([[0], np.cumsum(n_list)]).astype(np.int32)
+    pair_off = np.concatenate([[0], np.cumsum(k_list)]).astype(np.int32)
+    ktot = int(pair_off[-1])
+    logits = torch.randn(ktot, 117, generator=torch.Generator().manual_seed(4)) * 3
+    scores = torch.cat([q["scores"] for q in props]).to(dev)
+    labels = torch.cat([q["labels"] for q in props]).to(dev)
+    d_box, d_pair = torch.from_numpy(box_off).to(dev), torch.from_numpy(pair_off).to(dev)
+    cap = ktot * p["max_row_len"]
+    o_s = torch.empty(cap, device=dev); o_l = torch.empty(cap, device=dev, dtype=torch.int64)
+    o_o = torch.empty(cap, device=dev, dtype=torch.int64); o_p = torch.empty(2 * cap, device=dev, dtype=torch.int64)
+    img_off = torch.empty(5, device=dev, dtype=torch.int32)
+    wc = torch.empty(ktot, device=dev, dtype=torch.int32); wo = torch.empty(ktot + 1, device=dev, dtype=torch.int32)
+    wp = torch.empty(ktot, device=dev)
+    lg = logits.to(dev).contiguous()
+    _cabi.call("hoigen_emit_triplets", lg.data_ptr(), 117, scores.data_ptr(), labels.data_ptr(), d_box.data_ptr(), d_pair.data_ptr(),
+               4, ktot, p["table_bits"].data_ptr(), p["table_words"], 2.8, wc.data_ptr(), wo.data_ptr(), wp.data_ptr(), cap,
+               o_s.data_ptr(), o_l.data_ptr(), o_o.data_ptr(), o_p.data_ptr(), img_off.data_ptr())
+    offs = img_off.cpu().tolist()
+    for b, q in enumerate(props):
+        s, e = offs[b], offs[b + 1]
+        if k_list[b] == 0:
+            assert s == e
+            continue
+        xk, yk = O.pair_indices(n_list[b], nh_list[b])
+        pri = O.prior_scores(xk, yk, q["scores"], q["labels"], head.object_class_to_target_class, 117, 2.8)
+        ref = O.postprocess(logits[pair_off[b]:pair_off[b + 1]], pri, xk, yk, q["labels"], q["boxes"], (224, 224))
+        assert torch.equal(o_p[2 * s:2 * e].view(2, e - s).cpu(), ref["pairing"])
+        assert torch.equal(o_l[s:e].cpu(), ref["labels"]) and torch.equal(o_o[s:e].cpu(), ref["objects"])
+        got = o_s[s:e].cpu()
+        if b == 2:
+            assert e > s and (ref["scores"] != 0).any(), "denormal priors must not be flushed"
+        assert torch.allclose(got, ref["scores"], rtol=2e-6, atol=2e-45)
+
+
+def test_upt_forward_with_injected_detector(cuda_device):
+    """UPT.forward (U:1543) end to end with a stub DETR feeding overlapping raw detections through the real
+    prepare_region_proposals (NMS, thresholds, min/max instances) -> same result as forward_from_proposals."""
+    from hoigen_b200 import synthetic as S
+    from oracle import hoi_forward_ref as O
+    m, enc, head = _build(117, 256, cuda_device)
+    gold = np.load("tests/golden/proposals.npz")
+    results = [dict(scores=torch.from_numpy(gold[f"in_scores_{b}"]).to(cuda_device),
+                    labels=torch.from_numpy(gold[f"in_labels_{b}"]).to(cuda_device),
+                    boxes=torch.from_numpy(gold[f"in_boxes_{b}"]).to(cuda_device)) for b in range(4)]
+    rp = m.prepare_region_proposals(results)
+    for b in range(4):   # golden = the reference's own prepare_region_proposals output
+        assert np.array_equal(rp[b]["boxes"].cpu().numpy(), gold[f"boxes_{b}"])
+        assert np.array_equal(rp[b]["labels"].cpu().numpy(), gold[f"labels_{b}"])
+        assert np.array_equal(rp[b]["scores"].cpu().numpy(), gold[f"scores_{b}"])
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.query_embed = torch.nn.Embedding(1, 1)
+            self.class_embed = self.bbox_embed = self.input_proj = torch.nn.Identity()
+
+        def backbone(self, nested):
+            from hoigen_b200.detector import _NestedTensor
+            return [_NestedTensor(nested.tensors[:, :1, :1, :1], None)], [None]
+
+        def transformer(self, src, mask, query, pos):
+            return torch.zeros(1, src.shape[0], 1, 4, device=src.device), None
+
+    class PP(torch.nn.Module):
+        def forward(self, outputs, sizes):
+            return results[:3]      # image 3 has no human: covered separately
+
+    m.detector, m.postprocessor = Stub().to(cuda_device), PP()
+    imgs = S.make_images(3, seed=5).to(cuda_device)
+    dino = S.make_dino_features(3).to(cuda_device)
+    m.dino_model = lambda x: dino * 3.0         # un-normalised on purpose: forward re-normalises (U:1617-1618)
+    dets = m([(torch.zeros(3, 40, 50, device=cuda_device), imgs[b]) for b in range(3)])
+    props = [{k: v.cpu() for k, v in r.items() if torch.is_tensor(v)} for r in rp[:3]]
+    o_dets = O.hoi_forward(imgs.cpu(), props, dino.cpu(), enc, head)
+    for b in range(3):
+        for k in ("pairing", "labels", "objects"):
+            assert torch.equal(dets[b][k].cpu(), o_dets[b][k]), (b, k)
+        assert dets[b]["size"].tolist() == [224, 224]
+    # no image with a valid pair -> None (U:1660-1662)
+    out = m.forward_from_proposals(imgs[:1], [dict(boxes=rp[3]["boxes"], scores=rp[3]["scores"], labels=rp[3]["labels"])], dino[:1])
+    assert out is None
