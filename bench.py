@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""HOI-forward throughput benchmark (BASELINE.json metric: images/sec of the per-image HOI scoring forward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path (region proposals -> detections: prior tokens, ViT-B/16+InsAdapter encoder,
+RoIAlign/pair assembly, cache+text logits, prior scores + triplet emission) over ONE batch of synthetic images:
+configs[1] of BASELINE.json — HICO-DET 117 verbs, batch 64, 8 human + 8 object boxes (120 pairs/image under the
+reference's pairing rule), 4096x512 caches, bf16 tensor-core path.
+
+  value     images/s with inputs resident in HBM (CUDA events; max over ranks; whole job)
+  e2e       same metric through UPT.forward_from_proposals with HOST (pinned) inputs: H2D of the step's images /
+            boxes and D2H of every detection tensor inside the timed region (wall clock between synchronisations)
+  roofline  the dominant kernel (tcgen05 GEMM): algorithmic FLOPs of its launches / CUDA-event time, vs the measured
+            bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (reference algorithm, torch-CPU fp32, all host threads) on a bounded sample
+
+`--impl reference` times the reference's CPU implementation of the path (oracle port; the reference is Python and
+cannot travel to the GPU box) with all host threads on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "hoi_forward_images_per_sec"
+UNIT = "images/s"
+ENC_GFLOP_PER_IMG = 35.875
+BOXES_H, BOXES_O = 8, 8
+
+
+def workload_config(args, world):
+    return {
+        "workload": "HICO-DET HOI scoring forward (BASELINE configs[1]): ViT-B/16+InsAdapter 224^2, 117 verbs, "
+                    f"{BOXES_H}h+{BOXES_O}o boxes = 120 pairs/img, {args.cache_rows}x512 caches (H,O,U,global,DINO) + text",
+        "batch_per_gpu": args.batch, "global_batch": args.batch * world, "pairs_per_image": BOXES_H * (BOXES_H + BOXES_O - 1),
+        "cache_rows": args.cache_rows, "num_classes": 117, "parallelism": f"image-sharded dp{world}",
+        "l2": f"inputs rotate over {args.rotate} distinct batches ({args.rotate * args.batch * 3 * 224 * 224 * 4 / 1e6:.0f} MB "
+              "> 126 MB L2); weights + activations per step >> L2",
+        "dino_features": "supplied as input (SURVEY.md 8 row a8: stock ResNet-50 is outside the path)",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_port_images_per_sec(batch: int, passes: int, cache_rows: int, warmup: int = 1):
+    from hoigen_b200 import synthetic as S
+    from oracle import hoi_forward_ref as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    enc = S.make_encoder_state(0)
+    head = S.make_head_state(117, cache_rows)
+    imgs = S.make_images(batch, seed=1)
+    props = S.make_region_props(batch, BOXES_H, BOXES_O)
+    dino = S.make_dino_features(batch)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + passes):
+            t0 = time.perf_counter()
+            O.hoi_forward(imgs, props, dino, enc, head, roi_impl="torchvision")
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return batch / dt, dt * 1e3, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    batch = 8
+    value, ms, cores = cpu_port_images_per_sec(batch, max(args.steps, 1), args.cache_rows, warmup=min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (seeded random-init weights, images, boxes)",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"each step = one batch of {batch} images of the same workload through the oracle port "
+                                   "(reference algorithm, torch-CPU fp32 + torchvision roi_align, all host threads)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from hoigen_b200 import _cabi, synthetic as S
+    from hoigen_b200.detector import UPT
+    from hoigen_b200.gather import gather_detections
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.init(dev)
+    B = args.batch
+    model = UPT.from_state(S.make_encoder_state(0), S.make_head_state(117, args.cache_rows)).to(dev)
+    model.pack_weights()
+    model.clip_head.image_encoder.pack_weights()
+
+    # ---- rotating input sets: host (pinned) + device resident copies ------------------------------------------------
+    R = args.rotate
+    host_imgs, host_props, host_dino = [], [], []
+    for r in range(R):
+        host_imgs.append(S.make_images(B, seed=1000 * rank + r + 1).pin_memory())
+        props = [S.make_boxes(1000 * rank + 64 * r + b, BOXES_H, BOXES_O) for b in range(B)]
+        host_props.append([{k: v.pin_memory() for k, v in p.items()} for p in props])
+        host_dino.append(S.make_dino_features(B, seed=7 + r).pin_memory())
+    dev_imgs = [t.to(dev) for t in host_imgs]
+    dev_props = [[dict({k: v.to(dev) for k, v in p.items()}, n_human=BOXES_H) for p in ps] for ps in host_props]
+    dev_dino = [t.to(dev) for t in host_dino]
+
+    def step_resident(i):
+        r = i % R
+        dets = model.forward_from_proposals(dev_imgs[r], dev_props[r], dev_dino[r])
+        if world > 1:
+            dets = gather_detections(dets)
+        return dets
+
+    def step_host(i):
+        r = i % R
+        imgs = host_imgs[r].to(dev, non_blocking=True)
+        props = [dict({k: v.to(dev, non_blocking=True) for k, v in p.items()}, n_human=BOXES_H) for p in host_props[r]]
+        dino = host_dino[r].to(dev, non_blocking=True)
+        dets = model.forward_from_proposals(imgs, props, dino)
+        out = [{k: d[k].to("cpu", non_blocking=True) for k in ("pairing", "scores", "labels", "objects")} for d in dets]
+        torch.cuda.synchronize()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing -----------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    _cabi.profile(False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        dets = step_resident(args.warmup + i)
+    e1.record()
+    barrier()
+    launches = _cabi.launch_count()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    value = world * B / (ms_step * 1e-3)
+    triplets = sum(int(d["scores"].numel()) for d in dets[:B])
+
+    # ---- end-to-end timing with host buffers -----------------------------------------------------------------------------
+    for i in range(max(3, args.warmup // 2)):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = step_host(i)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    h2d = host_imgs[0].numel() * 4 + sum(sum(v.numel() * v.element_size() for v in p.values()) for p in host_props[0]) \
+        + host_dino[0].numel() * 4
+    d2h = sum(sum(v.numel() * v.element_size() for v in d.values()) for d in out)
+
+    # ---- per-kernel event profile of one step (separate from the timed regions) ---------------------------------------------
+    _cabi.profile(True)
+    for i in range(2):
+        model.forward_from_proposals(dev_imgs[i % R], dev_props[i % R], dev_dino[i % R])
+    recs = _cabi.profile_read()
+    _cabi.profile(False)
+    agg = {}
+    for tag, ms, fl, by in recs:
+        a = agg.setdefault(tag, [0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += ms; a[2] += fl; a[3] += by
+    nprof = 2
+    gemm_ms = sum(a[1] for t, a in agg.items() if t.startswith("gemm_"))
+    gemm_fl = sum(a[2] for t, a in agg.items() if t.startswith("gemm_"))
+    gemm_n = sum(a[0] for t, a in agg.items() if t.startswith("gemm_"))
+    total_ms = sum(a[1] for a in agg.values())
+    peak_tf, peak_hbm, peak_src = peaks()
+    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tr = ROOT / "profiles" / "ncu_gemm_traffic.json"
+    if tr.exists():
+        traffic = json.loads(tr.read_text()).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "hoigen::gemm_bf16_kernel<BN> (tcgen05/TMA, all GEMM shapes of the step)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                "peak_source": peak_src, "traffic": traffic, "launches_per_step": gemm_n / nprof,
+                "avg_launch_us": gemm_ms / gemm_n * 1e3 if gemm_n else None,
+                "algorithmic_gflop_per_launch": gemm_fl / gemm_n / 1e9 if gemm_n else None,
+                "share_of_step": gemm_ms / total_ms if total_ms else None}
+    breakdown = {t: {"launches_per_step": a[0] / nprof, "ms_per_step": a[1] / nprof,
+                     "tflops": (a[2] / (a[1] * 1e-3) / 1e12) if a[1] > 0 and a[2] > 0 else None,
+                     "gbs": (a[3] / (a[1] * 1e-3) / 1e9) if a[1] > 0 and a[3] > 0 else None} for t, a in sorted(agg.items())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms, cores = cpu_port_images_per_sec(8, 2, args.cache_rows)
+        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "2 timed passes (1 warm-up) of one batch of 8 images of the same workload through the oracle port "
+                              "(torch-CPU fp32 + torchvision roi_align, all host threads)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (seeded random-init ViT-B/16+adapter weights, randn images, NMS-safe grid boxes)",
+        "config": workload_config(args, world),
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roofline,
+        "cpu_baseline": cpu_base,
+        "encoder_tflops_effective": ENC_GFLOP_PER_IMG * B / (ms_step * 1e-3) / 1e3,
+        "triplets_per_step": triplets,
+        "kernel_breakdown": breakdown,
+    }
+    print(json.dumps(line))
+    out_dir = ROOT / "gpurun_out"
+    if out_dir.exists():
+        (out_dir / f"bench_detail_n{world}.json").write_text(json.dumps(line, indent=1))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--cache-rows", type=int, default=4096)
+    ap.add_argument("--rotate", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

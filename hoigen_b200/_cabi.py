@@ -60,6 +60,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = sig
+    lib.hoigen_launch_count.restype = C.c_longlong
+    lib.hoigen_profile_enable.argtypes = [C.c_int]
+    lib.hoigen_profile_read.restype = C.c_longlong
+    lib.hoigen_profile_read.argtypes = [C.c_char_p, C.c_longlong]
     _lib = lib
     return lib
 
@@ -158,7 +162,33 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_emit_triplets": [_P, _I, _P, _P, _P, _P, _I, _I, _P, _I, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
 }
 
-EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", *_SIGNATURES.keys()]
+EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", "hoigen_launch_count",
+                    "hoigen_profile_enable", "hoigen_profile_reset", "hoigen_profile_read", *_SIGNATURES.keys()]
+
+
+def launch_count() -> int:
+    """Kernels launched by this library since the last profile_reset()."""
+    return int(load().hoigen_launch_count())
+
+
+def profile(enable: bool) -> None:
+    lib = load()
+    lib.hoigen_profile_reset()
+    lib.hoigen_profile_enable(1 if enable else 0)
+
+
+def profile_read() -> list:
+    """[(tag, ms, flops, bytes)] per recorded launch (synchronises the device)."""
+    lib = load()
+    buf = C.create_string_buffer(1 << 20)
+    n = lib.hoigen_profile_read(buf, len(buf))
+    if n < 0:
+        raise HoigenError("hoigen_profile_read failed")
+    out = []
+    for line in buf.raw[:n].decode().splitlines():
+        tag, ms, fl, by = line.split()
+        out.append((tag, float(ms), float(fl), float(by)))
+    return out
 
 
 def call(name: str, *args) -> None:

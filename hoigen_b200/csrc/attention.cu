@@ -203,6 +203,8 @@ int hoigen_attention(const void* qkv, void* out, int32_t batch, hoigen_stream_t 
   const CUtensorMap* tkv = get_tmap_3d_bf16(qkv, 3 * ATT_WIDTH, ATT_TOKENS, uint64_t(batch), row_bytes,
                                             row_bytes * ATT_TOKENS, 64, ATT_KEYS, 1);
   if (!tkv) return HOIGEN_ERR_CUDA;
+  KernelScope ks("attention", reinterpret_cast<cudaStream_t>(stream), 4.0 * ATT_TOKENS * ATT_TOKENS * ATT_DH * ATT_HEADS * batch,
+                 double(batch) * ATT_TOKENS * ATT_WIDTH * 2 * 4);
   attention_kernel<<<batch * ATT_HEADS * 2, ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
       *tq, *tkv, reinterpret_cast<__nv_bfloat16*>(out), batch);
   HOIGEN_CHECK_LAUNCH();

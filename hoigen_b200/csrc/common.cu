@@ -117,9 +117,68 @@ const CUtensorMap* get_tmap_3d_bf16(const void* ptr, uint64_t dim0, uint64_t dim
   return get_tmap(3, ptr, dims, strides, box);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// launch counter + optional per-launch CUDA-event profiler
+// ---------------------------------------------------------------------------------------------------
+struct ProfRec {
+  const char* tag;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static const int kMaxProf = 8192;
+static ProfRec g_prof[kMaxProf];
+static int g_prof_n = 0;
+static int g_prof_events = 0;  // events created so far (reused across resets)
+static bool g_prof_on = false;
+static long long g_launches = 0;
+
+KernelScope::KernelScope(const char* tag, cudaStream_t stream, double flops, double bytes) : slot_(-1), stream_(stream) {
+  ++g_launches;
+  if (!g_prof_on || g_prof_n >= kMaxProf) return;
+  ProfRec& r = g_prof[g_prof_n];
+  if (g_prof_n >= g_prof_events) {
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    g_prof_events = g_prof_n + 1;
+  }
+  r.tag = tag; r.flops = flops; r.bytes = bytes;
+  cudaEventRecord(r.e0, stream);
+  slot_ = g_prof_n++;
+}
+KernelScope::~KernelScope() {
+  if (slot_ >= 0) cudaEventRecord(g_prof[slot_].e1, stream_);
+}
+
 }  // namespace hoigen
 
 extern "C" {
+
+long long hoigen_launch_count(void) { return hoigen::g_launches; }
+
+int hoigen_profile_enable(int on) {
+  hoigen::g_prof_on = on != 0;
+  return HOIGEN_OK;
+}
+
+int hoigen_profile_reset(void) {
+  hoigen::g_prof_n = 0;
+  hoigen::g_launches = 0;
+  return HOIGEN_OK;
+}
+
+// Writes one line per recorded launch: "tag ms flops bytes\n". Synchronises the device. Returns bytes written.
+long long hoigen_profile_read(char* buf, long long cap) {
+  using namespace hoigen;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  long long off = 0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof[i].e0, g_prof[i].e1) != cudaSuccess) ms = -1.f;
+    int n = snprintf(buf + off, size_t(cap - off), "%s %.6f %.0f %.0f\n", g_prof[i].tag, ms, g_prof[i].flops, g_prof[i].bytes);
+    if (n < 0 || off + n >= cap) break;
+    off += n;
+  }
+  return off;
+}
 
 int hoigen_abi_version(void) { return HOIGEN_ABI_VERSION; }
 

@@ -21,6 +21,15 @@ const CUtensorMap* get_tmap_3d_bf16(const void* ptr, uint64_t dim0, uint64_t dim
                                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
                                     uint32_t box1, uint32_t box2);
 
+// Counts every kernel launch of this library and, when profiling is enabled (hoigen_profile_enable), brackets
+// the launch with CUDA events on the launching stream. flops / bytes are the ALGORITHMIC work of the launch.
+struct KernelScope {
+  KernelScope(const char* tag, cudaStream_t stream, double flops = 0.0, double bytes = 0.0);
+  ~KernelScope();
+  int slot_;
+  cudaStream_t stream_;
+};
+
 #define HOIGEN_CHECK_ARG(cond, ...)        \
   do {                                     \
     if (!(cond)) {                         \

@@ -377,6 +377,7 @@ int hoigen_patchify_bf16(const float* images, void* patches, int32_t batch, hoig
   HOIGEN_CHECK_ARG(images && patches && batch > 0, "patchify: bad arguments");
   const long total = long(batch) * 3 * 224 * 28;
   const int blocks = int(min(long(num_sms()) * 8, (total + 255) / 256));
+  KernelScope ks("patchify", reinterpret_cast<cudaStream_t>(stream), 0, double(batch) * 3 * 224 * 224 * 6);
   patchify_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       images, reinterpret_cast<__nv_bfloat16*>(patches), batch);
   HOIGEN_CHECK_LAUNCH();
@@ -388,6 +389,7 @@ int hoigen_embed_lnpre(const float* patch_emb, const float* cls, const float* po
   using namespace hoigen;
   HOIGEN_CHECK_ARG(patch_emb && cls && pos && gamma && beta && batch > 0, "embed_lnpre: bad arguments");
   const int rows = batch * TOKENS;
+  KernelScope ks("embed_lnpre", reinterpret_cast<cudaStream_t>(stream), 0, double(rows) * WIDTH * (4 + (x_f32 ? 4 : 0) + (x_bf16 ? 2 : 0)));
   layernorm768_kernel<true><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       patch_emb, cls, pos, gamma, beta, x_f32, reinterpret_cast<__nv_bfloat16*>(x_bf16), rows);
   HOIGEN_CHECK_LAUNCH();
@@ -398,6 +400,7 @@ int hoigen_layernorm768(const float* x, const float* gamma, const float* beta, f
                         int32_t rows, hoigen_stream_t stream) {
   using namespace hoigen;
   HOIGEN_CHECK_ARG(x && gamma && beta && rows > 0 && (out_f32 || out_bf16), "layernorm768: bad arguments");
+  KernelScope ks("layernorm768", reinterpret_cast<cudaStream_t>(stream), 0, double(rows) * WIDTH * (4 + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)));
   layernorm768_kernel<false><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, nullptr, nullptr, gamma, beta, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows);
   HOIGEN_CHECK_LAUNCH();
@@ -409,6 +412,7 @@ int hoigen_adapter_kv(const float* prior, const float* in_proj_w, const float* i
   using namespace hoigen;
   HOIGEN_CHECK_ARG(prior && in_proj_w && in_proj_b && kv && tokens > 0 && layers > 0, "adapter_kv: bad arguments");
   dim3 grid((tokens + 15) / 16, layers);
+  KernelScope ks("adapter_kv", reinterpret_cast<cudaStream_t>(stream), 2.0 * tokens * 128 * 64 * layers, double(tokens) * (64 + 128.0 * layers) * 4);
   adapter_kv_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(prior, in_proj_w, in_proj_b, kv, tokens);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
@@ -432,6 +436,8 @@ int hoigen_adapter_mid(const float* d, const float* kv_layer, const uint8_t* mas
   int split = 1;
   while (batch * split < 2 * num_sms() && split < 8) split *= 2;
   dim3 grid(batch, split);
+  KernelScope ks("adapter_mid", reinterpret_cast<cudaStream_t>(stream), 2.0 * batch * TOKENS * (64 * 64 * 2 + 2 * 64 * 128 + 2 * 64 * n_max),
+                 double(batch) * TOKENS * 64 * (4 + 2));
   adapter_mid_kernel<<<grid, AM_THREADS, AM_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
       d, kv_layer, mask, mw, reinterpret_cast<__nv_bfloat16*>(out_bf16), n_max, split);
   HOIGEN_CHECK_LAUNCH();

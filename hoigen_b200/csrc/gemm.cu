@@ -10,6 +10,9 @@
 // Replaces the cuBLAS SGEMMs the reference dispatches from CLIP_models_adapter_prior2.py:443-445 (in/out
 // proj), :428-432 (c_fc/c_proj), :184/:201 (adapter down/up), :491 (conv1 as GEMM), :505 (@ proj) and
 // upt_tip_cache_model_free_finetune_distill3.py:1156-1163 (cache / text GEMMs).
+#include <map>
+#include <string>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -336,6 +339,14 @@ static int choose_block_n(int M, int N) {
   return best;
 }
 
+// interned "gemm_n<N>_k<K>" tags for the launch profiler
+static const char* gemm_tag(int N, int K) {
+  static std::map<std::pair<int, int>, std::string> tags;
+  auto it = tags.find({N, K});
+  if (it == tags.end()) it = tags.emplace(std::make_pair(N, K), "gemm_n" + std::to_string(N) + "_k" + std::to_string(K)).first;
+  return it->second.c_str();
+}
+
 template <int BN>
 static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -351,6 +362,8 @@ static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
   if (!tb) return HOIGEN_ERR_CUDA;
   const int num_tiles = ((p->M + BM - 1) / BM) * ((p->N + BN - 1) / BN);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  KernelScope ks(gemm_tag(p->N, p->K), stream, 2.0 * p->M * p->N * p->K,
+                 2.0 * (double(p->M) * p->K + double(p->N) * p->K) + double(p->M) * p->N * ((p->out_f32 ? 4 : 0) + (p->out_bf16 ? 2 : 0) + (p->residual ? 4 : 0)));
   gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, to_args(p));
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
@@ -380,6 +393,7 @@ int hoigen_debug_gemm_simt(const hoigen_gemm_params* p, hoigen_stream_t stream) 
   int rc = validate(p);
   if (rc != HOIGEN_OK) return rc;
   dim3 grid((p->N + 127) / 128, p->M);
+  KernelScope ks("gemm_simt_debug", reinterpret_cast<cudaStream_t>(stream), 2.0 * p->M * p->N * p->K, 0);
   gemm_simt_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(p->a), reinterpret_cast<const __nv_bfloat16*>(p->w), p->lda, p->ldw,
       to_args(p));

@@ -405,6 +405,8 @@ int hoigen_prior_tokens(const float* boxes, const float* scores, const int64_t* 
     HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(prior_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
+  KernelScope ks("prior_tokens", reinterpret_cast<cudaStream_t>(stream), 2.0 * batch * n_max * (517 * 128 + 128 * 128 + 128 * 64),
+                 double(batch) * n_max * (517 + 64) * 4);
   prior_tokens_kernel<<<batch, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       boxes, scores, labels, box_off, obj_emb, w0t, b0, w1t, b1, w2t, b2, img_w, img_h, n_max, prior, mask);
   HOIGEN_CHECK_LAUNCH();
@@ -425,10 +427,16 @@ int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int3
     HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(roi_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROI_SMEM_BYTES));
     attr_set = true;
   }
-  roi_features_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES, s>>>(
-      tokens, boxes, box_off, n_human, pair_off, spatial_scale, single_feat, union_feat);
+  {
+    // algorithmic bytes: token map read once + boxes + one fp32 feature row per single / union box;
+    // the number of single boxes is not known on the host here, it is bounded by 32 per image
+    KernelScope ks("roi_features", s, 0, double(batch) * 196 * FEAT * 4 + double(ktot) * (16 + FEAT * 4));
+    roi_features_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES, s>>>(
+        tokens, boxes, box_off, n_human, pair_off, spatial_scale, single_feat, union_feat);
+  }
   HOIGEN_CHECK_LAUNCH();
   if (ktot > 0) {
+    KernelScope ks("pair_assemble", s, 0, double(ktot) * FEAT * (3 * 4 + 3 * 2 + (pair_feat_f32 ? 12 : 0)));
     pair_assemble_kernel<<<(ktot * 32 + 255) / 256, 256, 0, s>>>(single_feat, union_feat, box_off, pair_off, batch, ktot,
                                                                  reinterpret_cast<__nv_bfloat16*>(pair_feat_bf16), pair_feat_f32);
     HOIGEN_CHECK_LAUNCH();
@@ -440,6 +448,7 @@ int hoigen_rows_to_bf16(const float* in, int64_t ld_in, int32_t rows, int32_t co
                         hoigen_stream_t stream) {
   using namespace hoigen;
   HOIGEN_CHECK_ARG(in && out && rows > 0 && cols > 0, "rows_to_bf16: bad arguments");
+  KernelScope ks("rows_to_bf16", reinterpret_cast<cudaStream_t>(stream), 0, double(rows) * cols * 6);
   rows_to_bf16_kernel<<<(rows * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       in, ld_in, rows, cols, normalize, reinterpret_cast<__nv_bfloat16*>(out));
   HOIGEN_CHECK_LAUNCH();
@@ -453,6 +462,7 @@ int hoigen_broadcast_image_logits(const float* img_logits, const int32_t* pair_o
   if (ktot == 0) return HOIGEN_OK;
   const long total = long(ktot) * num_classes;
   const int blocks = int(min(long(num_sms()) * 8, (total + 255) / 256));
+  KernelScope ks("broadcast_image_logits", reinterpret_cast<cudaStream_t>(stream), 0, double(total) * 4 + double(batch) * num_classes * 4);
   broadcast_rows_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img_logits, pair_off, batch, ktot,
                                                                                       num_classes, logits);
   HOIGEN_CHECK_LAUNCH();
@@ -472,13 +482,20 @@ int hoigen_emit_triplets(const float* logits, int32_t num_classes, const float* 
   HOIGEN_CHECK_ARG(batch > 0 && ktot >= 0 && num_classes > 0 && table_words * 32 >= num_classes, "emit_triplets: bad sizes");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (ktot > 0) {
+    KernelScope ks("pair_count", s, 0, double(ktot) * 24);
     pair_count_kernel<<<(ktot + 255) / 256, 256, 0, s>>>(scores, labels, box_off, pair_off, batch, ktot, table_bits,
                                                          table_words, hyper_lambda, work_counts, work_pr);
     HOIGEN_CHECK_LAUNCH();
   }
-  scan_kernel<<<1, 1024, 0, s>>>(work_counts, ktot, work_offsets, pair_off, batch, img_off);
+  {
+    KernelScope ks("emit_scan", s, 0, double(ktot) * 8);
+    scan_kernel<<<1, 1024, 0, s>>>(work_counts, ktot, work_offsets, pair_off, batch, img_off);
+  }
   HOIGEN_CHECK_LAUNCH();
   if (ktot > 0) {
+    // reads the logits row of every pair; writes 36 bytes per emitted triplet (count unknown on the host: the
+    // per-class average of the object->target table bounds it; bench.py recomputes the exact figure from img_off)
+    KernelScope ks("emit_triplets", s, 0, double(ktot) * num_classes * 4);
     emit_kernel<<<(ktot * 32 + 255) / 256, 256, 0, s>>>(logits, num_classes, work_pr, work_offsets, labels, box_off, pair_off,
                                                         img_off, batch, ktot, table_bits, table_words, long(capacity),
                                                         out_scores, out_labels, out_objects, out_pairing);

@@ -45,6 +45,13 @@ HOIGEN_API const char* hoigen_last_error(void);
 /* Resolve driver entry points, check the device is sm_100, raise shared-memory limits. */
 HOIGEN_API int hoigen_init(int device);
 
+/* Launch accounting + optional per-launch CUDA-event timing (used by bench.py for gpu_launches / roofline).
+ * hoigen_profile_read writes one line per recorded launch, "tag ms flops bytes", and returns the byte count. */
+HOIGEN_API long long hoigen_launch_count(void);
+HOIGEN_API int hoigen_profile_enable(int on);
+HOIGEN_API int hoigen_profile_reset(void);
+HOIGEN_API long long hoigen_profile_read(char* buf, long long cap);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM: out = epilogue(A[M,K] @ W[N,K]^T), bf16 operands, fp32 accumulate (TMA + tcgen05 + TMEM).
  * Replaces every nn.Linear / F.linear / `@` on the path: conv1-as-GEMM C:491, in_proj/out_proj

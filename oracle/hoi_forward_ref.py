@@ -192,8 +192,19 @@ def pair_indices(n: int, n_h: int) -> Tuple[np.ndarray, np.ndarray]:
     return np.asarray(xs, dtype=np.int64), np.asarray(ys, dtype=np.int64)
 
 
-def roi_pair_features(tokens_b: torch.Tensor, props: dict, human_idx: int, image_size: int = 224):
+def roi_align_mean_torchvision(feat_hw_c: np.ndarray, boxes: np.ndarray, spatial_scale: float) -> np.ndarray:
+    """The reference's own call (U:1028-1037) through the installed torchvision C++ op — used for the CPU-baseline
+    timing only (the restatement above is the checker; tests pin the two against each other)."""
+    import torchvision
+    f = torch.from_numpy(np.ascontiguousarray(feat_hw_c)).permute(2, 0, 1)[None]
+    out = torchvision.ops.roi_align(f, [torch.from_numpy(np.ascontiguousarray(boxes))], output_size=(7, 7),
+                                    spatial_scale=spatial_scale, aligned=True)
+    return out.flatten(2).mean(-1).numpy()
+
+
+def roi_pair_features(tokens_b: torch.Tensor, props: dict, human_idx: int, image_size: int = 224, roi_impl: str = "restated"):
     """U:981-1057 for one image. tokens_b (197,512). Returns x_keep, y_keep, f_H, f_O, f_U (K,512) (L2-normalised)."""
+    roi = roi_align_mean if roi_impl == "restated" else roi_align_mean_torchvision
     boxes = props["boxes"].numpy().astype(np.float32)
     labels = props["labels"].numpy()
     n = boxes.shape[0]
@@ -206,8 +217,8 @@ def roi_pair_features(tokens_b: torch.Tensor, props: dict, human_idx: int, image
     union = np.concatenate([np.minimum(sub[:, :2], obj[:, :2]), np.maximum(sub[:, 2:], obj[:, 2:])], axis=1)  # U:1021-1023
     feat = tokens_b[1:].reshape(GRID, GRID, -1).numpy()
     scale = 1.0 / (image_size / GRID)                                          # U:1027
-    uf = torch.from_numpy(roi_align_mean(feat, union, scale))
-    sf = torch.from_numpy(roi_align_mean(feat, boxes, scale))
+    uf = torch.from_numpy(roi(feat, union, scale))
+    sf = torch.from_numpy(roi(feat, boxes, scale))
     hf, of = sf[x_keep], sf[y_keep]                                            # U:1044-1045
     norm = lambda t: t / t.norm(dim=-1, keepdim=True)                          # U:1048-1050
     return x_keep, y_keep, norm(hf), norm(of), norm(uf)
@@ -274,7 +285,7 @@ def postprocess(logits: torch.Tensor, prior: torch.Tensor, x_keep, y_keep, label
 # --------------------------------------------------------------------------------------------------------------
 def hoi_forward(images: torch.Tensor, region_props: Sequence[dict], dino_feats: torch.Tensor,
                 enc_sd: Dict[str, torch.Tensor], head, *, return_intermediates: bool = False,
-                affinity: str = "linear"):
+                affinity: str = "linear", roi_impl: str = "restated"):
     """images (B,3,224,224); region_props as from prepare_region_proposals; dino_feats (B,2048) L2-normalised.
     head: hoigen_b200.synthetic.HeadState-like (tensors, attrs, object_class_to_target_class, num_classes, hyper)."""
     T, A = head.tensors, head.attrs
@@ -284,7 +295,7 @@ def hoi_forward(images: torch.Tensor, region_props: Sequence[dict], dino_feats: 
     g = feat_global / feat_global.norm(dim=-1, keepdim=True)                   # U:960
     dets, inter = [], dict(prior=prior, mask=mask, feat_global=feat_global, tokens=tokens, logits=[], feats=[], priors=[])
     for b, props in enumerate(region_props):
-        rp = roi_pair_features(tokens[b], props, head.hyper["human_idx"], hw[0])
+        rp = roi_pair_features(tokens[b], props, head.hyper["human_idx"], hw[0], roi_impl)
         if rp is None:  # U:998-1004: empty detection for this image
             dets.append(dict(boxes=props["boxes"], pairing=torch.zeros(2, 0, dtype=torch.int64), scores=torch.zeros(0),
                              labels=torch.zeros(0, dtype=torch.int64), objects=torch.zeros(0, dtype=torch.int64),

@@ -1,0 +1,70 @@
+"""CPU: the N>1 path (image sharding + variable-length detection gather) with world_size=2 over gloo."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hoigen_b200.gather import gather_detections, pack_detections, shard_range, unpack_detections
+
+
+def _fake_dets(rank, n_img):
+    g = torch.Generator().manual_seed(100 + rank)
+    out = []
+    for b in range(n_img):
+        m = int(torch.randint(0, 50, (1,), generator=g)) if (rank + b) % 3 else 0     # some images emit nothing
+        n = int(torch.randint(2, 9, (1,), generator=g))
+        out.append(dict(boxes=torch.rand(n, 4, generator=g), pairing=torch.randint(0, n, (2, m), generator=g),
+                        scores=torch.rand(m, generator=g), labels=torch.randint(0, 117, (m,), generator=g),
+                        objects=torch.randint(0, 80, (m,), generator=g), size=torch.tensor([224, 224])))
+    return out
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(7, rank, world)
+        mine = _fake_dets(rank, hi - lo)
+        allv = gather_detections(mine)
+        expect = _fake_dets(0, shard_range(7, 0, world)[1]) + _fake_dets(1, 7 - shard_range(7, 0, world)[1])
+        ok = len(allv) == 7
+        for a, e in zip(allv, expect):
+            for k in ("boxes", "pairing", "scores", "labels", "objects"):
+                ok = ok and torch.equal(a[k], e[k]) and a[k].dtype == e[k].dtype
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_partitions():
+    for total in (0, 1, 7, 512, 4097):
+        for world in (1, 2, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_pack_unpack_roundtrip_with_empty_and_none():
+    dets = _fake_dets(0, 5) + [None]
+    c, f, i = pack_detections(dets)
+    back = unpack_detections(c, f, i)
+    assert len(back) == 6 and back[5]["scores"].numel() == 0 and back[5]["pairing"].shape == (2, 0)
+    for a, e in zip(back[:5], dets[:5]):
+        for k in ("boxes", "pairing", "scores", "labels", "objects"):
+            assert torch.equal(a[k], e[k])
+
+
+def test_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
