@@ -241,7 +241,7 @@ def run_b200(args, rank, world, local_rank):
     recs = _cabi.profile_read()
     _cabi.profile(False)
     agg = {}
-    for tag, ms, fl, by in recs:
+    for tag, ms, fl, by, _t0 in recs:
         a = agg.setdefault(tag, [0, 0.0, 0.0, 0.0])
         a[0] += 1; a[1] += ms; a[2] += fl; a[3] += by
     nprof = 2
@@ -294,6 +294,11 @@ def run_b200(args, rank, world, local_rank):
     out_dir = ROOT / "gpurun_out"
     if out_dir.exists():
         (out_dir / f"bench_detail_n{world}.json").write_text(json.dumps(line, indent=1))
+        with open(out_dir / f"bench_timeline_n{world}.txt", "w") as f:   # launch timeline of the profiled steps (gaps = host stalls)
+            prev_end = 0.0
+            for tag, ms, fl, by, t0 in recs:
+                f.write(f"{t0:10.4f} {ms:9.4f} gap={t0 - prev_end:8.4f} {tag}\n")
+                prev_end = t0 + ms
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -99,16 +99,14 @@ def ptr(t: torch.Tensor | None) -> C.c_void_p:
 
 class AdapterMidWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "linear1_w", "linear1_b", "linear2_w", "linear2_b",
-        "norm2_w", "norm2_b", "norm3_w", "norm3_b")]
+        "packed", "in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w", "norm2_b", "norm3_w", "norm3_b")]
 
 
 ENCODER_WEIGHT_FIELDS = (
     "conv_w", "class_embedding", "positional_embedding", "ln_pre_w", "ln_pre_b", "ln_post_w", "ln_post_b", "proj_t",
     "ln1_w", "ln1_b", "ln2_w", "ln2_b", "qkv_w", "qkv_b", "out_w", "out_b", "fc_w", "fc_b", "proj_w", "proj_b",
-    "ad_down_w", "ad_down_b", "ad_up_w", "ad_up_b", "ad_scale", "ad_in_proj_w", "ad_in_proj_b", "ad_out_proj_w",
-    "ad_out_proj_b", "ad_linear1_w", "ad_linear1_b", "ad_linear2_w", "ad_linear2_b", "ad_norm2_w", "ad_norm2_b",
-    "ad_norm3_w", "ad_norm3_b")
+    "ad_down_w", "ad_down_b", "ad_up_w", "ad_up_b", "ad_scale", "ad_in_proj_w", "ad_in_proj_b", "ad_mid_packed",
+    "ad_out_proj_b", "ad_linear1_b", "ad_linear2_b", "ad_norm2_w", "ad_norm2_b", "ad_norm3_w", "ad_norm3_b")
 
 
 class EncoderWeights(C.Structure):
@@ -178,7 +176,7 @@ def profile(enable: bool) -> None:
 
 
 def profile_read() -> list:
-    """[(tag, ms, flops, bytes)] per recorded launch (synchronises the device)."""
+    """[(tag, ms, flops, bytes, start_ms)] per recorded launch (synchronises the device)."""
     lib = load()
     buf = C.create_string_buffer(1 << 20)
     n = lib.hoigen_profile_read(buf, len(buf))
@@ -186,8 +184,8 @@ def profile_read() -> list:
         raise HoigenError("hoigen_profile_read failed")
     out = []
     for line in buf.raw[:n].decode().splitlines():
-        tag, ms, fl, by = line.split()
-        out.append((tag, float(ms), float(fl), float(by)))
+        tag, ms, fl, by, t0 = line.split()
+        out.append((tag, float(ms), float(fl), float(by), float(t0)))
     return out
 
 

@@ -165,15 +165,16 @@ int hoigen_profile_reset(void) {
   return HOIGEN_OK;
 }
 
-// Writes one line per recorded launch: "tag ms flops bytes\n". Synchronises the device. Returns bytes written.
+// Writes one line per recorded launch: "tag ms flops bytes start_ms\n". Synchronises the device. Returns bytes written.
 long long hoigen_profile_read(char* buf, long long cap) {
   using namespace hoigen;
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
   long long off = 0;
   for (int i = 0; i < g_prof_n; ++i) {
-    float ms = 0.f;
+    float ms = 0.f, t0 = 0.f;
     if (cudaEventElapsedTime(&ms, g_prof[i].e0, g_prof[i].e1) != cudaSuccess) ms = -1.f;
-    int n = snprintf(buf + off, size_t(cap - off), "%s %.6f %.0f %.0f\n", g_prof[i].tag, ms, g_prof[i].flops, g_prof[i].bytes);
+    if (cudaEventElapsedTime(&t0, g_prof[0].e0, g_prof[i].e0) != cudaSuccess) t0 = -1.f;
+    int n = snprintf(buf + off, size_t(cap - off), "%s %.6f %.0f %.0f %.6f\n", g_prof[i].tag, ms, g_prof[i].flops, g_prof[i].bytes, t0);
     if (n < 0 || off + n >= cap) break;
     off += n;
   }

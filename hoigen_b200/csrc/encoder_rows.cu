@@ -150,23 +150,25 @@ adapter_kv_kernel(const float* __restrict__ prior, const float* __restrict__ in_
 // lane owns elements (lane, lane+32) of every 64-vector.  Weights live transposed in shared memory.
 // ------------------------------------------------------------------------------------------------
 struct AdapterMidW {
-  const float* in_w;   // (192,64)  rows [q;k;v]
-  const float* in_b;   // (192)
-  const float* out_w;  // (64,64)
-  const float* out_b;  // (64)
-  const float* l1_w;   // (128,64)
-  const float* l1_b;   // (128)
-  const float* l2_w;   // (64,128)
-  const float* l2_b;   // (64)
+  const uint32_t* packed;  // AM_W_WORDS words: the shared-memory image of the four matrices (see below)
+  const float* in_b;       // (192) in_proj bias, q part = first 64
+  const float* out_b;      // (64)
+  const float* l1_b;       // (128)
+  const float* l2_b;       // (64)
   const float* n2_w; const float* n2_b; const float* n3_w; const float* n3_b;  // (64) each
 };
 
 constexpr int AM_ROWS = 4;       // rows per warp pass
 constexpr int AM_THREADS = 256;
 constexpr int AM_MAXKEYS = 32;
-// shared memory floats: WqT 64x64, WoT 64x64, W1T 64x128, W2T 128x64, K (32 x 65), V (32 x 64)
-constexpr int AM_SMEM_FLOATS = 64 * 64 * 2 + 64 * 128 * 2 + AM_MAXKEYS * 65 * 2 + AM_MAXKEYS * 64 * 0 + 64;
-constexpr int AM_SMEM_BYTES = AM_SMEM_FLOATS * 4;
+// Shared memory (65 KiB -> 3 CTAs / SM): the four weight matrices as bf16 PAIRS, transposed to [input][output] with
+// inputs (i, i + half) packed in one 32-bit word (halves the LDS count, fp32 FMAs), then K and V (fp32, padded rows).
+constexpr int AM_W_WORDS = 32 * 64 * 2 + 32 * 128 + 64 * 64;   // WqP, WoP, W1P, W2P
+constexpr int AM_SMEM_BYTES = (AM_W_WORDS + 2 * AM_MAXKEYS * 65) * 4;
+
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t bf_pack(float lo, float hi) { return pack_bf16x2(lo, hi); }
 
 __device__ __forceinline__ void ln64(float (&a)[AM_ROWS], float (&b)[AM_ROWS], float g0, float g1, float b0, float b1) {
 #pragma unroll
@@ -179,30 +181,41 @@ __device__ __forceinline__ void ln64(float (&a)[AM_ROWS], float (&b)[AM_ROWS], f
   }
 }
 
-__global__ void __launch_bounds__(AM_THREADS)
+// y(lane), y(lane+32) += W[64 in][64 out] x, weights packed as P[i][o] = (W[i][o], W[i+32][o]), i < 32
+__device__ __forceinline__ void matvec64(const uint32_t* __restrict__ P, int lane, const float (&x0)[AM_ROWS],
+                                         const float (&x1)[AM_ROWS], float (&y0)[AM_ROWS], float (&y1)[AM_ROWS]) {
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const uint32_t wa = P[i * 64 + lane], wb = P[i * 64 + lane + 32];
+    const float a0 = bf_lo(wa), b0 = bf_hi(wa), a1 = bf_lo(wb), b1 = bf_hi(wb);
+#pragma unroll
+    for (int r = 0; r < AM_ROWS; ++r) {
+      const float xa = __shfl_sync(0xffffffffu, x0[r], i), xb = __shfl_sync(0xffffffffu, x1[r], i);
+      y0[r] = fmaf(a0, xa, fmaf(b0, xb, y0[r]));
+      y1[r] = fmaf(a1, xa, fmaf(b1, xb, y1[r]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AM_THREADS, 3)
 adapter_mid_kernel(const float* __restrict__ D, const float* __restrict__ kv /* (tokens_total,128) this layer */,
                    const uint8_t* __restrict__ mask /* (B,n_max) 1 = padding */, AdapterMidW w,
                    __nv_bfloat16* __restrict__ out, int n_max, int row_split) {
-  extern __shared__ float sm[];
-  float* WqT = sm;                  // [i][o] 64x64
-  float* WoT = WqT + 64 * 64;       // [i][o]
-  float* W1T = WoT + 64 * 64;       // [i][o] 64x128
-  float* W2T = W1T + 64 * 128;      // [i][o] 128x64
-  float* Ks = W2T + 128 * 64;       // [j][65]  (64 used, +1 pad: lane j reads column d)
-  float* Vs = Ks + AM_MAXKEYS * 65; // [j][65]
+  extern __shared__ uint32_t smw[];
+  uint32_t* WqP = smw;                   // [32][64]
+  uint32_t* WoP = WqP + 32 * 64;         // [32][64]
+  uint32_t* W1P = WoP + 32 * 64;         // [32][128]   (W1[i][o], W1[i+32][o])
+  uint32_t* W2P = W1P + 32 * 128;        // [64][64]    (W2[j][o], W2[j+64][o]),  j < 64
+  float* Ks = reinterpret_cast<float*>(W2P + 64 * 64);   // [j][65]
+  float* Vs = Ks + AM_MAXKEYS * 65;                      // [j][65]
   __shared__ int s_nkeys;
   __shared__ int s_keyidx[AM_MAXKEYS];
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 64 * 64; i += AM_THREADS) {
-    WqT[(i % 64) * 64 + i / 64] = __ldg(w.in_w + i);  // q rows are the first 64 of in_proj
-    WoT[(i % 64) * 64 + i / 64] = __ldg(w.out_w + i);
-  }
-  for (int i = tid; i < 128 * 64; i += AM_THREADS) {
-    W1T[(i % 64) * 128 + i / 64] = __ldg(w.l1_w + i);   // l1_w[o][i], o<128, i<64
-    W2T[(i % 128) * 64 + i / 128] = __ldg(w.l2_w + i);  // l2_w[o][i], o<64, i<128
-  }
+  // the packed image was laid out at build time (hoigen_b200/encoder.py::pack_adapter_mid): straight 16-byte copy
+  for (int e = tid; e < AM_W_WORDS / 4; e += AM_THREADS)
+    reinterpret_cast<uint4*>(smw)[e] = __ldg(reinterpret_cast<const uint4*>(w.packed) + e);
   if (tid == 0) {
     int n = 0;
     for (int j = 0; j < n_max; ++j)
@@ -242,21 +255,11 @@ adapter_mid_kernel(const float* __restrict__ D, const float* __restrict__ kv /* 
       d0[r] = src[lane];
       d1[r] = src[lane + 32];
     }
-    // ---- q = Wq d + bq, scaled ----
+    // ---- q = Wq d + bq ----
     float q0[AM_ROWS], q1[AM_ROWS];
 #pragma unroll
     for (int r = 0; r < AM_ROWS; ++r) { q0[r] = bq0; q1[r] = bq1; }
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-      const float wa0 = WqT[i * 64 + lane], wa1 = WqT[i * 64 + lane + 32];
-      const float wb0 = WqT[(i + 32) * 64 + lane], wb1 = WqT[(i + 32) * 64 + lane + 32];
-#pragma unroll
-      for (int r = 0; r < AM_ROWS; ++r) {
-        const float xa = __shfl_sync(0xffffffffu, d0[r], i), xb = __shfl_sync(0xffffffffu, d1[r], i);
-        q0[r] = fmaf(wa0, xa, fmaf(wb0, xb, q0[r]));
-        q1[r] = fmaf(wa1, xa, fmaf(wb1, xb, q1[r]));
-      }
-    }
+    matvec64(WqP, lane, d0, d1, q0, q1);
     // ---- 2-head attention over the compacted keys: lane j scores key j ----
     float a0[AM_ROWS], a1[AM_ROWS];  // attention output (head 0 -> dims 0..31 held as a0, head 1 -> a1)
     {
@@ -301,17 +304,7 @@ adapter_mid_kernel(const float* __restrict__ D, const float* __restrict__ kv /* 
     float t0v[AM_ROWS], t1v[AM_ROWS];
 #pragma unroll
     for (int r = 0; r < AM_ROWS; ++r) { t0v[r] = bo0; t1v[r] = bo1; }
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-      const float wa0 = WoT[i * 64 + lane], wa1 = WoT[i * 64 + lane + 32];
-      const float wb0 = WoT[(i + 32) * 64 + lane], wb1 = WoT[(i + 32) * 64 + lane + 32];
-#pragma unroll
-      for (int r = 0; r < AM_ROWS; ++r) {
-        const float xa = __shfl_sync(0xffffffffu, a0[r], i), xb = __shfl_sync(0xffffffffu, a1[r], i);
-        t0v[r] = fmaf(wa0, xa, fmaf(wb0, xb, t0v[r]));
-        t1v[r] = fmaf(wa1, xa, fmaf(wb1, xb, t1v[r]));
-      }
-    }
+    matvec64(WoP, lane, a0, a1, t0v, t1v);
 #pragma unroll
     for (int r = 0; r < AM_ROWS; ++r) { t0v[r] += d0[r]; t1v[r] += d1[r]; }
     ln64(t0v, t1v, n2g0, n2g1, n2b0, n2b1);
@@ -323,14 +316,14 @@ adapter_mid_kernel(const float* __restrict__ D, const float* __restrict__ kv /* 
       for (int r = 0; r < AM_ROWS; ++r) h[k][r] = b1v[k];
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
-      float wa[4], wb[4];
+      uint32_t wv[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { wa[k] = W1T[i * 128 + lane + 32 * k]; wb[k] = W1T[(i + 32) * 128 + lane + 32 * k]; }
+      for (int k = 0; k < 4; ++k) wv[k] = W1P[i * 128 + lane + 32 * k];
 #pragma unroll
       for (int r = 0; r < AM_ROWS; ++r) {
         const float xa = __shfl_sync(0xffffffffu, t0v[r], i), xb = __shfl_sync(0xffffffffu, t1v[r], i);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[k][r] = fmaf(wa[k], xa, fmaf(wb[k], xb, h[k][r]));
+        for (int k = 0; k < 4; ++k) h[k][r] = fmaf(bf_lo(wv[k]), xa, fmaf(bf_hi(wv[k]), xb, h[k][r]));
       }
     }
 #pragma unroll
@@ -341,15 +334,15 @@ adapter_mid_kernel(const float* __restrict__ D, const float* __restrict__ kv /* 
 #pragma unroll
     for (int r = 0; r < AM_ROWS; ++r) { f0[r] = b2_0; f1[r] = b2_1; }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll 8
       for (int i = 0; i < 32; ++i) {
-        const float w0 = W2T[(k * 32 + i) * 64 + lane], w1 = W2T[(k * 32 + i) * 64 + lane + 32];
+        const uint32_t w0 = W2P[(kk * 32 + i) * 64 + lane], w1 = W2P[(kk * 32 + i) * 64 + lane + 32];
 #pragma unroll
         for (int r = 0; r < AM_ROWS; ++r) {
-          const float x = __shfl_sync(0xffffffffu, h[k][r], i);
-          f0[r] = fmaf(w0, x, f0[r]);
-          f1[r] = fmaf(w1, x, f1[r]);
+          const float xl = __shfl_sync(0xffffffffu, h[kk][r], i), xh = __shfl_sync(0xffffffffu, h[kk + 2][r], i);
+          f0[r] = fmaf(bf_lo(w0), xl, fmaf(bf_hi(w0), xh, f0[r]));
+          f1[r] = fmaf(bf_lo(w1), xl, fmaf(bf_hi(w1), xh, f1[r]));
         }
       }
     }
@@ -421,7 +414,8 @@ int hoigen_adapter_kv(const float* prior, const float* in_proj_w, const float* i
 int hoigen_adapter_mid(const float* d, const float* kv_layer, const uint8_t* mask, const hoigen_adapter_mid_weights* w,
                        void* out_bf16, int32_t batch, int32_t n_max, hoigen_stream_t stream) {
   using namespace hoigen;
-  HOIGEN_CHECK_ARG(d && kv_layer && mask && w && out_bf16 && batch > 0, "adapter_mid: bad arguments");
+  HOIGEN_CHECK_ARG(d && kv_layer && mask && w && w->packed && out_bf16 && batch > 0, "adapter_mid: bad arguments");
+  HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(w->packed) & 15) == 0, "adapter_mid: packed weights must be 16-byte aligned");
   HOIGEN_CHECK_ARG(n_max > 0 && n_max <= AM_MAXKEYS, "adapter_mid: n_max must be in [1,%d] (got %d)", AM_MAXKEYS, n_max);
   static bool attr_set = false;
   if (!attr_set) {
@@ -429,12 +423,12 @@ int hoigen_adapter_mid(const float* d, const float* kv_layer, const uint8_t* mas
     attr_set = true;
   }
   AdapterMidW mw;
-  mw.in_w = w->in_proj_w; mw.in_b = w->in_proj_b; mw.out_w = w->out_proj_w; mw.out_b = w->out_proj_b;
-  mw.l1_w = w->linear1_w; mw.l1_b = w->linear1_b; mw.l2_w = w->linear2_w; mw.l2_b = w->linear2_b;
+  mw.packed = w->packed; mw.in_b = w->in_proj_b; mw.out_b = w->out_proj_b;
+  mw.l1_b = w->linear1_b; mw.l2_b = w->linear2_b;
   mw.n2_w = w->norm2_w; mw.n2_b = w->norm2_b; mw.n3_w = w->norm3_w; mw.n3_b = w->norm3_b;
   // split each image's 197 rows so that the grid covers the SMs at least ~2x
   int split = 1;
-  while (batch * split < 2 * num_sms() && split < 8) split *= 2;
+  while (batch * split < 3 * num_sms() && split < 8) split *= 2;
   dim3 grid(batch, split);
   KernelScope ks("adapter_mid", reinterpret_cast<cudaStream_t>(stream), 2.0 * batch * TOKENS * (64 * 64 * 2 + 2 * 64 * 128 + 2 * 64 * n_max),
                  double(batch) * TOKENS * 64 * (4 + 2));

@@ -4,7 +4,7 @@
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0    : TMA producer   (A tile 128x64, W tile BNx64, 128B swizzle, STAGES-deep mbarrier ring)
 //   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accum in TMEM)
-//   warps 2-5 : epilogue       (tcgen05.ld 32 lanes x 32 columns -> registers -> global)
+//   warps 2-9 : epilogue       (tcgen05.ld 32 lanes x 32 columns -> registers -> global; residual prefetched)
 // Two TMEM accumulator stages (2*BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Replaces the cuBLAS SGEMMs the reference dispatches from CLIP_models_adapter_prior2.py:443-445 (in/out
@@ -21,7 +21,7 @@ namespace hoigen {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 
 struct GemmArgs {
   int M, N, K;
@@ -48,8 +48,10 @@ struct GemmCfg {
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == HOIGEN_ACT_QUICKGELU) {
-    // x * sigmoid(1.702 x)   (CLIP_models_adapter_prior2.py:420)
-    return v / (1.0f + __expf(-1.702f * v));
+    // x * sigmoid(1.702 x)   (CLIP_models_adapter_prior2.py:420); sigmoid(z) = 0.5 + 0.5 tanh(z/2): one MUFU op
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.851f * v));
+    return v * fmaf(0.5f, th, 0.5f);
   } else if (act == HOIGEN_ACT_RELU) {
     return fmaxf(v, 0.0f);
   }
@@ -90,7 +92,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8u * a, 1);
-      mbar_init(bar_tempty + 8u * a, 4);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8u * a, 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -153,29 +155,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue warps (8: two per TMEM lane quadrant, each owning half of the BN columns) ======
+    // Thread = one output row. The fp32 residual of the NEXT 32-column chunk is prefetched while the current chunk is
+    // being processed (and the first chunk's before the accumulator is even ready), so the global-load latency of the
+    // read-modify-write epilogue hides behind the MMAs instead of serialising with them.
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;          // 0 / 1: which half of the tile's columns
+    constexpr int CHUNKS = (BN / 2) / 32;      // 32-column chunks per warp
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      mbar_wait(bar_tfull + 8u * acc, acc_phase);
-      tc_fence_after();
       const int row = m_blk * BM + quad * 32 + lane;
       const bool row_ok = row < g.M;
-      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN);
+      const int colbase = n_blk * BN + half * (BN / 2);
+      const bool res_vec = g.residual && row_ok && (g.ld_res & 3) == 0;
+      const float* res_row = g.residual ? g.residual + size_t(row_ok ? row : 0) * g.ld_res : nullptr;
+      float4 res_next[8];
+      if (res_vec && colbase + 32 <= g.N) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
+      }
+      mbar_wait(bar_tfull + 8u * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN + half * (BN / 2));
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n_blk * BN + c * 32;
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int col0 = colbase + c * 32;
         if (col0 >= g.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + uint32_t(c * 32), r);
+        const bool full_chunk = (col0 + 32 <= g.N);
+        float4 res_cur[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) res_cur[j] = res_next[j];
+        if (res_vec && c + 1 < CHUNKS && col0 + 64 <= g.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(res_row + col0 + 32 + 4 * j);
+        }
         tmem_wait_ld();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const bool full_chunk = (col0 + 32 <= g.N);
         if (g.bias) {
           if (full_chunk) {
 #pragma unroll
@@ -208,17 +230,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (row_ok) {
           if (g.residual) {
-            const float* rp = g.residual + size_t(row) * g.ld_res + col0;
-            if (full_chunk && (g.ld_res & 3) == 0) {
+            if (res_vec && full_chunk) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 x = *reinterpret_cast<const float4*>(rp + j);
-                v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += res_cur[j].x; v[4 * j + 1] += res_cur[j].y; v[4 * j + 2] += res_cur[j].z; v[4 * j + 3] += res_cur[j].w;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < g.N) v[j] += rp[j];
+                if (col0 + j < g.N) v[j] += res_row[col0 + j];
             }
           }
           if (g.out_f32) {

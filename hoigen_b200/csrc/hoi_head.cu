@@ -23,12 +23,13 @@ __device__ __forceinline__ float warp_sum_h(float v) {
 
 // ------------------------------------------------------------------------------------------------
 // prior tokens: [score, box/(w,h,w,h), object_embedding[label]] (517) -> 128 -> 128 -> 64 (ReLU between)
-// one block per image, 128 threads; thread o owns output feature o for every token of the image.
+// one block per (image, 4 tokens), 128 threads; thread o owns output feature o of those tokens.
 // Padding tokens (t >= n_b) are MLP(0) constants and mask = 1 (U:1448-1450, 1469, 1495).
 // weights are passed TRANSPOSED (in, out) so that the per-thread reads are coalesced.
 // ------------------------------------------------------------------------------------------------
 constexpr int PRIOR_IN = 517;
 constexpr int PRIOR_MAXTOK = 32;
+constexpr int PRIOR_TPB = 4;  // tokens per block
 
 __global__ void __launch_bounds__(128)
 prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ labels,
@@ -36,71 +37,69 @@ prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ s
                     const float* __restrict__ b0, const float* __restrict__ w1t, const float* __restrict__ b1,
                     const float* __restrict__ w2t, const float* __restrict__ b2, float img_w, float img_h, int n_max,
                     float* __restrict__ prior, uint8_t* __restrict__ mask) {
-  extern __shared__ float sm[];
-  float* xin = sm;                                // [n_max][520]
-  float* h1 = xin + PRIOR_MAXTOK * 520;           // [n_max][128]
-  float* h2 = h1 + PRIOR_MAXTOK * 128;            // [n_max][128]
+  __shared__ float xin[PRIOR_TPB][520];
+  __shared__ float h1[PRIOR_TPB][128];
+  __shared__ float h2[PRIOR_TPB][128];
   const int b = blockIdx.x;
+  const int tbase = blockIdx.y * PRIOR_TPB;
   const int o = threadIdx.x;
   const int base = box_off[b];
   const int n = box_off[b + 1] - base;
-  for (int i = threadIdx.x; i < n_max * 520; i += 128) {
-    const int t = i / 520, c = i % 520;
+  for (int i = threadIdx.x; i < PRIOR_TPB * 520; i += 128) {
+    const int t = tbase + i / 520, c = i % 520;
     float v = 0.f;
     if (t < n && c < PRIOR_IN) {
       if (c == 0) v = scores[base + t];
       else if (c < 5) v = boxes[(base + t) * 4 + (c - 1)] / ((c & 1) ? img_w : img_h);  // x1/w, y1/h, x2/w, y2/h
       else v = __ldg(obj_emb + labels[base + t] * FEAT + (c - 5));
     }
-    xin[i] = v;
+    xin[i / 520][c] = v;
   }
-  for (int t = threadIdx.x; t < n_max; t += 128) mask[b * n_max + t] = t < n ? 0 : 1;
+  if (threadIdx.x < PRIOR_TPB && tbase + threadIdx.x < n_max)
+    mask[b * n_max + tbase + threadIdx.x] = (tbase + threadIdx.x) < n ? 0 : 1;
   __syncthreads();
-  float acc[PRIOR_MAXTOK];
-  // layer 0
+  float acc[PRIOR_TPB];
   {
     const float bias = b0[o];
 #pragma unroll
-    for (int t = 0; t < PRIOR_MAXTOK; ++t) acc[t] = bias;
+    for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = bias;
+#pragma unroll 4
     for (int k = 0; k < PRIOR_IN; ++k) {
       const float w = __ldg(w0t + k * 128 + o);
 #pragma unroll
-      for (int t = 0; t < PRIOR_MAXTOK; ++t)
-        if (t < n_max) acc[t] = fmaf(w, xin[t * 520 + k], acc[t]);
+      for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = fmaf(w, xin[t][k], acc[t]);
     }
 #pragma unroll
-    for (int t = 0; t < PRIOR_MAXTOK; ++t)
-      if (t < n_max) h1[t * 128 + o] = fmaxf(acc[t], 0.f);
+    for (int t = 0; t < PRIOR_TPB; ++t) h1[t][o] = fmaxf(acc[t], 0.f);
   }
   __syncthreads();
   {
     const float bias = b1[o];
 #pragma unroll
-    for (int t = 0; t < PRIOR_MAXTOK; ++t) acc[t] = bias;
+    for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = bias;
+#pragma unroll 4
     for (int k = 0; k < 128; ++k) {
       const float w = __ldg(w1t + k * 128 + o);
 #pragma unroll
-      for (int t = 0; t < PRIOR_MAXTOK; ++t)
-        if (t < n_max) acc[t] = fmaf(w, h1[t * 128 + k], acc[t]);
+      for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = fmaf(w, h1[t][k], acc[t]);
     }
 #pragma unroll
-    for (int t = 0; t < PRIOR_MAXTOK; ++t)
-      if (t < n_max) h2[t * 128 + o] = fmaxf(acc[t], 0.f);
+    for (int t = 0; t < PRIOR_TPB; ++t) h2[t][o] = fmaxf(acc[t], 0.f);
   }
   __syncthreads();
   if (o < 64) {
     const float bias = b2[o];
 #pragma unroll
-    for (int t = 0; t < PRIOR_MAXTOK; ++t) acc[t] = bias;
+    for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = bias;
+#pragma unroll 4
     for (int k = 0; k < 128; ++k) {
       const float w = __ldg(w2t + k * 64 + o);
 #pragma unroll
-      for (int t = 0; t < PRIOR_MAXTOK; ++t)
-        if (t < n_max) acc[t] = fmaf(w, h2[t * 128 + k], acc[t]);
+      for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = fmaf(w, h2[t][k], acc[t]);
     }
 #pragma unroll
-    for (int t = 0; t < PRIOR_MAXTOK; ++t)
-      if (t < n_max) prior[(size_t(b) * n_max + t) * 64 + o] = acc[t];
+    for (int t = 0; t < PRIOR_TPB; ++t)
+      if (tbase + t < n_max) prior[(size_t(b) * n_max + tbase + t) * 64 + o] = acc[t];
   }
 }
 
@@ -399,15 +398,9 @@ int hoigen_prior_tokens(const float* boxes, const float* scores, const int64_t* 
   using namespace hoigen;
   HOIGEN_CHECK_ARG(boxes && scores && labels && box_off && obj_emb && prior && mask && batch > 0, "prior_tokens: bad arguments");
   HOIGEN_CHECK_ARG(n_max > 0 && n_max <= PRIOR_MAXTOK, "prior_tokens: n_max must be in [1,%d] (got %d)", PRIOR_MAXTOK, n_max);
-  const int smem = (PRIOR_MAXTOK * 520 + 2 * PRIOR_MAXTOK * 128) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(prior_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
   KernelScope ks("prior_tokens", reinterpret_cast<cudaStream_t>(stream), 2.0 * batch * n_max * (517 * 128 + 128 * 128 + 128 * 64),
                  double(batch) * n_max * (517 + 64) * 4);
-  prior_tokens_kernel<<<batch, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  prior_tokens_kernel<<<dim3(batch, (n_max + PRIOR_TPB - 1) / PRIOR_TPB), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       boxes, scores, labels, box_off, obj_emb, w0t, b0, w1t, b1, w2t, b2, img_w, img_h, n_max, prior, mask);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;

@@ -52,10 +52,11 @@ int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder
     HOIGEN_TRY(gemm(buf->xb, D, (const uint16_t*)w->ad_down_w + size_t(l) * 64 * D, D, M, 64, D, w->ad_down_b + o64,
                     HOIGEN_ACT_RELU, nullptr, nullptr, 0, buf->adapter_d, 64, nullptr, 0, s));
     hoigen_adapter_mid_weights mw;
-    mw.in_proj_w = w->ad_in_proj_w + size_t(l) * 192 * 64; mw.in_proj_b = w->ad_in_proj_b + size_t(l) * 192;
-    mw.out_proj_w = w->ad_out_proj_w + size_t(l) * 64 * 64; mw.out_proj_b = w->ad_out_proj_b + o64;
-    mw.linear1_w = w->ad_linear1_w + size_t(l) * 128 * 64; mw.linear1_b = w->ad_linear1_b + size_t(l) * 128;
-    mw.linear2_w = w->ad_linear2_w + size_t(l) * 64 * 128; mw.linear2_b = w->ad_linear2_b + o64;
+    mw.packed = w->ad_mid_packed + size_t(l) * HOIGEN_ADAPTER_MID_PACKED_WORDS;
+    mw.in_proj_b = w->ad_in_proj_b + size_t(l) * 192;
+    mw.out_proj_b = w->ad_out_proj_b + o64;
+    mw.linear1_b = w->ad_linear1_b + size_t(l) * 128;
+    mw.linear2_b = w->ad_linear2_b + o64;
     mw.norm2_w = w->ad_norm2_w + o64; mw.norm2_b = w->ad_norm2_b + o64;
     mw.norm3_w = w->ad_norm3_w + o64; mw.norm3_b = w->ad_norm3_b + o64;
     HOIGEN_TRY(hoigen_adapter_mid(buf->adapter_d, buf->adapter_kv + size_t(l) * batch * n_max * 128, mask, &mw,

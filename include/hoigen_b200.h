@@ -46,7 +46,7 @@ HOIGEN_API const char* hoigen_last_error(void);
 HOIGEN_API int hoigen_init(int device);
 
 /* Launch accounting + optional per-launch CUDA-event timing (used by bench.py for gpu_launches / roofline).
- * hoigen_profile_read writes one line per recorded launch, "tag ms flops bytes", and returns the byte count. */
+ * hoigen_profile_read writes one line per recorded launch, "tag ms flops bytes start_ms", and returns the byte count. */
 HOIGEN_API long long hoigen_launch_count(void);
 HOIGEN_API int hoigen_profile_enable(int on);
 HOIGEN_API int hoigen_profile_reset(void);
@@ -99,14 +99,16 @@ HOIGEN_API int hoigen_layernorm768(const float* x, const float* gamma, const flo
 HOIGEN_API int hoigen_adapter_kv(const float* prior, const float* in_proj_w, const float* in_proj_b, float* kv,
                                  int32_t tokens, int32_t layers, hoigen_stream_t stream);
 
+#define HOIGEN_ADAPTER_MID_PACKED_WORDS 12288
 typedef struct {
-  const float* in_proj_w;  /* (192,64) rows [q;k;v]   multihead_attn.in_proj_weight */
-  const float* in_proj_b;  /* (192) */
-  const float* out_proj_w; /* (64,64) */
+  /* bf16-pair image of the four 64-wide matrices, transposed to [input][output]; word = (W[i][o], W[i+half][o]):
+   *   [0,2048)      q rows of in_proj (64x64):  i<32, half=32     [2048,4096)  out_proj (64x64): i<32, half=32
+   *   [4096,8192)   linear1 (64 in, 128 out):   i<32, half=32     [8192,12288) linear2 (128 in, 64 out): i<64, half=64
+   * built by hoigen_b200/encoder.py::pack_adapter_mid at weight-packing time; 16-byte aligned. */
+  const uint32_t* packed;
+  const float* in_proj_b;  /* (192) multihead_attn.in_proj_bias (q part used here) */
   const float* out_proj_b; /* (64) */
-  const float* linear1_w;  /* (128,64) */
   const float* linear1_b;  /* (128) */
-  const float* linear2_w;  /* (64,128) */
   const float* linear2_b;  /* (64) */
   const float* norm2_w; const float* norm2_b; const float* norm3_w; const float* norm3_b; /* (64) */
 } hoigen_adapter_mid_weights;
@@ -139,9 +141,10 @@ typedef struct {
   const void* ad_up_w; const float* ad_up_b;      /* bf16 (12,768,64), (12,768) adaptermlp.up_proj.* */
   const float* ad_scale;                          /* (12,768)                   adaptermlp.scale */
   const float* ad_in_proj_w; const float* ad_in_proj_b;    /* (12,192,64), (12,192)  mhsa_layers.0.multihead_attn */
-  const float* ad_out_proj_w; const float* ad_out_proj_b;  /* (12,64,64), (12,64) */
-  const float* ad_linear1_w; const float* ad_linear1_b;    /* (12,128,64), (12,128) */
-  const float* ad_linear2_w; const float* ad_linear2_b;    /* (12,64,128), (12,64) */
+  const uint32_t* ad_mid_packed;                           /* (12, 12288) see hoigen_adapter_mid_weights.packed */
+  const float* ad_out_proj_b;                              /* (12,64) */
+  const float* ad_linear1_b;                               /* (12,128) */
+  const float* ad_linear2_b;                               /* (12,64) */
   const float* ad_norm2_w; const float* ad_norm2_b; const float* ad_norm3_w; const float* ad_norm3_b; /* (12,64) */
 } hoigen_encoder_weights;
 

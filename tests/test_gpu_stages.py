@@ -58,7 +58,8 @@ def test_gemm_epilogue(cuda_device, act):
     ob = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
     _cabi.gemm_bf16(a, w, bias=bias, colscale=cs, act=act, residual=of, out_f32=of, out_bf16=ob)
     ref = _ref_gemm(a, w, bias, act, cs, res)
-    assert (of - ref).abs().max().item() < 1e-4          # fp32 epilogue; __expf in QuickGELU
+    # fp32 epilogue; QuickGELU uses tanh.approx.f32 (rel 2^-11) because its consumer is a bf16 operand anyway
+    assert (of - ref).abs().max().item() < (1e-4 if act != 1 else 4e-3)
     assert (ob.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item()   # one bf16 rounding
 
 
@@ -155,8 +156,12 @@ def test_adapter_kv_and_mid(cuda_device, enc_state):
     kv_ref = torch.nn.functional.linear(prior, enc_state[blk + "multihead_attn.in_proj_weight"][64:],
                                         enc_state[blk + "multihead_attn.in_proj_bias"][64:]).view(B * n_max, 128)
     assert (kv[0].cpu() - kv_ref).abs().max().item() < 1e-5
+    from hoigen_b200.encoder import pack_adapter_mid
+    packed = pack_adapter_mid(w[0], w[2], w[4], w[6]).to(cuda_device)
     mw = _cabi.AdapterMidWeights()
-    for f, t in zip([f for f, _ in _cabi.AdapterMidWeights._fields_], w):
+    mw.packed = packed.data_ptr()
+    for f, t in zip(("in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w", "norm2_b", "norm3_w", "norm3_b"),
+                    (w[1], w[3], w[5], w[7], w[8], w[9], w[10], w[11])):
         setattr(mw, f, t.data_ptr())
     out = torch.zeros(B * 197, 64, device=cuda_device, dtype=torch.bfloat16)
     dd = d.to(cuda_device).contiguous()
