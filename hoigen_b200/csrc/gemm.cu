@@ -58,6 +58,116 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// One epilogue warp: thread = one output row, CHUNKS x 32 consecutive columns starting at colbase, accumulators at
+// TMEM address t_addr (this warp's lane quadrant). The fp32 residual of the NEXT 32-column chunk is prefetched while
+// the current chunk is processed, and the first chunk's before the accumulator is ready (wait_acc), so the latency
+// of the read-modify-write epilogue hides behind the MMAs instead of serialising with them.
+template <int CHUNKS, typename WaitFn>
+__device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int colbase, uint32_t t_addr, WaitFn wait_acc) {
+  const bool row_ok = row < g.M;
+  const bool res_vec = g.residual && row_ok && (g.ld_res & 3) == 0;
+  const float* res_row = g.residual ? g.residual + size_t(row_ok ? row : 0) * g.ld_res : nullptr;
+  float4 res_next[8];
+  if (res_vec && colbase + 32 <= g.N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
+  }
+  wait_acc();
+#pragma unroll 1
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col0 = colbase + c * 32;
+    if (col0 >= g.N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_addr + uint32_t(c * 32), r);
+    const bool full_chunk = (col0 + 32 <= g.N);
+    float4 res_cur[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) res_cur[j] = res_next[j];
+    if (res_vec && c + 1 < CHUNKS && col0 + 64 <= g.N) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(res_row + col0 + 32 + 4 * j);
+    }
+    tmem_wait_ld();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (g.bias) {
+      if (full_chunk) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
+      }
+    }
+    if (g.act != HOIGEN_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
+    }
+    if (g.colscale) {
+      if (full_chunk) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(g.colscale + col0 + j));
+          v[j] *= b.x; v[j + 1] *= b.y; v[j + 2] *= b.z; v[j + 3] *= b.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < g.N) v[j] *= __ldg(g.colscale + col0 + j);
+      }
+    }
+    if (row_ok) {
+      if (g.residual) {
+        if (res_vec && full_chunk) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] += res_cur[j].x; v[4 * j + 1] += res_cur[j].y; v[4 * j + 2] += res_cur[j].z; v[4 * j + 3] += res_cur[j].w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < g.N) v[j] += res_row[col0 + j];
+        }
+      }
+      if (g.out_f32) {
+        float* op = g.out_f32 + size_t(row) * g.ld_f32 + col0;
+        if (full_chunk && (g.ld_f32 & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < g.N) op[j] = v[j];
+        }
+      }
+      if (g.out_bf16) {
+        __nv_bfloat16* op = g.out_bf16 + size_t(row) * g.ld_bf16 + col0;
+        if (full_chunk && (g.ld_bf16 & 7) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            pk.x = pack_bf16x2(v[j], v[j + 1]);
+            pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(op + j) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < g.N) op[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
@@ -156,123 +266,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps (8: two per TMEM lane quadrant, each owning half of the BN columns) ======
-    // Thread = one output row. The fp32 residual of the NEXT 32-column chunk is prefetched while the current chunk is
-    // being processed (and the first chunk's before the accumulator is even ready), so the global-load latency of the
-    // read-modify-write epilogue hides behind the MMAs instead of serialising with them.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;          // 0 / 1: which half of the tile's columns
-    constexpr int CHUNKS = (BN / 2) / 32;      // 32-column chunks per warp
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int row = m_blk * BM + quad * 32 + lane;
-      const bool row_ok = row < g.M;
       const int colbase = n_blk * BN + half * (BN / 2);
-      const bool res_vec = g.residual && row_ok && (g.ld_res & 3) == 0;
-      const float* res_row = g.residual ? g.residual + size_t(row_ok ? row : 0) * g.ld_res : nullptr;
-      float4 res_next[8];
-      if (res_vec && colbase + 32 <= g.N) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
-      }
-      mbar_wait(bar_tfull + 8u * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN + half * (BN / 2));
-#pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
-        const int col0 = colbase + c * 32;
-        if (col0 >= g.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + uint32_t(c * 32), r);
-        const bool full_chunk = (col0 + 32 <= g.N);
-        float4 res_cur[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res_cur[j] = res_next[j];
-        if (res_vec && c + 1 < CHUNKS && col0 + 64 <= g.N) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(res_row + col0 + 32 + 4 * j);
-        }
-        tmem_wait_ld();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (g.bias) {
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
-          }
-        }
-        if (g.act != HOIGEN_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
-        }
-        if (g.colscale) {
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(g.colscale + col0 + j));
-              v[j] *= b.x; v[j + 1] *= b.y; v[j + 2] *= b.z; v[j + 3] *= b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) v[j] *= __ldg(g.colscale + col0 + j);
-          }
-        }
-        if (row_ok) {
-          if (g.residual) {
-            if (res_vec && full_chunk) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[4 * j] += res_cur[j].x; v[4 * j + 1] += res_cur[j].y; v[4 * j + 2] += res_cur[j].z; v[4 * j + 3] += res_cur[j].w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < g.N) v[j] += res_row[col0 + j];
-            }
-          }
-          if (g.out_f32) {
-            float* op = g.out_f32 + size_t(row) * g.ld_f32 + col0;
-            if (full_chunk && (g.ld_f32 & 3) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < g.N) op[j] = v[j];
-            }
-          }
-          if (g.out_bf16) {
-            __nv_bfloat16* op = g.out_bf16 + size_t(row) * g.ld_bf16 + col0;
-            if (full_chunk && (g.ld_bf16 & 7) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                pk.x = pack_bf16x2(v[j], v[j + 1]);
-                pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(op + j) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < g.N) op[j] = __float2bfloat16_rn(v[j]);
-            }
-          }
-        }
-      }
+      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN + half * (BN / 2));
+      epilogue_warp<(BN / 2) / 32>(g, row, colbase, t_addr, [&]() {
+        mbar_wait(bar_tfull + 8u * acc, acc_phase);
+        tc_fence_after();
+      });
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -285,6 +292,158 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs computes one 256 x BN tile. Each CTA TMA-loads its own
+// 128 rows of A and HALF of the W tile (BN/2 rows) per k-block, the leader CTA's single MMA thread issues
+// UMMA 256 x BN x 16 over both CTAs' shared memory, and every CTA drains its own 128 x BN half of the accumulator
+// from its own TMEM.  Against the one-CTA kernel this cuts the L2 -> SM operand traffic per FLOP by 1.5x
+// (BN = 256), which is what bounds the one-CTA kernel on these shapes, and frees smem for a deeper TMA ring.
+//   full[s]      (leader's)  2 arrivals: leader producer arrive.expect_tx(bytes of BOTH CTAs) + peer producer arrive;
+//                            both CTAs' TMA loads credit their bytes to the leader's barrier
+//   empty[s]     (per CTA)   tcgen05.commit multicast from the leader's MMA thread
+//   tmem_full[a] (per CTA)   tcgen05.commit multicast
+//   tmem_empty[a](leader's)  16 arrivals: 8 epilogue warps of each CTA
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;          // 16 KiB: this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;    // this CTA's half of the W tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int ACC_STRIDE = 256;               // TMEM columns between the two accumulator stages
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * Cfg::STAGE_BYTES);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8u * STAGES;
+  const uint32_t bar_tfull = bar_full + 16u * STAGES;
+  const uint32_t bar_tempty = bar_tfull + 16u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();   // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int num_m = (g.M + 2 * BM - 1) / (2 * BM);
+  const int num_n = (g.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8u * s, 2);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8u * a, 1);
+      mbar_init(bar_tempty + 8u * a, 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits + TMEM allocation visible to the peer before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+          const uint32_t a_dst = tiles_addr + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+          const uint32_t full = bar_full + 8u * stage;
+          if (rank == 0) mbar_arrive_expect_tx(full, 2 * Cfg::STAGE_BYTES);
+          else mbar_arrive_leader(full);
+          tma_load_2d_2sm(a_dst, &tmA, full, kb * BK, m_blk * (2 * BM) + int(rank) * BM);
+          tma_load_2d_2sm(b_dst, &tmB, full, kb * BK, n_blk * BN + int(rank) * (BN / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * Cfg::ACC_STRIDE);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(bar_full + 8u * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = tiles_addr + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_sdesc_sw128(a_addr + k * (UMMA_K * 2));
+            const uint64_t bdesc = make_sdesc_sw128(b_addr + k * (UMMA_K * 2));
+            umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit_2sm(bar_empty + 8u * stage);   // frees the stage in BOTH CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_2sm(bar_tfull + 8u * acc);       // accumulator halves complete in BOTH CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs: own 128 rows) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int row = m_blk * (2 * BM) + int(rank) * BM + quad * 32 + lane;
+      const int colbase = n_blk * BN + half * (BN / 2);
+      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_STRIDE + half * (BN / 2));
+      epilogue_warp<(BN / 2) / 32>(g, row, colbase, t_addr, [&]() {
+        mbar_wait(bar_tfull + 8u * acc, acc_phase);
+        tc_fence_after();
+      });
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * acc);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // neither CTA may exit (or free TMEM) while the peer can still touch its smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -339,26 +498,6 @@ static GemmArgs to_args(const hoigen_gemm_params* p) {
   return g;
 }
 
-// tiles-per-SM rounds x relative tile cost; smaller is better.
-static int choose_block_n(int M, int N) {
-  const int sms = num_sms();
-  const int num_m = (M + BM - 1) / BM;
-  int best = 256;
-  double best_cost = 1e30;
-  const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    if (bn > 64 && N <= bn / 2) continue;  // do not pad N by 2x or more
-    const int tiles = num_m * ((N + bn - 1) / bn);
-    const int rounds = (tiles + sms - 1) / sms;
-    // narrower tiles re-read A more often and amortise the pipeline fill worse
-    const double tile_cost = double(bn) + 24.0;
-    const double cost = rounds * tile_cost;
-    if (cost < best_cost) { best_cost = cost; best = bn; }
-  }
-  return best;
-}
-
 // interned "gemm_n<N>_k<K>" tags for the launch profiler
 static const char* gemm_tag(int N, int K) {
   static std::map<std::pair<int, int>, std::string> tags;
@@ -389,6 +528,69 @@ static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
   return HOIGEN_OK;
 }
 
+template <int BN>
+static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
+  if (!ta) return HOIGEN_ERR_CUDA;
+  const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN / 2);
+  if (!tb) return HOIGEN_ERR_CUDA;
+  const int num_tiles = ((p->M + 2 * BM - 1) / (2 * BM)) * ((p->N + BN - 1) / BN);
+  const int max_clusters = num_sms() / 2;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  KernelScope ks(gemm_tag(p->N, p->K), stream, 2.0 * p->M * p->N * p->K,
+                 2.0 * (double(p->M) * p->K + double(p->N) * p->K) + double(p->M) * p->N * ((p->out_f32 ? 4 : 0) + (p->out_bf16 ? 2 : 0) + (p->residual ? 4 : 0)));
+  HOIGEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN>, *ta, *tb, to_args(p)));
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+// Pick (cta pair?, BN): fewest scheduling rounds x relative tile time. The one-CTA kernel is L2-operand-bound
+// (~87 FLOP per L2 byte at BN = 256) so its tiles are charged 1.35x.
+static void choose_config(int M, int N, int* pair, int* bn) {
+  const int sms = num_sms();
+  double best = 1e30;
+  *pair = 0; *bn = 256;
+  const int c1[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int b = c1[i];
+    if (b > 64 && N <= b / 2) continue;
+    const int tiles = ((M + BM - 1) / BM) * ((N + b - 1) / b);
+    const int rounds = (tiles + sms - 1) / sms;
+    const double cost = rounds * (double(b) * 1.35 + 24.0);
+    if (cost < best) { best = cost; *pair = 0; *bn = b; }
+  }
+  if (M > BM) {
+    const int c2[3] = {256, 192, 128};
+    for (int i = 0; i < 3; ++i) {
+      const int b = c2[i];
+      if (N <= b / 2) continue;
+      const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + b - 1) / b);
+      const int rounds = (tiles + sms / 2 - 1) / (sms / 2);
+      const double cost = rounds * (double(b) + 40.0);
+      if (cost < best) { best = cost; *pair = 1; *bn = b; }
+    }
+  }
+}
+
 }  // namespace hoigen
 
 extern "C" {
@@ -397,15 +599,28 @@ int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream) {
   using namespace hoigen;
   int rc = validate(p);
   if (rc != HOIGEN_OK) return rc;
-  int bn = p->block_n;
-  if (bn == 0) bn = choose_block_n(p->M, p->N);
+  // block_n: 0 = choose; 64/128/256 = one-CTA kernel; 2128/2192/2256 = CTA-pair kernel (256 x {128,192,256} tiles)
+  int bn = p->block_n, pair = 0;
+  if (bn == 0) choose_config(p->M, p->N, &pair, &bn);
+  else if (bn > 2000) { pair = 1; bn -= 2000; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  switch (bn) {
-    case 256: return launch_gemm<256>(p, s);
-    case 128: return launch_gemm<128>(p, s);
-    case 64: return launch_gemm<64>(p, s);
-    default: set_error("gemm: block_n must be 0/64/128/256 (got %d)", bn); return HOIGEN_ERR_INVALID;
+  if (pair) {
+    switch (bn) {
+      case 256: return launch_gemm2<256>(p, s);
+      case 192: return launch_gemm2<192>(p, s);
+      case 128: return launch_gemm2<128>(p, s);
+      default: break;
+    }
+  } else {
+    switch (bn) {
+      case 256: return launch_gemm<256>(p, s);
+      case 128: return launch_gemm<128>(p, s);
+      case 64: return launch_gemm<64>(p, s);
+      default: break;
+    }
   }
+  set_error("gemm: block_n must be 0, 64/128/256 (one CTA) or 2128/2192/2256 (CTA pair); got %d", p->block_n);
+  return HOIGEN_ERR_INVALID;
 }
 
 int hoigen_debug_gemm_simt(const hoigen_gemm_params* p, hoigen_stream_t stream) {

@@ -29,7 +29,10 @@ def _ref_gemm(a, w, bias=None, act=0, colscale=None, residual=None):
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (300, 200, 136, 0), (1000, 776, 320, 128), (2500, 2304, 768, 256),
-                                      (197 * 8, 768, 3072, 0), (5, 117, 4096, 0)])
+                                      (197 * 8, 768, 3072, 0), (5, 117, 4096, 0),
+                                      # CTA-pair (cta_group::2) kernels: 256 x {256,192,128} tiles, ragged M / N / K
+                                      (256, 256, 64, 2256), (2500, 2304, 768, 2256), (1000, 776, 320, 2192),
+                                      (197 * 9, 768, 3072, 2192), (333, 117, 4096, 2128), (12608, 512, 768, 2128)])
 def test_gemm_tcgen05_matches_fp32(cuda_device, M, N, K, bn):
     from hoigen_b200 import _cabi
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
@@ -44,8 +47,9 @@ def test_gemm_tcgen05_matches_fp32(cuda_device, M, N, K, bn):
     assert (out[:, N:] == 0).all()
 
 
+@pytest.mark.parametrize("bn", [0, 128, 2192])
 @pytest.mark.parametrize("act", [0, 1, 2])
-def test_gemm_epilogue(cuda_device, act):
+def test_gemm_epilogue(cuda_device, act, bn):
     from hoigen_b200 import _cabi
     g = torch.Generator(device="cpu").manual_seed(3 + act)
     M, N, K = 777, 776, 192
@@ -56,7 +60,7 @@ def test_gemm_epilogue(cuda_device, act):
     res = torch.randn(M, N, generator=g).to(cuda_device)
     of = res.clone()
     ob = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
-    _cabi.gemm_bf16(a, w, bias=bias, colscale=cs, act=act, residual=of, out_f32=of, out_bf16=ob)
+    _cabi.gemm_bf16(a, w, bias=bias, colscale=cs, act=act, residual=of, out_f32=of, out_bf16=ob, block_n=bn)
     ref = _ref_gemm(a, w, bias, act, cs, res)
     # fp32 epilogue; QuickGELU uses tanh.approx.f32 (rel 2^-11) because its consumer is a bf16 operand anyway
     assert (of - ref).abs().max().item() < (1e-4 if act != 1 else 4e-3)
