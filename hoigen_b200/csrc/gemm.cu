@@ -43,7 +43,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (power of two >= 32)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // [tiles][256 B barriers][2 x 2 x BN floats: double-buffered bias / colscale staging]
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN * 4;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -58,114 +59,133 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// One epilogue warp: thread = one output row, CHUNKS x 32 consecutive columns starting at colbase, accumulators at
-// TMEM address t_addr (this warp's lane quadrant). The fp32 residual of the NEXT 32-column chunk is prefetched while
-// the current chunk is processed, and the first chunk's before the accumulator is ready (wait_acc), so the latency
-// of the read-modify-write epilogue hides behind the MMAs instead of serialising with them.
-template <int CHUNKS, typename WaitFn>
-__device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int colbase, uint32_t t_addr, WaitFn wait_acc) {
+// Epilogue-warp helpers.  Thread = one output row; a warp owns CHUNKS x 32 consecutive columns of the tile.
+// Latency is the enemy here (few warps, long dependent chains), so everything that does not depend on the MMA is
+// fetched early: the tile's bias / column-scale vectors are staged once per tile in shared memory (broadcast LDS
+// instead of per-chunk global loads), the fp32 residual of chunk c+1 is prefetched while chunk c is processed (the
+// first chunk's before the accumulator is ready), and the TMEM load of chunk c+1 is in flight during chunk c.
+constexpr int EPI_THREADS = 256;
+
+// stage bias (0 if absent) and colscale (1 if absent) of columns [col_begin, col_begin + BN) ; tid in [0, 256)
+template <int BN>
+__device__ __forceinline__ void epilogue_stage_vectors(const GemmArgs& g, int col_begin, float* s_bias, float* s_cs, int tid) {
+  for (int i = tid; i < BN; i += EPI_THREADS) {
+    const int col = col_begin + i;
+    const bool ok = col < g.N;
+    s_bias[i] = (g.bias && ok) ? __ldg(g.bias + col) : 0.f;
+    s_cs[i] = (g.colscale && ok) ? __ldg(g.colscale + col) : 1.f;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
+}
+
+// Pull one row's residual segment of a tile into L2 ahead of the read-modify-write epilogue (one tile of lead): the
+// epilogue's own loads then see L2 latency instead of HBM latency, which its few bytes in flight could not cover.
+__device__ __forceinline__ void prefetch_residual_row(const GemmArgs& g, int row, int col_begin, int bn) {
+  if (g.residual == nullptr || row >= g.M || col_begin >= g.N || (g.ld_res & 3) != 0) return;
+  const int cols = min(bn, g.N - col_begin) & ~3;
+  if (cols > 0) prefetch_l2_bulk(g.residual + size_t(row) * g.ld_res + col_begin, uint32_t(cols) * 4u);
+}
+
+constexpr int CW = 16;  // columns per epilogue chunk (register budget: two chunks of accumulators + residual in flight)
+
+__device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const uint32_t (&r)[CW], const float4 (&res)[CW / 4],
+                                                       bool res_vec, const float* res_row, const float* s_bias,
+                                                       const float* s_cs, int row, bool row_ok, int col0) {
+  const bool full_chunk = (col0 + CW <= g.N);
+  float v[CW];
+#pragma unroll
+  for (int j = 0; j < CW; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(s_bias + j);
+    v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+    v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+  }
+  if (g.act != HOIGEN_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) v[j] = apply_act(v[j], g.act);
+  }
+#pragma unroll
+  for (int j = 0; j < CW; j += 4) {
+    const float4 c = *reinterpret_cast<const float4*>(s_cs + j);
+    v[j] *= c.x; v[j + 1] *= c.y; v[j + 2] *= c.z; v[j + 3] *= c.w;
+  }
+  if (!row_ok) return;
+  if (g.residual) {
+    if (res_vec && full_chunk) {
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (col0 + j < g.N) v[j] += res_row[col0 + j];
+    }
+  }
+  if (g.out_f32) {
+    float* op = g.out_f32 + size_t(row) * g.ld_f32 + col0;
+    if (full_chunk && (g.ld_f32 & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (col0 + j < g.N) op[j] = v[j];
+    }
+  }
+  if (g.out_bf16) {
+    __nv_bfloat16* op = g.out_bf16 + size_t(row) * g.ld_bf16 + col0;
+    if (full_chunk && (g.ld_bf16 & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < CW; j += 8) {
+        uint4 pk;
+        pk.x = pack_bf16x2(v[j], v[j + 1]);
+        pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(op + j) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (col0 + j < g.N) op[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+// s_bias / s_cs point at this warp's first column (colbase) inside the staged vectors. COLS = columns per warp.
+template <int COLS, typename WaitFn>
+__device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int colbase, uint32_t t_addr, const float* s_bias,
+                                              const float* s_cs, WaitFn wait_acc) {
+  constexpr int CHUNKS = COLS / CW;
   const bool row_ok = row < g.M;
   const bool res_vec = g.residual && row_ok && (g.ld_res & 3) == 0;
   const float* res_row = g.residual ? g.residual + size_t(row_ok ? row : 0) * g.ld_res : nullptr;
-  float4 res_next[8];
-  if (res_vec && colbase + 32 <= g.N) {
+  float4 res[2][CW / 4];
+  uint32_t r[2][CW];
+  if (res_vec && colbase + CW <= g.N) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
+    for (int j = 0; j < CW / 4; ++j) res[0][j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
   }
   wait_acc();
-#pragma unroll 1
+  if (colbase >= g.N) return;  // warp-uniform: nothing to do for this half
+  tmem_ld_32x32b_x16(t_addr, r[0]);
+#pragma unroll
   for (int c = 0; c < CHUNKS; ++c) {
-    const int col0 = colbase + c * 32;
-    if (col0 >= g.N) break;  // warp-uniform
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(t_addr + uint32_t(c * 32), r);
-    const bool full_chunk = (col0 + 32 <= g.N);
-    float4 res_cur[8];
+    const int col0 = colbase + c * CW;
+    tmem_wait_ld();   // chunk c is in registers
+    const bool more = (c + 1 < CHUNKS) && (col0 + CW < g.N);
+    if (more) {
+      tmem_ld_32x32b_x16(t_addr + uint32_t((c + 1) * CW), r[(c + 1) & 1]);   // in flight while chunk c is processed
+      if (res_vec && col0 + 2 * CW <= g.N) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) res_cur[j] = res_next[j];
-    if (res_vec && c + 1 < CHUNKS && col0 + 64 <= g.N) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(res_row + col0 + 32 + 4 * j);
-    }
-    tmem_wait_ld();
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (g.bias) {
-      if (full_chunk) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
+        for (int j = 0; j < CW / 4; ++j)
+          res[(c + 1) & 1][j] = *reinterpret_cast<const float4*>(res_row + col0 + CW + 4 * j);
       }
     }
-    if (g.act != HOIGEN_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
-    }
-    if (g.colscale) {
-      if (full_chunk) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(g.colscale + col0 + j));
-          v[j] *= b.x; v[j + 1] *= b.y; v[j + 2] *= b.z; v[j + 3] *= b.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < g.N) v[j] *= __ldg(g.colscale + col0 + j);
-      }
-    }
-    if (row_ok) {
-      if (g.residual) {
-        if (res_vec && full_chunk) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j] += res_cur[j].x; v[4 * j + 1] += res_cur[j].y; v[4 * j + 2] += res_cur[j].z; v[4 * j + 3] += res_cur[j].w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) v[j] += res_row[col0 + j];
-        }
-      }
-      if (g.out_f32) {
-        float* op = g.out_f32 + size_t(row) * g.ld_f32 + col0;
-        if (full_chunk && (g.ld_f32 & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) op[j] = v[j];
-        }
-      }
-      if (g.out_bf16) {
-        __nv_bfloat16* op = g.out_bf16 + size_t(row) * g.ld_bf16 + col0;
-        if (full_chunk && (g.ld_bf16 & 7) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            pk.x = pack_bf16x2(v[j], v[j + 1]);
-            pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
-            pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(op + j) = pk;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) op[j] = __float2bfloat16_rn(v[j]);
-        }
-      }
-    }
+    epilogue_process_chunk(g, r[c & 1], res[c & 1], res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0);
+    if (!more) break;
   }
+  tmem_wait_ld();
 }
 
 template <int BN>
@@ -269,14 +289,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;          // 0 / 1: which half of the tile's columns
     int it = 0;
+    if (half == 0 && int(blockIdx.x) < num_tiles)
+      prefetch_residual_row(g, (blockIdx.x / num_n) * BM + quad * 32 + lane, (blockIdx.x % num_n) * BN, BN);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int row = m_blk * BM + quad * 32 + lane;
       const int colbase = n_blk * BN + half * (BN / 2);
+      if (half == 0 && tile + int(gridDim.x) < num_tiles) {
+        const int nt = tile + gridDim.x;
+        prefetch_residual_row(g, (nt / num_n) * BM + quad * 32 + lane, (nt % num_n) * BN, BN);
+      }
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN + half * (BN / 2));
-      epilogue_warp<(BN / 2) / 32>(g, row, colbase, t_addr, [&]() {
+      float* s_bias = reinterpret_cast<float*>(tiles + STAGES * Cfg::STAGE_BYTES + 256) + (it & 1) * 2 * BN;
+      float* s_cs = s_bias + BN;
+      epilogue_stage_vectors<BN>(g, n_blk * BN, s_bias, s_cs, threadIdx.x - 64);
+      epilogue_warp<BN / 2>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
         mbar_wait(bar_tfull + 8u * acc, acc_phase);
         tc_fence_after();
       });
@@ -315,7 +344,7 @@ struct Gemm2Cfg {
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int ACC_STRIDE = 256;               // TMEM columns between the two accumulator stages
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * BN * 4;
 };
 
 template <int BN>
@@ -422,14 +451,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     int it = 0;
+    if (half == 0 && cluster_id < num_tiles)
+      prefetch_residual_row(g, (cluster_id / num_n) * (2 * BM) + int(rank) * BM + quad * 32 + lane, (cluster_id % num_n) * BN, BN);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
+      if (half == 0 && tile + num_clusters < num_tiles) {
+        const int nt = tile + num_clusters;
+        prefetch_residual_row(g, (nt / num_n) * (2 * BM) + int(rank) * BM + quad * 32 + lane, (nt % num_n) * BN, BN);
+      }
       const int row = m_blk * (2 * BM) + int(rank) * BM + quad * 32 + lane;
       const int colbase = n_blk * BN + half * (BN / 2);
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_STRIDE + half * (BN / 2));
-      epilogue_warp<(BN / 2) / 32>(g, row, colbase, t_addr, [&]() {
+      float* s_bias = reinterpret_cast<float*>(tiles + STAGES * Cfg::STAGE_BYTES + 256) + (it & 1) * 2 * BN;
+      float* s_cs = s_bias + BN;
+      epilogue_stage_vectors<BN>(g, n_blk * BN, s_bias, s_cs, threadIdx.x - 64);
+      epilogue_warp<BN / 2>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
         mbar_wait(bar_tfull + 8u * acc, acc_phase);
         tc_fence_after();
       });

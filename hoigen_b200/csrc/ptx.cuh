@@ -98,6 +98,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// fire-and-forget L2 prefetch of `bytes` (multiple of 16) contiguous bytes at a 16-byte aligned global address
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM management
 // ----------------------------------------------------------------------------------------------
