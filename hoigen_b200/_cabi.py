@@ -113,7 +113,7 @@ class EncoderWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ENCODER_WEIGHT_FIELDS]
 
 
-ENCODER_BUFFER_FIELDS = ("patches", "patch_emb", "x", "xb", "h", "qkv", "attn", "mlp", "adapter_d", "adapter_t",
+ENCODER_BUFFER_FIELDS = ("patches", "patch_emb", "x", "xb", "h", "qkv", "attn", "mlp", "delta", "adapter_d", "adapter_t",
                          "adapter_kv", "tokens_out")
 
 
@@ -148,6 +148,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_patchify_bf16": [_P, _P, _I, _P],
     "hoigen_embed_lnpre": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
     "hoigen_layernorm768": [_P, _P, _P, _P, _P, _I, _P],
+    "hoigen_add_layernorm768": [_P, _P, _P, _P, _P, _I, _P],
     "hoigen_adapter_kv": [_P, _P, _P, _P, _I, _I, _P],
     "hoigen_adapter_mid": [_P, _P, _P, C.POINTER(AdapterMidWeights), _P, _I, _I, _P],
     "hoigen_attention": [_P, _P, _I, _P],

@@ -54,11 +54,14 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
 //   EMBED = false: x = in[row]                                         -> out_bf16 (and optionally out_f32)
 //   EMBED = true : x = (t == 0 ? cls : in[b*196 + t - 1]) + pos[t]      (C:494-496), row = b*197 + t
 // ------------------------------------------------------------------------------------------------
+//   delta != nullptr (EMBED = false): x = in[row] + delta[row] (bf16), and x is written back to `stream_out` (the
+//                  deferred residual add of the preceding GEMM: X += up-proj / out-proj output)
 template <bool EMBED>
 __global__ void __launch_bounds__(256)
 layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls, const float* __restrict__ pos,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out_f32,
-                    __nv_bfloat16* __restrict__ out_bf16, int rows) {
+                    __nv_bfloat16* __restrict__ out_bf16, int rows, const __nv_bfloat16* __restrict__ delta = nullptr,
+                    float* __restrict__ stream_out = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -77,6 +80,18 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
     const float4* src = reinterpret_cast<const float4*>(in + long(row) * WIDTH);
 #pragma unroll
     for (int j = 0; j < 6; ++j) v[j] = src[lane + 32 * j];
+    if (delta) {
+      const uint2* dsrc = reinterpret_cast<const uint2*>(delta + long(row) * WIDTH);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const uint2 d = __ldg(dsrc + lane + 32 * j);
+        v[j].x += __uint_as_float(d.x << 16); v[j].y += __uint_as_float(d.x & 0xffff0000u);
+        v[j].z += __uint_as_float(d.y << 16); v[j].w += __uint_as_float(d.y & 0xffff0000u);
+      }
+      float4* dst = reinterpret_cast<float4*>(stream_out + long(row) * WIDTH);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) dst[lane + 32 * j] = v[j];
+    }
   }
   float s = 0.f;
 #pragma unroll
@@ -396,6 +411,18 @@ int hoigen_layernorm768(const float* x, const float* gamma, const float* beta, f
   KernelScope ks("layernorm768", reinterpret_cast<cudaStream_t>(stream), 0, double(rows) * WIDTH * (4 + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)));
   layernorm768_kernel<false><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, nullptr, nullptr, gamma, beta, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows);
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+int hoigen_add_layernorm768(float* x, const void* delta_bf16, const float* gamma, const float* beta, void* out_bf16,
+                            int32_t rows, hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(x && delta_bf16 && gamma && beta && out_bf16 && rows > 0, "add_layernorm768: bad arguments");
+  KernelScope ks("add_layernorm768", reinterpret_cast<cudaStream_t>(stream), 0, double(rows) * WIDTH * (4 + 2 + 4 + 2));
+  layernorm768_kernel<false><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, nullptr, nullptr, gamma, beta, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows,
+      reinterpret_cast<const __nv_bfloat16*>(delta_bf16), x);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }

@@ -61,17 +61,20 @@ int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder
     mw.norm3_w = w->ad_norm3_w + o64; mw.norm3_b = w->ad_norm3_b + o64;
     HOIGEN_TRY(hoigen_adapter_mid(buf->adapter_d, buf->adapter_kv + size_t(l) * batch * n_max * 128, mask, &mw,
                                   buf->adapter_t, batch, n_max, s));
+    // The residual adds of the two short-K GEMMs (up-proj K=64, out-proj K=768) are deferred into the LayerNorm that
+    // follows: their MMA time is too short to hide a read-modify-write epilogue on the fp32 stream, whereas the
+    // LayerNorm kernel streams the same rows anyway.
     HOIGEN_TRY(gemm(buf->adapter_t, 64, (const uint16_t*)w->ad_up_w + size_t(l) * D * 64, 64, M, D, 64,
-                    w->ad_up_b + o768, HOIGEN_ACT_NONE, w->ad_scale + o768, buf->x, D, buf->x, D, nullptr, 0, s));
-    // (2) x += out_proj(attention(ln_1(x)))
-    HOIGEN_TRY(hoigen_layernorm768(buf->x, w->ln1_w + o768, w->ln1_b + o768, nullptr, buf->h, M, s));
+                    w->ad_up_b + o768, HOIGEN_ACT_NONE, w->ad_scale + o768, nullptr, 0, nullptr, 0, buf->delta, D, s));
+    // (2) x += adapter ; x += out_proj(attention(ln_1(x)))
+    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, w->ln1_w + o768, w->ln1_b + o768, buf->h, M, s));
     HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->qkv_w + size_t(l) * 3 * D * D, D, M, 3 * D, D,
                     w->qkv_b + size_t(l) * 3 * D, HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->qkv, 3 * D, s));
     HOIGEN_TRY(hoigen_attention(buf->qkv, buf->attn, batch, s));
     HOIGEN_TRY(gemm(buf->attn, D, (const uint16_t*)w->out_w + size_t(l) * D * D, D, M, D, D, w->out_b + o768,
-                    HOIGEN_ACT_NONE, nullptr, buf->x, D, buf->x, D, nullptr, 0, s));
+                    HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->delta, D, s));
     // (3) x += c_proj(quickgelu(c_fc(ln_2(x))))  (the c_proj epilogue also emits the bf16 copy the next adapter reads)
-    HOIGEN_TRY(hoigen_layernorm768(buf->x, w->ln2_w + o768, w->ln2_b + o768, nullptr, buf->h, M, s));
+    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, w->ln2_w + o768, w->ln2_b + o768, buf->h, M, s));
     HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->fc_w + size_t(l) * 4 * D * D, D, M, 4 * D, D,
                     w->fc_b + size_t(l) * 4 * D, HOIGEN_ACT_QUICKGELU, nullptr, nullptr, 0, nullptr, 0, buf->mlp, 4 * D, s));
     HOIGEN_TRY(gemm(buf->mlp, 4 * D, (const uint16_t*)w->proj_w + size_t(l) * D * 4 * D, 4 * D, M, D, 4 * D,

@@ -94,6 +94,10 @@ HOIGEN_API int hoigen_embed_lnpre(const float* patch_emb, const float* class_emb
 /* LayerNorm over 768 columns, fp32 statistics, eps 1e-5 (C:409-415) -> bf16 and/or fp32 */
 HOIGEN_API int hoigen_layernorm768(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
                                    int32_t rows, hoigen_stream_t stream);
+/* x += delta (bf16) in place on the fp32 residual stream, then LayerNorm(x) -> bf16: the residual adds of
+ * C:456 (x + adapter) and C:457 (x + attention) deferred from the producing GEMM into the LayerNorm that follows. */
+HOIGEN_API int hoigen_add_layernorm768(float* x, const void* delta_bf16, const float* gamma, const float* beta,
+                                       void* out_bf16, int32_t rows, hoigen_stream_t stream);
 /* Adapter cross-attention K/V of the prior tokens for all layers: kv[l][tok][0:64]=K, [64:128]=V  (C:63-66).
  * in_proj_w (layers,192,64) rows [q;k;v], in_proj_b (layers,192); prior (tokens,64). */
 HOIGEN_API int hoigen_adapter_kv(const float* prior, const float* in_proj_w, const float* in_proj_b, float* kv,
@@ -157,6 +161,7 @@ typedef struct {            /* caller-owned workspace, M = B*197 */
   void* qkv;                /* bf16 (M, 2304) */
   void* attn;               /* bf16 (M, 768) */
   void* mlp;                /* bf16 (M, 3072) */
+  void* delta;              /* bf16 (M, 768)   adapter up-proj / attention out-proj output awaiting its residual add */
   float* adapter_d;         /* f32  (M, 64) */
   void* adapter_t;          /* bf16 (M, 64) */
   float* adapter_kv;        /* f32  (12, B*n_max, 128) */
