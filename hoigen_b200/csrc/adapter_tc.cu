@@ -1,0 +1,368 @@
+// InsAdapter bottleneck body on the tensor cores: one CTA per 128-token tile, thread = token row.
+//
+//   q  = D Wq^T + bq                         UMMA 128x64x64   (D = relu(down_proj(x)) as bf16 tile, TMA-loaded)
+//   a  = softmax_2heads(q K^T / sqrt(32)) V  registers; K/V (<= 32 unmasked prior tokens of the tile's <= 2 images) in smem
+//   t  = LN_norm2(D + a Wo^T + bo)           UMMA 128x64x64   + per-thread LayerNorm over 64 registers
+//   h  = relu(t W1^T + b1)                   UMMA 128x128x64
+//   o  = LN_norm3(t + h W2^T + b2)           UMMA 128x64x128  -> bf16 (M,64), the A operand of the up-proj GEMM
+//
+// Accumulators live in TMEM (128 columns); between the four MMAs the activations make a register round trip
+// (tcgen05.ld -> fp32 math -> bf16 -> 128B-swizzled smem A tile). Row-per-thread ownership makes both LayerNorms and
+// the cross-attention shuffle-free.
+//
+// Reference: Adapter.forward CLIP_models_adapter_prior2.py:186-200 with TransformerDecoderLayer.forward_post :51-72
+// (multihead_attn with key_padding_mask, norm2, linear1/relu/linear2, norm3; dropout off in eval).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace hoigen {
+
+constexpr int AT_TOKENS = 197;
+constexpr int AT_THREADS = 128;
+constexpr int AT_MAXKEYS = 32;
+// shared memory map (bytes, every tile 1024-aligned)
+constexpr int AT_A0 = 0;          // 16 KiB  D tile, later the t tile          [128 rows x 64 k]
+constexpr int AT_A1 = 16384;      // 16 KiB  attention output tile
+constexpr int AT_P = 32768;       // 32 KiB  hidden tile, two k-atoms           [128 x 128]
+constexpr int AT_WQ = 65536;      //  8 KiB  [64 n x 64 k]
+constexpr int AT_WO = 73728;      //  8 KiB
+constexpr int AT_W1 = 81920;      // 16 KiB  [128 n x 64 k]
+constexpr int AT_W2 = 98304;      // 16 KiB  two k-atoms of [64 n x 64 k]
+constexpr int AT_KV = 114688;     // 32 KiB  fp32 [2 images][32 keys][K 64 | V 64]
+constexpr int AT_MISC = 147456;   // barriers, tmem slot, key counts
+constexpr int AT_SMEM_BYTES = AT_MISC + 512 + 1024;
+constexpr int AT_TMEM_COLS = 128;
+
+struct AdapterTcArgs {
+  const float* d_f32;        // (M,64) fp32 copy of D for the residual
+  const float* kv;           // (B*n_max,128) this layer
+  const uint8_t* mask;       // (B,n_max) 1 = padding
+  const float* bq;           // in_proj bias (q part = first 64)
+  const float* bo; const float* b1; const float* b2;
+  const float* n2_w; const float* n2_b; const float* n3_w; const float* n3_b;
+  __nv_bfloat16* out;        // (M,64)
+  int M, n_max, batch;
+};
+
+template <int NVALS>
+__device__ __forceinline__ void store_row_bf16(uint8_t* tile, int row, int chunk0, const float (&v)[NVALS]) {
+  // v[0..NVALS) -> 16-byte chunks chunk0.. of `row` in a 128B-swizzled tile (NVALS multiple of 8)
+#pragma unroll
+  for (int c = 0; c < NVALS / 8; ++c) {
+    uint4 pk;
+    pk.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+    pk.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    pk.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+    pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    *reinterpret_cast<uint4*>(tile + sw128_offset(row, chunk0 + c)) = pk;
+  }
+}
+
+// LayerNorm over 64 per-thread values (eps 1e-5), affine from global (L1-broadcast)
+__device__ __forceinline__ void ln64_regs(float (&v)[64], const float* __restrict__ gamma, const float* __restrict__ beta) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s += v[i];
+  const float mean = s * (1.0f / 64);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(q * (1.0f / 64) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 64; i += 4) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i));
+    v[i] = (v[i] - mean) * rstd * g.x + b.x;
+    v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
+    v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z;
+    v[i + 3] = (v[i + 3] - mean) * rstd * g.w + b.w;
+  }
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmWq,
+                  const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmW1,
+                  const __grid_constant__ CUtensorMap tmW2, AdapterTcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AT_MISC);
+  const uint32_t bar_ld = smem_u32(bars);
+  const uint32_t bar_mma = bar_ld + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  int* s_nkeys = reinterpret_cast<int*>(bars + 3);           // [2]
+  int* s_keyidx = s_nkeys + 2;                               // [2][32]
+  float* sKV = reinterpret_cast<float*>(sm + AT_KV);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = blockIdx.x * 128;
+  const int row = r0 + tid;
+  const bool row_ok = row < g.M;
+  const int b0 = r0 / AT_TOKENS;
+  const int b1 = min(r0 + 127, g.M - 1) / AT_TOKENS;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmD); tma_prefetch_desc(&tmWq); tma_prefetch_desc(&tmWo);
+    tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), AT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  // compact the unmasked prior tokens of the (at most two) images this tile touches   (key_padding_mask, C:66)
+  if (warp >= 2) {
+    const int img = warp - 2;
+    const int b = img == 0 ? b0 : b1;
+    const bool valid = lane < g.n_max && g.mask[b * g.n_max + lane] == 0;
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (valid) s_keyidx[img * AT_MAXKEYS + __popc(m & ((1u << lane) - 1u))] = lane;
+    if (lane == 0) s_nkeys[img] = __popc(m);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_ld, 16384 + 8192 + 8192 + 16384 + 16384);
+    tma_load_2d(base + AT_A0, &tmD, bar_ld, 0, r0);
+    tma_load_2d(base + AT_WQ, &tmWq, bar_ld, 0, 0);
+    tma_load_2d(base + AT_WO, &tmWo, bar_ld, 0, 0);
+    tma_load_2d(base + AT_W1, &tmW1, bar_ld, 0, 0);
+    tma_load_2d(base + AT_W2, &tmW2, bar_ld, 0, 0);
+    tma_load_2d(base + AT_W2 + 8192, &tmW2, bar_ld, 64, 0);
+  }
+  // stage K | V rows of the compacted keys (fp32) while the TMA loads fly
+  for (int img = 0; img < 2; ++img) {
+    const int b = img == 0 ? b0 : b1;
+    const int n = s_nkeys[img];
+    for (int i = tid; i < n * 32; i += AT_THREADS) {
+      const int j = i >> 5, c4 = i & 31;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g.kv + (size_t(b) * g.n_max + s_keyidx[img * AT_MAXKEYS + j]) * 128) + c4);
+      reinterpret_cast<float4*>(sKV + (img * AT_MAXKEYS + j) * 128)[c4] = v;
+    }
+  }
+  __syncthreads();
+
+  uint32_t mma_phase = 0;
+  // ---------------- MMA 1: q = D Wq^T ----------------
+  if (tid == 0) {
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16_ss(tmem, make_sdesc_sw128(base + AT_A0 + k * 32), make_sdesc_sw128(base + AT_WQ + k * 32), idesc, k > 0);
+    tc_commit(bar_mma);
+  }
+  mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  tc_fence_after();
+  const uint32_t t_row = tmem + (uint32_t(warp * 32) << 16);
+
+  // ---------------- cross-attention, one head at a time ----------------
+  {
+    const int img = (row_ok ? row : g.M - 1) / AT_TOKENS == b0 ? 0 : 1;
+    const int n = s_nkeys[img];
+    const float* kvb = sKV + img * AT_MAXKEYS * 128;
+    const float qscale = 0.17677669529663687f;  // 32^-0.5
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_row + h * 32, r);
+      tmem_wait_ld();
+      float q[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) q[i] = (__uint_as_float(r[i]) + __ldg(g.bq + h * 32 + i)) * qscale;
+      float s[AT_MAXKEYS];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < AT_MAXKEYS; ++j) {
+        s[j] = -INFINITY;
+        if (j < n) {
+          const float4* kr = reinterpret_cast<const float4*>(kvb + j * 128 + h * 32);
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 kk = kr[c];
+            acc = fmaf(q[4 * c], kk.x, acc); acc = fmaf(q[4 * c + 1], kk.y, acc);
+            acc = fmaf(q[4 * c + 2], kk.z, acc); acc = fmaf(q[4 * c + 3], kk.w, acc);
+          }
+          s[j] = acc;
+          mx = fmaxf(mx, acc);
+        }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < AT_MAXKEYS; ++j) {
+        s[j] = (j < n) ? __expf(s[j] - mx) : 0.f;
+        sum += s[j];
+      }
+      const float inv = 1.0f / sum;   // n == 0: 0 * inf = NaN below, as in the reference (all keys masked)
+      float a[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < AT_MAXKEYS; ++j) {
+        if (j < n) {
+          const float4* vr = reinterpret_cast<const float4*>(kvb + j * 128 + 64 + h * 32);
+          const float p = s[j];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 vv = vr[c];
+            a[4 * c] = fmaf(p, vv.x, a[4 * c]); a[4 * c + 1] = fmaf(p, vv.y, a[4 * c + 1]);
+            a[4 * c + 2] = fmaf(p, vv.z, a[4 * c + 2]); a[4 * c + 3] = fmaf(p, vv.w, a[4 * c + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a[i] *= inv;
+      store_row_bf16<32>(sm + AT_A1, tid, h * 4, a);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  // ---------------- MMA 2: a Wo^T ; t = LN2(D + . + bo) ----------------
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16_ss(tmem, make_sdesc_sw128(base + AT_A1 + k * 32), make_sdesc_sw128(base + AT_WO + k * 32), idesc, k > 0);
+    tc_commit(bar_mma);
+  }
+  float t[64];
+  {
+    // residual D (fp32) for this row while the MMA runs
+    const float4* dsrc = reinterpret_cast<const float4*>(g.d_f32 + size_t(row_ok ? row : 0) * 64);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 d = __ldg(dsrc + i);
+      t[4 * i] = d.x; t[4 * i + 1] = d.y; t[4 * i + 2] = d.z; t[4 * i + 3] = d.w;
+    }
+  }
+  mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  tc_fence_after();
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + hh * 32, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[hh * 32 + i] += __uint_as_float(r[i]) + __ldg(g.bo + hh * 32 + i);
+  }
+  ln64_regs(t, g.n2_w, g.n2_b);
+  store_row_bf16<64>(sm + AT_A0, tid, 0, t);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  // ---------------- MMA 3: hidden = relu(t W1^T + b1) ----------------
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16_ss(tmem, make_sdesc_sw128(base + AT_A0 + k * 32), make_sdesc_sw128(base + AT_W1 + k * 32), idesc, k > 0);
+    tc_commit(bar_mma);
+  }
+  mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + c * 32, r);
+    tmem_wait_ld();
+    float hv[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) hv[i] = fmaxf(__uint_as_float(r[i]) + __ldg(g.b1 + c * 32 + i), 0.f);
+    store_row_bf16<32>(sm + AT_P + (c >> 1) * 16384, tid, (c & 1) * 4, hv);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  // ---------------- MMA 4: hidden W2^T ; out = LN3(t + . + b2) ----------------
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      umma_bf16_ss(tmem, make_sdesc_sw128(base + AT_P + (k >> 2) * 16384 + (k & 3) * 32),
+                   make_sdesc_sw128(base + AT_W2 + (k >> 2) * 8192 + (k & 3) * 32), idesc, k > 0);
+    tc_commit(bar_mma);
+  }
+  mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  tc_fence_after();
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + hh * 32, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[hh * 32 + i] += __uint_as_float(r[i]) + __ldg(g.b2 + hh * 32 + i);
+  }
+  ln64_regs(t, g.n3_w, g.n3_b);
+  if (row_ok) {
+    uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(row) * 64);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 pk;
+      pk.x = pack_bf16x2(t[8 * c], t[8 * c + 1]);
+      pk.y = pack_bf16x2(t[8 * c + 2], t[8 * c + 3]);
+      pk.z = pack_bf16x2(t[8 * c + 4], t[8 * c + 5]);
+      pk.w = pack_bf16x2(t[8 * c + 6], t[8 * c + 7]);
+      dst[c] = pk;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, AT_TMEM_COLS);
+  }
+}
+
+}  // namespace hoigen
+
+extern "C" {
+
+int hoigen_adapter_mid(const float* d_f32, const void* d_bf16, const float* kv_layer, const uint8_t* mask,
+                       const hoigen_adapter_mid_weights* w, void* out_bf16, int32_t batch, int32_t n_max,
+                       hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(d_f32 && d_bf16 && kv_layer && mask && w && out_bf16 && batch > 0, "adapter_mid: bad arguments");
+  HOIGEN_CHECK_ARG(w->wq && w->wo && w->w1 && w->w2, "adapter_mid: null weight");
+  HOIGEN_CHECK_ARG(n_max > 0 && n_max <= AT_MAXKEYS, "adapter_mid: n_max must be in [1,%d] (got %d)", AT_MAXKEYS, n_max);
+  static bool attr_set = false;
+  if (!attr_set) {
+    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(adapter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int M = batch * AT_TOKENS;
+  const CUtensorMap* td = get_tmap_2d_bf16(d_bf16, 64, uint64_t(M), 128, 64, 128);
+  const CUtensorMap* tq = get_tmap_2d_bf16(w->wq, 64, 64, 128, 64, 64);
+  const CUtensorMap* to = get_tmap_2d_bf16(w->wo, 64, 64, 128, 64, 64);
+  const CUtensorMap* t1 = get_tmap_2d_bf16(w->w1, 64, 128, 128, 64, 128);
+  const CUtensorMap* t2 = get_tmap_2d_bf16(w->w2, 128, 64, 256, 64, 64);
+  if (!td || !tq || !to || !t1 || !t2) return HOIGEN_ERR_CUDA;
+  AdapterTcArgs a;
+  a.d_f32 = d_f32; a.kv = kv_layer; a.mask = mask;
+  a.bq = w->in_proj_b; a.bo = w->out_proj_b; a.b1 = w->linear1_b; a.b2 = w->linear2_b;
+  a.n2_w = w->norm2_w; a.n2_b = w->norm2_b; a.n3_w = w->norm3_w; a.n3_b = w->norm3_b;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  a.M = M; a.n_max = n_max; a.batch = batch;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  KernelScope ks("adapter_mid", s, 2.0 * M * (64 * 64 * 2 + 2 * 64 * 128 + 2 * 64 * n_max), double(M) * 64 * (4 + 2 + 2));
+  adapter_tc_kernel<<<(M + 127) / 128, AT_THREADS, AT_SMEM_BYTES, s>>>(*td, *tq, *to, *t1, *t2, a);
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+}  // extern "C"

@@ -50,16 +50,17 @@ int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder
     const size_t o768 = size_t(l) * D, o64 = size_t(l) * 64;
     // (1) adapter: down-proj + ReLU (tensor cores) -> bottleneck body (SIMT) -> up-proj * scale + residual
     HOIGEN_TRY(gemm(buf->xb, D, (const uint16_t*)w->ad_down_w + size_t(l) * 64 * D, D, M, 64, D, w->ad_down_b + o64,
-                    HOIGEN_ACT_RELU, nullptr, nullptr, 0, buf->adapter_d, 64, nullptr, 0, s));
+                    HOIGEN_ACT_RELU, nullptr, nullptr, 0, buf->adapter_d, 64, buf->adapter_db, 64, s));
     hoigen_adapter_mid_weights mw;
-    mw.packed = w->ad_mid_packed + size_t(l) * HOIGEN_ADAPTER_MID_PACKED_WORDS;
+    mw.wq = (const uint16_t*)w->ad_wq + size_t(l) * 64 * 64; mw.wo = (const uint16_t*)w->ad_wo + size_t(l) * 64 * 64;
+    mw.w1 = (const uint16_t*)w->ad_w1 + size_t(l) * 128 * 64; mw.w2 = (const uint16_t*)w->ad_w2 + size_t(l) * 64 * 128;
     mw.in_proj_b = w->ad_in_proj_b + size_t(l) * 192;
     mw.out_proj_b = w->ad_out_proj_b + o64;
     mw.linear1_b = w->ad_linear1_b + size_t(l) * 128;
     mw.linear2_b = w->ad_linear2_b + o64;
     mw.norm2_w = w->ad_norm2_w + o64; mw.norm2_b = w->ad_norm2_b + o64;
     mw.norm3_w = w->ad_norm3_w + o64; mw.norm3_b = w->ad_norm3_b + o64;
-    HOIGEN_TRY(hoigen_adapter_mid(buf->adapter_d, buf->adapter_kv + size_t(l) * batch * n_max * 128, mask, &mw,
+    HOIGEN_TRY(hoigen_adapter_mid(buf->adapter_d, buf->adapter_db, buf->adapter_kv + size_t(l) * batch * n_max * 128, mask, &mw,
                                   buf->adapter_t, batch, n_max, s));
     // The residual adds of the two short-K GEMMs (up-proj K=64, out-proj K=768) are deferred into the LayerNorm that
     // follows: their MMA time is too short to hide a read-modify-write epilogue on the fp32 stream, whereas the

@@ -20,20 +20,6 @@ TOKENS = 197
 MAX_PRIOR_TOKENS = 32
 
 
-def pack_adapter_mid(in_proj_w: torch.Tensor, out_proj_w: torch.Tensor, linear1_w: torch.Tensor,
-                     linear2_w: torch.Tensor) -> torch.Tensor:
-    """Shared-memory image of the adapter body's four matrices for hoigen_adapter_mid (see the layout in
-    include/hoigen_b200.h): transposed to [input][output], inputs (i, i+half) packed as a bf16 pair per 32-bit word.
-    -> int32 tensor (12288,)."""
-    def pair(wt: torch.Tensor, half: int) -> torch.Tensor:      # wt: [in][out] fp32
-        bits = wt.detach().float().bfloat16().contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
-        return (bits[:half] | (bits[half:2 * half] << 16)).reshape(-1)
-    parts = [pair(in_proj_w[:64].t(), 32), pair(out_proj_w.t(), 32), pair(linear1_w.t(), 32), pair(linear2_w.t(), 64)]
-    out = torch.cat(parts).to(torch.int32).contiguous()
-    assert out.numel() == 12288
-    return out
-
-
 class _ParamBag(nn.Module):
     """A module that only holds parameters (keeps the reference's dotted state_dict names)."""
 
@@ -174,8 +160,9 @@ class VisionTransformer(nn.Module):
             "ad_scale": f32(st(lambda b: b.adaptermlp.scale)),
             "ad_in_proj_w": f32(st(lambda b: dl(b).multihead_attn.in_proj_weight)),
             "ad_in_proj_b": f32(st(lambda b: dl(b).multihead_attn.in_proj_bias)),
-            "ad_mid_packed": torch.stack([pack_adapter_mid(dl(b).multihead_attn.in_proj_weight, dl(b).multihead_attn.out_proj.weight,
-                                                           dl(b).linear1.weight, dl(b).linear2.weight) for b in blocks]).to(dev).contiguous(),
+            "ad_wq": bf(st(lambda b: dl(b).multihead_attn.in_proj_weight[:64])),
+            "ad_wo": bf(st(lambda b: dl(b).multihead_attn.out_proj.weight)),
+            "ad_w1": bf(st(lambda b: dl(b).linear1.weight)), "ad_w2": bf(st(lambda b: dl(b).linear2.weight)),
             "ad_out_proj_b": f32(st(lambda b: dl(b).multihead_attn.out_proj.bias)),
             "ad_linear1_b": f32(st(lambda b: dl(b).linear1.bias)),
             "ad_linear2_b": f32(st(lambda b: dl(b).linear2.bias)),
@@ -199,7 +186,7 @@ class VisionTransformer(nn.Module):
             b = {
                 "patches": e((batch * 196, 768), bf), "patch_emb": e((batch * 196, 768), f32),
                 "x": e((M, 768), f32), "xb": e((M, 768), bf), "h": e((M, 768), bf), "qkv": e((M, 2304), bf),
-                "attn": e((M, 768), bf), "mlp": e((M, 3072), bf), "delta": e((M, 768), bf), "adapter_d": e((M, 64), f32),
+                "attn": e((M, 768), bf), "mlp": e((M, 3072), bf), "delta": e((M, 768), bf), "adapter_d": e((M, 64), f32), "adapter_db": e((M, 64), bf),
                 "adapter_t": e((M, 64), bf), "adapter_kv": e((12, batch * n_max, 128), f32),
                 "tokens_out": e((M, 512), f32),
             }

@@ -103,23 +103,21 @@ HOIGEN_API int hoigen_add_layernorm768(float* x, const void* delta_bf16, const f
 HOIGEN_API int hoigen_adapter_kv(const float* prior, const float* in_proj_w, const float* in_proj_b, float* kv,
                                  int32_t tokens, int32_t layers, hoigen_stream_t stream);
 
-#define HOIGEN_ADAPTER_MID_PACKED_WORDS 12288
 typedef struct {
-  /* bf16-pair image of the four 64-wide matrices, transposed to [input][output]; word = (W[i][o], W[i+half][o]):
-   *   [0,2048)      q rows of in_proj (64x64):  i<32, half=32     [2048,4096)  out_proj (64x64): i<32, half=32
-   *   [4096,8192)   linear1 (64 in, 128 out):   i<32, half=32     [8192,12288) linear2 (128 in, 64 out): i<64, half=64
-   * built by hoigen_b200/encoder.py::pack_adapter_mid at weight-packing time; 16-byte aligned. */
-  const uint32_t* packed;
+  const void* wq;          /* bf16 (64,64)   q rows of multihead_attn.in_proj_weight */
+  const void* wo;          /* bf16 (64,64)   multihead_attn.out_proj.weight */
+  const void* w1;          /* bf16 (128,64)  linear1.weight */
+  const void* w2;          /* bf16 (64,128)  linear2.weight */
   const float* in_proj_b;  /* (192) multihead_attn.in_proj_bias (q part used here) */
   const float* out_proj_b; /* (64) */
   const float* linear1_b;  /* (128) */
   const float* linear2_b;  /* (64) */
   const float* norm2_w; const float* norm2_b; const float* norm3_w; const float* norm3_b; /* (64) */
 } hoigen_adapter_mid_weights;
-/* Adapter bottleneck body for one layer, Adapter.forward C:186-200 / forward_post C:51-72:
- * d = relu(down_proj(x)) (B*197,64) fp32 -> LN3(t + FFN(t)), t = LN2(d + MHA_2h(d, prior, mask)) -> bf16 (B*197,64).
- * kv_layer (B*n_max,128) from hoigen_adapter_kv; mask (B,n_max) uint8, 1 = padding. n_max <= 32. */
-HOIGEN_API int hoigen_adapter_mid(const float* d, const float* kv_layer, const uint8_t* mask,
+/* Adapter bottleneck body for one layer on the tensor cores, Adapter.forward C:186-200 / forward_post C:51-72:
+ * d = relu(down_proj(x)) given as fp32 (B*197,64) and bf16 (B*197,64) -> LN3(t + FFN(t)), t = LN2(d + MHA_2h(d, prior, mask))
+ * -> bf16 (B*197,64). kv_layer (B*n_max,128) from hoigen_adapter_kv; mask (B,n_max) uint8, 1 = padding. n_max <= 32. */
+HOIGEN_API int hoigen_adapter_mid(const float* d_f32, const void* d_bf16, const float* kv_layer, const uint8_t* mask,
                                   const hoigen_adapter_mid_weights* w, void* out_bf16, int32_t batch, int32_t n_max,
                                   hoigen_stream_t stream);
 /* 12-head attention over 197 tokens (tcgen05): qkv bf16 (B*197, 2304) = [q|k|v] -> out bf16 (B*197, 768). C:443-445 */
@@ -145,7 +143,8 @@ typedef struct {
   const void* ad_up_w; const float* ad_up_b;      /* bf16 (12,768,64), (12,768) adaptermlp.up_proj.* */
   const float* ad_scale;                          /* (12,768)                   adaptermlp.scale */
   const float* ad_in_proj_w; const float* ad_in_proj_b;    /* (12,192,64), (12,192)  mhsa_layers.0.multihead_attn */
-  const uint32_t* ad_mid_packed;                           /* (12, 12288) see hoigen_adapter_mid_weights.packed */
+  const void* ad_wq; const void* ad_wo;                    /* bf16 (12,64,64) each: q rows of in_proj, out_proj */
+  const void* ad_w1; const void* ad_w2;                    /* bf16 (12,128,64), (12,64,128): linear1, linear2 */
   const float* ad_out_proj_b;                              /* (12,64) */
   const float* ad_linear1_b;                               /* (12,128) */
   const float* ad_linear2_b;                               /* (12,64) */
@@ -162,7 +161,8 @@ typedef struct {            /* caller-owned workspace, M = B*197 */
   void* attn;               /* bf16 (M, 768) */
   void* mlp;                /* bf16 (M, 3072) */
   void* delta;              /* bf16 (M, 768)   adapter up-proj / attention out-proj output awaiting its residual add */
-  float* adapter_d;         /* f32  (M, 64) */
+  float* adapter_d;         /* f32  (M, 64)    relu(down_proj(x)) */
+  void* adapter_db;         /* bf16 (M, 64)    same, as the tensor-core operand */
   void* adapter_t;          /* bf16 (M, 64) */
   float* adapter_kv;        /* f32  (12, B*n_max, 128) */
   float* tokens_out;        /* f32  (M, 512)   OUTPUT: ln_post(x) @ proj for all tokens; row b*197 = feat_global[b],

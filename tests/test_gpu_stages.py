@@ -160,17 +160,16 @@ def test_adapter_kv_and_mid(cuda_device, enc_state):
     kv_ref = torch.nn.functional.linear(prior, enc_state[blk + "multihead_attn.in_proj_weight"][64:],
                                         enc_state[blk + "multihead_attn.in_proj_bias"][64:]).view(B * n_max, 128)
     assert (kv[0].cpu() - kv_ref).abs().max().item() < 1e-5
-    from hoigen_b200.encoder import pack_adapter_mid
-    packed = pack_adapter_mid(w[0], w[2], w[4], w[6]).to(cuda_device)
+    wb = [w[0][:64].bfloat16().contiguous(), w[2].bfloat16().contiguous(), w[4].bfloat16().contiguous(), w[6].bfloat16().contiguous()]
     mw = _cabi.AdapterMidWeights()
-    mw.packed = packed.data_ptr()
-    for f, t in zip(("in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w", "norm2_b", "norm3_w", "norm3_b"),
-                    (w[1], w[3], w[5], w[7], w[8], w[9], w[10], w[11])):
+    for f, t in zip(("wq", "wo", "w1", "w2", "in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w", "norm2_b",
+                     "norm3_w", "norm3_b"), (*wb, w[1], w[3], w[5], w[7], w[8], w[9], w[10], w[11])):
         setattr(mw, f, t.data_ptr())
     out = torch.zeros(B * 197, 64, device=cuda_device, dtype=torch.bfloat16)
     dd = d.to(cuda_device).contiguous()
     m8 = mask.to(cuda_device).view(torch.uint8).contiguous()
-    _cabi.call("hoigen_adapter_mid", dd.data_ptr(), kv.data_ptr(), m8.data_ptr(), C.byref(mw), out.data_ptr(), B, n_max)
+    db = dd.bfloat16().contiguous()
+    _cabi.call("hoigen_adapter_mid", dd.data_ptr(), db.data_ptr(), kv.data_ptr(), m8.data_ptr(), C.byref(mw), out.data_ptr(), B, n_max)
     # oracle: the same sub-graph of adapter_forward, starting from `down`
     sd = enc_state
     t2 = O._mha(d, prior, prior, sd[blk + "multihead_attn.in_proj_weight"], sd[blk + "multihead_attn.in_proj_bias"],
@@ -180,7 +179,8 @@ def test_adapter_kv_and_mid(cuda_device, enc_state):
                                     sd[blk + "linear2.weight"], sd[blk + "linear2.bias"])
     ref = O._ln(t + t2, sd[blk + "norm3.weight"], sd[blk + "norm3.bias"]).view(B * 197, 64)
     err = (out.float().cpu() - ref).abs().max().item()
-    assert err < 2 ** -7 * ref.abs().max().item() + 1e-4, err     # fp32 math, one bf16 rounding at the output
+    # bf16 tensor-core operands (weights + activations between the four MMAs), fp32 accumulation / softmax / LayerNorm
+    assert err < 3e-2 * max(1.0, ref.abs().max().item()), err
 
 
 def test_encoder_matches_oracle_and_golden(cuda_device, enc_state):
