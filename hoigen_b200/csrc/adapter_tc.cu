@@ -1,4 +1,5 @@
-// InsAdapter bottleneck body on the tensor cores: one CTA per 128-token tile, thread = token row.
+// InsAdapter bottleneck body on the tensor cores: one CTA per 128-token tile, two threads per token row
+// (one per attention head / column half).
 //
 //   q  = D Wq^T + bq                         UMMA 128x64x64   (D = relu(down_proj(x)) as bf16 tile, TMA-loaded)
 //   a  = softmax_2heads(q K^T / sqrt(32)) V  registers; K/V (<= 32 unmasked prior tokens of the tile's <= 2 images) in smem
@@ -18,7 +19,7 @@
 namespace hoigen {
 
 constexpr int AT_TOKENS = 197;
-constexpr int AT_THREADS = 128;
+constexpr int AT_THREADS = 256;
 constexpr int AT_MAXKEYS = 32;
 // shared memory map (bytes, every tile 1024-aligned)
 constexpr int AT_A0 = 0;          // 16 KiB  D tile, later the t tile          [128 rows x 64 k]
@@ -30,7 +31,7 @@ constexpr int AT_W1 = 81920;      // 16 KiB  [128 n x 64 k]
 constexpr int AT_W2 = 98304;      // 16 KiB  two k-atoms of [64 n x 64 k]
 constexpr int AT_KV = 114688;     // 32 KiB  fp32 [2 images][32 keys][K 64 | V 64]
 constexpr int AT_MISC = 147456;   // barriers, tmem slot, key counts
-constexpr int AT_SMEM_BYTES = AT_MISC + 512 + 1024;
+constexpr int AT_SMEM_BYTES = AT_MISC + 512 + 2048 + 1024;
 constexpr int AT_TMEM_COLS = 128;
 
 struct AdapterTcArgs {
@@ -58,20 +59,26 @@ __device__ __forceinline__ void store_row_bf16(uint8_t* tile, int row, int chunk
   }
 }
 
-// LayerNorm over 64 per-thread values (eps 1e-5), affine from global (L1-broadcast)
-__device__ __forceinline__ void ln64_regs(float (&v)[64], const float* __restrict__ gamma, const float* __restrict__ beta) {
+// LayerNorm over a 64-wide row held by TWO threads (32 values each; partner = same row, other column half).
+// Partial sums are exchanged through shared memory: red[half][row].
+__device__ __forceinline__ void ln64_pair(float (&v)[32], int half, int rrow, float* red, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) s += v[i];
-  const float mean = s * (1.0f / 64);
+  for (int i = 0; i < 32; ++i) s += v[i];
+  red[half * 128 + rrow] = s;
+  __syncthreads();
+  const float mean = (s + red[(half ^ 1) * 128 + rrow]) * (1.0f / 64);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(q * (1.0f / 64) + 1e-5f);
+  for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+  red[256 + half * 128 + rrow] = q;
+  __syncthreads();
+  const float rstd = rsqrtf((q + red[256 + (half ^ 1) * 128 + rrow]) * (1.0f / 64) + 1e-5f);
 #pragma unroll
-  for (int i = 0; i < 64; i += 4) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i));
+  for (int i = 0; i < 32; i += 4) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + half * 32 + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + half * 32 + i));
     v[i] = (v[i] - mean) * rstd * g.x + b.x;
     v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
     v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z;
@@ -93,11 +100,16 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   int* s_nkeys = reinterpret_cast<int*>(bars + 3);           // [2]
   int* s_keyidx = s_nkeys + 2;                               // [2][32]
+  float* red = reinterpret_cast<float*>(sm + AT_MISC + 512); // [2][2][128] LayerNorm partials
   float* sKV = reinterpret_cast<float*>(sm + AT_KV);
 
+  // 8 warps: warp w and w+4 share TMEM lane quadrant (w & 3) = the same 32 rows; `half` selects the column half
+  // (the attention head, 32 of the 64 bottleneck channels, 64 of the 128 hidden channels).
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
+  const int rrow = (warp & 3) * 32 + lane;      // row within the tile
   const int r0 = blockIdx.x * 128;
-  const int row = r0 + tid;
+  const int row = r0 + rrow;
   const bool row_ok = row < g.M;
   const int b0 = r0 / AT_TOKENS;
   const int b1 = min(r0 + 127, g.M - 1) / AT_TOKENS;
@@ -115,7 +127,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
     tmem_relinquish();
   }
   // compact the unmasked prior tokens of the (at most two) images this tile touches   (key_padding_mask, C:66)
-  if (warp >= 2) {
+  if (warp == 2 || warp == 3) {
     const int img = warp - 2;
     const int b = img == 0 ? b0 : b1;
     const bool valid = lane < g.n_max && g.mask[b * g.n_max + lane] == 0;
@@ -162,67 +174,68 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
   }
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
   tc_fence_after();
-  const uint32_t t_row = tmem + (uint32_t(warp * 32) << 16);
+  const uint32_t t_row = tmem + (uint32_t((warp & 3) * 32) << 16);
 
-  // ---------------- cross-attention, one head at a time ----------------
+  // ---------------- cross-attention: this thread's head (= half) of its row ----------------
   {
     const int img = (row_ok ? row : g.M - 1) / AT_TOKENS == b0 ? 0 : 1;
     const int n = s_nkeys[img];
     const float* kvb = sKV + img * AT_MAXKEYS * 128;
     const float qscale = 0.17677669529663687f;  // 32^-0.5
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_row + h * 32, r);
-      tmem_wait_ld();
-      float q[32];
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + half * 32, r);
+    tmem_wait_ld();
+    float q[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) q[i] = (__uint_as_float(r[i]) + __ldg(g.bq + h * 32 + i)) * qscale;
-      float s[AT_MAXKEYS];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < AT_MAXKEYS; ++j) {
-        s[j] = -INFINITY;
-        if (j < n) {
-          const float4* kr = reinterpret_cast<const float4*>(kvb + j * 128 + h * 32);
-          float acc = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 kk = kr[c];
-            acc = fmaf(q[4 * c], kk.x, acc); acc = fmaf(q[4 * c + 1], kk.y, acc);
-            acc = fmaf(q[4 * c + 2], kk.z, acc); acc = fmaf(q[4 * c + 3], kk.w, acc);
-          }
-          s[j] = acc;
-          mx = fmaxf(mx, acc);
-        }
-      }
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < AT_MAXKEYS; ++j) {
-        s[j] = (j < n) ? __expf(s[j] - mx) : 0.f;
-        sum += s[j];
-      }
-      const float inv = 1.0f / sum;   // n == 0: 0 * inf = NaN below, as in the reference (all keys masked)
-      float a[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) a[i] = 0.f;
-#pragma unroll
-      for (int j = 0; j < AT_MAXKEYS; ++j) {
-        if (j < n) {
-          const float4* vr = reinterpret_cast<const float4*>(kvb + j * 128 + 64 + h * 32);
-          const float p = s[j];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 vv = vr[c];
-            a[4 * c] = fmaf(p, vv.x, a[4 * c]); a[4 * c + 1] = fmaf(p, vv.y, a[4 * c + 1]);
-            a[4 * c + 2] = fmaf(p, vv.z, a[4 * c + 2]); a[4 * c + 3] = fmaf(p, vv.w, a[4 * c + 3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) a[i] *= inv;
-      store_row_bf16<32>(sm + AT_A1, tid, h * 4, a);
+    for (int i = 0; i < 32; i += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bq + half * 32 + i));
+      q[i] = (__uint_as_float(r[i]) + bb.x) * qscale; q[i + 1] = (__uint_as_float(r[i + 1]) + bb.y) * qscale;
+      q[i + 2] = (__uint_as_float(r[i + 2]) + bb.z) * qscale; q[i + 3] = (__uint_as_float(r[i + 3]) + bb.w) * qscale;
     }
+    float s[AT_MAXKEYS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < AT_MAXKEYS; ++j) {
+      s[j] = -INFINITY;
+      if (j < n) {
+        const float4* kr = reinterpret_cast<const float4*>(kvb + j * 128 + half * 32);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent chains
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 kk = kr[c];
+          a0 = fmaf(q[4 * c], kk.x, a0); a1 = fmaf(q[4 * c + 1], kk.y, a1);
+          a2 = fmaf(q[4 * c + 2], kk.z, a2); a3 = fmaf(q[4 * c + 3], kk.w, a3);
+        }
+        s[j] = (a0 + a1) + (a2 + a3);
+        mx = fmaxf(mx, s[j]);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < AT_MAXKEYS; ++j) {
+      s[j] = (j < n) ? __expf(s[j] - mx) : 0.f;
+      sum += s[j];
+    }
+    const float inv = 1.0f / sum;   // n == 0: 0 * inf = NaN below, as in the reference (all keys masked)
+    float a[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < AT_MAXKEYS; ++j) {
+      if (j < n) {
+        const float4* vr = reinterpret_cast<const float4*>(kvb + j * 128 + 64 + half * 32);
+        const float p = s[j];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 vv = vr[c];
+          a[4 * c] = fmaf(p, vv.x, a[4 * c]); a[4 * c + 1] = fmaf(p, vv.y, a[4 * c + 1]);
+          a[4 * c + 2] = fmaf(p, vv.z, a[4 * c + 2]); a[4 * c + 3] = fmaf(p, vv.w, a[4 * c + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] *= inv;
+    store_row_bf16<32>(sm + AT_A1, rrow, half * 4, a);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -237,28 +250,31 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
       umma_bf16_ss(tmem, make_sdesc_sw128(base + AT_A1 + k * 32), make_sdesc_sw128(base + AT_WO + k * 32), idesc, k > 0);
     tc_commit(bar_mma);
   }
-  float t[64];
+  float t[32];
   {
-    // residual D (fp32) for this row while the MMA runs
-    const float4* dsrc = reinterpret_cast<const float4*>(g.d_f32 + size_t(row_ok ? row : 0) * 64);
+    // residual D (fp32) for this thread's half row while the MMA runs
+    const float4* dsrc = reinterpret_cast<const float4*>(g.d_f32 + size_t(row_ok ? row : 0) * 64 + half * 32);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const float4 d = __ldg(dsrc + i);
       t[4 * i] = d.x; t[4 * i + 1] = d.y; t[4 * i + 2] = d.z; t[4 * i + 3] = d.w;
     }
   }
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
   tc_fence_after();
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
+  {
     uint32_t r[32];
-    tmem_ld_32x32b_x32(t_row + hh * 32, r);
+    tmem_ld_32x32b_x32(t_row + half * 32, r);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t[hh * 32 + i] += __uint_as_float(r[i]) + __ldg(g.bo + hh * 32 + i);
+    for (int i = 0; i < 32; i += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bo + half * 32 + i));
+      t[i] += __uint_as_float(r[i]) + bb.x; t[i + 1] += __uint_as_float(r[i + 1]) + bb.y;
+      t[i + 2] += __uint_as_float(r[i + 2]) + bb.z; t[i + 3] += __uint_as_float(r[i + 3]) + bb.w;
+    }
   }
-  ln64_regs(t, g.n2_w, g.n2_b);
-  store_row_bf16<64>(sm + AT_A0, tid, 0, t);
+  ln64_pair(t, half, rrow, red, g.n2_w, g.n2_b);
+  store_row_bf16<32>(sm + AT_A0, rrow, half * 4, t);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -274,15 +290,19 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
   }
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
   tc_fence_after();
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {          // this thread's 64 hidden channels = k-atom `half` of the hidden tile
     uint32_t r[32];
-    tmem_ld_32x32b_x32(t_row + c * 32, r);
+    tmem_ld_32x32b_x32(t_row + half * 64 + c * 32, r);
     tmem_wait_ld();
     float hv[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) hv[i] = fmaxf(__uint_as_float(r[i]) + __ldg(g.b1 + c * 32 + i), 0.f);
-    store_row_bf16<32>(sm + AT_P + (c >> 1) * 16384, tid, (c & 1) * 4, hv);
+    for (int i = 0; i < 32; i += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.b1 + half * 64 + c * 32 + i));
+      hv[i] = fmaxf(__uint_as_float(r[i]) + bb.x, 0.f); hv[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + bb.y, 0.f);
+      hv[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + bb.z, 0.f); hv[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + bb.w, 0.f);
+    }
+    store_row_bf16<32>(sm + AT_P + half * 16384, rrow, c * 4, hv);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -300,19 +320,22 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
   }
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
   tc_fence_after();
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
+  {
     uint32_t r[32];
-    tmem_ld_32x32b_x32(t_row + hh * 32, r);
+    tmem_ld_32x32b_x32(t_row + half * 32, r);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t[hh * 32 + i] += __uint_as_float(r[i]) + __ldg(g.b2 + hh * 32 + i);
+    for (int i = 0; i < 32; i += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.b2 + half * 32 + i));
+      t[i] += __uint_as_float(r[i]) + bb.x; t[i + 1] += __uint_as_float(r[i + 1]) + bb.y;
+      t[i + 2] += __uint_as_float(r[i + 2]) + bb.z; t[i + 3] += __uint_as_float(r[i + 3]) + bb.w;
+    }
   }
-  ln64_regs(t, g.n3_w, g.n3_b);
+  ln64_pair(t, half, rrow, red, g.n3_w, g.n3_b);
   if (row_ok) {
-    uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(row) * 64);
+    uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(row) * 64 + half * 32);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       uint4 pk;
       pk.x = pack_bf16x2(t[8 * c], t[8 * c + 1]);
       pk.y = pack_bf16x2(t[8 * c + 2], t[8 * c + 3]);
