@@ -31,6 +31,28 @@ constexpr int PRIOR_IN = 517;
 constexpr int PRIOR_MAXTOK = 32;
 constexpr int PRIOR_TPB = 4;  // tokens per block
 
+// y[t][o] (+)= sum_k x[t][k] * Wt[k][o] for PRIOR_TPB tokens; Wt (K x NOUT, row-major) is streamed through shared
+// memory in 64-row chunks with coalesced, fully independent loads (the per-thread dependent LDG chain was pure latency).
+template <int NOUT>
+__device__ __forceinline__ void prior_layer(const float* __restrict__ wt, int K, const float* __restrict__ x, int ldx,
+                                            float* __restrict__ wchunk, float (&acc)[4], int o) {
+  for (int k0 = 0; k0 < K; k0 += 64) {
+    const int kn = min(64, K - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kn * NOUT / 4; i += 128)
+      reinterpret_cast<float4*>(wchunk)[i] = __ldg(reinterpret_cast<const float4*>(wt + size_t(k0) * NOUT) + i);
+    __syncthreads();
+    if (o < NOUT) {
+#pragma unroll 8
+      for (int k = 0; k < kn; ++k) {
+        const float w = wchunk[k * NOUT + o];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t] = fmaf(w, x[t * ldx + k0 + k], acc[t]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ labels,
                     const int* __restrict__ box_off, const float* __restrict__ obj_emb, const float* __restrict__ w0t,
@@ -40,6 +62,8 @@ prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ s
   __shared__ float xin[PRIOR_TPB][520];
   __shared__ float h1[PRIOR_TPB][128];
   __shared__ float h2[PRIOR_TPB][128];
+  __shared__ __align__(16) float wchunk[64 * 128];
+  static_assert(PRIOR_TPB == 4, "prior_layer is written for 4 tokens per block");
   const int b = blockIdx.x;
   const int tbase = blockIdx.y * PRIOR_TPB;
   const int o = threadIdx.x;
@@ -57,49 +81,33 @@ prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ s
   }
   if (threadIdx.x < PRIOR_TPB && tbase + threadIdx.x < n_max)
     mask[b * n_max + tbase + threadIdx.x] = (tbase + threadIdx.x) < n ? 0 : 1;
-  __syncthreads();
-  float acc[PRIOR_TPB];
+  float acc[4];
   {
     const float bias = b0[o];
 #pragma unroll
-    for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = bias;
-#pragma unroll 4
-    for (int k = 0; k < PRIOR_IN; ++k) {
-      const float w = __ldg(w0t + k * 128 + o);
+    for (int t = 0; t < 4; ++t) acc[t] = bias;
+    prior_layer<128>(w0t, PRIOR_IN, &xin[0][0], 520, wchunk, acc, o);
 #pragma unroll
-      for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = fmaf(w, xin[t][k], acc[t]);
-    }
-#pragma unroll
-    for (int t = 0; t < PRIOR_TPB; ++t) h1[t][o] = fmaxf(acc[t], 0.f);
+    for (int t = 0; t < 4; ++t) h1[t][o] = fmaxf(acc[t], 0.f);
   }
-  __syncthreads();
   {
     const float bias = b1[o];
 #pragma unroll
-    for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = bias;
-#pragma unroll 4
-    for (int k = 0; k < 128; ++k) {
-      const float w = __ldg(w1t + k * 128 + o);
+    for (int t = 0; t < 4; ++t) acc[t] = bias;
+    prior_layer<128>(w1t, 128, &h1[0][0], 128, wchunk, acc, o);
 #pragma unroll
-      for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = fmaf(w, h1[t][k], acc[t]);
-    }
-#pragma unroll
-    for (int t = 0; t < PRIOR_TPB; ++t) h2[t][o] = fmaxf(acc[t], 0.f);
+    for (int t = 0; t < 4; ++t) h2[t][o] = fmaxf(acc[t], 0.f);
   }
-  __syncthreads();
-  if (o < 64) {
-    const float bias = b2[o];
+  {
+    const float bias = o < 64 ? b2[o] : 0.f;
 #pragma unroll
-    for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = bias;
-#pragma unroll 4
-    for (int k = 0; k < 128; ++k) {
-      const float w = __ldg(w2t + k * 64 + o);
+    for (int t = 0; t < 4; ++t) acc[t] = bias;
+    prior_layer<64>(w2t, 128, &h2[0][0], 128, wchunk, acc, o);
+    if (o < 64) {
 #pragma unroll
-      for (int t = 0; t < PRIOR_TPB; ++t) acc[t] = fmaf(w, h2[t][k], acc[t]);
+      for (int t = 0; t < 4; ++t)
+        if (tbase + t < n_max) prior[(size_t(b) * n_max + tbase + t) * 64 + o] = acc[t];
     }
-#pragma unroll
-    for (int t = 0; t < PRIOR_TPB; ++t)
-      if (tbase + t < n_max) prior[(size_t(b) * n_max + tbase + t) * 64 + o] = acc[t];
   }
 }
 
@@ -134,11 +142,17 @@ __device__ __forceinline__ float axis_weight(int t, float start, float bin, int 
   return w;
 }
 
+// Per-axis RoIAlign weights of every single / union box, computed ONCE (not once per channel slice): one warp per box,
+// lanes 0..13 -> Wy, lanes 16..29 -> Wx, lane 31 -> 1 / (49 * count).  job index: [0, Ntot) singles, [Ntot, Ntot+Ktot)
+// unions, in global (CSR) numbering.
+__global__ void __launch_bounds__(256)
+roi_weights_kernel(const float* __restrict__ boxes, const int* __restrict__ box_off, const int* __restrict__ pair_off,
+                   int nimg, int ntot, int ktot, float spatial_scale, float* __restrict__ wts /* (Ntot+Ktot, 32) */);
+
 __global__ void __launch_bounds__(ROI_THREADS)
-roi_features_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const float* __restrict__ boxes,
-                    const int* __restrict__ box_off, const int* __restrict__ n_human, const int* __restrict__ pair_off,
-                    float spatial_scale, float* __restrict__ single_feat /* (Ntot,512) */,
-                    float* __restrict__ union_feat /* (Ktot,512) */) {
+roi_features_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const float* __restrict__ wts,
+                    const int* __restrict__ box_off, const int* __restrict__ pair_off, int ntot,
+                    float* __restrict__ single_feat /* (Ntot,512) */, float* __restrict__ union_feat /* (Ktot,512) */) {
   extern __shared__ float4 fs4[];  // [196][32] float4
   const int b = blockIdx.x, slice = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,36 +161,19 @@ roi_features_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const f
   __syncthreads();
   const int bbase = box_off[b];
   const int n = box_off[b + 1] - bbase;
-  const int nh = n_human[b];
   const int pbase = pair_off[b];
   const int K = pair_off[b + 1] - pbase;
   for (int job = warp; job < n + K; job += ROI_THREADS / 32) {
-    float x1, y1, x2, y2;
     float* dst;
+    int gjob;
     if (job < n) {
-      const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + job);
-      x1 = bx.x; y1 = bx.y; x2 = bx.z; y2 = bx.w;
+      gjob = bbase + job;
       dst = single_feat + size_t(bbase + job) * FEAT;
     } else {
-      const int i = job - n;
-      const int px = i / (n - 1), r = i % (n - 1);
-      const int py = r < px ? r : r + 1;           // row-major enumeration of (x, y != x), x < n_h  (U:1007-1012)
-      const float4 bh = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + px);
-      const float4 bo = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + py);
-      x1 = fminf(bh.x, bo.x); y1 = fminf(bh.y, bo.y); x2 = fmaxf(bh.z, bo.z); y2 = fmaxf(bh.w, bo.w);  // U:1021-1023
-      dst = union_feat + size_t(pbase + i) * FEAT;
+      gjob = ntot + pbase + (job - n);
+      dst = union_feat + size_t(pbase + job - n) * FEAT;
     }
-    (void)nh;
-    const float sx = x1 * spatial_scale - 0.5f, sy = y1 * spatial_scale - 0.5f;
-    const float ex = x2 * spatial_scale - 0.5f, ey = y2 * spatial_scale - 0.5f;
-    const float rw = ex - sx, rh = ey - sy;
-    const float bw = rw / float(POOL), bh_ = rh / float(POOL);
-    const int gw = int(ceilf(rw / float(POOL))), gh = int(ceilf(rh / float(POOL)));
-    const float count = float(max(gh * gw, 1));
-    // lanes 0..13 hold Wy[lane], lanes 16..29 hold Wx[lane-16]
-    float wl = 0.f;
-    if (lane < G14) wl = axis_weight(lane, sy, bh_, gh);
-    else if (lane >= 16 && lane < 16 + G14) wl = axis_weight(lane - 16, sx, bw, gw);
+    const float wl = __ldg(wts + size_t(gjob) * 32 + lane);
     const unsigned nzy = __ballot_sync(0xffffffffu, lane < G14 && wl != 0.f);
     const unsigned nzx = __ballot_sync(0xffffffffu, lane >= 16 && lane < 16 + G14 && wl != 0.f) >> 16;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -196,10 +193,45 @@ roi_features_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const f
         acc.z = fmaf(wy, rowacc.z, acc.z); acc.w = fmaf(wy, rowacc.w, acc.w);
       }
     }
-    const float inv = 1.0f / (count * float(POOL * POOL));
+    const float inv = __shfl_sync(0xffffffffu, wl, 31);
     acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
     reinterpret_cast<float4*>(dst + slice * ROI_SLICE)[lane] = acc;
   }
+}
+
+__device__ __forceinline__ int find_image(const int* __restrict__ off, int nimg, int idx);
+
+__global__ void __launch_bounds__(256)
+roi_weights_kernel(const float* __restrict__ boxes, const int* __restrict__ box_off, const int* __restrict__ pair_off,
+                   int nimg, int ntot, int ktot, float spatial_scale, float* __restrict__ wts) {
+  const int gjob = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gjob >= ntot + ktot) return;
+  float x1, y1, x2, y2;
+  if (gjob < ntot) {
+    const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + gjob);
+    x1 = bx.x; y1 = bx.y; x2 = bx.z; y2 = bx.w;
+  } else {
+    const int gi = gjob - ntot;
+    const int b = find_image(pair_off, nimg, gi);
+    const int bbase = box_off[b], n = box_off[b + 1] - bbase;
+    const int i = gi - pair_off[b];
+    const int px = i / (n - 1), r = i % (n - 1);
+    const int py = r < px ? r : r + 1;           // row-major enumeration of (x, y != x), x < n_h  (U:1007-1012)
+    const float4 bh = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + px);
+    const float4 bo = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + py);
+    x1 = fminf(bh.x, bo.x); y1 = fminf(bh.y, bo.y); x2 = fmaxf(bh.z, bo.z); y2 = fmaxf(bh.w, bo.w);  // U:1021-1023
+  }
+  const float sx = x1 * spatial_scale - 0.5f, sy = y1 * spatial_scale - 0.5f;
+  const float ex = x2 * spatial_scale - 0.5f, ey = y2 * spatial_scale - 0.5f;
+  const float rw = ex - sx, rh = ey - sy;
+  const float bw = rw / float(POOL), bh_ = rh / float(POOL);
+  const int gw = int(ceilf(rw / float(POOL))), gh = int(ceilf(rh / float(POOL)));
+  const float count = float(max(gh * gw, 1));
+  float wl = 0.f;
+  if (lane < G14) wl = axis_weight(lane, sy, bh_, gh);
+  else if (lane >= 16 && lane < 16 + G14) wl = axis_weight(lane - 16, sx, bw, gw);
+  else if (lane == 31) wl = 1.0f / (count * float(POOL * POOL));
+  wts[size_t(gjob) * 32 + lane] = wl;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -406,14 +438,14 @@ int hoigen_prior_tokens(const float* boxes, const float* scores, const int64_t* 
   return HOIGEN_OK;
 }
 
-int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int32_t* box_off, const int32_t* n_human,
-                             const int32_t* pair_off, int32_t batch, int32_t ktot, float spatial_scale,
+int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int32_t* box_off, const int32_t* pair_off,
+                             int32_t batch, int32_t ntot, int32_t ktot, float spatial_scale, float* roi_weights,
                              float* single_feat, float* union_feat, void* pair_feat_bf16, float* pair_feat_f32,
                              hoigen_stream_t stream) {
   using namespace hoigen;
-  HOIGEN_CHECK_ARG(tokens && boxes && box_off && n_human && pair_off && single_feat && union_feat && pair_feat_bf16,
+  HOIGEN_CHECK_ARG(tokens && boxes && box_off && pair_off && roi_weights && single_feat && union_feat && pair_feat_bf16,
                    "roi_pair_features: null argument");
-  HOIGEN_CHECK_ARG(batch > 0 && ktot >= 0, "roi_pair_features: bad sizes");
+  HOIGEN_CHECK_ARG(batch > 0 && ntot > 0 && ktot >= 0, "roi_pair_features: bad sizes");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static bool attr_set = false;
   if (!attr_set) {
@@ -421,11 +453,16 @@ int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int3
     attr_set = true;
   }
   {
-    // algorithmic bytes: token map read once + boxes + one fp32 feature row per single / union box;
-    // the number of single boxes is not known on the host here, it is bounded by 32 per image
-    KernelScope ks("roi_features", s, 0, double(batch) * 196 * FEAT * 4 + double(ktot) * (16 + FEAT * 4));
+    KernelScope ks("roi_weights", s, 0, double(ntot + ktot) * (16 + 128));
+    roi_weights_kernel<<<((ntot + ktot) * 32 + 255) / 256, 256, 0, s>>>(boxes, box_off, pair_off, batch, ntot, ktot,
+                                                                        spatial_scale, roi_weights);
+  }
+  HOIGEN_CHECK_LAUNCH();
+  {
+    // algorithmic bytes: token map read once + boxes + one fp32 feature row per single / union box
+    KernelScope ks("roi_features", s, 0, double(batch) * 196 * FEAT * 4 + double(ntot + ktot) * (16 + FEAT * 4));
     roi_features_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES, s>>>(
-        tokens, boxes, box_off, n_human, pair_off, spatial_scale, single_feat, union_feat);
+        tokens, roi_weights, box_off, pair_off, ntot, single_feat, union_feat);
   }
   HOIGEN_CHECK_LAUNCH();
   if (ktot > 0) {

@@ -357,9 +357,10 @@ class UPT(nn.Module):
         pf_bf16 = self._buf("pair_bf16", 3 * ktot * 512, torch.bfloat16, dev)
         pf_f32 = self._buf("pair_f32", 3 * ktot * 512, torch.float32, dev) if return_intermediates else None
         spatial_scale = 1.0 / (img_h / 14.0)                                          # U:1027
-        _cabi.call("hoigen_roi_pair_features", tokens.data_ptr(), boxes.data_ptr(), d_box_off.data_ptr(), d_nh.data_ptr(),
-                   d_pair_off.data_ptr(), B, ktot, float(spatial_scale), single.data_ptr(), union.data_ptr(),
-                   pf_bf16.data_ptr(), pf_f32.data_ptr() if pf_f32 is not None else None)
+        roi_w = self._buf("roi_weights", (ntot + ktot) * 32, torch.float32, dev)
+        _cabi.call("hoigen_roi_pair_features", tokens.data_ptr(), boxes.data_ptr(), d_box_off.data_ptr(),
+                   d_pair_off.data_ptr(), B, ntot, ktot, float(spatial_scale), roi_w.data_ptr(), single.data_ptr(),
+                   union.data_ptr(), pf_bf16.data_ptr(), pf_f32.data_ptr() if pf_f32 is not None else None)
         # ---- a10: cache + text logits --------------------------------------------------------------------------------
         N = sw.cache_rows
         logits = self._buf("logits", ktot * Cn, torch.float32, dev)

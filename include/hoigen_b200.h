@@ -188,9 +188,10 @@ HOIGEN_API int hoigen_prior_tokens(const float* boxes, const float* scores, cons
  * box and every union box on the 14x14 token grid (torchvision.ops.roi_align call sites U:1028-1029), then
  * f_H = single[x]/|.|, f_O = single[y]/|.|, f_U = union/|.|  -> pair_feat [3][Ktot][512] (H,O,U) bf16 (+fp32). */
 HOIGEN_API int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int32_t* box_off,
-                                        const int32_t* n_human, const int32_t* pair_off, int32_t batch, int32_t ktot,
-                                        float spatial_scale, float* single_feat, float* union_feat,
-                                        void* pair_feat_bf16, float* pair_feat_f32, hoigen_stream_t stream);
+                                        const int32_t* pair_off, int32_t batch, int32_t ntot, int32_t ktot,
+                                        float spatial_scale, float* roi_weights /* workspace (ntot+ktot, 32) */,
+                                        float* single_feat, float* union_feat, void* pair_feat_bf16,
+                                        float* pair_feat_f32, hoigen_stream_t stream);
 HOIGEN_API int hoigen_rows_to_bf16(const float* in, int64_t ld_in, int32_t rows, int32_t cols, int32_t normalize,
                                    void* out_bf16, hoigen_stream_t stream);
 HOIGEN_API int hoigen_broadcast_image_logits(const float* img_logits, const int32_t* pair_off, int32_t batch,

@@ -279,8 +279,9 @@ def test_roi_pair_features_fp32(cuda_device, mode):
     union = torch.empty(ktot, 512, device=dev)
     pb = torch.empty(3, ktot, 512, device=dev, dtype=torch.bfloat16)
     pf = torch.empty(3, ktot, 512, device=dev)
-    _cabi.call("hoigen_roi_pair_features", t_tok.data_ptr(), boxes.data_ptr(), d_box.data_ptr(), d_nh.data_ptr(),
-               d_pair.data_ptr(), B, ktot, 14.0 / 224.0, single.data_ptr(), union.data_ptr(), pb.data_ptr(), pf.data_ptr())
+    ws = torch.empty((ntot + ktot) * 32, device=dev)
+    _cabi.call("hoigen_roi_pair_features", t_tok.data_ptr(), boxes.data_ptr(), d_box.data_ptr(), d_pair.data_ptr(), B, ntot,
+               ktot, 14.0 / 224.0, ws.data_ptr(), single.data_ptr(), union.data_ptr(), pb.data_ptr(), pf.data_ptr())
     pf = pf.cpu()
     for b, p in enumerate(props):
         x_keep, y_keep, fh, fo, fu = O.roi_pair_features(tokens[b], p, 0)
@@ -313,8 +314,9 @@ def test_roi_align_golden_torchvision(cuda_device):
         single = torch.empty(n, 512, device=dev)
         union = torch.empty(1, 512, device=dev)
         pb = torch.empty(3, 1, 512, device=dev, dtype=torch.bfloat16)
-        _cabi.call("hoigen_roi_pair_features", t.data_ptr(), bx.data_ptr(), d_box.data_ptr(), d_nh.data_ptr(), d_pair.data_ptr(),
-                   1, 0, 14.0 / 224.0, single.data_ptr(), union.data_ptr(), pb.data_ptr(), None)
+        ws = torch.empty(n * 32, device=dev)
+        _cabi.call("hoigen_roi_pair_features", t.data_ptr(), bx.data_ptr(), d_box.data_ptr(), d_pair.data_ptr(), 1, n, 0,
+                   14.0 / 224.0, ws.data_ptr(), single.data_ptr(), union.data_ptr(), pb.data_ptr(), None)
         outs.append(single.cpu())
     got = torch.cat(outs)
     assert (got - ref).abs().max().item() < 2e-5
