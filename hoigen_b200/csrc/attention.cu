@@ -1,13 +1,17 @@
-// 12-head self-attention over the 197-token sequence as ONE tcgen05 pass per (image, head, 128-row tile):
-//   S = Q K^T  (UMMA 128 x 208 x 16, 4 k-steps, fp32 in TMEM)  ->  softmax in registers (tcgen05.ld)
-//   -> P (bf16) into 128B-swizzled shared memory  ->  O = P V  (UMMA 128 x 64 x 16, 13 k-steps,
-//   V consumed MN-major straight from the QKV buffer, no transpose)  ->  O / rowsum -> bf16.
+// 12-head self-attention over the 197-token sequence on tcgen05: PERSISTENT, warp-specialised CTAs (one per SM) that
+// stream (image, head, 128-row tile) work items through a TMA -> UMMA -> softmax -> UMMA pipeline:
+//
+//   warp 0      TMA producer: Q tile (128x64), K (208x64), V (208x64) of item i+1 land while item i is computed
+//   warp 1      MMA issuer:   S_i = Q K^T  (UMMA 128x208x16, 4 k-steps, fp32 in TMEM buffer i&1), issued one item
+//                              ahead of the softmax;  O_i = P_i V (UMMA 128x64x16, 13 k-steps, V consumed MN-major
+//                              straight from the QKV buffer, O overlays columns [0,64) of its own S buffer)
+//   warps 2-9   softmax + epilogue, TWO threads per query row (key halves [0,112) and [112,208)):
+//                              row max -> exp2 -> P (bf16) into 128B-swizzled smem -> ... -> O / rowsum -> bf16 -> global
 // The whole key range (197 -> 208) fits one tile, so no online-softmax rescaling is needed.
 //
-// Shared memory (90 KiB => 2 CTAs / SM; P overlays Q and K once S has been produced):
-//   [0,16K)  Q tile / P atom 0     [16K,48K) K tile (26 KiB used) / P atoms 1,2     [48K,64K) P atom 3
-//   [64K,90K) V tile
-// TMEM: 256 columns (S uses 208; O overlays columns [0,64) after the softmax has consumed S).
+// Shared memory: 2 stages x [Q 16K | K 26K | V 26K] + P 64K = 200 KiB.  TMEM: 2 x 208 columns (512 allocated).
+// Barriers: full[s]/empty[s] (TMA<->MMA), s_ready[b] (S in TMEM), p_ready (P in smem), o_ready (PV done),
+// epi_done[b] (TMEM buffer b drained).
 //
 // Replaces F.multi_head_attention_forward -> SDPA at CLIP_models_adapter_prior2.py:443-445 (no mask,
 // scale = 64^-0.5, dropout off).
@@ -21,44 +25,53 @@ constexpr int ATT_KEYS = 208;      // 197 padded to a multiple of 16 (UMMA N / K
 constexpr int ATT_DH = 64;
 constexpr int ATT_HEADS = 12;
 constexpr int ATT_WIDTH = 768;
-constexpr int ATT_THREADS = 128;
-constexpr int ATT_SMEM_Q = 0;
-constexpr int ATT_SMEM_K = 16384;
-constexpr int ATT_SMEM_P3 = 49152;
-constexpr int ATT_SMEM_V = 65536;
-constexpr int ATT_SMEM_TILES = 65536 + ATT_KEYS * 128;  // 92160
-constexpr int ATT_SMEM_BYTES = ATT_SMEM_TILES + 1024 + 64;
-constexpr int ATT_TMEM_COLS = 256;
+constexpr int ATT_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax/epilogue
+constexpr int ATT_STAGE_Q = 0;
+constexpr int ATT_STAGE_K = 16384;
+constexpr int ATT_STAGE_V = 16384 + ATT_KEYS * 128;            // 43008
+constexpr int ATT_STAGE_BYTES = 16384 + 2 * ATT_KEYS * 128;    // 69632
+constexpr int ATT_SMEM_P = 2 * ATT_STAGE_BYTES;                // 139264 (1024-aligned)
+constexpr int ATT_SMEM_MISC = ATT_SMEM_P + 65536;              // barriers + row-stat exchange
+constexpr int ATT_SMEM_BYTES = ATT_SMEM_MISC + 128 + 4 * 256 * 4 + 1024;
+constexpr int ATT_TMEM_COLS = 512;
+constexpr int ATT_SPLIT = 112;     // keys [0,112) -> column half 0 (7 chunks of 16), [112,208) -> half 1 (6 chunks)
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
                  const __grid_constant__ CUtensorMap tmKV /* box 64 x 208 x 1 */, __nv_bfloat16* __restrict__ out,
-                 int batch) {
+                 int num_items) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* tiles = smem_raw + (base - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + ATT_SMEM_TILES);
-  const uint32_t bar_load = smem_u32(bars);
-  const uint32_t bar_s = bar_load + 8;
-  const uint32_t bar_o = bar_load + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint8_t* sm = smem_raw + (base - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + ATT_SMEM_MISC);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t bar_full = bar0;            // [2]
+  const uint32_t bar_empty = bar0 + 16;      // [2]
+  const uint32_t bar_sready = bar0 + 32;     // [2]
+  const uint32_t bar_epi = bar0 + 48;        // [2]
+  const uint32_t bar_pready = bar0 + 64;
+  const uint32_t bar_oready = bar0 + 72;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* stat_max = reinterpret_cast<float*>(sm + ATT_SMEM_MISC + 128);   // [2 item parities][2 halves][128 rows]
+  float* stat_sum = stat_max + 512;                                       // [2 item parities][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x & 1;            // 128-row tile of the 197 queries
-  const int h = (blockIdx.x >> 1) % ATT_HEADS;
-  const int b = (blockIdx.x >> 1) / ATT_HEADS;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+      mbar_init(bar_sready + 8u * s, 1);
+      mbar_init(bar_epi + 8u * s, 8);     // one arrive per softmax warp
+    }
+    mbar_init(bar_pready, 8);
+    mbar_init(bar_oready, 1);
     fence_barrier_init();
   }
-  if (warp == 0) {
-    __syncwarp();
+  if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), ATT_TMEM_COLS);
     tmem_relinquish();
   }
@@ -67,116 +80,166 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (threadIdx.x == 0) {
-    // ---- loads: Q (128 x 64), K (208 x 64), V (208 x 64); rows past token 196 are zero-filled by TMA ----
-    mbar_arrive_expect_tx(bar_load, 128 * 128 + 2 * ATT_KEYS * 128);
-    tma_load_3d(base + ATT_SMEM_Q, &tmQ, bar_load, h * ATT_DH, mt * 128, b);
-    tma_load_3d(base + ATT_SMEM_K, &tmKV, bar_load, ATT_WIDTH + h * ATT_DH, 0, b);
-    tma_load_3d(base + ATT_SMEM_V, &tmKV, bar_load, 2 * ATT_WIDTH + h * ATT_DH, 0, b);
-    mbar_wait(bar_load, 0);
-    tc_fence_after();
-    // ---- S = Q K^T ----
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_KEYS);
-#pragma unroll
-    for (int k = 0; k < ATT_DH / 16; ++k) {
-      umma_bf16_ss(tmem, make_sdesc_sw128(base + ATT_SMEM_Q + k * 32), make_sdesc_sw128(base + ATT_SMEM_K + k * 32),
-                   idesc_s, k > 0 ? 1u : 0u);
-    }
-    tc_commit(bar_s);
-  }
+  // item -> (image b, head h, row tile mt); consecutive items of a CTA stride by gridDim.x
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_local = first < num_items ? (num_items - first + stride - 1) / stride : 0;
 
-  // ---- softmax: thread r owns query row r of the tile ----
-  mbar_wait(bar_s, 0);
-  tc_fence_after();
-  const int row = warp * 32 + lane;
-  const uint32_t t_row = tmem + (uint32_t(warp * 32) << 16);
-  const float scale_log2 = 0.125f * 1.4426950408889634f;  // 64^-0.5 * log2(e)
-  float mx = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < ATT_KEYS / 16; ++c) {
-    uint32_t r[16];
-    tmem_ld_32x32b_x16(t_row + c * 16, r);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (c * 16 + j < ATT_TOKENS) mx = fmaxf(mx, __uint_as_float(r[j]));
-  }
-  const float mxs = mx * scale_log2;
-  float sum = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < ATT_KEYS / 16; ++c) {
-    uint32_t r[16];
-    tmem_ld_32x32b_x16(t_row + c * 16, r);
-    tmem_wait_ld();
-    float p[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float e = exp2f(fmaf(__uint_as_float(r[j]), scale_log2, -mxs));
-      p[j] = (c * 16 + j < ATT_TOKENS) ? e : 0.f;
-    }
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // the row sum is taken over the bf16-rounded probabilities that the PV MMA actually consumes
-      const __nv_bfloat162 v2 = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
-      sum += __low2float(v2) + __high2float(v2);
-      pk[j] = *reinterpret_cast<const uint32_t*>(&v2);
-    }
-    // P[row][c*16 .. c*16+15] -> K-major SW128 atoms: atom = c/4 (64 keys each), 16-byte chunks (c%4)*2, +1
-    const int atom = c >> 2;
-    const uint32_t atom_off = (atom == 0) ? ATT_SMEM_Q : (atom == 3 ? ATT_SMEM_P3 : ATT_SMEM_K + (atom - 1) * 16384);
-    uint8_t* pa = tiles + atom_off;
-    const uint32_t ch = uint32_t(c & 3) * 2;
-    *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-  }
-  // make the generic-proxy smem writes visible to the tensor core (async proxy), and order the TMEM reads of S
-  // before the PV MMA overwrites columns [0,64)
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-
-  if (threadIdx.x == 0) {
-    tc_fence_after();
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, ATT_DH, /*a_mn_major=*/0, /*b_mn_major=*/1);
-#pragma unroll
-    for (int ks = 0; ks < ATT_KEYS / 16; ++ks) {
-      const int atom = ks >> 2;
-      const uint32_t atom_off = (atom == 0) ? ATT_SMEM_Q : (atom == 3 ? ATT_SMEM_P3 : ATT_SMEM_K + (atom - 1) * 16384);
-      const uint64_t adesc = make_sdesc_sw128(base + atom_off + (ks & 3) * 32);
-      // V tile rows are keys (MN-major B operand): one k-step = 16 keys = two 8-row groups = 2048 bytes
-      const uint64_t bdesc = make_sdesc_sw128(base + ATT_SMEM_V + ks * 2048);
-      umma_bf16_ss(tmem, adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
-    }
-    tc_commit(bar_o);
-  }
-
-  // ---- epilogue: O / rowsum -> bf16 -> out[b*197 + t][h*64 .. +63] ----
-  mbar_wait(bar_o, 0);
-  tc_fence_after();
-  const int t = mt * 128 + row;
-  const float inv = 1.0f / sum;
-#pragma unroll
-  for (int c = 0; c < ATT_DH / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(t_row + c * 32, r);
-    tmem_wait_ld();
-    if (t < ATT_TOKENS) {
-      __nv_bfloat16* dst = out + (size_t(b) * ATT_TOKENS + t) * ATT_WIDTH + h * ATT_DH + c * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 pk;
-        pk.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
-        pk.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
-        pk.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
-        pk.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + j) = pk;
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < n_local; ++i) {
+        const int item = first + i * stride;
+        const int mt = item & 1, h = (item >> 1) % ATT_HEADS, b = (item >> 1) / ATT_HEADS;
+        const int s = i & 1;
+        mbar_wait(bar_empty + 8u * s, ((i >> 1) & 1u) ^ 1u);
+        const uint32_t st = base + s * ATT_STAGE_BYTES;
+        const uint32_t full = bar_full + 8u * s;
+        mbar_arrive_expect_tx(full, ATT_STAGE_BYTES);
+        tma_load_3d(st + ATT_STAGE_Q, &tmQ, full, h * ATT_DH, mt * 128, b);
+        tma_load_3d(st + ATT_STAGE_K, &tmKV, full, ATT_WIDTH + h * ATT_DH, 0, b);
+        tma_load_3d(st + ATT_STAGE_V, &tmKV, full, 2 * ATT_WIDTH + h * ATT_DH, 0, b);
       }
     }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && n_local > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_KEYS);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, ATT_DH, /*a_mn_major=*/0, /*b_mn_major=*/1);
+      auto issue_s = [&](int i) {
+        const int s = i & 1;
+        mbar_wait(bar_full + 8u * s, (i >> 1) & 1u);
+        if (i >= 2) mbar_wait(bar_epi + 8u * s, ((i >> 1) - 1) & 1u);   // TMEM buffer s drained by item i-2
+        tc_fence_after();
+        const uint32_t st = base + s * ATT_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < ATT_DH / 16; ++k)
+          umma_bf16_ss(tmem + uint32_t(s * 256), make_sdesc_sw128(st + ATT_STAGE_Q + k * 32),
+                       make_sdesc_sw128(st + ATT_STAGE_K + k * 32), idesc_s, k > 0 ? 1u : 0u);
+        tc_commit(bar_sready + 8u * s);
+      };
+      issue_s(0);
+      for (int i = 0; i < n_local; ++i) {
+        if (i + 1 < n_local) issue_s(i + 1);       // S of the next item overlaps the softmax of this one
+        const int s = i & 1;
+        mbar_wait(bar_pready, i & 1u);
+        tc_fence_after();
+        const uint32_t st = base + s * ATT_STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < ATT_KEYS / 16; ++ks) {
+          const uint64_t adesc = make_sdesc_sw128(base + ATT_SMEM_P + (ks >> 2) * 16384 + (ks & 3) * 32);
+          // V tile rows are keys (MN-major B operand): one k-step = 16 keys = two 8-row groups = 2048 bytes
+          const uint64_t bdesc = make_sdesc_sw128(st + ATT_STAGE_V + ks * 2048);
+          umma_bf16_ss(tmem + uint32_t(s * 256), adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_oready);             // O_i complete (and P consumed)
+        tc_commit(bar_empty + 8u * s);     // stage s (Q, K, V) free for item i+2
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue (256 threads, two per query row) =====================
+    const int quad = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int c_begin = colhalf == 0 ? 0 : ATT_SPLIT / 16;            // 16-column chunk range of this thread
+    const int c_end = colhalf == 0 ? ATT_SPLIT / 16 : ATT_KEYS / 16;
+    const float scale_log2 = 0.125f * 1.4426950408889634f;  // 64^-0.5 * log2(e)
+    uint8_t* smP = sm + ATT_SMEM_P;
+
+    auto epilogue = [&](int i) {
+      // O_i / rowsum -> bf16 -> out[b*197 + t][h*64 + colhalf*32 .. +31]
+      const int item = first + i * stride;
+      const int mt = item & 1, h = (item >> 1) % ATT_HEADS, b = (item >> 1) / ATT_HEADS;
+      const int t = mt * 128 + row;
+      const float inv = 1.0f / (stat_sum[(i & 1) * 256 + row] + stat_sum[(i & 1) * 256 + 128 + row]);
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem + (uint32_t(quad * 32) << 16) + uint32_t((i & 1) * 256 + colhalf * 32), r);
+      tmem_wait_ld();
+      if (t < ATT_TOKENS) {
+        __nv_bfloat16* dst = out + (size_t(b) * ATT_TOKENS + t) * ATT_WIDTH + h * ATT_DH + colhalf * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+          pk.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+          pk.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+          pk.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + j) = pk;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_epi + 8u * (i & 1));
+    };
+
+    for (int i = 0; i < n_local; ++i) {
+      const int sb = i & 1;
+      const uint32_t t_row = tmem + (uint32_t(quad * 32) << 16) + uint32_t(sb * 256);
+      mbar_wait(bar_sready + 8u * sb, (i >> 1) & 1u);
+      tc_fence_after();
+      // ---- pass 1: row max over this thread's key range ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_row + c * 16, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c * 16 + j < ATT_TOKENS) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
+      stat_max[sb * 256 + colhalf * 128 + row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, stat_max[sb * 256 + (colhalf ^ 1) * 128 + row]);
+      const float mxs = mx * scale_log2;
+      // P (single buffer) is free once the PV MMA of the previous item has completed
+      if (i > 0) {
+        mbar_wait(bar_oready, (i - 1) & 1u);
+        tc_fence_after();
+      }
+      // ---- pass 2: p = exp2(s*scale - max) -> bf16 -> swizzled smem; partial row sum ----
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_row + c * 16, r);
+        tmem_wait_ld();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float e0 = exp2f(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+          const float e1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
+          // the row sum is taken over the bf16-rounded probabilities that the PV MMA actually consumes
+          const __nv_bfloat162 v2 = __floats2bfloat162_rn((c * 16 + 2 * j < ATT_TOKENS) ? e0 : 0.f,
+                                                          (c * 16 + 2 * j + 1 < ATT_TOKENS) ? e1 : 0.f);
+          sum += __low2float(v2) + __high2float(v2);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&v2);
+        }
+        // P[row][c*16 .. +15] -> K-major SW128 atoms: atom = c/4 (64 keys each), 16-byte chunks (c%4)*2, +1
+        uint8_t* pa = smP + (c >> 2) * 16384;
+        const uint32_t ch = uint32_t(c & 3) * 2;
+        *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      stat_sum[sb * 256 + colhalf * 128 + row] = sum;
+      // generic-proxy smem writes -> visible to the tensor core; TMEM reads of S ordered before PV overwrites [0,64)
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pready);
+      // ---- epilogue of the PREVIOUS item overlaps this item's PV MMA ----
+      if (i > 0) epilogue(i - 1);
+    }
+    if (n_local > 0) {
+      mbar_wait(bar_oready, (n_local - 1) & 1u);
+      tc_fence_after();
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // partner's partial row sum of the last item is visible
+      epilogue(n_local - 1);
+    }
   }
+
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, ATT_TMEM_COLS);
   }
@@ -203,10 +266,12 @@ int hoigen_attention(const void* qkv, void* out, int32_t batch, hoigen_stream_t 
   const CUtensorMap* tkv = get_tmap_3d_bf16(qkv, 3 * ATT_WIDTH, ATT_TOKENS, uint64_t(batch), row_bytes,
                                             row_bytes * ATT_TOKENS, 64, ATT_KEYS, 1);
   if (!tkv) return HOIGEN_ERR_CUDA;
+  const int items = batch * ATT_HEADS * 2;
+  const int grid = items < num_sms() ? items : num_sms();
   KernelScope ks("attention", reinterpret_cast<cudaStream_t>(stream), 4.0 * ATT_TOKENS * ATT_TOKENS * ATT_DH * ATT_HEADS * batch,
                  double(batch) * ATT_TOKENS * ATT_WIDTH * 2 * 4);
-  attention_kernel<<<batch * ATT_HEADS * 2, ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-      *tq, *tkv, reinterpret_cast<__nv_bfloat16*>(out), batch);
+  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
+      *tq, *tkv, reinterpret_cast<__nv_bfloat16*>(out), items);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
