@@ -10,7 +10,8 @@
 // The whole key range (197 -> 208) fits one tile, so no online-softmax rescaling is needed.
 //
 // Shared memory: 2 stages x [Q 16K | K 26K | V 26K] + P 64K = 200 KiB.  TMEM: 2 x 208 columns (512 allocated).
-// Barriers: full[s]/empty[s] (TMA<->MMA), s_ready[b] (S in TMEM), p_ready (P in smem), o_ready (PV done),
+// Barriers: full/empty[s] (Q,K: released right after S), vfull/vempty[s] (V: released after PV), s_ready[b] (S in TMEM),
+// p_ready (P in smem), o_ready (PV done),
 // epi_done[b] (TMEM buffer b drained).
 //
 // Replaces F.multi_head_attention_forward -> SDPA at CLIP_models_adapter_prior2.py:443-445 (no mask,
@@ -36,6 +37,12 @@ constexpr int ATT_SMEM_BYTES = ATT_SMEM_MISC + 128 + 4 * 256 * 4 + 1024;
 constexpr int ATT_TMEM_COLS = 512;
 constexpr int ATT_SPLIT = 112;     // keys [0,112) -> column half 0 (7 chunks of 16), [112,208) -> half 1 (6 chunks)
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
                  const __grid_constant__ CUtensorMap tmKV /* box 64 x 208 x 1 */, __nv_bfloat16* __restrict__ out,
@@ -46,13 +53,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
   uint8_t* sm = smem_raw + (base - raw_addr);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + ATT_SMEM_MISC);
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t bar_full = bar0;            // [2]
-  const uint32_t bar_empty = bar0 + 16;      // [2]
+  const uint32_t bar_full = bar0;            // [2]  Q + K of a stage landed
+  const uint32_t bar_empty = bar0 + 16;      // [2]  Q + K consumed (S MMA done)  -> reload two items ahead, early
   const uint32_t bar_sready = bar0 + 32;     // [2]
   const uint32_t bar_epi = bar0 + 48;        // [2]
   const uint32_t bar_pready = bar0 + 64;
   const uint32_t bar_oready = bar0 + 72;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const uint32_t bar_vfull = bar0 + 80;      // [2]  V of a stage landed
+  const uint32_t bar_vempty = bar0 + 96;     // [2]  V consumed (PV MMA done)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   float* stat_max = reinterpret_cast<float*>(sm + ATT_SMEM_MISC + 128);   // [2 item parities][2 halves][128 rows]
   float* stat_sum = stat_max + 512;                                       // [2 item parities][2 halves][128 rows]
 
@@ -65,6 +74,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
       mbar_init(bar_full + 8u * s, 1);
       mbar_init(bar_empty + 8u * s, 1);
       mbar_init(bar_sready + 8u * s, 1);
+      mbar_init(bar_vfull + 8u * s, 1);
+      mbar_init(bar_vempty + 8u * s, 1);
       mbar_init(bar_epi + 8u * s, 8);     // one arrive per softmax warp
     }
     mbar_init(bar_pready, 8);
@@ -91,13 +102,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
         const int item = first + i * stride;
         const int mt = item & 1, h = (item >> 1) % ATT_HEADS, b = (item >> 1) / ATT_HEADS;
         const int s = i & 1;
-        mbar_wait(bar_empty + 8u * s, ((i >> 1) & 1u) ^ 1u);
         const uint32_t st = base + s * ATT_STAGE_BYTES;
+        // Q and K are released as soon as S_{i-2} has been computed (early), V only after P V of item i-2
+        mbar_wait(bar_empty + 8u * s, ((i >> 1) & 1u) ^ 1u);
         const uint32_t full = bar_full + 8u * s;
-        mbar_arrive_expect_tx(full, ATT_STAGE_BYTES);
+        mbar_arrive_expect_tx(full, 16384 + ATT_KEYS * 128);
         tma_load_3d(st + ATT_STAGE_Q, &tmQ, full, h * ATT_DH, mt * 128, b);
         tma_load_3d(st + ATT_STAGE_K, &tmKV, full, ATT_WIDTH + h * ATT_DH, 0, b);
-        tma_load_3d(st + ATT_STAGE_V, &tmKV, full, 2 * ATT_WIDTH + h * ATT_DH, 0, b);
+        mbar_wait(bar_vempty + 8u * s, ((i >> 1) & 1u) ^ 1u);
+        const uint32_t vfull = bar_vfull + 8u * s;
+        mbar_arrive_expect_tx(vfull, ATT_KEYS * 128);
+        tma_load_3d(st + ATT_STAGE_V, &tmKV, vfull, 2 * ATT_WIDTH + h * ATT_DH, 0, b);
       }
     }
   } else if (warp == 1) {
@@ -116,12 +131,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
           umma_bf16_ss(tmem + uint32_t(s * 256), make_sdesc_sw128(st + ATT_STAGE_Q + k * 32),
                        make_sdesc_sw128(st + ATT_STAGE_K + k * 32), idesc_s, k > 0 ? 1u : 0u);
         tc_commit(bar_sready + 8u * s);
+        tc_commit(bar_empty + 8u * s);     // Q, K of stage s free for item i+2
       };
       issue_s(0);
       for (int i = 0; i < n_local; ++i) {
         if (i + 1 < n_local) issue_s(i + 1);       // S of the next item overlaps the softmax of this one
         const int s = i & 1;
         mbar_wait(bar_pready, i & 1u);
+        mbar_wait(bar_vfull + 8u * s, (i >> 1) & 1u);
         tc_fence_after();
         const uint32_t st = base + s * ATT_STAGE_BYTES;
 #pragma unroll
@@ -132,7 +149,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
           umma_bf16_ss(tmem + uint32_t(s * 256), adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
         }
         tc_commit(bar_oready);             // O_i complete (and P consumed)
-        tc_commit(bar_empty + 8u * s);     // stage s (Q, K, V) free for item i+2
+        tc_commit(bar_vempty + 8u * s);    // V of stage s free for item i+2
       }
     }
   } else {
@@ -176,16 +193,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
       const uint32_t t_row = tmem + (uint32_t(quad * 32) << 16) + uint32_t(sb * 256);
       mbar_wait(bar_sready + 8u * sb, (i >> 1) & 1u);
       tc_fence_after();
-      // ---- pass 1: row max over this thread's key range ----
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_row + c * 16, r);
-        tmem_wait_ld();
+      // ---- this thread's half row of S (7 or 6 chunks of 16 fp32) -> registers with ONE TMEM round trip ----
+      uint32_t r[7][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c * 16 + j < ATT_TOKENS) mx = fmaxf(mx, __uint_as_float(r[j]));
+      for (int cc = 0; cc < 7; ++cc)
+        if (cc < c_end - c_begin) tmem_ld_32x32b_x16(t_row + (c_begin + cc) * 16, r[cc]);
+      tmem_wait_ld();
+      // keys 197..207 of the last chunk are padding: force them to -inf once, so no per-element masking is needed
+      if (colhalf == 1) {
+#pragma unroll
+        for (int j = ATT_TOKENS - 192; j < 16; ++j) r[5][j] = 0xff800000u;   // chunk 12 = keys 192..207
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < 7; ++cc) {
+        if (cc < c_end - c_begin) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[cc][j]));
+        }
       }
       stat_max[sb * 256 + colhalf * 128 + row] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -196,29 +221,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
         mbar_wait(bar_oready, (i - 1) & 1u);
         tc_fence_after();
       }
-      // ---- pass 2: p = exp2(s*scale - max) -> bf16 -> swizzled smem; partial row sum ----
+      // ---- p = exp2(s*scale - max) -> bf16 -> swizzled smem; partial row sum (fp32) ----
       float sum = 0.f;
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_row + c * 16, r);
-        tmem_wait_ld();
-        uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float e0 = exp2f(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
-          const float e1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
-          // the row sum is taken over the bf16-rounded probabilities that the PV MMA actually consumes
-          const __nv_bfloat162 v2 = __floats2bfloat162_rn((c * 16 + 2 * j < ATT_TOKENS) ? e0 : 0.f,
-                                                          (c * 16 + 2 * j + 1 < ATT_TOKENS) ? e1 : 0.f);
-          sum += __low2float(v2) + __high2float(v2);
-          pk[j] = *reinterpret_cast<const uint32_t*>(&v2);
+      for (int cc = 0; cc < 7; ++cc) {
+        if (cc < c_end - c_begin) {
+          const int c = c_begin + cc;
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(r[cc][2 * j]), scale_log2, -mxs));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(r[cc][2 * j + 1]), scale_log2, -mxs));
+            sum += e0 + e1;
+            pk[j] = pack_bf16x2(e0, e1);
+          }
+          // P[row][c*16 .. +15] -> K-major SW128 atoms: atom = c/4 (64 keys each), 16-byte chunks (c%4)*2, +1
+          uint8_t* pa = smP + (c >> 2) * 16384;
+          const uint32_t ch = uint32_t(c & 3) * 2;
+          *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        // P[row][c*16 .. +15] -> K-major SW128 atoms: atom = c/4 (64 keys each), 16-byte chunks (c%4)*2, +1
-        uint8_t* pa = smP + (c >> 2) * 16384;
-        const uint32_t ch = uint32_t(c & 3) * 2;
-        *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
       stat_sum[sb * 256 + colhalf * 128 + row] = sum;
       // generic-proxy smem writes -> visible to the tensor core; TMEM reads of S ordered before PV overwrites [0,64)
