@@ -23,6 +23,30 @@ from . import _cabi
 from .encoder import MAX_PRIOR_TOKENS, TOKENS, VisionTransformer, _ParamBag, _linear_params
 
 
+class PackedDetections:
+    """The batch's detections as the kernels wrote them: flat per-field tensors + host-side CSR offsets.
+    `pairing` holds, per image b, a contiguous [2][M_b] block starting at 2*triplet_off[b]."""
+
+    def __init__(self, scores, labels, objects, pairing, boxes, triplet_off, box_off, size):
+        self.scores, self.labels, self.objects, self.pairing, self.boxes = scores, labels, objects, pairing, boxes
+        self.triplet_off, self.box_off, self.size = list(triplet_off), list(box_off), tuple(size)
+
+    @property
+    def num_images(self) -> int:
+        return len(self.triplet_off) - 1
+
+    def image(self, b: int) -> dict:
+        s, e = self.triplet_off[b], self.triplet_off[b + 1]
+        return dict(boxes=self.boxes[self.box_off[b]: self.box_off[b + 1]], pairing=self.pairing[2 * s: 2 * e].view(2, e - s),
+                    scores=self.scores[s:e], labels=self.labels[s:e], objects=self.objects[s:e],
+                    size=torch.tensor(self.size, dtype=torch.int64, device=self.scores.device))
+
+
+class DetectionList(list):
+    """List[dict] exactly as the reference returns it (U:1421-1425), plus `.packed` for the zero-copy gather."""
+    packed: "PackedDetections" = None
+
+
 class _NestedTensor:
     """Minimal stand-in for detr.util.misc.NestedTensor (tensors + padding mask), U:1592-1593."""
 
@@ -389,14 +413,20 @@ class UPT(nn.Module):
                    out_labels.data_ptr(), out_objects.data_ptr(), out_pairing.data_ptr(), img_off.data_ptr())
         # ---- the single device->host read of the path: per-image triplet offsets --------------------------------------
         offs = img_off.cpu().tolist()
-        sizes = torch.tensor([[img_h, img_w]] * B, device=dev, dtype=torch.int64)
-        detections = []
-        for b in range(B):
-            s, e = offs[b], offs[b + 1]
-            detections.append(dict(
-                boxes=region_props[b]["boxes"],
-                pairing=out_pairing[2 * s: 2 * e].view(2, e - s),
-                scores=out_scores[s:e], labels=out_labels[s:e], objects=out_objects[s:e], size=sizes[b]))
+        mtot = offs[-1]
+        sizes_m = [offs[b + 1] - offs[b] for b in range(B)]
+        size_t = torch.tensor([img_h, img_w], device=dev, dtype=torch.int64)
+        # bulk views (one split call per field) instead of 5 Python slices per image
+        sc_v = out_scores[:mtot].split(sizes_m)
+        lb_v = out_labels[:mtot].split(sizes_m)
+        ob_v = out_objects[:mtot].split(sizes_m)
+        pr_v = out_pairing[: 2 * mtot].split([2 * m for m in sizes_m])
+        detections = DetectionList(
+            dict(boxes=region_props[b]["boxes"], pairing=pr_v[b].view(2, sizes_m[b]), scores=sc_v[b], labels=lb_v[b],
+                 objects=ob_v[b], size=size_t) for b in range(B))
+        detections.packed = PackedDetections(scores=out_scores[:mtot], labels=out_labels[:mtot], objects=out_objects[:mtot],
+                                             pairing=out_pairing[: 2 * mtot], boxes=boxes, triplet_off=offs, box_off=box_off,
+                                             size=(img_h, img_w))
         if return_intermediates:
             inter = dict(prior=prior, mask=mask.bool(), tokens=tokens.view(B, TOKENS, 512),
                          logits=[logits[: ktot * Cn].view(ktot, Cn)[pair_off[b]: pair_off[b + 1]] for b in range(B)],

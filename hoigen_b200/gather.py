@@ -60,6 +60,52 @@ def unpack_detections(counts: torch.Tensor, floats: torch.Tensor, ints: torch.Te
     return out
 
 
+def gather_packed(packed, group=None):
+    """Exchange the flat per-field detection tensors of every rank with TWO collectives (sizes, then one padded byte
+    payload) and return a list of PackedDetections, one per rank, in rank order. No per-image Python work."""
+    from .detector import PackedDetections
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [packed]
+    world = dist.get_world_size(group)
+    dev = packed.scores.device
+    nimg = packed.num_images
+    meta = torch.tensor(packed.triplet_off + packed.box_off, dtype=torch.int64, device=dev)       # 2*(B+1)
+    # int64 fields first so every typed view of the byte payload stays 8-byte aligned
+    parts = [packed.labels.contiguous().view(torch.uint8), packed.objects.contiguous().view(torch.uint8),
+             packed.pairing.contiguous().view(torch.uint8), meta.view(torch.uint8),
+             packed.scores.contiguous().view(torch.uint8), packed.boxes.contiguous().view(torch.uint8).reshape(-1)]
+    payload = torch.cat(parts)
+    sizes = torch.tensor([payload.numel(), nimg, packed.scores.numel(), packed.boxes.shape[0]], dtype=torch.int64, device=dev)
+    all_sizes = torch.empty(world * 4, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+    all_sizes = all_sizes.view(world, 4).cpu().tolist()
+    cap = (max(r[0] for r in all_sizes) + 15) // 16 * 16
+    mine = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    mine[: payload.numel()] = payload
+    gathered = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    out = []
+    for r in range(world):
+        nbytes, nb, m, nbox = all_sizes[r]
+        buf = gathered[r * cap: r * cap + nbytes]
+        o = 0
+
+        def take(n_elems, dtype, esize):
+            nonlocal o
+            v = buf[o: o + n_elems * esize].view(dtype)
+            o += n_elems * esize
+            return v
+        lb = take(m, torch.int64, 8)
+        ob = take(m, torch.int64, 8)
+        pr = take(2 * m, torch.int64, 8)
+        mt_dev = take(2 * (nb + 1), torch.int64, 8)
+        sc = take(m, torch.float32, 4)
+        bx = take(nbox * 4, torch.float32, 4).view(nbox, 4)
+        mt = mt_dev.cpu().tolist() if r != dist.get_rank(group) else packed.triplet_off + packed.box_off
+        out.append(PackedDetections(sc, lb, ob, pr, bx, mt[: nb + 1], mt[nb + 1:], packed.size))
+    return out
+
+
 def gather_detections(dets: Sequence[Optional[dict]], group=None) -> List[dict]:
     """All ranks end up with the detections of every image, in global (rank-major, shard) order."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

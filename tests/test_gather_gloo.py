@@ -38,6 +38,53 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _fake_packed(rank, n_img):
+    from hoigen_b200.detector import PackedDetections
+    dets = _fake_dets(rank, n_img)
+    toff, boff = [0], [0]
+    for d in dets:
+        toff.append(toff[-1] + d["scores"].numel())
+        boff.append(boff[-1] + d["boxes"].shape[0])
+    pairing = torch.cat([d["pairing"].reshape(-1) for d in dets]) if dets else torch.zeros(0, dtype=torch.int64)
+    return dets, PackedDetections(torch.cat([d["scores"] for d in dets]), torch.cat([d["labels"] for d in dets]),
+                                  torch.cat([d["objects"] for d in dets]), pairing, torch.cat([d["boxes"] for d in dets]),
+                                  toff, boff, (224, 224))
+
+
+def _worker_packed(rank, world, port, q):
+    from hoigen_b200.gather import gather_packed
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_img = 3 + rank      # ragged shards, odd triplet counts (alignment of the byte payload)
+        _, mine = _fake_packed(rank, n_img)
+        got = gather_packed(mine)
+        ok = len(got) == world
+        for r in range(world):
+            ref_dets, _ = _fake_packed(r, 3 + r)
+            ok = ok and got[r].num_images == 3 + r
+            for b, e in enumerate(ref_dets):
+                a = got[r].image(b)
+                for k in ("boxes", "pairing", "scores", "labels", "objects"):
+                    ok = ok and torch.equal(a[k], e[k]) and a[k].dtype == e[k].dtype
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_packed_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_packed, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_shard_range_partitions():
     for total in (0, 1, 7, 512, 4097):
         for world in (1, 2, 8):
