@@ -101,6 +101,66 @@ def test_matches_oracle_fresh_inputs(cuda_device):
     print(f"N=4096: tokens max-abs {feat_err:.3e}")
 
 
+@pytest.mark.parametrize("num_classes,N,n_h,n_o,B", [(600, 1024, 8, 8, 3),      # config 5 shape: 600-triplet HICO classifier
+                                                     (117, 16384, 8, 8, 2),     # config 3 shape: 16k x 512 cache
+                                                     (24, 4096, 16, 16, 3)])    # config 4 shape: V-COCO, 32 boxes = 496 pairs
+def test_other_baseline_configs_match_oracle(cuda_device, num_classes, N, n_h, n_o, B):
+    """BASELINE.json configs 3-5 at small batch: same bars (indices bit-exact, logits <= 1e-2) against the oracle."""
+    from hoigen_b200 import synthetic as S
+    from oracle import hoi_forward_ref as O
+    m, enc, head = _build(num_classes, N, cuda_device, max_instances=16)
+    props = S.make_region_props(B, n_h, n_o, ragged=True)
+    imgs = S.make_images(B, seed=21)
+    dino = S.make_dino_features(B, seed=22)
+    o_dets, o_int = O.hoi_forward(imgs, props, dino, enc, head, return_intermediates=True)
+    dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                           return_intermediates=True)
+    worst = 0.0
+    for b in range(B):
+        for k in ("pairing", "labels", "objects"):
+            assert torch.equal(dets[b][k].cpu(), o_dets[b][k]), (b, k)
+        worst = max(worst, (inter["logits"][b].cpu() - o_int["logits"][b]).abs().max().item())
+        rel = ((dets[b]["scores"].cpu() - o_dets[b]["scores"]).abs() / o_dets[b]["scores"].abs().clamp_min(1e-30)).max().item()
+        assert rel <= SCORE_RTOL, rel
+    print(f"C={num_classes} N={N}: logits max-abs {worst:.3e}")
+    assert worst <= LOGIT_TOL, worst
+
+
+def test_full_batch_properties(cuda_device):
+    """BASELINE batch size (64 images): size-independent properties instead of the (slow) oracle — K = n_h*(n-1) pairs
+    per image in row-major order, labels drawn only from the object's target classes, triplet counts per pair equal
+    to the table row length, scores in (0,1), finite, and the batch result equals the same images run in two halves
+    (image independence => sharding across GPUs is exact)."""
+    from hoigen_b200 import synthetic as S
+    m, enc, head = _build(117, 4096, cuda_device)
+    B = 64
+    props = S.make_region_props(B, 8, 8, ragged=True)
+    imgs = S.make_images(B, seed=5).to(cuda_device)
+    dino = S.make_dino_features(B, seed=6).to(cuda_device)
+    pd = _props_to(props, cuda_device)
+    dets = m.forward_from_proposals(imgs, pd, dino)
+    table = head.object_class_to_target_class
+    for b, d in enumerate(dets):
+        n = props[b]["boxes"].shape[0]
+        nh = int((props[b]["labels"] == 0).sum())
+        pr = d["pairing"].cpu()
+        lab, obj = d["labels"].cpu(), d["objects"].cpu()
+        pairs = torch.unique_consecutive(pr, dim=1)
+        assert pairs.shape[1] == nh * (n - 1)
+        exp_x = torch.arange(nh).repeat_interleave(n - 1)
+        assert torch.equal(pairs[0], exp_x) and (pairs[0] != pairs[1]).all()
+        assert torch.equal(obj, props[b]["labels"][pr[1]])
+        for o in obj.unique().tolist():
+            assert set(lab[obj == o].tolist()) <= set(table[o])
+        assert d["scores"].numel() == sum(len(set(table[int(l)])) for l in props[b]["labels"][pairs[1]])
+        sc = d["scores"]
+        assert torch.isfinite(sc).all() and (sc > 0).all() and (sc < 1).all()
+    halves = list(m.forward_from_proposals(imgs[:32], pd[:32], dino[:32])) + list(m.forward_from_proposals(imgs[32:], pd[32:], dino[32:]))
+    for a, c in zip(dets, halves):
+        assert torch.equal(a["pairing"], c["pairing"]) and torch.equal(a["labels"], c["labels"])
+        assert torch.allclose(a["scores"], c["scores"], rtol=1e-5, atol=0)   # same kernels, tile shapes may differ with M
+
+
 def test_scoring_stage_given_identical_features(cuda_device):
     """a10 alone: feed the oracle's fp32 features, compare logits. bf16 operands (keys, features) with fp32
     accumulation and an exact fp32 bias carrier: max-abs <= 3e-3."""
