@@ -10,6 +10,8 @@
 // Replaces the cuBLAS SGEMMs the reference dispatches from CLIP_models_adapter_prior2.py:443-445 (in/out
 // proj), :428-432 (c_fc/c_proj), :184/:201 (adapter down/up), :491 (conv1 as GEMM), :505 (@ proj) and
 // upt_tip_cache_model_free_finetune_distill3.py:1156-1163 (cache / text GEMMs).
+#include <stdlib.h>
+
 #include <map>
 #include <string>
 
@@ -34,6 +36,7 @@ struct GemmArgs {
   int ld_f32;
   __nv_bfloat16* out_bf16;
   int ld_bf16;
+  int debug;  // diagnostics only (HOIGEN_GEMM_DEBUG): 1 = TMA loads without MMAs, 2 = MMAs without TMA loads
 };
 
 template <int BN>
@@ -88,27 +91,49 @@ __device__ __forceinline__ void prefetch_residual_row(const GemmArgs& g, int row
 
 constexpr int CW = 16;  // columns per epilogue chunk (register budget: two chunks of accumulators + residual in flight)
 
+// out_tile != nullptr: bf16 results go to the 128B-swizzled smem staging tile (64-column panels of 16 KiB, row = rrow)
+// for a TMA store instead of per-thread global stores; tile_col = column of this chunk inside the tile.
+template <int EPI>
 __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const uint32_t (&r)[CW], const float4 (&res)[CW / 4],
                                                        bool res_vec, const float* res_row, const float* s_bias,
-                                                       const float* s_cs, int row, bool row_ok, int col0) {
+                                                       const float* s_cs, int row, bool row_ok, int col0,
+                                                       uint8_t* out_tile = nullptr, int rrow = 0, int tile_col = 0) {
   const bool full_chunk = (col0 + CW <= g.N);
+  // EPI >= 0: the epilogue recipe is a compile-time constant (act | colscale << 4 | bias << 5), no work for absent terms
+  const int act = EPI >= 0 ? (EPI & 15) : g.act;
+  const bool has_cs = EPI >= 0 ? ((EPI >> 4) & 1) != 0 : true;
+  const bool has_bias = EPI >= 0 ? ((EPI >> 5) & 1) != 0 : true;
   float v[CW];
 #pragma unroll
-  for (int j = 0; j < CW; j += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(s_bias + j);
-    v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
-    v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
-  }
-  if (g.act != HOIGEN_ACT_NONE) {
+  for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+  if (has_bias) {
 #pragma unroll
-    for (int j = 0; j < CW; ++j) v[j] = apply_act(v[j], g.act);
+    for (int j = 0; j < CW; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(s_bias + j);
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
   }
+  if (act != HOIGEN_ACT_NONE) {
 #pragma unroll
-  for (int j = 0; j < CW; j += 4) {
-    const float4 c = *reinterpret_cast<const float4*>(s_cs + j);
-    v[j] *= c.x; v[j + 1] *= c.y; v[j + 2] *= c.z; v[j + 3] *= c.w;
+    for (int j = 0; j < CW; ++j) v[j] = apply_act(v[j], act);
   }
-  if (!row_ok) return;
+  if (has_cs) {
+#pragma unroll
+    for (int j = 0; j < CW; j += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(s_cs + j);
+      v[j] *= c.x; v[j + 1] *= c.y; v[j + 2] *= c.z; v[j + 3] *= c.w;
+    }
+  }
+  if (out_tile) {
+    uint8_t* panel = out_tile + (tile_col >> 6) * 16384;
+    const uint32_t ch = uint32_t(tile_col & 63) >> 3;
+    *reinterpret_cast<uint4*>(panel + sw128_offset(rrow, ch)) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(panel + sw128_offset(rrow, ch + 1)) =
+        make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    return;
+  }
+  if (!row_ok || g.debug == 3) return;
   if (g.residual) {
     if (res_vec && full_chunk) {
 #pragma unroll
@@ -153,9 +178,10 @@ __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const 
 }
 
 // s_bias / s_cs point at this warp's first column (colbase) inside the staged vectors. COLS = columns per warp.
-template <int COLS, typename WaitFn>
+template <int COLS, int EPI, typename WaitFn>
 __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int colbase, uint32_t t_addr, const float* s_bias,
-                                              const float* s_cs, WaitFn wait_acc) {
+                                              const float* s_cs, WaitFn wait_acc, uint8_t* out_tile = nullptr, int rrow = 0,
+                                              int tile_col0 = 0) {
   constexpr int CHUNKS = COLS / CW;
   const bool row_ok = row < g.M;
   const bool res_vec = g.residual && row_ok && (g.ld_res & 3) == 0;
@@ -167,7 +193,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
     for (int j = 0; j < CW / 4; ++j) res[0][j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
   }
   wait_acc();
-  if (colbase >= g.N) return;  // warp-uniform: nothing to do for this half
+  if (colbase >= g.N || g.debug == 4) return;  // warp-uniform: nothing to do for this half
   tmem_ld_32x32b_x16(t_addr, r[0]);
 #pragma unroll
   for (int c = 0; c < CHUNKS; ++c) {
@@ -182,7 +208,8 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
           res[(c + 1) & 1][j] = *reinterpret_cast<const float4*>(res_row + col0 + CW + 4 * j);
       }
     }
-    epilogue_process_chunk(g, r[c & 1], res[c & 1], res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0);
+    epilogue_process_chunk<EPI>(g, r[c & 1], res[c & 1], res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0,
+                           out_tile, rrow, tile_col0 + c * CW);
     if (!more) break;
   }
   tmem_wait_ld();
@@ -305,7 +332,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* s_bias = reinterpret_cast<float*>(tiles + STAGES * Cfg::STAGE_BYTES + 256) + (it & 1) * 2 * BN;
       float* s_cs = s_bias + BN;
       epilogue_stage_vectors<BN>(g, n_blk * BN, s_bias, s_cs, threadIdx.x - 64);
-      epilogue_warp<BN / 2>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
+      epilogue_warp<BN / 2, -1>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
         mbar_wait(bar_tfull + 8u * acc, acc_phase);
         tc_fence_after();
       });
@@ -336,27 +363,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //   tmem_full[a] (per CTA)   tcgen05.commit multicast
 //   tmem_empty[a](leader's)  16 arrivals: 8 epilogue warps of each CTA
 // ---------------------------------------------------------------------------------------------
-template <int BN>
+// TMA_OUT: bf16-only outputs are staged in a swizzled smem tile and written with TMA stores (full-line writes, and
+// the TMEM accumulator is released as soon as it has been read, not when the global stores have been issued).
+template <int BN, bool TMA_OUT>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;          // 16 KiB: this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * BK * 2;    // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int OUT_BYTES = TMA_OUT ? (BN / 64) * 16384 : 0;
+  static constexpr int STAGES_FIT = (196608 - OUT_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int ACC_STRIDE = 256;               // TMEM columns between the two accumulator stages
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * BN * 4;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 4 * BN * 4;
 };
 
-template <int BN>
+template <int BN, bool TMA_OUT, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
-  using Cfg = Gemm2Cfg<BN>;
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, GemmArgs g) {
+  using Cfg = Gemm2Cfg<BN, TMA_OUT>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + Cfg::BAR_OFF);
+  uint8_t* out_stage = tiles + STAGES * Cfg::STAGE_BYTES;   // TMA_OUT staging tile (1024-aligned)
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8u * STAGES;
   const uint32_t bar_tfull = bar_full + 16u * STAGES;
@@ -408,10 +442,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t a_dst = tiles_addr + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + Cfg::A_BYTES;
           const uint32_t full = bar_full + 8u * stage;
-          if (rank == 0) mbar_arrive_expect_tx(full, 2 * Cfg::STAGE_BYTES);
-          else mbar_arrive_leader(full);
-          tma_load_2d_2sm(a_dst, &tmA, full, kb * BK, m_blk * (2 * BM) + int(rank) * BM);
-          tma_load_2d_2sm(b_dst, &tmB, full, kb * BK, n_blk * BN + int(rank) * (BN / 2));
+          if (g.debug == 2) {   // diagnostics: no loads, just hand the stage over
+            if (rank == 0) mbar_arrive(full); else mbar_arrive_leader(full);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(full, 2 * Cfg::STAGE_BYTES);
+            else mbar_arrive_leader(full);
+            tma_load_2d_2sm(a_dst, &tmA, full, kb * BK, m_blk * (2 * BM) + int(rank) * BM);
+            tma_load_2d_2sm(b_dst, &tmB, full, kb * BK, n_blk * BN + int(rank) * (BN / 2));
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -434,11 +472,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t a_addr = tiles_addr + stage * Cfg::STAGE_BYTES;
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          if (g.debug != 1) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = make_sdesc_sw128(a_addr + k * (UMMA_K * 2));
-            const uint64_t bdesc = make_sdesc_sw128(b_addr + k * (UMMA_K * 2));
-            umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = make_sdesc_sw128(a_addr + k * (UMMA_K * 2));
+              const uint64_t bdesc = make_sdesc_sw128(b_addr + k * (UMMA_K * 2));
+              umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           tc_commit_2sm(bar_empty + 8u * stage);   // frees the stage in BOTH CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -464,17 +504,30 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int row = m_blk * (2 * BM) + int(rank) * BM + quad * 32 + lane;
       const int colbase = n_blk * BN + half * (BN / 2);
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_STRIDE + half * (BN / 2));
-      float* s_bias = reinterpret_cast<float*>(tiles + STAGES * Cfg::STAGE_BYTES + 256) + (it & 1) * 2 * BN;
+      float* s_bias = reinterpret_cast<float*>(tiles + Cfg::BAR_OFF + 256) + (it & 1) * 2 * BN;
       float* s_cs = s_bias + BN;
-      epilogue_stage_vectors<BN>(g, n_blk * BN, s_bias, s_cs, threadIdx.x - 64);
-      epilogue_warp<BN / 2>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
+      if (TMA_OUT && threadIdx.x == 64) tma_store_wait_read();   // previous tile's TMA stores have drained the staging tile
+      epilogue_stage_vectors<BN>(g, n_blk * BN, s_bias, s_cs, threadIdx.x - 64);   // (contains the epilogue-wide barrier)
+      epilogue_warp<BN / 2, EPI>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
         mbar_wait(bar_tfull + 8u * acc, acc_phase);
         tc_fence_after();
-      });
+      }, TMA_OUT ? out_stage : nullptr, quad * 32 + lane, half * (BN / 2));
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * acc);
+      if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * acc);   // TMEM drained: the next-but-one tile's MMAs may start
+      if (TMA_OUT) {
+        fence_proxy_async_smem();                                  // staging writes -> visible to the TMA engine
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int row0 = m_blk * (2 * BM) + int(rank) * BM;
+#pragma unroll
+          for (int pnl = 0; pnl < BN / 64; ++pnl)
+            if (n_blk * BN + pnl * 64 < g.N) tma_store_2d(&tmC, smem_u32(out_stage) + pnl * 16384, n_blk * BN + pnl * 64, row0);
+          tma_store_commit();
+        }
+      }
     }
+    if (TMA_OUT && threadIdx.x == 64) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -533,6 +586,8 @@ static GemmArgs to_args(const hoigen_gemm_params* p) {
   g.residual = p->residual; g.ld_res = p->ld_res;
   g.out_f32 = p->out_f32; g.ld_f32 = p->ld_f32;
   g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16); g.ld_bf16 = p->ld_bf16;
+  static const int dbg = getenv("HOIGEN_GEMM_DEBUG") ? atoi(getenv("HOIGEN_GEMM_DEBUG")) : 0;
+  g.debug = dbg;
   return g;
 }
 
@@ -566,12 +621,12 @@ static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
   return HOIGEN_OK;
 }
 
-template <int BN>
-static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
+template <int BN, bool TMA_OUT, int EPI>
+static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN, TMA_OUT>;
   static bool attr_set = false;
   if (!attr_set) {
-    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, TMA_OUT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -579,6 +634,11 @@ static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream) {
   if (!ta) return HOIGEN_ERR_CUDA;
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN / 2);
   if (!tb) return HOIGEN_ERR_CUDA;
+  const CUtensorMap* tc = ta;   // unused unless TMA_OUT
+  if (TMA_OUT) {
+    tc = get_tmap_2d_bf16(p->out_bf16, uint64_t(p->N), uint64_t(p->M), uint64_t(p->ld_bf16) * 2, 64, BM);
+    if (!tc) return HOIGEN_ERR_CUDA;
+  }
   const int num_tiles = ((p->M + 2 * BM - 1) / (2 * BM)) * ((p->N + BN - 1) / BN);
   const int max_clusters = num_sms() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
@@ -596,9 +656,24 @@ static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream) {
   cfg.numAttrs = 1;
   KernelScope ks(gemm_tag(p->N, p->K), stream, 2.0 * p->M * p->N * p->K,
                  2.0 * (double(p->M) * p->K + double(p->N) * p->K) + double(p->M) * p->N * ((p->out_f32 ? 4 : 0) + (p->out_bf16 ? 2 : 0) + (p->residual ? 4 : 0)));
-  HOIGEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN>, *ta, *tb, to_args(p)));
+  HOIGEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, TMA_OUT, EPI>, *ta, *tb, *tc, to_args(p)));
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
+}
+
+template <int BN>
+static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream) {
+  // bf16-only outputs with TMA-compatible strides go through the smem-staged TMA-store epilogue
+  static const bool no_tma_out = getenv("HOIGEN_GEMM_NO_TMA_STORE") != nullptr;
+  const bool tma_out = !no_tma_out && p->out_bf16 && !p->out_f32 && !p->residual && (p->ld_bf16 % 8) == 0 && (p->N % 8) == 0;
+  if (!tma_out) return launch_gemm2_impl<BN, false, -1>(p, stream);
+  // compile-time epilogue recipes of the encoder's bf16-output GEMMs; anything else uses the runtime-flag epilogue
+  const bool b = p->bias != nullptr, c = p->colscale != nullptr;
+  if (b && !c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 5)>(p, stream);                          // QKV, out-proj
+  if (b && !c && p->act == HOIGEN_ACT_QUICKGELU) return launch_gemm2_impl<BN, true, (1 << 5) | HOIGEN_ACT_QUICKGELU>(p, stream);  // c_fc
+  if (b && c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 5) | (1 << 4)>(p, stream);                 // adapter up-proj
+  if (!b && !c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, 0>(p, stream);                                 // cache affinity
+  return launch_gemm2_impl<BN, true, -1>(p, stream);
 }
 
 // Pick (cta pair?, BN): fewest scheduling rounds x relative tile time. The one-CTA kernel is L2-operand-bound
@@ -623,7 +698,7 @@ static void choose_config(int M, int N, int* pair, int* bn) {
       if (N <= b / 2) continue;
       const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + b - 1) / b);
       const int rounds = (tiles + sms / 2 - 1) / (sms / 2);
-      const double cost = rounds * (double(b) + 40.0);
+      const double cost = rounds * (double(b) + 96.0);
       if (cost < best) { best = cost; *pair = 1; *bn = b; }
     }
   }

@@ -67,6 +67,24 @@ def test_gemm_epilogue(cuda_device, act, bn):
     assert (ob.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item()   # one bf16 rounding
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(1000, 776, 320, 2192), (2500, 2304, 768, 2256), (333, 200, 64, 2128), (12608, 768, 64, 0),
+                                      (129, 64, 192, 2128)])
+def test_gemm_bf16_only_output_tma_store(cuda_device, M, N, K, bn):
+    """bf16-only outputs of the CTA-pair kernel go through the smem-staged TMA-store epilogue (ragged M, N % 64 != 0)."""
+    from hoigen_b200 import _cabi
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).bfloat16().to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16().to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    cs = (torch.rand(N, generator=g) + 0.5).to(cuda_device)
+    ld = N + 8
+    ob = torch.full((M + 3, ld), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.gemm_bf16(a, w, bias=bias, colscale=cs, act=1, out_bf16=ob[:M, :N], block_n=bn)
+    ref = _ref_gemm(a, w, bias, 1, cs, None)
+    assert (ob[:M, :N].float() - ref).abs().max().item() < 2 ** -7 * max(1.0, ref.abs().max().item())
+    assert (ob[M:] == 7.0).all() and (ob[:, N:] == 7.0).all()      # nothing written outside the M x N window
+
+
 def test_gemm_rejects_bad_arguments(cuda_device):
     from hoigen_b200 import _cabi
     a = torch.zeros(16, 20, device=cuda_device, dtype=torch.bfloat16)   # lda = 20 is not a multiple of 8
