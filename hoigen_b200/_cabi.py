@@ -97,9 +97,9 @@ def ptr(t: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
-class AdapterMidWeights(C.Structure):
+class AdapterWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "wq", "wo", "w1", "w2", "in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w", "norm2_b", "norm3_w",
+        "wd", "down_b", "wq", "wo", "w1", "w2", "in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w", "norm2_b", "norm3_w",
         "norm3_b")]
 
 
@@ -114,7 +114,7 @@ class EncoderWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ENCODER_WEIGHT_FIELDS]
 
 
-ENCODER_BUFFER_FIELDS = ("patches", "patch_emb", "x", "xb", "h", "qkv", "attn", "mlp", "delta", "adapter_d", "adapter_db", "adapter_t",
+ENCODER_BUFFER_FIELDS = ("patches", "patch_emb", "x", "xb", "h", "qkv", "attn", "mlp", "delta", "delta2", "adapter_t",
                          "adapter_kv", "tokens_out")
 
 
@@ -149,9 +149,9 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_patchify_bf16": [_P, _P, _I, _P],
     "hoigen_embed_lnpre": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
     "hoigen_layernorm768": [_P, _P, _P, _P, _P, _I, _P],
-    "hoigen_add_layernorm768": [_P, _P, _P, _P, _P, _I, _P],
+    "hoigen_add_layernorm768": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
     "hoigen_adapter_kv": [_P, _P, _P, _P, _I, _I, _P],
-    "hoigen_adapter_mid": [_P, _P, _P, _P, C.POINTER(AdapterMidWeights), _P, _I, _I, _P],
+    "hoigen_adapter_block": [_P, _P, _P, _P, C.POINTER(AdapterWeights), _P, _I, _I, _P],
     "hoigen_attention": [_P, _P, _I, _P],
     "hoigen_encoder_forward": [C.POINTER(EncoderWeights), C.POINTER(EncoderBuffers), _P, _P, _P, _I, _I, _I, _P],
     "hoigen_prior_tokens": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P],

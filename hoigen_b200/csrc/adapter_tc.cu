@@ -1,7 +1,10 @@
 // InsAdapter bottleneck body on the tensor cores: one CTA per 128-token tile, two threads per token row
 // (one per attention head / column half).
 //
-//   q  = D Wq^T + bq                         UMMA 128x64x64   (D = relu(down_proj(x)) as bf16 tile, TMA-loaded)
+//   D = relu((xb + delta_c) Wd^T + bd)       12 or 24 x UMMA 128x64x64 fed by a 4-stage TMA ring: the down-projection
+//                                            with the pending residual of the previous block's MLP output folded in by
+//                                            linearity (xb Wd^T + delta_c Wd^T), no thread touches the operands
+//   q  = D Wq^T + bq                         UMMA 128x64x64
 //   a  = softmax_2heads(q K^T / sqrt(32)) V  registers; K/V (<= 32 unmasked prior tokens of the tile's <= 2 images) in smem
 //   t  = LN_norm2(D + a Wo^T + bo)           UMMA 128x64x64   + per-thread LayerNorm over 64 registers
 //   h  = relu(t W1^T + b1)                   UMMA 128x128x64
@@ -35,7 +38,8 @@ constexpr int AT_SMEM_BYTES = AT_MISC + 512 + 2048 + 1024;
 constexpr int AT_TMEM_COLS = 128;
 
 struct AdapterTcArgs {
-  const float* d_f32;        // (M,64) fp32 copy of D for the residual
+  int has_delta;             // 1: the adapter input is xb + delta_c (pending residual of the previous block's MLP)
+  const float* bd;           // (64) down_proj bias
   const float* kv;           // (B*n_max,128) this layer
   const uint8_t* mask;       // (B,n_max) 1 = padding
   const float* bq;           // in_proj bias (q part = first 64)
@@ -87,7 +91,8 @@ __device__ __forceinline__ void ln64_pair(float (&v)[32], int half, int rrow, fl
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
-adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmWq,
+adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDelta,
+                  const __grid_constant__ CUtensorMap tmWd, const __grid_constant__ CUtensorMap tmWq,
                   const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, AdapterTcArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -97,8 +102,10 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AT_MISC);
   const uint32_t bar_ld = smem_u32(bars);
   const uint32_t bar_mma = bar_ld + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  int* s_nkeys = reinterpret_cast<int*>(bars + 3);           // [2]
+  const uint32_t bar_full0 = bar_ld + 16;                     // [4] phase-0 ring: A + Wd k-block landed
+  const uint32_t bar_empty0 = bar_ld + 48;                    // [4] phase-0 ring: stage consumed by its MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  int* s_nkeys = reinterpret_cast<int*>(bars + 11);          // [2]
   int* s_keyidx = s_nkeys + 2;                               // [2][32]
   float* red = reinterpret_cast<float*>(sm + AT_MISC + 512); // [2][2][128] LayerNorm partials
   float* sKV = reinterpret_cast<float*>(sm + AT_KV);
@@ -115,10 +122,15 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
   const int b1 = min(r0 + 127, g.M - 1) / AT_TOKENS;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tmD); tma_prefetch_desc(&tmWq); tma_prefetch_desc(&tmWo);
+    tma_prefetch_desc(&tmWd); tma_prefetch_desc(&tmWq); tma_prefetch_desc(&tmWo);
     tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     mbar_init(bar_ld, 1);
     mbar_init(bar_mma, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar_full0 + 8u * i, 1);
+      mbar_init(bar_empty0 + 8u * i, 1);
+    }
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDelta);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -140,16 +152,65 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  uint32_t mma_phase = 0;
+  const uint32_t t_row = tmem + (uint32_t((warp & 3) * 32) << 16);
+  // ---------------- phase 0: D = relu((xb + delta_c) Wd^T + bd) as ONE accumulation over the concatenated K ------------
+  // A k-blocks come straight from the bf16 stream copy xb (12 k-blocks) and, if pending, from delta_c (12 more, the same
+  // Wd k-blocks again): (xb + delta_c) Wd^T = xb Wd^T + delta_c Wd^T.  Pure TMA -> UMMA, no thread touches the data.
+  // Ring of 4 stages x [A 16 KiB | Wd 8 KiB] in [P+16K, end of KV) — those regions are (re)loaded afterwards.
+  constexpr int AT_RING = AT_P + 16384;
+  constexpr int RING_STAGE = 16384 + 8192;
+  const int nkb = g.has_delta ? 24 : 12;
+  if (warp == 1 && lane == 0) {            // TMA producer
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb & 3;
+      if (kb >= 4) mbar_wait(bar_empty0 + 8u * st, ((kb >> 2) - 1) & 1u);
+      const uint32_t dst = base + AT_RING + st * RING_STAGE;
+      const uint32_t full = bar_full0 + 8u * st;
+      mbar_arrive_expect_tx(full, RING_STAGE);
+      const int kk = (kb % 12) * 64;
+      tma_load_2d(dst, kb < 12 ? &tmX : &tmDelta, full, kk, r0);
+      tma_load_2d(dst + 16384, &tmWd, full, kk, 0);
+    }
+  } else if (tid == 0) {                   // MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb & 3;
+      mbar_wait(bar_full0 + 8u * st, (kb >> 2) & 1u);
+      tc_fence_after();
+      const uint32_t a_addr = base + AT_RING + st * RING_STAGE;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_ss(tmem, make_sdesc_sw128(a_addr + k * 32), make_sdesc_sw128(a_addr + 16384 + k * 32), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+      tc_commit(bar_empty0 + 8u * st);
+    }
+    tc_commit(bar_mma);
+  }
+  float d[32];   // this thread's half row of D (fp32) — also the residual of the norm2 step
+  mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  tc_fence_after();
+  // Wd is dead: bring in the four body weight matrices; stage K | V of the compacted keys meanwhile
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_ld, 16384 + 8192 + 8192 + 16384 + 16384);
-    tma_load_2d(base + AT_A0, &tmD, bar_ld, 0, r0);
+    mbar_arrive_expect_tx(bar_ld, 8192 + 8192 + 16384 + 16384);
     tma_load_2d(base + AT_WQ, &tmWq, bar_ld, 0, 0);
     tma_load_2d(base + AT_WO, &tmWo, bar_ld, 0, 0);
     tma_load_2d(base + AT_W1, &tmW1, bar_ld, 0, 0);
     tma_load_2d(base + AT_W2, &tmW2, bar_ld, 0, 0);
     tma_load_2d(base + AT_W2 + 8192, &tmW2, bar_ld, 64, 0);
   }
-  // stage K | V rows of the compacted keys (fp32) while the TMA loads fly
+  {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + half * 32, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bd + half * 32 + i));
+      d[i] = fmaxf(__uint_as_float(r[i]) + bb.x, 0.f); d[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + bb.y, 0.f);
+      d[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + bb.z, 0.f); d[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + bb.w, 0.f);
+    }
+    store_row_bf16<32>(sm + AT_A0, rrow, half * 4, d);
+  }
   for (int img = 0; img < 2; ++img) {
     const int b = img == 0 ? b0 : b1;
     const int n = s_nkeys[img];
@@ -159,9 +220,10 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
       reinterpret_cast<float4*>(sKV + (img * AT_MAXKEYS + j) * 128)[c4] = v;
     }
   }
+  fence_proxy_async_smem();
+  tc_fence_before();
   __syncthreads();
 
-  uint32_t mma_phase = 0;
   // ---------------- MMA 1: q = D Wq^T ----------------
   if (tid == 0) {
     mbar_wait(bar_ld, 0);
@@ -174,7 +236,6 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
   }
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
   tc_fence_after();
-  const uint32_t t_row = tmem + (uint32_t((warp & 3) * 32) << 16);
 
   // ---------------- cross-attention: this thread's head (= half) of its row ----------------
   {
@@ -251,15 +312,8 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
     tc_commit(bar_mma);
   }
   float t[32];
-  {
-    // residual D (fp32) for this thread's half row while the MMA runs
-    const float4* dsrc = reinterpret_cast<const float4*>(g.d_f32 + size_t(row_ok ? row : 0) * 64 + half * 32);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 d = __ldg(dsrc + i);
-      t[4 * i] = d.x; t[4 * i + 1] = d.y; t[4 * i + 2] = d.z; t[4 * i + 3] = d.w;
-    }
-  }
+  for (int i = 0; i < 32; ++i) t[i] = d[i];     // residual D (fp32, still in registers from phase 0)
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
   tc_fence_after();
   {
@@ -356,34 +410,38 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
 
 extern "C" {
 
-int hoigen_adapter_mid(const float* d_f32, const void* d_bf16, const float* kv_layer, const uint8_t* mask,
-                       const hoigen_adapter_mid_weights* w, void* out_bf16, int32_t batch, int32_t n_max,
-                       hoigen_stream_t stream) {
+int hoigen_adapter_block(const void* xb, const void* delta_c, const float* kv_layer, const uint8_t* mask,
+                         const hoigen_adapter_weights* w, void* out_bf16, int32_t batch, int32_t n_max,
+                         hoigen_stream_t stream) {
   using namespace hoigen;
-  HOIGEN_CHECK_ARG(d_f32 && d_bf16 && kv_layer && mask && w && out_bf16 && batch > 0, "adapter_mid: bad arguments");
-  HOIGEN_CHECK_ARG(w->wq && w->wo && w->w1 && w->w2, "adapter_mid: null weight");
-  HOIGEN_CHECK_ARG(n_max > 0 && n_max <= AT_MAXKEYS, "adapter_mid: n_max must be in [1,%d] (got %d)", AT_MAXKEYS, n_max);
+  HOIGEN_CHECK_ARG(xb && kv_layer && mask && w && out_bf16 && batch > 0, "adapter_block: bad arguments");
+  HOIGEN_CHECK_ARG(w->wd && w->wq && w->wo && w->w1 && w->w2 && w->down_b, "adapter_block: null weight");
+  HOIGEN_CHECK_ARG(n_max > 0 && n_max <= AT_MAXKEYS, "adapter_block: n_max must be in [1,%d] (got %d)", AT_MAXKEYS, n_max);
   static bool attr_set = false;
   if (!attr_set) {
     HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(adapter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
     attr_set = true;
   }
   const int M = batch * AT_TOKENS;
-  const CUtensorMap* td = get_tmap_2d_bf16(d_bf16, 64, uint64_t(M), 128, 64, 128);
+  const CUtensorMap* tx = get_tmap_2d_bf16(xb, 768, uint64_t(M), 1536, 64, 128);
+  const CUtensorMap* tdl = delta_c ? get_tmap_2d_bf16(delta_c, 768, uint64_t(M), 1536, 64, 128) : tx;
+  const CUtensorMap* td = get_tmap_2d_bf16(w->wd, 768, 64, 1536, 64, 64);
   const CUtensorMap* tq = get_tmap_2d_bf16(w->wq, 64, 64, 128, 64, 64);
   const CUtensorMap* to = get_tmap_2d_bf16(w->wo, 64, 64, 128, 64, 64);
   const CUtensorMap* t1 = get_tmap_2d_bf16(w->w1, 64, 128, 128, 64, 128);
   const CUtensorMap* t2 = get_tmap_2d_bf16(w->w2, 128, 64, 256, 64, 64);
-  if (!td || !tq || !to || !t1 || !t2) return HOIGEN_ERR_CUDA;
+  if (!tx || !tdl || !td || !tq || !to || !t1 || !t2) return HOIGEN_ERR_CUDA;
   AdapterTcArgs a;
-  a.d_f32 = d_f32; a.kv = kv_layer; a.mask = mask;
+  a.has_delta = delta_c ? 1 : 0; a.bd = w->down_b;
+  a.kv = kv_layer; a.mask = mask;
   a.bq = w->in_proj_b; a.bo = w->out_proj_b; a.b1 = w->linear1_b; a.b2 = w->linear2_b;
   a.n2_w = w->norm2_w; a.n2_b = w->norm2_b; a.n3_w = w->norm3_w; a.n3_b = w->norm3_b;
   a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   a.M = M; a.n_max = n_max; a.batch = batch;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  KernelScope ks("adapter_mid", s, 2.0 * M * (64 * 64 * 2 + 2 * 64 * 128 + 2 * 64 * n_max), double(M) * 64 * (4 + 2 + 2));
-  adapter_tc_kernel<<<(M + 127) / 128, AT_THREADS, AT_SMEM_BYTES, s>>>(*td, *tq, *to, *t1, *t2, a);
+  KernelScope ks("adapter_block", s, 2.0 * M * (768 * 64 * (delta_c ? 2 : 1) + 64 * 64 * 2 + 2 * 64 * 128 + 2 * 64 * n_max),
+                 double(M) * (768 * 2 * (delta_c ? 2 : 1) + 64 * 2));
+  adapter_tc_kernel<<<(M + 127) / 128, AT_THREADS, AT_SMEM_BYTES, s>>>(*tx, *tdl, *td, *tq, *to, *t1, *t2, a);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }

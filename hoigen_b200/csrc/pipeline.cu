@@ -46,43 +46,48 @@ int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder
   // ---- adapter K/V of the prior tokens, all layers at once ------------------------------------------------
   HOIGEN_TRY(hoigen_adapter_kv(prior, w->ad_in_proj_w, w->ad_in_proj_b, buf->adapter_kv, batch * n_max, 12, s));
 
+  // Residual adds are DEFERRED out of the GEMM epilogues: every GEMM that feeds the fp32 stream writes a bf16 delta
+  // (TMA-store epilogue) and the next LayerNorm pass (which streams x anyway) applies it.  The MLP output of layer
+  // l-1 (delta2) is consumed twice: by linearity inside the adapter block's down-projection, and by ln_1's pass.
   for (int l = 0; l < num_layers; ++l) {
     const size_t o768 = size_t(l) * D, o64 = size_t(l) * 64;
-    // (1) adapter: down-proj + ReLU (tensor cores) -> bottleneck body (SIMT) -> up-proj * scale + residual
-    HOIGEN_TRY(gemm(buf->xb, D, (const uint16_t*)w->ad_down_w + size_t(l) * 64 * D, D, M, 64, D, w->ad_down_b + o64,
-                    HOIGEN_ACT_RELU, nullptr, nullptr, 0, buf->adapter_d, 64, buf->adapter_db, 64, s));
-    hoigen_adapter_mid_weights mw;
-    mw.wq = (const uint16_t*)w->ad_wq + size_t(l) * 64 * 64; mw.wo = (const uint16_t*)w->ad_wo + size_t(l) * 64 * 64;
-    mw.w1 = (const uint16_t*)w->ad_w1 + size_t(l) * 128 * 64; mw.w2 = (const uint16_t*)w->ad_w2 + size_t(l) * 64 * 128;
-    mw.in_proj_b = w->ad_in_proj_b + size_t(l) * 192;
-    mw.out_proj_b = w->ad_out_proj_b + o64;
-    mw.linear1_b = w->ad_linear1_b + size_t(l) * 128;
-    mw.linear2_b = w->ad_linear2_b + o64;
-    mw.norm2_w = w->ad_norm2_w + o64; mw.norm2_b = w->ad_norm2_b + o64;
-    mw.norm3_w = w->ad_norm3_w + o64; mw.norm3_b = w->ad_norm3_b + o64;
-    HOIGEN_TRY(hoigen_adapter_mid(buf->adapter_d, buf->adapter_db, buf->adapter_kv + size_t(l) * batch * n_max * 128, mask, &mw,
-                                  buf->adapter_t, batch, n_max, s));
-    // The residual adds of the two short-K GEMMs (up-proj K=64, out-proj K=768) are deferred into the LayerNorm that
-    // follows: their MMA time is too short to hide a read-modify-write epilogue on the fp32 stream, whereas the
-    // LayerNorm kernel streams the same rows anyway.
+    // (1) x += mlp(l-1) ; adapter: down-proj + body (one tensor-core kernel) ; up-proj * scale -> delta
+    hoigen_adapter_weights aw;
+    aw.wd = (const uint16_t*)w->ad_down_w + size_t(l) * 64 * D; aw.down_b = w->ad_down_b + o64;
+    aw.wq = (const uint16_t*)w->ad_wq + size_t(l) * 64 * 64; aw.wo = (const uint16_t*)w->ad_wo + size_t(l) * 64 * 64;
+    aw.w1 = (const uint16_t*)w->ad_w1 + size_t(l) * 128 * 64; aw.w2 = (const uint16_t*)w->ad_w2 + size_t(l) * 64 * 128;
+    aw.in_proj_b = w->ad_in_proj_b + size_t(l) * 192;
+    aw.out_proj_b = w->ad_out_proj_b + o64;
+    aw.linear1_b = w->ad_linear1_b + size_t(l) * 128;
+    aw.linear2_b = w->ad_linear2_b + o64;
+    aw.norm2_w = w->ad_norm2_w + o64; aw.norm2_b = w->ad_norm2_b + o64;
+    aw.norm3_w = w->ad_norm3_w + o64; aw.norm3_b = w->ad_norm3_b + o64;
+    HOIGEN_TRY(hoigen_adapter_block(buf->xb, l == 0 ? nullptr : buf->delta2, buf->adapter_kv + size_t(l) * batch * n_max * 128,
+                                    mask, &aw, buf->adapter_t, batch, n_max, s));
     HOIGEN_TRY(gemm(buf->adapter_t, 64, (const uint16_t*)w->ad_up_w + size_t(l) * D * 64, 64, M, D, 64,
                     w->ad_up_b + o768, HOIGEN_ACT_NONE, w->ad_scale + o768, nullptr, 0, nullptr, 0, buf->delta, D, s));
     // (2) x += adapter ; x += out_proj(attention(ln_1(x)))
-    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, w->ln1_w + o768, w->ln1_b + o768, buf->h, M, s));
+    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, l == 0 ? nullptr : buf->delta2, w->ln1_w + o768, w->ln1_b + o768,
+                                       buf->h, nullptr, M, s));
     HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->qkv_w + size_t(l) * 3 * D * D, D, M, 3 * D, D,
                     w->qkv_b + size_t(l) * 3 * D, HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->qkv, 3 * D, s));
     HOIGEN_TRY(hoigen_attention(buf->qkv, buf->attn, batch, s));
     HOIGEN_TRY(gemm(buf->attn, D, (const uint16_t*)w->out_w + size_t(l) * D * D, D, M, D, D, w->out_b + o768,
                     HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->delta, D, s));
-    // (3) x += c_proj(quickgelu(c_fc(ln_2(x))))  (the c_proj epilogue also emits the bf16 copy the next adapter reads)
-    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, w->ln2_w + o768, w->ln2_b + o768, buf->h, M, s));
+    // (3) mlp: c_proj(quickgelu(c_fc(ln_2(x)))) -> delta2, added by the next adapter block (or the final LayerNorm)
+    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, nullptr, w->ln2_w + o768, w->ln2_b + o768, buf->h,
+                                       l + 1 < num_layers ? buf->xb : nullptr, M, s));
     HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->fc_w + size_t(l) * 4 * D * D, D, M, 4 * D, D,
                     w->fc_b + size_t(l) * 4 * D, HOIGEN_ACT_QUICKGELU, nullptr, nullptr, 0, nullptr, 0, buf->mlp, 4 * D, s));
     HOIGEN_TRY(gemm(buf->mlp, 4 * D, (const uint16_t*)w->proj_w + size_t(l) * D * 4 * D, 4 * D, M, D, 4 * D,
-                    w->proj_b + o768, HOIGEN_ACT_NONE, nullptr, buf->x, D, buf->x, D, buf->xb, D, s));
+                    w->proj_b + o768, HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->delta2, D, s));
   }
-  // ---- ln_post on ALL tokens, @ proj (768 -> 512) ----------------------------------------------------------
-  HOIGEN_TRY(hoigen_layernorm768(buf->x, w->ln_post_w, w->ln_post_b, nullptr, buf->h, M, s));
+  // ---- ln_post on ALL tokens (with the last pending residual), @ proj (768 -> 512) ---------------------------
+  if (num_layers > 0) {
+    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta2, nullptr, w->ln_post_w, w->ln_post_b, buf->h, nullptr, M, s));
+  } else {
+    HOIGEN_TRY(hoigen_layernorm768(buf->x, w->ln_post_w, w->ln_post_b, nullptr, buf->h, M, s));
+  }
   HOIGEN_TRY(gemm(buf->h, D, w->proj_t, D, M, 512, D, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0, buf->tokens_out, 512,
                   nullptr, 0, s));
   return HOIGEN_OK;

@@ -186,7 +186,7 @@ class VisionTransformer(nn.Module):
             b = {
                 "patches": e((batch * 196, 768), bf), "patch_emb": e((batch * 196, 768), f32),
                 "x": e((M, 768), f32), "xb": e((M, 768), bf), "h": e((M, 768), bf), "qkv": e((M, 2304), bf),
-                "attn": e((M, 768), bf), "mlp": e((M, 3072), bf), "delta": e((M, 768), bf), "adapter_d": e((M, 64), f32), "adapter_db": e((M, 64), bf),
+                "attn": e((M, 768), bf), "mlp": e((M, 3072), bf), "delta": e((M, 768), bf), "delta2": e((M, 768), bf),
                 "adapter_t": e((M, 64), bf), "adapter_kv": e((12, batch * n_max, 128), f32),
                 "tokens_out": e((M, 512), f32),
             }

@@ -94,16 +94,20 @@ HOIGEN_API int hoigen_embed_lnpre(const float* patch_emb, const float* class_emb
 /* LayerNorm over 768 columns, fp32 statistics, eps 1e-5 (C:409-415) -> bf16 and/or fp32 */
 HOIGEN_API int hoigen_layernorm768(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
                                    int32_t rows, hoigen_stream_t stream);
-/* x += delta (bf16) in place on the fp32 residual stream, then LayerNorm(x) -> bf16: the residual adds of
- * C:456 (x + adapter) and C:457 (x + attention) deferred from the producing GEMM into the LayerNorm that follows. */
-HOIGEN_API int hoigen_add_layernorm768(float* x, const void* delta_bf16, const float* gamma, const float* beta,
-                                       void* out_bf16, int32_t rows, hoigen_stream_t stream);
+/* x += delta (+ delta2, optional) in place on the fp32 residual stream, then LayerNorm(x) -> out_bf16, and optionally a
+ * bf16 copy of the updated stream (x_bf16): the residual adds of C:456-458 deferred from the producing GEMMs into the
+ * LayerNorm pass that streams the same rows anyway. */
+HOIGEN_API int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2_bf16, const float* gamma,
+                                       const float* beta, void* out_bf16, void* x_bf16, int32_t rows,
+                                       hoigen_stream_t stream);
 /* Adapter cross-attention K/V of the prior tokens for all layers: kv[l][tok][0:64]=K, [64:128]=V  (C:63-66).
  * in_proj_w (layers,192,64) rows [q;k;v], in_proj_b (layers,192); prior (tokens,64). */
 HOIGEN_API int hoigen_adapter_kv(const float* prior, const float* in_proj_w, const float* in_proj_b, float* kv,
                                  int32_t tokens, int32_t layers, hoigen_stream_t stream);
 
 typedef struct {
+  const void* wd;          /* bf16 (64,768)  adaptermlp.down_proj.weight */
+  const float* down_b;     /* (64)           adaptermlp.down_proj.bias */
   const void* wq;          /* bf16 (64,64)   q rows of multihead_attn.in_proj_weight */
   const void* wo;          /* bf16 (64,64)   multihead_attn.out_proj.weight */
   const void* w1;          /* bf16 (128,64)  linear1.weight */
@@ -113,13 +117,16 @@ typedef struct {
   const float* linear1_b;  /* (128) */
   const float* linear2_b;  /* (64) */
   const float* norm2_w; const float* norm2_b; const float* norm3_w; const float* norm3_b; /* (64) */
-} hoigen_adapter_mid_weights;
-/* Adapter bottleneck body for one layer on the tensor cores, Adapter.forward C:186-200 / forward_post C:51-72:
- * d = relu(down_proj(x)) given as fp32 (B*197,64) and bf16 (B*197,64) -> LN3(t + FFN(t)), t = LN2(d + MHA_2h(d, prior, mask))
- * -> bf16 (B*197,64). kv_layer (B*n_max,128) from hoigen_adapter_kv; mask (B,n_max) uint8, 1 = padding. n_max <= 32. */
-HOIGEN_API int hoigen_adapter_mid(const float* d_f32, const void* d_bf16, const float* kv_layer, const uint8_t* mask,
-                                  const hoigen_adapter_mid_weights* w, void* out_bf16, int32_t batch, int32_t n_max,
-                                  hoigen_stream_t stream);
+} hoigen_adapter_weights;
+/* One adapter block up to (not including) the up-projection, on the tensor cores — Adapter.forward C:183-200 with
+ * forward_post C:51-72.  The adapter input is xb + delta_c: xb = bf16 copy of the stream (B*197,768), delta_c = the
+ * still-pending bf16 residual of the previous block's MLP output (C:458) or NULL; the sum is never materialised
+ * ((xb + delta_c) Wd^T = xb Wd^T + delta_c Wd^T inside one TMEM accumulation).
+ *   d = relu(down_proj(xb + delta_c)) ; t = LN2(d + MHA_2h(d, prior, mask)) ; out = LN3(t + FFN(t))  -> bf16 (B*197,64)
+ * kv_layer (B*n_max,128) from hoigen_adapter_kv; mask (B,n_max) uint8, 1 = padding. n_max <= 32. */
+HOIGEN_API int hoigen_adapter_block(const void* xb, const void* delta_c, const float* kv_layer, const uint8_t* mask,
+                                    const hoigen_adapter_weights* w, void* out_bf16, int32_t batch, int32_t n_max,
+                                    hoigen_stream_t stream);
 /* 12-head attention over 197 tokens (tcgen05): qkv bf16 (B*197, 2304) = [q|k|v] -> out bf16 (B*197, 768). C:443-445 */
 HOIGEN_API int hoigen_attention(const void* qkv_bf16, void* out_bf16, int32_t batch, hoigen_stream_t stream);
 
@@ -155,14 +162,13 @@ typedef struct {            /* caller-owned workspace, M = B*197 */
   void* patches;            /* bf16 (B*196, 768) */
   float* patch_emb;         /* f32  (B*196, 768) */
   float* x;                 /* f32  (M, 768)   residual stream */
-  void* xb;                 /* bf16 (M, 768)   bf16 copy of x (adapter down-proj operand) */
+  void* xb;                 /* bf16 (M, 768)   bf16 copy of x as of the last LayerNorm pass (adapter down-proj operand) */
   void* h;                  /* bf16 (M, 768)   LayerNorm output */
   void* qkv;                /* bf16 (M, 2304) */
   void* attn;               /* bf16 (M, 768) */
   void* mlp;                /* bf16 (M, 3072) */
   void* delta;              /* bf16 (M, 768)   adapter up-proj / attention out-proj output awaiting its residual add */
-  float* adapter_d;         /* f32  (M, 64)    relu(down_proj(x)) */
-  void* adapter_db;         /* bf16 (M, 64)    same, as the tensor-core operand */
+  void* delta2;             /* bf16 (M, 768)   MLP c_proj output awaiting its residual add (applied by the next adapter block) */
   void* adapter_t;          /* bf16 (M, 64) */
   float* adapter_kv;        /* f32  (12, B*n_max, 128) */
   float* tokens_out;        /* f32  (M, 512)   OUTPUT: ln_post(x) @ proj for all tokens; row b*197 = feat_global[b],

@@ -131,6 +131,33 @@ def test_patchify_and_embed(cuda_device, enc_state):
     assert (xb.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item()
 
 
+def test_add_layernorm768(cuda_device):
+    """Deferred residual adds (C:456-458): x += delta (+ delta2) exactly in fp32, LayerNorm -> bf16, optional bf16 copy."""
+    from hoigen_b200 import _cabi
+    g = torch.Generator(device="cpu").manual_seed(31)
+    rows = 1003
+    x0 = torch.randn(rows, 768, generator=g) * 2
+    d1 = torch.randn(rows, 768, generator=g).bfloat16()
+    d2 = torch.randn(rows, 768, generator=g).bfloat16()
+    gamma, beta = torch.rand(768, generator=g) + 0.5, torch.randn(768, generator=g)
+    for two, copy in ((False, False), (True, False), (False, True), (True, True)):
+        x = x0.clone().to(cuda_device)
+        h = torch.zeros(rows, 768, device=cuda_device, dtype=torch.bfloat16)
+        xb = torch.zeros(rows, 768, device=cuda_device, dtype=torch.bfloat16)
+        a, b, gw, gb = d1.to(cuda_device), d2.to(cuda_device), gamma.to(cuda_device), beta.to(cuda_device)
+        _cabi.call("hoigen_add_layernorm768", x.data_ptr(), a.data_ptr(), b.data_ptr() if two else None,
+                   gw.data_ptr(), gb.data_ptr(), h.data_ptr(),
+                   xb.data_ptr() if copy else None, rows)
+        xr = x0 + d1.float() + (d2.float() if two else 0)
+        assert torch.equal(x.cpu(), xr)
+        ref = torch.nn.functional.layer_norm(xr, (768,), gamma, beta, 1e-5)
+        assert (h.float().cpu() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item()
+        if copy:
+            assert torch.equal(xb.cpu(), xr.bfloat16())
+        else:
+            assert not xb.any()
+
+
 def test_attention_matches_sdpa(cuda_device):
     from hoigen_b200 import _cabi
     g = torch.Generator(device="cpu").manual_seed(21)
@@ -164,13 +191,14 @@ def _adapter_inputs(enc_state, layer, B, n_list, device, seed=5):
     return prior, mask, d, w, blk
 
 
-def test_adapter_kv_and_mid(cuda_device, enc_state):
-    """Adapter body (C:186-200 / C:51-72) against the oracle's restatement, ragged key counts incl. n=1."""
+def test_adapter_kv_and_block(cuda_device, enc_state):
+    """Adapter block (down-proj of xb + delta_c by linearity; body: C:183-200 / C:51-72) against the oracle's
+    restatement, ragged key counts incl. n=1, with and without a pending residual."""
     import ctypes as C
     from hoigen_b200 import _cabi
     from oracle import hoi_forward_ref as O
     B, n_list, layer = 4, [16, 9, 1, 13], 3
-    prior, mask, d, w, blk = _adapter_inputs(enc_state, layer, B, n_list, cuda_device)
+    prior, mask, _, w, blk = _adapter_inputs(enc_state, layer, B, n_list, cuda_device)
     n_max = max(n_list)
     kv = torch.empty(1, B * n_max, 128, device=cuda_device)
     pr = prior.to(cuda_device).contiguous()
@@ -178,27 +206,36 @@ def test_adapter_kv_and_mid(cuda_device, enc_state):
     kv_ref = torch.nn.functional.linear(prior, enc_state[blk + "multihead_attn.in_proj_weight"][64:],
                                         enc_state[blk + "multihead_attn.in_proj_bias"][64:]).view(B * n_max, 128)
     assert (kv[0].cpu() - kv_ref).abs().max().item() < 1e-5
-    wb = [w[0][:64].bfloat16().contiguous(), w[2].bfloat16().contiguous(), w[4].bfloat16().contiguous(), w[6].bfloat16().contiguous()]
-    mw = _cabi.AdapterMidWeights()
-    for f, t in zip(("wq", "wo", "w1", "w2", "in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w", "norm2_b",
-                     "norm3_w", "norm3_b"), (*wb, w[1], w[3], w[5], w[7], w[8], w[9], w[10], w[11])):
-        setattr(mw, f, t.data_ptr())
-    out = torch.zeros(B * 197, 64, device=cuda_device, dtype=torch.bfloat16)
-    dd = d.to(cuda_device).contiguous()
+    ad = blk.replace("mhsa_layers.0.", "")
+    wd, bd = enc_state[ad + "down_proj.weight"], enc_state[ad + "down_proj.bias"]
+    wb = [wd.bfloat16().contiguous().to(cuda_device), bd.contiguous().to(cuda_device), w[0][:64].bfloat16().contiguous(),
+          w[2].bfloat16().contiguous(), w[4].bfloat16().contiguous(), w[6].bfloat16().contiguous()]
+    aw = _cabi.AdapterWeights()
+    for f, t in zip(("wd", "down_b", "wq", "wo", "w1", "w2", "in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w",
+                     "norm2_b", "norm3_w", "norm3_b"), (*wb, w[1], w[3], w[5], w[7], w[8], w[9], w[10], w[11])):
+        setattr(aw, f, t.data_ptr())
+    g = torch.Generator().manual_seed(17)
+    x0 = torch.randn(B, 197, 768, generator=g)
+    delta = (0.3 * torch.randn(B, 197, 768, generator=g)).bfloat16()
     m8 = mask.to(cuda_device).view(torch.uint8).contiguous()
-    db = dd.bfloat16().contiguous()
-    _cabi.call("hoigen_adapter_mid", dd.data_ptr(), db.data_ptr(), kv.data_ptr(), m8.data_ptr(), C.byref(mw), out.data_ptr(), B, n_max)
-    # oracle: the same sub-graph of adapter_forward, starting from `down`
     sd = enc_state
-    t2 = O._mha(d, prior, prior, sd[blk + "multihead_attn.in_proj_weight"], sd[blk + "multihead_attn.in_proj_bias"],
-                sd[blk + "multihead_attn.out_proj.weight"], sd[blk + "multihead_attn.out_proj.bias"], 2, mask)
-    t = O._ln(d + t2, sd[blk + "norm2.weight"], sd[blk + "norm2.bias"])
-    t2 = torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(t, sd[blk + "linear1.weight"], sd[blk + "linear1.bias"])),
-                                    sd[blk + "linear2.weight"], sd[blk + "linear2.bias"])
-    ref = O._ln(t + t2, sd[blk + "norm3.weight"], sd[blk + "norm3.bias"]).view(B * 197, 64)
-    err = (out.float().cpu() - ref).abs().max().item()
-    # bf16 tensor-core operands (weights + activations between the four MMAs), fp32 accumulation / softmax / LayerNorm
-    assert err < 3e-2 * max(1.0, ref.abs().max().item()), err
+    for use_delta in (False, True):
+        x = x0.bfloat16().view(B * 197, 768).to(cuda_device).contiguous()
+        dl = delta.view(B * 197, 768).to(cuda_device).contiguous()
+        out = torch.zeros(B * 197, 64, device=cuda_device, dtype=torch.bfloat16)
+        _cabi.call("hoigen_adapter_block", x.data_ptr(), dl.data_ptr() if use_delta else None, kv.data_ptr(), m8.data_ptr(),
+                   C.byref(aw), out.data_ptr(), B, n_max)
+        xr = x0.bfloat16().float() + (delta.float() if use_delta else 0)
+        d = torch.relu(torch.nn.functional.linear(xr, wd, bd))
+        t2 = O._mha(d, prior, prior, sd[blk + "multihead_attn.in_proj_weight"], sd[blk + "multihead_attn.in_proj_bias"],
+                    sd[blk + "multihead_attn.out_proj.weight"], sd[blk + "multihead_attn.out_proj.bias"], 2, mask)
+        t = O._ln(d + t2, sd[blk + "norm2.weight"], sd[blk + "norm2.bias"])
+        t2 = torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(t, sd[blk + "linear1.weight"], sd[blk + "linear1.bias"])),
+                                        sd[blk + "linear2.weight"], sd[blk + "linear2.bias"])
+        ref = O._ln(t + t2, sd[blk + "norm3.weight"], sd[blk + "norm3.bias"]).view(B * 197, 64)
+        err = (out.float().cpu() - ref).abs().max().item()
+        # bf16 tensor-core operands (weights + activations between the MMAs), fp32 accumulation / softmax / LayerNorm
+        assert err < 4e-2 * max(1.0, ref.abs().max().item()), (use_delta, err)
 
 
 def test_encoder_matches_oracle_and_golden(cuda_device, enc_state):
