@@ -53,38 +53,87 @@ def workload_config(args, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + clock-event (throttle) reasons sampled DURING the timed regions (B200_PROFILING.md clocks line).
+    In-process NVML (nvidia_ml_py) on a thread: a looping `nvidia-smi -lms` child was measured to stall this process's
+    kernel launches for ~4 ms per query, i.e. it perturbed the number it was there to qualify.  Falls back to one
+    nvidia-smi query per second if NVML cannot be loaded."""
 
-    def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+    _REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.index, self.period = index, period_s
+        self.sm, self.mx, self.reasons, self.stop_flag, self.thread, self.source = [], [], set(), False, None, None
+        self.active = False     # samples are kept only while a timed region is running
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.nv = pynvml
+            self.source = "nvml"
+            target = self._loop_nvml
         except Exception:
-            self.proc = None
+            self.source = "nvidia-smi"
+            target = self._loop_smi
+        self.thread = threading.Thread(target=target, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop_nvml(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            if not self.active:
+                time.sleep(self.period)
+                continue
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                bits = int(get_reasons(self.h))
+                for name, _attr, bit in self._REASONS:
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _loop_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            if not self.active:
+                time.sleep(0.05)
+                continue
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self._visible_index()}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+                r = [c.strip() for c in out[0].split(",")]
+                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(1.0)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=15)
+        sm = sorted(self.sm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0, "source": self.source}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": self.source}
 
 
 def peaks():
@@ -172,11 +221,31 @@ def run_b200(args, rank, world, local_rank):
     dev_props = [[dict({k: v.to(dev) for k, v in p.items()}, n_human=BOXES_H) for p in ps] for ps in host_props]
     dev_dino = [t.to(dev) for t in host_dino]
 
-    def step_resident(i):
+    def launch_resident(i):
         r = i % R
-        dets = model.forward_from_proposals(dev_imgs[r], dev_props[r], dev_dino[r])
+        return model.launch_from_proposals(dev_imgs[r], dev_props[r], dev_dino[r])
+
+    def finish_resident(pend):
+        dets = model.finish(pend)          # the path's device->host read (triplet offsets) + detection views
         if world > 1:
             gather_packed(dets.packed)     # the path's one collective: every rank ends up with every rank's detections
+        return dets
+
+    def run_resident(first, count):
+        """`count` complete steps; step i+1 is enqueued before step i is waited for, so the host's per-step work (layout,
+        launches, result views) overlaps the GPU instead of leaving it idle.  Every step is launched AND finished here."""
+        trace = os.environ.get("HOIGEN_BENCH_TRACE")
+        pend = launch_resident(first)
+        dets = None
+        for i in range(count):
+            ta = time.perf_counter()
+            nxt = launch_resident(first + i + 1) if i + 1 < count else None
+            tb = time.perf_counter()
+            dets = finish_resident(pend)
+            pend = nxt
+            if trace:
+                print(f"[trace] step {first + i}: launch {1e3 * (tb - ta):.2f} ms, finish {1e3 * (time.perf_counter() - tb):.2f} ms",
+                      file=sys.stderr, flush=True)
         return dets
 
     # ---- end-to-end step: HOST (pinned) inputs -> device -> detections -> HOST, H2D of step i+1 overlapped with step i --
@@ -187,18 +256,23 @@ def run_b200(args, rank, world, local_rank):
         host_packed.append((torch.cat([p["boxes"] for p in host_props[r]]).pin_memory(),
                             torch.cat([p["scores"] for p in host_props[r]]).pin_memory(),
                             torch.cat([p["labels"] for p in host_props[r]]).pin_memory()))
+    NSLOT = 3   # input slots: one being computed on, one launched ahead, one being uploaded
     dev_in = [dict(imgs=torch.empty_like(dev_imgs[0]), boxes=torch.empty(B * n_per, 4, device=dev),
                    scores=torch.empty(B * n_per, device=dev), labels=torch.empty(B * n_per, dtype=torch.int64, device=dev),
-                   dino=torch.empty_like(dev_dino[0]), ev=torch.cuda.Event()) for _ in range(2)]
+                   dino=torch.empty_like(dev_dino[0]), ev=torch.cuda.Event(), free=None) for _ in range(NSLOT)]
     cap_out = B * 120 * 30
-    host_out = dict(scores=torch.empty(cap_out, dtype=torch.float32).pin_memory(),
-                    labels=torch.empty(cap_out, dtype=torch.int64).pin_memory(),
-                    objects=torch.empty(cap_out, dtype=torch.int64).pin_memory(),
-                    pairing=torch.empty(2 * cap_out, dtype=torch.int64).pin_memory())
+    host_out = [dict(scores=torch.empty(cap_out, dtype=torch.float32).pin_memory(),
+                     labels=torch.empty(cap_out, dtype=torch.int64).pin_memory(),
+                     objects=torch.empty(cap_out, dtype=torch.int64).pin_memory(),
+                     pairing=torch.empty(2 * cap_out, dtype=torch.int64).pin_memory(), ev=torch.cuda.Event(), keep=None)
+                for _ in range(2)]
+    d2h_stream = torch.cuda.Stream(device=dev)
 
     def upload(i):
-        r, slot = i % R, dev_in[i % 2]
+        r, slot = i % R, dev_in[i % NSLOT]
         with torch.cuda.stream(copy_stream):
+            if slot["free"] is not None:
+                copy_stream.wait_event(slot["free"])     # the forward that last read this slot has finished
             slot["imgs"].copy_(host_imgs[r], non_blocking=True)
             slot["boxes"].copy_(host_packed[r][0], non_blocking=True)
             slot["scores"].copy_(host_packed[r][1], non_blocking=True)
@@ -207,20 +281,51 @@ def run_b200(args, rank, world, local_rank):
             slot["ev"].record(copy_stream)
         return slot
 
-    def step_host(slot, nxt):
-        pending = upload(nxt) if nxt is not None else None          # next step's H2D runs under this step's compute
+    def launch_host(i):
+        slot = dev_in[i % NSLOT]
         torch.cuda.current_stream().wait_event(slot["ev"])
         bx, sc, lb = slot["boxes"].split(n_per), slot["scores"].split(n_per), slot["labels"].split(n_per)
         props = [dict(boxes=bx[k], scores=sc[k], labels=lb[k], n_human=BOXES_H) for k in range(B)]
-        dets = model.forward_from_proposals(slot["imgs"], props, slot["dino"])
+        pend = model.launch_from_proposals(slot["imgs"], props, slot["dino"])
+        slot["free"] = pend.done
+        return pend
+
+    def finish_host(i, pend):
+        """Wait for step i, then start the device->host copy of its detections on the D2H stream (it overlaps the next
+        step's compute; the host buffer is double-buffered and waited for one step later)."""
+        dets = model.finish(pend)
         pk = dets.packed
         m = pk.scores.numel()
-        host_out["scores"][:m].copy_(pk.scores, non_blocking=True)
-        host_out["labels"][:m].copy_(pk.labels, non_blocking=True)
-        host_out["objects"][:m].copy_(pk.objects, non_blocking=True)
-        host_out["pairing"][: 2 * m].copy_(pk.pairing, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return pending, m
+        ho = host_out[i % 2]
+        if ho["keep"] is not None:
+            ho["ev"].synchronize()                       # the copy that last used this host buffer has landed
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(pk.done)
+            ho["scores"][:m].copy_(pk.scores, non_blocking=True)
+            ho["labels"][:m].copy_(pk.labels, non_blocking=True)
+            ho["objects"][:m].copy_(pk.objects, non_blocking=True)
+            ho["pairing"][: 2 * m].copy_(pk.pairing, non_blocking=True)
+            ho["ev"].record(d2h_stream)
+        ho["keep"] = dets                                # keeps the device tensors alive until the copy is done
+        return m
+
+    def run_host(first, count, pend):
+        """`count` end-to-end steps starting at step `first` (already uploaded and launched as `pend`).  Per step: one
+        upload (two steps ahead), one launch (one step ahead), one finish + D2H.  Returns the next pending step."""
+        m = 0
+        trace = os.environ.get("HOIGEN_BENCH_TRACE")
+        for i in range(first, first + count):
+            ta = time.perf_counter()
+            nxt = launch_host(i + 1)
+            tb = time.perf_counter()
+            m = finish_host(i, pend)
+            tc = time.perf_counter()
+            upload(i + 3)                                # its slot was read by step i, which has finished
+            pend = nxt
+            if trace:
+                print(f"[trace-e2e] step {i}: launch {1e3 * (tb - ta):.2f} ms, finish+d2h {1e3 * (tc - tb):.2f} ms, "
+                      f"upload {1e3 * (time.perf_counter() - tc):.2f} ms", file=sys.stderr, flush=True)
+        return pend, m
 
     def barrier():
         if world > 1:
@@ -235,34 +340,39 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item())
 
     # ---- device-resident timing -----------------------------------------------------------------------------------------
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
-        clocks.start()
+        clocks.start()                           # NVML is initialised here, outside the timed regions
+    run_resident(0, args.warmup)
+    barrier()
     _cabi.profile(False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.active = True
     e0.record()
-    for i in range(args.steps):
-        dets = step_resident(args.warmup + i)
+    dets = run_resident(args.warmup, args.steps)
     e1.record()
     barrier()
+    clocks.active = False
     launches = _cabi.launch_count()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = world * B / (ms_step * 1e-3)
     triplets = sum(int(d["scores"].numel()) for d in dets[:B])
 
     # ---- end-to-end timing with host buffers -----------------------------------------------------------------------------
-    slot = upload(0)
-    for i in range(max(3, args.warmup // 2)):
-        slot, m_out = step_host(slot, i + 1)
-    barrier()
+    for i in range(3):
+        upload(i)
+    w_e2e = max(8, args.warmup)      # long enough for the allocator to reach its steady state with two steps in flight
+    pend, m_out = run_host(0, w_e2e, launch_host(0))
+    barrier()                                    # drains the step launched ahead: nothing of it runs inside the timed region
+    clocks.active = True
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        slot, m_out = step_host(slot, i + 1)    # K uploads inside the timed region (the first was issued before it)
+    # K uploads, K launches, K finishes + K D2H copies; the barrier below waits for the last launched step and the copies
+    pend, m_out = run_host(w_e2e, args.steps, pend)
+    for ho in host_out:
+        ho["ev"].synchronize()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    clocks.active = False
     clk = clocks.stop() if rank == 0 else None
     h2d = host_imgs[0].numel() * 4 + sum(t.numel() * t.element_size() for t in host_packed[0]) + host_dino[0].numel() * 4
     d2h = m_out * (4 + 8 + 8 + 16) + (B + 1) * 4

@@ -148,6 +148,38 @@ KernelScope::~KernelScope() {
   if (slot_ >= 0) cudaEventRecord(g_prof[slot_].e1, stream_);
 }
 
+StreamKWorkspace get_streamk_workspace(cudaStream_t stream, size_t slot_bytes, int num_flags) {
+  struct Entry { StreamKWorkspace ws; size_t bytes; int flags; };
+  static std::mutex mu;
+  static std::unordered_map<cudaStream_t, Entry> table;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = table.find(stream);
+  if (it != table.end() && it->second.bytes >= slot_bytes && it->second.flags >= num_flags) return it->second.ws;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    set_error("stream-K workspace must be created before stream capture starts (run the path once, uncaptured, first)");
+    return StreamKWorkspace{nullptr, nullptr};
+  }
+  if (it != table.end()) {   // grow: the old launches on this stream must be done with the old buffers
+    cudaStreamSynchronize(stream);
+    cudaFree(it->second.ws.slots);
+    cudaFree(it->second.ws.flags);
+    table.erase(it);
+  }
+  Entry e{{nullptr, nullptr}, slot_bytes, num_flags};
+  cudaError_t err = cudaMalloc(reinterpret_cast<void**>(&e.ws.slots), slot_bytes);
+  if (err == cudaSuccess) err = cudaMalloc(reinterpret_cast<void**>(&e.ws.flags), size_t(num_flags) * sizeof(int));
+  if (err == cudaSuccess) err = cudaMemset(e.ws.flags, 0, size_t(num_flags) * sizeof(int));
+  if (err != cudaSuccess) {
+    set_error("stream-K workspace allocation failed: %s", cudaGetErrorString(err));
+    cudaFree(e.ws.slots);
+    cudaFree(e.ws.flags);
+    return StreamKWorkspace{nullptr, nullptr};
+  }
+  table.emplace(stream, e);
+  return e.ws;
+}
+
 }  // namespace hoigen
 
 extern "C" {

@@ -21,6 +21,14 @@ const CUtensorMap* get_tmap_3d_bf16(const void* ptr, uint64_t dim0, uint64_t dim
                                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
                                     uint32_t box1, uint32_t box2);
 
+// Scratch of the CTA-pair GEMM's stream-K split: fp32 partial-accumulator slots + one flag per slot (zeroed).  One
+// workspace per stream (launches on one stream are ordered, launches on different streams must not share slots).
+struct StreamKWorkspace {
+  float* slots;
+  int* flags;
+};
+StreamKWorkspace get_streamk_workspace(cudaStream_t stream, size_t slot_bytes, int num_flags);
+
 // Counts every kernel launch of this library and, when profiling is enabled (hoigen_profile_enable), brackets
 // the launch with CUDA events on the launching stream. flops / bytes are the ALGORITHMIC work of the launch.
 struct KernelScope {

@@ -37,6 +37,11 @@ struct GemmArgs {
   __nv_bfloat16* out_bf16;
   int ld_bf16;
   int debug;  // diagnostics only (HOIGEN_GEMM_DEBUG): 1 = TMA loads without MMAs, 2 = MMAs without TMA loads
+  // CTA-pair kernel work split (stream-K): work unit = one k-block of one tile; pair p owns units [bound(p), bound(p+1))
+  float* sk_ws;     // fp32 partial-accumulator slots, one per (pair, cta rank)
+  int* sk_flags;    // one flag per slot: 1 = partial published
+  int sk_snap;      // unit-range boundaries closer than this to a tile edge snap to it
+  int sk_tiles;     // the LAST sk_tiles tiles are split at k-block granularity; the others are dealt out round-robin
 };
 
 template <int BN>
@@ -181,7 +186,8 @@ __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const 
 template <int COLS, int EPI, typename WaitFn>
 __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int colbase, uint32_t t_addr, const float* s_bias,
                                               const float* s_cs, WaitFn wait_acc, uint8_t* out_tile = nullptr, int rrow = 0,
-                                              int tile_col0 = 0) {
+                                              int tile_col0 = 0, const float* part = nullptr, int n_parts = 0,
+                                              size_t part_stride = 0) {
   constexpr int CHUNKS = COLS / CW;
   const bool row_ok = row < g.M;
   const bool res_vec = g.residual && row_ok && (g.ld_res & 3) == 0;
@@ -206,6 +212,18 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
 #pragma unroll
         for (int j = 0; j < CW / 4; ++j)
           res[(c + 1) & 1][j] = *reinterpret_cast<const float4*>(res_row + col0 + CW + 4 * j);
+      }
+    }
+    if (n_parts > 0) {   // stream-K fix-up: add the other pairs' partial accumulators of this tile (fixed order)
+      const float* pp = part + size_t(c) * (BM * CW);
+      for (int q = 0; q < n_parts; ++q, pp += part_stride) {
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) {
+          const float4 a = __ldcg(reinterpret_cast<const float4*>(pp) + j);
+          uint32_t* rr = r[c & 1] + 4 * j;
+          rr[0] = __float_as_uint(__uint_as_float(rr[0]) + a.x); rr[1] = __float_as_uint(__uint_as_float(rr[1]) + a.y);
+          rr[2] = __float_as_uint(__uint_as_float(rr[2]) + a.z); rr[3] = __float_as_uint(__uint_as_float(rr[3]) + a.w);
+        }
       }
     }
     epilogue_process_chunk<EPI>(g, r[c & 1], res[c & 1], res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0,
@@ -365,6 +383,73 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // TMA_OUT: bf16-only outputs are staged in a swizzled smem tile and written with TMA stores (full-line writes, and
 // the TMEM accumulator is released as soon as it has been read, not when the global stores have been issued).
+// Stream-K work split of the CTA-pair kernel.  Wave quantisation is what the data-parallel schedule loses on the
+// encoder's shapes (12608 rows = 49.25 row panels: 150 / 450 / 600 tiles on 74 pairs = 2.03 / 6.08 / 8.1 rounds), so
+// the unit of work is one k-block of one tile and pair p owns the contiguous unit range [sk_bound(p), sk_bound(p+1))
+// of the tile-major order.  A range therefore is: [tail of a tile] [whole tiles] [head of a tile].
+//   tail (k-blocks [kb0 > 0, ...))   processed FIRST: the pair dumps its raw fp32 accumulator into its slot and
+//                                    publishes a flag (contributor);
+//   head (k-blocks [0, kb1 < num_k)) processed LAST: the pair waits for the flags of the pairs that hold the rest of the
+//                                    tile (they produced it at the start of their ranges), adds their slots in pair
+//                                    order (deterministic) and runs the normal epilogue (finisher), then clears the flags.
+// All pairs are co-resident (grid <= SM pairs, one CTA per SM), so the wait cannot deadlock.
+__device__ __forceinline__ int sk_bound(int p, int P, int total, int num_k, int snap) {
+  if (p >= P) return total;
+  int b = int((long long)total * p / P);
+  const int r = b % num_k;
+  if (r < snap) b -= r;
+  else if (num_k - r <= snap) b += num_k - r;
+  return b;
+}
+
+// Per-pair work sequence: first the pair's unit range of the split region (so its fix-up traffic hides behind the
+// whole tiles that follow), then whole tiles dealt round-robin (neighbouring pairs share operand panels in L2).
+struct PairWork {
+  int u, u_end, num_k, sk_tile0, tile_dp, dp_end, stride;
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    if (u < u_end) {
+      const int t = u / num_k;
+      kb0 = u - t * num_k;
+      kb1 = min(num_k, kb0 + (u_end - u));
+      u += kb1 - kb0;
+      tile = sk_tile0 + t;
+      return true;
+    }
+    if (tile_dp < dp_end) {
+      tile = tile_dp; tile_dp += stride; kb0 = 0; kb1 = num_k;
+      return true;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// contributor epilogue: raw accumulator -> slot, layout [chunk of 16 columns][128 rows][16 floats] (a warp writes 2 KiB
+// contiguous per chunk).  COLS = columns this warp owns; slot points at this thread's row of the warp's first chunk.
+template <int COLS>
+__device__ __forceinline__ void epilogue_dump_partial(uint32_t t_addr, float* slot) {
+  uint32_t r[2][CW];
+  tmem_ld_32x32b_x16(t_addr, r[0]);
+#pragma unroll
+  for (int c = 0; c < COLS / CW; ++c) {
+    tmem_wait_ld();
+    if (c + 1 < COLS / CW) tmem_ld_32x32b_x16(t_addr + uint32_t((c + 1) * CW), r[(c + 1) & 1]);
+    float4* dst = reinterpret_cast<float4*>(slot + size_t(c) * (BM * CW));
+#pragma unroll
+    for (int j = 0; j < CW / 4; ++j)
+      __stcg(dst + j, make_float4(__uint_as_float(r[c & 1][4 * j]), __uint_as_float(r[c & 1][4 * j + 1]),
+                                  __uint_as_float(r[c & 1][4 * j + 2]), __uint_as_float(r[c & 1][4 * j + 3])));
+  }
+}
+
 template <int BN, bool TMA_OUT>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;          // 16 KiB: this CTA's 128 rows of A
@@ -407,6 +492,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_n = (g.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (g.K + BK - 1) / BK;
+  const int total_units = g.sk_tiles * num_k;   // of the split region = tiles [num_tiles - sk_tiles, num_tiles)
+  PairWork work0;
+  work0.u = sk_bound(cluster_id, num_clusters, total_units, num_k, g.sk_snap);
+  work0.u_end = sk_bound(cluster_id + 1, num_clusters, total_units, num_k, g.sk_snap);
+  work0.num_k = num_k; work0.sk_tile0 = num_tiles - g.sk_tiles;
+  work0.tile_dp = cluster_id; work0.dp_end = num_tiles - g.sk_tiles; work0.stride = num_clusters;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -435,9 +526,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      PairWork work = work0;
+      for (int tile, kb0, kb1; work.next(tile, kb0, kb1);) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
           const uint32_t a_dst = tiles_addr + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + Cfg::A_BYTES;
@@ -461,13 +553,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      PairWork work = work0;
+      for (int tile, kb0, kb1; work.next(tile, kb0, kb1); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * Cfg::ACC_STRIDE);
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8u * stage, phase);
           tc_fence_after();
           const uint32_t a_addr = tiles_addr + stage * Cfg::STAGE_BYTES;
@@ -477,7 +570,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adesc = make_sdesc_sw128(a_addr + k * (UMMA_K * 2));
               const uint64_t bdesc = make_sdesc_sw128(b_addr + k * (UMMA_K * 2));
-              umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
           tc_commit_2sm(bar_empty + 8u * stage);   // frees the stage in BOTH CTAs
@@ -490,20 +583,46 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== epilogue warps (both CTAs: own 128 rows) =====================
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
+    const int rrow = quad * 32 + lane;
+    constexpr size_t SLOT = size_t(BN) * BM;                 // floats per (pair, rank) slot
+    // this thread's row inside the warp's first chunk of a slot
+    const size_t slot_off = (size_t(half * (BN / 2) / CW) * BM + rrow) * CW;
     int it = 0;
-    if (half == 0 && cluster_id < num_tiles)
-      prefetch_residual_row(g, (cluster_id / num_n) * (2 * BM) + int(rank) * BM + quad * 32 + lane, (cluster_id % num_n) * BN, BN);
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    PairWork work = work0;
+    for (int tile, kb0, kb1; work.next(tile, kb0, kb1); ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      if (half == 0 && tile + num_clusters < num_tiles) {
-        const int nt = tile + num_clusters;
-        prefetch_residual_row(g, (nt / num_n) * (2 * BM) + int(rank) * BM + quad * 32 + lane, (nt % num_n) * BN, BN);
-      }
-      const int row = m_blk * (2 * BM) + int(rank) * BM + quad * 32 + lane;
-      const int colbase = n_blk * BN + half * (BN / 2);
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_STRIDE + half * (BN / 2));
+      if (kb0 > 0) {
+        // ---- contributor: tail of a tile another pair finishes ----
+        mbar_wait(bar_tfull + 8u * acc, acc_phase);
+        tc_fence_after();
+        if (g.debug != 8) epilogue_dump_partial<BN / 2>(t_addr, g.sk_ws + (size_t(cluster_id) * 2 + rank) * SLOT + slot_off);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * acc);
+        if (g.debug != 8) __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) st_release_gpu(g.sk_flags + cluster_id * 2 + int(rank), 1);
+        continue;
+      }
+      int n_parts = 0;
+      if (kb1 < num_k) {
+        // ---- finisher of a split tile: the pairs after this one hold the rest ----
+        const int tile_end = (tile - work0.sk_tile0 + 1) * num_k;
+        for (int q = cluster_id + 1; q < num_clusters && sk_bound(q, num_clusters, total_units, num_k, g.sk_snap) < tile_end; ++q) {
+          const int* flag = g.sk_flags + q * 2 + int(rank);
+          uint32_t spins = 0;
+          while (g.debug != 7 && ld_acquire_gpu(flag) != 1) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();   // a contributor that never arrives is a scheduling bug, not a wait
+          }
+          ++n_parts;
+        }
+      }
+      const int row = m_blk * (2 * BM) + int(rank) * BM + rrow;
+      const int colbase = n_blk * BN + half * (BN / 2);
       float* s_bias = reinterpret_cast<float*>(tiles + Cfg::BAR_OFF + 256) + (it & 1) * 2 * BN;
       float* s_cs = s_bias + BN;
       if (TMA_OUT && threadIdx.x == 64) tma_store_wait_read();   // previous tile's TMA stores have drained the staging tile
@@ -511,7 +630,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       epilogue_warp<BN / 2, EPI>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
         mbar_wait(bar_tfull + 8u * acc, acc_phase);
         tc_fence_after();
-      }, TMA_OUT ? out_stage : nullptr, quad * 32 + lane, half * (BN / 2));
+      }, TMA_OUT ? out_stage : nullptr, rrow, half * (BN / 2),
+      n_parts ? g.sk_ws + (size_t(cluster_id + 1) * 2 + rank) * SLOT + slot_off : nullptr,
+      (g.debug == 6 || g.debug == 7) ? 0 : n_parts, 2 * SLOT);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * acc);   // TMEM drained: the next-but-one tile's MMAs may start
@@ -525,7 +646,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (n_blk * BN + pnl * 64 < g.N) tma_store_2d(&tmC, smem_u32(out_stage) + pnl * 16384, n_blk * BN + pnl * 64, row0);
           tma_store_commit();
         }
+      } else if (n_parts) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      if (n_parts && threadIdx.x == 64)   // every epilogue thread is past its slot reads: re-arm the flags
+        for (int q = 1; q <= n_parts; ++q) g.sk_flags[(cluster_id + q) * 2 + int(rank)] = 0;
     }
     if (TMA_OUT && threadIdx.x == 64) tma_store_wait_all();
   }
@@ -588,6 +713,7 @@ static GemmArgs to_args(const hoigen_gemm_params* p) {
   g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16); g.ld_bf16 = p->ld_bf16;
   static const int dbg = getenv("HOIGEN_GEMM_DEBUG") ? atoi(getenv("HOIGEN_GEMM_DEBUG")) : 0;
   g.debug = dbg;
+  g.sk_ws = nullptr; g.sk_flags = nullptr; g.sk_snap = 0; g.sk_tiles = 0;
   return g;
 }
 
@@ -622,7 +748,7 @@ static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
 }
 
 template <int BN, bool TMA_OUT, int EPI>
-static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream) {
+static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream, bool force_split) {
   using Cfg = Gemm2Cfg<BN, TMA_OUT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -640,8 +766,27 @@ static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream) {
     if (!tc) return HOIGEN_ERR_CUDA;
   }
   const int num_tiles = ((p->M + 2 * BM - 1) / (2 * BM)) * ((p->N + BN - 1) / BN);
+  const int num_k = (p->K + BK - 1) / BK;
   const int max_clusters = num_sms() / 2;
-  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  GemmArgs args = to_args(p);
+  // Tiles that do not fill the last round: split the last (1 + remainder) rounds' tiles across all pairs by k-blocks
+  static const bool no_streamk = getenv("HOIGEN_GEMM_NO_STREAMK") != nullptr;
+  const int rem = num_tiles % max_clusters;
+  int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  if (!no_streamk && rem != 0) {
+    const int sk_tiles = num_tiles < max_clusters ? num_tiles : rem + max_clusters;
+    // Measured (B200): the split's fixed cost (partial dump + fix-up, ~8 us) only pays when a round is long; the
+    // K = 768 shapes are epilogue-bound and lose.  HOIGEN_GEMM_STREAMK_MIN_K overrides the threshold (k-blocks).
+    static const int min_k = getenv("HOIGEN_GEMM_STREAMK_MIN_K") ? atoi(getenv("HOIGEN_GEMM_STREAMK_MIN_K")) : 32;
+    if ((num_k >= min_k || force_split) && (long long)sk_tiles * num_k / max_clusters >= 6) {
+      StreamKWorkspace ws = get_streamk_workspace(stream, size_t(max_clusters) * 2 * 256 * BM * sizeof(float), max_clusters * 2);
+      if (!ws.slots) return HOIGEN_ERR_CUDA;
+      args.sk_ws = ws.slots; args.sk_flags = ws.flags;
+      args.sk_tiles = sk_tiles;
+      args.sk_snap = num_k >= 12 ? 2 : (num_k >= 6 ? 1 : 0);
+      clusters = max_clusters;
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -656,29 +801,29 @@ static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream) {
   cfg.numAttrs = 1;
   KernelScope ks(gemm_tag(p->N, p->K), stream, 2.0 * p->M * p->N * p->K,
                  2.0 * (double(p->M) * p->K + double(p->N) * p->K) + double(p->M) * p->N * ((p->out_f32 ? 4 : 0) + (p->out_bf16 ? 2 : 0) + (p->residual ? 4 : 0)));
-  HOIGEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, TMA_OUT, EPI>, *ta, *tb, *tc, to_args(p)));
+  HOIGEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, TMA_OUT, EPI>, *ta, *tb, *tc, args));
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
 
 template <int BN>
-static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream) {
+static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream, bool force_split) {
   // bf16-only outputs with TMA-compatible strides go through the smem-staged TMA-store epilogue
   static const bool no_tma_out = getenv("HOIGEN_GEMM_NO_TMA_STORE") != nullptr;
   const bool tma_out = !no_tma_out && p->out_bf16 && !p->out_f32 && !p->residual && (p->ld_bf16 % 8) == 0 && (p->N % 8) == 0;
-  if (!tma_out) return launch_gemm2_impl<BN, false, -1>(p, stream);
+  if (!tma_out) return launch_gemm2_impl<BN, false, -1>(p, stream, force_split);
   // compile-time epilogue recipes of the encoder's bf16-output GEMMs; anything else uses the runtime-flag epilogue
   const bool b = p->bias != nullptr, c = p->colscale != nullptr;
-  if (b && !c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 5)>(p, stream);                          // QKV, out-proj
-  if (b && !c && p->act == HOIGEN_ACT_QUICKGELU) return launch_gemm2_impl<BN, true, (1 << 5) | HOIGEN_ACT_QUICKGELU>(p, stream);  // c_fc
-  if (b && c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 5) | (1 << 4)>(p, stream);                 // adapter up-proj
-  if (!b && !c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, 0>(p, stream);                                 // cache affinity
-  return launch_gemm2_impl<BN, true, -1>(p, stream);
+  if (b && !c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 5)>(p, stream, force_split);                          // QKV, out-proj
+  if (b && !c && p->act == HOIGEN_ACT_QUICKGELU) return launch_gemm2_impl<BN, true, (1 << 5) | HOIGEN_ACT_QUICKGELU>(p, stream, force_split);  // c_fc
+  if (b && c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 5) | (1 << 4)>(p, stream, force_split);                 // adapter up-proj
+  if (!b && !c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, 0>(p, stream, force_split);                                 // cache affinity
+  return launch_gemm2_impl<BN, true, -1>(p, stream, force_split);
 }
 
-// Pick (cta pair?, BN): fewest scheduling rounds x relative tile time. The one-CTA kernel is L2-operand-bound
+// Pick (cta pair?, BN): fewest (possibly fractional, see stream-K) scheduling rounds x relative tile time. The one-CTA kernel is L2-operand-bound
 // (~87 FLOP per L2 byte at BN = 256) so its tiles are charged 1.35x.
-static void choose_config(int M, int N, int* pair, int* bn) {
+static void choose_config(int M, int N, int K, int* pair, int* bn) {
   const int sms = num_sms();
   double best = 1e30;
   *pair = 0; *bn = 256;
@@ -697,7 +842,11 @@ static void choose_config(int M, int N, int* pair, int* bn) {
       const int b = c2[i];
       if (N <= b / 2) continue;
       const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + b - 1) / b);
-      const int rounds = (tiles + sms / 2 - 1) / (sms / 2);
+      const int pairs = sms / 2, num_k = (K + BK - 1) / BK;
+      // the stream-K split (launch_gemm2_impl) balances to a k-block: fractional rounds plus the fix-up's share
+      const int sk_tiles = tiles < pairs ? tiles : tiles % pairs + pairs;
+      const bool split = num_k >= 32 && tiles % pairs != 0 && (long long)sk_tiles * num_k / pairs >= 6;
+      const double rounds = split ? double(tiles) / pairs + 0.4 : double((tiles + pairs - 1) / pairs);
       const double cost = rounds * (double(b) + 96.0);
       if (cost < best) { best = cost; *pair = 1; *bn = b; }
     }
@@ -714,14 +863,16 @@ int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream) {
   if (rc != HOIGEN_OK) return rc;
   // block_n: 0 = choose; 64/128/256 = one-CTA kernel; 2128/2192/2256 = CTA-pair kernel (256 x {128,192,256} tiles)
   int bn = p->block_n, pair = 0;
-  if (bn == 0) choose_config(p->M, p->N, &pair, &bn);
+  const bool force_split = bn >= 10000;   // testing: +10000 forces the stream-K split whatever K is
+  if (force_split) bn -= 10000;
+  if (bn == 0) choose_config(p->M, p->N, p->K, &pair, &bn);
   else if (bn > 2000) { pair = 1; bn -= 2000; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pair) {
     switch (bn) {
-      case 256: return launch_gemm2<256>(p, s);
-      case 192: return launch_gemm2<192>(p, s);
-      case 128: return launch_gemm2<128>(p, s);
+      case 256: return launch_gemm2<256>(p, s, force_split);
+      case 192: return launch_gemm2<192>(p, s, force_split);
+      case 128: return launch_gemm2<128>(p, s, force_split);
       default: break;
     }
   } else {

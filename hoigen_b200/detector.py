@@ -42,6 +42,16 @@ class PackedDetections:
                     size=torch.tensor(self.size, dtype=torch.int64, device=self.scores.device))
 
 
+class _PinnedSlot:
+    buf = None
+    event = None
+    generation = 0
+
+
+class _PendingForward:
+    """Handle of a forward that has been enqueued but not waited for (UPT.launch_from_proposals -> UPT.finish)."""
+
+
 class DetectionList(list):
     """List[dict] exactly as the reference returns it (U:1421-1425), plus `.packed` for the zero-copy gather."""
     packed: "PackedDetections" = None
@@ -310,6 +320,25 @@ class UPT(nn.Module):
     # ------------------------------------------------------------------------------------------------------
     # the accelerated path: region proposals -> detections
     # ------------------------------------------------------------------------------------------------------
+    _PINNED_RING = 8
+
+    def _pinned_slot(self, numel: int):
+        """Next slot of the pinned int32 staging ring (layout upload + triplet-offset download of one forward).  A slot is
+        reused _PINNED_RING forwards later, after its event (the end of the forward that used it) has completed."""
+        ring = self._ws.setdefault("_pinned_ring", [])
+        idx = self._ws.get("_pinned_next", 0)
+        self._ws["_pinned_next"] = (idx + 1) % self._PINNED_RING
+        if len(ring) <= idx:
+            ring.append(_PinnedSlot())
+        slot = ring[idx]
+        if slot.event is not None:
+            slot.event.synchronize()
+            slot.event = None
+        if slot.buf is None or slot.buf.numel() < numel:
+            slot.buf = torch.empty(max(numel, 1024), dtype=torch.int32, pin_memory=True)
+        slot.generation += 1
+        return slot
+
     def _buf(self, name: str, numel: int, dtype: torch.dtype, device) -> torch.Tensor:
         t = self._ws.get(name)
         if t is None or t.numel() < numel or t.dtype != dtype or t.device != device:
@@ -324,6 +353,17 @@ class UPT(nn.Module):
         """(B,3,224,224) CLIP images + region proposals (+ L2-normalised DINO features) -> List[dict] as U:1421-1425.
 
         Equivalent to U:1609-1663 with `prepare_region_proposals` outputs as input (humans lead each image)."""
+        return self.finish(self.launch_from_proposals(images_clip, region_props, dino_image_features,
+                                                      return_intermediates=return_intermediates))
+
+    @torch.no_grad()
+    def launch_from_proposals(self, images_clip: torch.Tensor, region_props: Sequence[dict],
+                              dino_image_features: Optional[torch.Tensor] = None, *,
+                              return_intermediates: bool = False) -> Optional["_PendingForward"]:
+        """Enqueue the whole forward on the current stream WITHOUT waiting for it; `finish(handle)` does the path's one
+        device->host read (per-image triplet offsets) and builds the detections.  A serving loop calls
+        launch(batch i+1) before finish(batch i) so the host never leaves the GPU idle; `forward_from_proposals` is
+        launch + finish.  Returns None when no image has a valid pair (U:1660-1662)."""
         dev = images_clip.device
         _cabi.init(dev)
         if self._packed is None:
@@ -350,7 +390,11 @@ class UPT(nn.Module):
             box_off.append(box_off[-1] + n)
             pair_off.append(pair_off[-1] + k)
         ntot, ktot = box_off[-1], pair_off[-1]
-        layout = torch.tensor(box_off + pair_off + nh_list, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        # pinned staging comes from a small per-module ring: allocating pinned memory per call (cudaHostAlloc) would
+        # synchronise the device and serialise launch-ahead callers
+        stage = self._pinned_slot(3 * B + 2 + B + 1)
+        stage.buf[: 3 * B + 2] = torch.tensor(box_off + pair_off + nh_list, dtype=torch.int32)
+        layout = stage.buf[: 3 * B + 2].to(dev, non_blocking=True)
         d_box_off, d_pair_off, d_nh = layout[: B + 1], layout[B + 1: 2 * B + 2], layout[2 * B + 2:]
         boxes = torch.cat([rp["boxes"] for rp in region_props]).float().contiguous()
         scores = torch.cat([rp["scores"] for rp in region_props]).float().contiguous()
@@ -411,8 +455,32 @@ class UPT(nn.Module):
                    self._buf("emit_offsets", ktot + 1, torch.int32, dev).data_ptr(),
                    self._buf("emit_pr", ktot, torch.float32, dev).data_ptr(), cap, out_scores.data_ptr(),
                    out_labels.data_ptr(), out_objects.data_ptr(), out_pairing.data_ptr(), img_off.data_ptr())
-        # ---- the single device->host read of the path: per-image triplet offsets --------------------------------------
-        offs = img_off.cpu().tolist()
+        # ---- the single device->host read of the path (per-image triplet offsets), asynchronous until finish() --------
+        host_off = stage.buf[3 * B + 2: 4 * B + 3]
+        host_off.copy_(img_off, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        stage.event = done
+        pend = _PendingForward()
+        pend.__dict__.update(B=B, img_h=img_h, img_w=img_w, dev=dev, region_props=region_props, boxes=boxes,
+                             box_off=box_off, pair_off=pair_off, ktot=ktot, host_off=host_off, done=done, img_off=img_off,
+                             stage=stage, generation=stage.generation,
+                             out=(out_scores, out_labels, out_objects, out_pairing), prior=prior, mask=mask, tokens=tokens,
+                             logits=logits, pf_f32=pf_f32, return_intermediates=return_intermediates)
+        return pend
+
+    def finish(self, pend: Optional["_PendingForward"]):
+        """Wait for a launched forward and return its detections (List[dict] as U:1421-1425, `.packed` = CSR views)."""
+        if pend is None:
+            return None
+        B, img_h, img_w, dev = pend.B, pend.img_h, pend.img_w, pend.dev
+        region_props, boxes, box_off, pair_off, ktot = pend.region_props, pend.boxes, pend.box_off, pend.pair_off, pend.ktot
+        out_scores, out_labels, out_objects, out_pairing = pend.out
+        Cn = self.num_classes
+        pend.done.synchronize()
+        if pend.stage.generation != pend.generation:
+            raise RuntimeError(f"more than {self._PINNED_RING - 1} forwards were launched before this one was finished")
+        offs = pend.host_off.tolist()
         mtot = offs[-1]
         sizes_m = [offs[b + 1] - offs[b] for b in range(B)]
         size_t = torch.tensor([img_h, img_w], device=dev, dtype=torch.int64)
@@ -427,10 +495,11 @@ class UPT(nn.Module):
         detections.packed = PackedDetections(scores=out_scores[:mtot], labels=out_labels[:mtot], objects=out_objects[:mtot],
                                              pairing=out_pairing[: 2 * mtot], boxes=boxes, triplet_off=offs, box_off=box_off,
                                              size=(img_h, img_w))
-        if return_intermediates:
-            inter = dict(prior=prior, mask=mask.bool(), tokens=tokens.view(B, TOKENS, 512),
-                         logits=[logits[: ktot * Cn].view(ktot, Cn)[pair_off[b]: pair_off[b + 1]] for b in range(B)],
-                         pair_feats=pf_f32[: 3 * ktot * 512].view(3, ktot, 512), pair_off=pair_off, box_off=box_off)
+        detections.packed.done = pend.done     # recorded after the last kernel of this forward (for copies on other streams)
+        if pend.return_intermediates:
+            inter = dict(prior=pend.prior, mask=pend.mask.bool(), tokens=pend.tokens.view(B, TOKENS, 512),
+                         logits=[pend.logits[: ktot * Cn].view(ktot, Cn)[pair_off[b]: pair_off[b + 1]] for b in range(B)],
+                         pair_feats=pend.pf_f32[: 3 * ktot * 512].view(3, ktot, 512), pair_off=pair_off, box_off=box_off)
             return detections, inter
         return detections
 

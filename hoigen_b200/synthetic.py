@@ -201,12 +201,12 @@ def make_boxes(image_index: int, n_human: int = 8, n_object: int = 8, *, size: i
     return dict(boxes=boxes[order], scores=scores[order], labels=labels[order])
 
 
-def make_region_props(batch: int, n_human: int = 8, n_object: int = 8, *, ragged: bool = False) -> List[dict]:
+def make_region_props(batch: int, n_human: int = 8, n_object: int = 8, *, ragged: bool = False, seed: int = 0) -> List[dict]:
     props = []
     for b in range(batch):
         nh, no = n_human, n_object
         if ragged:  # vary the instance counts per image (exercises CSR offsets / n_max padding)
             nh = max(1, n_human - (b % 3))
             no = max(1, n_object - ((2 * b) % 5))
-        props.append(make_boxes(b, nh, no))
+        props.append(make_boxes(seed + b, nh, no))
     return props

@@ -75,7 +75,9 @@ typedef struct {
   int32_t ld_f32;
   void* out_bf16;        /* bf16 [M, ld_bf16] or NULL */
   int32_t ld_bf16;
-  int32_t block_n;       /* 0 = choose; 64/128/256 = one-CTA tiles 128xBN; 2128/2192/2256 = CTA-pair tiles 256xBN */
+  int32_t block_n;       /* 0 = choose; 64/128/256 = one-CTA tiles 128xBN; 2128/2192/2256 = CTA-pair tiles 256xBN;
+                            +10000 (tests) = split leftover tiles across SM pairs by k-blocks even when K is short
+                            (by default only K >= 2048 is split, where it pays) */
 } hoigen_gemm_params;
 
 HOIGEN_API int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream);

@@ -158,7 +158,34 @@ def test_full_batch_properties(cuda_device):
     halves = list(m.forward_from_proposals(imgs[:32], pd[:32], dino[:32])) + list(m.forward_from_proposals(imgs[32:], pd[32:], dino[32:]))
     for a, c in zip(dets, halves):
         assert torch.equal(a["pairing"], c["pairing"]) and torch.equal(a["labels"], c["labels"])
-        assert torch.allclose(a["scores"], c["scores"], rtol=1e-5, atol=0)   # same kernels, tile shapes may differ with M
+        # same kernels, but the GEMMs' tile schedule (and with the k-split of c_proj the fp32 summation order) depends on
+        # M: a bf16 rounding of an intermediate may flip, far inside the parity budget
+        assert torch.allclose(a["scores"], c["scores"], rtol=5e-3, atol=0)
+
+
+def test_launch_ahead_equals_sequential(cuda_device):
+    """launch_from_proposals / finish (a serving loop keeps one forward in flight while it finishes the previous one):
+    detections are bit-identical to the blocking forward, whatever was launched behind them."""
+    from hoigen_b200 import synthetic as S
+    m, enc, head = _build(117, 256, cuda_device)
+    batches = []
+    for r in range(4):
+        B = 3 + r
+        props = _props_to(S.make_region_props(B, 4, 5, ragged=True, seed=40 + r), cuda_device)
+        batches.append((S.make_images(B, seed=50 + r).to(cuda_device), props, S.make_dino_features(B, seed=60 + r).to(cuda_device)))
+    ref = [m.forward_from_proposals(*b) for b in batches]
+    pend = [m.launch_from_proposals(*b) for b in batches]           # four forwards in flight
+    got = [m.finish(p) for p in pend]
+    for a, c in zip(ref, got):
+        assert a.packed.triplet_off == c.packed.triplet_off
+        for x, y in zip(a, c):
+            for k in ("pairing", "labels", "objects", "scores", "boxes"):
+                assert torch.equal(x[k], y[k]), k
+    stale = m.launch_from_proposals(*batches[0])
+    for _ in range(m._PINNED_RING):
+        m.finish(m.launch_from_proposals(*batches[1]))
+    with pytest.raises(RuntimeError):
+        m.finish(stale)                                              # its staging slot has been recycled: loud, not wrong
 
 
 def test_scoring_stage_given_identical_features(cuda_device):

@@ -85,6 +85,37 @@ def test_gemm_bf16_only_output_tma_store(cuda_device, M, N, K, bn):
     assert (ob[M:] == 7.0).all() and (ob[:, N:] == 7.0).all()      # nothing written outside the M x N window
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(12608, 768, 768, 12256), (12608, 768, 3072, 0), (12608, 2304, 768, 12256),
+                                      (20000, 117, 512, 12128), (19000, 200, 1024, 12192), (12608, 3072, 768, 12256),
+                                      (7680, 117, 4096, 0)])
+def test_gemm_stream_k_split(cuda_device, M, N, K, bn):
+    """Tile counts that do not divide the SM-pair count are split at k-block granularity (stream-K): partial
+    accumulators cross pairs through the fp32 workspace.  Checks both epilogues (fp32 + residual, bf16 TMA store),
+    run-to-run bit-reproducibility (fixed summation order, flags re-armed) and agreement with the unsplit schedule."""
+    from hoigen_b200 import _cabi
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + K)
+    a = torch.randn(M, K, generator=g).bfloat16().to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16().to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    res = torch.randn(M, N, generator=g).to(cuda_device)
+    ref = _ref_gemm(a, w, bias, 0, None, res)
+    outs = []
+    for _ in range(3):
+        of = res.clone()
+        _cabi.gemm_bf16(a, w, bias=bias, residual=of, out_f32=of, block_n=bn)
+        outs.append(of)
+    assert (outs[0] - ref).abs().max().item() < 2e-4 * max(1.0, math.sqrt(K / 64))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    if N % 8 == 0:
+        ob = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+        ob2 = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+        _cabi.gemm_bf16(a, w, bias=bias, act=1, out_bf16=ob, block_n=bn)
+        _cabi.gemm_bf16(a, w, bias=bias, act=1, out_bf16=ob2, block_n=bn)
+        refb = _ref_gemm(a, w, bias, 1, None, None)
+        assert (ob.float() - refb).abs().max().item() < 2 ** -7 * max(1.0, refb.abs().max().item())
+        assert torch.equal(ob, ob2)
+
+
 def test_gemm_rejects_bad_arguments(cuda_device):
     from hoigen_b200 import _cabi
     a = torch.zeros(16, 20, device=cuda_device, dtype=torch.bfloat16)   # lda = 20 is not a multiple of 8
