@@ -153,6 +153,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_adapter_kv": [_P, _P, _P, _P, _I, _I, _P],
     "hoigen_adapter_block": [_P, _P, _P, _P, C.POINTER(AdapterWeights), _P, _I, _I, _P],
     "hoigen_attention": [_P, _P, _I, _P],
+    "hoigen_debug_attention_trace": [_P, _P, _I, _P, _P],
     "hoigen_encoder_forward": [C.POINTER(EncoderWeights), C.POINTER(EncoderBuffers), _P, _P, _P, _I, _I, _I, _P],
     "hoigen_prior_tokens": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P],
     "hoigen_roi_pair_features": [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P],

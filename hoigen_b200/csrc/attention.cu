@@ -3,16 +3,23 @@
 //
 //   warp 0      TMA producer: Q tile (128x64), K (208x64), V (208x64) of item i+1 land while item i is computed
 //   warp 1      MMA issuer:   S_i = Q K^T  (UMMA 128x208x16, 4 k-steps, fp32 in TMEM buffer i&1), issued one item
-//                              ahead of the softmax;  O_i = P_i V (UMMA 128x64x16, 13 k-steps, V consumed MN-major
-//                              straight from the QKV buffer, O overlays columns [0,64) of its own S buffer)
+//                              ahead of the softmax;  O_i = P_i V (13 k-steps of UMMA 128x64x16 with the A operand P read
+//                              straight from TMEM and V consumed MN-major straight from the QKV tile)
 //   warps 2-9   softmax + epilogue, TWO threads per query row (key halves [0,112) and [112,208)):
-//                              row max -> exp2 -> P (bf16) into 128B-swizzled smem -> ... -> O / rowsum -> bf16 -> global
+//                              row max -> exp2 -> P (bf16 pairs) back into TMEM over the dead S columns -> ... ->
+//                              O / rowsum -> bf16 -> swizzled smem tile -> ONE TMA store per item
 // The whole key range (197 -> 208) fits one tile, so no online-softmax rescaling is needed.
 //
-// Shared memory: 2 stages x [Q 16K | K 26K | V 26K] + P 64K = 200 KiB.  TMEM: 2 x 208 columns (512 allocated).
+// TMEM buffer b (256 columns): S in [0,208); once every thread holds its half row of S in registers the columns are
+// dead, P (104 packed columns) overlays [0,104) and O accumulates into [128,192).  P never touches shared memory.
+// Per item the softmax threads run  load S / max  ->  first exponentials  ->  drain O of the PREVIOUS item  ->  the
+// remaining exponentials: the P V MMA of item i-1 completes under the first half, and draining O_{i-1} frees its TMEM
+// buffer so S of item i+1 is computed under the second half (measured with hoigen_debug_attention_trace: the old
+// order stalled ~700 clocks per item on P V and spent ~1700 on uncoalesced 16-byte row stores).
+//
+// Shared memory: 2 stages x [Q 16K | K 26K | V 26K] + O staging 16K = 152 KiB.  TMEM: 2 x 256 columns.
 // Barriers: full/empty[s] (Q,K: released right after S), vfull/vempty[s] (V: released after PV), s_ready[b] (S in TMEM),
-// p_ready (P in smem), o_ready (PV done),
-// epi_done[b] (TMEM buffer b drained).
+// p_ready (P in TMEM), o_ready (PV done), epi_done[b] (TMEM buffer b drained).
 //
 // Replaces F.multi_head_attention_forward -> SDPA at CLIP_models_adapter_prior2.py:443-445 (no mask,
 // scale = 64^-0.5, dropout off).
@@ -31,8 +38,9 @@ constexpr int ATT_STAGE_Q = 0;
 constexpr int ATT_STAGE_K = 16384;
 constexpr int ATT_STAGE_V = 16384 + ATT_KEYS * 128;            // 43008
 constexpr int ATT_STAGE_BYTES = 16384 + 2 * ATT_KEYS * 128;    // 69632
-constexpr int ATT_SMEM_P = 2 * ATT_STAGE_BYTES;                // 139264 (1024-aligned)
-constexpr int ATT_SMEM_MISC = ATT_SMEM_P + 65536;              // barriers + row-stat exchange
+constexpr int ATT_SMEM_O = 2 * ATT_STAGE_BYTES;                // 139264 (1024-aligned): O tile staged for the TMA store
+constexpr int ATT_SMEM_MISC = ATT_SMEM_O + 16384;              // barriers + row-stat exchange
+constexpr int ATT_O_COL = 128;     // O accumulator columns [128,192) of a TMEM buffer; P overlays [0,104)
 constexpr int ATT_SMEM_BYTES = ATT_SMEM_MISC + 128 + 4 * 256 * 4 + 1024;
 constexpr int ATT_TMEM_COLS = 512;
 constexpr int ATT_SPLIT = 112;     // keys [0,112) -> column half 0 (7 chunks of 16), [112,208) -> half 1 (6 chunks)
@@ -45,8 +53,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
-                 const __grid_constant__ CUtensorMap tmKV /* box 64 x 208 x 1 */, __nv_bfloat16* __restrict__ out,
-                 int num_items) {
+                 const __grid_constant__ CUtensorMap tmKV /* box 64 x 208 x 1 */,
+                 const __grid_constant__ CUtensorMap tmO /* box 64 x 128 x 1 on the (B,197,768) output */,
+                 int num_items, long long* __restrict__ trace /* diagnostics: CTA 0 phase timestamps, or nullptr */) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -70,6 +79,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_full + 8u * s, 1);
       mbar_init(bar_empty + 8u * s, 1);
@@ -143,10 +153,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
         const uint32_t st = base + s * ATT_STAGE_BYTES;
 #pragma unroll
         for (int ks = 0; ks < ATT_KEYS / 16; ++ks) {
-          const uint64_t adesc = make_sdesc_sw128(base + ATT_SMEM_P + (ks >> 2) * 16384 + (ks & 3) * 32);
-          // V tile rows are keys (MN-major B operand): one k-step = 16 keys = two 8-row groups = 2048 bytes
+          // A = P from TMEM (16 keys = 8 packed columns per k-step); V tile rows are keys (MN-major B operand): one
+          // k-step = 16 keys = two 8-row groups = 2048 bytes
           const uint64_t bdesc = make_sdesc_sw128(st + ATT_STAGE_V + ks * 2048);
-          umma_bf16_ss(tmem + uint32_t(s * 256), adesc, bdesc, idesc_o, ks > 0 ? 1u : 0u);
+          umma_bf16_ts(tmem + uint32_t(s * 256 + ATT_O_COL), tmem + uint32_t(s * 256 + ks * 8), bdesc, idesc_o, ks > 0 ? 1u : 0u);
         }
         tc_commit(bar_oready);             // O_i complete (and P consumed)
         tc_commit(bar_vempty + 8u * s);    // V of stage s free for item i+2
@@ -160,39 +170,64 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
     const int c_begin = colhalf == 0 ? 0 : ATT_SPLIT / 16;            // 16-column chunk range of this thread
     const int c_end = colhalf == 0 ? ATT_SPLIT / 16 : ATT_KEYS / 16;
     const float scale_log2 = 0.125f * 1.4426950408889634f;  // 64^-0.5 * log2(e)
-    uint8_t* smP = sm + ATT_SMEM_P;
+    uint8_t* smO = sm + ATT_SMEM_O;
+    const bool tracing = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+    auto stamp = [&](int i, int k) { if (tracing && i < 16) trace[i * 8 + k] = clock64(); };
 
+    // O_i / rowsum -> bf16 -> 128B-swizzled staging tile [128 rows x 64 cols] -> one TMA store (rows >= 197 clipped)
     auto epilogue = [&](int i) {
-      // O_i / rowsum -> bf16 -> out[b*197 + t][h*64 + colhalf*32 .. +31]
       const int item = first + i * stride;
       const int mt = item & 1, h = (item >> 1) % ATT_HEADS, b = (item >> 1) / ATT_HEADS;
-      const int t = mt * 128 + row;
       const float inv = 1.0f / (stat_sum[(i & 1) * 256 + row] + stat_sum[(i & 1) * 256 + 128 + row]);
       uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem + (uint32_t(quad * 32) << 16) + uint32_t((i & 1) * 256 + colhalf * 32), r);
+      tmem_ld_32x32b_x32(tmem + (uint32_t(quad * 32) << 16) + uint32_t((i & 1) * 256 + ATT_O_COL + colhalf * 32), r);
       tmem_wait_ld();
-      if (t < ATT_TOKENS) {
-        __nv_bfloat16* dst = out + (size_t(b) * ATT_TOKENS + t) * ATT_WIDTH + h * ATT_DH + colhalf * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
-          pk.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
-          pk.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
-          pk.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + j) = pk;
-        }
-      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_epi + 8u * (i & 1));
+      if (lane == 0) mbar_arrive(bar_epi + 8u * (i & 1));     // TMEM buffer drained: S of item i+2 may be issued
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        pk.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+        pk.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+        pk.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+        pk.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+        *reinterpret_cast<uint4*>(smO + sw128_offset(row, uint32_t(colhalf * 4 + (j >> 3)))) = pk;
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (threadIdx.x == 64) {
+        tma_store_3d(&tmO, smem_u32(smO), h * ATT_DH, mt * 128, b);
+        tma_store_commit();
+      }
+    };
+
+    // exponentials of chunks [cc0, cc1) of this thread's half row -> packed bf16 pairs -> TMEM (P overlays S)
+    float sum4[4];
+    auto exp_chunks = [&](uint32_t (&r)[7][16], int cc0, int cc1, float mxs, uint32_t p_row) {
+#pragma unroll
+      for (int cc = 0; cc < 7; ++cc) {
+        if (cc >= cc0 && cc < cc1 && cc < c_end - c_begin) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(r[cc][2 * j]), scale_log2, -mxs));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(r[cc][2 * j + 1]), scale_log2, -mxs));
+            sum4[j & 3] += e0 + e1;
+            pk[j] = pack_bf16x2(e0, e1);
+          }
+          tmem_st_32x32b_x8(p_row + uint32_t((c_begin + cc) * 8), pk);   // keys 16c .. 16c+15 -> columns 8c .. 8c+7
+        }
+      }
     };
 
     for (int i = 0; i < n_local; ++i) {
       const int sb = i & 1;
       const uint32_t t_row = tmem + (uint32_t(quad * 32) << 16) + uint32_t(sb * 256);
+      stamp(i, 0);
       mbar_wait(bar_sready + 8u * sb, (i >> 1) & 1u);
       tc_fence_after();
+      stamp(i, 1);
       // ---- this thread's half row of S (7 or 6 chunks of 16 fp32) -> registers with ONE TMEM round trip ----
       uint32_t r[7][16];
 #pragma unroll
@@ -204,58 +239,50 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
 #pragma unroll
         for (int j = ATT_TOKENS - 192; j < 16; ++j) r[5][j] = 0xff800000u;   // chunk 12 = keys 192..207
       }
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains, not one of 112
 #pragma unroll
       for (int cc = 0; cc < 7; ++cc) {
         if (cc < c_end - c_begin) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[cc][j]));
+          for (int j = 0; j < 16; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(r[cc][j]));
         }
       }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       stat_max[sb * 256 + colhalf * 128 + row] = mx;
+      if (threadIdx.x == 64) tma_store_wait_read();   // the O staging tile has been read by the previous item's store
+      stamp(i, 2);
+      // after this barrier: the partner's row max is visible, every thread holds its S (the columns are dead and may
+      // take P), the partner's row sum of item i-1 is visible, and the staging tile is free
+      tc_fence_before();
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc_fence_after();
+      stamp(i, 3);
       mx = fmaxf(mx, stat_max[sb * 256 + (colhalf ^ 1) * 128 + row]);
       const float mxs = mx * scale_log2;
-      // P (single buffer) is free once the PV MMA of the previous item has completed
+      sum4[0] = sum4[1] = sum4[2] = sum4[3] = 0.f;
+      exp_chunks(r, 0, 3, mxs, t_row);
+      stamp(i, 4);
       if (i > 0) {
         mbar_wait(bar_oready, (i - 1) & 1u);
         tc_fence_after();
+        epilogue(i - 1);
       }
-      // ---- p = exp2(s*scale - max) -> bf16 -> swizzled smem; partial row sum (fp32) ----
-      float sum = 0.f;
-#pragma unroll
-      for (int cc = 0; cc < 7; ++cc) {
-        if (cc < c_end - c_begin) {
-          const int c = c_begin + cc;
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(r[cc][2 * j]), scale_log2, -mxs));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(r[cc][2 * j + 1]), scale_log2, -mxs));
-            sum += e0 + e1;
-            pk[j] = pack_bf16x2(e0, e1);
-          }
-          // P[row][c*16 .. +15] -> K-major SW128 atoms: atom = c/4 (64 keys each), 16-byte chunks (c%4)*2, +1
-          uint8_t* pa = smP + (c >> 2) * 16384;
-          const uint32_t ch = uint32_t(c & 3) * 2;
-          *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(pa + sw128_offset(row, ch + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
-      stat_sum[sb * 256 + colhalf * 128 + row] = sum;
-      // generic-proxy smem writes -> visible to the tensor core; TMEM reads of S ordered before PV overwrites [0,64)
-      fence_proxy_async_smem();
+      stamp(i, 5);
+      exp_chunks(r, 3, 7, mxs, t_row);
+      stat_sum[sb * 256 + colhalf * 128 + row] = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      tmem_wait_st();                 // P is in TMEM
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pready);
-      // ---- epilogue of the PREVIOUS item overlaps this item's PV MMA ----
-      if (i > 0) epilogue(i - 1);
+      stamp(i, 6);
     }
     if (n_local > 0) {
       mbar_wait(bar_oready, (n_local - 1) & 1u);
       tc_fence_after();
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // partner's partial row sum of the last item is visible
+      if (threadIdx.x == 64) tma_store_wait_read();
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // partner's partial row sum of the last item is visible; staging free
       epilogue(n_local - 1);
+      if (threadIdx.x == 64) tma_store_wait_all();
     }
   }
 
@@ -271,7 +298,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
 
 extern "C" {
 
+static int attention_launch(const void* qkv, void* out, int32_t batch, long long* trace, hoigen_stream_t stream);
+
 int hoigen_attention(const void* qkv, void* out, int32_t batch, hoigen_stream_t stream) {
+  return attention_launch(qkv, out, batch, nullptr, stream);
+}
+
+/* diagnostics: same launch, CTA 0's softmax-leader thread writes clock64() stamps [16 items][8 phases] to trace */
+int hoigen_debug_attention_trace(const void* qkv, void* out, int32_t batch, int64_t* trace, hoigen_stream_t stream) {
+  return attention_launch(qkv, out, batch, reinterpret_cast<long long*>(trace), stream);
+}
+
+static int attention_launch(const void* qkv, void* out, int32_t batch, long long* trace, hoigen_stream_t stream) {
   using namespace hoigen;
   HOIGEN_CHECK_ARG(qkv && out && batch > 0, "attention: bad arguments");
   HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
@@ -288,12 +326,16 @@ int hoigen_attention(const void* qkv, void* out, int32_t batch, hoigen_stream_t 
   const CUtensorMap* tkv = get_tmap_3d_bf16(qkv, 3 * ATT_WIDTH, ATT_TOKENS, uint64_t(batch), row_bytes,
                                             row_bytes * ATT_TOKENS, 64, ATT_KEYS, 1);
   if (!tkv) return HOIGEN_ERR_CUDA;
+  const uint64_t orow_bytes = uint64_t(ATT_WIDTH) * 2;
+  const CUtensorMap* to = get_tmap_3d_bf16(out, ATT_WIDTH, ATT_TOKENS, uint64_t(batch), orow_bytes, orow_bytes * ATT_TOKENS,
+                                           64, 128, 1);
+  if (!to) return HOIGEN_ERR_CUDA;
   const int items = batch * ATT_HEADS * 2;
   const int grid = items < num_sms() ? items : num_sms();
   KernelScope ks("attention", reinterpret_cast<cudaStream_t>(stream), 4.0 * ATT_TOKENS * ATT_TOKENS * ATT_DH * ATT_HEADS * batch,
                  double(batch) * ATT_TOKENS * ATT_WIDTH * 2 * 4);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-      *tq, *tkv, reinterpret_cast<__nv_bfloat16*>(out), items);
+      *tq, *tkv, *to, items, trace);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }

@@ -131,6 +131,9 @@ HOIGEN_API int hoigen_adapter_block(const void* xb, const void* delta_c, const f
                                     hoigen_stream_t stream);
 /* 12-head attention over 197 tokens (tcgen05): qkv bf16 (B*197, 2304) = [q|k|v] -> out bf16 (B*197, 768). C:443-445 */
 HOIGEN_API int hoigen_attention(const void* qkv_bf16, void* out_bf16, int32_t batch, hoigen_stream_t stream);
+/* Diagnostics only: the same launch; CTA 0 writes clock64() stamps [16 items][8 phases] of its softmax loop to trace. */
+HOIGEN_API int hoigen_debug_attention_trace(const void* qkv, void* out_bf16, int32_t batch, int64_t* trace,
+                                            hoigen_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole visual encoder = VisionTransformer.forward(x, prior), C:489-506.  One call per batch.
