@@ -270,6 +270,8 @@ def run_b200(args, rank, world, local_rank):
 
     def upload(i):
         r, slot = i % R, dev_in[i % NSLOT]
+        if os.environ.get("HOIGEN_BENCH_NO_UPLOAD") and i >= NSLOT:     # diagnostics: how much does the concurrent H2D cost?
+            return slot
         with torch.cuda.stream(copy_stream):
             if slot["free"] is not None:
                 copy_stream.wait_event(slot["free"])     # the forward that last read this slot has finished
@@ -284,9 +286,8 @@ def run_b200(args, rank, world, local_rank):
     def launch_host(i):
         slot = dev_in[i % NSLOT]
         torch.cuda.current_stream().wait_event(slot["ev"])
-        bx, sc, lb = slot["boxes"].split(n_per), slot["scores"].split(n_per), slot["labels"].split(n_per)
-        props = [dict(boxes=bx[k], scores=sc[k], labels=lb[k], n_human=BOXES_H) for k in range(B)]
-        pend = model.launch_from_proposals(slot["imgs"], props, slot["dino"])
+        pend = model.launch_packed(slot["imgs"], slot["boxes"], slot["scores"], slot["labels"], [n_per] * B, [BOXES_H] * B,
+                                   slot["dino"])
         slot["free"] = pend.done
         return pend
 
@@ -314,8 +315,12 @@ def run_b200(args, rank, world, local_rank):
         upload (two steps ahead), one launch (one step ahead), one finish + D2H.  Returns the next pending step."""
         m = 0
         trace = os.environ.get("HOIGEN_BENCH_TRACE")
+        evs = []
         for i in range(first, first + count):
             ta = time.perf_counter()
+            if trace:
+                evs.append(torch.cuda.Event(enable_timing=True))
+                evs[-1].record()
             nxt = launch_host(i + 1)
             tb = time.perf_counter()
             m = finish_host(i, pend)
@@ -325,6 +330,10 @@ def run_b200(args, rank, world, local_rank):
             if trace:
                 print(f"[trace-e2e] step {i}: launch {1e3 * (tb - ta):.2f} ms, finish+d2h {1e3 * (tc - tb):.2f} ms, "
                       f"upload {1e3 * (time.perf_counter() - tc):.2f} ms", file=sys.stderr, flush=True)
+        if trace and len(evs) > 2:
+            torch.cuda.synchronize()
+            print("[trace-e2e] GPU period between step starts (ms): " +
+                  " ".join(f"{evs[k].elapsed_time(evs[k + 1]):.2f}" for k in range(len(evs) - 1)), file=sys.stderr, flush=True)
         return pend, m
 
     def barrier():
@@ -377,6 +386,24 @@ def run_b200(args, rank, world, local_rank):
     h2d = host_imgs[0].numel() * 4 + sum(t.numel() * t.element_size() for t in host_packed[0]) + host_dino[0].numel() * 4
     d2h = m_out * (4 + 8 + 8 + 16) + (B + 1) * 4
 
+    if os.environ.get("HOIGEN_BENCH_TRACE"):     # diagnostics: the same per-kernel profile, but of end-to-end steps
+        torch.cuda.synchronize()
+        _cabi.profile(True)
+        pend, _ = run_host(w_e2e + args.steps, 2, pend)
+        torch.cuda.synchronize()
+        recs_e = _cabi.profile_read()
+        _cabi.profile(False)
+        agg_e = {}
+        for tag, ms, fl, by, _t0 in recs_e:
+            a = agg_e.setdefault(tag, [0, 0.0])
+            a[0] += 1; a[1] += ms
+        print("[trace-e2e] profiled kernels: %d launches, sum %.3f ms; per tag ms: %s" % (
+            len(recs_e), sum(a[1] for a in agg_e.values()),
+            " ".join(f"{t}={a[1] / a[0] * 1e3:.1f}us" for t, a in sorted(agg_e.items(), key=lambda kv: -kv[1][1])[:10])),
+            file=sys.stderr, flush=True)
+        ts = sorted((t0, ms, tag) for tag, ms, fl, by, t0 in recs_e)
+        gaps = sorted(((ts[k + 1][0] - (ts[k][0] + ts[k][1])), ts[k][2], ts[k + 1][2]) for k in range(len(ts) - 1))[-6:]
+        print("[trace-e2e] largest gaps (ms, after, before): " + "; ".join(f"{g:.3f} {a}->{b}" for g, a, b in gaps), file=sys.stderr, flush=True)
     # ---- per-kernel event profile of one step (separate from the timed regions) ---------------------------------------------
     _cabi.profile(True)
     for i in range(2):

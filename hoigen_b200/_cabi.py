@@ -157,6 +157,8 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_encoder_forward": [C.POINTER(EncoderWeights), C.POINTER(EncoderBuffers), _P, _P, _P, _I, _I, _I, _P],
     "hoigen_prior_tokens": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P],
     "hoigen_roi_pair_features": [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P],
+    "hoigen_set_words": [_P, _P, _I, _P],
+    "hoigen_copy_words": [_P, _P, _I, _P],
     "hoigen_rows_to_bf16": [_P, _L, _I, _I, _I, _P, _P],
     "hoigen_broadcast_image_logits": [_P, _P, _I, _I, _I, _P, _P],
     "hoigen_score_pairs": [C.POINTER(ScoreWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],

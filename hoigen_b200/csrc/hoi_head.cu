@@ -5,6 +5,8 @@
 // Reference (U = upt_tip_cache_model_free_finetune_distill3.py):
 //   get_prior U:1445-1495, compute_roi_embeddings U:981-1057 (torchvision.ops.roi_align call sites U:1028-1029),
 //   compute_prior_scores U:806-833, postprocessing U:1408-1427.
+#include <string.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -283,6 +285,26 @@ pair_assemble_kernel(const float* __restrict__ single_feat, const float* __restr
   }
 }
 
+// A few 32-bit words between device memory and MAPPED pinned host memory (either direction) by a kernel on the
+// compute stream.  The path's tiny transfers (CSR layout up, triplet offsets down) must not go through the copy
+// engines: there they queue behind a caller's bulk image upload / detection download and stall the compute stream.
+__global__ void __launch_bounds__(256)
+copy_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// Host values -> device memory THROUGH THE KERNEL PARAMETERS (no DMA, no PCIe read by the kernel): while a caller's bulk
+// image upload saturates the link, a memcpy queues behind it on the copy engine and a kernel reading mapped host memory
+// queues behind it on the link — both were measured to stall the compute stream 0.3-0.9 ms per step.
+constexpr int SET_WORDS_MAX = 960;   // 3840 of the 4096 parameter bytes
+struct WordPack { uint32_t v[SET_WORDS_MAX]; };
+__global__ void __launch_bounds__(256)
+set_words_kernel(uint32_t* __restrict__ dst, const __grid_constant__ WordPack pack, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = pack.v[i];
+}
+
 // rows of `in` (ld_in floats apart) -> L2-normalised (optional) bf16 rows (cols wide); one warp per row.
 __global__ void __launch_bounds__(256)
 rows_to_bf16_kernel(const float* __restrict__ in, long ld_in, int rows, int cols, int normalize,
@@ -469,6 +491,34 @@ int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int3
     KernelScope ks("pair_assemble", s, 0, double(ktot) * FEAT * (3 * 4 + 3 * 2 + (pair_feat_f32 ? 12 : 0)));
     pair_assemble_kernel<<<(ktot * 32 + 255) / 256, 256, 0, s>>>(single_feat, union_feat, box_off, pair_off, batch, ktot,
                                                                  reinterpret_cast<__nv_bfloat16*>(pair_feat_bf16), pair_feat_f32);
+    HOIGEN_CHECK_LAUNCH();
+  }
+  return HOIGEN_OK;
+}
+
+int hoigen_copy_words(void* dst, const void* src, int32_t n_words, hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(dst && src && n_words > 0, "copy_words: bad arguments");
+  HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0,
+                   "copy_words: pointers must be 4-byte aligned");
+  KernelScope ks("copy_words", reinterpret_cast<cudaStream_t>(stream), 0, double(n_words) * 8);
+  copy_words_kernel<<<(n_words + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(src), n_words);
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+int hoigen_set_words(void* dst, const void* host_values, int32_t n_words, hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(dst && host_values && n_words > 0, "set_words: bad arguments");
+  HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 3) == 0, "set_words: dst must be 4-byte aligned");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(host_values);
+  for (int done = 0; done < n_words; done += SET_WORDS_MAX) {
+    const int n = n_words - done < SET_WORDS_MAX ? n_words - done : SET_WORDS_MAX;
+    WordPack pack;
+    memcpy(pack.v, src + done, size_t(n) * 4);     // read on the host NOW: the caller may reuse host_values on return
+    KernelScope ks("set_words", reinterpret_cast<cudaStream_t>(stream), 0, double(n) * 4);
+    set_words_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint32_t*>(dst) + done, pack, n);
     HOIGEN_CHECK_LAUNCH();
   }
   return HOIGEN_OK;

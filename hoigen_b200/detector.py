@@ -364,21 +364,35 @@ class UPT(nn.Module):
         device->host read (per-image triplet offsets) and builds the detections.  A serving loop calls
         launch(batch i+1) before finish(batch i) so the host never leaves the GPU idle; `forward_from_proposals` is
         launch + finish.  Returns None when no image has a valid pair (U:1660-1662)."""
-        dev = images_clip.device
-        _cabi.init(dev)
-        if self._packed is None:
-            self.pack_weights()
-        p, sw = self._packed
-        B = len(region_props)
-        Cn = self.num_classes
-        img_h, img_w = int(images_clip.shape[-2]), int(images_clip.shape[-1])
-        # ---- layout (host): CSR offsets of boxes and pairs -------------------------------------------------
         n_list = [int(rp["boxes"].shape[0]) for rp in region_props]
         if all("n_human" in rp for rp in region_props):
             nh_list = [int(rp["n_human"]) for rp in region_props]
         else:  # one batched device->host read instead of the reference's per-image syncs (U:985-998)
             counts = torch.stack([(rp["labels"] == self.human_idx).sum() for rp in region_props]).cpu()
             nh_list = [int(v) for v in counts]
+        boxes = torch.cat([rp["boxes"] for rp in region_props])
+        scores = torch.cat([rp["scores"] for rp in region_props])
+        labels = torch.cat([rp["labels"] for rp in region_props])
+        return self.launch_packed(images_clip, boxes, scores, labels, n_list, nh_list, dino_image_features,
+                                  return_intermediates=return_intermediates,
+                                  image_boxes=[rp["boxes"] for rp in region_props])
+
+    @torch.no_grad()
+    def launch_packed(self, images_clip: torch.Tensor, boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor,
+                      n_list: Sequence[int], nh_list: Sequence[int], dino_image_features: Optional[torch.Tensor] = None, *,
+                      return_intermediates: bool = False, image_boxes: Optional[Sequence[torch.Tensor]] = None):
+        """`launch_from_proposals` for a caller that already holds the batch's proposals as flat arrays: boxes (sum n, 4),
+        scores (sum n,), labels (sum n,) with image b owning n_list[b] consecutive rows, its nh_list[b] humans first."""
+        dev = images_clip.device
+        _cabi.init(dev)
+        if self._packed is None:
+            self.pack_weights()
+        p, sw = self._packed
+        B = len(n_list)
+        n_list, nh_list = [int(v) for v in n_list], [int(v) for v in nh_list]
+        Cn = self.num_classes
+        img_h, img_w = int(images_clip.shape[-2]), int(images_clip.shape[-1])
+        # ---- layout (host): CSR offsets of boxes and pairs -------------------------------------------------
         n_max = max(n_list)
         if n_max > MAX_PRIOR_TOKENS:
             raise ValueError(f"at most {MAX_PRIOR_TOKENS} boxes per image are supported (got {n_max}); the reference caps "
@@ -392,13 +406,15 @@ class UPT(nn.Module):
         ntot, ktot = box_off[-1], pair_off[-1]
         # pinned staging comes from a small per-module ring: allocating pinned memory per call (cudaHostAlloc) would
         # synchronise the device and serialise launch-ahead callers
-        stage = self._pinned_slot(3 * B + 2 + B + 1)
-        stage.buf[: 3 * B + 2] = torch.tensor(box_off + pair_off + nh_list, dtype=torch.int32)
-        layout = stage.buf[: 3 * B + 2].to(dev, non_blocking=True)
+        stage = self._pinned_slot(4 * B + 3)
+        layout_host = torch.tensor(box_off + pair_off + nh_list, dtype=torch.int32)
+        layout = torch.empty(3 * B + 2, dtype=torch.int32, device=dev)
+        # carried in kernel parameters: neither a copy-engine memcpy nor a PCIe read that could queue behind a bulk upload
+        _cabi.call("hoigen_set_words", layout.data_ptr(), layout_host.data_ptr(), 3 * B + 2)
         d_box_off, d_pair_off, d_nh = layout[: B + 1], layout[B + 1: 2 * B + 2], layout[2 * B + 2:]
-        boxes = torch.cat([rp["boxes"] for rp in region_props]).float().contiguous()
-        scores = torch.cat([rp["scores"] for rp in region_props]).float().contiguous()
-        labels = torch.cat([rp["labels"] for rp in region_props]).to(torch.int64).contiguous()
+        boxes, scores, labels = boxes.float().contiguous(), scores.float().contiguous(), labels.to(torch.int64).contiguous()
+        if boxes.shape[0] != ntot or scores.numel() != ntot or labels.numel() != ntot:
+            raise ValueError(f"packed proposals hold {boxes.shape[0]} boxes, n_list sums to {ntot}")
 
         # ---- a3: prior tokens --------------------------------------------------------------------------------
         prior = self._buf("prior", B * n_max * 64, torch.float32, dev)[: B * n_max * 64].view(B, n_max, 64)
@@ -457,12 +473,14 @@ class UPT(nn.Module):
                    out_labels.data_ptr(), out_objects.data_ptr(), out_pairing.data_ptr(), img_off.data_ptr())
         # ---- the single device->host read of the path (per-image triplet offsets), asynchronous until finish() --------
         host_off = stage.buf[3 * B + 2: 4 * B + 3]
-        host_off.copy_(img_off, non_blocking=True)
+        _cabi.call("hoigen_copy_words", host_off.data_ptr(), img_off.data_ptr(), B + 1)
         done = torch.cuda.Event()
         done.record()
         stage.event = done
         pend = _PendingForward()
-        pend.__dict__.update(B=B, img_h=img_h, img_w=img_w, dev=dev, region_props=region_props, boxes=boxes,
+        if image_boxes is None:
+            image_boxes = boxes.split(n_list)
+        pend.__dict__.update(B=B, img_h=img_h, img_w=img_w, dev=dev, image_boxes=image_boxes, boxes=boxes,
                              box_off=box_off, pair_off=pair_off, ktot=ktot, host_off=host_off, done=done, img_off=img_off,
                              stage=stage, generation=stage.generation,
                              out=(out_scores, out_labels, out_objects, out_pairing), prior=prior, mask=mask, tokens=tokens,
@@ -474,7 +492,7 @@ class UPT(nn.Module):
         if pend is None:
             return None
         B, img_h, img_w, dev = pend.B, pend.img_h, pend.img_w, pend.dev
-        region_props, boxes, box_off, pair_off, ktot = pend.region_props, pend.boxes, pend.box_off, pend.pair_off, pend.ktot
+        image_boxes, boxes, box_off, pair_off, ktot = pend.image_boxes, pend.boxes, pend.box_off, pend.pair_off, pend.ktot
         out_scores, out_labels, out_objects, out_pairing = pend.out
         Cn = self.num_classes
         pend.done.synchronize()
@@ -490,7 +508,7 @@ class UPT(nn.Module):
         ob_v = out_objects[:mtot].split(sizes_m)
         pr_v = out_pairing[: 2 * mtot].split([2 * m for m in sizes_m])
         detections = DetectionList(
-            dict(boxes=region_props[b]["boxes"], pairing=pr_v[b].view(2, sizes_m[b]), scores=sc_v[b], labels=lb_v[b],
+            dict(boxes=image_boxes[b], pairing=pr_v[b].view(2, sizes_m[b]), scores=sc_v[b], labels=lb_v[b],
                  objects=ob_v[b], size=size_t) for b in range(B))
         detections.packed = PackedDetections(scores=out_scores[:mtot], labels=out_labels[:mtot], objects=out_objects[:mtot],
                                              pairing=out_pairing[: 2 * mtot], boxes=boxes, triplet_off=offs, box_off=box_off,

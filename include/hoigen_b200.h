@@ -203,6 +203,13 @@ HOIGEN_API int hoigen_roi_pair_features(const float* tokens, const float* boxes,
                                         float spatial_scale, float* roi_weights /* workspace (ntot+ktot, 32) */,
                                         float* single_feat, float* union_feat, void* pair_feat_bf16,
                                         float* pair_feat_f32, hoigen_stream_t stream);
+/* n 32-bit words dst <- src by a kernel; either side may be mapped pinned host memory (cudaHostAlloc under UVA).  Used
+ * for the path's two tiny transfers (CSR layout host->device, per-image triplet offsets device->host, U:1421-1425's
+ * list lengths) so that they never queue behind bulk copies on the copy engines. */
+HOIGEN_API int hoigen_copy_words(void* dst, const void* src, int32_t n_words, hoigen_stream_t stream);
+/* n 32-bit words from HOST memory (read before the call returns) -> device memory, carried in the kernel parameters:
+ * no DMA and no PCIe read, so the CSR layout of a forward cannot queue behind a bulk upload that shares the link. */
+HOIGEN_API int hoigen_set_words(void* dst, const void* host_values, int32_t n_words, hoigen_stream_t stream);
 HOIGEN_API int hoigen_rows_to_bf16(const float* in, int64_t ld_in, int32_t rows, int32_t cols, int32_t normalize,
                                    void* out_bf16, hoigen_stream_t stream);
 HOIGEN_API int hoigen_broadcast_image_logits(const float* img_logits, const int32_t* pair_off, int32_t batch,
