@@ -100,13 +100,13 @@ def ptr(t: torch.Tensor | None) -> C.c_void_p:
 class AdapterWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "wd", "down_b", "wq", "wo", "w1", "w2", "in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w", "norm2_b", "norm3_w",
-        "norm3_b")]
+        "norm3_b", "wup")]
 
 
 ENCODER_WEIGHT_FIELDS = (
     "conv_w", "class_embedding", "positional_embedding", "ln_pre_w", "ln_pre_b", "ln_post_w", "ln_post_b", "proj_t",
     "ln1_w", "ln1_b", "ln2_w", "ln2_b", "qkv_w", "qkv_b", "out_w", "out_b", "fc_w", "fc_b", "proj_w", "proj_b",
-    "ad_down_w", "ad_down_b", "ad_up_w", "ad_up_b", "ad_scale", "ad_in_proj_w", "ad_in_proj_b", "ad_wq", "ad_wo", "ad_w1", "ad_w2",
+    "ad_down_w", "ad_down_b", "ad_up_w", "ad_up_b", "ad_in_proj_w", "ad_in_proj_b", "ad_wq", "ad_wo", "ad_w1", "ad_w2",
     "ad_out_proj_b", "ad_linear1_b", "ad_linear2_b", "ad_norm2_w", "ad_norm2_b", "ad_norm3_w", "ad_norm3_b")
 
 
@@ -114,7 +114,7 @@ class EncoderWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ENCODER_WEIGHT_FIELDS]
 
 
-ENCODER_BUFFER_FIELDS = ("patches", "patch_emb", "x", "xb", "h", "qkv", "attn", "mlp", "delta", "delta2", "adapter_t",
+ENCODER_BUFFER_FIELDS = ("patches", "patch_emb", "x", "xb", "h", "qkv", "attn", "mlp", "delta", "delta2",
                          "adapter_kv", "tokens_out")
 
 
@@ -149,11 +149,12 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_patchify_bf16": [_P, _P, _I, _P],
     "hoigen_embed_lnpre": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
     "hoigen_layernorm768": [_P, _P, _P, _P, _P, _I, _P],
-    "hoigen_add_layernorm768": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "hoigen_add_layernorm768": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "hoigen_adapter_kv": [_P, _P, _P, _P, _I, _I, _P],
-    "hoigen_adapter_block": [_P, _P, _P, _P, C.POINTER(AdapterWeights), _P, _I, _I, _P],
+    "hoigen_adapter_block": [_P, _P, _P, _P, C.POINTER(AdapterWeights), _P, _P, _I, _I, _P],
     "hoigen_attention": [_P, _P, _I, _P],
     "hoigen_debug_attention_trace": [_P, _P, _I, _P, _P],
+    "hoigen_debug_adapter_trace": [_P],
     "hoigen_encoder_forward": [C.POINTER(EncoderWeights), C.POINTER(EncoderBuffers), _P, _P, _P, _I, _I, _I, _P],
     "hoigen_prior_tokens": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P],
     "hoigen_roi_pair_features": [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P],

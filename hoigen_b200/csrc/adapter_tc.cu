@@ -34,10 +34,17 @@ constexpr int AT_W1 = 81920;      // 16 KiB  [128 n x 64 k]
 constexpr int AT_W2 = 98304;      // 16 KiB  two k-atoms of [64 n x 64 k]
 constexpr int AT_KV = 114688;     // 32 KiB  fp32 [2 images][32 keys][K 64 | V 64]
 constexpr int AT_MISC = 147456;   // barriers, tmem slot, key counts
-constexpr int AT_SMEM_BYTES = AT_MISC + 512 + 2048 + 1024;
-constexpr int AT_TMEM_COLS = 128;
+constexpr int AT_WUP = 151552;    // 64 KiB  up-projection weight rows [0,512) as two [256 n x 64 k] tiles (rows [512,768) reuse WQ..W1)
+constexpr int AT_SMEM_BYTES = AT_WUP + 65536 + 1024;
+constexpr int AT_TMEM_COLS = 512; // body accumulators use [0,128); the up-projection two 256-column buffers
+// output staging panels (128 rows x 64 cols bf16, 16 KiB each) in tiles that are dead once MMA 4 has completed
+__device__ __constant__ int AT_STAGE_PANEL[4] = {AT_A1, AT_P, AT_P + 16384, AT_W2};
+
+// diagnostics: thread 0 of CTA 0 records clock64() at phase k (hoigen_debug_adapter_trace)
+#define STAMP(k) do { if (g.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g.trace[k] = clock64(); } while (0)
 
 struct AdapterTcArgs {
+  long long* trace;
   int has_delta;             // 1: the adapter input is xb + delta_c (pending residual of the previous block's MLP)
   const float* bd;           // (64) down_proj bias
   const float* kv;           // (B*n_max,128) this layer
@@ -45,7 +52,7 @@ struct AdapterTcArgs {
   const float* bq;           // in_proj bias (q part = first 64)
   const float* bo; const float* b1; const float* b2;
   const float* n2_w; const float* n2_b; const float* n3_w; const float* n3_b;
-  __nv_bfloat16* out;        // (M,64)
+  __nv_bfloat16* out;        // (M,64) bottleneck output before the up-projection, or nullptr
   int M, n_max, batch;
 };
 
@@ -94,7 +101,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDelta,
                   const __grid_constant__ CUtensorMap tmWd, const __grid_constant__ CUtensorMap tmWq,
                   const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmW1,
-                  const __grid_constant__ CUtensorMap tmW2, AdapterTcArgs g) {
+                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmWup,
+                  const __grid_constant__ CUtensorMap tmOut, AdapterTcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -104,6 +112,9 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t bar_mma = bar_ld + 8;
   const uint32_t bar_full0 = bar_ld + 16;                     // [4] phase-0 ring: A + Wd k-block landed
   const uint32_t bar_empty0 = bar_ld + 48;                    // [4] phase-0 ring: stage consumed by its MMAs
+  const uint32_t bar_up = bar_ld + 384;                       // up-projection weight rows [0,512) landed
+  const uint32_t bar_up2 = bar_ld + 392;                      // rows [512,768) landed
+  const uint32_t bar_um = bar_ld + 400;                       // [2] up-projection accumulator buffer complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   int* s_nkeys = reinterpret_cast<int*>(bars + 11);          // [2]
   int* s_keyidx = s_nkeys + 2;                               // [2][32]
@@ -131,7 +142,14 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(bar_empty0 + 8u * i, 1);
     }
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDelta);
+    tma_prefetch_desc(&tmWup); tma_prefetch_desc(&tmOut);
+    mbar_init(bar_up, 1); mbar_init(bar_up2, 1);
+    mbar_init(bar_um, 1); mbar_init(bar_um + 8, 1);
     fence_barrier_init();
+    // the first two thirds of the up-projection weight have their own tiles: fetch them now, far off the critical path
+    mbar_arrive_expect_tx(bar_up, 65536);
+    tma_load_2d(base + AT_WUP, &tmWup, bar_up, 0, 0);
+    tma_load_2d(base + AT_WUP + 32768, &tmWup, bar_up, 0, 256);
   }
   if (warp == 0) {
     __syncwarp();
@@ -149,6 +167,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  STAMP(0);
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -189,6 +208,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   float d[32];   // this thread's half row of D (fp32) — also the residual of the norm2 step
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  STAMP(1);
   tc_fence_after();
   // Wd is dead: bring in the four body weight matrices; stage K | V of the compacted keys meanwhile
   if (tid == 0) {
@@ -223,6 +243,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  STAMP(2);
 
   // ---------------- MMA 1: q = D Wq^T ----------------
   if (tid == 0) {
@@ -235,6 +256,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tc_commit(bar_mma);
   }
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  STAMP(3);
   tc_fence_after();
 
   // ---------------- cross-attention: this thread's head (= half) of its row ----------------
@@ -301,6 +323,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  STAMP(4);
 
   // ---------------- MMA 2: a Wo^T ; t = LN2(D + . + bo) ----------------
   if (tid == 0) {
@@ -315,6 +338,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
   for (int i = 0; i < 32; ++i) t[i] = d[i];     // residual D (fp32, still in registers from phase 0)
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  STAMP(5);
   tc_fence_after();
   {
     uint32_t r[32];
@@ -332,6 +356,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  STAMP(6);
 
   // ---------------- MMA 3: hidden = relu(t W1^T + b1) ----------------
   if (tid == 0) {
@@ -343,7 +368,12 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tc_commit(bar_mma);
   }
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  STAMP(7);
   tc_fence_after();
+  if (tid == 0) {   // WQ | WO | W1 are dead now (MMA 1-3 complete): they take up-projection weight rows [512,768)
+    mbar_arrive_expect_tx(bar_up2, 32768);
+    tma_load_2d(base + AT_WQ, &tmWup, bar_up2, 0, 512);
+  }
 #pragma unroll
   for (int c = 0; c < 2; ++c) {          // this thread's 64 hidden channels = k-atom `half` of the hidden tile
     uint32_t r[32];
@@ -361,6 +391,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  STAMP(8);
 
   // ---------------- MMA 4: hidden W2^T ; out = LN3(t + . + b2) ----------------
   if (tid == 0) {
@@ -373,6 +404,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tc_commit(bar_mma);
   }
   mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  STAMP(9);
   tc_fence_after();
   {
     uint32_t r[32];
@@ -386,7 +418,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   }
   ln64_pair(t, half, rrow, red, g.n3_w, g.n3_b);
-  if (row_ok) {
+  if (g.out != nullptr && row_ok) {
     uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(row) * 64 + half * 32);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -398,8 +430,73 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       dst[c] = pk;
     }
   }
+
+  // ---------------- up-projection: delta = out (scale . Wup)^T   (C:201-203; + scale . b_up in the LayerNorm pass) ------
+  // three UMMA 128x256x64 over the 768 output columns, two TMEM buffers; each buffer is drained through four 16 KiB
+  // staging panels and written with TMA stores (rows >= M clipped).
+  store_row_bf16<32>(sm + AT_A0, rrow, half * 4, t);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  STAMP(10);
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 256);
+    mbar_wait(bar_up, 0);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_ss(tmem + uint32_t(c * 256), make_sdesc_sw128(base + AT_A0 + k * 32),
+                     make_sdesc_sw128(base + AT_WUP + c * 32768 + k * 32), idesc, k > 0);
+      tc_commit(bar_um + 8u * c);
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    if (c > 0) {
+      if (tid == 0) tma_store_wait_read();     // the previous chunk's stores have read the staging panels
+      __syncthreads();
+    }
+    mbar_wait(bar_um + 8u * (c & 1), uint32_t(c >> 1));
+    tc_fence_after();
+    // this thread: row rrow, columns [half*128, half*128 + 128) of the chunk = staging panels half*2, half*2 + 1
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_row + uint32_t((c & 1) * 256 + half * 128 + q * 32), r);
+      tmem_wait_ld();
+      // no per-column vectors here: every thread of a warp would pull the same 128 values through the 128 B/clk
+      // shared-memory return path (measured: 2/3 of this phase).  The scale is folded into the weight rows by the
+      // host and the bias row is added by the LayerNorm pass that consumes delta, where a lane owns fixed columns.
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      store_row_bf16<32>(sm + AT_STAGE_PANEL[half * 2 + (q >> 1)], rrow, (q & 1) * 4, v);
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    STAMP(11 + c);
+    if (tid == 0) {
+      if (c == 0) {   // every thread has read buffer 0 out: it takes the last 256 columns
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_bf16(128, 256);
+        mbar_wait(bar_up2, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem, make_sdesc_sw128(base + AT_A0 + k * 32), make_sdesc_sw128(base + AT_WQ + k * 32), idesc, k > 0);
+        tc_commit(bar_um);
+      }
+#pragma unroll
+      for (int pnl = 0; pnl < 4; ++pnl) tma_store_2d(&tmOut, base + AT_STAGE_PANEL[pnl], c * 256 + pnl * 64, r0);
+      tma_store_commit();
+    }
+  }
+  if (tid == 0) tma_store_wait_read();   // the panels must outlive the stores' reads; the writes complete with the grid
+  tc_fence_before();
+  __syncthreads();
+  STAMP(15);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, AT_TMEM_COLS);
@@ -408,14 +505,22 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
 }  // namespace hoigen
 
+static long long* g_adapter_trace = nullptr;
+
 extern "C" {
 
+/* diagnostics: the next hoigen_adapter_block launches record CTA 0's phase timestamps (16 x int64) here; NULL = off */
+int hoigen_debug_adapter_trace(int64_t* trace) {
+  g_adapter_trace = reinterpret_cast<long long*>(trace);
+  return HOIGEN_OK;
+}
+
 int hoigen_adapter_block(const void* xb, const void* delta_c, const float* kv_layer, const uint8_t* mask,
-                         const hoigen_adapter_weights* w, void* out_bf16, int32_t batch, int32_t n_max,
-                         hoigen_stream_t stream) {
+                         const hoigen_adapter_weights* w, void* bottleneck_bf16, void* delta_out_bf16, int32_t batch,
+                         int32_t n_max, hoigen_stream_t stream) {
   using namespace hoigen;
-  HOIGEN_CHECK_ARG(xb && kv_layer && mask && w && out_bf16 && batch > 0, "adapter_block: bad arguments");
-  HOIGEN_CHECK_ARG(w->wd && w->wq && w->wo && w->w1 && w->w2 && w->down_b, "adapter_block: null weight");
+  HOIGEN_CHECK_ARG(xb && kv_layer && mask && w && delta_out_bf16 && batch > 0, "adapter_block: bad arguments");
+  HOIGEN_CHECK_ARG(w->wd && w->wq && w->wo && w->w1 && w->w2 && w->down_b && w->wup, "adapter_block: null weight");
   HOIGEN_CHECK_ARG(n_max > 0 && n_max <= AT_MAXKEYS, "adapter_block: n_max must be in [1,%d] (got %d)", AT_MAXKEYS, n_max);
   static bool attr_set = false;
   if (!attr_set) {
@@ -430,18 +535,21 @@ int hoigen_adapter_block(const void* xb, const void* delta_c, const float* kv_la
   const CUtensorMap* to = get_tmap_2d_bf16(w->wo, 64, 64, 128, 64, 64);
   const CUtensorMap* t1 = get_tmap_2d_bf16(w->w1, 64, 128, 128, 64, 128);
   const CUtensorMap* t2 = get_tmap_2d_bf16(w->w2, 128, 64, 256, 64, 64);
-  if (!tx || !tdl || !td || !tq || !to || !t1 || !t2) return HOIGEN_ERR_CUDA;
+  const CUtensorMap* tu = get_tmap_2d_bf16(w->wup, 64, 768, 128, 64, 256);
+  const CUtensorMap* tout = get_tmap_2d_bf16(delta_out_bf16, 768, uint64_t(M), 1536, 64, 128);
+  if (!tx || !tdl || !td || !tq || !to || !t1 || !t2 || !tu || !tout) return HOIGEN_ERR_CUDA;
   AdapterTcArgs a;
+  a.trace = g_adapter_trace;
   a.has_delta = delta_c ? 1 : 0; a.bd = w->down_b;
   a.kv = kv_layer; a.mask = mask;
   a.bq = w->in_proj_b; a.bo = w->out_proj_b; a.b1 = w->linear1_b; a.b2 = w->linear2_b;
   a.n2_w = w->norm2_w; a.n2_b = w->norm2_b; a.n3_w = w->norm3_w; a.n3_b = w->norm3_b;
-  a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  a.out = reinterpret_cast<__nv_bfloat16*>(bottleneck_bf16);
   a.M = M; a.n_max = n_max; a.batch = batch;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  KernelScope ks("adapter_block", s, 2.0 * M * (768 * 64 * (delta_c ? 2 : 1) + 64 * 64 * 2 + 2 * 64 * 128 + 2 * 64 * n_max),
-                 double(M) * (768 * 2 * (delta_c ? 2 : 1) + 64 * 2));
-  adapter_tc_kernel<<<(M + 127) / 128, AT_THREADS, AT_SMEM_BYTES, s>>>(*tx, *tdl, *td, *tq, *to, *t1, *t2, a);
+  KernelScope ks("adapter_block", s, 2.0 * M * (768 * 64 * (delta_c ? 3 : 2) + 64 * 64 * 2 + 2 * 64 * 128 + 2 * 64 * n_max),
+                 double(M) * (768 * 2 * (delta_c ? 3 : 2)));
+  adapter_tc_kernel<<<(M + 127) / 128, AT_THREADS, AT_SMEM_BYTES, s>>>(*tx, *tdl, *td, *tq, *to, *t1, *t2, *tu, *tout, a);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }

@@ -62,7 +62,7 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out_f32,
                     __nv_bfloat16* __restrict__ out_bf16, int rows, const __nv_bfloat16* __restrict__ delta = nullptr,
                     float* __restrict__ stream_out = nullptr, const __nv_bfloat16* __restrict__ delta_b = nullptr,
-                    __nv_bfloat16* __restrict__ stream_bf16 = nullptr) {
+                    __nv_bfloat16* __restrict__ stream_bf16 = nullptr, const float* __restrict__ col_bias = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -96,6 +96,13 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
           const uint2 d = __ldg(dsrc2 + lane + 32 * j);
           v[j].x += __uint_as_float(d.x << 16); v[j].y += __uint_as_float(d.x & 0xffff0000u);
           v[j].z += __uint_as_float(d.y << 16); v[j].w += __uint_as_float(d.y & 0xffff0000u);
+        }
+      }
+      if (col_bias) {   // bias row of the GEMM that produced delta (kept out of that GEMM's epilogue)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(col_bias) + lane + 32 * j);
+          v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;
         }
       }
       float4* dst = reinterpret_cast<float4*>(stream_out + long(row) * WIDTH);
@@ -211,8 +218,9 @@ int hoigen_layernorm768(const float* x, const float* gamma, const float* beta, f
   return HOIGEN_OK;
 }
 
-int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2_bf16, const float* gamma, const float* beta,
-                            void* out_bf16, void* x_bf16, int32_t rows, hoigen_stream_t stream) {
+int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2_bf16, const float* col_bias,
+                            const float* gamma, const float* beta, void* out_bf16, void* x_bf16, int32_t rows,
+                            hoigen_stream_t stream) {
   using namespace hoigen;
   HOIGEN_CHECK_ARG(x && delta_bf16 && gamma && beta && out_bf16 && rows > 0, "add_layernorm768: bad arguments");
   KernelScope ks("add_layernorm768", reinterpret_cast<cudaStream_t>(stream), 0,
@@ -220,7 +228,7 @@ int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2
   layernorm768_kernel<false><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, nullptr, nullptr, gamma, beta, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows,
       reinterpret_cast<const __nv_bfloat16*>(delta_bf16), x, reinterpret_cast<const __nv_bfloat16*>(delta2_bf16),
-      reinterpret_cast<__nv_bfloat16*>(x_bf16));
+      reinterpret_cast<__nv_bfloat16*>(x_bf16), col_bias);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }

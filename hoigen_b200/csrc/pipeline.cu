@@ -62,20 +62,19 @@ int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder
     aw.linear2_b = w->ad_linear2_b + o64;
     aw.norm2_w = w->ad_norm2_w + o64; aw.norm2_b = w->ad_norm2_b + o64;
     aw.norm3_w = w->ad_norm3_w + o64; aw.norm3_b = w->ad_norm3_b + o64;
+    aw.wup = (const uint16_t*)w->ad_up_w + size_t(l) * D * 64;
     HOIGEN_TRY(hoigen_adapter_block(buf->xb, l == 0 ? nullptr : buf->delta2, buf->adapter_kv + size_t(l) * batch * n_max * 128,
-                                    mask, &aw, buf->adapter_t, batch, n_max, s));
-    HOIGEN_TRY(gemm(buf->adapter_t, 64, (const uint16_t*)w->ad_up_w + size_t(l) * D * 64, 64, M, D, 64,
-                    w->ad_up_b + o768, HOIGEN_ACT_NONE, w->ad_scale + o768, nullptr, 0, nullptr, 0, buf->delta, D, s));
+                                    mask, &aw, nullptr, buf->delta, batch, n_max, s));
     // (2) x += adapter ; x += out_proj(attention(ln_1(x)))
-    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, l == 0 ? nullptr : buf->delta2, w->ln1_w + o768, w->ln1_b + o768,
-                                       buf->h, nullptr, M, s));
+    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, l == 0 ? nullptr : buf->delta2, w->ad_up_b + o768,
+                                       w->ln1_w + o768, w->ln1_b + o768, buf->h, nullptr, M, s));
     HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->qkv_w + size_t(l) * 3 * D * D, D, M, 3 * D, D,
                     w->qkv_b + size_t(l) * 3 * D, HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->qkv, 3 * D, s));
     HOIGEN_TRY(hoigen_attention(buf->qkv, buf->attn, batch, s));
     HOIGEN_TRY(gemm(buf->attn, D, (const uint16_t*)w->out_w + size_t(l) * D * D, D, M, D, D, w->out_b + o768,
                     HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->delta, D, s));
     // (3) mlp: c_proj(quickgelu(c_fc(ln_2(x)))) -> delta2, added by the next adapter block (or the final LayerNorm)
-    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, nullptr, w->ln2_w + o768, w->ln2_b + o768, buf->h,
+    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, nullptr, nullptr, w->ln2_w + o768, w->ln2_b + o768, buf->h,
                                        l + 1 < num_layers ? buf->xb : nullptr, M, s));
     HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->fc_w + size_t(l) * 4 * D * D, D, M, 4 * D, D,
                     w->fc_b + size_t(l) * 4 * D, HOIGEN_ACT_QUICKGELU, nullptr, nullptr, 0, nullptr, 0, buf->mlp, 4 * D, s));
@@ -84,7 +83,7 @@ int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder
   }
   // ---- ln_post on ALL tokens (with the last pending residual), @ proj (768 -> 512) ---------------------------
   if (num_layers > 0) {
-    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta2, nullptr, w->ln_post_w, w->ln_post_b, buf->h, nullptr, M, s));
+    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta2, nullptr, nullptr, w->ln_post_w, w->ln_post_b, buf->h, nullptr, M, s));
   } else {
     HOIGEN_TRY(hoigen_layernorm768(buf->x, w->ln_post_w, w->ln_post_b, nullptr, buf->h, M, s));
   }

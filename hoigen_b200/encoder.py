@@ -155,9 +155,9 @@ class VisionTransformer(nn.Module):
             "proj_w": bf(st(lambda b: b.mlp.c_proj.weight)), "proj_b": f32(st(lambda b: b.mlp.c_proj.bias)),
             "ad_down_w": bf(st(lambda b: b.adaptermlp.down_proj.weight)),
             "ad_down_b": f32(st(lambda b: b.adaptermlp.down_proj.bias)),
-            "ad_up_w": bf(st(lambda b: b.adaptermlp.up_proj.weight)),
-            "ad_up_b": f32(st(lambda b: b.adaptermlp.up_proj.bias)),
-            "ad_scale": f32(st(lambda b: b.adaptermlp.scale)),
+            # the adapter's per-channel output scale (C:203) is folded into the up-projection: (o W^T + b) * s = o (s W)^T + s b
+            "ad_up_w": bf(st(lambda b: b.adaptermlp.scale.float()[:, None] * b.adaptermlp.up_proj.weight.float())),
+            "ad_up_b": f32(st(lambda b: b.adaptermlp.scale.float() * b.adaptermlp.up_proj.bias.float())),
             "ad_in_proj_w": f32(st(lambda b: dl(b).multihead_attn.in_proj_weight)),
             "ad_in_proj_b": f32(st(lambda b: dl(b).multihead_attn.in_proj_bias)),
             "ad_wq": bf(st(lambda b: dl(b).multihead_attn.in_proj_weight[:64])),
@@ -187,7 +187,7 @@ class VisionTransformer(nn.Module):
                 "patches": e((batch * 196, 768), bf), "patch_emb": e((batch * 196, 768), f32),
                 "x": e((M, 768), f32), "xb": e((M, 768), bf), "h": e((M, 768), bf), "qkv": e((M, 2304), bf),
                 "attn": e((M, 768), bf), "mlp": e((M, 3072), bf), "delta": e((M, 768), bf), "delta2": e((M, 768), bf),
-                "adapter_t": e((M, 64), bf), "adapter_kv": e((12, batch * n_max, 128), f32),
+                "adapter_kv": e((12, batch * n_max, 128), f32),
                 "tokens_out": e((M, 512), f32),
             }
             s = _cabi.EncoderBuffers()

@@ -96,11 +96,11 @@ HOIGEN_API int hoigen_embed_lnpre(const float* patch_emb, const float* class_emb
 /* LayerNorm over 768 columns, fp32 statistics, eps 1e-5 (C:409-415) -> bf16 and/or fp32 */
 HOIGEN_API int hoigen_layernorm768(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
                                    int32_t rows, hoigen_stream_t stream);
-/* x += delta (+ delta2, optional) in place on the fp32 residual stream, then LayerNorm(x) -> out_bf16, and optionally a
- * bf16 copy of the updated stream (x_bf16): the residual adds of C:456-458 deferred from the producing GEMMs into the
- * LayerNorm pass that streams the same rows anyway. */
-HOIGEN_API int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2_bf16, const float* gamma,
-                                       const float* beta, void* out_bf16, void* x_bf16, int32_t rows,
+/* x += delta (+ delta2) (+ col_bias, a (768) row vector) in place on the fp32 residual stream, then LayerNorm(x) ->
+ * out_bf16, and optionally a bf16 copy of the updated stream (x_bf16): the residual adds of C:456-458 deferred from the
+ * producing GEMMs into the LayerNorm pass that streams the same rows anyway.  delta2, col_bias, x_bf16 may be NULL. */
+HOIGEN_API int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2_bf16, const float* col_bias,
+                                       const float* gamma, const float* beta, void* out_bf16, void* x_bf16, int32_t rows,
                                        hoigen_stream_t stream);
 /* Adapter cross-attention K/V of the prior tokens for all layers: kv[l][tok][0:64]=K, [64:128]=V  (C:63-66).
  * in_proj_w (layers,192,64) rows [q;k;v], in_proj_b (layers,192); prior (tokens,64). */
@@ -119,16 +119,21 @@ typedef struct {
   const float* linear1_b;  /* (128) */
   const float* linear2_b;  /* (64) */
   const float* norm2_w; const float* norm2_b; const float* norm3_w; const float* norm3_b; /* (64) */
+  const void* wup;         /* bf16 (768, 64)  scale[:,None] * up_proj.weight (the adapter's output scale folded in) */
 } hoigen_adapter_weights;
-/* One adapter block up to (not including) the up-projection, on the tensor cores — Adapter.forward C:183-200 with
- * forward_post C:51-72.  The adapter input is xb + delta_c: xb = bf16 copy of the stream (B*197,768), delta_c = the
+/* One whole adapter block on the tensor cores — Adapter.forward C:183-203 with forward_post C:51-72.  The adapter input is xb + delta_c: xb = bf16 copy of the stream (B*197,768), delta_c = the
  * still-pending bf16 residual of the previous block's MLP output (C:458) or NULL; the sum is never materialised
  * ((xb + delta_c) Wd^T = xb Wd^T + delta_c Wd^T inside one TMEM accumulation).
- *   d = relu(down_proj(xb + delta_c)) ; t = LN2(d + MHA_2h(d, prior, mask)) ; out = LN3(t + FFN(t))  -> bf16 (B*197,64)
+ *   d = relu(down_proj(xb + delta_c)) ; t = LN2(d + MHA_2h(d, prior, mask)) ; o = LN3(t + FFN(t))   (B*197,64)
+ *   delta_out = o wup^T -> bf16 (B*197,768) = scale * (up_proj(o) - up_proj.bias): the residual of C:456 less its
+ *   constant row scale * up_proj.bias, which the caller adds with hoigen_add_layernorm768(col_bias)
+ * bottleneck_bf16 (B*197,64) receives o when not NULL (tests).
  * kv_layer (B*n_max,128) from hoigen_adapter_kv; mask (B,n_max) uint8, 1 = padding. n_max <= 32. */
 HOIGEN_API int hoigen_adapter_block(const void* xb, const void* delta_c, const float* kv_layer, const uint8_t* mask,
-                                    const hoigen_adapter_weights* w, void* out_bf16, int32_t batch, int32_t n_max,
-                                    hoigen_stream_t stream);
+                                    const hoigen_adapter_weights* w, void* bottleneck_bf16, void* delta_out_bf16,
+                                    int32_t batch, int32_t n_max, hoigen_stream_t stream);
+/* Diagnostics only: later hoigen_adapter_block launches write CTA 0's clock64() phase stamps (16 x int64) to trace. */
+HOIGEN_API int hoigen_debug_adapter_trace(int64_t* trace);
 /* 12-head attention over 197 tokens (tcgen05): qkv bf16 (B*197, 2304) = [q|k|v] -> out bf16 (B*197, 768). C:443-445 */
 HOIGEN_API int hoigen_attention(const void* qkv_bf16, void* out_bf16, int32_t batch, hoigen_stream_t stream);
 /* Diagnostics only: the same launch; CTA 0 writes clock64() stamps [16 items][8 phases] of its softmax loop to trace. */
@@ -152,8 +157,7 @@ typedef struct {
   const void* fc_w; const float* fc_b;       /* bf16 (12,3072,768), (12,3072)   mlp.c_fc.* */
   const void* proj_w; const float* proj_b;   /* bf16 (12,768,3072), (12,768)    mlp.c_proj.* */
   const void* ad_down_w; const float* ad_down_b;  /* bf16 (12,64,768), (12,64)  adaptermlp.down_proj.* */
-  const void* ad_up_w; const float* ad_up_b;      /* bf16 (12,768,64), (12,768) adaptermlp.up_proj.* */
-  const float* ad_scale;                          /* (12,768)                   adaptermlp.scale */
+  const void* ad_up_w; const float* ad_up_b;      /* bf16 (12,768,64), (12,768) adaptermlp.scale * up_proj.{weight,bias} */
   const float* ad_in_proj_w; const float* ad_in_proj_b;    /* (12,192,64), (12,192)  mhsa_layers.0.multihead_attn */
   const void* ad_wq; const void* ad_wo;                    /* bf16 (12,64,64) each: q rows of in_proj, out_proj */
   const void* ad_w1; const void* ad_w2;                    /* bf16 (12,128,64), (12,64,128): linear1, linear2 */
@@ -174,7 +178,6 @@ typedef struct {            /* caller-owned workspace, M = B*197 */
   void* mlp;                /* bf16 (M, 3072) */
   void* delta;              /* bf16 (M, 768)   adapter up-proj / attention out-proj output awaiting its residual add */
   void* delta2;             /* bf16 (M, 768)   MLP c_proj output awaiting its residual add (applied by the next adapter block) */
-  void* adapter_t;          /* bf16 (M, 64) */
   float* adapter_kv;        /* f32  (12, B*n_max, 128) */
   float* tokens_out;        /* f32  (M, 512)   OUTPUT: ln_post(x) @ proj for all tokens; row b*197 = feat_global[b],
                                                rows b*197+1.. = feat_local[b] token-major (C:503-506) */

@@ -163,7 +163,8 @@ def test_patchify_and_embed(cuda_device, enc_state):
 
 
 def test_add_layernorm768(cuda_device):
-    """Deferred residual adds (C:456-458): x += delta (+ delta2) exactly in fp32, LayerNorm -> bf16, optional bf16 copy."""
+    """Deferred residual adds (C:456-458): x += delta (+ delta2) (+ bias row) exactly in fp32, LayerNorm -> bf16,
+    optional bf16 copy."""
     from hoigen_b200 import _cabi
     g = torch.Generator(device="cpu").manual_seed(31)
     rows = 1003
@@ -171,15 +172,17 @@ def test_add_layernorm768(cuda_device):
     d1 = torch.randn(rows, 768, generator=g).bfloat16()
     d2 = torch.randn(rows, 768, generator=g).bfloat16()
     gamma, beta = torch.rand(768, generator=g) + 0.5, torch.randn(768, generator=g)
+    cb = torch.randn(768, generator=g)
+    cbd = cb.to(cuda_device)
     for two, copy in ((False, False), (True, False), (False, True), (True, True)):
         x = x0.clone().to(cuda_device)
         h = torch.zeros(rows, 768, device=cuda_device, dtype=torch.bfloat16)
         xb = torch.zeros(rows, 768, device=cuda_device, dtype=torch.bfloat16)
         a, b, gw, gb = d1.to(cuda_device), d2.to(cuda_device), gamma.to(cuda_device), beta.to(cuda_device)
         _cabi.call("hoigen_add_layernorm768", x.data_ptr(), a.data_ptr(), b.data_ptr() if two else None,
-                   gw.data_ptr(), gb.data_ptr(), h.data_ptr(),
+                   cbd.data_ptr() if copy else None, gw.data_ptr(), gb.data_ptr(), h.data_ptr(),
                    xb.data_ptr() if copy else None, rows)
-        xr = x0 + d1.float() + (d2.float() if two else 0)
+        xr = x0 + d1.float() + (d2.float() if two else 0) + (cb if copy else 0)
         assert torch.equal(x.cpu(), xr)
         ref = torch.nn.functional.layer_norm(xr, (768,), gamma, beta, 1e-5)
         assert (h.float().cpu() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item()
@@ -223,8 +226,8 @@ def _adapter_inputs(enc_state, layer, B, n_list, device, seed=5):
 
 
 def test_adapter_kv_and_block(cuda_device, enc_state):
-    """Adapter block (down-proj of xb + delta_c by linearity; body: C:183-200 / C:51-72) against the oracle's
-    restatement, ragged key counts incl. n=1, with and without a pending residual."""
+    """Adapter block (down-proj of xb + delta_c by linearity; body: C:183-200 / C:51-72; up-proj + scale C:201-203)
+    against the oracle's restatement, ragged key counts incl. n=1, with and without a pending residual."""
     import ctypes as C
     from hoigen_b200 import _cabi
     from oracle import hoi_forward_ref as O
@@ -241,9 +244,15 @@ def test_adapter_kv_and_block(cuda_device, enc_state):
     wd, bd = enc_state[ad + "down_proj.weight"], enc_state[ad + "down_proj.bias"]
     wb = [wd.bfloat16().contiguous().to(cuda_device), bd.contiguous().to(cuda_device), w[0][:64].bfloat16().contiguous(),
           w[2].bfloat16().contiguous(), w[4].bfloat16().contiguous(), w[6].bfloat16().contiguous()]
+    wu, bu = enc_state[ad + "up_proj.weight"], enc_state[ad + "up_proj.bias"]
+    g0 = torch.Generator().manual_seed(23)
+    sc = torch.rand(768, generator=g0) + 0.5
+    wus = (sc[:, None] * wu).bfloat16()                         # the output scale is folded into the weight rows
+    up = [wus.contiguous().to(cuda_device)]
     aw = _cabi.AdapterWeights()
     for f, t in zip(("wd", "down_b", "wq", "wo", "w1", "w2", "in_proj_b", "out_proj_b", "linear1_b", "linear2_b", "norm2_w",
-                     "norm2_b", "norm3_w", "norm3_b"), (*wb, w[1], w[3], w[5], w[7], w[8], w[9], w[10], w[11])):
+                     "norm2_b", "norm3_w", "norm3_b", "wup"),
+                    (*wb, w[1], w[3], w[5], w[7], w[8], w[9], w[10], w[11], *up)):
         setattr(aw, f, t.data_ptr())
     g = torch.Generator().manual_seed(17)
     x0 = torch.randn(B, 197, 768, generator=g)
@@ -254,8 +263,9 @@ def test_adapter_kv_and_block(cuda_device, enc_state):
         x = x0.bfloat16().view(B * 197, 768).to(cuda_device).contiguous()
         dl = delta.view(B * 197, 768).to(cuda_device).contiguous()
         out = torch.zeros(B * 197, 64, device=cuda_device, dtype=torch.bfloat16)
+        dout = torch.full((B * 197 + 5, 768), 3.0, device=cuda_device, dtype=torch.bfloat16)
         _cabi.call("hoigen_adapter_block", x.data_ptr(), dl.data_ptr() if use_delta else None, kv.data_ptr(), m8.data_ptr(),
-                   C.byref(aw), out.data_ptr(), B, n_max)
+                   C.byref(aw), out.data_ptr(), dout.data_ptr(), B, n_max)
         xr = x0.bfloat16().float() + (delta.float() if use_delta else 0)
         d = torch.relu(torch.nn.functional.linear(xr, wd, bd))
         t2 = O._mha(d, prior, prior, sd[blk + "multihead_attn.in_proj_weight"], sd[blk + "multihead_attn.in_proj_bias"],
@@ -267,6 +277,10 @@ def test_adapter_kv_and_block(cuda_device, enc_state):
         err = (out.float().cpu() - ref).abs().max().item()
         # bf16 tensor-core operands (weights + activations between the MMAs), fp32 accumulation / softmax / LayerNorm
         assert err < 4e-2 * max(1.0, ref.abs().max().item()), (use_delta, err)
+        ref_up = torch.nn.functional.linear(out.float().cpu(), wus.float())           # from the kernel's own bottleneck
+        err_up = (dout[: B * 197].float().cpu() - ref_up).abs().max().item()
+        assert err_up < 2 ** -7 * max(1.0, ref_up.abs().max().item()), (use_delta, err_up)
+        assert (dout[B * 197:] == 3.0).all()                                                   # rows past M are clipped
 
 
 def test_encoder_matches_oracle_and_golden(cuda_device, enc_state):
