@@ -32,9 +32,10 @@ constexpr int AT_WQ = 65536;      //  8 KiB  [64 n x 64 k]
 constexpr int AT_WO = 73728;      //  8 KiB
 constexpr int AT_W1 = 81920;      // 16 KiB  [128 n x 64 k]
 constexpr int AT_W2 = 98304;      // 16 KiB  two k-atoms of [64 n x 64 k]
-constexpr int AT_KV = 114688;     // 32 KiB  fp32 [2 images][32 keys][K 64 | V 64]
+constexpr int AT_KV = 114688;     // 32 KiB  bf16 block-diagonal key / value tiles: [2 images][Kbd 8 KiB | Vbd 8 KiB]
 constexpr int AT_MISC = 147456;   // barriers, tmem slot, key counts
-constexpr int AT_WUP = 151552;    // 64 KiB  up-projection weight rows [0,512) as two [256 n x 64 k] tiles (rows [512,768) reuse WQ..W1)
+constexpr int AT_VEC = AT_MISC + 2560;   // 704 floats: the block's small fp32 vectors (biases, LayerNorm affine)
+constexpr int AT_WUP = 153600;    // 64 KiB  up-projection weight rows [0,512) as two [256 n x 64 k] tiles (rows [512,768) reuse WQ..W1)
 constexpr int AT_SMEM_BYTES = AT_WUP + 65536 + 1024;
 constexpr int AT_TMEM_COLS = 512; // body accumulators use [0,128); the up-projection two 256-column buffers
 // output staging panels (128 rows x 64 cols bf16, 16 KiB each) in tiles that are dead once MMA 4 has completed
@@ -42,6 +43,9 @@ __device__ __constant__ int AT_STAGE_PANEL[4] = {AT_A1, AT_P, AT_P + 16384, AT_W
 
 // diagnostics: thread 0 of CTA 0 records clock64() at phase k (hoigen_debug_adapter_trace)
 #define STAMP(k) do { if (g.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g.trace[k] = clock64(); } while (0)
+
+// offsets (floats) inside the staged vector block
+constexpr int V_BD = 0, V_BQ = 64, V_BO = 128, V_B1 = 192, V_B2 = 320, V_N2W = 384, V_N2B = 448, V_N3W = 512, V_N3B = 576, V_END = 640;
 
 struct AdapterTcArgs {
   long long* trace;
@@ -70,6 +74,25 @@ __device__ __forceinline__ void store_row_bf16(uint8_t* tile, int row, int chunk
   }
 }
 
+// 32 TMEM columns of this thread's row from the image-0 block (taddr) or the image-1 block (taddr + 64).  tcgen05.ld is
+// warp-collective with a warp-uniform address, and the one warp that straddles two images needs both blocks.
+__device__ __forceinline__ void load_by_image(uint32_t taddr, int img_of_row, uint32_t (&r)[32]) {
+  const unsigned in1 = __ballot_sync(0xffffffffu, img_of_row == 1);
+  if (in1 != 0xffffffffu) {
+    tmem_ld_32x32b_x32(taddr, r);
+    tmem_wait_ld();
+  }
+  if (in1 != 0u) {
+    uint32_t r1[32];
+    tmem_ld_32x32b_x32(taddr + 64u, r1);
+    tmem_wait_ld();
+    if (img_of_row == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = r1[i];
+    }
+  }
+}
+
 // LayerNorm over a 64-wide row held by TWO threads (32 values each; partner = same row, other column half).
 // Partial sums are exchanged through shared memory: red[half][row].
 __device__ __forceinline__ void ln64_pair(float (&v)[32], int half, int rrow, float* red, const float* __restrict__ gamma,
@@ -88,8 +111,8 @@ __device__ __forceinline__ void ln64_pair(float (&v)[32], int half, int rrow, fl
   const float rstd = rsqrtf((q + red[256 + (half ^ 1) * 128 + rrow]) * (1.0f / 64) + 1e-5f);
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + half * 32 + i));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + half * 32 + i));
+    const float4 g = *reinterpret_cast<const float4*>(gamma + half * 32 + i);
+    const float4 b = *reinterpret_cast<const float4*>(beta + half * 32 + i);
     v[i] = (v[i] - mean) * rstd * g.x + b.x;
     v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
     v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z;
@@ -119,7 +142,6 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   int* s_nkeys = reinterpret_cast<int*>(bars + 11);          // [2]
   int* s_keyidx = s_nkeys + 2;                               // [2][32]
   float* red = reinterpret_cast<float*>(sm + AT_MISC + 512); // [2][2][128] LayerNorm partials
-  float* sKV = reinterpret_cast<float*>(sm + AT_KV);
 
   // 8 warps: warp w and w+4 share TMEM lane quadrant (w & 3) = the same 32 rows; `half` selects the column half
   // (the attention head, 32 of the 64 bottleneck channels, 64 of the 128 hidden channels).
@@ -170,6 +192,16 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   STAMP(0);
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // the block's small vectors -> smem now: every later phase would otherwise start with a dependent global-load latency
+  float* s_vec = reinterpret_cast<float*>(sm + AT_VEC);
+  {
+    const float* srcs[9] = {g.bd, g.bq, g.bo, g.b1, g.b2, g.n2_w, g.n2_b, g.n3_w, g.n3_b};
+    const int offs[10] = {V_BD, V_BQ, V_BO, V_B1, V_B2, V_N2W, V_N2B, V_N3W, V_N3B, V_END};
+#pragma unroll
+    for (int v = 0; v < 9; ++v)
+      for (int i = tid; i < offs[v + 1] - offs[v]; i += AT_THREADS) s_vec[offs[v] + i] = __ldg(srcs[v] + i);
+  }
+  __syncthreads();   // (phase 0 below synchronises through mbarriers only)
 
   uint32_t mma_phase = 0;
   const uint32_t t_row = tmem + (uint32_t((warp & 3) * 32) << 16);
@@ -225,20 +257,28 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bd + half * 32 + i));
+      const float4 bb = *reinterpret_cast<const float4*>(s_vec + V_BD + half * 32 + i);
       d[i] = fmaxf(__uint_as_float(r[i]) + bb.x, 0.f); d[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + bb.y, 0.f);
       d[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + bb.z, 0.f); d[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + bb.w, 0.f);
     }
     store_row_bf16<32>(sm + AT_A0, rrow, half * 4, d);
   }
-  for (int img = 0; img < 2; ++img) {
-    const int b = img == 0 ? b0 : b1;
-    const int n = s_nkeys[img];
-    for (int i = tid; i < n * 32; i += AT_THREADS) {
-      const int j = i >> 5, c4 = i & 31;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(g.kv + (size_t(b) * g.n_max + s_keyidx[img * AT_MAXKEYS + j]) * 128) + c4);
-      reinterpret_cast<float4*>(sKV + (img * AT_MAXKEYS + j) * 128)[c4] = v;
+  // Block-diagonal bf16 key / value tiles of the (at most two) images of this tile, 64 rows x 64 dims each:
+  // row h*32 + j holds head h's 32 dims of compacted key j in columns [h*32, h*32+32) and zeros elsewhere (rows j >= n
+  // all zero).  One UMMA 128x64x64 then yields both heads' scores (q Kbd^T, column h*32 + j) and one more both heads'
+  // outputs (P Vbd, Vbd consumed MN-major) — the tensor core instead of 1024 FMAs + 256 broadcast LDS.128 per thread.
+  for (int i = tid; i < 2 * 2 * 64 * 8; i += AT_THREADS) {
+    const int ch = i & 7, rw = (i >> 3) & 63, kv = (i >> 9) & 1, img = i >> 10;
+    const int h = rw >> 5, j = rw & 31;
+    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+    if ((ch >> 2) == h && j < s_nkeys[img]) {
+      const int b = img == 0 ? b0 : b1;
+      const float4* src = reinterpret_cast<const float4*>(
+          g.kv + (size_t(b) * g.n_max + s_keyidx[img * AT_MAXKEYS + j]) * 128 + kv * 64 + ch * 8);
+      const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+      pk = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
     }
+    *reinterpret_cast<uint4*>(sm + AT_KV + img * 16384 + kv * 8192 + sw128_offset(rw, uint32_t(ch))) = pk;
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -259,11 +299,10 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   STAMP(3);
   tc_fence_after();
 
-  // ---------------- cross-attention: this thread's head (= half) of its row ----------------
+  // ---------------- cross-attention (C:51-72, 2 heads of 32 dims, key_padding_mask) on the tensor cores ----------------
+  const int img_of_row = (row_ok ? row : g.M - 1) / AT_TOKENS == b0 ? 0 : 1;
   {
-    const int img = (row_ok ? row : g.M - 1) / AT_TOKENS == b0 ? 0 : 1;
-    const int n = s_nkeys[img];
-    const float* kvb = sKV + img * AT_MAXKEYS * 128;
+    // q (+ bias, * 32^-0.5) -> bf16 A tile
     const float qscale = 0.17677669529663687f;  // 32^-0.5
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_row + half * 32, r);
@@ -271,54 +310,71 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     float q[32];
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bq + half * 32 + i));
+      const float4 bb = *reinterpret_cast<const float4*>(s_vec + V_BQ + half * 32 + i);
       q[i] = (__uint_as_float(r[i]) + bb.x) * qscale; q[i + 1] = (__uint_as_float(r[i + 1]) + bb.y) * qscale;
       q[i + 2] = (__uint_as_float(r[i + 2]) + bb.z) * qscale; q[i + 3] = (__uint_as_float(r[i + 3]) + bb.w) * qscale;
     }
-    float s[AT_MAXKEYS];
+    store_row_bf16<32>(sm + AT_A1, rrow, half * 4, q);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {   // scores of both heads against image 0's keys -> columns [0,64), image 1's -> [64,128)
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+    for (int img = 0; img < (b1 != b0 ? 2 : 1); ++img)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_ss(tmem + uint32_t(img * 64), make_sdesc_sw128(base + AT_A1 + k * 32),
+                     make_sdesc_sw128(base + AT_KV + img * 16384 + k * 32), idesc, k > 0);
+    tc_commit(bar_mma);
+  }
+  mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  tc_fence_after();
+  {
+    const int n = s_nkeys[img_of_row];
+    uint32_t r[32];
+    load_by_image(t_row + uint32_t(half * 32), img_of_row, r);
+    float p[32];
     float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < AT_MAXKEYS; ++j) {
-      s[j] = -INFINITY;
-      if (j < n) {
-        const float4* kr = reinterpret_cast<const float4*>(kvb + j * 128 + half * 32);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent chains
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 kk = kr[c];
-          a0 = fmaf(q[4 * c], kk.x, a0); a1 = fmaf(q[4 * c + 1], kk.y, a1);
-          a2 = fmaf(q[4 * c + 2], kk.z, a2); a3 = fmaf(q[4 * c + 3], kk.w, a3);
-        }
-        s[j] = (a0 + a1) + (a2 + a3);
-        mx = fmaxf(mx, s[j]);
-      }
+    for (int j = 0; j < 32; ++j) {
+      p[j] = j < n ? __uint_as_float(r[j]) : -INFINITY;
+      mx = fmaxf(mx, p[j]);
     }
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < AT_MAXKEYS; ++j) {
-      s[j] = (j < n) ? __expf(s[j] - mx) : 0.f;
-      sum += s[j];
+    for (int j = 0; j < 32; ++j) {
+      p[j] = j < n ? __expf(p[j] - mx) : 0.f;
+      sum += p[j];
     }
-    const float inv = 1.0f / sum;   // n == 0: 0 * inf = NaN below, as in the reference (all keys masked)
+    const float inv = 1.0f / sum;   // n == 0: 0 * inf = NaN, as in the reference (all keys masked)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) p[j] *= inv;
+    store_row_bf16<32>(sm + AT_P, rrow, half * 4, p);      // P[row][h*32 + j]
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {   // attention output of both heads: P Vbd -> columns [128,192) (image 0's values), [192,256) (image 1's)
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, /*a_mn_major=*/0, /*b_mn_major=*/1);
+    for (int img = 0; img < (b1 != b0 ? 2 : 1); ++img)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_ss(tmem + uint32_t(128 + img * 64), make_sdesc_sw128(base + AT_P + k * 32),
+                     make_sdesc_sw128(base + AT_KV + img * 16384 + 8192 + k * 2048), idesc, k > 0);
+    tc_commit(bar_mma);
+  }
+  mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+  tc_fence_after();
+  {
+    uint32_t r[32];
+    load_by_image(t_row + uint32_t(128 + half * 32), img_of_row, r);
     float a[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) a[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < AT_MAXKEYS; ++j) {
-      if (j < n) {
-        const float4* vr = reinterpret_cast<const float4*>(kvb + j * 128 + 64 + half * 32);
-        const float p = s[j];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 vv = vr[c];
-          a[4 * c] = fmaf(p, vv.x, a[4 * c]); a[4 * c + 1] = fmaf(p, vv.y, a[4 * c + 1]);
-          a[4 * c + 2] = fmaf(p, vv.z, a[4 * c + 2]); a[4 * c + 3] = fmaf(p, vv.w, a[4 * c + 3]);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) a[i] *= inv;
-    store_row_bf16<32>(sm + AT_A1, rrow, half * 4, a);
+    for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(r[i]);
+    store_row_bf16<32>(sm + AT_A1, rrow, half * 4, a);     // the q tile has been consumed by the score MMAs
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -346,12 +402,12 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bo + half * 32 + i));
+      const float4 bb = *reinterpret_cast<const float4*>(s_vec + V_BO + half * 32 + i);
       t[i] += __uint_as_float(r[i]) + bb.x; t[i + 1] += __uint_as_float(r[i + 1]) + bb.y;
       t[i + 2] += __uint_as_float(r[i + 2]) + bb.z; t[i + 3] += __uint_as_float(r[i + 3]) + bb.w;
     }
   }
-  ln64_pair(t, half, rrow, red, g.n2_w, g.n2_b);
+  ln64_pair(t, half, rrow, red, s_vec + V_N2W, s_vec + V_N2B);
   store_row_bf16<32>(sm + AT_A0, rrow, half * 4, t);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -382,7 +438,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     float hv[32];
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.b1 + half * 64 + c * 32 + i));
+      const float4 bb = *reinterpret_cast<const float4*>(s_vec + V_B1 + half * 64 + c * 32 + i);
       hv[i] = fmaxf(__uint_as_float(r[i]) + bb.x, 0.f); hv[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + bb.y, 0.f);
       hv[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + bb.z, 0.f); hv[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + bb.w, 0.f);
     }
@@ -412,12 +468,12 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(g.b2 + half * 32 + i));
+      const float4 bb = *reinterpret_cast<const float4*>(s_vec + V_B2 + half * 32 + i);
       t[i] += __uint_as_float(r[i]) + bb.x; t[i + 1] += __uint_as_float(r[i + 1]) + bb.y;
       t[i + 2] += __uint_as_float(r[i + 2]) + bb.z; t[i + 3] += __uint_as_float(r[i + 3]) + bb.w;
     }
   }
-  ln64_pair(t, half, rrow, red, g.n3_w, g.n3_b);
+  ln64_pair(t, half, rrow, red, s_vec + V_N3W, s_vec + V_N3B);
   if (g.out != nullptr && row_ok) {
     uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(row) * 64 + half * 32);
 #pragma unroll
