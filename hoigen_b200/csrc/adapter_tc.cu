@@ -1,7 +1,7 @@
 // InsAdapter bottleneck body on the tensor cores: one CTA per 128-token tile, two threads per token row
 // (one per attention head / column half).
 //
-//   D = relu((xb + delta_c) Wd^T + bd)       12 or 24 x UMMA 128x64x64 fed by a 4-stage TMA ring: the down-projection
+//   D = relu((xb + delta_c) Wd^T + bd)       12 or 24 x UMMA 128x64x64 fed by a 6-stage TMA ring: the down-projection
 //                                            with the pending residual of the previous block's MLP output folded in by
 //                                            linearity (xb Wd^T + delta_c Wd^T), no thread touches the operands
 //   q  = D Wq^T + bq                         UMMA 128x64x64
@@ -58,6 +58,7 @@ struct AdapterTcArgs {
   const float* n2_w; const float* n2_b; const float* n3_w; const float* n3_b;
   __nv_bfloat16* out;        // (M,64) bottleneck output before the up-projection, or nullptr
   int M, n_max, batch;
+  int tile_rows;             // rows of the stream per CTA (<= 128, multiple of 8): M spread over all SMs in one wave
 };
 
 template <int NVALS>
@@ -133,8 +134,8 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AT_MISC);
   const uint32_t bar_ld = smem_u32(bars);
   const uint32_t bar_mma = bar_ld + 8;
-  const uint32_t bar_full0 = bar_ld + 16;                     // [4] phase-0 ring: A + Wd k-block landed
-  const uint32_t bar_empty0 = bar_ld + 48;                    // [4] phase-0 ring: stage consumed by its MMAs
+  const uint32_t bar_full0 = bar_ld + 416;                    // [6] phase-0 ring: A + Wd k-block landed
+  const uint32_t bar_empty0 = bar_ld + 464;                   // [6] phase-0 ring: stage consumed by its MMAs
   const uint32_t bar_up = bar_ld + 384;                       // up-projection weight rows [0,512) landed
   const uint32_t bar_up2 = bar_ld + 392;                      // rows [512,768) landed
   const uint32_t bar_um = bar_ld + 400;                       // [2] up-projection accumulator buffer complete
@@ -148,18 +149,20 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;
   const int rrow = (warp & 3) * 32 + lane;      // row within the tile
-  const int r0 = blockIdx.x * 128;
+  // The UMMAs are 128 rows tall whatever tile_rows is: rows >= tile_rows of the A tiles are never loaded, their
+  // accumulator lanes hold garbage that only the (idle) threads of those rows ever see.
+  const int r0 = blockIdx.x * g.tile_rows;
   const int row = r0 + rrow;
-  const bool row_ok = row < g.M;
+  const bool row_ok = rrow < g.tile_rows && row < g.M;
   const int b0 = r0 / AT_TOKENS;
-  const int b1 = min(r0 + 127, g.M - 1) / AT_TOKENS;
+  const int b1 = min(r0 + g.tile_rows - 1, g.M - 1) / AT_TOKENS;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmWd); tma_prefetch_desc(&tmWq); tma_prefetch_desc(&tmWo);
     tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     mbar_init(bar_ld, 1);
     mbar_init(bar_mma, 1);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 6; ++i) {
       mbar_init(bar_full0 + 8u * i, 1);
       mbar_init(bar_empty0 + 8u * i, 1);
     }
@@ -208,17 +211,20 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // ---------------- phase 0: D = relu((xb + delta_c) Wd^T + bd) as ONE accumulation over the concatenated K ------------
   // A k-blocks come straight from the bf16 stream copy xb (12 k-blocks) and, if pending, from delta_c (12 more, the same
   // Wd k-blocks again): (xb + delta_c) Wd^T = xb Wd^T + delta_c Wd^T.  Pure TMA -> UMMA, no thread touches the data.
-  // Ring of 4 stages x [A 16 KiB | Wd 8 KiB] in [P+16K, end of KV) — those regions are (re)loaded afterwards.
-  constexpr int AT_RING = AT_P + 16384;
+  // Ring of 6 stages x [A 16 KiB | Wd 8 KiB] over ALL the tile regions [0, MISC) — they are only filled afterwards.  The
+  // phase is bound by bytes in flight per SM (99 CTAs, ~1.5 us L2/HBM latency), hence as deep as shared memory allows.
+  constexpr int AT_RING = 0;
   constexpr int RING_STAGE = 16384 + 8192;
+  constexpr int RING_DEPTH = 6;
+  static_assert(RING_DEPTH * RING_STAGE <= AT_MISC, "phase-0 ring overruns the barrier block");
   const int nkb = g.has_delta ? 24 : 12;
   if (warp == 1 && lane == 0) {            // TMA producer
     for (int kb = 0; kb < nkb; ++kb) {
-      const int st = kb & 3;
-      if (kb >= 4) mbar_wait(bar_empty0 + 8u * st, ((kb >> 2) - 1) & 1u);
+      const int st = kb % RING_DEPTH;
+      if (kb >= RING_DEPTH) mbar_wait(bar_empty0 + 8u * st, ((kb / RING_DEPTH) - 1) & 1u);
       const uint32_t dst = base + AT_RING + st * RING_STAGE;
       const uint32_t full = bar_full0 + 8u * st;
-      mbar_arrive_expect_tx(full, RING_STAGE);
+      mbar_arrive_expect_tx(full, uint32_t(g.tile_rows) * 128u + 8192u);
       const int kk = (kb % 12) * 64;
       tma_load_2d(dst, kb < 12 ? &tmX : &tmDelta, full, kk, r0);
       tma_load_2d(dst + 16384, &tmWd, full, kk, 0);
@@ -226,8 +232,8 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   } else if (tid == 0) {                   // MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(128, 64);
     for (int kb = 0; kb < nkb; ++kb) {
-      const int st = kb & 3;
-      mbar_wait(bar_full0 + 8u * st, (kb >> 2) & 1u);
+      const int st = kb % RING_DEPTH;
+      mbar_wait(bar_full0 + 8u * st, (kb / RING_DEPTH) & 1u);
       tc_fence_after();
       const uint32_t a_addr = base + AT_RING + st * RING_STAGE;
 #pragma unroll
@@ -267,7 +273,9 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // row h*32 + j holds head h's 32 dims of compacted key j in columns [h*32, h*32+32) and zeros elsewhere (rows j >= n
   // all zero).  One UMMA 128x64x64 then yields both heads' scores (q Kbd^T, column h*32 + j) and one more both heads'
   // outputs (P Vbd, Vbd consumed MN-major) — the tensor core instead of 1024 FMAs + 256 broadcast LDS.128 per thread.
-  for (int i = tid; i < 2 * 2 * 64 * 8; i += AT_THREADS) {
+#pragma unroll
+  for (int it = 0; it < 2 * 2 * 64 * 8 / AT_THREADS; ++it) {   // unrolled: the 8 x 2 global loads of a thread overlap
+    const int i = tid + it * AT_THREADS;
     const int ch = i & 7, rw = (i >> 3) & 63, kv = (i >> 9) & 1, img = i >> 10;
     const int h = rw >> 5, j = rw & 31;
     uint4 pk = make_uint4(0u, 0u, 0u, 0u);
@@ -584,15 +592,19 @@ int hoigen_adapter_block(const void* xb, const void* delta_c, const float* kv_la
     attr_set = true;
   }
   const int M = batch * AT_TOKENS;
-  const CUtensorMap* tx = get_tmap_2d_bf16(xb, 768, uint64_t(M), 1536, 64, 128);
-  const CUtensorMap* tdl = delta_c ? get_tmap_2d_bf16(delta_c, 768, uint64_t(M), 1536, 64, 128) : tx;
+  // one wave over all SMs: 12608 rows / 148 SMs -> 88-row tiles on 144 CTAs instead of 128-row tiles on 99 (the
+  // bandwidth phases — down-projection operands in, up-projection residual out — are bound per SM)
+  int tile_rows = ((M + num_sms() - 1) / num_sms() + 7) / 8 * 8;
+  tile_rows = tile_rows < 8 ? 8 : (tile_rows > 128 ? 128 : tile_rows);
+  const CUtensorMap* tx = get_tmap_2d_bf16(xb, 768, uint64_t(M), 1536, 64, uint32_t(tile_rows));
+  const CUtensorMap* tdl = delta_c ? get_tmap_2d_bf16(delta_c, 768, uint64_t(M), 1536, 64, uint32_t(tile_rows)) : tx;
   const CUtensorMap* td = get_tmap_2d_bf16(w->wd, 768, 64, 1536, 64, 64);
   const CUtensorMap* tq = get_tmap_2d_bf16(w->wq, 64, 64, 128, 64, 64);
   const CUtensorMap* to = get_tmap_2d_bf16(w->wo, 64, 64, 128, 64, 64);
   const CUtensorMap* t1 = get_tmap_2d_bf16(w->w1, 64, 128, 128, 64, 128);
   const CUtensorMap* t2 = get_tmap_2d_bf16(w->w2, 128, 64, 256, 64, 64);
   const CUtensorMap* tu = get_tmap_2d_bf16(w->wup, 64, 768, 128, 64, 256);
-  const CUtensorMap* tout = get_tmap_2d_bf16(delta_out_bf16, 768, uint64_t(M), 1536, 64, 128);
+  const CUtensorMap* tout = get_tmap_2d_bf16(delta_out_bf16, 768, uint64_t(M), 1536, 64, uint32_t(tile_rows));
   if (!tx || !tdl || !td || !tq || !to || !t1 || !t2 || !tu || !tout) return HOIGEN_ERR_CUDA;
   AdapterTcArgs a;
   a.trace = g_adapter_trace;
@@ -601,11 +613,11 @@ int hoigen_adapter_block(const void* xb, const void* delta_c, const float* kv_la
   a.bq = w->in_proj_b; a.bo = w->out_proj_b; a.b1 = w->linear1_b; a.b2 = w->linear2_b;
   a.n2_w = w->norm2_w; a.n2_b = w->norm2_b; a.n3_w = w->norm3_w; a.n3_b = w->norm3_b;
   a.out = reinterpret_cast<__nv_bfloat16*>(bottleneck_bf16);
-  a.M = M; a.n_max = n_max; a.batch = batch;
+  a.M = M; a.n_max = n_max; a.batch = batch; a.tile_rows = tile_rows;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   KernelScope ks("adapter_block", s, 2.0 * M * (768 * 64 * (delta_c ? 3 : 2) + 64 * 64 * 2 + 2 * 64 * 128 + 2 * 64 * n_max),
                  double(M) * (768 * 2 * (delta_c ? 3 : 2)));
-  adapter_tc_kernel<<<(M + 127) / 128, AT_THREADS, AT_SMEM_BYTES, s>>>(*tx, *tdl, *td, *tq, *to, *t1, *t2, *tu, *tout, a);
+  adapter_tc_kernel<<<(M + tile_rows - 1) / tile_rows, AT_THREADS, AT_SMEM_BYTES, s>>>(*tx, *tdl, *td, *tq, *to, *t1, *t2, *tu, *tout, a);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
