@@ -49,6 +49,9 @@ def workload_config(args, world):
         "l2": f"inputs rotate over {args.rotate} distinct batches ({args.rotate * args.batch * 3 * 224 * 224 * 4 / 1e6:.0f} MB "
               "> 126 MB L2); weights + activations per step >> L2",
         "dino_features": "supplied as input (SURVEY.md 8 row a8: stock ResNet-50 is outside the path)",
+        "collective": ("none (single GPU)" if world == 1 else
+                       ("one NCCL all-gather of the sweep's accumulated detections, inside each timed region"
+                        if getattr(args, "gather_every", 0) == 0 else "one NCCL all-gather of the step's detections per step")),
     }
 
 
@@ -195,7 +198,7 @@ def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from hoigen_b200 import _cabi, synthetic as S
     from hoigen_b200.detector import UPT
-    from hoigen_b200.gather import gather_packed
+    from hoigen_b200.gather import gather_packed, gather_packed_begin, gather_packed_end, merge_packed
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
@@ -228,8 +231,49 @@ def run_b200(args, rank, world, local_rank):
     def finish_resident(pend):
         dets = model.finish(pend)          # the path's device->host read (triplet offsets) + detection views
         if world > 1:
-            gather_packed(dets.packed)     # the path's one collective: every rank ends up with every rank's detections
+            exchange(dets.packed)
         return dets
+
+    # The path's one collective: every rank ends up with every rank's detections.  One fixed-capacity all-gather per
+    # step, enqueued without a host sync and read back one step later (so it never stalls the step launched ahead).
+    gather_cap = B * 120 * 30 * 36 + B * (BOXES_H + BOXES_O) * 16
+    pending_gather = []
+
+    gather_ev = []
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    sweep = []
+
+    def exchange(packed):
+        if os.environ.get("HOIGEN_BENCH_NO_GATHER"):    # diagnostics only: the floor without any collective
+            return
+        if args.gather_every == 0:         # default: accumulate on the device, ONE exchange per sweep (= timed region)
+            sweep.append(packed)
+            return
+        if os.environ.get("HOIGEN_BENCH_TRACE"):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pending_gather.append(gather_packed_begin(packed, gather_cap, B))
+            e1.record()
+            gather_ev.append((e0, e1))
+            if len(gather_ev) == 12:
+                torch.cuda.synchronize()
+                print("[trace] exchange on-stream ms: " + " ".join(f"{a.elapsed_time(c):.3f}" for a, c in gather_ev), file=sys.stderr, flush=True)
+        elif os.environ.get("HOIGEN_BENCH_GATHER_SIDE"):
+            gather_stream.wait_event(packed.done)
+            with torch.cuda.stream(gather_stream):
+                pending_gather.append(gather_packed_begin(packed, gather_cap, B))
+        else:
+            pending_gather.append(gather_packed_begin(packed, gather_cap, B))
+        if len(pending_gather) > 1:
+            gather_packed_end(pending_gather.pop(0))
+
+    def drain_exchanges():
+        while pending_gather:
+            gather_packed_end(pending_gather.pop(0))
+        if sweep:
+            gather_packed(merge_packed(sweep))
+            sweep.clear()
 
     def run_resident(first, count):
         """`count` complete steps; step i+1 is enqueued before step i is waited for, so the host's per-step work (layout,
@@ -243,6 +287,8 @@ def run_b200(args, rank, world, local_rank):
             tb = time.perf_counter()
             dets = finish_resident(pend)
             pend = nxt
+            if nxt is None:
+                drain_exchanges()
             if trace:
                 print(f"[trace] step {first + i}: launch {1e3 * (tb - ta):.2f} ms, finish {1e3 * (time.perf_counter() - tb):.2f} ms",
                       file=sys.stderr, flush=True)
@@ -296,6 +342,8 @@ def run_b200(args, rank, world, local_rank):
         step's compute; the host buffer is double-buffered and waited for one step later)."""
         dets = model.finish(pend)
         pk = dets.packed
+        if world > 1:
+            exchange(pk)
         m = pk.scores.numel()
         ho = host_out[i % 2]
         if ho["keep"] is not None:
@@ -352,7 +400,10 @@ def run_b200(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()                           # NVML is initialised here, outside the timed regions
-    run_resident(0, args.warmup)
+    wdets = run_resident(0, args.warmup)
+    if world > 1 and args.gather_every == 0:
+        # warm the sweep-sized exchange too (NCCL channel setup / allocator growth for a K-step payload are one-time costs)
+        gather_packed(merge_packed([wdets.packed] * args.steps))
     barrier()
     _cabi.profile(False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -379,6 +430,7 @@ def run_b200(args, rank, world, local_rank):
     pend, m_out = run_host(w_e2e, args.steps, pend)
     for ho in host_out:
         ho["ev"].synchronize()
+    drain_exchanges()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     clocks.active = False
@@ -484,6 +536,9 @@ def main():
     ap.add_argument("--cache-rows", type=int, default=4096)
     ap.add_argument("--rotate", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-every", type=int, default=0,
+                    help="N>1 only. 0 (default): detections accumulate on the device and are exchanged with ONE all-gather per "
+                         "sweep (= per timed region, inside it); 1: one non-blocking fixed-capacity all-gather per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -60,6 +60,21 @@ def _worker_packed(rank, world, port, q):
         _, mine = _fake_packed(rank, n_img)
         got = gather_packed(mine)
         ok = len(got) == world
+        # the non-blocking form: two exchanges in flight, read back in order; fixed capacity agreed by all ranks
+        from hoigen_b200.gather import gather_packed_begin, gather_packed_end
+        h1 = gather_packed_begin(mine, 1 << 16, 8)
+        h2 = gather_packed_begin(mine, 1 << 16, 8)
+        for got2 in (gather_packed_end(h1), gather_packed_end(h2)):
+            ok = ok and len(got2) == world
+            for r in range(world):
+                ok = ok and got2[r].triplet_off == got[r].triplet_off and got2[r].box_off == got[r].box_off
+                for f in ("scores", "labels", "objects", "pairing", "boxes"):
+                    ok = ok and torch.equal(getattr(got2[r], f), getattr(got[r], f))
+        try:
+            gather_packed_begin(mine, 64, 8)        # capacity too small: loud, before any collective is issued
+            ok = False
+        except ValueError:
+            pass
         for r in range(world):
             ref_dets, _ = _fake_packed(r, 3 + r)
             ok = ok and got[r].num_images == 3 + r
