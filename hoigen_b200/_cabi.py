@@ -133,11 +133,16 @@ class ScoreWeights(C.Structure):
     ]
 
 
-SCORE_BUFFER_FIELDS = ("pair_feat_bf16", "phi", "phi_img", "g_bf16", "d_bf16", "img_logits", "logits")
+SCORE_BUFFER_FIELDS = ("pair_feat_bf16", "phi", "phi_img", "g_bf16", "d_bf16", "img_logits", "logits", "ld_logits")
 
 
 class ScoreBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in SCORE_BUFFER_FIELDS]
+
+
+class FoldedWeights(C.Structure):
+    _fields_ = [("num_classes", C.c_int32), ("pair_w", C.c_void_p), ("global_w", C.c_void_p), ("dino_w", C.c_void_p),
+                ("bias_total", C.c_void_p)]
 
 
 _P, _I, _F, _L = C.c_void_p, C.c_int32, C.c_float, C.c_int64
@@ -161,9 +166,10 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_set_words": [_P, _P, _I, _P],
     "hoigen_copy_words": [_P, _P, _I, _P],
     "hoigen_rows_to_bf16": [_P, _L, _I, _I, _I, _P, _P],
-    "hoigen_broadcast_image_logits": [_P, _P, _I, _I, _I, _P, _P],
+    "hoigen_broadcast_image_logits": [_P, _P, _I, _I, _I, _I, _P, _P],
     "hoigen_score_pairs": [C.POINTER(ScoreWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
-    "hoigen_emit_triplets": [_P, _I, _P, _P, _P, _P, _I, _I, _P, _I, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
+    "hoigen_score_pairs_folded": [C.POINTER(FoldedWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
+    "hoigen_emit_triplets": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
 }
 
 EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", "hoigen_launch_count",

@@ -320,12 +320,12 @@ rows_to_bf16_kernel(const float* __restrict__ in, long ld_in, int rows, int cols
 
 // logits[i][:] = img_logits[image(i)][:]   (the per-image global-CLIP + DINO cache terms, U:1115, U:1138)
 __global__ void broadcast_rows_kernel(const float* __restrict__ img_logits, const int* __restrict__ pair_off, int nimg,
-                                      int ktot, int C, float* __restrict__ logits) {
+                                      int ktot, int C, int ld, float* __restrict__ logits) {
   const long total = long(ktot) * C;
   for (long e = blockIdx.x * long(blockDim.x) + threadIdx.x; e < total; e += long(gridDim.x) * blockDim.x) {
     const int i = int(e / C), c = int(e % C);
     const int b = find_image(pair_off, nimg, i);
-    logits[e] = img_logits[size_t(b) * C + c];
+    logits[size_t(i) * ld + c] = img_logits[size_t(b) * C + c];
   }
 }
 
@@ -401,7 +401,7 @@ scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ offsets, co
 }
 
 __global__ void __launch_bounds__(256)
-emit_kernel(const float* __restrict__ logits, int C, const float* __restrict__ pr_in, const int* __restrict__ offsets,
+emit_kernel(const float* __restrict__ logits, int C, int ld, const float* __restrict__ pr_in, const int* __restrict__ offsets,
             const int64_t* __restrict__ labels, const int* __restrict__ box_off, const int* __restrict__ pair_off,
             const int* __restrict__ img_off, int nimg, int ktot, const uint32_t* __restrict__ table_bits, int words,
             long capacity, float* __restrict__ out_scores, int64_t* __restrict__ out_labels,
@@ -428,7 +428,7 @@ emit_kernel(const float* __restrict__ logits, int C, const float* __restrict__ p
     if ((m >> lane) & 1u) {
       const long p = long(pos) + __popc(m & ((1u << lane) - 1u));
       if (p < capacity) {
-        const float x = logits[size_t(i) * C + c];
+        const float x = logits[size_t(i) * ld + c];
         out_scores[p] = (1.0f / (1.0f + expf(-x))) * pr;
         out_labels[p] = c;
         out_objects[p] = obj;
@@ -536,20 +536,21 @@ int hoigen_rows_to_bf16(const float* in, int64_t ld_in, int32_t rows, int32_t co
 }
 
 int hoigen_broadcast_image_logits(const float* img_logits, const int32_t* pair_off, int32_t batch, int32_t ktot,
-                                  int32_t num_classes, float* logits, hoigen_stream_t stream) {
+                                  int32_t num_classes, int32_t ld_logits, float* logits, hoigen_stream_t stream) {
   using namespace hoigen;
   HOIGEN_CHECK_ARG(img_logits && pair_off && logits && batch > 0 && num_classes > 0, "broadcast_image_logits: bad arguments");
+  HOIGEN_CHECK_ARG(ld_logits >= num_classes, "broadcast_image_logits: ld_logits < num_classes");
   if (ktot == 0) return HOIGEN_OK;
   const long total = long(ktot) * num_classes;
   const int blocks = int(min(long(num_sms()) * 8, (total + 255) / 256));
   KernelScope ks("broadcast_image_logits", reinterpret_cast<cudaStream_t>(stream), 0, double(total) * 4 + double(batch) * num_classes * 4);
   broadcast_rows_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img_logits, pair_off, batch, ktot,
-                                                                                      num_classes, logits);
+                                                                                      num_classes, ld_logits, logits);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
 
-int hoigen_emit_triplets(const float* logits, int32_t num_classes, const float* scores, const int64_t* labels,
+int hoigen_emit_triplets(const float* logits, int32_t num_classes, int32_t ld_logits, const float* scores, const int64_t* labels,
                          const int32_t* box_off, const int32_t* pair_off, int32_t batch, int32_t ktot,
                          const uint32_t* table_bits, int32_t table_words, float hyper_lambda, int32_t* work_counts,
                          int32_t* work_offsets, float* work_pr, int64_t capacity, float* out_scores,
@@ -576,7 +577,7 @@ int hoigen_emit_triplets(const float* logits, int32_t num_classes, const float* 
     // reads the logits row of every pair; writes 36 bytes per emitted triplet (count unknown on the host: the
     // per-class average of the object->target table bounds it; bench.py recomputes the exact figure from img_off)
     KernelScope ks("emit_triplets", s, 0, double(ktot) * num_classes * 4);
-    emit_kernel<<<(ktot * 32 + 255) / 256, 256, 0, s>>>(logits, num_classes, work_pr, work_offsets, labels, box_off, pair_off,
+    emit_kernel<<<(ktot * 32 + 255) / 256, 256, 0, s>>>(logits, num_classes, ld_logits, work_pr, work_offsets, labels, box_off, pair_off,
                                                         img_off, batch, ktot, table_bits, table_words, long(capacity),
                                                         out_scores, out_labels, out_objects, out_pairing);
     HOIGEN_CHECK_LAUNCH();

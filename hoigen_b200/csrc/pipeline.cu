@@ -102,6 +102,8 @@ int hoigen_score_pairs(const hoigen_score_weights* w, const hoigen_score_buffers
                    "score_pairs: cache_rows must be a positive multiple of 8 (got %d)", w->cache_rows);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int C = w->num_classes, N = w->cache_rows;
+  const int L = buf->ld_logits > 0 ? int(buf->ld_logits) : C;   // row pitch of the logits accumulator
+  HOIGEN_CHECK_ARG(L >= C, "score_pairs: ld_logits (%d) < num_classes (%d)", L, C);
   // The affinity is LINEAR in the reference (phi = f W^T + b, no exp: U:1156-1158), so the bias is carried exactly
   // in fp32 through the second GEMM's epilogue: ((f W^T + b) Y)/s = (f W^T) Y / s + (b Y)/s, bias_term = b Y.
   // ---- per-image terms: global-CLIP cache (U:1133-1138) and DINO cache (U:1112-1115) -------------------------
@@ -120,18 +122,55 @@ int hoigen_score_pairs(const hoigen_score_weights* w, const hoigen_score_buffers
                     buf->img_logits, C, buf->img_logits, C, nullptr, 0, s));
   }
   if (ktot == 0) return HOIGEN_OK;
-  HOIGEN_TRY(hoigen_broadcast_image_logits(buf->img_logits, pair_off, batch, ktot, C, buf->logits, s));
+  HOIGEN_TRY(hoigen_broadcast_image_logits(buf->img_logits, pair_off, batch, ktot, C, L, buf->logits, s));
   // ---- pair terms: three cache branches (H, O, U) + text classifier, accumulated in place ---------------------
   for (int x = 0; x < 3; ++x) {
     const uint16_t* f = (const uint16_t*)buf->pair_feat_bf16 + size_t(x) * ktot * 512;
     HOIGEN_TRY(gemm(f, 512, w->cache_keys[x], 512, ktot, N, 512, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
                     nullptr, 0, buf->phi, N, s));
-    HOIGEN_TRY(gemm(buf->phi, N, w->label_t[x], N, ktot, C, N, w->bias_term[x], HOIGEN_ACT_NONE, w->colscale[x], buf->logits, C,
-                    buf->logits, C, nullptr, 0, s));
+    HOIGEN_TRY(gemm(buf->phi, N, w->label_t[x], N, ktot, C, N, w->bias_term[x], HOIGEN_ACT_NONE, w->colscale[x], buf->logits, L,
+                    buf->logits, L, nullptr, 0, s));
   }
   const uint16_t* fu = (const uint16_t*)buf->pair_feat_bf16 + size_t(2) * ktot * 512;
-  HOIGEN_TRY(gemm(fu, 512, w->text_w, 512, ktot, C, 512, nullptr, HOIGEN_ACT_NONE, w->colscale_text, buf->logits, C,
-                  buf->logits, C, nullptr, 0, s));
+  HOIGEN_TRY(gemm(fu, 512, w->text_w, 512, ktot, C, 512, nullptr, HOIGEN_ACT_NONE, w->colscale_text, buf->logits, L,
+                  buf->logits, L, nullptr, 0, s));
+  return HOIGEN_OK;
+}
+
+int hoigen_score_pairs_folded(const hoigen_folded_weights* w, const hoigen_score_buffers* buf, const float* tokens,
+                              const float* dino_feats, const int32_t* pair_off, int32_t batch, int32_t ktot,
+                              hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(w && buf && tokens && pair_off, "score_pairs_folded: null argument");
+  HOIGEN_CHECK_ARG(batch > 0 && ktot >= 0 && w->num_classes > 0 && w->pair_w && w->bias_total, "score_pairs_folded: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int C = w->num_classes;
+  const int L = buf->ld_logits > 0 ? int(buf->ld_logits) : C;
+  HOIGEN_CHECK_ARG(L >= C, "score_pairs_folded: ld_logits (%d) < num_classes (%d)", L, C);
+  // per-image terms: img_logits = bias_total + g E_G + d E_D
+  bool have_img = false;
+  if (w->global_w) {
+    HOIGEN_TRY(hoigen_rows_to_bf16(tokens, 197L * 512, batch, 512, 1, buf->g_bf16, s));
+    HOIGEN_TRY(gemm(buf->g_bf16, 512, w->global_w, 512, batch, C, 512, w->bias_total, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                    buf->img_logits, C, nullptr, 0, s));
+    have_img = true;
+  }
+  if (w->dino_w) {
+    HOIGEN_CHECK_ARG(dino_feats != nullptr, "score_pairs_folded: the folded weights include a DINO branch but no features were given");
+    HOIGEN_TRY(hoigen_rows_to_bf16(dino_feats, 2048, batch, 2048, 0, buf->d_bf16, s));
+    HOIGEN_TRY(gemm(buf->d_bf16, 2048, w->dino_w, 2048, batch, C, 2048, have_img ? nullptr : w->bias_total, HOIGEN_ACT_NONE,
+                    nullptr, have_img ? buf->img_logits : nullptr, C, buf->img_logits, C, nullptr, 0, s));
+    have_img = true;
+  }
+  if (ktot == 0) return HOIGEN_OK;
+  if (have_img) HOIGEN_TRY(hoigen_broadcast_image_logits(buf->img_logits, pair_off, batch, ktot, C, L, buf->logits, s));
+  // pair terms: the planar [3][Ktot][512] features against the three 512-column blocks of pair_w, accumulated in place
+  for (int x = 0; x < 3; ++x) {
+    const uint16_t* f = (const uint16_t*)buf->pair_feat_bf16 + size_t(x) * ktot * 512;
+    const bool first = (x == 0 && !have_img);
+    HOIGEN_TRY(gemm(f, 512, (const uint16_t*)w->pair_w + x * 512, 1536, ktot, C, 512, first ? w->bias_total : nullptr,
+                    HOIGEN_ACT_NONE, nullptr, first ? nullptr : buf->logits, L, buf->logits, L, nullptr, 0, s));
+  }
   return HOIGEN_OK;
 }
 

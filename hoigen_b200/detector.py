@@ -109,8 +109,10 @@ class UPT(nn.Module):
                  clip_head: Optional[nn.Module] = None, human_idx: int = 0, box_score_thresh: float = 0.2,
                  min_instances: int = 3, max_instances: int = 15, hyper_lambda: float = 2.8,
                  object_class_to_target_class: Optional[List[List[int]]] = None, dino: bool = True,
-                 clip_global: bool = True, dataset: str = "hicodet"):
+                 clip_global: bool = True, dataset: str = "hicodet", fold_cache: bool = False):
         super().__init__()
+        # opt-in: contract every (linear) cache with its label matrix at pack time — see hoigen_score_pairs_folded
+        self.fold_cache = fold_cache
         C_, N = num_classes, cache_rows
         self.detector, self.postprocessor, self.dino_model = detector, postprocessor, dino_model
         self.clip_head = clip_head if clip_head is not None else _ClipHead(VisionTransformer())
@@ -261,6 +263,35 @@ class UPT(nn.Module):
         p["text_w"] = bf(self.adapter_union_weight)
         p["colscale_text"] = f32(self.logit_scale_text.float().expand(C_))
         sw.text_w, sw.colscale_text = p["text_w"].data_ptr(), p["colscale_text"].data_ptr()
+        if self.fold_cache:
+            # ((f W^T + b) Y) s / L = f (W^T Y s / L) + (b Y) s / L  for every branch; products in fp32, operands to bf16 once
+            fw = _cabi.FoldedWeights()
+            fw.num_classes = C_
+            bias_total = torch.zeros(C_, device=dev)
+            blocks = []
+            for X in ("H", "O", "U"):
+                W, b, Y = (getattr(self, f"gen_adapter_{X}_weight").float().to(dev), getattr(self, f"gen_adapter_{X}_bias").float().to(dev),
+                           getattr(self, f"gen_label_{X}").float().to(dev))
+                cs = (getattr(self, f"gen_logit_scale_{X}").float().to(dev) / lens(f"sample_lens_{X}", Y))       # (C)
+                blocks.append((Y.t() @ W) * cs[:, None])                                              # (C, 512)
+                bias_total += (b @ Y) * cs
+            blocks[2] = blocks[2] + self.adapter_union_weight.float().to(dev) * self.logit_scale_text.float().to(dev)
+            p["fold_pair_w"] = bf(torch.cat(blocks, dim=1))                                            # (C, 1536)
+            fw.pair_w = p["fold_pair_w"].data_ptr()
+            Yu_d = Yu.to(dev)
+            if self.clip_global:
+                cs = self.clip_cache_logit.float().to(dev) / lens("global_sample_len", Yu_d)
+                p["fold_global_w"] = bf((Yu_d.t() @ self.global_cache.float().to(dev).t()) * cs[:, None])     # (C, 512)
+                bias_total += (self.global_cache_bias.float().to(dev) @ Yu_d) * cs
+                fw.global_w = p["fold_global_w"].data_ptr()
+            if self.dino:
+                cs = self.dino_cache_logit.float().to(dev) / lens("dino_sample_len", Yu_d)
+                p["fold_dino_w"] = bf((Yu_d.t() @ self.dino_cache.float().to(dev).t()) * cs[:, None])         # (C, 2048)
+                bias_total += (self.dino_cache_bias.float().to(dev) @ Yu_d) * cs
+                fw.dino_w = p["fold_dino_w"].data_ptr()
+            p["fold_bias_total"] = f32(bias_total)
+            fw.bias_total = p["fold_bias_total"].data_ptr()
+            p["folded"] = fw
         # prior MLP, transposed to (in,out)
         for i, lyr in enumerate(self.priors_downproj.layers):
             p[f"prior_w{i}t"] = f32(lyr.weight.t())
@@ -447,7 +478,8 @@ class UPT(nn.Module):
                    union.data_ptr(), pf_bf16.data_ptr(), pf_f32.data_ptr() if pf_f32 is not None else None)
         # ---- a10: cache + text logits --------------------------------------------------------------------------------
         N = sw.cache_rows
-        logits = self._buf("logits", ktot * Cn, torch.float32, dev)
+        ldl = (Cn + 3) // 4 * 4           # padded row pitch: the accumulating GEMM epilogues stay on their float4 path
+        logits = self._buf("logits", ktot * ldl, torch.float32, dev)
         sb = _cabi.ScoreBuffers()
         sb.pair_feat_bf16 = pf_bf16.data_ptr()
         sb.phi = self._buf("phi", ktot * N, torch.bfloat16, dev).data_ptr()
@@ -456,8 +488,13 @@ class UPT(nn.Module):
         sb.d_bf16 = self._buf("d_bf16", B * 2048, torch.bfloat16, dev).data_ptr()
         sb.img_logits = self._buf("img_logits", B * Cn, torch.float32, dev).data_ptr()
         sb.logits = logits.data_ptr()
-        _cabi.call("hoigen_score_pairs", C.byref(sw), C.byref(sb), tokens.data_ptr(),
-                   dino_ptr.data_ptr() if dino_ptr is not None else None, d_pair_off.data_ptr(), B, ktot)
+        sb.ld_logits = ldl
+        if self.fold_cache:
+            _cabi.call("hoigen_score_pairs_folded", C.byref(p["folded"]), C.byref(sb), tokens.data_ptr(),
+                       dino_ptr.data_ptr() if dino_ptr is not None else None, d_pair_off.data_ptr(), B, ktot)
+        else:
+            _cabi.call("hoigen_score_pairs", C.byref(sw), C.byref(sb), tokens.data_ptr(),
+                       dino_ptr.data_ptr() if dino_ptr is not None else None, d_pair_off.data_ptr(), B, ktot)
         # ---- a11-a12: prior scores + ordered triplet emission ----------------------------------------------------------
         cap = ktot * p["max_row_len"]
         out_scores = torch.empty(max(cap, 1), device=dev, dtype=torch.float32)
@@ -465,7 +502,7 @@ class UPT(nn.Module):
         out_objects = torch.empty(max(cap, 1), device=dev, dtype=torch.int64)
         out_pairing = torch.empty(max(2 * cap, 2), device=dev, dtype=torch.int64)
         img_off = torch.empty(B + 1, device=dev, dtype=torch.int32)
-        _cabi.call("hoigen_emit_triplets", logits.data_ptr(), Cn, scores.data_ptr(), labels.data_ptr(), d_box_off.data_ptr(),
+        _cabi.call("hoigen_emit_triplets", logits.data_ptr(), Cn, ldl, scores.data_ptr(), labels.data_ptr(), d_box_off.data_ptr(),
                    d_pair_off.data_ptr(), B, ktot, p["table_bits"].data_ptr(), p["table_words"], float(self.hyper_lambda),
                    self._buf("emit_counts", ktot, torch.int32, dev).data_ptr(),
                    self._buf("emit_offsets", ktot + 1, torch.int32, dev).data_ptr(),
@@ -482,7 +519,7 @@ class UPT(nn.Module):
             image_boxes = boxes.split(n_list)
         pend.__dict__.update(B=B, img_h=img_h, img_w=img_w, dev=dev, image_boxes=image_boxes, boxes=boxes,
                              box_off=box_off, pair_off=pair_off, ktot=ktot, host_off=host_off, done=done, img_off=img_off,
-                             stage=stage, generation=stage.generation,
+                             stage=stage, generation=stage.generation, ldl=ldl,
                              out=(out_scores, out_labels, out_objects, out_pairing), prior=prior, mask=mask, tokens=tokens,
                              logits=logits, pf_f32=pf_f32, return_intermediates=return_intermediates)
         return pend
@@ -516,7 +553,8 @@ class UPT(nn.Module):
         detections.packed.done = pend.done     # recorded after the last kernel of this forward (for copies on other streams)
         if pend.return_intermediates:
             inter = dict(prior=pend.prior, mask=pend.mask.bool(), tokens=pend.tokens.view(B, TOKENS, 512),
-                         logits=[pend.logits[: ktot * Cn].view(ktot, Cn)[pair_off[b]: pair_off[b + 1]] for b in range(B)],
+                         logits=[pend.logits[: ktot * pend.ldl].view(ktot, pend.ldl)[pair_off[b]: pair_off[b + 1], :Cn]
+                                 for b in range(B)],
                          pair_feats=pend.pf_f32[: 3 * ktot * 512].view(3, ktot, 512), pair_off=pair_off, box_off=box_off)
             return detections, inter
         return detections

@@ -216,7 +216,8 @@ HOIGEN_API int hoigen_set_words(void* dst, const void* host_values, int32_t n_wo
 HOIGEN_API int hoigen_rows_to_bf16(const float* in, int64_t ld_in, int32_t rows, int32_t cols, int32_t normalize,
                                    void* out_bf16, hoigen_stream_t stream);
 HOIGEN_API int hoigen_broadcast_image_logits(const float* img_logits, const int32_t* pair_off, int32_t batch,
-                                             int32_t ktot, int32_t num_classes, float* logits, hoigen_stream_t stream);
+                                             int32_t ktot, int32_t num_classes, int32_t ld_logits, float* logits,
+                                             hoigen_stream_t stream);
 
 typedef struct {                   /* scoring weights, packed once at build time (U:1156-1163, 1112-1115, 1133-1138) */
   int32_t num_classes;             /* C */
@@ -242,7 +243,9 @@ typedef struct {                   /* caller-owned workspace */
   void* g_bf16;                    /* bf16 (B, 512) */
   void* d_bf16;                    /* bf16 (B, 2048) */
   float* img_logits;               /* f32 (B, C) */
-  float* logits;                   /* f32 (Ktot, C)   OUTPUT */
+  float* logits;                   /* f32 (Ktot, ld_logits)   OUTPUT: columns [0, C) of every row */
+  int64_t ld_logits;               /* floats between logits rows, >= C (0 = C).  A multiple of 4 keeps the accumulating
+                                      GEMM epilogues (6 terms summed into this buffer) on their float4 path */
 } hoigen_score_buffers;
 
 /* logits = sum_X scale_X * ((f_X W_X^T + b_X) Y_X)/s_X + scale_T f_U T^T + per-image global/DINO cache terms.
@@ -251,11 +254,28 @@ HOIGEN_API int hoigen_score_pairs(const hoigen_score_weights* w, const hoigen_sc
                                   const float* dino_feats, const int32_t* pair_off, int32_t batch, int32_t ktot,
                                   hoigen_stream_t stream);
 
+/* Opt-in "folded cache" form of hoigen_score_pairs.  The reference's cache affinity is linear (no exp: U:1156-1158), so
+ * ((f W^T + b) Y) s / L = f (W^T Y s / L) + (b Y) s / L : the host contracts every cache with its label matrix ONCE and
+ * the six logit terms of U:1185-1186 become one (C x 1536) matrix for the pair features [H | O | U], one (C x 512) for
+ * the global feature, one (C x 2048) for the DINO feature and a constant row.  Same outputs (tested), no 4096-wide
+ * intermediate.  NOT the default of the Python surface: bench.py's headline runs the unfolded path above. */
+typedef struct {
+  int32_t num_classes;             /* C */
+  const void* pair_w;              /* bf16 (C, 1536)  [E_H | E_O | E_U + s_T W_T],  E_X = s_X/L_X . (Y_X^T W_X) */
+  const void* global_w;            /* bf16 (C, 512)   or NULL */
+  const void* dino_w;              /* bf16 (C, 2048)  or NULL */
+  const float* bias_total;         /* f32 (C)         sum over present branches of s_X/L_X . (b_X Y_X) */
+} hoigen_folded_weights;
+HOIGEN_API int hoigen_score_pairs_folded(const hoigen_folded_weights* w, const hoigen_score_buffers* buf, const float* tokens,
+                                         const float* dino_feats, const int32_t* pair_off, int32_t batch, int32_t ktot,
+                                         hoigen_stream_t stream);
+
 /* compute_prior_scores U:806-833 + postprocessing U:1408-1427, whole batch, reference (row-major) order.
  * table_bits (80, table_words) uint32 bitmask of object_class_to_target_class. Outputs are packed over images:
  * scores/labels/objects [Mtot]; pairing holds, per image b, a contiguous [2][M_b] block at 2*img_off[b];
  * img_off (B+1) int32 triplet offsets. capacity = allocated Mtot; entries beyond it are dropped (check img_off[B]). */
-HOIGEN_API int hoigen_emit_triplets(const float* logits, int32_t num_classes, const float* scores, const int64_t* labels,
+HOIGEN_API int hoigen_emit_triplets(const float* logits, int32_t num_classes, int32_t ld_logits, const float* scores,
+                                    const int64_t* labels,
                                     const int32_t* box_off, const int32_t* pair_off, int32_t batch, int32_t ktot,
                                     const uint32_t* table_bits, int32_t table_words, float hyper_lambda,
                                     int32_t* work_counts, int32_t* work_offsets, float* work_pr, int64_t capacity,
