@@ -212,6 +212,47 @@ def test_launch_ahead_equals_sequential(cuda_device):
         m.finish(stale)                                              # its staging slot has been recycled: loud, not wrong
 
 
+@pytest.mark.parametrize("num_classes,N,n_h,n_o,B", [(24, 4096, 16, 16, 128),     # config 4 at full size: V-COCO, batch 128, 32 boxes/img
+                                                     (117, 16384, 8, 8, 64),     # config 3 at full size: 16k x 512 cache
+                                                     (600, 4096, 8, 8, 512)])    # config 5 at full size: 600 triplets, batch 512/GPU
+def test_full_size_configs_properties(cuda_device, num_classes, N, n_h, n_o, B):
+    """BASELINE.json configs 3-5 at their full sizes, through size-independent properties (the oracle would take
+    minutes): K = n_h (n-1) pairs per image in row-major order, objects = labels[pairing[1]], verbs only from the
+    object's target classes, one triplet per (pair, allowed verb), scores finite in (0,1); and a random sample of 4
+    images re-run as its own small batch gives the same detections (image independence = exact sharding)."""
+    from hoigen_b200 import synthetic as S
+    m, enc, head = _build(num_classes, N, cuda_device, max_instances=16)
+    props = S.make_region_props(B, n_h, n_o, ragged=True)
+    imgs = S.make_images(B, seed=9).to(cuda_device)
+    dino = S.make_dino_features(B, seed=10).to(cuda_device)
+    pd = _props_to(props, cuda_device)
+    dets = m.forward_from_proposals(imgs, pd, dino)
+    assert len(dets) == B
+    table = head.object_class_to_target_class
+    scores = dets.packed.scores
+    assert torch.isfinite(scores).all() and (scores > 0).all() and (scores < 1).all()
+    for b in range(0, B, max(1, B // 16)):
+        d = dets[b]
+        n = props[b]["boxes"].shape[0]
+        nh = int((props[b]["labels"] == 0).sum())
+        pr, lab, obj = d["pairing"].cpu(), d["labels"].cpu(), d["objects"].cpu()
+        pairs = torch.unique_consecutive(pr, dim=1)
+        # every (x, y != x), x < n_h in row-major order — minus the pairs whose object class has no target verb at all
+        lb = props[b]["labels"].tolist()
+        exp = [(x, y) for x in range(nh) for y in range(n) if y != x and len(table[lb[y]]) > 0]
+        assert pairs.t().tolist() == [list(e) for e in exp]
+        assert torch.equal(obj, props[b]["labels"][pr[1]])
+        for o in obj.unique().tolist():
+            assert set(lab[obj == o].tolist()) <= set(table[o])
+        assert d["scores"].numel() == sum(len(set(table[lb[y]])) for _, y in exp)
+    pick = [0, B // 3, B // 2, B - 1]
+    sub = m.forward_from_proposals(imgs[pick], [pd[i] for i in pick], dino[pick])
+    for i, c in zip(pick, sub):
+        a = dets[i]
+        assert torch.equal(a["pairing"], c["pairing"]) and torch.equal(a["labels"], c["labels"]) and torch.equal(a["objects"], c["objects"])
+        assert torch.allclose(a["scores"], c["scores"], rtol=5e-3, atol=0)
+
+
 def test_scoring_stage_given_identical_features(cuda_device):
     """a10 alone: feed the oracle's fp32 features, compare logits. bf16 operands (keys, features) with fp32
     accumulation and an exact fp32 bias carrier: max-abs <= 3e-3."""
