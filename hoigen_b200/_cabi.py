@@ -30,7 +30,7 @@ class GemmParams(C.Structure):
         ("residual", C.c_void_p), ("ld_res", C.c_int32),
         ("out_f32", C.c_void_p), ("ld_f32", C.c_int32),
         ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int32),
-        ("block_n", C.c_int32),
+        ("block_n", C.c_int32), ("split_k", C.c_int32),
     ]
 
 
@@ -208,7 +208,7 @@ def call(name: str, *args) -> None:
 
 
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act=ACT_NONE, residual=None,
-              out_f32=None, out_bf16=None, block_n: int = 0, simt: bool = False) -> None:
+              out_f32=None, out_bf16=None, block_n: int = 0, split_k: int = 0, simt: bool = False) -> None:
     """out = epi(a[M,K] @ w[N,K]^T); see hoigen_gemm_bf16 in include/hoigen_b200.h."""
     lib = init(a.device)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -235,5 +235,6 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act
         assert out_bf16.dtype == torch.bfloat16 and out_bf16.stride(1) == 1 and out_bf16.shape[0] >= M
         p.out_bf16, p.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
     p.block_n = block_n
+    p.split_k = split_k
     fn = lib.hoigen_debug_gemm_simt if simt else lib.hoigen_gemm_bf16
     check(fn(C.byref(p), stream_ptr()), "hoigen_gemm_bf16")

@@ -42,6 +42,7 @@ struct GemmArgs {
   int* sk_flags;    // one flag per slot: 1 = partial published
   int sk_snap;      // unit-range boundaries closer than this to a tile edge snap to it
   int sk_tiles;     // the LAST sk_tiles tiles are split at k-block granularity; the others are dealt out round-robin
+  int split_k;      // one-CTA kernel: every tile's k-range is cut into split_k units (sk_ws slots + sk_flags tile counters)
 };
 
 template <int BN>
@@ -233,6 +234,45 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
   tmem_wait_ld();
 }
 
+// Split-K finisher: the accumulator of a tile is the sum of its n_parts partial slots (fixed order -> bit-reproducible),
+// then the normal epilogue.  Slot layout as written by epilogue_dump_partial: [16-column chunk][128 rows][16 floats].
+template <int COLS, int EPI>
+__device__ __forceinline__ void epilogue_from_parts(const GemmArgs& g, int row, int colbase, const float* s_bias, const float* s_cs,
+                                                    const float* part, int n_parts, size_t part_stride) {
+  const bool row_ok = row < g.M;
+  const bool res_vec = g.residual && row_ok && (g.ld_res & 3) == 0;
+  const float* res_row = g.residual ? g.residual + size_t(row_ok ? row : 0) * g.ld_res : nullptr;
+  if (colbase >= g.N) return;
+#pragma unroll 1
+  for (int c = 0; c < COLS / CW; ++c) {
+    const int col0 = colbase + c * CW;
+    if (col0 >= g.N) break;
+    float acc[CW];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+    const float* pp = part + size_t(c) * (BM * CW);
+    for (int q = 0; q < n_parts; ++q, pp += part_stride) {
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(pp) + j);
+        acc[4 * j] += a.x; acc[4 * j + 1] += a.y; acc[4 * j + 2] += a.z; acc[4 * j + 3] += a.w;
+      }
+    }
+    uint32_t r[CW];
+    float4 res[CW / 4];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) r[j] = __float_as_uint(acc[j]);
+    if (res_vec && col0 + CW <= g.N) {
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) res[j] = *reinterpret_cast<const float4*>(res_row + col0 + 4 * j);
+    }
+    epilogue_process_chunk<EPI>(g, r, res, res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0);
+  }
+}
+
+template <int COLS>
+__device__ __forceinline__ void epilogue_dump_partial(uint32_t t_addr, float* slot);
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
@@ -255,8 +295,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int num_m = (g.M + BM - 1) / BM;
   const int num_n = (g.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
   const int num_k = (g.K + BK - 1) / BK;
+  // work unit = (tile, k-split): unit u -> tile u / S, k-blocks [sp * num_k / S, (sp + 1) * num_k / S)
+  const int S = g.split_k;
+  const int num_tiles = num_m * num_n * S;    // units (== tiles when S == 1)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -285,9 +327,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x) {
+        const int tile = unit / S, sp = unit - tile * S;
         const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = sp * num_k / S; kb < (sp + 1) * num_k / S; ++kb) {
           mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
           const uint32_t a_dst = tiles_addr + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + Cfg::A_BYTES;
@@ -306,13 +349,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x, ++it) {
+        const int sp = unit % S;
+        const int kb0 = sp * num_k / S, kb1 = (sp + 1) * num_k / S;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8u * stage, phase);
           tc_fence_after();
           const uint32_t a_addr = tiles_addr + stage * Cfg::STAGE_BYTES;
@@ -321,7 +366,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_sdesc_sw128(a_addr + k * (UMMA_K * 2));
             const uint64_t bdesc = make_sdesc_sw128(b_addr + k * (UMMA_K * 2));
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(bar_empty + 8u * stage);  // frees this smem stage once the MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -334,30 +379,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;          // 0 / 1: which half of the tile's columns
     int it = 0;
-    if (half == 0 && int(blockIdx.x) < num_tiles)
-      prefetch_residual_row(g, (blockIdx.x / num_n) * BM + quad * 32 + lane, (blockIdx.x % num_n) * BN, BN);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    int* s_last = reinterpret_cast<int*>(tiles + STAGES * Cfg::STAGE_BYTES + 192);   // split-K: "this CTA finishes the tile"
+    constexpr size_t SLOT = size_t(BN) * BM;
+    const size_t slot_off = (size_t(half * (BN / 2) / CW) * BM + size_t(quad * 32 + lane)) * CW;
+    for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x, ++it) {
+      const int tile = unit / S;
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int row = m_blk * BM + quad * 32 + lane;
       const int colbase = n_blk * BN + half * (BN / 2);
-      if (half == 0 && tile + int(gridDim.x) < num_tiles) {
-        const int nt = tile + gridDim.x;
-        prefetch_residual_row(g, (nt / num_n) * BM + quad * 32 + lane, (nt % num_n) * BN, BN);
-      }
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN + half * (BN / 2));
       float* s_bias = reinterpret_cast<float*>(tiles + STAGES * Cfg::STAGE_BYTES + 256) + (it & 1) * 2 * BN;
       float* s_cs = s_bias + BN;
       epilogue_stage_vectors<BN>(g, n_blk * BN, s_bias, s_cs, threadIdx.x - 64);
-      epilogue_warp<BN / 2, -1>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
-        mbar_wait(bar_tfull + 8u * acc, acc_phase);
-        tc_fence_after();
-      });
-      // release the accumulator stage back to the MMA warp
+      if (S == 1) {
+        epilogue_warp<BN / 2, -1>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
+          mbar_wait(bar_tfull + 8u * acc, acc_phase);
+          tc_fence_after();
+        });
+        // release the accumulator stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
+        continue;
+      }
+      // ---- split-K: publish this unit's raw accumulator; whoever arrives last at the tile's counter sums all of the
+      //      tile's slots in split order (so the result does not depend on who that is) and runs the epilogue ----
+      mbar_wait(bar_tfull + 8u * acc, acc_phase);
+      tc_fence_after();
+      epilogue_dump_partial<BN / 2>(t_addr, g.sk_ws + size_t(unit) * SLOT + slot_off);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) *s_last = (atomicAdd(g.sk_flags + tile, 1) == S - 1) ? 1 : 0;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (*s_last) {
+        __threadfence();
+        epilogue_from_parts<BN / 2, -1>(g, row, colbase, s_bias + half * (BN / 2), s_cs + half * (BN / 2),
+                                        g.sk_ws + size_t(tile) * S * SLOT + slot_off, S, SLOT);
+        if (threadIdx.x == 64) g.sk_flags[tile] = 0;      // re-arm for the next launch
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // s_last is rewritten by the next unit
     }
   }
 
@@ -713,7 +778,7 @@ static GemmArgs to_args(const hoigen_gemm_params* p) {
   g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16); g.ld_bf16 = p->ld_bf16;
   static const int dbg = getenv("HOIGEN_GEMM_DEBUG") ? atoi(getenv("HOIGEN_GEMM_DEBUG")) : 0;
   g.debug = dbg;
-  g.sk_ws = nullptr; g.sk_flags = nullptr; g.sk_snap = 0; g.sk_tiles = 0;
+  g.sk_ws = nullptr; g.sk_flags = nullptr; g.sk_snap = 0; g.sk_tiles = 0; g.split_k = 1;
   return g;
 }
 
@@ -723,6 +788,17 @@ static const char* gemm_tag(int N, int K) {
   auto it = tags.find({N, K});
   if (it == tags.end()) it = tags.emplace(std::make_pair(N, K), "gemm_n" + std::to_string(N) + "_k" + std::to_string(K)).first;
   return it->second.c_str();
+}
+
+// Split-K of the one-CTA kernel: a long-K GEMM with few tiles (the M = 64 per-image cache terms: 2 tiles x 64 k-blocks)
+// is bound by ONE SM's TMA service rate (~0.4 us per 24 KiB k-block); cutting every tile's k-range over idle SMs is the
+// only parallelism there is.  Only when all units still fit one wave and every unit keeps >= 8 k-blocks.
+static int auto_split_k(int num_tiles, int num_k) {
+  if (num_k < 32 || num_tiles >= num_sms()) return 1;
+  int s = num_sms() / num_tiles;
+  if (s > num_k / 8) s = num_k / 8;
+  if (s > 8) s = 8;
+  return s < 2 ? 1 : s;
 }
 
 template <int BN>
@@ -739,10 +815,20 @@ static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN);
   if (!tb) return HOIGEN_ERR_CUDA;
   const int num_tiles = ((p->M + BM - 1) / BM) * ((p->N + BN - 1) / BN);
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  const int num_k = (p->K + BK - 1) / BK;
+  GemmArgs args = to_args(p);
+  int S = p->split_k > 0 ? p->split_k : auto_split_k(num_tiles, num_k);
+  if (S > num_k) S = num_k;
+  if (S > 1) {
+    StreamKWorkspace ws = get_streamk_workspace(stream, size_t(num_tiles) * S * BN * BM * sizeof(float), num_tiles);
+    if (!ws.slots) return HOIGEN_ERR_CUDA;
+    args.sk_ws = ws.slots; args.sk_flags = ws.flags; args.split_k = S;
+  }
+  const int units = num_tiles * S;
+  const int grid = units < num_sms() ? units : num_sms();
   KernelScope ks(gemm_tag(p->N, p->K), stream, 2.0 * p->M * p->N * p->K,
                  2.0 * (double(p->M) * p->K + double(p->N) * p->K) + double(p->M) * p->N * ((p->out_f32 ? 4 : 0) + (p->out_bf16 ? 2 : 0) + (p->residual ? 4 : 0)));
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, to_args(p));
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, args);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
@@ -823,8 +909,27 @@ static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream, bool f
 
 // Pick (cta pair?, BN): fewest (possibly fractional, see stream-K) scheduling rounds x relative tile time. The one-CTA kernel is L2-operand-bound
 // (~87 FLOP per L2 byte at BN = 256) so its tiles are charged 1.35x.
+static int auto_split_k(int num_tiles, int num_k);
 static void choose_config(int M, int N, int K, int* pair, int* bn) {
   const int sms = num_sms();
+  const int nk = (K + BK - 1) / BK;
+  if (nk >= 32 && N <= 128 && ((M + BM - 1) / BM) * ((N + 63) / 64) <= sms / 2) {
+    // long K, skinny N, few tiles (measured: M = 64 x N = 117 x K = 4096 runs 25 -> 19 us with the split; with 120 tiles
+    // the unsplit BN = 64 schedule below stays the best): compare bytes per CTA chain,
+    // rounds x k-blocks per unit x (A 16 KiB + W tile), with the k-split the launcher will pick
+    double best = 1e30;
+    const int cand[2] = {64, 128};
+    for (int i = 0; i < 2; ++i) {
+      const int b = cand[i];
+      if (b > 64 && N <= b / 2) continue;
+      const int tiles = ((M + BM - 1) / BM) * ((N + b - 1) / b);
+      const int S = auto_split_k(tiles, nk);
+      const int rounds = (tiles * S + sms - 1) / sms;
+      const double cost = double(rounds) * (double(nk) / S) * (16384.0 + b * 128.0) + (S > 1 ? 40000.0 : 0.0);
+      if (cost < best) { best = cost; *pair = 0; *bn = b; }
+    }
+    return;
+  }
   double best = 1e30;
   *pair = 0; *bn = 256;
   const int c1[3] = {256, 128, 64};

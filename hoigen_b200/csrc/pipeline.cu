@@ -15,6 +15,7 @@ static int gemm(const void* a, int lda, const void* w, int ldw, int M, int N, in
   p.residual = residual; p.ld_res = ld_res;
   p.out_f32 = out_f32; p.ld_f32 = ld_f32;
   p.out_bf16 = out_bf16; p.ld_bf16 = ld_bf16;
+  p.split_k = 0;
   p.block_n = 0;
   return hoigen_gemm_bf16(&p, s);
 }

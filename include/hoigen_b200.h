@@ -78,6 +78,8 @@ typedef struct {
   int32_t block_n;       /* 0 = choose; 64/128/256 = one-CTA tiles 128xBN; 2128/2192/2256 = CTA-pair tiles 256xBN;
                             +10000 (tests) = split leftover tiles across SM pairs by k-blocks even when K is short
                             (by default only K >= 2048 is split, where it pays) */
+  int32_t split_k;       /* one-CTA tiles only: 0 = choose, n >= 1 = cut every tile's k-range into n units that run on
+                            different SMs; partials meet in a workspace and are summed in split order (deterministic) */
 } hoigen_gemm_params;
 
 HOIGEN_API int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream);

@@ -116,6 +116,30 @@ def test_gemm_stream_k_split(cuda_device, M, N, K, bn):
         assert torch.equal(ob, ob2)
 
 
+@pytest.mark.parametrize("M,N,K,bn,split", [(64, 117, 4096, 0, 0), (300, 117, 4096, 64, 4), (7680, 117, 4096, 0, 0),
+                                            (64, 4096, 2048, 0, 0), (200, 200, 2048, 128, 3), (130, 64, 1024, 64, 2)])
+def test_gemm_split_k_one_cta(cuda_device, M, N, K, bn, split):
+    """One-CTA kernel with every tile's k-range cut over several SMs (long K, few tiles: the per-image cache terms).
+    Partials are summed in split order by whichever CTA arrives last: results must not depend on the arrival order."""
+    from hoigen_b200 import _cabi
+    g = torch.Generator(device="cpu").manual_seed(M + N + K + split)
+    a = torch.randn(M, K, generator=g).bfloat16().to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16().to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    cs = (torch.rand(N, generator=g) + 0.5).to(cuda_device)
+    ld = (N + 3) // 4 * 4
+    res = torch.randn(M, ld, generator=g).to(cuda_device)
+    ref = _ref_gemm(a, w, bias, 0, cs, res[:, :N])
+    outs = []
+    for _ in range(4):
+        of = res.clone()
+        _cabi.gemm_bf16(a, w, bias=bias, colscale=cs, residual=of[:, :N], out_f32=of[:, :N], block_n=bn, split_k=split)
+        outs.append(of)
+    assert (outs[0][:, :N] - ref).abs().max().item() < 2e-4 * max(1.0, math.sqrt(K / 64))
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    assert torch.equal(outs[0][:, N:], res[:, N:])
+
+
 def test_gemm_rejects_bad_arguments(cuda_device):
     from hoigen_b200 import _cabi
     a = torch.zeros(16, 20, device=cuda_device, dtype=torch.bfloat16)   # lda = 20 is not a multiple of 8
