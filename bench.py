@@ -49,6 +49,8 @@ def workload_config(args, world):
         "l2": f"inputs rotate over {args.rotate} distinct batches ({args.rotate * args.batch * 3 * 224 * 224 * 4 / 1e6:.0f} MB "
               "> 126 MB L2); weights + activations per step >> L2",
         "dino_features": "supplied as input (SURVEY.md 8 row a8: stock ResNet-50 is outside the path)",
+        "batches_in_flight": (f"{getattr(args, 'streams', 1)} (consecutive steps alternate over {getattr(args, 'streams', 1)} CUDA streams and "
+                              "overlap on the GPU; kernel_breakdown / roofline are single-stream per-launch times)"),
         "collective": ("none (single GPU)" if world == 1 else
                        ("one NCCL all-gather of the sweep's accumulated detections, inside each timed region"
                         if getattr(args, "gather_every", 0) == 0 else "one NCCL all-gather of the step's detections per step")),
@@ -224,9 +226,14 @@ def run_b200(args, rank, world, local_rank):
     dev_props = [[dict({k: v.to(dev) for k, v in p.items()}, n_human=BOXES_H) for p in ps] for ps in host_props]
     dev_dino = [t.to(dev) for t in host_dino]
 
+    # consecutive steps alternate over `--streams` CUDA streams: the latency-bound head / prologue kernels of one batch
+    # then overlap the GEMMs of the next instead of leaving most SMs idle
+    streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else [torch.cuda.current_stream(dev)]
+
     def launch_resident(i):
         r = i % R
-        return model.launch_from_proposals(dev_imgs[r], dev_props[r], dev_dino[r])
+        with torch.cuda.stream(streams[i % len(streams)]):
+            return model.launch_from_proposals(dev_imgs[r], dev_props[r], dev_dino[r])
 
     def finish_resident(pend):
         dets = model.finish(pend)          # the path's device->host read (triplet offsets) + detection views
@@ -331,9 +338,10 @@ def run_b200(args, rank, world, local_rank):
 
     def launch_host(i):
         slot = dev_in[i % NSLOT]
-        torch.cuda.current_stream().wait_event(slot["ev"])
-        pend = model.launch_packed(slot["imgs"], slot["boxes"], slot["scores"], slot["labels"], [n_per] * B, [BOXES_H] * B,
-                                   slot["dino"])
+        with torch.cuda.stream(streams[i % len(streams)]):
+            torch.cuda.current_stream().wait_event(slot["ev"])
+            pend = model.launch_packed(slot["imgs"], slot["boxes"], slot["scores"], slot["labels"], [n_per] * B, [BOXES_H] * B,
+                                       slot["dino"])
         slot["free"] = pend.done
         return pend
 
@@ -409,7 +417,11 @@ def run_b200(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.active = True
     e0.record()
+    for st in streams:
+        st.wait_event(e0)
     dets = run_resident(args.warmup, args.steps)
+    for st in streams:
+        torch.cuda.current_stream().wait_stream(st)
     e1.record()
     barrier()
     clocks.active = False
@@ -467,7 +479,11 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
+        for st in streams:
+            st.wait_event(f0)
         run_resident(3, args.steps)
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
         f1.record()
         torch.cuda.synchronize()
         fms = f0.elapsed_time(f1) / args.steps
@@ -559,6 +575,9 @@ def main():
     ap.add_argument("--cache-rows", type=int, default=4096)
     ap.add_argument("--rotate", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="CUDA streams that consecutive steps alternate over: 2 (default) = two batches overlap on the GPU, "
+                         "1 = strictly one batch at a time")
     ap.add_argument("--gather-every", type=int, default=0,
                     help="N>1 only. 0 (default): detections accumulate on the device and are exchanged with ONE all-gather per "
                          "sweep (= per timed region, inside it); 1: one non-blocking fixed-capacity all-gather per step")

@@ -371,10 +371,12 @@ class UPT(nn.Module):
         return slot
 
     def _buf(self, name: str, numel: int, dtype: torch.dtype, device) -> torch.Tensor:
-        t = self._ws.get(name)
+        # per CUDA stream: forwards launched on different streams may overlap on the GPU and must not share scratch
+        key = (name, torch.cuda.current_stream(device).cuda_stream) if device.type == "cuda" else name
+        t = self._ws.get(key)
         if t is None or t.numel() < numel or t.dtype != dtype or t.device != device:
             t = torch.empty(max(numel, 1), device=device, dtype=dtype)
-            self._ws[name] = t
+            self._ws[key] = t
         return t
 
     @torch.no_grad()

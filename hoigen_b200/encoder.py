@@ -177,7 +177,8 @@ class VisionTransformer(nn.Module):
         return p
 
     def _workspace(self, batch: int, n_max: int):
-        key = (batch, n_max)
+        # one workspace per (shape, CUDA stream): forwards launched on different streams may overlap on the GPU
+        key = (batch, n_max, torch.cuda.current_stream(self.proj.device).cuda_stream)
         if key not in self._ws_cache:
             dev = self.proj.device
             M = batch * TOKENS
@@ -193,7 +194,7 @@ class VisionTransformer(nn.Module):
             s = _cabi.EncoderBuffers()
             for k, v in b.items():
                 setattr(s, k, v.data_ptr())
-            if len(self._ws_cache) > 4:
+            if len(self._ws_cache) > 6:
                 self._ws_cache.clear()
             self._ws_cache[key] = (b, s)
         return self._ws_cache[key]

@@ -253,6 +253,33 @@ def test_full_size_configs_properties(cuda_device, num_classes, N, n_h, n_o, B):
         assert torch.allclose(a["scores"], c["scores"], rtol=5e-3, atol=0)
 
 
+def test_concurrent_streams_equal_sequential(cuda_device):
+    """Forwards launched on different CUDA streams overlap on the GPU (bench.py --streams 2): every scratch buffer is
+    per stream, so the detections are bit-identical to running the same batches one after the other."""
+    from hoigen_b200 import synthetic as S
+    m, enc, head = _build(117, 4096, cuda_device)
+    batches = []
+    for r in range(6):
+        B = 24 + 8 * (r % 3)
+        props = _props_to(S.make_region_props(B, 8, 8, ragged=(r % 2 == 1), seed=300 + r), cuda_device)
+        batches.append((S.make_images(B, seed=310 + r).to(cuda_device), props, S.make_dino_features(B, seed=320 + r).to(cuda_device)))
+    ref = [m.forward_from_proposals(*b) for b in batches]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=cuda_device) for _ in range(3)]
+    for rep in range(2):                                   # second repetition: every stream's workspace already exists
+        pend = []
+        for i, b in enumerate(batches):
+            st = streams[i % 3]
+            st.wait_stream(torch.cuda.current_stream(cuda_device))
+            with torch.cuda.stream(st):
+                pend.append(m.launch_from_proposals(*b))
+        got = [m.finish(p) for p in pend]
+        for a, c in zip(ref, got):
+            assert a.packed.triplet_off == c.packed.triplet_off
+            for f in ("scores", "labels", "objects", "pairing"):
+                assert torch.equal(getattr(a.packed, f), getattr(c.packed, f)), (rep, f)
+
+
 def test_scoring_stage_given_identical_features(cuda_device):
     """a10 alone: feed the oracle's fp32 features, compare logits. bf16 operands (keys, features) with fp32
     accumulation and an exact fp32 bias carrier: max-abs <= 3e-3."""
