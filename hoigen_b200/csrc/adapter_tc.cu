@@ -1,20 +1,26 @@
-// InsAdapter bottleneck body on the tensor cores: one CTA per 128-token tile, two threads per token row
-// (one per attention head / column half).
+// The whole InsAdapter block (Adapter.forward, CLIP_models_adapter_prior2.py:183-203) on the tensor cores: one CTA per
+// row tile of the token stream (<= 128 rows, sized so that ONE wave covers all SMs), two threads per token row (one per
+// attention head / column half).
 //
 //   D = relu((xb + delta_c) Wd^T + bd)       12 or 24 x UMMA 128x64x64 fed by a 6-stage TMA ring: the down-projection
 //                                            with the pending residual of the previous block's MLP output folded in by
 //                                            linearity (xb Wd^T + delta_c Wd^T), no thread touches the operands
 //   q  = D Wq^T + bq                         UMMA 128x64x64
-//   a  = softmax_2heads(q K^T / sqrt(32)) V  registers; K/V (<= 32 unmasked prior tokens of the tile's <= 2 images) in smem
-//   t  = LN_norm2(D + a Wo^T + bo)           UMMA 128x64x64   + per-thread LayerNorm over 64 registers
+//   S  = q Kbd^T ; P = softmax_2heads(S)     UMMA 128x64x64 against a block-diagonal bf16 key tile (both heads at once,
+//   a  = P Vbd                               <= 32 unmasked prior tokens of each of the tile's <= 2 images), softmax over
+//                                            32 registers, UMMA 128x64x64 against the block-diagonal value tile (MN-major)
+//   t  = LN_norm2(D + a Wo^T + bo)           UMMA 128x64x64   + LayerNorm over 64 values held by two threads
 //   h  = relu(t W1^T + b1)                   UMMA 128x128x64
-//   o  = LN_norm3(t + h W2^T + b2)           UMMA 128x64x128  -> bf16 (M,64), the A operand of the up-proj GEMM
+//   o  = LN_norm3(t + h W2^T + b2)           UMMA 128x64x128
+//   delta_out = o (scale . Wup)^T            3 x UMMA 128x256x64 through two TMEM buffers -> bf16 -> four 16 KiB staging
+//                                            panels -> TMA stores (the bias row scale . b_up is added by the LayerNorm
+//                                            pass that applies delta_out to the stream)
 //
-// Accumulators live in TMEM (128 columns); between the four MMAs the activations make a register round trip
-// (tcgen05.ld -> fp32 math -> bf16 -> 128B-swizzled smem A tile). Row-per-thread ownership makes both LayerNorms and
-// the cross-attention shuffle-free.
+// Accumulators live in TMEM (512 columns); between the MMAs the activations make a register round trip
+// (tcgen05.ld -> fp32 math -> bf16 -> 128B-swizzled smem A tile).  All small fp32 vectors are staged in smem once.
+// hoigen_debug_adapter_trace records CTA 0's phase timestamps (see DESIGN.md for the numbers that shaped this kernel).
 //
-// Reference: Adapter.forward CLIP_models_adapter_prior2.py:186-200 with TransformerDecoderLayer.forward_post :51-72
+// Reference: Adapter.forward CLIP_models_adapter_prior2.py:183-203 with TransformerDecoderLayer.forward_post :51-72
 // (multihead_attn with key_padding_mask, norm2, linear1/relu/linear2, norm3; dropout off in eval).
 #include "common.h"
 #include "ptx.cuh"

@@ -4,8 +4,11 @@
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0    : TMA producer   (A tile 128x64, W tile BNx64, 128B swizzle, STAGES-deep mbarrier ring)
 //   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accum in TMEM)
-//   warps 2-9 : epilogue       (tcgen05.ld 32 lanes x 32 columns -> registers -> global; residual prefetched)
-// Two TMEM accumulator stages (2*BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//   warps 2-9 : epilogue       (tcgen05.ld 32 lanes x 16 columns -> registers -> global / smem staging + TMA store)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// Two kernels: gemm_bf16_kernel (one CTA per 128 x BN tile, optional deterministic split-K for long-K / few-tile shapes)
+// and gemm2_bf16_kernel (a cluster of two CTAs per 256 x BN tile, cta_group::2, stream-K split of the leftover tiles);
+// choose_config picks per call.
 //
 // Replaces the cuBLAS SGEMMs the reference dispatches from CLIP_models_adapter_prior2.py:443-445 (in/out
 // proj), :428-432 (c_fc/c_proj), :184/:201 (adapter down/up), :491 (conv1 as GEMM), :505 (@ proj) and
