@@ -785,11 +785,13 @@ static GemmArgs to_args(const hoigen_gemm_params* p) {
   return g;
 }
 
-// interned "gemm_n<N>_k<K>" tags for the launch profiler
-static const char* gemm_tag(int N, int K) {
-  static std::map<std::pair<int, int>, std::string> tags;
-  auto it = tags.find({N, K});
-  if (it == tags.end()) it = tags.emplace(std::make_pair(N, K), "gemm_n" + std::to_string(N) + "_k" + std::to_string(K)).first;
+// interned "gemm<1|2>_n<N>_k<K>" tags for the launch profiler (1 = one-CTA kernel, 2 = CTA-pair kernel)
+static const char* gemm_tag(int N, int K, int kind = 1) {
+  static std::map<std::pair<std::pair<int, int>, int>, std::string> tags;
+  const auto key = std::make_pair(std::make_pair(N, K), kind);
+  auto it = tags.find(key);
+  if (it == tags.end())
+    it = tags.emplace(key, "gemm" + std::to_string(kind) + "_n" + std::to_string(N) + "_k" + std::to_string(K)).first;
   return it->second.c_str();
 }
 
@@ -888,7 +890,7 @@ static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream, b
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  KernelScope ks(gemm_tag(p->N, p->K), stream, 2.0 * p->M * p->N * p->K,
+  KernelScope ks(gemm_tag(p->N, p->K, 2), stream, 2.0 * p->M * p->N * p->K,
                  2.0 * (double(p->M) * p->K + double(p->N) * p->K) + double(p->M) * p->N * ((p->out_f32 ? 4 : 0) + (p->out_bf16 ? 2 : 0) + (p->residual ? 4 : 0)));
   HOIGEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, TMA_OUT, EPI>, *ta, *tb, *tc, args));
   HOIGEN_CHECK_LAUNCH();
