@@ -246,32 +246,13 @@ def run_b200(args, rank, world, local_rank):
     gather_cap = B * 120 * 30 * 36 + B * (BOXES_H + BOXES_O) * 16
     pending_gather = []
 
-    gather_ev = []
-    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-
     sweep = []
 
     def exchange(packed):
-        if os.environ.get("HOIGEN_BENCH_NO_GATHER"):    # diagnostics only: the floor without any collective
-            return
         if args.gather_every == 0:         # default: accumulate on the device, ONE exchange per sweep (= timed region)
             sweep.append(packed)
             return
-        if os.environ.get("HOIGEN_BENCH_TRACE"):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            pending_gather.append(gather_packed_begin(packed, gather_cap, B))
-            e1.record()
-            gather_ev.append((e0, e1))
-            if len(gather_ev) == 12:
-                torch.cuda.synchronize()
-                print("[trace] exchange on-stream ms: " + " ".join(f"{a.elapsed_time(c):.3f}" for a, c in gather_ev), file=sys.stderr, flush=True)
-        elif os.environ.get("HOIGEN_BENCH_GATHER_SIDE"):
-            gather_stream.wait_event(packed.done)
-            with torch.cuda.stream(gather_stream):
-                pending_gather.append(gather_packed_begin(packed, gather_cap, B))
-        else:
-            pending_gather.append(gather_packed_begin(packed, gather_cap, B))
+        pending_gather.append(gather_packed_begin(packed, gather_cap, B))
         if len(pending_gather) > 1:
             gather_packed_end(pending_gather.pop(0))
 
@@ -323,8 +304,6 @@ def run_b200(args, rank, world, local_rank):
 
     def upload(i):
         r, slot = i % R, dev_in[i % NSLOT]
-        if os.environ.get("HOIGEN_BENCH_NO_UPLOAD") and i >= NSLOT:     # diagnostics: how much does the concurrent H2D cost?
-            return slot
         with torch.cuda.stream(copy_stream):
             if slot["free"] is not None:
                 copy_stream.wait_event(slot["free"])     # the forward that last read this slot has finished
