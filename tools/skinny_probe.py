@@ -1,3 +1,4 @@
+"""Long-K / small-N GEMM shapes of the scoring head under every tile configuration (cold L2 and hot) — DESIGN.md 4."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
