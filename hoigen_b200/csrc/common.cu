@@ -5,6 +5,7 @@
 
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 namespace hoigen {
 
@@ -71,6 +72,16 @@ static const CUtensorMap* get_tmap(int rank, const void* ptr, const uint64_t* di
   std::lock_guard<std::mutex> lock(g_tmap_mu);
   auto it = g_tmaps.find(key);
   if (it != g_tmaps.end()) return it->second;
+  // Bound the cache for callers that keep passing fresh buffers: retire a full generation, free it one generation later
+  // (descriptors are copied into kernel parameters at launch, and no single call creates thousands of them, so a
+  // pointer handed out earlier in the same C-ABI call stays valid).
+  static std::vector<CUtensorMap*> retired;
+  if (g_tmaps.size() >= 8192) {
+    for (CUtensorMap* old : retired) free(old);
+    retired.clear();
+    for (auto& kv : g_tmaps) retired.push_back(kv.second);
+    g_tmaps.clear();
+  }
   CUtensorMap* m = nullptr;
   if (posix_memalign(reinterpret_cast<void**>(&m), 64, sizeof(CUtensorMap)) != 0) {
     set_error("posix_memalign failed");
