@@ -253,6 +253,34 @@ def test_full_size_configs_properties(cuda_device, num_classes, N, n_h, n_o, B):
         assert torch.allclose(a["scores"], c["scores"], rtol=5e-3, atol=0)
 
 
+def test_images_without_pairs_inside_a_batch(cuda_device):
+    """U:998-1004: an image with no human, or with a single box, contributes no pairs — it still gets a (empty)
+    detection entry and must not disturb its neighbours (CSR offsets with zero-length segments, n = 1 prior token)."""
+    from hoigen_b200 import synthetic as S
+    from oracle import hoi_forward_ref as O
+    m, enc, head = _build(117, 256, cuda_device)
+    props = S.make_region_props(4, 5, 4, ragged=True, seed=70)
+    props[1]["labels"] = props[1]["labels"].clone()
+    props[1]["labels"][:] = 17                                   # no human at all
+    props[2] = {k: (v[:1].clone() if torch.is_tensor(v) else v) for k, v in props[2].items()}   # one (human) box
+    imgs = S.make_images(4, seed=71)
+    dino = S.make_dino_features(4, seed=72)
+    o_dets, o_int = O.hoi_forward(imgs, props, dino, enc, head, return_intermediates=True)
+    dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                           return_intermediates=True)
+    assert len(dets) == 4
+    for b in (1, 2):
+        assert dets[b]["scores"].numel() == 0 and dets[b]["pairing"].shape == (2, 0) and dets[b]["labels"].numel() == 0
+        assert dets[b]["boxes"].shape[0] == props[b]["boxes"].shape[0]
+    assert len(o_int["logits"]) == 2                             # the reference keeps no logits entry for skipped images
+    for j, b in enumerate((0, 3)):
+        for k in ("pairing", "labels", "objects"):
+            assert torch.equal(dets[b][k].cpu(), o_dets[b][k]), (b, k)
+        assert (inter["logits"][b].cpu() - o_int["logits"][j]).abs().max().item() <= LOGIT_TOL
+        rel = ((dets[b]["scores"].cpu() - o_dets[b]["scores"]).abs() / o_dets[b]["scores"].abs().clamp_min(1e-30)).max().item()
+        assert rel <= SCORE_RTOL, rel
+
+
 def test_concurrent_streams_equal_sequential(cuda_device):
     """Forwards launched on different CUDA streams overlap on the GPU (bench.py --streams 2): every scratch buffer is
     per stream, so the detections are bit-identical to running the same batches one after the other."""
