@@ -281,6 +281,24 @@ def test_images_without_pairs_inside_a_batch(cuda_device):
         assert rel <= SCORE_RTOL, rel
 
 
+def test_no_pair_anywhere_returns_none(cuda_device):
+    """U:1660-1662: when no image of the batch yields a pair the reference's forward returns None; so does this one
+    (and launch / finish agree), and too many boxes per image are refused loudly."""
+    from hoigen_b200 import synthetic as S
+    m, enc, head = _build(117, 256, cuda_device)
+    props = S.make_region_props(2, 3, 3, seed=80)
+    for p in props:
+        p["labels"] = torch.full_like(p["labels"], 9)            # objects only
+    imgs = S.make_images(2, seed=81).to(cuda_device)
+    dino = S.make_dino_features(2, seed=82).to(cuda_device)
+    pd = _props_to(props, cuda_device)
+    assert m.forward_from_proposals(imgs, pd, dino) is None
+    assert m.finish(m.launch_from_proposals(imgs, pd, dino)) is None
+    big = _props_to(S.make_region_props(1, 20, 20, seed=83), cuda_device)
+    with pytest.raises(ValueError):
+        m.forward_from_proposals(imgs[:1], big, dino[:1])
+
+
 def test_concurrent_streams_equal_sequential(cuda_device):
     """Forwards launched on different CUDA streams overlap on the GPU (bench.py --streams 2): every scratch buffer is
     per stream, so the detections are bit-identical to running the same batches one after the other."""
