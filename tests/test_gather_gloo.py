@@ -100,6 +100,22 @@ def test_gather_packed_world2_gloo():
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def test_merge_packed_preserves_every_image():
+    """A sweep's batches merged into one record (what is exchanged once per sweep): per-image views are unchanged."""
+    from hoigen_b200.gather import merge_packed
+    dets_a, pa = _fake_packed(0, 3)
+    dets_b, pb = _fake_packed(1, 4)
+    dets_c, pc = _fake_packed(2, 1)
+    merged = merge_packed([pa, None, pb, pc])
+    assert merged.num_images == 8
+    for b, e in enumerate(dets_a + dets_b + dets_c):
+        a = merged.image(b)
+        for k in ("boxes", "pairing", "scores", "labels", "objects"):
+            assert torch.equal(a[k], e[k]) and a[k].dtype == e[k].dtype, (b, k)
+    with pytest.raises(ValueError):
+        merge_packed([None])
+
+
 def test_shard_range_partitions():
     for total in (0, 1, 7, 512, 4097):
         for world in (1, 2, 8):
