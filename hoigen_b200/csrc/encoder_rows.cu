@@ -80,7 +80,7 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
   } else {
     const float4* src = reinterpret_cast<const float4*>(in + long(row) * WIDTH);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) v[j] = src[lane + 32 * j];
+    for (int j = 0; j < 6; ++j) v[j] = __ldcs(src + lane + 32 * j);   // streamed: the fp32 stream is not re-read before ~100 MB of other traffic
     if (delta) {
       const uint2* dsrc = reinterpret_cast<const uint2*>(delta + long(row) * WIDTH);
 #pragma unroll
@@ -107,7 +107,7 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
       }
       float4* dst = reinterpret_cast<float4*>(stream_out + long(row) * WIDTH);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) dst[lane + 32 * j] = v[j];
+      for (int j = 0; j < 6; ++j) __stcs(dst + lane + 32 * j, v[j]);   // evict-first: keep L2 for h / delta / qkv, which ARE re-read
       if (stream_bf16) {   // bf16 copy of the updated stream: the next adapter block's tensor-core operand
         uint2* dstb = reinterpret_cast<uint2*>(stream_bf16 + long(row) * WIDTH);
 #pragma unroll
