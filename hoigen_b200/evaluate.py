@@ -1,0 +1,131 @@
+"""Batched evaluation-side association: the consumer of the detections.
+
+The reference's `CustomisedDLE.test_hico` (utils_tip_cache_and_union_finetune.py:348-411) copies every image's
+detections to the host and loops in Python over images and HOI classes, calling `BoxPairAssociation`
+(pocket/pocket/utils/association.py:51-125) for each.  `HOIAssociator` does the same for a whole batch with ONE
+kernel launch on the packed detections the forward already produced (`DetectionList.packed`), and returns per image
+exactly what the reference hands to `DetectionAPMeter.append(scores, interactions, labels)`.
+
+    assoc = HOIAssociator(dataset.object_n_verb_to_interaction)         # once
+    dets = upt.forward_from_proposals(...)                              # or upt(images)
+    for scores, interactions, labels in assoc(dets, targets):           # targets: the reference's dicts
+        meter.append(scores, interactions, labels)
+
+No CPU fallback: CUDA tensors only (the compute is `hoigen_associate_pairs`).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+
+MAX_GT_PER_IMAGE = 1024
+
+
+def recover_boxes(boxes: torch.Tensor, size: torch.Tensor) -> torch.Tensor:
+    """UPT.recover_boxes (upt_tip_cache_model_free_finetune_distill3.py:1269-1274): normalised cxcywh -> xyxy pixels."""
+    cx, cy, w, h = boxes.unbind(-1)
+    xyxy = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+    ih, iw = size
+    return xyxy * torch.stack([iw, ih, iw, ih]).to(xyxy.dtype)
+
+
+class HOIAssociator:
+    """`conversion[objects, verbs]` + per-class `BoxPairAssociation(min_iou)` of the reference, batched on the GPU.
+
+    object_n_verb_to_interaction: the dataset's 80 x num_verbs table (None / -1 = not an HOI class), or None when the
+    detector's classes already are HOI ids (the reference's `else: interactions = verbs` branch, T:389-390)."""
+
+    def __init__(self, object_n_verb_to_interaction: Optional[Sequence[Sequence[Optional[int]]]], min_iou: float = 0.5,
+                 return_float_interactions: bool = True):
+        self.min_iou = float(min_iou)
+        self.return_float = return_float_interactions
+        if object_n_verb_to_interaction is None:
+            self._table_host, self.num_verbs = None, 1
+        else:
+            rows = [[-1 if (v is None or v < 0) else int(v) for v in row] for row in object_n_verb_to_interaction]
+            if len(rows) != 80:
+                raise ValueError(f"object_n_verb_to_interaction must have 80 rows (got {len(rows)})")
+            self._table_host = torch.tensor(rows, dtype=torch.int32)
+            self.num_verbs = self._table_host.shape[1]
+        self._table_dev = {}
+
+    def _table(self, dev):
+        if self._table_host is None:
+            return None
+        t = self._table_dev.get(dev)
+        if t is None:
+            t = self._table_dev[dev] = self._table_host.to(dev).contiguous()
+        return t
+
+    @torch.no_grad()
+    def __call__(self, detections, targets: Sequence[dict]) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        """detections: the DetectionList of a forward (its `.packed` record is used as is) or a List[dict] in the
+        reference's format; targets: per image {boxes_h, boxes_o (G,4) normalised cxcywh, hoi (G,), size (2,) = (h, w)}.
+        Returns per image (scores, interactions, labels); interactions are float with NaN for invalid combinations when
+        `return_float_interactions` (the reference's dtype), else int64 with -1."""
+        packed = getattr(detections, "packed", None)
+        if packed is None:
+            packed = _pack(detections)
+        dev = packed.scores.device
+        if dev.type != "cuda":
+            raise _cabi.HoigenError("HOIAssociator needs CUDA tensors (there is no CPU fallback)")
+        _cabi.init(dev)
+        B = packed.num_images
+        if len(targets) != B:
+            raise ValueError(f"{B} images of detections, {len(targets)} targets")
+        # ground truth -> detection frame, CSR over images (tiny torch ops on the device)
+        gh, go, hoi, goff = [], [], [], [0]
+        for t in targets:
+            size = t["size"].to(dev, torch.float32)
+            gh.append(recover_boxes(t["boxes_h"].to(dev, torch.float32).view(-1, 4), size))
+            go.append(recover_boxes(t["boxes_o"].to(dev, torch.float32).view(-1, 4), size))
+            hoi.append(t["hoi"].to(dev, torch.int64).view(-1))
+            goff.append(goff[-1] + int(hoi[-1].numel()))
+        max_gt = max(b - a for a, b in zip(goff[:-1], goff[1:])) if B else 0
+        if max_gt > MAX_GT_PER_IMAGE:
+            raise ValueError(f"at most {MAX_GT_PER_IMAGE} ground-truth pairs per image (got {max_gt})")
+        gt_h = torch.cat(gh).contiguous() if goff[-1] else torch.zeros(1, 4, device=dev)
+        gt_o = torch.cat(go).contiguous() if goff[-1] else torch.zeros(1, 4, device=dev)
+        gt_hoi = torch.cat(hoi).contiguous() if goff[-1] else torch.zeros(1, dtype=torch.int64, device=dev)
+        offs = torch.tensor(packed.box_off + packed.triplet_off + goff, dtype=torch.int32)
+        d_offs = torch.empty_like(offs, device=dev)
+        _cabi.call("hoigen_set_words", d_offs.data_ptr(), offs.data_ptr(), offs.numel())
+        d_box_off, d_trip_off, d_gt_off = d_offs[: B + 1], d_offs[B + 1: 2 * B + 2], d_offs[2 * B + 2:]
+        mtot = int(packed.scores.numel())
+        interactions = torch.empty(max(mtot, 1), dtype=torch.int64, device=dev)
+        labels = torch.empty(max(mtot, 1), dtype=torch.float32, device=dev)
+        table = self._table(dev)
+        boxes = packed.boxes.float().contiguous()
+        if mtot:
+            _cabi.call("hoigen_associate_pairs", boxes.data_ptr(), d_box_off.data_ptr(), packed.pairing.data_ptr(),
+                       packed.objects.data_ptr(), packed.labels.data_ptr(), packed.scores.data_ptr(), d_trip_off.data_ptr(),
+                       table.data_ptr() if table is not None else None, self.num_verbs, gt_h.data_ptr(), gt_o.data_ptr(),
+                       gt_hoi.data_ptr(), d_gt_off.data_ptr(), max_gt, B, self.min_iou, interactions.data_ptr(),
+                       labels.data_ptr())
+        inter = interactions[:mtot]
+        if self.return_float:
+            inter = torch.where(inter < 0, torch.full((), float("nan"), device=dev, dtype=torch.float64), inter.double())
+        sizes = [b - a for a, b in zip(packed.triplet_off[:-1], packed.triplet_off[1:])]
+        return list(zip(packed.scores.split(sizes), inter.split(sizes), labels[:mtot].split(sizes)))
+
+
+def _pack(dets: Sequence[Optional[dict]]):
+    """List[dict] in the reference's format -> PackedDetections (images without detections get zero-length segments)."""
+    from .detector import PackedDetections
+    dev = next(d["scores"].device for d in dets if d is not None)
+    toff, boff = [0], [0]
+    sc, lb, ob, pr, bx = [], [], [], [], []
+    for d in dets:
+        m = 0 if d is None else int(d["scores"].numel())
+        n = 0 if d is None else int(d["boxes"].shape[0])
+        toff.append(toff[-1] + m)
+        boff.append(boff[-1] + n)
+        if d is not None:
+            sc.append(d["scores"].float()); lb.append(d["labels"].to(torch.int64)); ob.append(d["objects"].to(torch.int64))
+            pr.append(d["pairing"].to(torch.int64).reshape(-1)); bx.append(d["boxes"].float().view(-1, 4))
+    cat = lambda ts, dt, shape=(0,): torch.cat(ts) if ts else torch.zeros(shape, dtype=dt, device=dev)
+    return PackedDetections(cat(sc, torch.float32), cat(lb, torch.int64), cat(ob, torch.int64), cat(pr, torch.int64),
+                            cat(bx, torch.float32, (0, 4)), toff, boff, (0, 0))

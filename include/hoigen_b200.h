@@ -284,6 +284,25 @@ HOIGEN_API int hoigen_emit_triplets(const float* logits, int32_t num_classes, in
                                     float* out_scores, int64_t* out_labels, int64_t* out_objects, int64_t* out_pairing,
                                     int32_t* img_off, hoigen_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * f1 (the path's immediate consumer): batched detection <-> ground-truth association of the eval caller,
+ * CustomisedDLE.test_hico utils_tip_cache_and_union_finetune.py:375-407 + BoxPairAssociation
+ * pocket/pocket/utils/association.py:51-125, for all images of a batch in one launch.
+ *   interactions[d] = conversion[objects[d]][verbs[d]] (-1 where the table has none; = verbs[d] if conversion is NULL)
+ *   labels[d] = 1 iff d is the highest-scoring detection (first on ties) among those whose best-overlapping
+ *               ground-truth pair of the same HOI id (first on ties) is g, with pair IoU
+ *               min(IoU(human boxes), IoU(object boxes)) > min_iou; else 0.
+ * Detections are the packed outputs of hoigen_emit_triplets (boxes + box_off, pairing blocks, objects, verbs = labels,
+ * scores, trip_off); ground truth is CSR over images (gt_off), boxes xyxy in the detections' frame (UPT.recover_boxes
+ * already applied).  IoU arithmetic is bit-identical to torchvision.ops.box_iou in fp32.  Scores must be >= 0. */
+HOIGEN_API int hoigen_associate_pairs(const float* boxes, const int32_t* box_off, const int64_t* pairing,
+                                      const int64_t* objects, const int64_t* verbs, const float* scores,
+                                      const int32_t* trip_off, const int32_t* conversion /* (80, num_verbs) or NULL */,
+                                      int32_t num_verbs, const float* gt_boxes_h, const float* gt_boxes_o,
+                                      const int64_t* gt_hoi, const int32_t* gt_off, int32_t max_gt_per_image,
+                                      int32_t batch, float min_iou, int64_t* interactions, float* labels,
+                                      hoigen_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
