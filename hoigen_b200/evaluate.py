@@ -76,20 +76,30 @@ class HOIAssociator:
         B = packed.num_images
         if len(targets) != B:
             raise ValueError(f"{B} images of detections, {len(targets)} targets")
-        # ground truth -> detection frame, CSR over images (tiny torch ops on the device)
-        gh, go, hoi, goff = [], [], [], [0]
-        for t in targets:
-            size = t["size"].to(dev, torch.float32)
-            gh.append(recover_boxes(t["boxes_h"].to(dev, torch.float32).view(-1, 4), size))
-            go.append(recover_boxes(t["boxes_o"].to(dev, torch.float32).view(-1, 4), size))
-            hoi.append(t["hoi"].to(dev, torch.int64).view(-1))
-            goff.append(goff[-1] + int(hoi[-1].numel()))
-        max_gt = max(b - a for a, b in zip(goff[:-1], goff[1:])) if B else 0
+        # ground truth -> detection frame, CSR over images: ONE concatenation / upload / recover_boxes for the batch (the
+        # same fp32 operations per box as the reference's per-image recover_boxes calls)
+        counts = [int(t["hoi"].numel()) for t in targets]
+        goff = [0]
+        for c in counts:
+            goff.append(goff[-1] + c)
+        max_gt = max(counts) if counts else 0
         if max_gt > MAX_GT_PER_IMAGE:
             raise ValueError(f"at most {MAX_GT_PER_IMAGE} ground-truth pairs per image (got {max_gt})")
-        gt_h = torch.cat(gh).contiguous() if goff[-1] else torch.zeros(1, 4, device=dev)
-        gt_o = torch.cat(go).contiguous() if goff[-1] else torch.zeros(1, 4, device=dev)
-        gt_hoi = torch.cat(hoi).contiguous() if goff[-1] else torch.zeros(1, dtype=torch.int64, device=dev)
+        if goff[-1]:
+            raw = torch.cat([torch.cat([t["boxes_h"].reshape(-1, 4).float(), t["boxes_o"].reshape(-1, 4).float()], dim=1)
+                             for t in targets]).to(dev, non_blocking=True)                     # (G, 8) cxcywh | cxcywh
+            sizes_hw = torch.stack([t["size"].reshape(2).float() for t in targets]).to(dev, non_blocking=True)   # (B, 2) = (h, w)
+            per_gt = sizes_hw.repeat_interleave(torch.tensor(counts, device=dev), dim=0)                 # (G, 2)
+            scale = torch.stack([per_gt[:, 1], per_gt[:, 0], per_gt[:, 1], per_gt[:, 0]], dim=1)         # (w, h, w, h)
+
+            def rec(b):
+                cx, cy, w, h = b.unbind(-1)
+                return (torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1) * scale).contiguous()
+            gt_h, gt_o = rec(raw[:, :4]), rec(raw[:, 4:])
+            gt_hoi = torch.cat([t["hoi"].reshape(-1).to(torch.int64) for t in targets]).to(dev, non_blocking=True).contiguous()
+        else:
+            gt_h = gt_o = torch.zeros(1, 4, device=dev)
+            gt_hoi = torch.zeros(1, dtype=torch.int64, device=dev)
         offs = torch.tensor(packed.box_off + packed.triplet_off + goff, dtype=torch.int32)
         d_offs = torch.empty_like(offs, device=dev)
         _cabi.call("hoigen_set_words", d_offs.data_ptr(), offs.data_ptr(), offs.numel())
