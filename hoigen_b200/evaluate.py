@@ -139,3 +139,77 @@ def _pack(dets: Sequence[Optional[dict]]):
     cat = lambda ts, dt, shape=(0,): torch.cat(ts) if ts else torch.zeros(shape, dtype=dt, device=dev)
     return PackedDetections(cat(sc, torch.float32), cat(lb, torch.int64), cat(ob, torch.int64), cat(pr, torch.int64),
                             cat(bx, torch.float32, (0, 4)), toff, boff, (0, 0))
+
+
+class DetectionAPMeter:
+    """GPU counterpart of pocket.utils.DetectionAPMeter(num_cls, num_gt, algorithm='11P', precision=64)
+    (pocket/pocket/utils/meters.py:414-639) with the same append / eval / reset surface.  Results stay on the device
+    between `append`s (no `.tolist()` per class per image); `eval` orders the sweep once by (class, score) and computes
+    every class's precision / recall curve and 11-point AP in one kernel (`hoigen_ap_11point`).
+
+    Differences from the reference, both deliberate: detections of one class with EQUAL scores keep their arrival order
+    (the reference's `argsort` is unstable, i.e. its order among ties is unspecified), and invalid class ids (negative or
+    NaN `prediction`s) are dropped as the reference's per-class gathering effectively does."""
+
+    def __init__(self, num_cls: int, num_gt=None, algorithm: str = "11P", nproc: int = 1, precision: int = 64):
+        if algorithm != "11P":
+            raise NotImplementedError("hoigen_b200 implements the '11P' algorithm the reference's eval uses (T:363-367)")
+        if precision != 64:
+            raise NotImplementedError("fp64 only (the reference's default precision)")
+        if num_gt is not None and len(num_gt) != num_cls:
+            raise AssertionError("Provided ground truth instances do not have the same number of classes as specified")
+        self.num_cls = num_cls
+        self.num_gt = None if num_gt is None else [(-1.0 if g is None else float(g)) for g in num_gt]
+        self.algorithm = algorithm
+        self.reset()
+
+    def reset(self, keep_old: bool = False) -> None:
+        if not keep_old:
+            self._scores, self._classes, self._labels = [], [], []
+
+    def append(self, output: torch.Tensor, prediction: torch.Tensor, labels: torch.Tensor) -> None:
+        """output (N,) scores, prediction (N,) class ids (float with NaN or int), labels (N,) 0/1 — meters.py:585-604."""
+        if not (isinstance(output, torch.Tensor) and isinstance(prediction, torch.Tensor) and isinstance(labels, torch.Tensor)):
+            raise TypeError("Arguments should be torch.Tensor")
+        if output.device.type != "cuda":
+            raise _cabi.HoigenError("DetectionAPMeter needs CUDA tensors (there is no CPU fallback)")
+        pred = prediction
+        if pred.is_floating_point():
+            pred = torch.where(torch.isnan(pred), torch.full_like(pred, -1.0), pred)
+        self._scores.append(output.detach().float().reshape(-1))
+        self._classes.append(pred.detach().long().reshape(-1))
+        self._labels.append(labels.detach().float().reshape(-1))
+
+    @torch.no_grad()
+    def eval(self) -> torch.Tensor:
+        """-> ap (num_cls,) fp64 on the device; also sets .ap and .max_rec like the reference (meters.py:621-639)."""
+        if not self._scores:
+            raise RuntimeError("nothing has been appended")
+        dev = self._scores[0].device
+        _cabi.init(dev)
+        scores, classes, labels = torch.cat(self._scores), torch.cat(self._classes), torch.cat(self._labels)
+        keep = (classes >= 0) & (classes < self.num_cls)
+        scores, classes, labels = scores[keep], classes[keep], labels[keep]
+        # (class ascending, score descending), ties in arrival order: two stable sorts
+        o1 = torch.argsort(scores, descending=True, stable=True)
+        o2 = torch.argsort(classes[o1], stable=True)
+        order = o1[o2]
+        lab_sorted = labels[order].contiguous()
+        counts = torch.bincount(classes, minlength=self.num_cls)
+        class_off = torch.zeros(self.num_cls + 1, dtype=torch.int64, device=dev)
+        class_off[1:] = counts.cumsum(0)
+        if self.num_gt is not None:
+            tp = torch.zeros(self.num_cls, dtype=torch.float64, device=dev).index_add_(0, classes, labels.double())
+            ngt = torch.tensor(self.num_gt, dtype=torch.float64, device=dev)
+            bad = torch.nonzero((ngt >= 0) & (tp > ngt)).flatten()
+            if bad.numel():
+                raise AssertionError(f"Class {int(bad[0])}: Number of true positives larger than that of ground truth")
+        else:
+            ngt = torch.full((self.num_cls,), -1.0, dtype=torch.float64, device=dev)
+        thr = torch.linspace(0, 1, 11, dtype=torch.float64).to(dev)       # the reference's own threshold values
+        ap = torch.empty(self.num_cls, dtype=torch.float64, device=dev)
+        max_rec = torch.empty(self.num_cls, dtype=torch.float64, device=dev)
+        _cabi.call("hoigen_ap_11point", lab_sorted.data_ptr() if lab_sorted.numel() else None, class_off.data_ptr(),
+                   ngt.data_ptr(), thr.data_ptr(), self.num_cls, ap.data_ptr(), max_rec.data_ptr())
+        self.ap, self.max_rec = ap, max_rec
+        return ap

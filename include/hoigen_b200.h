@@ -303,6 +303,15 @@ HOIGEN_API int hoigen_associate_pairs(const float* boxes, const int32_t* box_off
                                       int32_t batch, float min_iou, int64_t* interactions, float* labels,
                                       hoigen_stream_t stream);
 
+/* f2: per-class 11-point interpolated AP of a sweep — DetectionAPMeter (algorithm '11P', precision 64),
+ * pocket/pocket/utils/meters.py:561-583 + 255-270, all classes in one launch.  labels_sorted: the 0/1 labels of every
+ * collected detection ordered by (class ascending, score descending); class_off (C+1) int64 CSR offsets into it;
+ * num_gt (C) fp64, < 0 = "not given" (recall over the collected true positives); thresholds = the 11 fp64 values of
+ * torch.linspace(0, 1, 11).  Outputs ap (C), max_rec (C) in fp64; an empty class gives 0, 0 as the reference does. */
+HOIGEN_API int hoigen_ap_11point(const float* labels_sorted, const int64_t* class_off, const double* num_gt,
+                                 const double* thresholds, int32_t num_classes, double* ap, double* max_rec,
+                                 hoigen_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

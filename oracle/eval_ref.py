@@ -180,3 +180,72 @@ def synthetic_detections(batch: int, seed: int, n_h: int = 4, n_o: int = 4, tie_
                          labels=torch.tensor(vs, dtype=torch.int64), scores=scores,
                          size=torch.tensor([224, 224], dtype=torch.int64)))
     return dets
+
+
+def ap_11point(scores: Sequence[torch.Tensor], labels: Sequence[torch.Tensor], num_gt=None):
+    """DetectionAPMeter.compute_ap with algorithm '11P', precision 64 (pocket/pocket/utils/meters.py:493-583 and
+    255-270): per class, order by score (descending; STABLE here, the reference's order among equal scores is
+    unspecified), tp / fp cumulative sums, prec = tp / (tp + fp), rec = tp / num_gt (or / collected positives),
+    ap = sum over t in linspace(0, 1, 11) of max{prec : rec >= t} / 11.  -> (ap, max_rec) fp64."""
+    k = len(scores)
+    ap = torch.zeros(k, dtype=torch.float64)
+    max_rec = torch.zeros(k, dtype=torch.float64)
+    thr = torch.linspace(0, 1, 11, dtype=torch.float64)
+    for c in range(k):
+        out, lab = scores[c].double(), labels[c].double()
+        if not (len(out) and len(lab)):
+            continue
+        order = torch.argsort(out, descending=True, stable=True)
+        tp = lab[order].cumsum(0)
+        fp = (1 - lab[order]).cumsum(0)
+        prec = tp / (tp + fp)
+        denom = lab.sum().item() if (num_gt is None or num_gt[c] is None) else num_gt[c]
+        rec = torch.zeros_like(tp) if denom == 0 else tp / denom          # meters.py:24-30 `div`: x / 0 := 0
+        a = 0
+        for t in thr:
+            inds = torch.nonzero(rec >= t).squeeze()
+            if inds.numel():
+                a += prec[inds].max() / 11
+        ap[c] = a
+        max_rec[c] = rec[-1]
+    return ap, max_rec
+
+
+def synthetic_meter_stream(seed: int, num_cls: int = 600, batches: int = 12, per_batch: int = 4000, with_invalid: bool = False):
+    """A sweep's worth of (scores, predictions, labels) appends with DISTINCT scores per class (the reference's unstable
+    argsort leaves ties unspecified), a few classes never predicted, a few without any true positive, and num_gt
+    >= the collected positives (test helper shared by the golden generator and the tests)."""
+    g = torch.Generator().manual_seed(seed)
+    stream = []
+    perm = torch.randperm(batches * per_batch, generator=g).float()
+    base = (perm + 0.5) / (batches * per_batch)                       # all distinct, in (0, 1), exact in fp32
+    for b in range(batches):
+        sc = base[b * per_batch: (b + 1) * per_batch].clone()
+        pr = torch.randint(0, num_cls - 5, (per_batch,), generator=g).double()       # the last 5 classes stay empty
+        lb = (torch.rand(per_batch, generator=g) < 0.2 * sc).float()                 # better scores -> more positives
+        lb[pr < 3] = 0                                                               # classes 0..2: no true positive
+        if with_invalid:                          # (the reference itself would fail on these: NaN.long() is no class index)
+            pr[::97] = float("nan")
+        stream.append((sc, pr, lb))
+    pos = torch.zeros(num_cls)
+    for sc, pr, lb in stream:
+        ok = ~torch.isnan(pr)
+        pos.index_add_(0, pr[ok].long(), lb[ok])
+    num_gt = (pos + torch.randint(0, 4, (num_cls,), generator=g).float()).clamp(min=1).tolist()
+    return stream, num_gt
+
+
+def group_by_class(stream, num_cls: int):
+    """What DetectionAPMeter.append accumulates (meters.py:585-604): per class, scores / labels in arrival order."""
+    sc = [[] for _ in range(num_cls)]
+    lb = [[] for _ in range(num_cls)]
+    for scores, pred, labels in stream:
+        ok = ~torch.isnan(pred.double())
+        p = pred[ok].long()
+        for c in p.unique().tolist():
+            if 0 <= c < num_cls:
+                sel = p == c
+                sc[c].append(scores[ok][sel].double())
+                lb[c].append(labels[ok][sel].double())
+    cat = lambda xs: torch.cat(xs) if xs else torch.zeros(0, dtype=torch.float64)
+    return [cat(x) for x in sc], [cat(x) for x in lb]

@@ -81,5 +81,23 @@ def main():
         print(f"{name}: oracle == reference on {len(ref)} images, {sum(int(r[0].numel()) for r in ref)} detections, {tp} true positives")
 
 
+def main_ap():
+    """DetectionAPMeter('11P', precision 64, nproc 1) of the reference on a seeded sweep -> tests/golden/ap11_*.npz."""
+    from pocket.utils import DetectionAPMeter
+    for name, seed, with_gt in (("ap11_with_num_gt", 21, True), ("ap11_no_num_gt", 22, False)):
+        stream, num_gt = E.synthetic_meter_stream(seed)
+        meter = DetectionAPMeter(600, nproc=1, num_gt=num_gt if with_gt else None, algorithm="11P")
+        for sc, pr, lb in stream:
+            meter.append(sc, pr, lb)
+        ap = meter.eval()
+        sc_c, lb_c = E.group_by_class(stream, 600)
+        o_ap, o_rec = E.ap_11point(sc_c, lb_c, num_gt if with_gt else None)
+        assert torch.equal(ap, o_ap), (name, (ap - o_ap).abs().max())
+        assert torch.equal(meter.max_rec.nan_to_num(-1), o_rec.nan_to_num(-1)), name
+        np.savez_compressed(ROOT / "tests" / "golden" / f"{name}.npz", ap=ap.numpy(), max_rec=meter.max_rec.numpy())
+        print(f"{name}: oracle == reference bit for bit over 600 classes, mAP {ap.mean().item():.6f}")
+
+
 if __name__ == "__main__":
     main()
+    main_ap()

@@ -87,3 +87,41 @@ def test_association_on_forward_output(cuda_device):
     for (rs, ri, rl), (gs, gi, gl) in zip(ref, got):
         assert torch.equal(ri.nan_to_num(-1), gi.cpu().nan_to_num(-1)) and torch.equal(rl, gl.cpu())
     assert sum(int(r[2].sum()) for r in ref) > 0
+
+
+@pytest.mark.parametrize("name,seed,with_gt", [("ap11_with_num_gt", 21, True), ("ap11_no_num_gt", 22, False)])
+def test_ap_meter_matches_reference_golden(cuda_device, name, seed, with_gt):
+    """hoigen_b200.evaluate.DetectionAPMeter (hoigen_ap_11point) against the committed outputs of the unmodified
+    pocket.utils.DetectionAPMeter: fp64 AP and max recall of all 600 classes bit for bit."""
+    from hoigen_b200.evaluate import DetectionAPMeter
+    from oracle import eval_ref as E
+    gold = np.load(f"tests/golden/{name}.npz")
+    stream, num_gt = E.synthetic_meter_stream(seed)
+    meter = DetectionAPMeter(600, num_gt=num_gt if with_gt else None, algorithm="11P")
+    for sc, pr, lb in stream:
+        meter.append(sc.to(cuda_device), pr.to(cuda_device), lb.to(cuda_device))
+    ap = meter.eval()
+    assert ap.dtype == torch.float64 and ap.shape == (600,)
+    assert np.array_equal(ap.cpu().numpy(), gold["ap"])
+    assert np.array_equal(meter.max_rec.cpu().numpy(), gold["max_rec"])
+
+
+def test_ap_meter_edges(cuda_device):
+    """Invalid class ids are dropped, ties keep arrival order (the oracle's stable order), a class larger than one
+    scan chunk, too many true positives are refused like the reference does."""
+    from hoigen_b200.evaluate import DetectionAPMeter
+    from oracle import eval_ref as E
+    stream, num_gt = E.synthetic_meter_stream(31, num_cls=40, batches=5, per_batch=3000, with_invalid=True)
+    stream = [(torch.round(sc * 50) / 50, pr, lb) for sc, pr, lb in stream]          # heavy score ties
+    sc, lb = E.group_by_class(stream, 40)
+    ref_ap, ref_rec = E.ap_11point(sc, lb, num_gt)
+    meter = DetectionAPMeter(40, num_gt=num_gt)
+    for s, p, l in stream:
+        meter.append(s.to(cuda_device), p.to(cuda_device), l.to(cuda_device))
+    ap = meter.eval()
+    assert torch.equal(ap.cpu(), ref_ap) and torch.equal(meter.max_rec.cpu(), ref_rec)
+    bad = DetectionAPMeter(2, num_gt=[1, 5])
+    bad.append(torch.tensor([0.9, 0.8, 0.7], device=cuda_device), torch.tensor([0, 0, 1], device=cuda_device),
+               torch.tensor([1.0, 1.0, 0.0], device=cuda_device))
+    with pytest.raises(AssertionError):
+        bad.eval()
