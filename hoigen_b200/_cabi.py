@@ -170,6 +170,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_score_pairs": [C.POINTER(ScoreWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
     "hoigen_score_pairs_folded": [C.POINTER(FoldedWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
     "hoigen_ap_11point": [_P, _P, _P, _P, _I, _P, _P, _P],
+    "hoigen_prepare_proposals": [_P, _P, _P, _I, _I, _L, _F, _I, _I, _F, _P, _P, _P, _P, _P],
     "hoigen_associate_pairs": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P],
     "hoigen_emit_triplets": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
 }

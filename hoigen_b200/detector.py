@@ -341,6 +341,36 @@ class UPT(nn.Module):
             region_props.append(dict(boxes=bx[k], scores=sc[k], labels=lb[k], n_human=int(keep_h.numel())))
         return region_props
 
+    @torch.no_grad()
+    def prepare_region_proposals_batched(self, results: Sequence[dict]):
+        """`prepare_region_proposals` (U:1361-1406) for the whole batch in ONE kernel (`hoigen_prepare_proposals`): same
+        selection, same order, outputs already in the flat form `launch_packed` takes.  Returns None when the batch is
+        not a uniform CUDA batch (different candidate counts per image, more than 256 candidates, CPU tensors): the
+        caller then uses the per-image torch form above."""
+        if not results:
+            return None
+        q = int(results[0]["scores"].numel())
+        dev = results[0]["scores"].device
+        if dev.type != "cuda" or q == 0 or q > 256 or any(int(r["scores"].numel()) != q for r in results):
+            return None
+        _cabi.init(dev)
+        B, cap = len(results), 2 * self.max_instances
+        sc = torch.stack([r["scores"].float().reshape(-1) for r in results]).contiguous()
+        lb = torch.stack([r["labels"].to(torch.int64).reshape(-1) for r in results]).contiguous()
+        bx = torch.stack([r["boxes"].float().reshape(-1, 4) for r in results]).contiguous()
+        o_bx = torch.empty(B, cap, 4, device=dev)
+        o_sc = torch.empty(B, cap, device=dev)
+        o_lb = torch.empty(B, cap, dtype=torch.int64, device=dev)
+        counts = torch.empty(B, 2, dtype=torch.int32, device=dev)
+        _cabi.call("hoigen_prepare_proposals", sc.data_ptr(), lb.data_ptr(), bx.data_ptr(), B, q, int(self.human_idx),
+                   float(self.box_score_thresh), int(self.min_instances), int(self.max_instances), 0.5, o_bx.data_ptr(),
+                   o_sc.data_ptr(), o_lb.data_ptr(), counts.data_ptr())
+        cnt = counts.cpu()                                   # the layout of the forward is computed on the host
+        nh_list = cnt[:, 0].tolist()
+        n_list = (cnt[:, 0] + cnt[:, 1]).tolist()
+        keep = (torch.arange(cap, device=dev)[None, :] < (counts[:, 0] + counts[:, 1])[:, None].long())
+        return o_bx[keep], o_sc[keep], o_lb[keep], n_list, nh_list
+
     def recover_boxes(self, boxes: torch.Tensor, size: torch.Tensor) -> torch.Tensor:
         """cxcywh in [0,1] -> xyxy pixels (U:1269-1274)."""
         cx, cy, w, h = boxes.unbind(-1)
@@ -580,6 +610,10 @@ class UPT(nn.Module):
         outputs_class = self.detector.class_embed(hs)
         outputs_coord = self.detector.bbox_embed(hs).sigmoid()
         results = self.postprocessor({"pred_logits": outputs_class[-1], "pred_boxes": outputs_coord[-1]}, image_sizes)
-        region_props = self.prepare_region_proposals(results)
         clip = nested_tensor_from_tensor_list(images_clip).tensors
+        batched = self.prepare_region_proposals_batched(results)
+        if batched is not None:          # one kernel + one (B,2)-int read-back instead of ~25 torch launches per image
+            boxes, scores, labels, n_list, nh_list = batched
+            return self.finish(self.launch_packed(clip, boxes, scores, labels, n_list, nh_list))
+        region_props = self.prepare_region_proposals(results)
         return self.forward_from_proposals(clip, region_props)

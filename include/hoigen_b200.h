@@ -312,6 +312,16 @@ HOIGEN_API int hoigen_ap_11point(const float* labels_sorted, const int64_t* clas
                                  const double* thresholds, int32_t num_classes, double* ap, double* max_rec,
                                  hoigen_stream_t stream);
 
+/* f3 (the non-network half of the proposal stage): UPT.prepare_region_proposals U:1361-1406 for a whole batch —
+ * batched_nms(boxes, scores, labels, nms_iou) with torchvision's coordinate trick and NMS arithmetic, score threshold,
+ * min / max-instance rule, humans first.  Inputs (B, Q) scores, (B, Q) int64 labels, (B, Q, 4) boxes, Q <= 256.
+ * Outputs are padded per image to 2*max_instances slots: the first counts[2b] are humans, the next counts[2b+1] objects,
+ * each group in descending score order; out_boxes (B, 2*max_instances, 4), out_scores, out_labels; counts (B, 2). */
+HOIGEN_API int hoigen_prepare_proposals(const float* scores, const int64_t* labels, const float* boxes, int32_t batch,
+                                        int32_t num_queries, int64_t human_idx, float box_score_thresh,
+                                        int32_t min_instances, int32_t max_instances, float nms_iou, float* out_boxes,
+                                        float* out_scores, int64_t* out_labels, int32_t* counts, hoigen_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -343,3 +343,91 @@ def prepare_region_proposals(results: Sequence[dict], human_idx: int, box_score_
         k = torch.cat([keep_h, keep_o])
         out.append(dict(boxes=bx[k], scores=sc[k], labels=lb[k]))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# f3: the proposal stage restated WITHOUT torchvision — batched_nms' coordinate trick
+# (torchvision/ops/boxes.py, 0.26.0: offsets = idxs.to(boxes) * (boxes.max() + 1); nms(boxes + offsets, ...)) and the
+# greedy NMS of torchvision/csrc/ops/cpu/nms_kernel.cpp (stable sort by score descending; areas = (x2-x1)*(y2-y1);
+# ovr = inter / (iarea + areas[j] - inter) > thr suppresses j), every operation rounded to fp32 separately; then the
+# threshold / min / max-instance selection of U:1361-1406.  Checks hoigen_prepare_proposals.
+# ----------------------------------------------------------------------------------------------------------------------
+def batched_nms_ref(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    if boxes.numel() == 0:
+        return torch.empty((0,), dtype=torch.int64)
+    b = boxes.float().numpy()
+    mx = np.float32(b.max())
+    off = idxs.numpy().astype(np.float32) * np.float32(mx + np.float32(1))
+    s = (b + off[:, None]).astype(np.float32)
+    x1, y1, x2, y2 = s[:, 0], s[:, 1], s[:, 2], s[:, 3]
+    areas = ((x2 - x1).astype(np.float32) * (y2 - y1).astype(np.float32)).astype(np.float32)
+    order = np.argsort(-scores.float().numpy(), kind="stable")
+    n = len(order)
+    supp = np.zeros(n, dtype=bool)
+    keep = []
+    thr = np.float32(iou_threshold)
+    for _i in range(n):
+        i = order[_i]
+        if supp[i]:
+            continue
+        keep.append(i)
+        for _j in range(_i + 1, n):
+            j = order[_j]
+            if supp[j]:
+                continue
+            w = np.float32(max(np.float32(0), np.float32(min(x2[i], x2[j]) - max(x1[i], x1[j]))))
+            h = np.float32(max(np.float32(0), np.float32(min(y2[i], y2[j]) - max(y1[i], y1[j]))))
+            inter = np.float32(w * h)
+            ovr = np.float32(inter / np.float32(np.float32(areas[i] + areas[j]) - inter))
+            if ovr > thr:
+                supp[j] = True
+    return torch.tensor(keep, dtype=torch.int64)
+
+
+def prepare_region_proposals_ref(results: Sequence[dict], human_idx: int, box_score_thresh: float, min_instances: int,
+                                 max_instances: int) -> List[dict]:
+    """U:1361-1406 with batched_nms_ref: after NMS everything is in descending-score order, so every branch of the
+    min / max-instance rule is "the first k humans (objects) in that order", k = min_instances (or all there are) if
+    fewer than min_instances pass the score threshold, max_instances if more than max_instances do, else the count."""
+    out = []
+    for res in results:
+        sc, lb, bx = res["scores"], res["labels"], res["boxes"]
+        keep = batched_nms_ref(bx, sc, lb, 0.5)
+        sc, lb, bx = sc[keep].view(-1), lb[keep].view(-1), bx[keep].view(-1, 4)
+        is_h = lb == human_idx
+        sel = []
+        for mask in (is_h, ~is_h):
+            pool = torch.nonzero(mask).squeeze(1)
+            n_ok = int((sc[pool] >= box_score_thresh).sum())
+            k = min_instances if n_ok < min_instances else (max_instances if n_ok > max_instances else n_ok)
+            sel.append(pool[:k])
+        k = torch.cat(sel)
+        out.append(dict(boxes=bx[k], scores=sc[k], labels=lb[k], n_human=int(sel[0].numel())))
+    return out
+
+
+def synthetic_detr_results(batch: int, seed: int, q: int = 100, tie_every: int = 0) -> List[dict]:
+    """DETR-like raw detections for the proposal-stage tests: q candidates per image clustered around a few centres (so
+    NMS has work to do inside a class and must NOT suppress across classes), ~35 % humans, scores spread around the
+    threshold.  Image b % 4 == 1 has no human at all, b % 4 == 2 has every score below the threshold (min-instance
+    branch), b % 4 == 3 has every score high (max-instance branch).  tie_every > 0 repeats scores (stable-order ties)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for b in range(batch):
+        centres = torch.rand(12, 2, generator=g) * 160 + 30
+        which = torch.randint(0, 12, (q,), generator=g)
+        ctr = centres[which] + torch.randn(q, 2, generator=g) * 6
+        wh = torch.rand(q, 2, generator=g) * 50 + 15
+        boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+        labels = torch.tensor([1, 2, 3, 40, 79])[torch.randint(0, 5, (q,), generator=g)]   # few classes: NMS inside each;
+        if b % 4 != 1:                                   # large ids: the coordinate trick's fp32 rounding matters
+            labels[torch.rand(q, generator=g) < 0.35] = 0
+        scores = torch.rand(q, generator=g)
+        if b % 4 == 2:
+            scores = scores * 0.19
+        elif b % 4 == 3:
+            scores = 0.5 + scores * 0.5
+        if tie_every:
+            scores[::tie_every] = scores[0]
+        out.append(dict(scores=scores, labels=labels, boxes=boxes))
+    return out
