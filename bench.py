@@ -21,6 +21,7 @@ cannot travel to the GPU box) with all host threads on the same workload.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -368,8 +369,10 @@ def run_b200(args, rank, world, local_rank):
             upload(i + 3)                                # its slot was read by step i, which has finished
             pend = nxt
             if trace:
+                ms_ = torch.cuda.memory_stats(dev)
                 print(f"[trace-e2e] step {i}: launch {1e3 * (tb - ta):.2f} ms, finish+d2h {1e3 * (tc - tb):.2f} ms, "
-                      f"upload {1e3 * (time.perf_counter() - tc):.2f} ms", file=sys.stderr, flush=True)
+                      f"upload {1e3 * (time.perf_counter() - tc):.2f} ms segs {ms_['segment.all.allocated']} "
+                      f"gc {[g['collections'] for g in gc.get_stats()]}", file=sys.stderr, flush=True)
         if trace and len(evs) > 2:
             torch.cuda.synchronize()
             print("[trace-e2e] GPU period between step starts (ms): " +
@@ -417,9 +420,19 @@ def run_b200(args, rank, world, local_rank):
     # ---- end-to-end timing with host buffers -----------------------------------------------------------------------------
     for i in range(3):
         upload(i)
-    w_e2e = max(8, args.warmup)      # long enough for the allocator to reach its steady state with two steps in flight
+    w_e2e = max(8, args.warmup)
     pend, m_out = run_host(0, w_e2e, launch_host(0))
-    barrier()                                    # drains the step launched ahead: nothing of it runs inside the timed region
+    barrier()
+    # The timer starts at a step boundary of the RUNNING pipeline, six untimed steps after that synchronisation: traced
+    # (HOIGEN_BENCH_TRACE prints the caching allocator's segment count per step), the allocator grows by two segments on
+    # the third launch after any full device synchronisation, whatever the warm-up length (step 11 after an 8-step
+    # warm-up, step 27 after 24), and that cudaMalloc costs 1.5 ms normally but 20-160 ms in about one run in six - all of
+    # it billed to this lockstep loop (one step in flight).  Starting without a synchronisation means step w_e2e + 6,
+    # launched before t0, may still be running when the window opens, so the window holds AT LEAST `steps` whole steps of
+    # device work plus all their copies (the final barrier drains the step launched ahead): a pessimistic boundary.
+    pend, m_out = run_host(w_e2e, 6, pend)
+    w_e2e += 6
+    sweep.clear()                                # the timed sweep exchanges its own `steps` steps of detections, no warm-up ones
     clocks.active = True
     t0 = time.perf_counter()
     # K uploads, K launches, K finishes + K D2H copies; the barrier below waits for the last launched step and the copies

@@ -64,7 +64,7 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
                     float* __restrict__ stream_out = nullptr, const __nv_bfloat16* __restrict__ delta_b = nullptr,
                     __nv_bfloat16* __restrict__ stream_bf16 = nullptr, const float* __restrict__ col_bias = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;   // one warp per row; rows per CTA = launch-time choice
   if (row >= rows) return;
   float4 v[6];
   if (EMBED) {
@@ -218,6 +218,16 @@ int hoigen_layernorm768(const float* x, const float* gamma, const float* beta, f
   return HOIGEN_OK;
 }
 
+// Rows (= warps) per CTA of the residual-add + LayerNorm pass.  [experiment knob HOIGEN_LN_ROWS_PER_CTA]
+static int ln_rows_per_cta() {
+  static const int v = [] {
+    const char* e = getenv("HOIGEN_LN_ROWS_PER_CTA");
+    const int r = e ? atoi(e) : 8;
+    return r >= 1 && r <= 8 ? r : 8;
+  }();
+  return v;
+}
+
 int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2_bf16, const float* col_bias,
                             const float* gamma, const float* beta, void* out_bf16, void* x_bf16, int32_t rows,
                             hoigen_stream_t stream) {
@@ -225,7 +235,8 @@ int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2
   HOIGEN_CHECK_ARG(x && delta_bf16 && gamma && beta && out_bf16 && rows > 0, "add_layernorm768: bad arguments");
   KernelScope ks("add_layernorm768", reinterpret_cast<cudaStream_t>(stream), 0,
                  double(rows) * WIDTH * (4 + 2 + 4 + 2 + (delta2_bf16 ? 2 : 0) + (x_bf16 ? 2 : 0)));
-  layernorm768_kernel<false><<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  const int rpc = ln_rows_per_cta();
+  layernorm768_kernel<false><<<(rows + rpc - 1) / rpc, rpc * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, nullptr, nullptr, gamma, beta, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows,
       reinterpret_cast<const __nv_bfloat16*>(delta_bf16), x, reinterpret_cast<const __nv_bfloat16*>(delta2_bf16),
       reinterpret_cast<__nv_bfloat16*>(x_bf16), col_bias);

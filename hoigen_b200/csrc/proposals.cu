@@ -11,7 +11,7 @@
 //   4. survivors are in descending-score order; humans (label == human_idx) and objects separately: if fewer than
 //      min_instances pass the score threshold take the first min_instances, if more than max_instances take the first
 //      max_instances, else those that pass (U:1374-1395 — every branch is a prefix of the score order)
-//   5. outputs, humans first: boxes / scores / labels into a (B, 2*max_instances) padded block + counts (B,2).
+//   5. outputs, humans first (slots by ballot / popc prefix counts, all positions in parallel): boxes / scores / labels into a (B, 2*max_instances) padded block + counts (B,2).
 #include "common.h"
 
 namespace hoigen {
@@ -55,11 +55,14 @@ prepare_proposals_kernel(const float* __restrict__ scores, const long long* __re
   }
   __syncthreads();
   // 2. stable descending order: rank = #{j : s_j > s_i  or  (s_j == s_i and j < i)}
+  //    (a NaN score orders first, as torch's descending sort puts it, so the ranks stay a permutation)
   if (live) {
+    const float key = sc != sc ? INFINITY : sc;
     int rank = 0;
     for (int j = 0; j < Q; ++j) {
       const float sj = sscore[j];
-      rank += (sj > sc) || (sj == sc && j < t);
+      const float kj = sj != sj ? INFINITY : sj;
+      rank += (kj > key) || (kj == key && j < t);
     }
     sorder[rank] = t;
   }
@@ -77,31 +80,36 @@ prepare_proposals_kernel(const float* __restrict__ scores, const long long* __re
     }
     __syncthreads();
   }
-  // 4. / 5. survivors in order; position among the surviving humans / objects by a serial count (Q <= 256, one thread)
-  if (t == 0) {
-    int ok_h = 0, ok_o = 0, all_h = 0, all_o = 0;
-    for (int p = 0; p < Q; ++p) {
-      const int i = sorder[p];
-      if (ssupp[i]) continue;
-      const bool pass = sscore[i] >= score_thresh;
-      if (shuman[i]) { ++all_h; ok_h += pass; } else { ++all_o; ok_o += pass; }
-    }
-    const int kh = min(all_h, ok_h < min_inst ? min_inst : (ok_h > max_inst ? max_inst : ok_h));
-    const int ko = min(all_o, ok_o < min_inst ? min_inst : (ok_o > max_inst ? max_inst : ok_o));
-    counts[2 * b] = kh; counts[2 * b + 1] = ko;
-    int ph = 0, po = 0;
+  // 4. / 5. thread t owns position t of the order: its slot is its rank among the surviving humans (objects), found with
+  //          warp ballots + per-warp totals; the selection is a prefix of each group (header), so no second pass
+  __shared__ int swh[PROP_MAXQ / 32], swo[PROP_MAXQ / 32], swokh[PROP_MAXQ / 32], swoko[PROP_MAXQ / 32];
+  const bool alive = live && !ssupp[me];
+  const bool hum = alive && shuman[me];
+  const bool obj = alive && !shuman[me];
+  const bool pass = alive && sscore[me] >= score_thresh;
+  const unsigned bh = __ballot_sync(0xffffffffu, hum), bo = __ballot_sync(0xffffffffu, obj);
+  const unsigned bph = __ballot_sync(0xffffffffu, hum && pass), bpo = __ballot_sync(0xffffffffu, obj && pass);
+  if (lane == 0) { swh[warp] = __popc(bh); swo[warp] = __popc(bo); swokh[warp] = __popc(bph); swoko[warp] = __popc(bpo); }
+  __syncthreads();
+  int all_h = 0, all_o = 0, ok_h = 0, ok_o = 0, before_h = 0, before_o = 0;
+#pragma unroll
+  for (int w = 0; w < PROP_MAXQ / 32; ++w) {
+    if (w < warp) { before_h += swh[w]; before_o += swo[w]; }
+    all_h += swh[w]; all_o += swo[w]; ok_h += swokh[w]; ok_o += swoko[w];
+  }
+  const int kh = min(all_h, ok_h < min_inst ? min_inst : (ok_h > max_inst ? max_inst : ok_h));
+  const int ko = min(all_o, ok_o < min_inst ? min_inst : (ok_o > max_inst ? max_inst : ok_o));
+  if (t == 0) { counts[2 * b] = kh; counts[2 * b + 1] = ko; }
+  const unsigned below = (1u << lane) - 1u;
+  const int ph = before_h + __popc(bh & below), po = before_o + __popc(bo & below);
+  int slot = -1;
+  if (hum && ph < kh) slot = ph;
+  if (obj && po < ko) slot = kh + po;
+  if (slot >= 0) {
     const size_t base = size_t(b) * 2 * max_inst;
-    for (int p = 0; p < Q; ++p) {
-      const int i = sorder[p];
-      if (ssupp[i]) continue;
-      int slot = -1;
-      if (shuman[i]) { if (ph < kh) slot = ph; ++ph; } else { if (po < ko) slot = kh + po; ++po; }
-      if (slot >= 0) {
-        out_boxes[base + slot] = boxes[size_t(b) * Q + i];        // the ORIGINAL (unshifted) box
-        out_scores[base + slot] = sscore[i];
-        out_labels[base + slot] = labels[size_t(b) * Q + i];
-      }
-    }
+    out_boxes[base + slot] = boxes[size_t(b) * Q + me];           // the ORIGINAL (unshifted) box
+    out_scores[base + slot] = sscore[me];
+    out_labels[base + slot] = labels[size_t(b) * Q + me];
   }
 }
 
