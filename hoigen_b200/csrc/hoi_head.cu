@@ -119,8 +119,8 @@ prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ s
 // with per-axis weights Wy / Wx accumulated over the 7*g samples of that axis (out-of-range samples,
 // coordinate < -1 or > 14, contribute zero exactly as in torchvision's kernel).
 // grid = (B, 4): a CTA stages a 128-channel slice of one image's 14x14x512 token map in shared memory (coalesced
-// float4 loads) and produces that slice for every single box and every union box of the image; one warp per box,
-// lane = 4 channels.
+// float4 loads) and produces that slice for every single box and every union box of the image; one warp per group of
+// four boxes, lane = 4 channels.
 // ------------------------------------------------------------------------------------------------
 constexpr int ROI_THREADS = 256;
 constexpr int ROI_SLICE = 128;
@@ -151,13 +151,23 @@ __global__ void __launch_bounds__(256)
 roi_weights_kernel(const float* __restrict__ boxes, const int* __restrict__ box_off, const int* __restrict__ pair_off,
                    int nimg, int ntot, int ktot, float spatial_scale, float* __restrict__ wts /* (Ntot+Ktot, 32) */);
 
+// A warp takes FOUR consecutive boxes of the image at a time (unions are enumerated pair-major, so the four usually
+// share their human and their windows nest) and walks the bounding window of the four ONCE: per cell one LDS.128 of the
+// token slice feeds 16 FMAs, and the four boxes' axis weights come as one broadcast LDS.128 from a per-warp scratch row.
+// (One box per warp with a SHFL per weight was bound by the shared-memory / shuffle pipe, 4 + 1 wavefront cycles per 4
+// FMAs: ncu smem pipe 52 %, 80 us at B = 64; this form measures 69 us.)  Cells outside a box's own window carry weight
+// 0 for it: fmaf(0, f, acc) == acc, so every box's sum is the sequence of its own non-zero terms.
+constexpr int ROI_GROUP = 4;
+constexpr int ROI_SMEM_BYTES_V2 = ROI_SMEM_BYTES + (ROI_THREADS / 32) * 32 * 16;   // + one float4[32] weight row per warp
+
 __global__ void __launch_bounds__(ROI_THREADS)
-roi_features_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const float* __restrict__ wts,
-                    const int* __restrict__ box_off, const int* __restrict__ pair_off, int ntot,
-                    float* __restrict__ single_feat /* (Ntot,512) */, float* __restrict__ union_feat /* (Ktot,512) */) {
-  extern __shared__ float4 fs4[];  // [196][32] float4
+roi_features_grouped_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const float* __restrict__ wts,
+                            const int* __restrict__ box_off, const int* __restrict__ pair_off, int ntot,
+                            float* __restrict__ single_feat /* (Ntot,512) */, float* __restrict__ union_feat /* (Ktot,512) */) {
+  extern __shared__ float4 fs4[];  // [196][32] float4 token slice, then [8 warps][32] float4 weight rows
   const int b = blockIdx.x, slice = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* wq = fs4 + 196 * 32 + warp * 32;
   const float4* src = reinterpret_cast<const float4*>(tokens + (size_t(b) * TOK + 1) * FEAT + slice * ROI_SLICE);
   for (int i = threadIdx.x; i < 196 * 32; i += ROI_THREADS) fs4[i] = __ldg(src + (i >> 5) * (FEAT / 4) + (i & 31));
   __syncthreads();
@@ -165,39 +175,66 @@ roi_features_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const f
   const int n = box_off[b + 1] - bbase;
   const int pbase = pair_off[b];
   const int K = pair_off[b + 1] - pbase;
-  for (int job = warp; job < n + K; job += ROI_THREADS / 32) {
-    float* dst;
-    int gjob;
-    if (job < n) {
-      gjob = bbase + job;
-      dst = single_feat + size_t(bbase + job) * FEAT;
-    } else {
-      gjob = ntot + pbase + (job - n);
-      dst = union_feat + size_t(pbase + job - n) * FEAT;
+  const int njobs = n + K;
+  for (int j0 = warp * ROI_GROUP; j0 < njobs; j0 += (ROI_THREADS / 32) * ROI_GROUP) {
+    float w[ROI_GROUP];
+    float* dst[ROI_GROUP];
+#pragma unroll
+    for (int r = 0; r < ROI_GROUP; ++r) {
+      const int job = j0 + r;
+      w[r] = 0.f;
+      dst[r] = nullptr;
+      if (job < njobs) {
+        const int gjob = job < n ? bbase + job : ntot + pbase + (job - n);
+        dst[r] = job < n ? single_feat + size_t(bbase + job) * FEAT : union_feat + size_t(pbase + job - n) * FEAT;
+        w[r] = __ldg(wts + size_t(gjob) * 32 + lane);
+      }
     }
-    const float wl = __ldg(wts + size_t(gjob) * 32 + lane);
-    const unsigned nzy = __ballot_sync(0xffffffffu, lane < G14 && wl != 0.f);
-    const unsigned nzx = __ballot_sync(0xffffffffu, lane >= 16 && lane < 16 + G14 && wl != 0.f) >> 16;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();                       // the previous group's reads of this warp's weight row are done
+    wq[lane] = make_float4(w[0], w[1], w[2], w[3]);
+    __syncwarp();
+    const bool any = (w[0] != 0.f) | (w[1] != 0.f) | (w[2] != 0.f) | (w[3] != 0.f);
+    const unsigned nzy = __ballot_sync(0xffffffffu, lane < G14 && any);
+    const unsigned nzx = __ballot_sync(0xffffffffu, lane >= 16 && lane < 16 + G14 && any) >> 16;
+    float4 acc[ROI_GROUP];
+#pragma unroll
+    for (int r = 0; r < ROI_GROUP; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (nzy && nzx) {
       const int ylo = __ffs(nzy) - 1, yhi = 31 - __clz(nzy);
       const int xlo = __ffs(nzx) - 1, xhi = 31 - __clz(nzx);
       for (int y = ylo; y <= yhi; ++y) {
-        const float wy = __shfl_sync(0xffffffffu, wl, y);
-        float4 rowacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 row[ROI_GROUP];
+#pragma unroll
+        for (int r = 0; r < ROI_GROUP; ++r) row[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* frow = fs4 + (y * G14) * 32 + lane;
         for (int x = xlo; x <= xhi; ++x) {
-          const float wx = __shfl_sync(0xffffffffu, wl, 16 + x);
-          const float4 f = fs4[(y * G14 + x) * 32 + lane];
-          rowacc.x = fmaf(wx, f.x, rowacc.x); rowacc.y = fmaf(wx, f.y, rowacc.y);
-          rowacc.z = fmaf(wx, f.z, rowacc.z); rowacc.w = fmaf(wx, f.w, rowacc.w);
+          const float4 wx = wq[16 + x];             // broadcast: the four boxes' x-weights of this column
+          const float4 f = frow[x * 32];
+          const float wxr[ROI_GROUP] = {wx.x, wx.y, wx.z, wx.w};
+#pragma unroll
+          for (int r = 0; r < ROI_GROUP; ++r) {
+            row[r].x = fmaf(wxr[r], f.x, row[r].x); row[r].y = fmaf(wxr[r], f.y, row[r].y);
+            row[r].z = fmaf(wxr[r], f.z, row[r].z); row[r].w = fmaf(wxr[r], f.w, row[r].w);
+          }
         }
-        acc.x = fmaf(wy, rowacc.x, acc.x); acc.y = fmaf(wy, rowacc.y, acc.y);
-        acc.z = fmaf(wy, rowacc.z, acc.z); acc.w = fmaf(wy, rowacc.w, acc.w);
+        const float4 wy = wq[y];
+        const float wyr[ROI_GROUP] = {wy.x, wy.y, wy.z, wy.w};
+#pragma unroll
+        for (int r = 0; r < ROI_GROUP; ++r) {
+          acc[r].x = fmaf(wyr[r], row[r].x, acc[r].x); acc[r].y = fmaf(wyr[r], row[r].y, acc[r].y);
+          acc[r].z = fmaf(wyr[r], row[r].z, acc[r].z); acc[r].w = fmaf(wyr[r], row[r].w, acc[r].w);
+        }
       }
     }
-    const float inv = __shfl_sync(0xffffffffu, wl, 31);
-    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-    reinterpret_cast<float4*>(dst + slice * ROI_SLICE)[lane] = acc;
+    const float4 inv4 = wq[31];
+    const float inv[ROI_GROUP] = {inv4.x, inv4.y, inv4.z, inv4.w};
+#pragma unroll
+    for (int r = 0; r < ROI_GROUP; ++r) {
+      if (dst[r]) {
+        acc[r].x *= inv[r]; acc[r].y *= inv[r]; acc[r].z *= inv[r]; acc[r].w *= inv[r];
+        reinterpret_cast<float4*>(dst[r] + slice * ROI_SLICE)[lane] = acc[r];
+      }
+    }
   }
 }
 
@@ -471,7 +508,7 @@ int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int3
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static bool attr_set = false;
   if (!attr_set) {
-    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(roi_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROI_SMEM_BYTES));
+    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(roi_features_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROI_SMEM_BYTES_V2));
     attr_set = true;
   }
   {
@@ -483,8 +520,8 @@ int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int3
   {
     // algorithmic bytes: token map read once + boxes + one fp32 feature row per single / union box
     KernelScope ks("roi_features", s, 0, double(batch) * 196 * FEAT * 4 + double(ntot + ktot) * (16 + FEAT * 4));
-    roi_features_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES, s>>>(
-        tokens, roi_weights, box_off, pair_off, ntot, single_feat, union_feat);
+    roi_features_grouped_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES_V2, s>>>(
+          tokens, roi_weights, box_off, pair_off, ntot, single_feat, union_feat);
   }
   HOIGEN_CHECK_LAUNCH();
   if (ktot > 0) {
