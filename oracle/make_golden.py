@@ -33,6 +33,9 @@ CASES = {
     "hico117_oob_b1": dict(num_classes=117, dataset="hicodet", B=1, n_h=4, n_o=5, N=128, ragged=False, boxes="oob"),
     "vcoco24_b2": dict(num_classes=24, dataset="vcoco", B=2, n_h=16, n_o=16, N=96, ragged=False, boxes="grid",
                        args=dict(max_instances=16, cache=True, eval=False)),
+    # BASELINE configs[4]'s classifier: 600 HOI triplets (`generate_feature=False`, class_corr = object -> interaction)
+    "hico600_b2": dict(num_classes=600, dataset="hicodet", B=2, n_h=8, n_o=8, N=600, ragged=False, boxes="grid",
+                       args=dict(generate_feature=False)),
 }
 
 

@@ -95,6 +95,22 @@ def _synthetic_cache_pickle(path: Path, num_classes: int, table, rng: np.random.
                         "huamn_features": rng.standard_normal((P, 512)).astype(np.float32),   # sic (U:686)
                     }
                     img += 1
+    elif num_classes == 600:
+        # HOI classes: (object, verb) pairs from the correspondence table; load_cache_model maps them to interaction ids
+        # through object_n_verb_to_interaction (U:650-651)
+        from hoigen_b200 import synthetic as S
+        for _hoi, obj, v in S.load_object_tables()["hico_correspondence"]:
+            for _ in range(2):
+                P = 1
+                anno[f"img_{img:06d}.jpg"] = {
+                    "verbs": np.array([v]), "objects": np.array([obj]),
+                    "boxes_h": rng.uniform(0, 100, (P, 4)).astype(np.float32) + np.array([0, 0, 100, 100], np.float32),
+                    "boxes_o": rng.uniform(0, 100, (P, 4)).astype(np.float32) + np.array([0, 0, 100, 100], np.float32),
+                    "union_features": rng.standard_normal((P, 512)).astype(np.float32),
+                    "object_features": rng.standard_normal((P, 512)).astype(np.float32),
+                    "huamn_features": rng.standard_normal((P, 512)).astype(np.float32),   # sic (U:686)
+                }
+                img += 1
     else:
         raise NotImplementedError(num_classes)
     with open(path, "wb") as f:

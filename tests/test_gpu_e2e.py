@@ -43,6 +43,7 @@ CASES = {
     "hico117_ragged_b3": dict(num_classes=117, B=3, n_h=6, n_o=7, N=234, ragged=True, oob=False),
     "hico117_oob_b1": dict(num_classes=117, B=1, n_h=4, n_o=5, N=128, ragged=False, oob=True),
     "vcoco24_b2": dict(num_classes=24, B=2, n_h=16, n_o=16, N=96, ragged=False, oob=False, max_instances=16),
+    "hico600_b2": dict(num_classes=600, B=2, n_h=8, n_o=8, N=600, ragged=False, oob=False),
 }
 
 
