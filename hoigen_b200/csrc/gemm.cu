@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 
 #include "common.h"
@@ -787,7 +788,9 @@ static GemmArgs to_args(const hoigen_gemm_params* p) {
 
 // interned "gemm<1|2>_n<N>_k<K>" tags for the launch profiler (1 = one-CTA kernel, 2 = CTA-pair kernel)
 static const char* gemm_tag(int N, int K, int kind = 1) {
-  static std::map<std::pair<std::pair<int, int>, int>, std::string> tags;
+  static std::map<std::pair<std::pair<int, int>, int>, std::string> tags;   // node-based: c_str() of an entry stays valid
+  static std::mutex mu;                                                       // callers may launch from several host threads
+  std::lock_guard<std::mutex> lock(mu);
   const auto key = std::make_pair(std::make_pair(N, K), kind);
   auto it = tags.find(key);
   if (it == tags.end())
