@@ -98,3 +98,20 @@ def test_synthetic_inputs_are_deterministic_and_nms_safe():
         assert (p["scores"][:8].diff() <= 0).all() and (p["scores"][8:].diff() <= 0).all()
     e1, e2 = S.make_encoder_state(0), S.make_encoder_state(0)
     assert all(torch.equal(e1[k], e2[k]) for k in e1)
+
+
+def test_batched_proposal_stage_declines_what_the_kernel_cannot_take():
+    """UPT.prepare_region_proposals_batched returns None (-> the per-image torch form of U:1361-1406 runs) for CPU tensors,
+    ragged candidate counts and empty batches; the per-image form then gives the oracle's selection."""
+    from oracle import hoi_forward_ref as O
+    m = UPT.from_state(S.make_encoder_state(0), S.make_head_state(117, 64))
+    results = O.synthetic_detr_results(3, 9, 40)
+    assert m.prepare_region_proposals_batched(results) is None            # CPU tensors: no kernel, no silent fallback inside
+    assert m.prepare_region_proposals_batched([]) is None
+    ragged = [dict(r) for r in results]
+    ragged[1] = {k: v[:17] for k, v in ragged[1].items()}
+    assert m.prepare_region_proposals_batched(ragged) is None
+    got = m.prepare_region_proposals(results)
+    ref = O.prepare_region_proposals_ref(results, m.human_idx, m.box_score_thresh, m.min_instances, m.max_instances)
+    for g, r in zip(got, ref):
+        assert torch.equal(g["boxes"], r["boxes"]) and torch.equal(g["labels"], r["labels"]) and int(g["n_human"]) == r["n_human"]
