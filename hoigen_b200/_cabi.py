@@ -161,7 +161,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_debug_attention_trace": [_P, _P, _I, _P, _P],
     "hoigen_debug_adapter_trace": [_P],
     "hoigen_encoder_forward": [C.POINTER(EncoderWeights), C.POINTER(EncoderBuffers), _P, _P, _P, _I, _I, _I, _P],
-    "hoigen_prior_tokens": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P],
+    "hoigen_prior_tokens": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P],
     "hoigen_roi_pair_features": [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P],
     "hoigen_set_words": [_P, _P, _I, _P],
     "hoigen_copy_words": [_P, _P, _I, _P],
@@ -172,7 +172,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_ap_11point": [_P, _P, _P, _P, _I, _P, _P, _P],
     "hoigen_prepare_proposals": [_P, _P, _P, _I, _I, _L, _F, _I, _I, _F, _P, _P, _P, _P, _P],
     "hoigen_associate_pairs": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P],
-    "hoigen_emit_triplets": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
+    "hoigen_emit_triplets": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
 }
 
 EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", "hoigen_launch_count",

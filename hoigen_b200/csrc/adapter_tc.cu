@@ -592,11 +592,7 @@ int hoigen_adapter_block(const void* xb, const void* delta_c, const float* kv_la
   HOIGEN_CHECK_ARG(xb && kv_layer && mask && w && delta_out_bf16 && batch > 0, "adapter_block: bad arguments");
   HOIGEN_CHECK_ARG(w->wd && w->wq && w->wo && w->w1 && w->w2 && w->down_b && w->wup, "adapter_block: null weight");
   HOIGEN_CHECK_ARG(n_max > 0 && n_max <= AT_MAXKEYS, "adapter_block: n_max must be in [1,%d] (got %d)", AT_MAXKEYS, n_max);
-  static bool attr_set = false;
-  if (!attr_set) {
-    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(adapter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-    attr_set = true;
-  }
+  HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(adapter_tc_kernel), AT_SMEM_BYTES));
   const int M = batch * AT_TOKENS;
   // one wave over all SMs: 12608 rows / 148 SMs -> 88-row tiles on 144 CTAs instead of 128-row tiles on 99 (the
   // bandwidth phases — down-projection operands in, up-projection residual out — are bound per SM)

@@ -314,11 +314,7 @@ static int attention_launch(const void* qkv, void* out, int32_t batch, long long
   HOIGEN_CHECK_ARG(qkv && out && batch > 0, "attention: bad arguments");
   HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                    "attention: buffers must be 16-byte aligned");
-  static bool attr_set = false;
-  if (!attr_set) {
-    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    attr_set = true;
-  }
+  HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(attention_kernel), ATT_SMEM_BYTES));
   const uint64_t row_bytes = 3ull * ATT_WIDTH * 2;
   const CUtensorMap* tq = get_tmap_3d_bf16(qkv, 3 * ATT_WIDTH, ATT_TOKENS, uint64_t(batch), row_bytes,
                                            row_bytes * ATT_TOKENS, 64, 128, 1);

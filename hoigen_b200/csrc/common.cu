@@ -3,14 +3,17 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <set>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 namespace hoigen {
 
 static thread_local char g_err[512] = "";
-static int g_num_sms = 0;
+static std::atomic<int> g_num_sms[64];   // per device ordinal, filled by hoigen_init
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -19,7 +22,24 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+int num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  const int n = g_num_sms[dev].load(std::memory_order_relaxed);
+  return n > 0 ? n : 148;
+}
+
+int set_max_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  HOIGEN_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kernel, dev})) return HOIGEN_OK;
+  HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({kernel, dev});
+  return HOIGEN_OK;
+}
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -140,12 +160,15 @@ static const int kMaxProf = 8192;
 static ProfRec g_prof[kMaxProf];
 static int g_prof_n = 0;
 static int g_prof_events = 0;  // events created so far (reused across resets)
-static bool g_prof_on = false;
-static long long g_launches = 0;
+static std::atomic<bool> g_prof_on{false};
+static std::atomic<long long> g_launches{0};
+static std::mutex g_prof_mu;   // callers may launch from several host threads
 
 KernelScope::KernelScope(const char* tag, cudaStream_t stream, double flops, double bytes) : slot_(-1), stream_(stream) {
-  ++g_launches;
-  if (!g_prof_on || g_prof_n >= kMaxProf) return;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (g_prof_n >= kMaxProf) return;
   ProfRec& r = g_prof[g_prof_n];
   if (g_prof_n >= g_prof_events) {
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
@@ -195,7 +218,7 @@ StreamKWorkspace get_streamk_workspace(cudaStream_t stream, size_t slot_bytes, i
 
 extern "C" {
 
-long long hoigen_launch_count(void) { return hoigen::g_launches; }
+long long hoigen_launch_count(void) { return hoigen::g_launches.load(); }
 
 int hoigen_profile_enable(int on) {
   hoigen::g_prof_on = on != 0;
@@ -203,6 +226,7 @@ int hoigen_profile_enable(int on) {
 }
 
 int hoigen_profile_reset(void) {
+  std::lock_guard<std::mutex> lock(hoigen::g_prof_mu);
   hoigen::g_prof_n = 0;
   hoigen::g_launches = 0;
   return HOIGEN_OK;
@@ -237,7 +261,7 @@ int hoigen_init(int device) {
                       prop.minor);
     return HOIGEN_ERR_ARCH;
   }
-  hoigen::g_num_sms = prop.multiProcessorCount;
+  if (device >= 0 && device < 64) hoigen::g_num_sms[device] = prop.multiProcessorCount;
   if (hoigen::resolve_driver() != 0) return HOIGEN_ERR_CUDA;
   return HOIGEN_OK;
 }

@@ -11,7 +11,11 @@
 namespace hoigen {
 
 void set_error(const char* fmt, ...);
-int num_sms();
+int num_sms();   // of the calling thread's current device
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device and several
+// devices may be driven from one process (one module per device), possibly from several host threads.
+int set_max_dynamic_smem(const void* kernel, int bytes);
 
 // 2-D / 3-D bf16 row-major tensor maps with 128-byte swizzle. dims/box innermost-first, strides in
 // BYTES for dims 1.. (dim 0 is contiguous).  Returns nullptr (and sets the error) on failure.
@@ -53,6 +57,12 @@ struct KernelScope {
       ::hoigen::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
       return HOIGEN_ERR_CUDA;                                                                \
     }                                                                                        \
+  } while (0)
+
+#define HOIGEN_TRY_RC(expr)               \
+  do {                                    \
+    int _rc = (expr);                     \
+    if (_rc != HOIGEN_OK) return _rc;     \
   } while (0)
 
 #define HOIGEN_CHECK_LAUNCH() HOIGEN_CHECK_CUDA(cudaGetLastError())

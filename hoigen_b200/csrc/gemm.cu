@@ -812,12 +812,7 @@ static int auto_split_k(int num_tiles, int num_k) {
 template <int BN>
 static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(gemm_bf16_kernel<BN>), Cfg::SMEM_BYTES));
   const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
   if (!ta) return HOIGEN_ERR_CUDA;
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN);
@@ -844,12 +839,7 @@ static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
 template <int BN, bool TMA_OUT, int EPI>
 static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream, bool force_split) {
   using Cfg = Gemm2Cfg<BN, TMA_OUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, TMA_OUT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(gemm2_bf16_kernel<BN, TMA_OUT, EPI>), Cfg::SMEM_BYTES));
   const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
   if (!ta) return HOIGEN_ERR_CUDA;
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN / 2);

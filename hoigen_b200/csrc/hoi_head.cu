@@ -60,7 +60,7 @@ prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ s
                     const int* __restrict__ box_off, const float* __restrict__ obj_emb, const float* __restrict__ w0t,
                     const float* __restrict__ b0, const float* __restrict__ w1t, const float* __restrict__ b1,
                     const float* __restrict__ w2t, const float* __restrict__ b2, float img_w, float img_h, int n_max,
-                    float* __restrict__ prior, uint8_t* __restrict__ mask) {
+                    int num_objects, float* __restrict__ prior, uint8_t* __restrict__ mask) {
   __shared__ float xin[PRIOR_TPB][520];
   __shared__ float h1[PRIOR_TPB][128];
   __shared__ float h2[PRIOR_TPB][128];
@@ -77,7 +77,10 @@ prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ s
     if (t < n && c < PRIOR_IN) {
       if (c == 0) v = scores[base + t];
       else if (c < 5) v = boxes[(base + t) * 4 + (c - 1)] / ((c & 1) ? img_w : img_h);  // x1/w, y1/h, x2/w, y2/h
-      else v = __ldg(obj_emb + labels[base + t] * FEAT + (c - 5));
+      else {   // a label outside the embedding table reads nothing (the host surface validates / the reference would raise)
+        const int64_t lb = labels[base + t];
+        v = (lb >= 0 && lb < num_objects) ? __ldg(obj_emb + lb * FEAT + (c - 5)) : 0.f;
+      }
     }
     xin[i / 520][c] = v;
   }
@@ -375,7 +378,7 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ img_logits, cons
 __global__ void __launch_bounds__(256)
 pair_count_kernel(const float* __restrict__ scores, const int64_t* __restrict__ labels, const int* __restrict__ box_off,
                   const int* __restrict__ pair_off, int nimg, int ktot, const uint32_t* __restrict__ table_bits,
-                  int words, float lambda, int* __restrict__ counts, float* __restrict__ pr_out) {
+                  int words, int table_rows, float lambda, int* __restrict__ counts, float* __restrict__ pr_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ktot) return;
   const int b = find_image(pair_off, nimg, i);
@@ -386,10 +389,12 @@ pair_count_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
   const int py = r < px ? r : r + 1;
   const float sh = powf(scores[base + px], lambda);
   const float so = powf(scores[base + py], lambda);
-  const float pr = sh * so;
+  float pr = sh * so;
+  const int64_t obj = labels[base + py];
   int cnt = 0;
+  if (obj < 0 || obj >= table_rows) pr = 0.f;   // no row in the object -> target-class table: emits nothing, reads nothing
   if (pr != 0.f) {
-    const uint32_t* bits = table_bits + size_t(labels[base + py]) * words;
+    const uint32_t* bits = table_bits + size_t(obj) * words;
     for (int w = 0; w < words; ++w) cnt += __popc(bits[w]);
   }
   counts[i] = cnt;
@@ -485,14 +490,15 @@ extern "C" {
 int hoigen_prior_tokens(const float* boxes, const float* scores, const int64_t* labels, const int32_t* box_off,
                         const float* obj_emb, const float* w0t, const float* b0, const float* w1t, const float* b1,
                         const float* w2t, const float* b2, float img_w, float img_h, int32_t batch, int32_t n_max,
-                        float* prior, uint8_t* mask, hoigen_stream_t stream) {
+                        int32_t num_objects, float* prior, uint8_t* mask, hoigen_stream_t stream) {
   using namespace hoigen;
   HOIGEN_CHECK_ARG(boxes && scores && labels && box_off && obj_emb && prior && mask && batch > 0, "prior_tokens: bad arguments");
   HOIGEN_CHECK_ARG(n_max > 0 && n_max <= PRIOR_MAXTOK, "prior_tokens: n_max must be in [1,%d] (got %d)", PRIOR_MAXTOK, n_max);
+  HOIGEN_CHECK_ARG(num_objects > 0, "prior_tokens: num_objects (rows of object_embedding) must be positive");
   KernelScope ks("prior_tokens", reinterpret_cast<cudaStream_t>(stream), 2.0 * batch * n_max * (517 * 128 + 128 * 128 + 128 * 64),
                  double(batch) * n_max * (517 + 64) * 4);
   prior_tokens_kernel<<<dim3(batch, (n_max + PRIOR_TPB - 1) / PRIOR_TPB), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      boxes, scores, labels, box_off, obj_emb, w0t, b0, w1t, b1, w2t, b2, img_w, img_h, n_max, prior, mask);
+      boxes, scores, labels, box_off, obj_emb, w0t, b0, w1t, b1, w2t, b2, img_w, img_h, n_max, num_objects, prior, mask);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
@@ -506,11 +512,7 @@ int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int3
                    "roi_pair_features: null argument");
   HOIGEN_CHECK_ARG(batch > 0 && ntot > 0 && ktot >= 0, "roi_pair_features: bad sizes");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    HOIGEN_CHECK_CUDA(cudaFuncSetAttribute(roi_features_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROI_SMEM_BYTES_V2));
-    attr_set = true;
-  }
+  HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(roi_features_grouped_kernel), ROI_SMEM_BYTES_V2));
   {
     KernelScope ks("roi_weights", s, 0, double(ntot + ktot) * (16 + 128));
     roi_weights_kernel<<<((ntot + ktot) * 32 + 255) / 256, 256, 0, s>>>(boxes, box_off, pair_off, batch, ntot, ktot,
@@ -589,7 +591,7 @@ int hoigen_broadcast_image_logits(const float* img_logits, const int32_t* pair_o
 
 int hoigen_emit_triplets(const float* logits, int32_t num_classes, int32_t ld_logits, const float* scores, const int64_t* labels,
                          const int32_t* box_off, const int32_t* pair_off, int32_t batch, int32_t ktot,
-                         const uint32_t* table_bits, int32_t table_words, float hyper_lambda, int32_t* work_counts,
+                         const uint32_t* table_bits, int32_t table_words, int32_t table_rows, float hyper_lambda, int32_t* work_counts,
                          int32_t* work_offsets, float* work_pr, int64_t capacity, float* out_scores,
                          int64_t* out_labels, int64_t* out_objects, int64_t* out_pairing, int32_t* img_off,
                          hoigen_stream_t stream) {
@@ -597,12 +599,13 @@ int hoigen_emit_triplets(const float* logits, int32_t num_classes, int32_t ld_lo
   HOIGEN_CHECK_ARG(logits && scores && labels && box_off && pair_off && table_bits && work_counts && work_offsets &&
                        work_pr && out_scores && out_labels && out_objects && out_pairing && img_off,
                    "emit_triplets: null argument");
-  HOIGEN_CHECK_ARG(batch > 0 && ktot >= 0 && num_classes > 0 && table_words * 32 >= num_classes, "emit_triplets: bad sizes");
+  HOIGEN_CHECK_ARG(batch > 0 && ktot >= 0 && num_classes > 0 && table_words * 32 >= num_classes && table_rows > 0,
+                   "emit_triplets: bad sizes");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (ktot > 0) {
     KernelScope ks("pair_count", s, 0, double(ktot) * 24);
     pair_count_kernel<<<(ktot + 255) / 256, 256, 0, s>>>(scores, labels, box_off, pair_off, batch, ktot, table_bits,
-                                                         table_words, hyper_lambda, work_counts, work_pr);
+                                                         table_words, table_rows, hyper_lambda, work_counts, work_pr);
     HOIGEN_CHECK_LAUNCH();
   }
   {

@@ -23,6 +23,10 @@ from . import _cabi
 from .encoder import MAX_PRIOR_TOKENS, TOKENS, VisionTransformer, _ParamBag, _linear_params
 
 
+# slots of DETR's 91-way COCO classifier that carry no category ('N/A' in the reference's COCO_CLASSES list, U:570-578)
+_COCO_UNNAMED_SLOTS = (0, 12, 26, 29, 30, 45, 66, 68, 69, 71, 83)
+
+
 class PackedDetections:
     """The batch's detections as the kernels wrote them: flat per-field tensors + host-side CSR offsets.
     `pairing` holds, per image b, a contiguous [2][M_b] block starting at 2*triplet_off[b]."""
@@ -125,6 +129,9 @@ class UPT(nn.Module):
         self.priors_initial_dim = 517
         self.logits_type, self.cache_model, self.prior_type, self.prior_method = "HO+U+T", "gen_feat", "cbe", 0
         self.use_insadapter = True
+        # U:579-581: the 80 named classes of DETR's 91-slot COCO head (+ the trailing no-object logit); applied to V-COCO
+        # models whose DETR emits 92 logits (U:1600-1602)
+        self.reserve_indices = torch.as_tensor([i for i in range(91) if i not in _COCO_UNNAMED_SLOTS] + [91])
         ls = math.log(1 / 0.07)
         P = lambda *shape: nn.Parameter(torch.zeros(*shape))
         if dino:
@@ -195,6 +202,8 @@ class UPT(nn.Module):
                   "object_embedding", "origin_text_embeddings"):
             if hasattr(ref, k):
                 setattr(m, k, getattr(ref, k))
+        if hasattr(ref, "reserve_indices"):
+            m.reserve_indices = torch.as_tensor(ref.reserve_indices).clone()
         if getattr(ref, "zs_type", None) == "rare_first":
             m.object_class_to_target_class = ref.object_to_verb   # U:821-822
         return m.eval()
@@ -428,14 +437,34 @@ class UPT(nn.Module):
         launch(batch i+1) before finish(batch i) so the host never leaves the GPU idle; `forward_from_proposals` is
         launch + finish.  Returns None when no image has a valid pair (U:1660-1662)."""
         n_list = [int(rp["boxes"].shape[0]) for rp in region_props]
-        if all("n_human" in rp for rp in region_props):
-            nh_list = [int(rp["n_human"]) for rp in region_props]
-        else:  # one batched device->host read instead of the reference's per-image syncs (U:985-998)
-            counts = torch.stack([(rp["labels"] == self.human_idx).sum() for rp in region_props]).cpu()
-            nh_list = [int(v) for v in counts]
         boxes = torch.cat([rp["boxes"] for rp in region_props])
         scores = torch.cat([rp["scores"] for rp in region_props])
         labels = torch.cat([rp["labels"] for rp in region_props])
+        if all("n_human" in rp for rp in region_props):
+            # produced by this module's own prepare_region_proposals: humans lead by construction (cat([keep_h, keep_o]))
+            nh_list = [int(rp["n_human"]) for rp in region_props]
+        else:
+            # externally supplied proposals: ONE batched device->host read instead of the reference's per-image syncs
+            # (U:985-998); it also lets the host validate the labels and apply the reference's humans-first permutation
+            lab_h = labels.to(torch.int64).cpu()
+            n_obj_classes = min(len(self.object_class_to_target_class), int(self.object_embedding.shape[0]))
+            if lab_h.numel() and (int(lab_h.min()) < 0 or int(lab_h.max()) >= n_obj_classes):
+                raise IndexError(f"object labels must lie in [0, {n_obj_classes}) (object_class_to_target_class / "
+                                 f"object_embedding rows); got [{int(lab_h.min())}, {int(lab_h.max())}]")
+            nh_list, perm, off, permuted = [], [], 0, False
+            for n in n_list:
+                is_h = lab_h[off: off + n] == self.human_idx
+                nh = int(is_h.sum())
+                nh_list.append(nh)
+                if bool(is_h[:nh].all()):
+                    perm.append(torch.arange(off, off + n))
+                else:   # U:989-996: stable [humans..., others...]; `pairing` then indexes this permuted order while the
+                    permuted = True          # returned `boxes` stay as given — exactly what the reference returns
+                    perm.append(off + torch.cat([torch.nonzero(is_h).squeeze(1), torch.nonzero(~is_h).squeeze(1)]))
+                off += n
+            if permuted:
+                idx = torch.cat(perm).to(boxes.device)
+                boxes, scores, labels = boxes[idx], scores[idx], labels[idx]
         return self.launch_packed(images_clip, boxes, scores, labels, n_list, nh_list, dino_image_features,
                                   return_intermediates=return_intermediates,
                                   image_boxes=[rp["boxes"] for rp in region_props])
@@ -467,6 +496,8 @@ class UPT(nn.Module):
             box_off.append(box_off[-1] + n)
             pair_off.append(pair_off[-1] + k)
         ntot, ktot = box_off[-1], pair_off[-1]
+        if ktot == 0:
+            return None  # U:1660-1662: no image produced logits (checked before any staging slot is taken or kernel enqueued)
         # pinned staging comes from a small per-module ring: allocating pinned memory per call (cudaHostAlloc) would
         # synchronise the device and serialise launch-ahead callers
         stage = self._pinned_slot(4 * B + 3)
@@ -485,7 +516,7 @@ class UPT(nn.Module):
         _cabi.call("hoigen_prior_tokens", boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), d_box_off.data_ptr(),
                    p["object_embedding"].data_ptr(), p["prior_w0t"].data_ptr(), p["prior_b0"].data_ptr(),
                    p["prior_w1t"].data_ptr(), p["prior_b1"].data_ptr(), p["prior_w2t"].data_ptr(), p["prior_b2"].data_ptr(),
-                   float(img_w), float(img_h), B, n_max, prior.data_ptr(), mask.data_ptr())
+                   float(img_w), float(img_h), B, n_max, int(p["object_embedding"].shape[0]), prior.data_ptr(), mask.data_ptr())
         # ---- a4-a7: encoder ------------------------------------------------------------------------------------
         tokens = self.clip_head.image_encoder.encode_tokens(images_clip, prior, mask)
         # ---- a8: DINO features are an input of this path (stock module, as in the reference U:1616-1618) ---------
@@ -496,8 +527,6 @@ class UPT(nn.Module):
             dino_image_features = dino_image_features / dino_image_features.norm(dim=-1, keepdim=True)
         dino_ptr = dino_image_features.float().contiguous() if self.dino else None
 
-        if ktot == 0:
-            return None  # U:1660-1662: no image produced logits
         # ---- a9: RoIAlign + pair assembly --------------------------------------------------------------------------
         single = self._buf("single", ntot * 512, torch.float32, dev)
         union = self._buf("union", ktot * 512, torch.float32, dev)
@@ -535,7 +564,8 @@ class UPT(nn.Module):
         out_pairing = torch.empty(max(2 * cap, 2), device=dev, dtype=torch.int64)
         img_off = torch.empty(B + 1, device=dev, dtype=torch.int32)
         _cabi.call("hoigen_emit_triplets", logits.data_ptr(), Cn, ldl, scores.data_ptr(), labels.data_ptr(), d_box_off.data_ptr(),
-                   d_pair_off.data_ptr(), B, ktot, p["table_bits"].data_ptr(), p["table_words"], float(self.hyper_lambda),
+                   d_pair_off.data_ptr(), B, ktot, p["table_bits"].data_ptr(), p["table_words"], int(p["table_bits"].shape[0]),
+                   float(self.hyper_lambda),
                    self._buf("emit_counts", ktot, torch.int32, dev).data_ptr(),
                    self._buf("emit_offsets", ktot + 1, torch.int32, dev).data_ptr(),
                    self._buf("emit_pr", ktot, torch.float32, dev).data_ptr(), cap, out_scores.data_ptr(),
@@ -609,6 +639,9 @@ class UPT(nn.Module):
         hs, _ = self.detector.transformer(self.detector.input_proj(src), mask, self.detector.query_embed.weight, pos[-1])
         outputs_class = self.detector.class_embed(hs)
         outputs_coord = self.detector.bbox_embed(hs).sigmoid()
+        if self.dataset == "vcoco" and outputs_class.shape[-1] == 92:                 # U:1600-1602
+            outputs_class = outputs_class[..., self.reserve_indices.to(outputs_class.device)]
+            assert outputs_class.shape[-1] == 81, "reserved shape NOT match 81"
         results = self.postprocessor({"pred_logits": outputs_class[-1], "pred_boxes": outputs_coord[-1]}, image_sizes)
         clip = nested_tensor_from_tensor_list(images_clip).tensors
         batched = self.prepare_region_proposals_batched(results)

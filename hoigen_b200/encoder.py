@@ -116,7 +116,7 @@ class VisionTransformer(nn.Module):
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_struct = None
-        self._ws_cache: Dict[Tuple[int, int], Tuple[Dict[str, torch.Tensor], object]] = {}
+        self._ws_cache: Dict[Tuple[int, int], Tuple[Dict[str, torch.Tensor], object]] = {}   # (batch, stream) -> buffers
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     # ------------------------------------------------------------------------------------------------------
@@ -176,9 +176,11 @@ class VisionTransformer(nn.Module):
         self._packed, self._packed_struct = p, s
         return p
 
-    def _workspace(self, batch: int, n_max: int):
-        # one workspace per (shape, CUDA stream): forwards launched on different streams may overlap on the GPU
-        key = (batch, n_max, torch.cuda.current_stream(self.proj.device).cuda_stream)
+    def _workspace(self, batch: int):
+        # one workspace per (batch, CUDA stream): forwards launched on different streams may overlap on the GPU.  Nothing in
+        # it depends on the batch's box count (adapter_kv is sized for MAX_PRIOR_TOKENS), so the pointers — and with them
+        # the cached TMA descriptors and stream-K slots — stay put while n_max changes from batch to batch on real data.
+        key = (batch, torch.cuda.current_stream(self.proj.device).cuda_stream)
         if key not in self._ws_cache:
             dev = self.proj.device
             M = batch * TOKENS
@@ -188,7 +190,7 @@ class VisionTransformer(nn.Module):
                 "patches": e((batch * 196, 768), bf), "patch_emb": e((batch * 196, 768), f32),
                 "x": e((M, 768), f32), "xb": e((M, 768), bf), "h": e((M, 768), bf), "qkv": e((M, 2304), bf),
                 "attn": e((M, 768), bf), "mlp": e((M, 3072), bf), "delta": e((M, 768), bf), "delta2": e((M, 768), bf),
-                "adapter_kv": e((12, batch * n_max, 128), f32),
+                "adapter_kv": e((12, batch * MAX_PRIOR_TOKENS, 128), f32),
                 "tokens_out": e((M, 512), f32),
             }
             s = _cabi.EncoderBuffers()
@@ -220,7 +222,7 @@ class VisionTransformer(nn.Module):
         x = x.contiguous().float()
         prior = prior.contiguous().float()
         mask_u8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous().to(torch.uint8)
-        bufs, bstruct = self._workspace(B, n_max)
+        bufs, bstruct = self._workspace(B)
         _cabi.call("hoigen_encoder_forward", C.byref(self._packed_struct), C.byref(bstruct), x.data_ptr(),
                    prior.data_ptr(), mask_u8.data_ptr(), B, n_max, num_layers)
         return bufs["tokens_out"]

@@ -199,7 +199,8 @@ HOIGEN_API int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoi
 HOIGEN_API int hoigen_prior_tokens(const float* boxes, const float* scores, const int64_t* labels, const int32_t* box_off,
                                    const float* object_embedding, const float* w0t, const float* b0, const float* w1t,
                                    const float* b1, const float* w2t, const float* b2, float img_w, float img_h,
-                                   int32_t batch, int32_t n_max, float* prior, uint8_t* mask, hoigen_stream_t stream);
+                                   int32_t batch, int32_t n_max, int32_t num_objects /* rows of object_embedding */,
+                                   float* prior, uint8_t* mask, hoigen_stream_t stream);
 /* compute_roi_embeddings geometry U:981-1057: RoIAlign(7x7, sampling_ratio=-1, aligned=True)+mean of every single
  * box and every union box on the 14x14 token grid (torchvision.ops.roi_align call sites U:1028-1029), then
  * f_H = single[x]/|.|, f_O = single[y]/|.|, f_U = union/|.|  -> pair_feat [3][Ktot][512] (H,O,U) bf16 (+fp32). */
@@ -279,8 +280,9 @@ HOIGEN_API int hoigen_score_pairs_folded(const hoigen_folded_weights* w, const h
 HOIGEN_API int hoigen_emit_triplets(const float* logits, int32_t num_classes, int32_t ld_logits, const float* scores,
                                     const int64_t* labels,
                                     const int32_t* box_off, const int32_t* pair_off, int32_t batch, int32_t ktot,
-                                    const uint32_t* table_bits, int32_t table_words, float hyper_lambda,
-                                    int32_t* work_counts, int32_t* work_offsets, float* work_pr, int64_t capacity,
+                                    const uint32_t* table_bits, int32_t table_words,
+                                    int32_t table_rows /* rows of table_bits; labels outside [0,rows) emit nothing */,
+                                    float hyper_lambda, int32_t* work_counts, int32_t* work_offsets, float* work_pr, int64_t capacity,
                                     float* out_scores, int64_t* out_labels, int64_t* out_objects, int64_t* out_pairing,
                                     int32_t* img_off, hoigen_stream_t stream);
 

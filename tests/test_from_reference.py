@@ -32,6 +32,7 @@ for k in ("clip_head.image_encoder.proj", "gen_adapter_U_weight", "priors_downpr
 assert ours.num_classes == 117 and ours.detector is upt.detector and ours.hyper_lambda == 2.8
 assert torch.equal(ours.sample_lens_U, upt.sample_lens_U) and torch.equal(ours.object_embedding, upt.object_embedding)
 ours.load_state_dict(ref_sd, strict=True)          # a reference checkpoint loads strictly
+assert torch.equal(ours.reserve_indices, torch.as_tensor(upt.reserve_indices))      # U:579-581 (V-COCO 92-logit DETR heads)
 p, sw = ours.pack_weights()
 assert sw.num_classes == 117 and sw.cache_rows == 256
 print("OK")

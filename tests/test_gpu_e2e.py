@@ -396,7 +396,7 @@ def test_emit_stage_exact_order_and_denormals(cuda_device):
     wp = torch.empty(ktot, device=dev)
     lg = logits.to(dev).contiguous()
     _cabi.call("hoigen_emit_triplets", lg.data_ptr(), 117, 117, scores.data_ptr(), labels.data_ptr(), d_box.data_ptr(), d_pair.data_ptr(),
-               4, ktot, p["table_bits"].data_ptr(), p["table_words"], 2.8, wc.data_ptr(), wo.data_ptr(), wp.data_ptr(), cap,
+               4, ktot, p["table_bits"].data_ptr(), p["table_words"], p["table_bits"].shape[0], 2.8, wc.data_ptr(), wo.data_ptr(), wp.data_ptr(), cap,
                o_s.data_ptr(), o_l.data_ptr(), o_o.data_ptr(), o_p.data_ptr(), img_off.data_ptr())
     offs = img_off.cpu().tolist()
     for b, q in enumerate(props):
@@ -462,3 +462,78 @@ def test_upt_forward_with_injected_detector(cuda_device):
     # no image with a valid pair -> None (U:1660-1662)
     out = m.forward_from_proposals(imgs[:1], [dict(boxes=rp[3]["boxes"], scores=rp[3]["scores"], labels=rp[3]["labels"])], dino[:1])
     assert out is None
+
+
+def test_external_proposals_humans_not_first_and_bad_labels(cuda_device):
+    """Externally supplied region proposals (no `n_human`): the reference permutes humans to the top of its LOCAL copy
+    (U:989-996) — pairing then indexes the permuted order while `boxes` is returned as given; labels outside the
+    object tables raise like the reference's table lookup would, instead of reading out of bounds."""
+    from hoigen_b200 import synthetic as S
+    from oracle import hoi_forward_ref as O
+    m, enc, head = _build(117, 256, cuda_device)
+    B = 2
+    props = S.make_region_props(B, 4, 5, seed=90)
+    g = torch.Generator().manual_seed(91)
+    shuffled = []
+    for p in props:
+        perm = torch.randperm(p["boxes"].shape[0], generator=g)
+        shuffled.append({k: v[perm] for k, v in p.items()})
+    imgs, dino = S.make_images(B, seed=92), S.make_dino_features(B, seed=93)
+    # oracle on the reference's permuted local copy
+    permuted = []
+    for p in shuffled:
+        is_h = p["labels"] == 0
+        idx = torch.cat([torch.nonzero(is_h).squeeze(1), torch.nonzero(~is_h).squeeze(1)])
+        permuted.append({k: v[idx] for k, v in p.items()})
+    o_dets = O.hoi_forward(imgs, permuted, dino, enc, head)
+    dets = m.forward_from_proposals(imgs.to(cuda_device), _props_to(shuffled, cuda_device), dino.to(cuda_device))
+    for b in range(B):
+        for k in ("pairing", "labels", "objects"):
+            assert torch.equal(dets[b][k].cpu(), o_dets[b][k]), (b, k)
+        assert torch.equal(dets[b]["boxes"].cpu(), shuffled[b]["boxes"])          # returned as given (U:1645)
+        rel = ((dets[b]["scores"].cpu() - o_dets[b]["scores"]).abs() / o_dets[b]["scores"].abs().clamp_min(1e-30)).max().item()
+        assert rel <= SCORE_RTOL, rel
+    bad = _props_to(S.make_region_props(1, 3, 3, seed=94), cuda_device)
+    bad[0]["labels"] = bad[0]["labels"].clone()
+    bad[0]["labels"][-1] = 90                                                # DETR's raw 91-slot label space
+    with pytest.raises(IndexError):
+        m.forward_from_proposals(imgs[:1].to(cuda_device), bad, dino[:1].to(cuda_device))
+
+
+def test_vcoco_forward_slices_92_logit_detr_head(cuda_device):
+    """U:1600-1602: a V-COCO model whose DETR emits 92 logits keeps the 81 reserved ones before the post-processor."""
+    from hoigen_b200 import synthetic as S
+    m, enc, head = _build(24, 96, cuda_device, max_instances=16, dataset="vcoco")
+    seen = {}
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.query_embed = torch.nn.Embedding(1, 1)
+            self.bbox_embed = self.input_proj = torch.nn.Identity()
+
+        def class_embed(self, hs):
+            return torch.arange(92, device=hs.device, dtype=torch.float32).expand(hs.shape[0], hs.shape[1], hs.shape[2], 92)
+
+        def backbone(self, nested):
+            from hoigen_b200.detector import _NestedTensor
+            return [_NestedTensor(nested.tensors[:, :1, :1, :1], None)], [None]
+
+        def transformer(self, src, mask, query, pos):
+            return torch.zeros(1, src.shape[0], 3, 4, device=src.device), None
+
+    props = _props_to(S.make_region_props(2, 3, 3, seed=95), cuda_device)
+
+    class PP(torch.nn.Module):
+        def forward(self, outputs, sizes):
+            seen["logits"] = outputs["pred_logits"]
+            return [dict(scores=p["scores"], labels=p["labels"], boxes=p["boxes"]) for p in props]
+
+    m.detector, m.postprocessor = Stub().to(cuda_device), PP()
+    imgs = S.make_images(2, seed=96).to(cuda_device)
+    dino = S.make_dino_features(2).to(cuda_device)
+    m.dino_model = lambda x: dino
+    dets = m([(torch.zeros(3, 40, 50, device=cuda_device), imgs[b]) for b in range(2)])
+    assert seen["logits"].shape[-1] == 81
+    assert seen["logits"][0, 0].tolist() == [float(i) for i in m.reserve_indices.tolist()]
+    assert len(dets) == 2

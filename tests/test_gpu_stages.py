@@ -469,6 +469,6 @@ def test_prior_tokens(cuda_device):
     mask = torch.empty(B, n_max, device=dev, dtype=torch.uint8)
     _cabi.call("hoigen_prior_tokens", boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), box_off.data_ptr(), oe.data_ptr(),
                w[0].data_ptr(), bb[0].data_ptr(), w[1].data_ptr(), bb[1].data_ptr(), w[2].data_ptr(), bb[2].data_ptr(),
-               224.0, 224.0, B, n_max, prior.data_ptr(), mask.data_ptr())
+               224.0, 224.0, B, n_max, oe.shape[0], prior.data_ptr(), mask.data_ptr())
     assert torch.equal(mask.bool().cpu(), ref_mask)
     assert (prior.cpu() - ref).abs().max().item() < 1e-4       # fp32 MLP, different summation order

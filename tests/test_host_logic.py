@@ -115,3 +115,13 @@ def test_batched_proposal_stage_declines_what_the_kernel_cannot_take():
     ref = O.prepare_region_proposals_ref(results, m.human_idx, m.box_score_thresh, m.min_instances, m.max_instances)
     for g, r in zip(got, ref):
         assert torch.equal(g["boxes"], r["boxes"]) and torch.equal(g["labels"], r["labels"]) and int(g["n_human"]) == r["n_human"]
+
+
+def test_vcoco_reserve_indices_select_the_80_named_coco_slots():
+    """U:579-581: indices of DETR's 92 logits kept for V-COCO = the 80 named COCO categories + the trailing no-object
+    logit; a 92-logit head sliced with them has 81 entries (U:1600-1602)."""
+    m = UPT(24, 8, object_class_to_target_class=S.object_table(24), dataset="vcoco")
+    r = m.reserve_indices.tolist()
+    assert len(r) == 81 and r[0] == 1 and r[-1] == 91 and r == sorted(r)
+    assert set(range(92)) - set(r) == {0, 12, 26, 29, 30, 45, 66, 68, 69, 71, 83}
+    assert torch.randn(6, 2, 100, 92)[..., m.reserve_indices].shape[-1] == 81
