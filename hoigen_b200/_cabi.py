@@ -140,6 +140,22 @@ class ScoreBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in SCORE_BUFFER_FIELDS]
 
 
+class ScoreWeightsFp32(C.Structure):
+    _fields_ = [
+        ("num_classes", C.c_int32), ("cache_rows", C.c_int32),
+        ("cache_keys6", C.c_void_p * 3), ("bias_term", C.c_void_p * 3), ("label3_t", C.c_void_p * 3),
+        ("colscale", C.c_void_p * 3),
+        ("global_keys6", C.c_void_p), ("global_bias_term", C.c_void_p), ("colscale_global", C.c_void_p),
+        ("dino_keys6", C.c_void_p), ("dino_bias_term", C.c_void_p), ("colscale_dino", C.c_void_p),
+        ("text_w6", C.c_void_p), ("colscale_text", C.c_void_p),
+    ]
+
+
+class ScoreBuffersFp32(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("feat6", "phi", "phi3", "phi_img", "phi_img3", "g6", "d6", "img_logits", "logits",
+                                          "ld_logits")]
+
+
 class FoldedWeights(C.Structure):
     _fields_ = [("num_classes", C.c_int32), ("pair_w", C.c_void_p), ("global_w", C.c_void_p), ("dino_w", C.c_void_p),
                 ("bias_total", C.c_void_p)]
@@ -168,6 +184,8 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_rows_to_bf16": [_P, _L, _I, _I, _I, _P, _P],
     "hoigen_broadcast_image_logits": [_P, _P, _I, _I, _I, _I, _P, _P],
     "hoigen_score_pairs": [C.POINTER(ScoreWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
+    "hoigen_rows_split3": [_P, _L, _I, _I, _I, _I, _P, _P],
+    "hoigen_score_pairs_fp32": [C.POINTER(ScoreWeightsFp32), C.POINTER(ScoreBuffersFp32), _P, _P, _P, _P, _I, _I, _P],
     "hoigen_score_pairs_folded": [C.POINTER(FoldedWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
     "hoigen_ap_11point": [_P, _P, _P, _P, _I, _P, _P, _P],
     "hoigen_prepare_proposals": [_P, _P, _P, _I, _I, _L, _F, _I, _I, _F, _P, _P, _P, _P, _P],

@@ -358,6 +358,39 @@ rows_to_bf16_kernel(const float* __restrict__ in, long ld_in, int rows, int cols
   for (int c = lane; c < cols; c += 32) out[size_t(warp) * cols + c] = __float2bfloat16_rn(src[c] / nrm);
 }
 
+// fp32 rows -> THREE bf16 planes hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid) (8 + 8 + 8 mantissa bits: the sum
+// restores the fp32 value), written side by side along K so that ONE bf16 tensor-core GEMM with fp32 accumulation evaluates
+// the fp32 product (the "3 x bf16 split"; every partial product of two bf16 numbers is exact in fp32):
+//   pattern 6: out row = [hi | hi | hi | mid | mid | lo]   against a packed weight row [hi | mid | lo | hi | mid | hi]
+//              (all cross terms whose weight is >= 2^-16 of the leading one)
+//   pattern 3: out row = [hi | mid | lo]                    against an operand that is EXACT in bf16, tiled three times
+// optional L2 normalisation of the row first (U:960, U:1618).  One warp per row.
+__global__ void __launch_bounds__(256)
+rows_split3_kernel(const float* __restrict__ in, long ld_in, int rows, int cols, int normalize, int pattern,
+                   __nv_bfloat16* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* src = in + size_t(warp) * ld_in;
+  float ss = 0.f;
+  if (normalize)
+    for (int c = lane; c < cols; c += 32) ss += src[c] * src[c];
+  const float nrm = normalize ? sqrtf(warp_sum_h(ss)) : 1.0f;
+  __nv_bfloat16* dst = out + size_t(warp) * cols * pattern;
+  for (int c = lane; c < cols; c += 32) {
+    const float x = normalize ? src[c] / nrm : src[c];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    if (pattern == 6) {
+      dst[c] = hi; dst[cols + c] = hi; dst[2 * cols + c] = hi;
+      dst[3 * cols + c] = mid; dst[4 * cols + c] = mid; dst[5 * cols + c] = lo;
+    } else {
+      dst[c] = hi; dst[cols + c] = mid; dst[2 * cols + c] = lo;
+    }
+  }
+}
+
 // logits[i][:] = img_logits[image(i)][:]   (the per-image global-CLIP + DINO cache terms, U:1115, U:1138)
 __global__ void broadcast_rows_kernel(const float* __restrict__ img_logits, const int* __restrict__ pair_off, int nimg,
                                       int ktot, int C, int ld, float* __restrict__ logits) {
@@ -570,6 +603,17 @@ int hoigen_rows_to_bf16(const float* in, int64_t ld_in, int32_t rows, int32_t co
   KernelScope ks("rows_to_bf16", reinterpret_cast<cudaStream_t>(stream), 0, double(rows) * cols * 6);
   rows_to_bf16_kernel<<<(rows * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       in, ld_in, rows, cols, normalize, reinterpret_cast<__nv_bfloat16*>(out));
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+int hoigen_rows_split3(const float* in, int64_t ld_in, int32_t rows, int32_t cols, int32_t normalize, int32_t pattern,
+                       void* out, hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(in && out && rows > 0 && cols > 0 && (pattern == 3 || pattern == 6), "rows_split3: bad arguments");
+  KernelScope ks("rows_split3", reinterpret_cast<cudaStream_t>(stream), 0, double(rows) * cols * (4 + 2 * pattern));
+  rows_split3_kernel<<<(rows * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, rows, cols, normalize, pattern, reinterpret_cast<__nv_bfloat16*>(out));
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }

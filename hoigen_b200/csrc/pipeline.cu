@@ -138,6 +138,56 @@ int hoigen_score_pairs(const hoigen_score_weights* w, const hoigen_score_buffers
   return HOIGEN_OK;
 }
 
+// fp32-accurate form of hoigen_score_pairs (north_star "fp32 <= 1e-4" for RoI + scoring on identical features): the same
+// chain, every product evaluated through the 3 x bf16 split on the SAME tcgen05 GEMM (operands K-concatenated, fp32
+// accumulation in TMEM), phi kept in fp32.  ~6x the FLOPs of the bf16 path: a parity mode, not the benchmarked one.
+int hoigen_score_pairs_fp32(const hoigen_score_weights_fp32* w, const hoigen_score_buffers_fp32* buf, const float* tokens,
+                            const float* dino_feats, const float* pair_feat_f32, const int32_t* pair_off, int32_t batch,
+                            int32_t ktot, hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(w && buf && tokens && pair_off, "score_pairs_fp32: null argument");
+  HOIGEN_CHECK_ARG(batch > 0 && ktot >= 0, "score_pairs_fp32: bad sizes");
+  HOIGEN_CHECK_ARG(w->num_classes > 0 && w->cache_rows > 0 && (w->cache_rows % 8) == 0,
+                   "score_pairs_fp32: cache_rows must be a positive multiple of 8 (got %d)", w->cache_rows);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int C = w->num_classes, N = w->cache_rows;
+  const int L = buf->ld_logits > 0 ? int(buf->ld_logits) : C;
+  HOIGEN_CHECK_ARG(L >= C, "score_pairs_fp32: ld_logits (%d) < num_classes (%d)", L, C);
+  // ---- per-image terms (U:1133-1138, U:1112-1115) ------------------------------------------------------------
+  HOIGEN_TRY(hoigen_rows_split3(tokens, 197L * 512, batch, 512, 1, 6, buf->g6, s));
+  HOIGEN_TRY(gemm(buf->g6, 3072, w->global_keys6, 3072, batch, N, 3072, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                  buf->phi_img, N, nullptr, 0, s));
+  HOIGEN_TRY(hoigen_rows_split3(buf->phi_img, N, batch, N, 0, 3, buf->phi_img3, s));
+  HOIGEN_TRY(gemm(buf->phi_img3, 3 * N, w->label3_t[2], 3 * N, batch, C, 3 * N, w->global_bias_term, HOIGEN_ACT_NONE,
+                  w->colscale_global, nullptr, 0, buf->img_logits, C, nullptr, 0, s));
+  if (dino_feats) {
+    HOIGEN_CHECK_ARG(w->dino_keys6 != nullptr, "score_pairs_fp32: dino features given but no dino cache");
+    HOIGEN_TRY(hoigen_rows_split3(dino_feats, 2048, batch, 2048, 0, 6, buf->d6, s));
+    HOIGEN_TRY(gemm(buf->d6, 6 * 2048, w->dino_keys6, 6 * 2048, batch, N, 6 * 2048, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                    buf->phi_img, N, nullptr, 0, s));
+    HOIGEN_TRY(hoigen_rows_split3(buf->phi_img, N, batch, N, 0, 3, buf->phi_img3, s));
+    HOIGEN_TRY(gemm(buf->phi_img3, 3 * N, w->label3_t[2], 3 * N, batch, C, 3 * N, w->dino_bias_term, HOIGEN_ACT_NONE,
+                    w->colscale_dino, buf->img_logits, C, buf->img_logits, C, nullptr, 0, s));
+  }
+  if (ktot == 0) return HOIGEN_OK;
+  HOIGEN_CHECK_ARG(pair_feat_f32 != nullptr, "score_pairs_fp32: needs the fp32 pair features");
+  HOIGEN_TRY(hoigen_broadcast_image_logits(buf->img_logits, pair_off, batch, ktot, C, L, buf->logits, s));
+  // ---- pair terms ----------------------------------------------------------------------------------------------
+  HOIGEN_TRY(hoigen_rows_split3(pair_feat_f32, 512, 3 * ktot, 512, 0, 6, buf->feat6, s));
+  for (int x = 0; x < 3; ++x) {
+    const uint16_t* f6 = (const uint16_t*)buf->feat6 + size_t(x) * ktot * 3072;
+    HOIGEN_TRY(gemm(f6, 3072, w->cache_keys6[x], 3072, ktot, N, 3072, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                    buf->phi, N, nullptr, 0, s));
+    HOIGEN_TRY(hoigen_rows_split3(buf->phi, N, ktot, N, 0, 3, buf->phi3, s));
+    HOIGEN_TRY(gemm(buf->phi3, 3 * N, w->label3_t[x], 3 * N, ktot, C, 3 * N, w->bias_term[x], HOIGEN_ACT_NONE, w->colscale[x],
+                    buf->logits, L, buf->logits, L, nullptr, 0, s));
+  }
+  const uint16_t* fu6 = (const uint16_t*)buf->feat6 + size_t(2) * ktot * 3072;
+  HOIGEN_TRY(gemm(fu6, 3072, w->text_w6, 3072, ktot, C, 3072, nullptr, HOIGEN_ACT_NONE, w->colscale_text, buf->logits, L,
+                  buf->logits, L, nullptr, 0, s));
+  return HOIGEN_OK;
+}
+
 int hoigen_score_pairs_folded(const hoigen_folded_weights* w, const hoigen_score_buffers* buf, const float* tokens,
                               const float* dino_feats, const int32_t* pair_off, int32_t batch, int32_t ktot,
                               hoigen_stream_t stream) {

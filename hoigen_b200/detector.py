@@ -113,8 +113,17 @@ class UPT(nn.Module):
                  clip_head: Optional[nn.Module] = None, human_idx: int = 0, box_score_thresh: float = 0.2,
                  min_instances: int = 3, max_instances: int = 15, hyper_lambda: float = 2.8,
                  object_class_to_target_class: Optional[List[List[int]]] = None, dino: bool = True,
-                 clip_global: bool = True, dataset: str = "hicodet", fold_cache: bool = False):
+                 clip_global: bool = True, dataset: str = "hicodet", fold_cache: bool = False,
+                 scoring_precision: str = "bf16"):
         super().__init__()
+        # "bf16" (default, the benchmarked path): bf16 operands, fp32 accumulation, logits within 1e-2 of the reference.
+        # "fp32": RoI features and every cache / text product in fp32-equivalent arithmetic (3 x bf16 split on the same
+        # tcgen05 GEMM, hoigen_score_pairs_fp32): logits within 1e-4 of the reference GIVEN the same encoder features
+        if scoring_precision not in ("bf16", "fp32"):
+            raise ValueError("scoring_precision must be 'bf16' or 'fp32'")
+        if fold_cache and scoring_precision == "fp32":
+            raise ValueError("fold_cache is a bf16 shortcut; use scoring_precision='bf16' with it")
+        self.scoring_precision = scoring_precision
         # opt-in: contract every (linear) cache with its label matrix at pack time — see hoigen_score_pairs_folded
         self.fold_cache = fold_cache
         C_, N = num_classes, cache_rows
@@ -272,6 +281,36 @@ class UPT(nn.Module):
         p["text_w"] = bf(self.adapter_union_weight)
         p["colscale_text"] = f32(self.logit_scale_text.float().expand(C_))
         sw.text_w, sw.colscale_text = p["text_w"].data_ptr(), p["colscale_text"].data_ptr()
+        if self.scoring_precision == "fp32":
+            def split3(t):
+                t = t.detach().to(device=dev, dtype=torch.float32)
+                hi = t.bfloat16()
+                r = t - hi.float()
+                mid = r.bfloat16()
+                return hi, mid, (r - mid.float()).bfloat16()
+
+            def pack6(t):      # weight side of the 3 x bf16 split: [hi | mid | lo | hi | mid | hi] along K
+                hi, mid, lo = split3(t)
+                return torch.cat([hi, mid, lo, hi, mid, hi], dim=1).contiguous()
+
+            sw32 = _cabi.ScoreWeightsFp32()
+            sw32.num_classes, sw32.cache_rows = C_, N
+            for i, X in enumerate(("H", "O", "U")):
+                p[f"keys6_{X}"] = pack6(padr(getattr(self, f"gen_adapter_{X}_weight").detach()))
+                p[f"label3_t_{X}"] = p[f"label_t_{X}"].repeat(1, 3).contiguous()
+                sw32.cache_keys6[i], sw32.label3_t[i] = p[f"keys6_{X}"].data_ptr(), p[f"label3_t_{X}"].data_ptr()
+                sw32.bias_term[i], sw32.colscale[i] = p[f"bias_term_{X}"].data_ptr(), p[f"colscale_{X}"].data_ptr()
+            p["global_keys6"] = (pack6(padr(self.global_cache.detach().t())) if self.clip_global
+                                 else torch.zeros(N, 3072, device=dev, dtype=torch.bfloat16))
+            sw32.global_keys6 = p["global_keys6"].data_ptr()
+            sw32.global_bias_term, sw32.colscale_global = p["global_bias_term"].data_ptr(), p["colscale_global"].data_ptr()
+            if self.dino:
+                p["dino_keys6"] = pack6(padr(self.dino_cache.detach().t()))
+                sw32.dino_keys6 = p["dino_keys6"].data_ptr()
+                sw32.dino_bias_term, sw32.colscale_dino = p["dino_bias_term"].data_ptr(), p["colscale_dino"].data_ptr()
+            p["text_w6"] = pack6(self.adapter_union_weight)
+            sw32.text_w6, sw32.colscale_text = p["text_w6"].data_ptr(), p["colscale_text"].data_ptr()
+            p["fp32"] = sw32
         if self.fold_cache:
             # ((f W^T + b) Y) s / L = f (W^T Y s / L) + (b Y) s / L  for every branch; products in fp32, operands to bf16 once
             fw = _cabi.FoldedWeights()
@@ -421,17 +460,19 @@ class UPT(nn.Module):
     @torch.no_grad()
     def forward_from_proposals(self, images_clip: torch.Tensor, region_props: Sequence[dict],
                                dino_image_features: Optional[torch.Tensor] = None, *,
-                               return_intermediates: bool = False):
+                               return_intermediates: bool = False, encoder_tokens: Optional[torch.Tensor] = None):
         """(B,3,224,224) CLIP images + region proposals (+ L2-normalised DINO features) -> List[dict] as U:1421-1425.
 
         Equivalent to U:1609-1663 with `prepare_region_proposals` outputs as input (humans lead each image)."""
         return self.finish(self.launch_from_proposals(images_clip, region_props, dino_image_features,
-                                                      return_intermediates=return_intermediates))
+                                                      return_intermediates=return_intermediates,
+                                                      encoder_tokens=encoder_tokens))
 
     @torch.no_grad()
     def launch_from_proposals(self, images_clip: torch.Tensor, region_props: Sequence[dict],
                               dino_image_features: Optional[torch.Tensor] = None, *,
-                              return_intermediates: bool = False) -> Optional["_PendingForward"]:
+                              return_intermediates: bool = False,
+                              encoder_tokens: Optional[torch.Tensor] = None) -> Optional["_PendingForward"]:
         """Enqueue the whole forward on the current stream WITHOUT waiting for it; `finish(handle)` does the path's one
         device->host read (per-image triplet offsets) and builds the detections.  A serving loop calls
         launch(batch i+1) before finish(batch i) so the host never leaves the GPU idle; `forward_from_proposals` is
@@ -467,14 +508,17 @@ class UPT(nn.Module):
                 boxes, scores, labels = boxes[idx], scores[idx], labels[idx]
         return self.launch_packed(images_clip, boxes, scores, labels, n_list, nh_list, dino_image_features,
                                   return_intermediates=return_intermediates,
-                                  image_boxes=[rp["boxes"] for rp in region_props])
+                                  image_boxes=[rp["boxes"] for rp in region_props], encoder_tokens=encoder_tokens)
 
     @torch.no_grad()
     def launch_packed(self, images_clip: torch.Tensor, boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor,
                       n_list: Sequence[int], nh_list: Sequence[int], dino_image_features: Optional[torch.Tensor] = None, *,
-                      return_intermediates: bool = False, image_boxes: Optional[Sequence[torch.Tensor]] = None):
+                      return_intermediates: bool = False, image_boxes: Optional[Sequence[torch.Tensor]] = None,
+                      encoder_tokens: Optional[torch.Tensor] = None):
         """`launch_from_proposals` for a caller that already holds the batch's proposals as flat arrays: boxes (sum n, 4),
-        scores (sum n,), labels (sum n,) with image b owning n_list[b] consecutive rows, its nh_list[b] humans first."""
+        scores (sum n,), labels (sum n,) with image b owning n_list[b] consecutive rows, its nh_list[b] humans first.
+        `encoder_tokens` (B*197, 512) fp32, when given, replaces the encoder's output (stage-level parity tests: RoI +
+        scoring on IDENTICAL features, north_star's fp32 <= 1e-4 gate)."""
         dev = images_clip.device
         _cabi.init(dev)
         if self._packed is None:
@@ -518,7 +562,10 @@ class UPT(nn.Module):
                    p["prior_w1t"].data_ptr(), p["prior_b1"].data_ptr(), p["prior_w2t"].data_ptr(), p["prior_b2"].data_ptr(),
                    float(img_w), float(img_h), B, n_max, int(p["object_embedding"].shape[0]), prior.data_ptr(), mask.data_ptr())
         # ---- a4-a7: encoder ------------------------------------------------------------------------------------
-        tokens = self.clip_head.image_encoder.encode_tokens(images_clip, prior, mask)
+        if encoder_tokens is None:
+            tokens = self.clip_head.image_encoder.encode_tokens(images_clip, prior, mask)
+        else:
+            tokens = encoder_tokens.to(device=dev, dtype=torch.float32).contiguous().view(B * TOKENS, 512)
         # ---- a8: DINO features are an input of this path (stock module, as in the reference U:1616-1618) ---------
         if self.dino and dino_image_features is None:
             if self.dino_model is None:
@@ -531,7 +578,8 @@ class UPT(nn.Module):
         single = self._buf("single", ntot * 512, torch.float32, dev)
         union = self._buf("union", ktot * 512, torch.float32, dev)
         pf_bf16 = self._buf("pair_bf16", 3 * ktot * 512, torch.bfloat16, dev)
-        pf_f32 = self._buf("pair_f32", 3 * ktot * 512, torch.float32, dev) if return_intermediates else None
+        fp32_mode = self.scoring_precision == "fp32"
+        pf_f32 = self._buf("pair_f32", 3 * ktot * 512, torch.float32, dev) if (return_intermediates or fp32_mode) else None
         spatial_scale = 1.0 / (img_h / 14.0)                                          # U:1027
         roi_w = self._buf("roi_weights", (ntot + ktot) * 32, torch.float32, dev)
         _cabi.call("hoigen_roi_pair_features", tokens.data_ptr(), boxes.data_ptr(), d_box_off.data_ptr(),
@@ -541,21 +589,35 @@ class UPT(nn.Module):
         N = sw.cache_rows
         ldl = (Cn + 3) // 4 * 4           # padded row pitch: the accumulating GEMM epilogues stay on their float4 path
         logits = self._buf("logits", ktot * ldl, torch.float32, dev)
-        sb = _cabi.ScoreBuffers()
-        sb.pair_feat_bf16 = pf_bf16.data_ptr()
-        sb.phi = self._buf("phi", ktot * N, torch.bfloat16, dev).data_ptr()
-        sb.phi_img = self._buf("phi_img", B * N, torch.bfloat16, dev).data_ptr()
-        sb.g_bf16 = self._buf("g_bf16", B * 512, torch.bfloat16, dev).data_ptr()
-        sb.d_bf16 = self._buf("d_bf16", B * 2048, torch.bfloat16, dev).data_ptr()
-        sb.img_logits = self._buf("img_logits", B * Cn, torch.float32, dev).data_ptr()
-        sb.logits = logits.data_ptr()
-        sb.ld_logits = ldl
-        if self.fold_cache:
-            _cabi.call("hoigen_score_pairs_folded", C.byref(p["folded"]), C.byref(sb), tokens.data_ptr(),
-                       dino_ptr.data_ptr() if dino_ptr is not None else None, d_pair_off.data_ptr(), B, ktot)
+        if fp32_mode:
+            sb32 = _cabi.ScoreBuffersFp32()
+            sb32.feat6 = self._buf("feat6", 3 * ktot * 3072, torch.bfloat16, dev).data_ptr()
+            sb32.phi = self._buf("phi_f32", ktot * N, torch.float32, dev).data_ptr()
+            sb32.phi3 = self._buf("phi3", ktot * 3 * N, torch.bfloat16, dev).data_ptr()
+            sb32.phi_img = self._buf("phi_img_f32", B * N, torch.float32, dev).data_ptr()
+            sb32.phi_img3 = self._buf("phi_img3", B * 3 * N, torch.bfloat16, dev).data_ptr()
+            sb32.g6 = self._buf("g6", B * 3072, torch.bfloat16, dev).data_ptr()
+            sb32.d6 = self._buf("d6", B * 6 * 2048, torch.bfloat16, dev).data_ptr()
+            sb32.img_logits = self._buf("img_logits", B * Cn, torch.float32, dev).data_ptr()
+            sb32.logits, sb32.ld_logits = logits.data_ptr(), ldl
+            _cabi.call("hoigen_score_pairs_fp32", C.byref(p["fp32"]), C.byref(sb32), tokens.data_ptr(),
+                       dino_ptr.data_ptr() if dino_ptr is not None else None, pf_f32.data_ptr(), d_pair_off.data_ptr(), B, ktot)
         else:
-            _cabi.call("hoigen_score_pairs", C.byref(sw), C.byref(sb), tokens.data_ptr(),
-                       dino_ptr.data_ptr() if dino_ptr is not None else None, d_pair_off.data_ptr(), B, ktot)
+            sb = _cabi.ScoreBuffers()
+            sb.pair_feat_bf16 = pf_bf16.data_ptr()
+            sb.phi = self._buf("phi", ktot * N, torch.bfloat16, dev).data_ptr()
+            sb.phi_img = self._buf("phi_img", B * N, torch.bfloat16, dev).data_ptr()
+            sb.g_bf16 = self._buf("g_bf16", B * 512, torch.bfloat16, dev).data_ptr()
+            sb.d_bf16 = self._buf("d_bf16", B * 2048, torch.bfloat16, dev).data_ptr()
+            sb.img_logits = self._buf("img_logits", B * Cn, torch.float32, dev).data_ptr()
+            sb.logits = logits.data_ptr()
+            sb.ld_logits = ldl
+            if self.fold_cache:
+                _cabi.call("hoigen_score_pairs_folded", C.byref(p["folded"]), C.byref(sb), tokens.data_ptr(),
+                           dino_ptr.data_ptr() if dino_ptr is not None else None, d_pair_off.data_ptr(), B, ktot)
+            else:
+                _cabi.call("hoigen_score_pairs", C.byref(sw), C.byref(sb), tokens.data_ptr(),
+                           dino_ptr.data_ptr() if dino_ptr is not None else None, d_pair_off.data_ptr(), B, ktot)
         # ---- a11-a12: prior scores + ordered triplet emission ----------------------------------------------------------
         cap = ktot * p["max_row_len"]
         out_scores = torch.empty(max(cap, 1), device=dev, dtype=torch.float32)

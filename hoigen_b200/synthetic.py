@@ -210,3 +210,132 @@ def make_region_props(batch: int, n_human: int = 8, n_object: int = 8, *, ragged
             no = max(1, n_object - ((2 * b) % 5))
         props.append(make_boxes(seed + b, nh, no))
     return props
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] ("UC zero-shot (uc0) with VAE-synthesized unseen-class union features appended to a 16k x 512
+# cache"): only the cache CONTENT differs from configs[1] (the eval forward never reads `zs` / `zs_type`).  The appended
+# rows follow main_tip_finetune.py:749-824 for the 120 held-out uc0 HOI classes:
+#     z ~ N(0,1) (R,512) -> Generator 512->4096->512 (M:247-261) -> bias
+#     prompt = [SOS emb | ctx (n_ctx,512) + bias | class-name + EOS + padding embs]  (PromptLearner_*.forward, M:106-115)
+#     frozen CLIP text encoder (TextEncoder M:262-279: + positional_embedding, 12 causal blocks, ln_final, EOT row @
+#     text_projection) -> L2 norm -> mlp_net 512->512->512->512 (M:313-324)
+# with random-init modules (seed 3) and synthetic token embeddings (no BPE vocabulary on the GPU box): offline cache
+# construction, torch-CPU, not part of the timed path.  oracle/make_golden.py pins this restatement against the
+# reference's own Generator / TextEncoder / mlp_net classes.
+# ----------------------------------------------------------------------------------------------------------------------
+TEXT_WIDTH, TEXT_LAYERS, TEXT_HEADS, TEXT_CTX = 512, 12, 8, 77
+
+
+def make_text_tower_state(seed: int = 3) -> Dict[str, torch.Tensor]:
+    """Random CLIP text tower (vanilla CLIP names: transformer.resblocks.{i}.*, positional_embedding, ln_final.*,
+    text_projection) with CLIP's initialisation scales."""
+    g = _gen(seed)
+    W, L = TEXT_WIDTH, TEXT_LAYERS
+    sd = {"positional_embedding": _randn(g, TEXT_CTX, W, std=0.01), "text_projection": _randn(g, W, OUT_DIM, std=W ** -0.5),
+          "ln_final.weight": 1.0 + _randn(g, W, std=0.05), "ln_final.bias": _randn(g, W, std=0.05)}
+    proj_std, attn_std, fc_std = (W ** -0.5) * ((2 * L) ** -0.5), W ** -0.5, (2 * W) ** -0.5
+    for i in range(L):
+        b = f"transformer.resblocks.{i}."
+        sd[b + "attn.in_proj_weight"] = _randn(g, 3 * W, W, std=attn_std)
+        sd[b + "attn.in_proj_bias"] = _randn(g, 3 * W, std=0.01)
+        sd[b + "attn.out_proj.weight"] = _randn(g, W, W, std=proj_std)
+        sd[b + "attn.out_proj.bias"] = _randn(g, W, std=0.01)
+        for ln in ("ln_1", "ln_2"):
+            sd[b + ln + ".weight"] = 1.0 + _randn(g, W, std=0.05)
+            sd[b + ln + ".bias"] = _randn(g, W, std=0.05)
+        sd[b + "mlp.c_fc.weight"] = _randn(g, 4 * W, W, std=fc_std)
+        sd[b + "mlp.c_fc.bias"] = _randn(g, 4 * W, std=0.01)
+        sd[b + "mlp.c_proj.weight"] = _randn(g, W, 4 * W, std=proj_std)
+        sd[b + "mlp.c_proj.bias"] = _randn(g, W, std=0.01)
+    return sd
+
+
+def make_generator_state(seed: int = 3, n_ctx: int = 5) -> Dict[str, torch.Tensor]:
+    """Generator (`net.0/2`: N(0,0.02) weights, zero biases = weights_init M:44-51), prompt context `ctx`, mlp_net
+    (`net.0/2/4`, torch Linear-style uniform init)."""
+    g = _gen(seed + 1000)
+    sd = {"gen.net.0.weight": _randn(g, 4096, 512, std=0.02), "gen.net.0.bias": torch.zeros(4096),
+          "gen.net.2.weight": _randn(g, 512, 4096, std=0.02), "gen.net.2.bias": torch.zeros(512),
+          "ctx": _randn(g, n_ctx, 512, std=0.02)}
+    for j in (0, 2, 4):
+        bound = 512 ** -0.5
+        sd[f"mlp.net.{j}.weight"] = (torch.rand(512, 512, generator=g) * 2 - 1) * bound
+        sd[f"mlp.net.{j}.bias"] = (torch.rand(512, generator=g) * 2 - 1) * bound
+    return sd
+
+
+def text_encoder_forward(prompts: torch.Tensor, eot: torch.Tensor, tw: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """TextEncoder.forward (M:270-279) over (R,77,512) prompt embeddings; `eot` (R,) = position of the EOT token."""
+    F = torch.nn.functional
+    R, T, W = prompts.shape
+    hd = W // TEXT_HEADS
+    causal = torch.full((T, T), float("-inf")).triu_(1)
+    x = prompts + tw["positional_embedding"]
+    for i in range(TEXT_LAYERS):
+        b = f"transformer.resblocks.{i}."
+        h = F.layer_norm(x, (W,), tw[b + "ln_1.weight"], tw[b + "ln_1.bias"])
+        q, k, v = F.linear(h, tw[b + "attn.in_proj_weight"], tw[b + "attn.in_proj_bias"]).view(R, T, 3, TEXT_HEADS, hd).unbind(2)
+        att = torch.softmax(torch.einsum("rthd,rshd->rhts", q * hd ** -0.5, k) + causal, dim=-1)
+        o = torch.einsum("rhts,rshd->rthd", att, v).reshape(R, T, W)
+        x = x + F.linear(o, tw[b + "attn.out_proj.weight"], tw[b + "attn.out_proj.bias"])
+        h = F.layer_norm(x, (W,), tw[b + "ln_2.weight"], tw[b + "ln_2.bias"])
+        h = F.linear(h, tw[b + "mlp.c_fc.weight"], tw[b + "mlp.c_fc.bias"])
+        x = x + F.linear(h * torch.sigmoid(1.702 * h), tw[b + "mlp.c_proj.weight"], tw[b + "mlp.c_proj.bias"])
+    x = F.layer_norm(x, (W,), tw["ln_final.weight"], tw["ln_final.bias"])
+    return x[torch.arange(R), eot] @ tw["text_projection"]
+
+
+def generated_rows(targets: torch.Tensor, num_names: int, seed: int = 3, n_ctx: int = 5, chunk: int = 64,
+                   return_inputs: bool = False):
+    """(R,512) generator-synthesised cache rows for class indices `targets` (R,) in [0, num_names)."""
+    F = torch.nn.functional
+    tw, gs = make_text_tower_state(seed), make_generator_state(seed, n_ctx)
+    g = _gen(seed + 2000)
+    # synthetic token embeddings of "X X X X X <name>." : SOS, (ctx), 1-4 name tokens, '.', EOT, padding (zeros row of the
+    # embedding table in real CLIP is a learnt row too; here every position is a random row, as in a random-init model)
+    name_len = 1 + (torch.arange(num_names) % 4)
+    table = _randn(g, num_names, TEXT_CTX, TEXT_WIDTH, std=0.02)
+    eot_pos = 1 + n_ctx + name_len + 1                      # SOS + ctx + name + '.' -> EOT
+    z = _randn(g, targets.numel(), 512)
+    out = []
+    for s0 in range(0, targets.numel(), chunk):
+        t = targets[s0: s0 + chunk]
+        bias = F.linear(F.relu(F.linear(z[s0: s0 + chunk], gs["gen.net.0.weight"], gs["gen.net.0.bias"])),
+                        gs["gen.net.2.weight"], gs["gen.net.2.bias"])
+        emb = table[t]
+        prompts = torch.cat([emb[:, :1], gs["ctx"][None] + bias[:, None, :], emb[:, 1 + n_ctx:]], dim=1)
+        f = text_encoder_forward(prompts, eot_pos[t], tw)
+        f = f / f.norm(dim=-1, keepdim=True)
+        for j in (0, 2):
+            f = F.relu(F.linear(f, gs[f"mlp.net.{j}.weight"], gs[f"mlp.net.{j}.bias"]))
+        out.append(F.linear(f, gs["mlp.net.4.weight"], gs["mlp.net.4.bias"]))
+    rows = torch.cat(out)
+    if return_inputs:
+        return rows, dict(z=z, table=table, eot=eot_pos, text=tw, gen=gs)
+    return rows
+
+
+def make_head_state_uc0(cache_rows: int = 16384, seed: int = 2, gen_seed: int = 3) -> HeadState:
+    """configs[2]: the configs[1] head with N rows whose LAST 120 rows per branch are generator-synthesised features of
+    the 120 held-out uc0 HOI classes (union rows from the 600 HOI prompts, human rows from the single 'person' prompt
+    family, object rows from the 80 object prompts), labelled with each class's verb."""
+    head = make_head_state(117, cache_rows, seed)
+    tabs = load_object_tables()
+    uc0 = tabs["hico_unseen_uc0"]
+    corr = {h: (o, v) for h, o, v in tabs["hico_correspondence"]}
+    R = len(uc0)
+    hoi = torch.tensor(uc0)
+    obj = torch.tensor([corr[h][0] for h in uc0])
+    verb = torch.tensor([corr[h][1] for h in uc0])
+    rows = {"U": generated_rows(hoi, 600, gen_seed, n_ctx=5), "H": generated_rows(obj, 80, gen_seed + 1, n_ctx=4),
+            "O": generated_rows(obj, 80, gen_seed + 2, n_ctx=4)}
+    y = torch.zeros(R, 117)
+    y[torch.arange(R), verb] = 1.0
+    for X in ("U", "H", "O"):
+        head.tensors[f"gen_adapter_{X}_weight"][-R:] = rows[X]
+        head.tensors[f"gen_label_{X}"][-R:] = y
+        head.attrs[f"sample_lens_{X}"] = head.tensors[f"gen_label_{X}"].sum(0)
+    head.attrs["dino_sample_len"] = head.attrs["sample_lens_U"].clone()
+    head.attrs["global_sample_len"] = head.attrs["sample_lens_U"].clone()
+    return head

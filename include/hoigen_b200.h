@@ -257,6 +257,51 @@ HOIGEN_API int hoigen_score_pairs(const hoigen_score_weights* w, const hoigen_sc
                                   const float* dino_feats, const int32_t* pair_off, int32_t batch, int32_t ktot,
                                   hoigen_stream_t stream);
 
+/* fp32 rows -> three bf16 planes (hi, mid, lo; hi + mid + lo == x to 2^-24) laid side by side along K:
+ * pattern 6 = [hi|hi|hi|mid|mid|lo] (multiplied against a weight packed as [hi|mid|lo|hi|mid|hi]: every cross term down
+ * to 2^-16), pattern 3 = [hi|mid|lo] (against an operand exact in bf16, tiled 3x).  out: bf16 (rows, pattern*cols).
+ * normalize != 0: the row is divided by its L2 norm first (U:960, U:1618). */
+HOIGEN_API int hoigen_rows_split3(const float* in, int64_t ld_in, int32_t rows, int32_t cols, int32_t normalize,
+                                  int32_t pattern, void* out, hoigen_stream_t stream);
+
+/* fp32-accurate scoring (north_star: "fp32 <= 1e-4" for RoI + scoring given identical features):
+ * hoigen_score_pairs' chain with every GEMM evaluated through the 3 x bf16 split on the tcgen05 kernel and phi kept in
+ * fp32.  Weights as below are packed once from the fp32 parameters. */
+typedef struct {
+  int32_t num_classes;             /* C */
+  int32_t cache_rows;              /* N (multiple of 8) */
+  const void* cache_keys6[3];      /* bf16 (N, 6*512)   [hi|mid|lo|hi|mid|hi] planes of gen_adapter_{H,O,U}_weight */
+  const float* bias_term[3];       /* f32 (C) */
+  const void* label3_t[3];         /* bf16 (C, 3N)      gen_label_X^T tiled three times along K */
+  const float* colscale[3];        /* f32 (C) */
+  const void* global_keys6;        /* bf16 (N, 6*512) */
+  const float* global_bias_term;   /* f32 (C) */
+  const float* colscale_global;    /* f32 (C) */
+  const void* dino_keys6;          /* bf16 (N, 6*2048), or NULL */
+  const float* dino_bias_term;     /* f32 (C) */
+  const float* colscale_dino;      /* f32 (C) */
+  const void* text_w6;             /* bf16 (C, 6*512) */
+  const float* colscale_text;      /* f32 (C) */
+} hoigen_score_weights_fp32;
+
+typedef struct {                   /* caller-owned workspace */
+  void* feat6;                     /* bf16 [3][Ktot][6*512] */
+  float* phi;                      /* f32  (Ktot, N) */
+  void* phi3;                      /* bf16 (Ktot, 3N) */
+  float* phi_img;                  /* f32  (B, N) */
+  void* phi_img3;                  /* bf16 (B, 3N) */
+  void* g6;                        /* bf16 (B, 6*512) */
+  void* d6;                        /* bf16 (B, 6*2048) */
+  float* img_logits;               /* f32 (B, C) */
+  float* logits;                   /* f32 (Ktot, ld_logits)   OUTPUT */
+  int64_t ld_logits;
+} hoigen_score_buffers_fp32;
+
+/* pair_feat_f32 = the fp32 [3][Ktot][512] output of hoigen_roi_pair_features. */
+HOIGEN_API int hoigen_score_pairs_fp32(const hoigen_score_weights_fp32* w, const hoigen_score_buffers_fp32* buf,
+                                       const float* tokens, const float* dino_feats, const float* pair_feat_f32,
+                                       const int32_t* pair_off, int32_t batch, int32_t ktot, hoigen_stream_t stream);
+
 /* Opt-in "folded cache" form of hoigen_score_pairs.  The reference's cache affinity is linear (no exp: U:1156-1158), so
  * ((f W^T + b) Y) s / L = f (W^T Y s / L) + (b Y) s / L : the host contracts every cache with its label matrix ONCE and
  * the six logit terms of U:1185-1186 become one (C x 1536) matrix for the pair features [H | O | U], one (C x 512) for

@@ -26,35 +26,15 @@ from oracle import ref_harness as RH  # noqa: E402
 
 GOLD = ROOT / "tests" / "golden"
 
-CASES = {
-    # name: (num_classes, dataset, B, n_h, n_o, cache_rows, ragged, box_mode, arg overrides)
-    "hico117_b2": dict(num_classes=117, dataset="hicodet", B=2, n_h=8, n_o=8, N=256, ragged=False, boxes="grid"),
-    "hico117_ragged_b3": dict(num_classes=117, dataset="hicodet", B=3, n_h=6, n_o=7, N=234, ragged=True, boxes="grid"),
-    "hico117_oob_b1": dict(num_classes=117, dataset="hicodet", B=1, n_h=4, n_o=5, N=128, ragged=False, boxes="oob"),
-    "vcoco24_b2": dict(num_classes=24, dataset="vcoco", B=2, n_h=16, n_o=16, N=96, ragged=False, boxes="grid",
-                       args=dict(max_instances=16, cache=True, eval=False)),
-    # BASELINE configs[4]'s classifier: 600 HOI triplets (`generate_feature=False`, class_corr = object -> interaction)
-    "hico600_b2": dict(num_classes=600, dataset="hicodet", B=2, n_h=8, n_o=8, N=600, ragged=False, boxes="grid",
-                       args=dict(generate_feature=False)),
-}
+from oracle.golden_cases import CASES, head_for, props_for  # noqa: E402
 
 
 def make_props(case):
-    props = S.make_region_props(case["B"], case["n_h"], case["n_o"], ragged=case["ragged"])
-    if case["boxes"] == "oob":
-        # boxes partly / mostly outside the 224^2 image: exercises the `< -1 / > size` zeroing rule and clamping
-        g = torch.Generator().manual_seed(4242)
-        for p in props:
-            n = p["boxes"].shape[0]
-            shift = (torch.rand(n, 2, generator=g) - 0.5) * 260.0
-            p["boxes"] = p["boxes"] + torch.cat([shift, shift], dim=1)
-            p["boxes"][0] = torch.tensor([-40.0, -30.0, 20.0, 260.0])
-            p["boxes"][-1] = torch.tensor([100.0, 180.0, 330.0, 300.0])
-    return props
+    return props_for(case)
 
 
 def run_case(name, case, refs):
-    key = (case["num_classes"], case["dataset"])
+    key = (case["num_classes"], case["dataset"], tuple(sorted(case.get("args", {}).items())))
     if key not in refs:
         t0 = time.time()
         over = dict(case.get("args", {}))
@@ -63,8 +43,7 @@ def run_case(name, case, refs):
     upt, pp = refs[key]
     over = case.get("args", {})
     enc = S.make_encoder_state(0)
-    head = S.make_head_state(case["num_classes"], case["N"], seed=2,
-                             max_instances=over.get("max_instances", 15))
+    head = head_for(case)
     RH.load_synthetic_state(upt, enc, head)
     imgs = S.make_images(case["B"], seed=1)
     props = make_props(case)
@@ -118,11 +97,9 @@ def run_case(name, case, refs):
     assert dev["prior"] < 1e-4 and dev["feat_local"] < 2e-3 and dev["logits"] < 1e-3 and dev["scores"] < 1e-4, dev
 
     # ---- fixture (reference outputs only) ----
-    out = dict(
-        prior=r_prior.numpy(), mask=r_mask.numpy(), feat_global=r_glob.numpy(),
-        tokens_local=r_tokens_local.numpy().astype(np.float32),
-        num_images=np.int64(case["B"]),
-    )
+    out = dict(feat_global=r_glob.numpy(), num_images=np.int64(case["B"]))
+    if not case.get("compact"):
+        out.update(prior=r_prior.numpy(), mask=r_mask.numpy(), tokens_local=r_tokens_local.numpy().astype(np.float32))
     for b, (d, lg, pr) in enumerate(zip(ref_dets, r_logits, r_pri)):
         out[f"logits_{b}"] = lg.numpy()
         out[f"pairing_{b}"] = d["pairing"].numpy()
@@ -185,18 +162,71 @@ def roi_align_case():
     return dev
 
 
+def generator_chain_case():
+    """Pin hoigen_b200.synthetic.generated_rows (the restated cache-synthesis chain of main_tip_finetune.py:749-824)
+    against the reference's OWN classes: Generator (M:247-261), PromptLearner_hoi.forward (M:106-115), TextEncoder
+    (M:262-279) over the reference's vanilla CLIP text transformer, mlp_net (M:313-324).  main_tip_finetune.py cannot be
+    imported (missing vcoco_text_label.py, dino/, clipnet/ side imports), so those class definitions are compiled
+    straight from its source with `ast` — unmodified — into an empty namespace."""
+    import ast
+    RH.install_shims()
+    import CLIP.clip.model as vanilla
+    src = (RH.REF / "main_tip_finetune.py").read_text()
+    tree = ast.parse(src)
+    want = {"weights_init", "Generator", "TextEncoder", "mlp_net", "PromptLearner_hoi"}
+    body = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name in want]
+    assert {n.name for n in body} == want
+    ns = {"torch": torch, "nn": torch.nn}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "main_tip_finetune.py", "exec"), ns)
+
+    targets = torch.tensor([0, 7, 7, 133, 599, 42, 318, 5])
+    rows, inp = S.generated_rows(targets, 600, seed=3, n_ctx=5, return_inputs=True)
+    torch.manual_seed(0)
+    clip_model = vanilla.CLIP(512, 224, 12, 768, 16, 77, 49408, 512, 8, 12)
+    missing, unexpected = clip_model.load_state_dict(inp["text"], strict=False)
+    assert not unexpected and all(not k.startswith(("transformer.", "ln_final", "text_projection", "positional_embedding"))
+                                  for k in missing)
+    gen = ns["Generator"]()
+    gen.load_state_dict({k[len("gen."):]: v for k, v in inp["gen"].items() if k.startswith("gen.")})
+    mlp = ns["mlp_net"](512, 512, 512)
+    mlp.load_state_dict({k[len("mlp."):]: v for k, v in inp["gen"].items() if k.startswith("mlp.")})
+    enc = ns["TextEncoder"](clip_model)
+    pl = ns["PromptLearner_hoi"].__new__(ns["PromptLearner_hoi"])     # its __init__ needs the BPE tokenizer; forward does not
+    torch.nn.Module.__init__(pl)
+    pl.ctx = torch.nn.Parameter(inp["gen"]["ctx"])
+    pl.register_buffer("token_prefix", inp["table"][:, :1])
+    pl.register_buffer("token_suffix", inp["table"][:, 1 + 5:])
+    tokenized = torch.zeros(600, 77, dtype=torch.int64)
+    tokenized[torch.arange(600), inp["eot"]] = 49407                  # argmax picks the EOT position (M:277)
+    with torch.no_grad():
+        bias = gen(inp["z"])
+        f = enc(pl(bias, targets), tokenized[targets])
+        f = f / f.norm(dim=-1, keepdim=True)
+        ref_rows = mlp(f)
+    dev = float((rows - ref_rows).abs().max())
+    print(f"[generator chain] restatement vs reference classes: max abs {dev:.2e} (row norm {float(ref_rows.norm(dim=-1).mean()):.3f})")
+    assert dev < 1e-5
+    return dev
+
+
 def main():
     assert RH.available(), "needs /root/reference"
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     pin = {"torch": torch.__version__, "cases": {}}
+    if (GOLD / "PINNING.json").exists() and sys.argv[1:]:     # a partial run keeps the other cases' records
+        pin = json.load(open(GOLD / "PINNING.json"))
+        pin["torch"] = torch.__version__
     pin["roi_align_vs_torchvision"] = roi_align_case()
     refs = {}
     only = sys.argv[1:] or list(CASES)
     for name in only:
         pin["cases"][name] = run_case(name, CASES[name], refs)
-    if (117, "hicodet") in refs:
-        proposals_case(refs)
+    base = (117, "hicodet", ())
+    if base in refs:
+        proposals_case({(117, "hicodet"): refs[base]})
+    if "hico117_uc0_n16384_b2" in only:
+        pin["generator_chain_vs_reference"] = generator_chain_case()
     with open(GOLD / "PINNING.json", "w") as f:
         json.dump(pin, f, indent=1)
     print("wrote", sorted(p.name for p in GOLD.iterdir()))

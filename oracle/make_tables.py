@@ -6,6 +6,8 @@ Runs only in the builder container (needs /root/reference); the output hoigen_b2
         hicodet/hicodet.py:145-185 over instances_test2015.json['correspondence'] = [hoi, obj, verb] x 600
   - vcoco_object_to_action: vcoco/vcoco.py:153-160 over instances_vcoco_test.json['action_to_object']
         then `list(object_to_action.values())` as main_tip_finetune.py:848 does (objects 1..80 -> rows 0..79).
+  - hico_unseen_uc0: hico_text_label.py:827-840 `hico_unseen_index['uc0']`, the 120 HOI ids the UC zero-shot split
+        (`--zs --zs_type uc0`, BASELINE configs[2]) holds out.
 """
 import json
 import sys
@@ -31,12 +33,18 @@ def main():
         for o in objs:
             if act not in o2a[o]:
                 o2a[o].append(act)
+    ns = {}
+    src = (REF / "hico_text_label.py").read_text()
+    exec(compile(src[src.index("hico_unseen_index = {"):].split("\n}\n")[0] + "\n}\n", "hico_unseen_index", "exec"), ns)
+    uc0 = [int(v) for v in ns["hico_unseen_index"]["uc0"]]
+    assert len(uc0) == 120 and len(set(uc0)) == 120 and max(uc0) < 600
     tables = dict(
         hico_object_to_verb=o2v,
         hico_object_to_interaction=o2i,
         hico_object_n_verb_to_interaction=onv,   # -1 where the reference has None
         hico_correspondence=corr,
         vcoco_object_to_action=list(o2a.values()),
+        hico_unseen_uc0=uc0,
     )
     OUT.parent.mkdir(exist_ok=True)
     with open(OUT, "w") as f:

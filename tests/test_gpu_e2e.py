@@ -27,38 +27,25 @@ def _build(num_classes, N, dev, max_instances=15, **kw):
     return UPT.from_state(enc, head, **kw).to(dev), enc, head
 
 
-def _oob_props(props):
-    g = torch.Generator().manual_seed(4242)
-    for p in props:
-        n = p["boxes"].shape[0]
-        shift = (torch.rand(n, 2, generator=g) - 0.5) * 260.0
-        p["boxes"] = p["boxes"] + torch.cat([shift, shift], dim=1)
-        p["boxes"][0] = torch.tensor([-40.0, -30.0, 20.0, 260.0])
-        p["boxes"][-1] = torch.tensor([100.0, 180.0, 330.0, 300.0])
-    return props
+def _build_case(c, dev, **kw):
+    from hoigen_b200 import synthetic as S
+    from hoigen_b200.detector import UPT
+    from oracle.golden_cases import head_for
+    enc, head = S.make_encoder_state(0), head_for(c)
+    return UPT.from_state(enc, head, **kw).to(dev), enc, head
 
 
-CASES = {
-    "hico117_b2": dict(num_classes=117, B=2, n_h=8, n_o=8, N=256, ragged=False, oob=False),
-    "hico117_ragged_b3": dict(num_classes=117, B=3, n_h=6, n_o=7, N=234, ragged=True, oob=False),
-    "hico117_oob_b1": dict(num_classes=117, B=1, n_h=4, n_o=5, N=128, ragged=False, oob=True),
-    "vcoco24_b2": dict(num_classes=24, B=2, n_h=16, n_o=16, N=96, ragged=False, oob=False, max_instances=16),
-    "hico600_b2": dict(num_classes=600, B=2, n_h=8, n_o=8, N=600, ragged=False, oob=False),
-}
+from oracle.golden_cases import CASES, inputs_for  # noqa: E402
 
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_matches_reference_golden(cuda_device, name):
-    from hoigen_b200 import synthetic as S
     c = CASES[name]
     gold = np.load(f"tests/golden/{name}.npz")
-    m, enc, head = _build(c["num_classes"], c["N"], cuda_device, c.get("max_instances", 15))
-    props = S.make_region_props(c["B"], c["n_h"], c["n_o"], ragged=c["ragged"])
-    if c["oob"]:
-        props = _oob_props(props)
-    imgs = S.make_images(c["B"], seed=1).to(cuda_device)
-    dino = S.make_dino_features(c["B"]).to(cuda_device)
-    dets, inter = m.forward_from_proposals(imgs, _props_to(props, cuda_device), dino, return_intermediates=True)
+    m, enc, head = _build_case(c, cuda_device)
+    imgs, props, dino = inputs_for(c)
+    dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                           return_intermediates=True)
     assert len(dets) == c["B"]
     worst_logit = 0.0
     for b, d in enumerate(dets):
@@ -79,19 +66,17 @@ def test_matches_reference_golden(cuda_device, name):
     assert worst_logit <= LOGIT_TOL, worst_logit
 
 
-@pytest.mark.parametrize("name", ["hico117_b2", "hico117_ragged_b3", "vcoco24_b2"])
+@pytest.mark.parametrize("name", ["hico117_b2", "hico117_ragged_b3", "vcoco24_b2", "hico117_n4096_b4", "hico117_uc0_n16384_b2"])
 def test_folded_cache_matches_reference_golden(cuda_device, name):
     """fold_cache=True (every linear cache contracted with its label matrix at pack time: hoigen_score_pairs_folded) gives
     the reference's detections too — indices bit-exact, logits inside the same 1e-2 bar — without any 4096-wide
     intermediate."""
-    from hoigen_b200 import synthetic as S
     c = CASES[name]
     gold = np.load(f"tests/golden/{name}.npz")
-    m, enc, head = _build(c["num_classes"], c["N"], cuda_device, c.get("max_instances", 15), fold_cache=True)
-    props = S.make_region_props(c["B"], c["n_h"], c["n_o"], ragged=c["ragged"])
-    imgs = S.make_images(c["B"], seed=1).to(cuda_device)
-    dino = S.make_dino_features(c["B"]).to(cuda_device)
-    dets, inter = m.forward_from_proposals(imgs, _props_to(props, cuda_device), dino, return_intermediates=True)
+    m, enc, head = _build_case(c, cuda_device, fold_cache=True)
+    imgs, props, dino = inputs_for(c)
+    dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                           return_intermediates=True)
     worst = 0.0
     for b, d in enumerate(dets):
         for k in ("pairing", "labels", "objects"):
@@ -151,8 +136,50 @@ def test_other_baseline_configs_match_oracle(cuda_device, num_classes, N, n_h, n
     assert worst <= LOGIT_TOL, worst
 
 
+@pytest.mark.parametrize("cfg", ["configs1_b64_n4096", "configs2_uc0_b64_n16384", "configs3_vcoco_b128_k496", "configs4_hico600_b512"])
+def test_benchmarked_sizes_match_oracle(cuda_device, cfg):
+    """Every BASELINE.json configuration at the size bench.py times it (full batch, full cache), against the oracle on the
+    same seeded inputs: indices bit-exact, logits max-abs <= 1e-2.  The oracle sees every image of the batch for configs[1]
+    and [2], and an evenly spread 32-image sample for the two largest batches (images are independent in the reference:
+    U:1111-1207 loops per image; the GPU runs the WHOLE batch, so the M = B*197 tile schedules — CTA-pair tiles, stream-K
+    and split-K — are the benchmarked ones)."""
+    from hoigen_b200 import synthetic as S
+    from hoigen_b200.detector import UPT
+    from oracle import hoi_forward_ref as O
+    spec = {"configs1_b64_n4096": dict(C=117, N=4096, B=64, n_h=8, n_o=8, sample=64, head="plain"),
+            "configs2_uc0_b64_n16384": dict(C=117, N=16384, B=64, n_h=8, n_o=8, sample=64, head="uc0"),
+            "configs3_vcoco_b128_k496": dict(C=24, N=4096, B=128, n_h=16, n_o=16, sample=32, head="plain"),
+            "configs4_hico600_b512": dict(C=600, N=4096, B=512, n_h=8, n_o=8, sample=32, head="plain")}[cfg]
+    enc = S.make_encoder_state(0)
+    head = (S.make_head_state_uc0(spec["N"]) if spec["head"] == "uc0"
+            else S.make_head_state(spec["C"], spec["N"], seed=2, max_instances=16))
+    m = UPT.from_state(enc, head).to(cuda_device)
+    B = spec["B"]
+    props = S.make_region_props(B, spec["n_h"], spec["n_o"], seed=500)
+    imgs = S.make_images(B, seed=501)
+    dino = S.make_dino_features(B, seed=502)
+    dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                           return_intermediates=True)
+    pick = list(range(B)) if spec["sample"] >= B else [round(i * (B - 1) / (spec["sample"] - 1)) for i in range(spec["sample"])]
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    worst, worst_rel = 0.0, 0.0
+    for s0 in range(0, len(pick), 16):                        # oracle in chunks of 16 images (bounded host memory)
+        idx = pick[s0: s0 + 16]
+        o_dets, o_int = O.hoi_forward(imgs[idx], [props[i] for i in idx], dino[idx], enc, head, return_intermediates=True,
+                                      roi_impl="torchvision")
+        for j, b in enumerate(idx):
+            for k in ("pairing", "labels", "objects"):
+                assert torch.equal(dets[b][k].cpu(), o_dets[j][k]), (cfg, b, k)
+            worst = max(worst, (inter["logits"][b].cpu() - o_int["logits"][j]).abs().max().item())
+            rel = ((dets[b]["scores"].cpu() - o_dets[j]["scores"]).abs() / o_dets[j]["scores"].abs().clamp_min(1e-30)).max().item()
+            worst_rel = max(worst_rel, rel)
+    print(f"{cfg}: logits max-abs vs oracle {worst:.3e}, scores max-rel {worst_rel:.3e} over {len(pick)} of {B} images")
+    assert worst <= LOGIT_TOL, worst
+    assert worst_rel <= SCORE_RTOL, worst_rel
+
+
 def test_full_batch_properties(cuda_device):
-    """BASELINE batch size (64 images): size-independent properties instead of the (slow) oracle — K = n_h*(n-1) pairs
+    """BASELINE batch size (64 images), ragged box counts: size-independent properties — K = n_h*(n-1) pairs
     per image in row-major order, labels drawn only from the object's target classes, triplet counts per pair equal
     to the table row length, scores in (0,1), finite, and the batch result equals the same images run in two halves
     (image independence => sharding across GPUs is exact)."""
@@ -217,8 +244,8 @@ def test_launch_ahead_equals_sequential(cuda_device):
                                                      (117, 16384, 8, 8, 64),     # config 3 at full size: 16k x 512 cache
                                                      (600, 4096, 8, 8, 512)])    # config 5 at full size: 600 triplets, batch 512/GPU
 def test_full_size_configs_properties(cuda_device, num_classes, N, n_h, n_o, B):
-    """BASELINE.json configs 3-5 at their full sizes, through size-independent properties (the oracle would take
-    minutes): K = n_h (n-1) pairs per image in row-major order, objects = labels[pairing[1]], verbs only from the
+    """BASELINE.json configs 3-5 at their full sizes with RAGGED box counts, through size-independent properties (the
+    oracle comparison at these sizes is test_benchmarked_sizes_match_oracle): K = n_h (n-1) pairs per image in row-major order, objects = labels[pairing[1]], verbs only from the
     object's target classes, one triplet per (pair, allowed verb), scores finite in (0,1); and a random sample of 4
     images re-run as its own small batch gives the same detections (image independence = exact sharding)."""
     from hoigen_b200 import synthetic as S
@@ -537,3 +564,57 @@ def test_vcoco_forward_slices_92_logit_detr_head(cuda_device):
     assert seen["logits"].shape[-1] == 81
     assert seen["logits"][0, 0].tolist() == [float(i) for i in m.reserve_indices.tolist()]
     assert len(dets) == 2
+
+
+FP32_LOGIT_TOL = 1e-4     # north_star: fp32 <= 1e-4 (RoI + scoring on identical features)
+
+
+@pytest.mark.parametrize("C,N,n_h,n_o", [(117, 4096, 8, 8), (24, 4096, 16, 16), (600, 1024, 8, 8)])
+def test_fp32_mode_roi_and_scoring_given_identical_features(cuda_device, C, N, n_h, n_o):
+    """scoring_precision='fp32' (SURVEY 8d config 2 "fp32 mode for RoI + scoring"): fed the ORACLE's encoder tokens, the
+    fp32 RoIAlign / pair assembly and the 3 x bf16-split cache + text GEMMs reproduce the oracle's logits to 1e-4 — two
+    orders tighter than the bf16 bar — and therefore its scores to 1e-4 relative; indices bit-exact."""
+    from hoigen_b200 import synthetic as S
+    from hoigen_b200.detector import UPT
+    from oracle import hoi_forward_ref as O
+    enc = S.make_encoder_state(0)
+    head = S.make_head_state(C, N, seed=2, max_instances=16)
+    m = UPT.from_state(enc, head, scoring_precision="fp32").to(cuda_device)
+    B = 3
+    props = S.make_region_props(B, n_h, n_o, ragged=True, seed=600)
+    imgs, dino = S.make_images(B, seed=601), S.make_dino_features(B, seed=602)
+    o_dets, o_int = O.hoi_forward(imgs, props, dino, enc, head, return_intermediates=True)
+    dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                           return_intermediates=True, encoder_tokens=o_int["tokens"].reshape(B * 197, 512))
+    worst, worst_rel = 0.0, 0.0
+    for b in range(B):
+        for k in ("pairing", "labels", "objects"):
+            assert torch.equal(dets[b][k].cpu(), o_dets[b][k]), (b, k)
+        worst = max(worst, (inter["logits"][b].cpu() - o_int["logits"][b]).abs().max().item())
+        rel = ((dets[b]["scores"].cpu() - o_dets[b]["scores"]).abs() / o_dets[b]["scores"].abs().clamp_min(1e-30)).max().item()
+        worst_rel = max(worst_rel, rel)
+    print(f"fp32 mode C={C} N={N}: logits max-abs vs oracle {worst:.3e}, scores max-rel {worst_rel:.3e}")
+    assert worst <= FP32_LOGIT_TOL, worst
+    assert worst_rel <= 2e-4, worst_rel
+
+
+def test_fp32_mode_end_to_end_matches_reference_golden(cuda_device):
+    """The fp32 scoring mode behind the whole forward (bf16 encoder): same detections as the reference, logits inside the
+    1e-2 end-to-end bar, and closer to the reference than the bf16 scoring path on the same fixture."""
+    from hoigen_b200 import synthetic as S
+    from hoigen_b200.detector import UPT
+    from oracle.golden_cases import head_for
+    c = CASES["hico117_n4096_b4"]
+    gold = np.load("tests/golden/hico117_n4096_b4.npz")
+    imgs, props, dino = inputs_for(c)
+    errs = {}
+    for mode in ("bf16", "fp32"):
+        m = UPT.from_state(S.make_encoder_state(0), head_for(c), scoring_precision=mode).to(cuda_device)
+        dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                               return_intermediates=True)
+        for b, d in enumerate(dets):
+            for k in ("pairing", "labels", "objects"):
+                assert np.array_equal(d[k].cpu().numpy(), gold[f"{k}_{b}"]), (mode, k)
+        errs[mode] = max(float(np.abs(inter["logits"][b].cpu().numpy() - gold[f"logits_{b}"]).max()) for b in range(c["B"]))
+    print(f"end-to-end logits max-abs vs reference: bf16 scoring {errs['bf16']:.3e}, fp32 scoring {errs['fp32']:.3e}")
+    assert errs["fp32"] <= LOGIT_TOL and errs["bf16"] <= LOGIT_TOL

@@ -228,6 +228,7 @@ def test_attention_matches_sdpa(cuda_device):
     ref = ref.transpose(1, 2).reshape(B * 197, 768)
     err = (out.float() - ref).abs().max().item()
     # P is rounded to bf16 before the PV MMA and the output is bf16: ~2^-8 relative
+    print(f"attention: max-abs err {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
     assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
     assert torch.isfinite(out.float()).all()
 
@@ -300,6 +301,7 @@ def test_adapter_kv_and_block(cuda_device, enc_state):
         ref = O._ln(t + t2, sd[blk + "norm3.weight"], sd[blk + "norm3.bias"]).view(B * 197, 64)
         err = (out.float().cpu() - ref).abs().max().item()
         # bf16 tensor-core operands (weights + activations between the MMAs), fp32 accumulation / softmax / LayerNorm
+        print(f"adapter block (delta={use_delta}): max-abs err {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
         assert err < 4e-2 * max(1.0, ref.abs().max().item()), (use_delta, err)
         ref_up = torch.nn.functional.linear(out.float().cpu(), wus.float())           # from the kernel's own bottleneck
         err_up = (dout[: B * 197].float().cpu() - ref_up).abs().max().item()
@@ -472,3 +474,24 @@ def test_prior_tokens(cuda_device):
                224.0, 224.0, B, n_max, oe.shape[0], prior.data_ptr(), mask.data_ptr())
     assert torch.equal(mask.bool().cpu(), ref_mask)
     assert (prior.cpu() - ref).abs().max().item() < 1e-4       # fp32 MLP, different summation order
+
+
+def test_rows_split3_restores_fp32(cuda_device):
+    """hoigen_rows_split3: hi + mid + lo == x to 2^-24 relative, plane layouts [hi|hi|hi|mid|mid|lo] and [hi|mid|lo], optional
+    L2 normalisation of the row."""
+    from hoigen_b200 import _cabi
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 200, generator=g) * torch.logspace(-3, 3, 37)[:, None]
+    xd = x.to(cuda_device).contiguous()
+    for pattern, normalize in ((6, 0), (3, 0), (6, 1)):
+        out = torch.empty(37, pattern * 200, device=cuda_device, dtype=torch.bfloat16)
+        _cabi.call("hoigen_rows_split3", xd.data_ptr(), 200, 37, 200, normalize, pattern, out.data_ptr())
+        o = out.float().cpu().view(37, pattern, 200)
+        ref = x / x.norm(dim=-1, keepdim=True) if normalize else x
+        if pattern == 6:
+            assert torch.equal(o[:, 0], o[:, 1]) and torch.equal(o[:, 0], o[:, 2]) and torch.equal(o[:, 3], o[:, 4])
+            rec = o[:, 0].double() + o[:, 3].double() + o[:, 5].double()
+        else:
+            rec = o.double().sum(1)
+        rel = ((rec - ref.double()).abs() / ref.abs().double().clamp_min(1e-30)).max().item()
+        assert rel <= (2.0 ** -22 if normalize else 2.0 ** -23), (pattern, normalize, rel)
