@@ -1,28 +1,36 @@
 #!/usr/bin/env python
 """HOI-forward throughput benchmark (BASELINE.json metric: images/sec of the per-image HOI scoring forward).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl b200|reference|reference-gpu]
 
 A "step" is one pass of the hot path (region proposals -> detections: prior tokens, ViT-B/16+InsAdapter encoder,
-RoIAlign/pair assembly, cache+text logits, prior scores + triplet emission) over ONE batch of synthetic images:
-configs[1] of BASELINE.json — HICO-DET 117 verbs, batch 64, 8 human + 8 object boxes (120 pairs/image under the
-reference's pairing rule), 4096x512 caches, bf16 tensor-core path.
+RoIAlign/pair assembly, cache+text logits, prior scores + triplet emission) over ONE batch of synthetic images.  The
+default workload is BASELINE.json configs[1] (SURVEY.md 8d "Config 2"): HICO-DET 117 verbs, batch 64, 8 human + 8
+object boxes (120 pairs/image under the reference's pairing rule), 4096x512 caches, bf16 tensor-core path.  `--config`
+selects the other BASELINE configurations (SURVEY 8d numbering): 3 = uc0 zero-shot 16384-row cache with generator-made
+rows, 4 = V-COCO 24 actions, batch 128, 16h+16o boxes (496 pairs), 5 = 600-triplet classifier, batch 512 per GPU.
 
   value     images/s with inputs resident in HBM (CUDA events; max over ranks; whole job)
-  e2e       same metric through UPT.forward_from_proposals with HOST (pinned) inputs: H2D of the step's images /
+  e2e       same metric through UPT.launch_packed / UPT.finish with HOST (pinned) inputs: H2D of the step's images /
             boxes and D2H of every detection tensor inside the timed region (wall clock between synchronisations)
+  sustained the resident loop again for >= 3 s, with its own clock record (the 20-step value is a burst number)
   roofline  the dominant kernel (tcgen05 GEMM): algorithmic FLOPs of its launches / CUDA-event time, vs the measured
             bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline  the oracle port (reference algorithm, torch-CPU fp32, all host threads) on a bounded sample
+  cpu_baseline        the reference's CPU implementation on a bounded sample: the UNMODIFIED reference staged under
+                      oracle/_ref (`kind: "reference"`), else the oracle port (`kind: "port"`)
+  gpu_torch_baseline  the UNMODIFIED reference on the same B200, same inputs: fp32 as shipped and under
+                      torch.autocast(bf16) (BASELINE configs[1] "vs reference torch path on the same GPU inputs")
+  full_with_dino_r50  the step with the stock torchvision ResNet-50 DINO branch (U:1616-1618) run per step on a side stream
 
-`--impl reference` times the reference's CPU implementation of the path (oracle port; the reference is Python and
-cannot travel to the GPU box) with all host threads on the same workload.
+`--impl reference` times the reference's CPU implementation of the path with all host threads on the same workload;
+`--impl reference-gpu` is the same-GPU torch comparator as a stand-alone run (what gpu_torch_baseline spawns).
 """
 from __future__ import annotations
 
 import argparse
 import gc
 import json
+import math
 import os
 import subprocess
 import sys
@@ -37,24 +45,56 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "hoi_forward_images_per_sec"
 UNIT = "images/s"
-ENC_GFLOP_PER_IMG = 35.875
-BOXES_H, BOXES_O = 8, 8
+
+# SURVEY.md 8d numbering ("Config 2" = BASELINE.json configs[1], the one the metric is quoted on)
+WORKLOADS = {
+    2: dict(name="BASELINE configs[1]: HICO-DET 117 verbs, bf16, batch 64", C=117, N=4096, B=64, nh=8, no=8, head="plain",
+            dataset="hicodet", max_instances=15, ref_args={}),
+    3: dict(name="BASELINE configs[2]: UC zero-shot (uc0), 16384x512 caches ending in generator-synthesised unseen-class rows",
+            C=117, N=16384, B=64, nh=8, no=8, head="uc0", dataset="hicodet", max_instances=15,
+            ref_args=dict(zs=True, zs_type="uc0")),
+    4: dict(name="BASELINE configs[3]: V-COCO 24 actions, batch 128, 16h+16o boxes", C=24, N=4096, B=128, nh=16, no=16,
+            head="plain", dataset="vcoco", max_instances=16, ref_args=dict(max_instances=16, cache=True, eval=False)),
+    5: dict(name="BASELINE configs[4]: 600-triplet HICO classifier, batch 512 per GPU, detection gather", C=600, N=4096, B=512,
+            nh=8, no=8, head="plain", dataset="hicodet", max_instances=15, ref_args=dict(generate_feature=False)),
+}
 
 
-def workload_config(args, world):
+def workload(args):
+    w = dict(WORKLOADS[args.config])
+    if args.batch:
+        w["B"] = args.batch
+    if args.cache_rows:
+        w["N"] = args.cache_rows
+    w["n"] = w["nh"] + w["no"]
+    w["K"] = w["nh"] * (w["n"] - 1)
+    return w
+
+
+def flops_per_image(w):
+    """SURVEY.md 8d algorithmic FLOPs: encoder (35.875 GFLOP with 16 prior tokens; the adapter's cross-attention and K/V
+    projection scale with the token count) and the scoring chain."""
+    n, K, N, C = w["n"], w["K"], w["N"], w["C"]
+    enc = 35.875e9 + 12 * (2 * 2 * 197 * 64 * (n - 16) + 2 * 64 * 128 * (n - 16))
+    score = 3 * 2 * K * 512 * N + 3 * 2 * K * N * C + 2 * K * 512 * C + (2 * 512 * N + 2 * N * C) + (2 * 2048 * N + 2 * N * C)
+    return enc, score
+
+
+def workload_config(args, world, w):
     return {
-        "workload": "HICO-DET HOI scoring forward (BASELINE configs[1]): ViT-B/16+InsAdapter 224^2, 117 verbs, "
-                    f"{BOXES_H}h+{BOXES_O}o boxes = 120 pairs/img, {args.cache_rows}x512 caches (H,O,U,global,DINO) + text",
-        "batch_per_gpu": args.batch, "global_batch": args.batch * world, "pairs_per_image": BOXES_H * (BOXES_H + BOXES_O - 1),
-        "cache_rows": args.cache_rows, "num_classes": 117, "parallelism": f"image-sharded dp{world}",
-        "l2": f"inputs rotate over {args.rotate} distinct batches ({args.rotate * args.batch * 3 * 224 * 224 * 4 / 1e6:.0f} MB "
+        "workload": f"{w['name']}: ViT-B/16+InsAdapter 224^2, {w['C']} classes, {w['nh']}h+{w['no']}o boxes = {w['K']} pairs/img, "
+                    f"{w['N']}x512 caches (H,O,U,global,DINO) + text",
+        "survey_config": args.config, "batch_per_gpu": w["B"], "global_batch": w["B"] * world, "pairs_per_image": w["K"],
+        "cache_rows": w["N"], "num_classes": w["C"], "parallelism": f"image-sharded dp{world}",
+        "l2": f"inputs rotate over {args.rotate} distinct batches ({args.rotate * w['B'] * 3 * 224 * 224 * 4 / 1e6:.0f} MB "
               "> 126 MB L2); weights + activations per step >> L2",
-        "dino_features": "supplied as input (SURVEY.md 8 row a8: stock ResNet-50 is outside the path)",
+        "dino_features": "supplied as input (SURVEY.md 8 row a8: stock ResNet-50 is outside the path); full_with_dino_r50 "
+                         "reports the step with the stock R50 run per step",
         "batches_in_flight": (f"{getattr(args, 'streams', 1)} (consecutive steps alternate over {getattr(args, 'streams', 1)} CUDA streams and "
                               "overlap on the GPU; kernel_breakdown / roofline are single-stream per-launch times)"),
         "collective": ("none (single GPU)" if world == 1 else
-                       ("one NCCL all-gather of the sweep's accumulated detections, inside each timed region"
-                        if getattr(args, "gather_every", 0) == 0 else "one NCCL all-gather of the step's detections per step")),
+                       f"NCCL all-gather of the detections in the compact wire format, one chunk every {args.gather_every} steps on a "
+                       "side stream, drained inside each timed region"),
     }
 
 
@@ -70,6 +110,7 @@ class ClockSampler:
     def __init__(self, index: int, period_s: float = 0.01):
         self.index, self.period = index, period_s
         self.sm, self.mx, self.reasons, self.stop_flag, self.thread, self.source = [], [], set(), False, None, None
+        self.power = []
         self.active = False     # samples are kept only while a timed region is running
 
     def _visible_index(self):
@@ -104,6 +145,7 @@ class ClockSampler:
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(float(nv.nvmlDeviceGetPowerUsage(self.h)) / 1e3)
                 bits = int(get_reasons(self.h))
                 for name, _attr, bit in self._REASONS:
                     if bits & bit:
@@ -131,67 +173,177 @@ class ClockSampler:
                 pass
             time.sleep(1.0)
 
+    def snapshot(self, reset: bool = True):
+        """Summary of the samples taken since the last snapshot."""
+        sm = sorted(self.sm)
+        if not sm:
+            out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0, "source": self.source}
+        else:
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons), "samples": len(sm),
+                   "source": self.source}
+            if self.power:
+                out["power_w_max"] = max(self.power)
+        if reset:
+            self.sm, self.mx, self.power, self.reasons = [], [], [], set()
+        return out
+
     def stop(self):
         self.stop_flag = True
         if self.thread is not None:
             self.thread.join(timeout=15)
-        sm = sorted(self.sm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0, "source": self.source}
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons), "samples": len(sm),
-                "source": self.source}
+        return self.snapshot(reset=False)
 
 
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return (d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("bf16_tflops"), d.get("hbm_gbs"),
+                "measured (MEASURED_PEAKS.json)")
+    return 1400.0, 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# ------------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
-# ------------------------------------------------------------------------------------------------------------------
-def cpu_port_images_per_sec(batch: int, passes: int, cache_rows: int, warmup: int = 1):
+def make_state(w):
     from hoigen_b200 import synthetic as S
-    from oracle import hoi_forward_ref as O
+    enc = S.make_encoder_state(0)
+    head = (S.make_head_state_uc0(w["N"]) if w["head"] == "uc0"
+            else S.make_head_state(w["C"], w["N"], seed=2, max_instances=w["max_instances"]))
+    return enc, head
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference legs: the UNMODIFIED reference (oracle/_ref, staged by __graft_entry__.build()) or the oracle port
+# ------------------------------------------------------------------------------------------------------------------
+def _build_reference(w, force_cpu):
+    from oracle import ref_harness as RH
+    if not RH.available():
+        return None
+    upt, pp = RH.build_reference_upt(w["C"], w["dataset"], force_cpu=force_cpu, **w["ref_args"])
+    enc, head = make_state(w)
+    RH.load_synthetic_state(upt, enc, head)
+    return RH, upt, pp
+
+
+def reference_cpu_images_per_sec(w, batch: int, passes: int, warmup: int = 1):
+    """-> (images/s, ms per pass, threads, kind).  kind 'reference' = the unmodified reference modules run through their
+    own UPT.forward (stub DETR feeding the synthetic boxes through the real prepare_region_proposals); 'port' = the
+    oracle restatement, when oracle/_ref is not staged."""
+    from hoigen_b200 import synthetic as S
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    enc = S.make_encoder_state(0)
-    head = S.make_head_state(117, cache_rows)
     imgs = S.make_images(batch, seed=1)
-    props = S.make_region_props(batch, BOXES_H, BOXES_O)
+    props = S.make_region_props(batch, w["nh"], w["no"])
     dino = S.make_dino_features(batch)
+    built = _build_reference(w, force_cpu=True)
     times = []
+    if built is not None:
+        RH, upt, pp = built
+        kind = "reference"
+        run = lambda: RH.run_reference(upt, pp, imgs, props, dino)
+    else:
+        from oracle import hoi_forward_ref as O
+        enc, head = make_state(w)
+        kind = "port"
+        run = lambda: O.hoi_forward(imgs, props, dino, enc, head, roi_impl="torchvision")
     with torch.no_grad():
         for i in range(warmup + passes):
             t0 = time.perf_counter()
-            O.hoi_forward(imgs, props, dino, enc, head, roi_impl="torchvision")
+            run()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return batch / dt, dt * 1e3, cores
+    return batch / dt, dt * 1e3, cores, kind
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, same workload; each step a
+    bounded sample (one batch of `ref_batch` images).  Rank 0 alone runs it."""
     if rank != 0:
         return 0
-    batch = 8
-    value, ms, cores = cpu_port_images_per_sec(batch, max(args.steps, 1), args.cache_rows, warmup=min(args.warmup, 2))
+    w = workload(args)
+    batch = args.ref_batch
+    value, ms, cores, kind = reference_cpu_images_per_sec(w, batch, max(args.steps, 1), warmup=min(args.warmup, 2))
+    what = ("the UNMODIFIED reference (oracle/_ref: build_detector + UPT.forward, stub DETR -> real prepare_region_proposals)"
+            if kind == "reference" else "the oracle port (oracle/_ref not staged)")
+    cfg = workload_config(args, 1, w)
+    cfg["reference_batch_per_step"] = batch
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (seeded random-init weights, images, boxes)",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"each step = one batch of {batch} images of the same workload through the oracle port "
-                                   "(reference algorithm, torch-CPU fp32 + torchvision roi_align, all host threads)"},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"each step = one batch of {batch} images of the same workload through {what}, torch-CPU fp32, "
+                                   f"{cores} host threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def run_reference_gpu(args):
+    """--impl reference-gpu: the UNMODIFIED reference on cuda:0 with the same inputs — (i) as shipped (fp32, no autocast:
+    U:1612 is commented out), (ii) under torch.autocast(bf16).  CUDA events, whole UPT.forward per step."""
+    w = workload(args)
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "no CUDA device"}))
+        return 0
+    built = _build_reference(w, force_cpu=False)
+    if built is None:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref not staged (run __graft_entry__.build() where /root/reference exists)"}))
+        return 0
+    from hoigen_b200 import synthetic as S
+    RH, upt, pp = built
+    dev = torch.device("cuda:0")
+    upt = upt.to(dev)
+    for name in ("sample_lens_H", "sample_lens_O", "sample_lens_U", "dino_sample_len", "global_sample_len", "object_embedding",
+                 "dino_cache_values", "clip_cache_values", "origin_text_embeddings"):
+        t = getattr(upt, name, None)
+        if torch.is_tensor(t):
+            setattr(upt, name, t.to(dev))
+    B = min(w["B"], args.ref_gpu_batch)
+    imgs = S.make_images(B, seed=1).to(dev)
+    props = [{k: v.to(dev) for k, v in p.items()} for p in S.make_region_props(B, w["nh"], w["no"])]
+    dino = S.make_dino_features(B).to(dev)
+    out = {"impl": "reference-gpu", "batch": B, "unit": UNIT,
+           "what": "UNMODIFIED reference UPT.forward (oracle/_ref) on the same B200, same seeded inputs; stub DETR, real "
+                   "prepare_region_proposals / get_prior / image_encoder / compute_roi_embeddings / postprocessing"}
+    for mode in ("fp32_as_shipped", "bf16_autocast"):
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "bf16_autocast" else torch.autocast("cuda", enabled=False)
+        times = []
+        try:
+            with ctx:
+                for i in range(args.warmup + args.steps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    dets = RH.run_reference(upt, pp, imgs, props, dino)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if i >= args.warmup:
+                        times.append(e0.elapsed_time(e1))
+            times.sort()
+            med = times[len(times) // 2]
+            out[mode] = {"value": B / (med * 1e-3), "ms_per_step": med, "steps": len(times),
+                         "triplets": int(sum(d["scores"].numel() for d in dets))}
+        except Exception as e:   # reported, not fatal: this leg is a comparator
+            out[mode] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    print(json.dumps(out))
+    return 0
+
+
+def spawn_leg(argv, timeout):
+    """Run a reference leg of this script in its own process (the harness monkey-patches `.cuda()` / chdir()s) and parse the
+    single JSON line it prints."""
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), *argv], capture_output=True, text=True, timeout=timeout,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": f"no JSON from {' '.join(argv)} (rc {r.returncode}): {r.stderr[-300:]}"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -201,7 +353,7 @@ def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from hoigen_b200 import _cabi, synthetic as S
     from hoigen_b200.detector import UPT
-    from hoigen_b200.gather import gather_packed, gather_packed_begin, gather_packed_end, merge_packed
+    from hoigen_b200.gather import SweepExchange
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
@@ -215,59 +367,72 @@ def run_b200(args, rank, world, local_rank):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _cabi.init(dev)
-    B = args.batch
-    model = UPT.from_state(S.make_encoder_state(0), S.make_head_state(117, args.cache_rows)).to(dev)
-    model.pack_weights()
+    w = workload(args)
+    B, NH, NO, n_per = w["B"], w["nh"], w["no"], w["n"]
+    enc_state, head_state = make_state(w)
+    model = UPT.from_state(enc_state, head_state).to(dev)
+    p_packed, _ = model.pack_weights()
     model.clip_head.image_encoder.pack_weights()
+    max_row_len = p_packed["max_row_len"]
 
     # ---- rotating input sets: host (pinned) + device resident copies ------------------------------------------------
     R = args.rotate
-    host_imgs, host_props, host_dino = [], [], []
+    host_imgs, host_packed, host_dino = [], [], []
     for r in range(R):
         host_imgs.append(S.make_images(B, seed=1000 * rank + r + 1).pin_memory())
-        props = [S.make_boxes(1000 * rank + 64 * r + b, BOXES_H, BOXES_O) for b in range(B)]
-        host_props.append([{k: v.pin_memory() for k, v in p.items()} for p in props])
+        props = [S.make_boxes(1000 * rank + B * r + b, NH, NO) for b in range(B)]
+        # what a host-side caller holds: per-image proposals packed into three pinned arrays
+        host_packed.append((torch.cat([p["boxes"] for p in props]).pin_memory(), torch.cat([p["scores"] for p in props]).pin_memory(),
+                            torch.cat([p["labels"] for p in props]).pin_memory()))
         host_dino.append(S.make_dino_features(B, seed=7 + r).pin_memory())
     dev_imgs = [t.to(dev) for t in host_imgs]
-    dev_props = [[dict({k: v.to(dev) for k, v in p.items()}, n_human=BOXES_H) for p in ps] for ps in host_props]
+    dev_packed = [tuple(t.to(dev) for t in hp) for hp in host_packed]
     dev_dino = [t.to(dev) for t in host_dino]
+    n_list, nh_list = [n_per] * B, [NH] * B
 
     # consecutive steps alternate over `--streams` CUDA streams: the latency-bound head / prologue kernels of one batch
     # then overlap the GEMMs of the next instead of leaving most SMs idle
     streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else [torch.cuda.current_stream(dev)]
 
+    # optional stock DINO ResNet-50 (U:1616-1618) on a side stream, for the "full" figure
+    dino_state = {"model": None, "stream": torch.cuda.Stream(device=dev), "autocast": False}
+
+    def dino_features_for(r, compute_stream):
+        if dino_state["model"] is None:
+            return dev_dino[r]
+        ds = dino_state["stream"]
+        with torch.cuda.stream(ds), torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dino_state["autocast"]):
+            x = dev_imgs[r]
+            if dino_state["autocast"]:
+                x = x.contiguous(memory_format=torch.channels_last)
+            f = dino_state["model"](x).float()
+            f = f / f.norm(dim=-1, keepdim=True)                  # U:1618
+        compute_stream.wait_stream(ds)
+        return f
+
     def launch_resident(i):
         r = i % R
-        with torch.cuda.stream(streams[i % len(streams)]):
-            return model.launch_from_proposals(dev_imgs[r], dev_props[r], dev_dino[r])
+        st = streams[i % len(streams)]
+        with torch.cuda.stream(st):
+            bx, sc, lb = dev_packed[r]
+            return model.launch_packed(dev_imgs[r], bx, sc, lb, n_list, nh_list, dino_features_for(r, st))
+
+    # The path's one collective (N > 1): every rank ends up with every rank's detections.  The sweep's detections travel in
+    # the compact wire format (9 B per triplet instead of 36), one fixed-capacity chunk every `--gather-every` steps on a
+    # side stream, no host synchronisation inside the loop; drained (headers read, records widened back to int64) inside
+    # the timed region.
+    exchange = SweepExchange(world, B, w["K"] * max_row_len * B, n_per * B, dev, chunk_steps=args.gather_every) if world > 1 else None
 
     def finish_resident(pend):
         dets = model.finish(pend)          # the path's device->host read (triplet offsets) + detection views
-        if world > 1:
-            exchange(dets.packed)
+        if exchange is not None:
+            exchange.add(dets.packed, pend)
         return dets
 
-    # The path's one collective: every rank ends up with every rank's detections.  One fixed-capacity all-gather per
-    # step, enqueued without a host sync and read back one step later (so it never stalls the step launched ahead).
-    gather_cap = B * 120 * 30 * 36 + B * (BOXES_H + BOXES_O) * 16
-    pending_gather = []
-
-    sweep = []
-
-    def exchange(packed):
-        if args.gather_every == 0:         # default: accumulate on the device, ONE exchange per sweep (= timed region)
-            sweep.append(packed)
-            return
-        pending_gather.append(gather_packed_begin(packed, gather_cap, B))
-        if len(pending_gather) > 1:
-            gather_packed_end(pending_gather.pop(0))
-
     def drain_exchanges():
-        while pending_gather:
-            gather_packed_end(pending_gather.pop(0))
-        if sweep:
-            gather_packed(merge_packed(sweep))
-            sweep.clear()
+        if exchange is not None:
+            return exchange.finish()
+        return None
 
     def run_resident(first, count):
         """`count` complete steps; step i+1 is enqueued before step i is waited for, so the host's per-step work (layout,
@@ -288,19 +453,24 @@ def run_b200(args, rank, world, local_rank):
                       file=sys.stderr, flush=True)
         return dets
 
+    def timed_resident(first, count):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for st in streams:
+            st.wait_event(e0)
+        dets = run_resident(first, count)
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        e1.record()
+        return e0, e1, dets
+
     # ---- end-to-end step: HOST (pinned) inputs -> device -> detections -> HOST, H2D of step i+1 overlapped with step i --
     copy_stream = torch.cuda.Stream(device=dev)
-    n_per = BOXES_H + BOXES_O
-    host_packed = []
-    for r in range(R):   # what a host-side caller holds: per-image proposals packed into three pinned arrays
-        host_packed.append((torch.cat([p["boxes"] for p in host_props[r]]).pin_memory(),
-                            torch.cat([p["scores"] for p in host_props[r]]).pin_memory(),
-                            torch.cat([p["labels"] for p in host_props[r]]).pin_memory()))
     NSLOT = 3   # input slots: one being computed on, one launched ahead, one being uploaded
     dev_in = [dict(imgs=torch.empty_like(dev_imgs[0]), boxes=torch.empty(B * n_per, 4, device=dev),
                    scores=torch.empty(B * n_per, device=dev), labels=torch.empty(B * n_per, dtype=torch.int64, device=dev),
                    dino=torch.empty_like(dev_dino[0]), ev=torch.cuda.Event(), free=None) for _ in range(NSLOT)]
-    cap_out = B * 120 * 30
+    cap_out = B * w["K"] * max_row_len
     host_out = [dict(scores=torch.empty(cap_out, dtype=torch.float32).pin_memory(),
                      labels=torch.empty(cap_out, dtype=torch.int64).pin_memory(),
                      objects=torch.empty(cap_out, dtype=torch.int64).pin_memory(),
@@ -325,8 +495,7 @@ def run_b200(args, rank, world, local_rank):
         slot = dev_in[i % NSLOT]
         with torch.cuda.stream(streams[i % len(streams)]):
             torch.cuda.current_stream().wait_event(slot["ev"])
-            pend = model.launch_packed(slot["imgs"], slot["boxes"], slot["scores"], slot["labels"], [n_per] * B, [BOXES_H] * B,
-                                       slot["dino"])
+            pend = model.launch_packed(slot["imgs"], slot["boxes"], slot["scores"], slot["labels"], n_list, nh_list, slot["dino"])
         slot["free"] = pend.done
         return pend
 
@@ -335,8 +504,8 @@ def run_b200(args, rank, world, local_rank):
         step's compute; the host buffer is double-buffered and waited for one step later)."""
         dets = model.finish(pend)
         pk = dets.packed
-        if world > 1:
-            exchange(pk)
+        if exchange is not None:
+            exchange.add(pk, pend)
         m = pk.scores.numel()
         ho = host_out[i % 2]
         if ho["keep"] is not None:
@@ -356,12 +525,8 @@ def run_b200(args, rank, world, local_rank):
         upload (two steps ahead), one launch (one step ahead), one finish + D2H.  Returns the next pending step."""
         m = 0
         trace = os.environ.get("HOIGEN_BENCH_TRACE")
-        evs = []
         for i in range(first, first + count):
             ta = time.perf_counter()
-            if trace:
-                evs.append(torch.cuda.Event(enable_timing=True))
-                evs[-1].record()
             nxt = launch_host(i + 1)
             tb = time.perf_counter()
             m = finish_host(i, pend)
@@ -373,10 +538,6 @@ def run_b200(args, rank, world, local_rank):
                 print(f"[trace-e2e] step {i}: launch {1e3 * (tb - ta):.2f} ms, finish+d2h {1e3 * (tc - tb):.2f} ms, "
                       f"upload {1e3 * (time.perf_counter() - tc):.2f} ms segs {ms_['segment.all.allocated']} "
                       f"gc {[g['collections'] for g in gc.get_stats()]}", file=sys.stderr, flush=True)
-        if trace and len(evs) > 2:
-            torch.cuda.synchronize()
-            print("[trace-e2e] GPU period between step starts (ms): " +
-                  " ".join(f"{evs[k].elapsed_time(evs[k + 1]):.2f}" for k in range(len(evs) - 1)), file=sys.stderr, flush=True)
         return pend, m
 
     def barrier():
@@ -395,27 +556,31 @@ def run_b200(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()                           # NVML is initialised here, outside the timed regions
-    wdets = run_resident(0, args.warmup)
-    if world > 1 and args.gather_every == 0:
-        # warm the sweep-sized exchange too (NCCL channel setup / allocator growth for a K-step payload are one-time costs)
-        gather_packed(merge_packed([wdets.packed] * args.steps))
+    run_resident(0, args.warmup)                 # (N > 1: also warms the exchange — NCCL channel setup, staging buffers)
     barrier()
     _cabi.profile(False)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.active = True
-    e0.record()
-    for st in streams:
-        st.wait_event(e0)
-    dets = run_resident(args.warmup, args.steps)
-    for st in streams:
-        torch.cuda.current_stream().wait_stream(st)
-    e1.record()
+    e0, e1, dets = timed_resident(args.warmup, args.steps)
     barrier()
     clocks.active = False
     launches = _cabi.launch_count()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = world * B / (ms_step * 1e-3)
     triplets = sum(int(d["scores"].numel()) for d in dets[:B])
+    clk = clocks.snapshot() if rank == 0 else None
+
+    # ---- sustained: the same loop for >= args.sustain_s seconds (the 20-step window above is a burst measurement) ---------
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(math.ceil(args.sustain_s * 1e3 / ms_step)))
+        n_sus = (n_sus + args.gather_every - 1) // args.gather_every * args.gather_every
+        clocks.active = True
+        s0, s1, _ = timed_resident(0, n_sus)
+        barrier()
+        clocks.active = False
+        sus_ms = max_over_ranks(s0.elapsed_time(s1) / n_sus)
+        sustained = {"steps": n_sus, "seconds": sus_ms * n_sus * 1e-3, "ms_per_step": sus_ms, "value": world * B / (sus_ms * 1e-3),
+                     "unit": UNIT, "clocks": clocks.snapshot() if rank == 0 else None}
 
     # ---- end-to-end timing with host buffers -----------------------------------------------------------------------------
     for i in range(3):
@@ -425,14 +590,15 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     # The timer starts at a step boundary of the RUNNING pipeline, six untimed steps after that synchronisation: traced
     # (HOIGEN_BENCH_TRACE prints the caching allocator's segment count per step), the allocator grows by two segments on
-    # the third launch after any full device synchronisation, whatever the warm-up length (step 11 after an 8-step
-    # warm-up, step 27 after 24), and that cudaMalloc costs 1.5 ms normally but 20-160 ms in about one run in six - all of
-    # it billed to this lockstep loop (one step in flight).  Starting without a synchronisation means step w_e2e + 6,
-    # launched before t0, may still be running when the window opens, so the window holds AT LEAST `steps` whole steps of
-    # device work plus all their copies (the final barrier drains the step launched ahead): a pessimistic boundary.
+    # the third launch after any full device synchronisation, whatever the warm-up length, and that cudaMalloc costs 1.5 ms
+    # normally but 20-160 ms in about one run in six - all of it billed to this lockstep loop (one step in flight).
+    # Starting without a synchronisation means step w_e2e + 6, launched before t0, may still be running when the window
+    # opens, so the window holds AT LEAST `steps` whole steps of device work plus all their copies (the final barrier
+    # drains the step launched ahead): a pessimistic boundary.
     pend, m_out = run_host(w_e2e, 6, pend)
     w_e2e += 6
-    sweep.clear()                                # the timed sweep exchanges its own `steps` steps of detections, no warm-up ones
+    if exchange is not None:
+        exchange.finish()                        # the timed sweep exchanges its own `steps` steps of detections
     clocks.active = True
     t0 = time.perf_counter()
     # K uploads, K launches, K finishes + K D2H copies; the barrier below waits for the last launched step and the copies
@@ -443,47 +609,28 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     clocks.active = False
-    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        clocks.snapshot()
     h2d = host_imgs[0].numel() * 4 + sum(t.numel() * t.element_size() for t in host_packed[0]) + host_dino[0].numel() * 4
     d2h = m_out * (4 + 8 + 8 + 16) + (B + 1) * 4
+    model.finish(pend)
+    torch.cuda.synchronize()
 
-    if os.environ.get("HOIGEN_BENCH_TRACE"):     # diagnostics: the same per-kernel profile, but of end-to-end steps
+    def quick_resident(steps):
+        run_resident(0, 3)
         torch.cuda.synchronize()
-        _cabi.profile(True)
-        pend, _ = run_host(w_e2e + args.steps, 2, pend)
+        f0, f1, _ = timed_resident(3, steps)
         torch.cuda.synchronize()
-        recs_e = _cabi.profile_read()
-        _cabi.profile(False)
-        agg_e = {}
-        for tag, ms, fl, by, _t0 in recs_e:
-            a = agg_e.setdefault(tag, [0, 0.0])
-            a[0] += 1; a[1] += ms
-        print("[trace-e2e] profiled kernels: %d launches, sum %.3f ms; per tag ms: %s" % (
-            len(recs_e), sum(a[1] for a in agg_e.values()),
-            " ".join(f"{t}={a[1] / a[0] * 1e3:.1f}us" for t, a in sorted(agg_e.items(), key=lambda kv: -kv[1][1])[:10])),
-            file=sys.stderr, flush=True)
-        ts = sorted((t0, ms, tag) for tag, ms, fl, by, t0 in recs_e)
-        gaps = sorted(((ts[k + 1][0] - (ts[k][0] + ts[k][1])), ts[k][2], ts[k + 1][2]) for k in range(len(ts) - 1))[-6:]
-        print("[trace-e2e] largest gaps (ms, after, before): " + "; ".join(f"{g:.3f} {a}->{b}" for g, a, b in gaps), file=sys.stderr, flush=True)
+        return f0.elapsed_time(f1) / steps
+
     # ---- opt-in folded-cache variant, reported NEXT TO the headline (which always runs the unfolded cache GEMMs) -------------
     folded = None
-    if world == 1:
-        torch.cuda.synchronize()
+    full_dino = None
+    if world == 1 and not args.no_variants:
         model.fold_cache = True
         model.invalidate_packed()
         model.pack_weights()
-        run_resident(0, 3)
-        torch.cuda.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for st in streams:
-            st.wait_event(f0)
-        run_resident(3, args.steps)
-        for st in streams:
-            torch.cuda.current_stream().wait_stream(st)
-        f1.record()
-        torch.cuda.synchronize()
-        fms = f0.elapsed_time(f1) / args.steps
+        fms = quick_resident(args.steps)
         folded = {"ms_per_step": fms, "value": B / (fms * 1e-3), "unit": UNIT,
                   "note": "UPT(fold_cache=True): every linear cache contracted with its label matrix at pack time "
                           "(hoigen_score_pairs_folded); same detections (tests), NOT used for value / e2e above"}
@@ -491,17 +638,38 @@ def run_b200(args, rank, world, local_rank):
         model.invalidate_packed()
         model.pack_weights()
         torch.cuda.synchronize()
+        # ---- "full" step: the stock DINO ResNet-50 (U:1616-1618) run per step on a side stream --------------------------------
+        try:
+            import torchvision
+            r50 = torchvision.models.resnet50(weights=None)
+            r50.fc = torch.nn.Identity()
+            r50 = r50.to(dev).eval()
+            full_dino = {"what": "same resident loop, DINO features computed per step by the stock torchvision ResNet-50 "
+                                 "(fc = Identity, random init) + L2 normalise on a side stream (U:1616-1618); cuDNN, outside the four "
+                                 "kernel groups (SURVEY 8 row a8)"}
+            for tag, ac in (("stock_fp32", False), ("bf16_channels_last", True)):
+                dino_state.update(model=(r50.to(memory_format=torch.channels_last) if ac else r50), autocast=ac)
+                fms = quick_resident(args.steps)
+                full_dino[tag] = {"ms_per_step": fms, "value": B / (fms * 1e-3), "unit": UNIT}
+            dino_state["model"] = None
+            del r50
+        except Exception as e:
+            full_dino = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+            dino_state["model"] = None
+        torch.cuda.synchronize()
+
     # ---- per-kernel event profile of one step (separate from the timed regions) ---------------------------------------------
     _cabi.profile(True)
-    for i in range(2):
-        model.forward_from_proposals(dev_imgs[i % R], dev_props[i % R], dev_dino[i % R])
+    nprof = 2
+    for i in range(nprof):
+        bx, sc, lb = dev_packed[i % R]
+        model.finish(model.launch_packed(dev_imgs[i % R], bx, sc, lb, n_list, nh_list, dev_dino[i % R]))
     recs = _cabi.profile_read()
     _cabi.profile(False)
     agg = {}
     for tag, ms, fl, by, _t0 in recs:
         a = agg.setdefault(tag, [0, 0.0, 0.0, 0.0])
         a[0] += 1; a[1] += ms; a[2] += fl; a[3] += by
-    nprof = 2
     # the dominant kernel = the CTA-pair GEMM (tags gemm2_*: every encoder GEMM + the cache-affinity GEMMs)
     gemm_ms = sum(a[1] for t, a in agg.items() if t.startswith("gemm2_"))
     gemm_fl = sum(a[2] for t, a in agg.items() if t.startswith("gemm2_"))
@@ -509,15 +677,20 @@ def run_b200(args, rank, world, local_rank):
     allg_ms = sum(a[1] for t, a in agg.items() if t.startswith("gemm"))
     allg_fl = sum(a[2] for t, a in agg.items() if t.startswith("gemm"))
     total_ms = sum(a[1] for a in agg.values())
-    peak_tf, peak_hbm, peak_src = peaks()
+    peak_sus, peak_burst, peak_hbm, peak_src = peaks()
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
     tr = ROOT / "profiles" / "ncu_gemm_traffic.json"
     if tr.exists():
         traffic = json.loads(tr.read_text()).get("dram_bytes_per_launch")
+    # the per-launch events come from a short single-stream profile pass at burst clocks: the like-for-like denominator is
+    # the burst peak; the fraction of the sustained peak is printed beside it
     roofline = {"bound": "tensor", "kernel": "hoigen::gemm2_bf16_kernel (CTA-pair tcgen05/TMA GEMM; all its launches of a step)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "peak_source": peak_src, "traffic": traffic, "launches_per_step": gemm_n / nprof,
+                "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst if peak_burst else None,
+                "peak_source": peak_src + ", bf16 burst (kernel timed alone, per launch)",
+                "frac_of_sustained_peak": achieved / peak_sus if peak_sus else None, "peak_sustained": peak_sus,
+                "traffic": traffic, "traffic_source": "profiles/ncu_gemm_traffic.json (ncu --set full capture, mean over the GEMM launches of a layer)",
+                "launches_per_step": gemm_n / nprof,
                 "avg_launch_us": gemm_ms / gemm_n * 1e3 if gemm_n else None,
                 "algorithmic_gflop_per_launch": gemm_fl / gemm_n / 1e9 if gemm_n else None,
                 "share_of_step": gemm_ms / total_ms if total_ms else None,
@@ -531,35 +704,47 @@ def run_b200(args, rank, world, local_rank):
         if world > 1:
             dist.destroy_process_group()
         return 0
+    clocks.stop()
+    cfg_flag = ["--config", str(args.config)] + (["--batch", str(args.batch)] if args.batch else []) + \
+               (["--cache-rows", str(args.cache_rows)] if args.cache_rows else [])
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_passes = 24                                  # ~12 s of CPU work at ~17 images/s
-        v, ms, cores = cpu_port_images_per_sec(8, cpu_passes, args.cache_rows)
-        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"{cpu_passes} timed passes (1 warm-up) of one batch of 8 images of the same workload "
-                              f"({cpu_passes * 8} images, ~{cpu_passes * 8 / max(v, 1e-9):.0f} s) through the oracle port "
-                              "(torch-CPU fp32 + torchvision roi_align, all host threads)"}
+        # ~10-25 s of CPU work on the box's host cores, in its own process (the harness neutralises the reference's
+        # hard-coded .cuda() calls there)
+        ref = spawn_leg(["--impl", "reference", "--steps", "24" if args.config == 2 else "6", "--warmup", "1",
+                         "--ref-batch", "8", *cfg_flag], timeout=900)
+        cpu_base = ref.get("cpu_baseline") or {"unavailable": ref.get("unavailable", "no cpu_baseline in the reference leg")}
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline:
+        torch.cuda.empty_cache()
+        gpu_base = spawn_leg(["--impl", "reference-gpu", "--steps", "5", "--warmup", "2", *cfg_flag], timeout=900)
+    enc_fl, score_fl = flops_per_image(w)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (seeded random-init ViT-B/16+adapter weights, randn images, NMS-safe grid boxes)",
-        "config": workload_config(args, world),
+        "config": workload_config(args, world, w),
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clk,
+        "sustained": sustained,
         "roofline": roofline,
         "cpu_baseline": cpu_base,
-        "encoder_tflops_effective": ENC_GFLOP_PER_IMG * B / (ms_step * 1e-3) / 1e3,
+        "gpu_torch_baseline": gpu_base,
+        "encoder_tflops_effective": enc_fl * B / (ms_step * 1e-3) / 1e12,
+        "encoder_frac_of_sustained_peak": enc_fl * B / (ms_step * 1e-3) / 1e12 / peak_sus if peak_sus else None,
+        "algorithmic_gflop_per_image": {"encoder": enc_fl / 1e9, "scoring": score_fl / 1e9},
         "triplets_per_step": triplets,
         "kernel_breakdown": breakdown,
         "folded_cache_variant": folded,
+        "full_with_dino_r50": full_dino,
     }
     print(json.dumps(line))
     out_dir = ROOT / "gpurun_out"
     if out_dir.exists():
-        (out_dir / f"bench_detail_n{world}.json").write_text(json.dumps(line, indent=1))
-        with open(out_dir / f"bench_timeline_n{world}.txt", "w") as f:   # launch timeline of the profiled steps (gaps = host stalls)
+        (out_dir / f"bench_detail_c{args.config}_n{world}.json").write_text(json.dumps(line, indent=1))
+        with open(out_dir / f"bench_timeline_c{args.config}_n{world}.txt", "w") as f:   # launch timeline of the profiled steps (gaps = host stalls)
             prev_end = 0.0
             for tag, ms, fl, by, t0 in recs:
                 f.write(f"{t0:10.4f} {ms:9.4f} gap={t0 - prev_end:8.4f} {tag}\n")
@@ -574,25 +759,37 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--cache-rows", type=int, default=4096)
-    ap.add_argument("--rotate", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS),
+                    help="SURVEY.md 8d configuration: 2 (default) = BASELINE configs[1]; 3 = uc0 16k cache; 4 = V-COCO batch 128; "
+                         "5 = 600 triplets, batch 512 per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="override the configuration's batch per GPU")
+    ap.add_argument("--cache-rows", type=int, default=0, help="override the configuration's cache rows")
+    ap.add_argument("--rotate", type=int, default=0, help="distinct input batches the steps rotate over (default: enough to exceed L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the folded-cache and full-with-DINO side measurements")
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the sustained block in seconds (0 = skip)")
+    ap.add_argument("--ref-batch", type=int, default=8, help="--impl reference: images per step (bounded CPU sample)")
+    ap.add_argument("--ref-gpu-batch", type=int, default=64, help="--impl reference-gpu: images per step (capped at the config's batch)")
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams that consecutive steps alternate over: 2 (default) = two batches overlap on the GPU, "
                          "1 = strictly one batch at a time")
-    ap.add_argument("--gather-every", type=int, default=0,
-                    help="N>1 only. 0 (default): detections accumulate on the device and are exchanged with ONE all-gather per "
-                         "sweep (= per timed region, inside it); 1: one non-blocking fixed-capacity all-gather per step")
+    ap.add_argument("--gather-every", type=int, default=4,
+                    help="N>1 only: steps per exchanged chunk of detections (one non-blocking all-gather per chunk on a side stream)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.rotate <= 0:
+        b = args.batch or WORKLOADS[args.config]["B"]
+        args.rotate = max(2, int(math.ceil(140e6 / (b * 3 * 224 * 224 * 4))))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.impl == "reference-gpu":
+        return run_reference_gpu(args) if rank == 0 else 0
     return run_b200(args, rank, world, local_rank)
 
 

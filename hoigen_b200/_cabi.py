@@ -60,6 +60,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = sig
+    lib.hoigen_wire_record_bytes.restype = C.c_int64
+    lib.hoigen_wire_record_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int64]
     lib.hoigen_launch_count.restype = C.c_longlong
     lib.hoigen_profile_enable.argtypes = [C.c_int]
     lib.hoigen_profile_read.restype = C.c_longlong
@@ -190,10 +192,12 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_ap_11point": [_P, _P, _P, _P, _I, _P, _P, _P],
     "hoigen_prepare_proposals": [_P, _P, _P, _I, _I, _L, _F, _I, _I, _F, _P, _P, _P, _P, _P],
     "hoigen_associate_pairs": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P],
+    "hoigen_pack_wire": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P, _P],
+    "hoigen_unpack_wire": [_P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P],
     "hoigen_emit_triplets": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
 }
 
-EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", "hoigen_launch_count",
+EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", "hoigen_launch_count", "hoigen_wire_record_bytes",
                     "hoigen_profile_enable", "hoigen_profile_reset", "hoigen_profile_read", *_SIGNATURES.keys()]
 
 

@@ -643,6 +643,7 @@ class UPT(nn.Module):
             image_boxes = boxes.split(n_list)
         pend.__dict__.update(B=B, img_h=img_h, img_w=img_w, dev=dev, image_boxes=image_boxes, boxes=boxes,
                              box_off=box_off, pair_off=pair_off, ktot=ktot, host_off=host_off, done=done, img_off=img_off,
+                             d_box_off=d_box_off,
                              stage=stage, generation=stage.generation, ldl=ldl,
                              out=(out_scores, out_labels, out_objects, out_pairing), prior=prior, mask=mask, tokens=tokens,
                              logits=logits, pf_f32=pf_f32, return_intermediates=return_intermediates)
@@ -675,6 +676,8 @@ class UPT(nn.Module):
                                              pairing=out_pairing[: 2 * mtot], boxes=boxes, triplet_off=offs, box_off=box_off,
                                              size=(img_h, img_w))
         detections.packed.done = pend.done     # recorded after the last kernel of this forward (for copies on other streams)
+        # the same offsets on the device (int32 B+1 each): consumers that stay on the GPU (the wire-format gather) read these
+        detections.packed.img_off_dev, detections.packed.box_off_dev = pend.img_off, pend.d_box_off
         if pend.return_intermediates:
             inter = dict(prior=pend.prior, mask=pend.mask.bool(), tokens=pend.tokens.view(B, TOKENS, 512),
                          logits=[pend.logits[: ktot * pend.ldl].view(ktot, pend.ldl)[pair_off[b]: pair_off[b + 1], :Cn]

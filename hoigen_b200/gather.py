@@ -270,3 +270,233 @@ def gather_detections(dets: Sequence[Optional[dict]], group=None) -> List[dict]:
         nb, nf, ni = all_sizes[r].tolist()
         out.extend(unpack_detections(bufs[0][r][:nb], bufs[1][r][:nf], bufs[2][r][:ni]))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Sweep exchange in the compact wire format (include/hoigen_b200.h "Multi-GPU"): 9 bytes per triplet instead of 36, one
+# fixed-capacity all-gather per chunk of steps on a side stream, no host synchronisation until the sweep ends.
+# ----------------------------------------------------------------------------------------------------------------------
+WIRE_MAGIC = 0x57494F48
+
+
+def _align(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+def wire_layout(max_images: int, m: int, nbox: int):
+    """Byte offsets of the planes of one record (mirrors csrc/wire.cu::wire_layout)."""
+    hdr_words = 4 + 2 * (max_images + 1)
+    boxes = _align(hdr_words * 4, 16)
+    scores = boxes + nbox * 16
+    labels = scores + m * 4
+    objects = labels + m * 2
+    ph = objects + m
+    po = ph + m
+    return dict(hdr_words=hdr_words, boxes=boxes, scores=scores, labels=labels, objects=objects, ph=ph, po=po, end=po + m)
+
+
+def wire_record_bytes(max_images: int, max_triplets: int, max_boxes: int) -> int:
+    return _align(wire_layout(max_images, max_triplets, max_boxes)["end"], 16)
+
+
+def pack_wire_torch(packed, max_images: int, cap_bytes: int, record: torch.Tensor) -> None:
+    """Host / torch form of hoigen_pack_wire (CPU tensors: the gloo tests; also the format's executable description)."""
+    nimg, m, nbox = packed.num_images, packed.scores.numel(), packed.boxes.shape[0]
+    lay = wire_layout(max_images, m, nbox)
+    hdr = torch.zeros(lay["hdr_words"], dtype=torch.int32)
+    fits = lay["end"] <= cap_bytes
+    hdr[:4] = torch.tensor([WIRE_MAGIC, nimg, m if fits else -1, nbox], dtype=torch.int64).to(torch.int32)
+    hdr[4: 4 + nimg + 1] = torch.tensor(packed.triplet_off, dtype=torch.int32)
+    hdr[4 + max_images + 1: 4 + max_images + 1 + nimg + 1] = torch.tensor(packed.box_off, dtype=torch.int32)
+    record[: lay["hdr_words"] * 4] = hdr.view(torch.uint8).to(record.device)
+    if not fits:
+        return
+    ph, po = [], []
+    for b in range(nimg):
+        s, e = packed.triplet_off[b], packed.triplet_off[b + 1]
+        blk = packed.pairing[2 * s: 2 * e].view(2, e - s)
+        ph.append(blk[0]); po.append(blk[1])
+    cat = lambda xs: torch.cat(xs) if xs else torch.zeros(0, dtype=torch.int64, device=record.device)
+    planes = [("boxes", packed.boxes.float().reshape(-1)), ("scores", packed.scores.float()),
+              ("labels", packed.labels.to(torch.int16)), ("objects", packed.objects.to(torch.uint8)),
+              ("ph", cat(ph).to(torch.uint8)), ("po", cat(po).to(torch.uint8))]
+    for name, t in planes:
+        raw = t.contiguous().view(torch.uint8).reshape(-1)
+        record[lay[name]: lay[name] + raw.numel()] = raw
+
+
+def unpack_wire_torch(record: torch.Tensor, max_images: int, size):
+    """Host / torch form of hoigen_unpack_wire for ONE record -> PackedDetections (int64 indices, [2][M_b] pairing blocks)."""
+    from .detector import PackedDetections
+    hdr_words = 4 + 2 * (max_images + 1)
+    hdr = record[: hdr_words * 4].contiguous().view(torch.int32).tolist()
+    if (hdr[0] & 0xFFFFFFFF) != WIRE_MAGIC:
+        raise ValueError("not a detection wire record")
+    nimg, m, nbox = hdr[1], hdr[2], hdr[3]
+    if m < 0:
+        raise ValueError("the sender's detections did not fit the record capacity")
+    toff, boff = hdr[4: 4 + nimg + 1], hdr[4 + max_images + 1: 4 + max_images + 1 + nimg + 1]
+    lay = wire_layout(max_images, m, nbox)
+    take = lambda name, n, dt, es: record[lay[name]: lay[name] + n * es].contiguous().view(dt)
+    boxes = take("boxes", nbox * 4, torch.float32, 4).view(nbox, 4)
+    scores = take("scores", m, torch.float32, 4)
+    labels = take("labels", m, torch.int16, 2).to(torch.int64) & 0xFFFF
+    objects = take("objects", m, torch.uint8, 1).to(torch.int64)
+    ph, po = take("ph", m, torch.uint8, 1).to(torch.int64), take("po", m, torch.uint8, 1).to(torch.int64)
+    pairing = torch.empty(2 * m, dtype=torch.int64, device=record.device)
+    for b in range(nimg):
+        s, e = toff[b], toff[b + 1]
+        pairing[2 * s: s + e] = ph[s:e]
+        pairing[s + e: 2 * e] = po[s:e]
+    return PackedDetections(scores, labels, objects, pairing, boxes, toff, boff, size)
+
+
+class SweepExchange:
+    """All ranks end up with every rank's detections of a sweep (an evaluation pass over a dataset shard).
+
+    `add(packed, pend)` after every finished step: the step's detections are packed into the compact wire record ON THE
+    DEVICE (hoigen_pack_wire reads the forward's own offsets — nothing is sized on the host) into the current chunk;
+    every `chunk_steps` steps the chunk is exchanged with ONE fixed-capacity all-gather, enqueued on a side stream so it
+    overlaps the next steps' compute.  No host synchronisation happens until `finish()`, which reads all headers back
+    once, widens every record to the reference's dtypes (hoigen_unpack_wire) and returns [rank][step] PackedDetections.
+    CPU tensors (gloo, the host-logic tests) take the torch forms of the same format."""
+
+    def __init__(self, world: int, max_images: int, max_triplets: int, max_boxes: int, device, chunk_steps: int = 4,
+                 group=None):
+        self.world, self.max_images, self.chunk_steps, self.group = world, max_images, max(1, chunk_steps), group
+        self.dev = torch.device(device)
+        self.cap = wire_record_bytes(max_images, max_triplets, max_boxes)
+        self.hdr_bytes = (4 + 2 * (max_images + 1)) * 4
+        self.cuda = self.dev.type == "cuda"
+        self.side = torch.cuda.Stream(device=self.dev) if self.cuda else None
+        self._reset()
+
+    def _reset(self):
+        self.chunks = []        # [(gathered (world*steps*cap,), n_steps, work)]
+        self.cur, self.cur_n = None, 0
+        self.keep = []          # the steps' own tensors: alive until the records have been built
+        self.size = None
+
+    def _new_chunk(self):
+        buf = torch.empty(self.chunk_steps * self.cap, dtype=torch.uint8, device=self.dev)
+        buf.view(self.chunk_steps, self.cap)[:, : self.hdr_bytes].zero_()        # unused slots read as "no record"
+        return buf
+
+    def add(self, packed, pend=None) -> None:
+        self.size = packed.size
+        if self.cuda:
+            from . import _cabi
+            done = getattr(packed, "done", None)
+            with torch.cuda.stream(self.side):
+                if done is not None:
+                    self.side.wait_event(done)
+                else:
+                    self.side.wait_stream(torch.cuda.current_stream(self.dev))
+                if self.cur is None:
+                    self.cur, self.cur_n = self._new_chunk(), 0
+                rec = self.cur[self.cur_n * self.cap: (self.cur_n + 1) * self.cap]
+                img_off = packed.img_off_dev if pend is None else pend.img_off       # device-side int32 offsets of the forward
+                box_off = packed.box_off_dev if pend is None else pend.d_box_off
+                _cabi.call("hoigen_pack_wire", packed.scores.data_ptr(), packed.labels.data_ptr(), packed.objects.data_ptr(),
+                           packed.pairing.data_ptr(), packed.boxes.data_ptr(), img_off.data_ptr(), box_off.data_ptr(),
+                           packed.num_images, self.max_images, self.cap, rec.data_ptr())
+                self.keep.append((packed, pend))
+                self.cur_n += 1
+                if self.cur_n == self.chunk_steps:
+                    self._flush()
+        else:
+            if self.cur is None:
+                self.cur, self.cur_n = self._new_chunk(), 0
+            pack_wire_torch(packed, self.max_images, self.cap, self.cur[self.cur_n * self.cap: (self.cur_n + 1) * self.cap])
+            self.cur_n += 1
+            if self.cur_n == self.chunk_steps:
+                self._flush()
+
+    def _flush(self):
+        """Exchange the current chunk (whole capacity: sizes are not known on the host, and need not be)."""
+        gathered = torch.empty(self.world * self.chunk_steps * self.cap, dtype=torch.uint8, device=self.dev)
+        if self.world > 1:
+            work = dist.all_gather_into_tensor(gathered, self.cur, group=self.group, async_op=True)
+        else:
+            gathered.copy_(self.cur)
+            work = None
+        self.chunks.append((gathered, self.cur, work))
+        self.cur, self.cur_n = None, 0
+
+    def finish(self):
+        """-> [rank][step] PackedDetections of everything added since the last finish()."""
+        from .detector import PackedDetections
+        if self.cur is not None:
+            if self.cuda:
+                with torch.cuda.stream(self.side):
+                    self._flush()
+            else:
+                self._flush()
+        if not self.chunks:
+            return [[] for _ in range(self.world)]
+        S, W, cap, hb = self.chunk_steps, self.world, self.cap, self.hdr_bytes
+        out = [[] for _ in range(W)]
+        if not self.cuda:
+            for gathered, _, work in self.chunks:
+                if work is not None:
+                    work.wait()
+                g = gathered.view(W, S, cap)
+                for r in range(W):
+                    for s in range(S):
+                        if int(g[r, s, :4].view(torch.int32)[0]) & 0xFFFFFFFF == WIRE_MAGIC:
+                            out[r].append(unpack_wire_torch(g[r, s], self.max_images, self.size))
+            self._reset()
+            return out
+        from . import _cabi
+        with torch.cuda.stream(self.side):
+            for _, _, work in self.chunks:
+                if work is not None:
+                    work.wait()                       # stream-level: the side stream waits for NCCL's
+            # ONE read-back: every record's header
+            hdrs = torch.cat([g.view(W * S, cap)[:, :hb] for g, _, _ in self.chunks]).contiguous()
+            host = torch.empty(hdrs.shape, dtype=torch.uint8).pin_memory()
+            host.copy_(hdrs, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        ev.synchronize()
+        H = host.view(torch.int32).view(len(self.chunks), W, S, -1)
+        recs = []            # (chunk, rank, slot, nimg, m, nbox, toff, boff)
+        mi = self.max_images
+        for c in range(len(self.chunks)):
+            for r in range(W):
+                for s in range(S):
+                    h = H[c, r, s]
+                    if int(h[0]) & 0xFFFFFFFF != WIRE_MAGIC:
+                        continue
+                    nimg, m, nbox = int(h[1]), int(h[2]), int(h[3])
+                    if m < 0:
+                        raise ValueError(f"rank {r}: a step's detections did not fit the record capacity ({cap} bytes)")
+                    recs.append((c, r, s, nimg, m, nbox, h[4: 4 + nimg + 1].tolist(), h[4 + mi + 1: 4 + mi + 1 + nimg + 1].tolist()))
+        m_tot, b_tot = sum(x[4] for x in recs), sum(x[5] for x in recs)
+        with torch.cuda.stream(self.side):
+            scores = torch.empty(max(m_tot, 1), dtype=torch.float32, device=self.dev)
+            labels = torch.empty(max(m_tot, 1), dtype=torch.int64, device=self.dev)
+            objects = torch.empty(max(m_tot, 1), dtype=torch.int64, device=self.dev)
+            pairing = torch.empty(max(2 * m_tot, 2), dtype=torch.int64, device=self.dev)
+            boxes = torch.empty(max(b_tot, 1), 4, dtype=torch.float32, device=self.dev)
+            bases = torch.full((len(self.chunks), W * S, 2), -1, dtype=torch.int64)
+            tb, bb, place = 0, 0, []
+            for (c, r, s, nimg, m, nbox, toff, boff) in recs:
+                bases[c, r * S + s, 0], bases[c, r * S + s, 1] = tb, bb
+                place.append((tb, bb))
+                tb += m
+                bb += nbox
+            bases_d = bases.pin_memory().to(self.dev, non_blocking=True)
+            for c, (gathered, _, _) in enumerate(self.chunks):
+                _cabi.call("hoigen_unpack_wire", gathered.data_ptr(), W * S, cap, mi, bases_d[c].data_ptr(), scores.data_ptr(),
+                           labels.data_ptr(), objects.data_ptr(), pairing.data_ptr(), boxes.data_ptr())
+            done = torch.cuda.Event()
+            done.record()
+        torch.cuda.current_stream(self.dev).wait_event(done)
+        for (c, r, s, nimg, m, nbox, toff, boff), (tb, bb) in zip(recs, place):
+            pk = PackedDetections(scores[tb: tb + m], labels[tb: tb + m], objects[tb: tb + m], pairing[2 * tb: 2 * (tb + m)],
+                                  boxes[bb: bb + nbox], toff, boff, self.size)
+            pk.done = done
+            out[r].append(pk)
+        self._reset()
+        return out

@@ -332,6 +332,27 @@ HOIGEN_API int hoigen_emit_triplets(const float* logits, int32_t num_classes, in
                                     int32_t* img_off, hoigen_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: compact wire record of one batch's detections for the path's one collective, the gather of
+ * per-image detections (no reference counterpart: single-GPU eval, main_tip_finetune.py:383-388).  9 bytes per triplet
+ * (f32 score, u16 label, u8 object class, u8 human index, u8 object index) instead of the 36 the reference's dtypes take
+ * (U:1421-1425); the record is built and parsed on the device, sizes travel in its header:
+ *   int32 header[4 + 2*(max_images+1)] = magic, nimg, M (-1: did not fit), nbox, triplet_off[0..nimg], box_off[0..nimg]
+ *   f32 boxes[nbox*4] (16-byte aligned) | f32 scores[M] | u16 labels[M] | u8 objects[M] | u8 human_idx[M] | u8 object_idx[M]
+ * ---------------------------------------------------------------------------------------------- */
+/* bytes a record needs for the given bounds (multiple of 16), or -1 */
+HOIGEN_API int64_t hoigen_wire_record_bytes(int32_t max_images, int64_t max_triplets, int64_t max_boxes);
+/* inputs = the packed outputs of hoigen_emit_triplets (+ boxes, box_off); record: cap_bytes bytes, 16-byte aligned */
+HOIGEN_API int hoigen_pack_wire(const float* scores, const int64_t* labels, const int64_t* objects, const int64_t* pairing,
+                                const float* boxes, const int32_t* img_off, const int32_t* box_off, int32_t nimg,
+                                int32_t max_images, int64_t cap_bytes, void* record, hoigen_stream_t stream);
+/* n_records records `record_stride` bytes apart -> the reference's dtypes.  bases (n_records, 2) int64 on the device:
+ * {first triplet, first box} of each record in the output arrays, or -1 to skip it; pairing gets per-image [2][M_b]
+ * blocks at 2*(base + triplet_off[b]). */
+HOIGEN_API int hoigen_unpack_wire(const void* records, int32_t n_records, int64_t record_stride, int32_t max_images,
+                                  const int64_t* bases, float* scores, int64_t* labels, int64_t* objects,
+                                  int64_t* pairing, float* boxes, hoigen_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * f1 (the path's immediate consumer): batched detection <-> ground-truth association of the eval caller,
  * CustomisedDLE.test_hico utils_tip_cache_and_union_finetune.py:375-407 + BoxPairAssociation
  * pocket/pocket/utils/association.py:51-125, for all images of a batch in one launch.

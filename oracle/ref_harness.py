@@ -1,8 +1,8 @@
-"""Builder-container-only harness: import the UNMODIFIED reference from /root/reference and build its UPT through
-the real `build_detector` (upt_tip_cache_model_free_finetune_distill3.py:1712) on CPU, then load the seeded
-synthetic state of hoigen_b200/synthetic.py into it.  Used by oracle/make_golden.py to pin the oracle and to
-generate tests/golden/*.  Nothing here is importable on the GPU box (no /root/reference there) and nothing
-under hoigen_b200/ imports it.
+"""Harness around the UNMODIFIED reference (from /root/reference, or its staged byte-identical copy oracle/_ref on the GPU
+box): builds its UPT through the real `build_detector` (upt_tip_cache_model_free_finetune_distill3.py:1712), then loads
+the seeded synthetic state of hoigen_b200/synthetic.py into it.  Used by oracle/make_golden.py to pin the oracle and
+generate tests/golden/*, and by bench.py's reference legs (CPU arm, same-GPU torch comparator).  Nothing under
+hoigen_b200/ imports it.
 
 Shims (none alters arithmetic):
   1. sys.path wiring + cwd=/root/reference (the modules do sys.path.append('detr'), `import clip`, `import pocket`)
@@ -27,7 +27,18 @@ from pathlib import Path
 import numpy as np
 import torch
 
-REF = Path(os.environ.get("HOIGEN_REFERENCE", "/root/reference"))
+def _resolve_ref() -> Path:
+    """/root/reference in the builder container; on the GPU box the byte-identical staged copy oracle/_ref/ (made by
+    oracle/stage_ref.py from __graft_entry__.build(), git-ignored, travels with the snapshot)."""
+    if os.environ.get("HOIGEN_REFERENCE"):
+        return Path(os.environ["HOIGEN_REFERENCE"])
+    for cand in (Path("/root/reference"), Path(__file__).resolve().parent / "_ref"):
+        if (cand / "upt_tip_cache_model_free_finetune_distill3.py").exists():
+            return cand
+    return Path("/root/reference")
+
+
+REF = _resolve_ref()
 
 
 def available() -> bool:
@@ -37,7 +48,9 @@ def available() -> bool:
 _installed = False
 
 
-def install_shims():
+def install_shims(force_cpu: bool = False):
+    """force_cpu: neutralise the reference's hard-coded `.cuda()` calls even when a GPU is present (the CPU reference arm
+    of bench.py on the GPU box).  Process-wide monkey-patch: only ever done in a process that runs nothing else."""
     global _installed
     if _installed:
         return
@@ -49,7 +62,7 @@ def install_shims():
     for p in [str(REF / "pocket"), str(REF / "CLIP"), str(REF / "detr"), str(REF), shim_dir]:
         sys.path.insert(0, p)
     os.chdir(REF)
-    if not torch.cuda.is_available():
+    if force_cpu or not torch.cuda.is_available():
         torch.nn.Module.cuda = lambda self, *a, **k: self
         torch.Tensor.cuda = lambda self, *a, **k: self
     _installed = True
@@ -130,10 +143,10 @@ class _StubDetr(torch.nn.Module):
     def backbone(self, nested):
         from detr.util.misc import NestedTensor
         t = nested.tensors
-        return [NestedTensor(t[:, :1, :1, :1], torch.zeros(t.shape[0], 1, 1, dtype=torch.bool))], [None]
+        return [NestedTensor(t[:, :1, :1, :1], torch.zeros(t.shape[0], 1, 1, dtype=torch.bool, device=t.device))], [None]
 
     def transformer(self, src, mask, query, pos):
-        return torch.zeros(1, src.shape[0], 1, 4), None
+        return torch.zeros(1, src.shape[0], 1, 4, device=src.device), None
 
 
 class _StubPostprocessor(torch.nn.Module):
@@ -147,9 +160,10 @@ class _StubPostprocessor(torch.nn.Module):
         return self.results
 
 
-def build_reference_upt(num_classes: int = 117, dataset: str = "hicodet", quiet: bool = True, **arg_over):
+def build_reference_upt(num_classes: int = 117, dataset: str = "hicodet", quiet: bool = True, force_cpu: bool = False,
+                        **arg_over):
     """Real build_detector on CPU -> (upt, stub_postprocessor)."""
-    install_shims()
+    install_shims(force_cpu)
     import detr.models.backbone as backbone_mod
     backbone_mod.is_main_process = lambda: False
     import CLIP.clip.model as vanilla
@@ -247,7 +261,7 @@ def run_reference(upt, stub_pp, images: torch.Tensor, detr_results, dino_feats: 
     stub_pp.results = [dict(scores=r["scores"], labels=r["labels"], boxes=r["boxes"]) for r in detr_results]
     upt.dino_model = _FixedDino()
     upt.dino_model.feats = dino_feats
-    inputs = [(torch.zeros(3, 32, 32), images[b]) for b in range(images.shape[0])]
+    inputs = [(torch.zeros(3, 32, 32, device=images.device), images[b]) for b in range(images.shape[0])]
     ctx = contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext()
     with torch.no_grad(), ctx:
         return upt(inputs)

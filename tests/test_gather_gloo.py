@@ -146,3 +146,69 @@ def test_gather_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_wire_record_roundtrip_and_layout():
+    """The compact wire record (9 B per triplet): torch pack -> torch unpack restores every field and dtype; the byte
+    layout agrees with the C library's size function; a record that does not fit says so."""
+    from hoigen_b200 import _cabi
+    from hoigen_b200.gather import pack_wire_torch, unpack_wire_torch, wire_layout, wire_record_bytes
+    dets, pk = _fake_packed(3, 6)
+    m, nbox = pk.scores.numel(), pk.boxes.shape[0]
+    cap = wire_record_bytes(8, m + 11, nbox + 3)
+    assert cap == _cabi.load().hoigen_wire_record_bytes(8, m + 11, nbox + 3)
+    lay = wire_layout(8, m, nbox)
+    assert lay["end"] - lay["scores"] == 9 * m and lay["boxes"] % 16 == 0 and lay["labels"] % 2 == 0
+    rec = torch.zeros(cap, dtype=torch.uint8)
+    pack_wire_torch(pk, 8, cap, rec)
+    back = unpack_wire_torch(rec, 8, (224, 224))
+    assert back.triplet_off == pk.triplet_off and back.box_off == pk.box_off
+    for b, e in enumerate(dets):
+        a = back.image(b)
+        for k in ("boxes", "pairing", "scores", "labels", "objects"):
+            assert torch.equal(a[k], e[k]) and a[k].dtype == e[k].dtype, (b, k)
+    small = torch.zeros(lay["end"] - 16, dtype=torch.uint8)
+    pack_wire_torch(pk, 8, small.numel(), small)
+    with pytest.raises(ValueError):
+        unpack_wire_torch(small, 8, (224, 224))
+
+
+def _worker_sweep(rank, world, port, q):
+    from hoigen_b200.gather import SweepExchange
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        steps = 5                                   # chunk_steps = 2: two full chunks + a partial one
+        ex = SweepExchange(world, 8, 8 * 50, 8 * 9, "cpu", chunk_steps=2)
+        ok = True
+        for sweep in range(2):                      # the exchanger is reusable across sweeps
+            for s in range(steps):
+                _, pk = _fake_packed(10 * rank + s + 100 * sweep, 3 + (rank + s) % 4)
+                ex.add(pk)
+            got = ex.finish()
+            ok = ok and len(got) == world
+            for r in range(world):
+                ok = ok and len(got[r]) == steps
+                for s in range(steps):
+                    ref_dets, _ = _fake_packed(10 * r + s + 100 * sweep, 3 + (r + s) % 4)
+                    ok = ok and got[r][s].num_images == len(ref_dets)
+                    for b, e in enumerate(ref_dets):
+                        a = got[r][s].image(b)
+                        for k in ("boxes", "pairing", "scores", "labels", "objects"):
+                            ok = ok and torch.equal(a[k], e[k]) and a[k].dtype == e[k].dtype
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sweep_exchange_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_sweep, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -356,7 +356,7 @@ def test_concurrent_streams_equal_sequential(cuda_device):
 
 def test_scoring_stage_given_identical_features(cuda_device):
     """a10 alone: feed the oracle's fp32 features, compare logits. bf16 operands (keys, features) with fp32
-    accumulation and an exact fp32 bias carrier: max-abs <= 3e-3."""
+    accumulation and an exact fp32 bias carrier: max-abs <= 2.7e-3 (2x the measured 1.34e-3)."""
     import ctypes as C
     from hoigen_b200 import _cabi, synthetic as S
     from oracle import hoi_forward_ref as O
@@ -388,7 +388,7 @@ def test_scoring_stage_given_identical_features(cuda_device):
         ref = O.scoring_logits(f[0, sl], f[1, sl], f[2, sl], gb, dino[b], head.tensors, head.attrs)
         worst = max(worst, (got[sl] - ref).abs().max().item())
     print(f"scoring stage max-abs {worst:.3e}")
-    assert worst <= 3e-3, worst
+    assert worst <= 2.7e-3, worst
 
 
 def test_emit_stage_exact_order_and_denormals(cuda_device):
@@ -618,3 +618,49 @@ def test_fp32_mode_end_to_end_matches_reference_golden(cuda_device):
         errs[mode] = max(float(np.abs(inter["logits"][b].cpu().numpy() - gold[f"logits_{b}"]).max()) for b in range(c["B"]))
     print(f"end-to-end logits max-abs vs reference: bf16 scoring {errs['bf16']:.3e}, fp32 scoring {errs['fp32']:.3e}")
     assert errs["fp32"] <= LOGIT_TOL and errs["bf16"] <= LOGIT_TOL
+
+
+def test_wire_format_kernels_match_torch_form(cuda_device):
+    """hoigen_pack_wire / hoigen_unpack_wire (the compact 9 B/triplet record of the multi-GPU gather) on the detections of
+    a real forward: the record's bytes equal the torch form's, and a single-rank SweepExchange (pack on a side stream,
+    chunked, one header read-back, unpack) returns every field of every step bit-for-bit with the reference's dtypes."""
+    from hoigen_b200 import _cabi, synthetic as S
+    from hoigen_b200.gather import SweepExchange, pack_wire_torch, wire_record_bytes
+    from hoigen_b200.detector import PackedDetections
+    m, enc, head = _build(117, 256, cuda_device)
+    steps = []
+    for s in range(5):
+        B = 3 + s
+        props = _props_to(S.make_region_props(B, 4, 5, ragged=True, seed=700 + s), cuda_device)
+        if s == 2:
+            props[1]["labels"] = torch.full_like(props[1]["labels"], 9)           # an image without pairs inside the batch
+        steps.append(m.forward_from_proposals(S.make_images(B, seed=710 + s).to(cuda_device), props,
+                                              S.make_dino_features(B, seed=720 + s).to(cuda_device)))
+    pk = steps[0].packed
+    cap = wire_record_bytes(8, pk.scores.numel() + 5, pk.boxes.shape[0] + 1)
+    rec = torch.zeros(cap, dtype=torch.uint8, device=cuda_device)
+    _cabi.call("hoigen_pack_wire", pk.scores.data_ptr(), pk.labels.data_ptr(), pk.objects.data_ptr(), pk.pairing.data_ptr(),
+               pk.boxes.data_ptr(), pk.img_off_dev.data_ptr(), pk.box_off_dev.data_ptr(), pk.num_images, 8, cap, rec.data_ptr())
+    host_pk = PackedDetections(pk.scores.cpu(), pk.labels.cpu(), pk.objects.cpu(), pk.pairing.cpu(), pk.boxes.cpu(),
+                               pk.triplet_off, pk.box_off, pk.size)
+    ref = torch.zeros(cap, dtype=torch.uint8)
+    pack_wire_torch(host_pk, 8, cap, ref)
+    from hoigen_b200.gather import wire_layout
+    end = wire_layout(8, pk.scores.numel(), pk.boxes.shape[0])["end"]
+    assert torch.equal(rec.cpu()[:end], ref[:end])
+    ex = SweepExchange(1, 8, 8 * 36 * 20, 8 * 9, cuda_device, chunk_steps=2)
+    for rep in range(2):
+        for d in steps:
+            ex.add(d.packed)
+        got = ex.finish()
+        torch.cuda.synchronize()
+        assert len(got) == 1 and len(got[0]) == len(steps)
+        for d, g in zip(steps, got[0]):
+            assert g.triplet_off == d.packed.triplet_off and g.box_off == d.packed.box_off
+            for f in ("scores", "labels", "objects", "pairing", "boxes"):
+                a, b = getattr(g, f), getattr(d.packed, f)
+                assert a.dtype == b.dtype and torch.equal(a, b), (rep, f)
+    tiny = SweepExchange(1, 8, 4, 8 * 9, cuda_device, chunk_steps=1)             # capacity too small: loud at finish()
+    tiny.add(steps[0].packed)
+    with pytest.raises(ValueError):
+        tiny.finish()

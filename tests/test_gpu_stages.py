@@ -229,7 +229,7 @@ def test_attention_matches_sdpa(cuda_device):
     err = (out.float() - ref).abs().max().item()
     # P is rounded to bf16 before the PV MMA and the output is bf16: ~2^-8 relative
     print(f"attention: max-abs err {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
-    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+    assert err < 6e-3 * max(1.0, ref.abs().max().item()), err      # measured 3.0e-3 * max (r02)
     assert torch.isfinite(out.float()).all()
 
 
@@ -302,7 +302,7 @@ def test_adapter_kv_and_block(cuda_device, enc_state):
         err = (out.float().cpu() - ref).abs().max().item()
         # bf16 tensor-core operands (weights + activations between the MMAs), fp32 accumulation / softmax / LayerNorm
         print(f"adapter block (delta={use_delta}): max-abs err {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
-        assert err < 4e-2 * max(1.0, ref.abs().max().item()), (use_delta, err)
+        assert err < 1e-2 * max(1.0, ref.abs().max().item()), (use_delta, err)   # measured 5.0e-3 * max (r02)
         ref_up = torch.nn.functional.linear(out.float().cpu(), wus.float())           # from the kernel's own bottleneck
         err_up = (dout[: B * 197].float().cpu() - ref_up).abs().max().item()
         assert err_up < 2 ** -7 * max(1.0, ref_up.abs().max().item()), (use_delta, err_up)
@@ -311,7 +311,7 @@ def test_adapter_kv_and_block(cuda_device, enc_state):
 
 def test_encoder_matches_oracle_and_golden(cuda_device, enc_state):
     """VisionTransformer.forward(x, prior) (C:489-506): bf16 tensor-core path vs the fp32 oracle and the committed
-    reference output.  Tolerance: feat_local max-abs <= 6e-2 on values up to ~5 (bf16 operands, fp32 residual
+    reference output.  Tolerance: feat_local max-abs <= 5e-2 (2x the measured 2.45e-2) on values up to ~5 (bf16 operands, fp32 residual
     stream / LN / softmax); the end-to-end logit budget (1e-2) is checked in test_gpu_e2e.py."""
     from hoigen_b200 import synthetic as S
     from hoigen_b200.encoder import VisionTransformer
@@ -334,7 +334,7 @@ def test_encoder_matches_oracle_and_golden(cuda_device, enc_state):
     err_g = (fg.cpu() - torch.from_numpy(gold["feat_global"])).abs().max().item()
     rel = ((tok - ref).norm() / ref.norm()).item()
     print(f"encoder vs reference: feat_local max-abs {err_l:.3e} (|ref| max {ref.abs().max():.2f}), rel-fro {rel:.3e}, feat_global {err_g:.3e}")
-    assert err_l < 6e-2 and err_g < 6e-2 and rel < 1e-2
+    assert err_l < 5e-2 and err_g < 3.5e-2 and rel < 9e-3      # measured 2.45e-2 / 1.72e-2 / 4.5e-3 (r02): bars = 2x
 
 
 def test_encoder_layers_progressive(cuda_device, enc_state):
@@ -365,7 +365,7 @@ def test_encoder_layers_progressive(cuda_device, enc_state):
         ref = O._ln(x, sd[O.ENC + "ln_post.weight"], sd[O.ENC + "ln_post.bias"]) @ sd[O.ENC + "proj"]
         err = (tok - ref).abs().max().item()
         print(f"layers={nl}: max-abs {err:.3e} (|ref| max {ref.abs().max():.2f})")
-        assert err < 4e-2, (nl, err)
+        assert err < 3.5e-2, (nl, err)          # measured 1.7e-2 (r02): bar = 2x
 
 
 def _head_inputs(case_props, num_classes=117, N=256):
