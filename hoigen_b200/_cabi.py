@@ -13,7 +13,7 @@ import torch
 
 from ._build import LIB_PATH
 
-ACT_NONE, ACT_QUICKGELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_QUICKGELU, ACT_RELU, ACT_EXP = 0, 1, 2, 3
 
 
 class HoigenError(RuntimeError):
@@ -31,6 +31,7 @@ class GemmParams(C.Structure):
         ("out_f32", C.c_void_p), ("ld_f32", C.c_int32),
         ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int32),
         ("block_n", C.c_int32), ("split_k", C.c_int32),
+        ("act_param", C.c_float), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p),
     ]
 
 
@@ -62,6 +63,8 @@ def load() -> C.CDLL:
         fn.argtypes = sig
     lib.hoigen_wire_record_bytes.restype = C.c_int64
     lib.hoigen_wire_record_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int64]
+    lib.hoigen_cache_fused_workspace_bytes.restype = C.c_int64
+    lib.hoigen_cache_fused_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.hoigen_launch_count.restype = C.c_longlong
     lib.hoigen_profile_enable.argtypes = [C.c_int]
     lib.hoigen_profile_read.restype = C.c_longlong
@@ -109,7 +112,8 @@ ENCODER_WEIGHT_FIELDS = (
     "conv_w", "class_embedding", "positional_embedding", "ln_pre_w", "ln_pre_b", "ln_post_w", "ln_post_b", "proj_t",
     "ln1_w", "ln1_b", "ln2_w", "ln2_b", "qkv_w", "qkv_b", "out_w", "out_b", "fc_w", "fc_b", "proj_w", "proj_b",
     "ad_down_w", "ad_down_b", "ad_up_w", "ad_up_b", "ad_in_proj_w", "ad_in_proj_b", "ad_wq", "ad_wo", "ad_w1", "ad_w2",
-    "ad_out_proj_b", "ad_linear1_b", "ad_linear2_b", "ad_norm2_w", "ad_norm2_b", "ad_norm3_w", "ad_norm3_b")
+    "ad_out_proj_b", "ad_linear1_b", "ad_linear2_b", "ad_norm2_w", "ad_norm2_b", "ad_norm3_w", "ad_norm3_b",
+    "qkv_wf", "qkv_colsum", "qkv_bf", "fc_wf", "fc_colsum", "fc_bf")
 
 
 class EncoderWeights(C.Structure):
@@ -117,7 +121,7 @@ class EncoderWeights(C.Structure):
 
 
 ENCODER_BUFFER_FIELDS = ("patches", "patch_emb", "x", "xb", "h", "qkv", "attn", "mlp", "delta", "delta2",
-                         "adapter_kv", "tokens_out")
+                         "adapter_kv", "row_stats", "tokens_out")
 
 
 class EncoderBuffers(C.Structure):
@@ -132,10 +136,13 @@ class ScoreWeights(C.Structure):
         ("global_keys", C.c_void_p), ("global_bias_term", C.c_void_p), ("colscale_global", C.c_void_p),
         ("dino_keys", C.c_void_p), ("dino_bias_term", C.c_void_p), ("colscale_dino", C.c_void_p),
         ("text_w", C.c_void_p), ("colscale_text", C.c_void_p),
+        ("affinity", C.c_int32), ("beta", C.c_float),
+        ("cache_bias", C.c_void_p * 3), ("global_bias", C.c_void_p), ("dino_bias", C.c_void_p),
     ]
 
 
-SCORE_BUFFER_FIELDS = ("pair_feat_bf16", "phi", "phi_img", "g_bf16", "d_bf16", "img_logits", "logits", "ld_logits")
+SCORE_BUFFER_FIELDS = ("pair_feat_bf16", "phi", "phi_img", "g_bf16", "d_bf16", "img_logits", "logits", "ld_logits",
+                       "cache_parts")
 
 
 class ScoreBuffers(C.Structure):
@@ -173,6 +180,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_embed_lnpre": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
     "hoigen_layernorm768": [_P, _P, _P, _P, _P, _I, _P],
     "hoigen_add_layernorm768": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "hoigen_add_rowstats768": [_P, _P, _P, _P, _P, _P, _I, _P],
     "hoigen_adapter_kv": [_P, _P, _P, _P, _I, _I, _P],
     "hoigen_adapter_block": [_P, _P, _P, _P, C.POINTER(AdapterWeights), _P, _P, _I, _I, _P],
     "hoigen_attention": [_P, _P, _I, _P],
@@ -186,6 +194,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_rows_to_bf16": [_P, _L, _I, _I, _I, _P, _P],
     "hoigen_broadcast_image_logits": [_P, _P, _I, _I, _I, _I, _P, _P],
     "hoigen_score_pairs": [C.POINTER(ScoreWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
+    "hoigen_score_cache_fused": [C.POINTER(ScoreWeights), _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _P],
     "hoigen_rows_split3": [_P, _L, _I, _I, _I, _I, _P, _P],
     "hoigen_score_pairs_fp32": [C.POINTER(ScoreWeightsFp32), C.POINTER(ScoreBuffersFp32), _P, _P, _P, _P, _I, _I, _P],
     "hoigen_score_pairs_folded": [C.POINTER(FoldedWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
@@ -197,7 +206,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_emit_triplets": [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
 }
 
-EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", "hoigen_launch_count", "hoigen_wire_record_bytes",
+EXPORTED_SYMBOLS = ["hoigen_abi_version", "hoigen_last_error", "hoigen_init", "hoigen_launch_count", "hoigen_wire_record_bytes", "hoigen_cache_fused_workspace_bytes",
                     "hoigen_profile_enable", "hoigen_profile_reset", "hoigen_profile_read", *_SIGNATURES.keys()]
 
 
@@ -233,7 +242,8 @@ def call(name: str, *args) -> None:
 
 
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act=ACT_NONE, residual=None,
-              out_f32=None, out_bf16=None, block_n: int = 0, split_k: int = 0, simt: bool = False) -> None:
+              out_f32=None, out_bf16=None, block_n: int = 0, split_k: int = 0, simt: bool = False,
+              act_param: float = 0.0, ln_stats=None, ln_colsum=None) -> None:
     """out = epi(a[M,K] @ w[N,K]^T); see hoigen_gemm_bf16 in include/hoigen_b200.h."""
     lib = init(a.device)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -261,5 +271,10 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act
         p.out_bf16, p.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
     p.block_n = block_n
     p.split_k = split_k
+    p.act_param = act_param
+    if ln_stats is not None:
+        assert ln_stats.dtype == torch.float32 and ln_stats.shape == (M, 2) and ln_stats.is_contiguous()
+        assert ln_colsum is not None and ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N
+        p.ln_stats, p.ln_colsum = ln_stats.data_ptr(), ln_colsum.data_ptr()
     fn = lib.hoigen_debug_gemm_simt if simt else lib.hoigen_gemm_bf16
     check(fn(C.byref(p), stream_ptr()), "hoigen_gemm_bf16")

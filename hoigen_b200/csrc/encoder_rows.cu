@@ -56,13 +56,16 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
 // ------------------------------------------------------------------------------------------------
 //   delta != nullptr (EMBED = false): x = in[row] + delta[row] (bf16), and x is written back to `stream_out` (the
 //                  deferred residual add of the preceding GEMM: X += up-proj / out-proj output)
-template <bool EMBED>
+//   STATS = true: the LayerNorm itself is folded into the consuming GEMM (gemm.cu, ln_stats): this pass only applies the
+//                  pending residuals, writes the fp32 stream + its bf16 copy and emits (mean, rstd) per row.
+template <bool EMBED, bool STATS = false>
 __global__ void __launch_bounds__(256)
 layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls, const float* __restrict__ pos,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out_f32,
                     __nv_bfloat16* __restrict__ out_bf16, int rows, const __nv_bfloat16* __restrict__ delta = nullptr,
                     float* __restrict__ stream_out = nullptr, const __nv_bfloat16* __restrict__ delta_b = nullptr,
-                    __nv_bfloat16* __restrict__ stream_bf16 = nullptr, const float* __restrict__ col_bias = nullptr) {
+                    __nv_bfloat16* __restrict__ stream_bf16 = nullptr, const float* __restrict__ col_bias = nullptr,
+                    float2* __restrict__ stats_out = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;   // one warp per row; rows per CTA = launch-time choice
   if (row >= rows) return;
@@ -126,6 +129,10 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
     q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / WIDTH) + 1e-5f);
+  if (STATS) {
+    if (lane == 0) stats_out[row] = make_float2(mean, rstd);
+    return;
+  }
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
@@ -230,6 +237,21 @@ int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2
       x, nullptr, nullptr, gamma, beta, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows,
       reinterpret_cast<const __nv_bfloat16*>(delta_bf16), x, reinterpret_cast<const __nv_bfloat16*>(delta2_bf16),
       reinterpret_cast<__nv_bfloat16*>(x_bf16), col_bias);
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
+int hoigen_add_rowstats768(float* x, const void* delta_bf16, const void* delta2_bf16, const float* col_bias, void* x_bf16,
+                           float* stats, int32_t rows, hoigen_stream_t stream) {
+  using namespace hoigen;
+  HOIGEN_CHECK_ARG(x && delta_bf16 && x_bf16 && stats && rows > 0, "add_rowstats768: bad arguments");
+  KernelScope ks("add_rowstats768", reinterpret_cast<cudaStream_t>(stream), 0,
+                 double(rows) * WIDTH * (4 + 2 + 4 + 2 + (delta2_bf16 ? 2 : 0)) + double(rows) * 8);
+  constexpr int rpc = 8;
+  layernorm768_kernel<false, true><<<(rows + rpc - 1) / rpc, rpc * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rows, reinterpret_cast<const __nv_bfloat16*>(delta_bf16), x,
+      reinterpret_cast<const __nv_bfloat16*>(delta2_bf16), reinterpret_cast<__nv_bfloat16*>(x_bf16), col_bias,
+      reinterpret_cast<float2*>(stats));
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }

@@ -40,6 +40,11 @@ struct GemmArgs {
   int ld_f32;
   __nv_bfloat16* out_bf16;
   int ld_bf16;
+  float act_param;          // HOIGEN_ACT_EXP: beta
+  // LayerNorm folded into the epilogue (C:443-445 / C:457-458 ln_1 -> in_proj, ln_2 -> c_fc): A = bf16 copy of the RAW
+  // stream x, W = W . diag(gamma); out = rstd[row] * (acc - mean[row] * colsum[col]) + bias'[col], colsum = sum_k W'[col][k]
+  // (staged where the column scale would be), bias' = bias + W beta.  ln_stats = (mean, rstd) per row from the residual pass.
+  const float2* ln_stats;
   int debug;  // diagnostics only (HOIGEN_GEMM_DEBUG): 1 = TMA loads without MMAs, 2 = MMAs without TMA loads
   // CTA-pair kernel work split (stream-K): work unit = one k-block of one tile; pair p owns units [bound(p), bound(p+1))
   float* sk_ws;     // fp32 partial-accumulator slots, one per (pair, cta rank)
@@ -60,7 +65,7 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN * 4;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
+__device__ __forceinline__ float apply_act(float v, int act, float param = 0.f) {
   if (act == HOIGEN_ACT_QUICKGELU) {
     // x * sigmoid(1.702 x)   (CLIP_models_adapter_prior2.py:420); sigmoid(z) = 0.5 + 0.5 tanh(z/2): one MUFU op
     float th;
@@ -68,6 +73,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v * fmaf(0.5f, th, 0.5f);
   } else if (act == HOIGEN_ACT_RELU) {
     return fmaxf(v, 0.0f);
+  } else if (act == HOIGEN_ACT_EXP) {
+    return exp2f(v * (param * 1.4426950408889634f));    // exp(param * v): the Tip-Adapter exp affinity of the per-image cache terms
   }
   return v;
 }
@@ -86,7 +93,7 @@ __device__ __forceinline__ void epilogue_stage_vectors(const GemmArgs& g, int co
     const int col = col_begin + i;
     const bool ok = col < g.N;
     s_bias[i] = (g.bias && ok) ? __ldg(g.bias + col) : 0.f;
-    s_cs[i] = (g.colscale && ok) ? __ldg(g.colscale + col) : 1.f;
+    s_cs[i] = (g.colscale && ok) ? __ldg(g.colscale + col) : 1.f;     // (LN-folded GEMMs: colscale points at colsum)
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
 }
@@ -107,15 +114,27 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const uint32_t (&r)[CW], const float4 (&res)[CW / 4],
                                                        bool res_vec, const float* res_row, const float* s_bias,
                                                        const float* s_cs, int row, bool row_ok, int col0,
-                                                       uint8_t* out_tile = nullptr, int rrow = 0, int tile_col = 0) {
+                                                       uint8_t* out_tile = nullptr, int rrow = 0, int tile_col = 0,
+                                                       float ln_mean = 0.f, float ln_rstd = 1.f) {
   const bool full_chunk = (col0 + CW <= g.N);
-  // EPI >= 0: the epilogue recipe is a compile-time constant (act | colscale << 4 | bias << 5), no work for absent terms
+  // EPI >= 0: the epilogue recipe is a compile-time constant (act | colscale << 4 | bias << 5 | layernorm << 6), no work
+  // for absent terms
   const int act = EPI >= 0 ? (EPI & 15) : g.act;
-  const bool has_cs = EPI >= 0 ? ((EPI >> 4) & 1) != 0 : true;
+  const bool has_ln = EPI >= 0 ? ((EPI >> 6) & 1) != 0 : (g.ln_stats != nullptr);
+  const bool has_cs = (EPI >= 0 ? ((EPI >> 4) & 1) != 0 : true) && !has_ln;
   const bool has_bias = EPI >= 0 ? ((EPI >> 5) & 1) != 0 : true;
   float v[CW];
 #pragma unroll
   for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+  if (has_ln) {   // rstd * (x W'^T - mean * colsum): s_cs holds colsum here
+    const float nm = -ln_mean;
+#pragma unroll
+    for (int j = 0; j < CW; j += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(s_cs + j);
+      v[j] = ln_rstd * fmaf(nm, c.x, v[j]); v[j + 1] = ln_rstd * fmaf(nm, c.y, v[j + 1]);
+      v[j + 2] = ln_rstd * fmaf(nm, c.z, v[j + 2]); v[j + 3] = ln_rstd * fmaf(nm, c.w, v[j + 3]);
+    }
+  }
   if (has_bias) {
 #pragma unroll
     for (int j = 0; j < CW; j += 4) {
@@ -125,7 +144,7 @@ __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const 
   }
   if (act != HOIGEN_ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < CW; ++j) v[j] = apply_act(v[j], act);
+    for (int j = 0; j < CW; ++j) v[j] = apply_act(v[j], act, g.act_param);
   }
   if (has_cs) {
 #pragma unroll
@@ -199,6 +218,11 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
   const float* res_row = g.residual ? g.residual + size_t(row_ok ? row : 0) * g.ld_res : nullptr;
   float4 res[2][CW / 4];
   uint32_t r[2][CW];
+  float ln_mean = 0.f, ln_rstd = 1.f;
+  if ((EPI >= 0 ? ((EPI >> 6) & 1) != 0 : g.ln_stats != nullptr) && row_ok) {
+    const float2 st = __ldg(g.ln_stats + row);
+    ln_mean = st.x; ln_rstd = st.y;
+  }
   if (res_vec && colbase + CW <= g.N) {
 #pragma unroll
     for (int j = 0; j < CW / 4; ++j) res[0][j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
@@ -232,7 +256,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
       }
     }
     epilogue_process_chunk<EPI>(g, r[c & 1], res[c & 1], res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0,
-                           out_tile, rrow, tile_col0 + c * CW);
+                           out_tile, rrow, tile_col0 + c * CW, ln_mean, ln_rstd);
     if (!more) break;
   }
   tmem_wait_ld();
@@ -270,7 +294,13 @@ __device__ __forceinline__ void epilogue_from_parts(const GemmArgs& g, int row, 
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) res[j] = *reinterpret_cast<const float4*>(res_row + col0 + 4 * j);
     }
-    epilogue_process_chunk<EPI>(g, r, res, res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0);
+    float ln_mean = 0.f, ln_rstd = 1.f;
+    if (g.ln_stats != nullptr && row_ok) {
+      const float2 st = __ldg(g.ln_stats + row);
+      ln_mean = st.x; ln_rstd = st.y;
+    }
+    epilogue_process_chunk<EPI>(g, r, res, res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0, nullptr, 0, 0,
+                                ln_mean, ln_rstd);
   }
 }
 
@@ -743,9 +773,10 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ a, const __nv
   float acc = 0.f;
   for (int k = 0; k < g.K; ++k)
     acc = fmaf(__bfloat162float(a[size_t(m) * lda + k]), __bfloat162float(w[size_t(n) * ldw + k]), acc);
+  if (g.ln_stats) acc = g.ln_stats[m].y * (acc - g.ln_stats[m].x * g.colscale[n]);
   if (g.bias) acc += g.bias[n];
-  acc = apply_act(acc, g.act);
-  if (g.colscale) acc *= g.colscale[n];
+  acc = apply_act(acc, g.act, g.act_param);
+  if (g.colscale && !g.ln_stats) acc *= g.colscale[n];
   if (g.residual) acc += g.residual[size_t(m) * g.ld_res + n];
   if (g.out_f32) g.out_f32[size_t(m) * g.ld_f32 + n] = acc;
   if (g.out_bf16) g.out_bf16[size_t(m) * g.ld_bf16 + n] = __float2bfloat16_rn(acc);
@@ -764,7 +795,10 @@ static int validate(const hoigen_gemm_params* p) {
   HOIGEN_CHECK_ARG(!p->out_f32 || p->ld_f32 >= p->N, "gemm: ld_f32 < N");
   HOIGEN_CHECK_ARG(!p->out_bf16 || p->ld_bf16 >= p->N, "gemm: ld_bf16 < N");
   HOIGEN_CHECK_ARG(!p->residual || p->ld_res >= p->N, "gemm: ld_res < N");
-  HOIGEN_CHECK_ARG(p->act >= 0 && p->act <= 2, "gemm: bad act %d", p->act);
+  HOIGEN_CHECK_ARG(p->act >= 0 && p->act <= 3, "gemm: bad act %d", p->act);
+  HOIGEN_CHECK_ARG(!p->ln_stats || (p->ln_colsum && !p->colscale), "gemm: ln_stats needs ln_colsum and excludes colscale");
+  HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(p->ln_colsum) & 15) == 0,
+                   "gemm: ln_stats / ln_colsum alignment");
   HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->colscale) & 15) == 0,
                    "gemm: bias/colscale must be 16-byte aligned");
   HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->residual) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->out_f32) & 15) == 0 &&
@@ -776,7 +810,9 @@ static int validate(const hoigen_gemm_params* p) {
 static GemmArgs to_args(const hoigen_gemm_params* p) {
   GemmArgs g;
   g.M = p->M; g.N = p->N; g.K = p->K;
-  g.bias = p->bias; g.colscale = p->colscale; g.act = p->act;
+  g.bias = p->bias; g.colscale = p->ln_stats ? p->ln_colsum : p->colscale; g.act = p->act;
+  g.act_param = p->act_param;
+  g.ln_stats = reinterpret_cast<const float2*>(p->ln_stats);
   g.residual = p->residual; g.ld_res = p->ld_res;
   g.out_f32 = p->out_f32; g.ld_f32 = p->ld_f32;
   g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16); g.ld_bf16 = p->ld_bf16;
@@ -898,6 +934,11 @@ static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream, bool f
   if (!tma_out) return launch_gemm2_impl<BN, false, -1>(p, stream, force_split);
   // compile-time epilogue recipes of the encoder's bf16-output GEMMs; anything else uses the runtime-flag epilogue
   const bool b = p->bias != nullptr, c = p->colscale != nullptr;
+  if (p->ln_stats) {   // LayerNorm-folded QKV / c_fc
+    if (b && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 6) | (1 << 5)>(p, stream, force_split);
+    if (b && p->act == HOIGEN_ACT_QUICKGELU) return launch_gemm2_impl<BN, true, (1 << 6) | (1 << 5) | HOIGEN_ACT_QUICKGELU>(p, stream, force_split);
+    return launch_gemm2_impl<BN, true, -1>(p, stream, force_split);
+  }
   if (b && !c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 5)>(p, stream, force_split);                          // QKV, out-proj
   if (b && !c && p->act == HOIGEN_ACT_QUICKGELU) return launch_gemm2_impl<BN, true, (1 << 5) | HOIGEN_ACT_QUICKGELU>(p, stream, force_split);  // c_fc
   if (b && c && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 5) | (1 << 4)>(p, stream, force_split);                 // adapter up-proj

@@ -2,6 +2,8 @@
 // otherwise pay ~120 ctypes round trips per encoder forward):
 //   hoigen_encoder_forward : VisionTransformer.forward(x, prior)      CLIP_models_adapter_prior2.py:489-506
 //   hoigen_score_pairs     : cache-model + text logits                upt_..._distill3.py:1111-1186
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace hoigen {
@@ -17,6 +19,42 @@ static int gemm(const void* a, int lda, const void* w, int ldw, int M, int N, in
   p.out_bf16 = out_bf16; p.ld_bf16 = ld_bf16;
   p.split_k = 0;
   p.block_n = 0;
+  p.act_param = 0.f;
+  p.ln_stats = nullptr;
+  p.ln_colsum = nullptr;
+  return hoigen_gemm_bf16(&p, s);
+}
+
+// bf16-output GEMM with the preceding LayerNorm folded into its epilogue (see hoigen_gemm_params.ln_stats)
+static int gemm_ln(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias, int act,
+                   const float* ln_stats, const float* ln_colsum, void* out_bf16, int ld_bf16, cudaStream_t s) {
+  hoigen_gemm_params p;
+  p.a = a; p.w = w; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw;
+  p.bias = bias; p.colscale = nullptr; p.act = act;
+  p.residual = nullptr; p.ld_res = 0;
+  p.out_f32 = nullptr; p.ld_f32 = 0;
+  p.out_bf16 = out_bf16; p.ld_bf16 = ld_bf16;
+  p.split_k = 0;
+  p.block_n = 0;
+  p.act_param = 0.f;
+  p.ln_stats = ln_stats;
+  p.ln_colsum = ln_colsum;
+  return hoigen_gemm_bf16(&p, s);
+}
+
+static int gemm_exp(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias, float beta,
+                    void* out_bf16, int ld_bf16, cudaStream_t s) {
+  hoigen_gemm_params p;
+  p.a = a; p.w = w; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw;
+  p.bias = bias; p.colscale = nullptr; p.act = HOIGEN_ACT_EXP;
+  p.residual = nullptr; p.ld_res = 0;
+  p.out_f32 = nullptr; p.ld_f32 = 0;
+  p.out_bf16 = out_bf16; p.ld_bf16 = ld_bf16;
+  p.split_k = 0;
+  p.block_n = 0;
+  p.act_param = beta;
+  p.ln_stats = nullptr;
+  p.ln_colsum = nullptr;
   return hoigen_gemm_bf16(&p, s);
 }
 
@@ -50,6 +88,9 @@ int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder
   // Residual adds are DEFERRED out of the GEMM epilogues: every GEMM that feeds the fp32 stream writes a bf16 delta
   // (TMA-store epilogue) and the next LayerNorm pass (which streams x anyway) applies it.  The MLP output of layer
   // l-1 (delta2) is consumed twice: by linearity inside the adapter block's down-projection, and by ln_1's pass.
+  // LayerNorm folded into the QKV / c_fc GEMMs (north_star item 1) when the folded weights were packed: the residual
+  // pass then writes the bf16 copy of the RAW stream + per-row (mean, rstd) instead of a normalised `h`.
+  const bool fold = w->qkv_wf && w->qkv_colsum && w->qkv_bf && w->fc_wf && w->fc_colsum && w->fc_bf && buf->row_stats;
   for (int l = 0; l < num_layers; ++l) {
     const size_t o768 = size_t(l) * D, o64 = size_t(l) * 64;
     // (1) x += mlp(l-1) ; adapter: down-proj + body (one tensor-core kernel) ; up-proj * scale -> delta
@@ -67,18 +108,33 @@ int hoigen_encoder_forward(const hoigen_encoder_weights* w, const hoigen_encoder
     HOIGEN_TRY(hoigen_adapter_block(buf->xb, l == 0 ? nullptr : buf->delta2, buf->adapter_kv + size_t(l) * batch * n_max * 128,
                                     mask, &aw, nullptr, buf->delta, batch, n_max, s));
     // (2) x += adapter ; x += out_proj(attention(ln_1(x)))
-    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, l == 0 ? nullptr : buf->delta2, w->ad_up_b + o768,
-                                       w->ln1_w + o768, w->ln1_b + o768, buf->h, nullptr, M, s));
-    HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->qkv_w + size_t(l) * 3 * D * D, D, M, 3 * D, D,
-                    w->qkv_b + size_t(l) * 3 * D, HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->qkv, 3 * D, s));
+    if (fold) {
+      HOIGEN_TRY(hoigen_add_rowstats768(buf->x, buf->delta, l == 0 ? nullptr : buf->delta2, w->ad_up_b + o768, buf->h,
+                                        buf->row_stats, M, s));
+      HOIGEN_TRY(gemm_ln(buf->h, D, (const uint16_t*)w->qkv_wf + size_t(l) * 3 * D * D, D, M, 3 * D, D,
+                         w->qkv_bf + size_t(l) * 3 * D, HOIGEN_ACT_NONE, buf->row_stats, w->qkv_colsum + size_t(l) * 3 * D,
+                         buf->qkv, 3 * D, s));
+    } else {
+      HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, l == 0 ? nullptr : buf->delta2, w->ad_up_b + o768,
+                                         w->ln1_w + o768, w->ln1_b + o768, buf->h, nullptr, M, s));
+      HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->qkv_w + size_t(l) * 3 * D * D, D, M, 3 * D, D,
+                      w->qkv_b + size_t(l) * 3 * D, HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->qkv, 3 * D, s));
+    }
     HOIGEN_TRY(hoigen_attention(buf->qkv, buf->attn, batch, s));
     HOIGEN_TRY(gemm(buf->attn, D, (const uint16_t*)w->out_w + size_t(l) * D * D, D, M, D, D, w->out_b + o768,
                     HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->delta, D, s));
     // (3) mlp: c_proj(quickgelu(c_fc(ln_2(x)))) -> delta2, added by the next adapter block (or the final LayerNorm)
-    HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, nullptr, nullptr, w->ln2_w + o768, w->ln2_b + o768, buf->h,
-                                       l + 1 < num_layers ? buf->xb : nullptr, M, s));
-    HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->fc_w + size_t(l) * 4 * D * D, D, M, 4 * D, D,
-                    w->fc_b + size_t(l) * 4 * D, HOIGEN_ACT_QUICKGELU, nullptr, nullptr, 0, nullptr, 0, buf->mlp, 4 * D, s));
+    if (fold) {
+      HOIGEN_TRY(hoigen_add_rowstats768(buf->x, buf->delta, nullptr, nullptr, buf->xb, buf->row_stats, M, s));
+      HOIGEN_TRY(gemm_ln(buf->xb, D, (const uint16_t*)w->fc_wf + size_t(l) * 4 * D * D, D, M, 4 * D, D,
+                         w->fc_bf + size_t(l) * 4 * D, HOIGEN_ACT_QUICKGELU, buf->row_stats, w->fc_colsum + size_t(l) * 4 * D,
+                         buf->mlp, 4 * D, s));
+    } else {
+      HOIGEN_TRY(hoigen_add_layernorm768(buf->x, buf->delta, nullptr, nullptr, w->ln2_w + o768, w->ln2_b + o768, buf->h,
+                                         l + 1 < num_layers ? buf->xb : nullptr, M, s));
+      HOIGEN_TRY(gemm(buf->h, D, (const uint16_t*)w->fc_w + size_t(l) * 4 * D * D, D, M, 4 * D, D,
+                      w->fc_b + size_t(l) * 4 * D, HOIGEN_ACT_QUICKGELU, nullptr, nullptr, 0, nullptr, 0, buf->mlp, 4 * D, s));
+    }
     HOIGEN_TRY(gemm(buf->mlp, 4 * D, (const uint16_t*)w->proj_w + size_t(l) * D * 4 * D, 4 * D, M, D, 4 * D,
                     w->proj_b + o768, HOIGEN_ACT_NONE, nullptr, nullptr, 0, nullptr, 0, buf->delta2, D, s));
   }
@@ -107,30 +163,51 @@ int hoigen_score_pairs(const hoigen_score_weights* w, const hoigen_score_buffers
   HOIGEN_CHECK_ARG(L >= C, "score_pairs: ld_logits (%d) < num_classes (%d)", L, C);
   // The affinity is LINEAR in the reference (phi = f W^T + b, no exp: U:1156-1158), so the bias is carried exactly
   // in fp32 through the second GEMM's epilogue: ((f W^T + b) Y)/s = (f W^T) Y / s + (b Y)/s, bias_term = b Y.
+  const bool exp_aff = w->affinity == 1;     // textbook Tip-Adapter exp(beta (f W^T + b)) instead of the reference's linear phi
+  HOIGEN_CHECK_ARG(w->affinity == 0 || w->affinity == 1, "score_pairs: affinity must be 0 (linear) or 1 (exp)");
   // ---- per-image terms: global-CLIP cache (U:1133-1138) and DINO cache (U:1112-1115) -------------------------
   // g = feat_global / |feat_global|  (U:960) = token row 0 of each image
   HOIGEN_TRY(hoigen_rows_to_bf16(tokens, 197L * 512, batch, 512, 1, buf->g_bf16, s));
-  HOIGEN_TRY(gemm(buf->g_bf16, 512, w->global_keys, 512, batch, N, 512, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
-                  nullptr, 0, buf->phi_img, N, s));
-  HOIGEN_TRY(gemm(buf->phi_img, N, w->label_t[2], N, batch, C, N, w->global_bias_term, HOIGEN_ACT_NONE, w->colscale_global,
-                  nullptr, 0, buf->img_logits, C, nullptr, 0, s));
+  if (exp_aff) {
+    HOIGEN_CHECK_ARG(w->global_bias != nullptr, "score_pairs: the exp affinity needs global_bias");
+    HOIGEN_TRY(gemm_exp(buf->g_bf16, 512, w->global_keys, 512, batch, N, 512, w->global_bias, w->beta, buf->phi_img, N, s));
+  } else {
+    HOIGEN_TRY(gemm(buf->g_bf16, 512, w->global_keys, 512, batch, N, 512, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                    nullptr, 0, buf->phi_img, N, s));
+  }
+  HOIGEN_TRY(gemm(buf->phi_img, N, w->label_t[2], N, batch, C, N, exp_aff ? nullptr : w->global_bias_term, HOIGEN_ACT_NONE,
+                  w->colscale_global, nullptr, 0, buf->img_logits, C, nullptr, 0, s));
   if (dino_feats) {
     HOIGEN_CHECK_ARG(w->dino_keys != nullptr, "score_pairs: dino features given but no dino cache");
     HOIGEN_TRY(hoigen_rows_to_bf16(dino_feats, 2048, batch, 2048, 0, buf->d_bf16, s));
-    HOIGEN_TRY(gemm(buf->d_bf16, 2048, w->dino_keys, 2048, batch, N, 2048, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
-                    nullptr, 0, buf->phi_img, N, s));
-    HOIGEN_TRY(gemm(buf->phi_img, N, w->label_t[2], N, batch, C, N, w->dino_bias_term, HOIGEN_ACT_NONE, w->colscale_dino,
-                    buf->img_logits, C, buf->img_logits, C, nullptr, 0, s));
+    if (exp_aff) {
+      HOIGEN_CHECK_ARG(w->dino_bias != nullptr, "score_pairs: the exp affinity needs dino_bias");
+      HOIGEN_TRY(gemm_exp(buf->d_bf16, 2048, w->dino_keys, 2048, batch, N, 2048, w->dino_bias, w->beta, buf->phi_img, N, s));
+    } else {
+      HOIGEN_TRY(gemm(buf->d_bf16, 2048, w->dino_keys, 2048, batch, N, 2048, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                      nullptr, 0, buf->phi_img, N, s));
+    }
+    HOIGEN_TRY(gemm(buf->phi_img, N, w->label_t[2], N, batch, C, N, exp_aff ? nullptr : w->dino_bias_term, HOIGEN_ACT_NONE,
+                    w->colscale_dino, buf->img_logits, C, buf->img_logits, C, nullptr, 0, s));
   }
   if (ktot == 0) return HOIGEN_OK;
-  HOIGEN_TRY(hoigen_broadcast_image_logits(buf->img_logits, pair_off, batch, ktot, C, L, buf->logits, s));
-  // ---- pair terms: three cache branches (H, O, U) + text classifier, accumulated in place ---------------------
-  for (int x = 0; x < 3; ++x) {
-    const uint16_t* f = (const uint16_t*)buf->pair_feat_bf16 + size_t(x) * ktot * 512;
-    HOIGEN_TRY(gemm(f, 512, w->cache_keys[x], 512, ktot, N, 512, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
-                    nullptr, 0, buf->phi, N, s));
-    HOIGEN_TRY(gemm(buf->phi, N, w->label_t[x], N, ktot, C, N, w->bias_term[x], HOIGEN_ACT_NONE, w->colscale[x], buf->logits, L,
-                    buf->logits, L, nullptr, 0, s));
+  // ---- pair terms: three cache branches (H, O, U) + text classifier ---------------------------------------------
+  static const bool unfused = getenv("HOIGEN_CACHE_UNFUSED") != nullptr;      // A/B switch: the two-GEMM form through `phi`
+  if (buf->cache_parts && C <= 128 && !unfused) {
+    // ONE fused GEMM - f - GEMM kernel for the three branches (no `phi` in memory) + the fixed-order combine pass
+    HOIGEN_TRY(hoigen_score_cache_fused(w, buf->pair_feat_bf16, exp_aff ? w->cache_bias : nullptr, buf->img_logits, pair_off, batch,
+                                        ktot, w->affinity, w->beta, buf->cache_parts, buf->logits, L, s));
+  } else {
+    HOIGEN_CHECK_ARG(!exp_aff, "score_pairs: the exp affinity is implemented by the fused kernel (num_classes <= 128, cache_parts)");
+    HOIGEN_CHECK_ARG(buf->phi != nullptr, "score_pairs: the two-GEMM form needs the phi workspace");
+    HOIGEN_TRY(hoigen_broadcast_image_logits(buf->img_logits, pair_off, batch, ktot, C, L, buf->logits, s));
+    for (int x = 0; x < 3; ++x) {
+      const uint16_t* f = (const uint16_t*)buf->pair_feat_bf16 + size_t(x) * ktot * 512;
+      HOIGEN_TRY(gemm(f, 512, w->cache_keys[x], 512, ktot, N, 512, nullptr, HOIGEN_ACT_NONE, nullptr, nullptr, 0,
+                      nullptr, 0, buf->phi, N, s));
+      HOIGEN_TRY(gemm(buf->phi, N, w->label_t[x], N, ktot, C, N, w->bias_term[x], HOIGEN_ACT_NONE, w->colscale[x], buf->logits, L,
+                      buf->logits, L, nullptr, 0, s));
+    }
   }
   const uint16_t* fu = (const uint16_t*)buf->pair_feat_bf16 + size_t(2) * ktot * 512;
   HOIGEN_TRY(gemm(fu, 512, w->text_w, 512, ktot, C, 512, nullptr, HOIGEN_ACT_NONE, w->colscale_text, buf->logits, L,

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -114,8 +115,15 @@ class UPT(nn.Module):
                  min_instances: int = 3, max_instances: int = 15, hyper_lambda: float = 2.8,
                  object_class_to_target_class: Optional[List[List[int]]] = None, dino: bool = True,
                  clip_global: bool = True, dataset: str = "hicodet", fold_cache: bool = False,
-                 scoring_precision: str = "bf16"):
+                 scoring_precision: str = "bf16", cache_affinity: str = "linear", cache_beta: float = 10.0):
         super().__init__()
+        # "linear" = the reference (phi = f W^T + b, U:1156-1158).  "exp" = the textbook Tip-Adapter exp(beta (f W^T + b)) that
+        # north_star names as an option of the fused cache kernel; it is NOT the reference's arithmetic (oracle: affinity='exp')
+        if cache_affinity not in ("linear", "exp"):
+            raise ValueError("cache_affinity must be 'linear' or 'exp'")
+        if cache_affinity == "exp" and (fold_cache or scoring_precision != "bf16" or num_classes > 128):
+            raise ValueError("cache_affinity='exp' runs in the fused bf16 cache kernel only (num_classes <= 128, no fold_cache)")
+        self.cache_affinity, self.cache_beta = cache_affinity, float(cache_beta)
         # "bf16" (default, the benchmarked path): bf16 operands, fp32 accumulation, logits within 1e-2 of the reference.
         # "fp32": RoI features and every cache / text product in fp32-equivalent arithmetic (3 x bf16 split on the same
         # tcgen05 GEMM, hoigen_score_pairs_fp32): logits within 1e-4 of the reference GIVEN the same encoder features
@@ -278,6 +286,17 @@ class UPT(nn.Module):
             p["colscale_dino"] = f32(self.dino_cache_logit.float() / lens("dino_sample_len", Yu))
             sw.dino_keys, sw.dino_bias_term = p["dino_keys"].data_ptr(), p["dino_bias_term"].data_ptr()
             sw.colscale_dino = p["colscale_dino"].data_ptr()
+        sw.affinity, sw.beta = (1 if self.cache_affinity == "exp" else 0), self.cache_beta
+        if self.cache_affinity == "exp":
+            for i, X in enumerate(("H", "O", "U")):
+                p[f"cache_bias_{X}"] = f32(padc(getattr(self, f"gen_adapter_{X}_bias").detach()))
+                sw.cache_bias[i] = p[f"cache_bias_{X}"].data_ptr()
+            if self.clip_global:
+                p["global_bias"] = f32(padc(self.global_cache_bias.detach()))
+                sw.global_bias = p["global_bias"].data_ptr()
+            if self.dino:
+                p["dino_bias"] = f32(padc(self.dino_cache_bias.detach()))
+                sw.dino_bias = p["dino_bias"].data_ptr()
         p["text_w"] = bf(self.adapter_union_weight)
         p["colscale_text"] = f32(self.logit_scale_text.float().expand(C_))
         sw.text_w, sw.colscale_text = p["text_w"].data_ptr(), p["colscale_text"].data_ptr()
@@ -605,7 +624,12 @@ class UPT(nn.Module):
         else:
             sb = _cabi.ScoreBuffers()
             sb.pair_feat_bf16 = pf_bf16.data_ptr()
-            sb.phi = self._buf("phi", ktot * N, torch.bfloat16, dev).data_ptr()
+            if Cn <= 128 and not self.fold_cache and os.environ.get("HOIGEN_CACHE_UNFUSED") is None:
+                # the three cache branches as ONE fused GEMM-f-GEMM kernel: no (Ktot x N) `phi` buffer at all
+                nbytes = int(_cabi.load().hoigen_cache_fused_workspace_bytes(ktot, Cn))
+                sb.cache_parts = self._buf("cache_parts", nbytes // 4, torch.float32, dev).data_ptr()
+            else:
+                sb.phi = self._buf("phi", ktot * N, torch.bfloat16, dev).data_ptr()
             sb.phi_img = self._buf("phi_img", B * N, torch.bfloat16, dev).data_ptr()
             sb.g_bf16 = self._buf("g_bf16", B * 512, torch.bfloat16, dev).data_ptr()
             sb.d_bf16 = self._buf("d_bf16", B * 2048, torch.bfloat16, dev).data_ptr()

@@ -9,6 +9,7 @@ PyTorch fallback — on a machine without the CUDA library `forward` raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -114,6 +115,8 @@ class VisionTransformer(nn.Module):
         self.transformer = Transformer(width, layers, use_adapter, adapter_layers, adapter_num_layers)
         self.ln_post = _ln_params(width)
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        # LayerNorm folded into the QKV / c_fc GEMM epilogues (default); False = stand-alone LayerNorm passes writing `h`
+        self.fold_layernorm = os.environ.get("HOIGEN_NO_LN_FOLD") is None
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_struct = None
         self._ws_cache: Dict[Tuple[int, int], Tuple[Dict[str, torch.Tensor], object]] = {}   # (batch, stream) -> buffers
@@ -169,8 +172,23 @@ class VisionTransformer(nn.Module):
             "ad_norm2_w": f32(st(lambda b: dl(b).norm2.weight)), "ad_norm2_b": f32(st(lambda b: dl(b).norm2.bias)),
             "ad_norm3_w": f32(st(lambda b: dl(b).norm3.weight)), "ad_norm3_b": f32(st(lambda b: dl(b).norm3.bias)),
         }
-        assert set(p) == set(_cabi.ENCODER_WEIGHT_FIELDS)
-        s = _cabi.EncoderWeights()
+        # LayerNorm folded into the QKV / c_fc GEMMs (C:457-458): LN(x) W^T + b = rstd (x (W diag(gamma))^T - mean colsum) + (b + W beta)
+        # with colsum taken over the bf16-ROUNDED folded weight (what the tensor cores multiply), so the mean term cancels
+        # against the same numbers the GEMM accumulated
+        def folded(get_w, get_b, get_ln):
+            wf, cs, bf_ = [], [], []
+            for blk in blocks:
+                W, bvec, ln = get_w(blk).detach().float().to(dev), get_b(blk).detach().float().to(dev), get_ln(blk)
+                w_g = (W * ln.weight.detach().float().to(dev)[None, :]).to(torch.bfloat16)
+                wf.append(w_g)
+                cs.append(w_g.float().sum(dim=1))
+                bf_.append(bvec + W @ ln.bias.detach().float().to(dev))
+            return torch.stack(wf).contiguous(), torch.stack(cs).contiguous(), torch.stack(bf_).contiguous()
+        if self.fold_layernorm:
+            p["qkv_wf"], p["qkv_colsum"], p["qkv_bf"] = folded(lambda b: b.attn.in_proj_weight, lambda b: b.attn.in_proj_bias, lambda b: b.ln_1)
+            p["fc_wf"], p["fc_colsum"], p["fc_bf"] = folded(lambda b: b.mlp.c_fc.weight, lambda b: b.mlp.c_fc.bias, lambda b: b.ln_2)
+        assert set(p) <= set(_cabi.ENCODER_WEIGHT_FIELDS)
+        s = _cabi.EncoderWeights()          # (the folded-LayerNorm fields stay NULL when fold_layernorm is off)
         for k, v in p.items():
             setattr(s, k, v.data_ptr())
         self._packed, self._packed_struct = p, s
@@ -190,7 +208,7 @@ class VisionTransformer(nn.Module):
                 "patches": e((batch * 196, 768), bf), "patch_emb": e((batch * 196, 768), f32),
                 "x": e((M, 768), f32), "xb": e((M, 768), bf), "h": e((M, 768), bf), "qkv": e((M, 2304), bf),
                 "attn": e((M, 768), bf), "mlp": e((M, 3072), bf), "delta": e((M, 768), bf), "delta2": e((M, 768), bf),
-                "adapter_kv": e((12, batch * MAX_PRIOR_TOKENS, 128), f32),
+                "adapter_kv": e((12, batch * MAX_PRIOR_TOKENS, 128), f32), "row_stats": e((M, 2), f32),
                 "tokens_out": e((M, 512), f32),
             }
             s = _cabi.EncoderBuffers()

@@ -38,7 +38,7 @@ enum hoigen_status {
   HOIGEN_ERR_CAPACITY = -4   /* caller-provided output buffer too small */
 };
 
-enum hoigen_act { HOIGEN_ACT_NONE = 0, HOIGEN_ACT_QUICKGELU = 1, HOIGEN_ACT_RELU = 2 };
+enum hoigen_act { HOIGEN_ACT_NONE = 0, HOIGEN_ACT_QUICKGELU = 1, HOIGEN_ACT_RELU = 2, HOIGEN_ACT_EXP = 3 /* exp(act_param * v) */ };
 
 HOIGEN_API int hoigen_abi_version(void);
 HOIGEN_API const char* hoigen_last_error(void);
@@ -80,6 +80,13 @@ typedef struct {
                             (by default only K >= 2048 is split, where it pays) */
   int32_t split_k;       /* one-CTA tiles only: 0 = choose, n >= 1 = cut every tile's k-range into n units that run on
                             different SMs; partials meet in a workspace and are summed in split order (deterministic) */
+  float act_param;       /* HOIGEN_ACT_EXP: beta */
+  /* LayerNorm folded into the GEMM (C:443-445, C:457-458: ln_1 -> attn.in_proj, ln_2 -> mlp.c_fc).  a = bf16 copy of
+   * the RAW rows x, w = W . diag(gamma) (bf16); out = act(rstd[m] * (a w^T - mean[m] * ln_colsum[n]) + bias[n]) with
+   * ln_stats[m] = {mean, rstd} of row m (fp32, eps 1e-5; hoigen_add_rowstats768), ln_colsum[n] = sum_k w[n][k] and
+   * bias = b + W beta.  NULL = plain GEMM.  Excludes colscale. */
+  const float* ln_stats;   /* (M, 2) */
+  const float* ln_colsum;  /* (N) */
 } hoigen_gemm_params;
 
 HOIGEN_API int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream);
@@ -104,6 +111,11 @@ HOIGEN_API int hoigen_layernorm768(const float* x, const float* gamma, const flo
 HOIGEN_API int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2_bf16, const float* col_bias,
                                        const float* gamma, const float* beta, void* out_bf16, void* x_bf16, int32_t rows,
                                        hoigen_stream_t stream);
+/* The same pass with the LayerNorm itself left to the consuming GEMM (hoigen_gemm_params.ln_stats): x += delta (+ delta2)
+ * (+ col_bias row) in fp32, x_bf16 = bf16 copy of the updated rows (the GEMM's A operand), stats (rows,2) = {mean, rstd}
+ * of each updated row (fp32, eps 1e-5: C:409-415). */
+HOIGEN_API int hoigen_add_rowstats768(float* x, const void* delta_bf16, const void* delta2_bf16, const float* col_bias,
+                                      void* x_bf16, float* stats, int32_t rows, hoigen_stream_t stream);
 /* Adapter cross-attention K/V of the prior tokens for all layers: kv[l][tok][0:64]=K, [64:128]=V  (C:63-66).
  * in_proj_w (layers,192,64) rows [q;k;v], in_proj_b (layers,192); prior (tokens,64). */
 HOIGEN_API int hoigen_adapter_kv(const float* prior, const float* in_proj_w, const float* in_proj_b, float* kv,
@@ -167,6 +179,9 @@ typedef struct {
   const float* ad_linear1_b;                               /* (12,128) */
   const float* ad_linear2_b;                               /* (12,64) */
   const float* ad_norm2_w; const float* ad_norm2_b; const float* ad_norm3_w; const float* ad_norm3_b; /* (12,64) */
+  /* LayerNorm folded into the QKV / c_fc GEMMs (north_star item 1; C:457-458).  All six NULL = unfused LayerNorm passes. */
+  const void* qkv_wf; const float* qkv_colsum; const float* qkv_bf;   /* bf16 (12,2304,768) = in_proj_weight . diag(ln_1.weight); (12,2304) row sums of it; (12,2304) in_proj_bias + in_proj_weight ln_1.bias */
+  const void* fc_wf; const float* fc_colsum; const float* fc_bf;      /* the same for mlp.c_fc and ln_2: (12,3072,768), (12,3072), (12,3072) */
 } hoigen_encoder_weights;
 
 typedef struct {            /* caller-owned workspace, M = B*197 */
@@ -181,6 +196,7 @@ typedef struct {            /* caller-owned workspace, M = B*197 */
   void* delta;              /* bf16 (M, 768)   adapter up-proj / attention out-proj output awaiting its residual add */
   void* delta2;             /* bf16 (M, 768)   MLP c_proj output awaiting its residual add (applied by the next adapter block) */
   float* adapter_kv;        /* f32  (12, B*n_max, 128) */
+  float* row_stats;         /* f32  (M, 2)     {mean, rstd} of the stream rows (LayerNorm folded into the next GEMM) */
   float* tokens_out;        /* f32  (M, 512)   OUTPUT: ln_post(x) @ proj for all tokens; row b*197 = feat_global[b],
                                                rows b*197+1.. = feat_local[b] token-major (C:503-506) */
 } hoigen_encoder_buffers;
@@ -237,11 +253,19 @@ typedef struct {                   /* scoring weights, packed once at build time
   const float* colscale_dino;      /* f32 (C)        dino_cache_logit / dino_sample_len */
   const void* text_w;              /* bf16 (C,512)   adapter_union_weight */
   const float* colscale_text;      /* f32 (C)        logit_scale_text broadcast */
+  /* cache affinity: 0 = linear phi = f W^T + b (THE REFERENCE, U:1156-1158; b enters through the bias_term carriers),
+   * 1 = exp(beta (f W^T + b)) (textbook Tip-Adapter, north_star item 3; not a parity mode).  The fields below are read
+   * only for affinity 1. */
+  int32_t affinity;
+  float beta;
+  const float* cache_bias[3];      /* f32 (N)        gen_adapter_{H,O,U}_bias, zero-padded */
+  const float* global_bias;        /* f32 (N)        global_cache_bias */
+  const float* dino_bias;          /* f32 (N)        dino_cache_bias */
 } hoigen_score_weights;
 
 typedef struct {                   /* caller-owned workspace */
   const void* pair_feat_bf16;      /* bf16 [3][Ktot][512] from hoigen_roi_pair_features */
-  void* phi;                       /* bf16 (Ktot, N) */
+  void* phi;                       /* bf16 (Ktot, N)   two-GEMM form only (may be NULL when cache_parts is given) */
   void* phi_img;                   /* bf16 (B, N) */
   void* g_bf16;                    /* bf16 (B, 512) */
   void* d_bf16;                    /* bf16 (B, 2048) */
@@ -249,6 +273,9 @@ typedef struct {                   /* caller-owned workspace */
   float* logits;                   /* f32 (Ktot, ld_logits)   OUTPUT: columns [0, C) of every row */
   int64_t ld_logits;               /* floats between logits rows, >= C (0 = C).  A multiple of 4 keeps the accumulating
                                       GEMM epilogues (6 terms summed into this buffer) on their float4 path */
+  float* cache_parts;              /* f32, hoigen_cache_fused_workspace_bytes(Ktot, C) bytes: when given and C <= 128 the three
+                                      cache branches run as ONE fused GEMM-f-GEMM kernel (hoigen_score_cache_fused) and `phi`
+                                      is not touched; NULL = two GEMMs per branch through `phi` */
 } hoigen_score_buffers;
 
 /* logits = sum_X scale_X * ((f_X W_X^T + b_X) Y_X)/s_X + scale_T f_U T^T + per-image global/DINO cache terms.
@@ -256,6 +283,19 @@ typedef struct {                   /* caller-owned workspace */
 HOIGEN_API int hoigen_score_pairs(const hoigen_score_weights* w, const hoigen_score_buffers* buf, const float* tokens,
                                   const float* dino_feats, const int32_t* pair_off, int32_t batch, int32_t ktot,
                                   hoigen_stream_t stream);
+
+/* The three cache branches of hoigen_score_pairs as ONE fused GEMM - f - GEMM tcgen05 kernel (north_star item 3; U:1156-1163):
+ * per 64 cache rows S = f W^T lives in TMEM, is converted to bf16 in registers and consumed from TMEM by the second MMA
+ * against the label tile — the (Ktot x N) affinity matrix never exists in memory.  affinity 0 = the reference's linear
+ * phi = f W^T + b (bias carried exactly in fp32 by the combine pass), 1 = exp(beta (f W^T + b)) (textbook Tip-Adapter;
+ * cache_bias[3] = gen_adapter_{H,O,U}_bias, (N) fp32, zero-padded).  Writes logits[i][c] = img_logits[image(i)][c] (or 0 if
+ * NULL) + sum_X colscale_X[c] ((bias_term_X[c]) + L_X[i][c]) in a fixed summation order.  num_classes <= 128.
+ * parts: fp32 workspace of hoigen_cache_fused_workspace_bytes(ktot, num_classes) bytes. */
+HOIGEN_API int64_t hoigen_cache_fused_workspace_bytes(int32_t ktot, int32_t num_classes);
+HOIGEN_API int hoigen_score_cache_fused(const hoigen_score_weights* w, const void* pair_feat_bf16,
+                                        const float* const* cache_bias, const float* img_logits, const int32_t* pair_off,
+                                        int32_t batch, int32_t ktot, int32_t affinity, float beta, float* parts,
+                                        float* logits, int32_t ld_logits, hoigen_stream_t stream);
 
 /* fp32 rows -> three bf16 planes (hi, mid, lo; hi + mid + lo == x to 2^-24) laid side by side along K:
  * pattern 6 = [hi|hi|hi|mid|mid|lo] (multiplied against a weight packed as [hi|mid|lo|hi|mid|hi]: every cross term down

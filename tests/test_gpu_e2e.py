@@ -664,3 +664,27 @@ def test_wire_format_kernels_match_torch_form(cuda_device):
     tiny.add(steps[0].packed)
     with pytest.raises(ValueError):
         tiny.finish()
+
+
+def test_exp_affinity_matches_oracle(cuda_device):
+    """cache_affinity='exp' (the textbook Tip-Adapter exp(beta (f W^T + b)) north_star names as an option of the fused
+    cache kernel; NOT the reference's arithmetic): against the oracle's affinity='exp' on identical encoder features."""
+    from hoigen_b200 import synthetic as S
+    from hoigen_b200.detector import UPT
+    from oracle import hoi_forward_ref as O
+    enc, head = S.make_encoder_state(0), S.make_head_state(117, 1024, seed=2)
+    m = UPT.from_state(enc, head, cache_affinity="exp", cache_beta=10.0).to(cuda_device)
+    B = 3
+    props = S.make_region_props(B, 5, 6, ragged=True, seed=800)
+    imgs, dino = S.make_images(B, seed=801), S.make_dino_features(B, seed=802)
+    o_dets, o_int = O.hoi_forward(imgs, props, dino, enc, head, return_intermediates=True, affinity="exp")
+    dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                           return_intermediates=True, encoder_tokens=o_int["tokens"].reshape(B * 197, 512))
+    worst, scale = 0.0, 0.0
+    for b in range(B):
+        for k in ("pairing", "labels", "objects"):
+            assert torch.equal(dets[b][k].cpu(), o_dets[b][k]), (b, k)
+        worst = max(worst, (inter["logits"][b].cpu() - o_int["logits"][b]).abs().max().item())
+        scale = max(scale, o_int["logits"][b].abs().max().item())
+    print(f"exp affinity: logits max-abs vs oracle {worst:.3e} (|logit| max {scale:.3f})")
+    assert worst <= 1e-2 * max(1.0, scale), worst

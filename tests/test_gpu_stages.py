@@ -495,3 +495,123 @@ def test_rows_split3_restores_fp32(cuda_device):
             rec = o.double().sum(1)
         rel = ((rec - ref.double()).abs() / ref.abs().double().clamp_min(1e-30)).max().item()
         assert rel <= (2.0 ** -22 if normalize else 2.0 ** -23), (pattern, normalize, rel)
+
+
+@pytest.mark.parametrize("M,N,bn,act", [(12608, 2304, 0, 0), (1000, 3072, 2256, 1), (300, 776, 128, 0), (700, 768, 2192, 1)])
+def test_gemm_layernorm_folded_epilogue(cuda_device, M, N, bn, act):
+    """LayerNorm folded into the GEMM (north_star item 1; C:457-458 ln -> Linear): A = bf16 copy of the RAW rows,
+    W' = W diag(gamma), epilogue rstd (acc - mean colsum) + (b + W beta) [+ QuickGELU] from per-row (mean, rstd).  Checked
+    against LayerNorm -> Linear in fp32 on rows with a sizeable mean (the cancellation the fold has to survive) through
+    both TMA-store recipes (compile-time epilogues), the generic epilogue and the one-CTA kernel; and hoigen_add_rowstats768,
+    the residual pass that emits the statistics."""
+    from hoigen_b200 import _cabi
+    K = 768
+    g = torch.Generator(device="cpu").manual_seed(M + N + act)
+    x = torch.randn(M, K, generator=g) * 1.3 + 0.4 * torch.randn(M, 1, generator=g)          # per-row mean ~ 0.3 sigma
+    delta = (0.2 * torch.randn(M, K, generator=g)).bfloat16()
+    gamma, beta = 1.0 + 0.1 * torch.randn(K, generator=g), 0.1 * torch.randn(K, generator=g)
+    W = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = 0.02 * torch.randn(N, generator=g)
+    # the residual pass: x += delta, bf16 copy, statistics
+    xd = x.to(cuda_device).contiguous()
+    dd = delta.to(cuda_device).contiguous()
+    xb = torch.empty(M, K, device=cuda_device, dtype=torch.bfloat16)
+    stats = torch.empty(M, 2, device=cuda_device)
+    _cabi.call("hoigen_add_rowstats768", xd.data_ptr(), dd.data_ptr(), None, None, xb.data_ptr(), stats.data_ptr(), M)
+    x1 = x + delta.float()
+    assert (xd.cpu() - x1).abs().max().item() < 1e-6
+    assert torch.equal(xb.cpu(), x1.bfloat16())
+    mean, var = x1.mean(-1), x1.var(-1, unbiased=False)
+    assert (stats[:, 0].cpu() - mean).abs().max().item() < 1e-5
+    assert ((stats[:, 1].cpu() - torch.rsqrt(var + 1e-5)).abs() / torch.rsqrt(var + 1e-5)).max().item() < 1e-5
+    # the folded GEMM
+    wf = (W * gamma[None, :]).bfloat16()
+    colsum = wf.float().sum(1).to(cuda_device).contiguous()
+    bf_ = (b + W @ beta).to(cuda_device).contiguous()
+    out = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.gemm_bf16(xb, wf.to(cuda_device).contiguous(), bias=bf_, act=act, out_bf16=out, block_n=bn, ln_stats=stats, ln_colsum=colsum)
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x1, (K,), gamma, beta), W, b)
+    if act == 1:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    err = (out.float().cpu() - ref).abs().max().item()
+    # unfused path for scale: h = bf16(LN(x)) @ bf16(W)
+    h = torch.nn.functional.layer_norm(x1, (K,), gamma, beta).bfloat16().float()
+    unf = torch.nn.functional.linear(h, W.bfloat16().float(), b)
+    if act == 1:
+        unf = unf * torch.sigmoid(1.702 * unf)
+    err_unf = (unf.bfloat16().float() - ref).abs().max().item()
+    print(f"LN-folded GEMM M={M} N={N} bn={bn} act={act}: max-abs err {err:.3e} (unfused bf16 path {err_unf:.3e}, |ref| max {ref.abs().max():.2f})")
+    assert err < 2.0 * err_unf + 2e-3, (err, err_unf)
+    # fp32-output generic epilogue: tighter (only the bf16 operand rounding remains)
+    of = torch.zeros(M, N, device=cuda_device)
+    _cabi.gemm_bf16(xb, wf.to(cuda_device).contiguous(), bias=bf_, act=0, out_f32=of, block_n=bn, ln_stats=stats, ln_colsum=colsum)
+    ref0 = torch.nn.functional.linear(torch.nn.functional.layer_norm(x1, (K,), gamma, beta), W, b)
+    assert (of.cpu() - ref0).abs().max().item() < 2.0 * err_unf + 2e-3
+
+
+def _cache_fused_reference(f, W, Y, bias, affinity, beta):
+    """torch restatement of what the fused kernel computes: S in fp32, P = bf16(aff(S)), L = P @ Y in fp32."""
+    S = f.float() @ W.float().t()
+    if affinity == 1:
+        S = torch.exp(beta * (S + bias[None, :]))
+    return S.bfloat16().float() @ Y.float()
+
+
+@pytest.mark.parametrize("ktot,N,C,affinity", [(7680, 4096, 117, 0), (500, 1000, 24, 0), (129, 4104, 117, 0), (1000, 16384, 117, 0),
+                                               (640, 2048, 117, 1), (77, 264, 24, 1)])
+def test_cache_fused_kernel(cuda_device, ktot, N, C, affinity):
+    """hoigen_score_cache_fused (ONE GEMM - f - GEMM kernel for the three cache branches, U:1156-1163; optional exp affinity):
+    ragged pair counts (partial 128-row tiles), cache sizes that are not multiples of the 64-row chunk or of the split,
+    narrow and wide classifiers, per-image terms added by the combine pass — against a torch restatement with the same
+    bf16 rounding of the affinity tile; and run twice: bit-identical (fixed summation order, no atomics)."""
+    import ctypes as C_
+    from hoigen_b200 import _cabi
+    g = torch.Generator(device="cpu").manual_seed(ktot + N + C)
+    dev = cuda_device
+    B = 5
+    bounds = sorted(torch.randint(0, ktot + 1, (B - 1,), generator=g).tolist())
+    pair_off = torch.tensor([0] + bounds + [ktot], dtype=torch.int32, device=dev)
+    f = torch.randn(3, ktot, 512, generator=g)
+    f = (f / f.norm(dim=-1, keepdim=True)).bfloat16()
+    sw = _cabi.ScoreWeights()
+    sw.num_classes, sw.cache_rows, sw.affinity, sw.beta = C, N, affinity, 5.0
+    keep, refs = [], []
+    img = torch.randn(B, C, generator=g)
+    ref = torch.zeros(ktot, C)
+    for b in range(B):
+        ref[pair_off[b].item(): pair_off[b + 1].item()] = img[b]
+    for x in range(3):
+        Wk = torch.randn(N, 512, generator=g)
+        Wk = (Wk / Wk.norm(dim=-1, keepdim=True)).bfloat16()
+        Y = (torch.rand(N, C, generator=g) < 0.02).float()
+        Y[torch.arange(N), torch.randint(0, C, (N,), generator=g)] = 1.0
+        bias = -1.0 + 0.01 * torch.randn(N, generator=g)
+        bt = torch.randn(C, generator=g)
+        cs = torch.rand(C, generator=g) + 0.5
+        L = _cache_fused_reference(f[x], Wk, Y, bias, affinity, 5.0)
+        ref += cs[None, :] * ((bt[None, :] if affinity == 0 else 0.0) + L)
+        t = [Wk.to(dev).contiguous(), Y.t().bfloat16().to(dev).contiguous(), bias.to(dev).contiguous(), bt.to(dev).contiguous(),
+             cs.to(dev).contiguous()]
+        keep.append(t)
+        sw.cache_keys[x], sw.label_t[x], sw.cache_bias[x] = t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr()
+        sw.bias_term[x], sw.colscale[x] = t[3].data_ptr(), t[4].data_ptr()
+    fd = f.to(dev).contiguous()
+    imgd = img.to(dev).contiguous()
+    nbytes = int(_cabi.load().hoigen_cache_fused_workspace_bytes(ktot, C))
+    assert nbytes > 0
+    parts = torch.empty(nbytes // 4, device=dev)
+    ld = (C + 3) // 4 * 4
+    outs = []
+    bias_ptrs = (C_.c_void_p * 3)(*[keep[x][2].data_ptr() for x in range(3)])
+    for rep in range(2):
+        logits = torch.full((ktot, ld), 7.0, device=dev)
+        _cabi.call("hoigen_score_cache_fused", C_.byref(sw), fd.data_ptr(), bias_ptrs, imgd.data_ptr(), pair_off.data_ptr(), B, ktot,
+                   affinity, 5.0, parts.data_ptr(), logits.data_ptr(), ld)
+        outs.append(logits.cpu())
+    assert torch.equal(outs[0], outs[1]), "not bit-reproducible"
+    got = outs[0][:, :C]
+    assert (outs[0][:, C:] == 7.0).all()
+    scale = max(1.0, ref.abs().max().item())
+    err = (got - ref).abs().max().item()
+    print(f"fused cache kernel ktot={ktot} N={N} C={C} affinity={affinity}: max-abs err {err:.3e} (|ref| max {ref.abs().max():.2f})")
+    assert err < 2e-3 * scale, err
