@@ -20,6 +20,8 @@
 // terms, the exact bias carriers and the parts of every branch and split into the logits.
 //
 // Replaces U:1156-1163 (gen_feat cache branches) for C <= 128; wider classifiers (600 HOI triplets) keep the two-GEMM form.
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -30,13 +32,12 @@ constexpr int CF_ROWS = 128;        // pairs per unit
 constexpr int CF_CHUNK = 64;        // cache rows per chunk
 constexpr int CF_K = 512;           // feature width
 constexpr int CF_KB = CF_K / 64;    // 8 k-blocks per chunk
-constexpr int CF_WSTAGES = 16;
-constexpr int CF_YSTAGES = 3;
-constexpr int CF_W_BYTES = CF_CHUNK * 128;          // 8 KiB
+constexpr int CF_KB_BYTES = CF_CHUNK * 128;         // 8 KiB: one [64 cache rows x 64 k] block
+constexpr int CF_W_BYTES = CF_KB * CF_KB_BYTES;     // 64 KiB: one chunk of keys
 constexpr int CF_Y_BYTES = 128 * 128;               // 16 KiB (C_pad <= 128 rows of 128 B)
-constexpr int CF_SMEM_Y = CF_WSTAGES * CF_W_BYTES;
-constexpr int CF_SMEM_BAR = CF_SMEM_Y + CF_YSTAGES * CF_Y_BYTES;
-constexpr int CF_SMEM_BYTES = CF_SMEM_BAR + 512 + 1024;
+constexpr int CF_SMEM_Y = 2 * CF_W_BYTES;
+constexpr int CF_SMEM_BAR = CF_SMEM_Y + 2 * CF_Y_BYTES;
+constexpr int CF_SMEM_BYTES = CF_SMEM_BAR + 256 + 1024;
 constexpr uint32_t CF_TM_F = 0, CF_TM_S = 256, CF_TM_L = 384;
 
 struct CacheFusedArgs {
@@ -45,14 +46,33 @@ struct CacheFusedArgs {
   float* parts;                   // [3 * nsplit][ktot_pad][c_pad]
   int ktot, ktot_pad, n_rows, c_pad, nsplit, chunks_per_split, num_tiles;
   float beta_log2e;
+  int debug;   // diagnostics (HOIGEN_CF_DEBUG): 1 = no S MMAs, 2 = no L MMAs, 3 = no F-tile load, 4 = no S -> P conversion, 5 = no TMA loads
 };
 
-__device__ __forceinline__ void ld_global_v4x2(const void* p, uint32_t (&r)[8]) {
-  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%8];\n\tld.global.nc.v4.u32 {%4, %5, %6, %7}, [%8 + 16];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
+// 4 x 32 bytes of one pair row in ONE statement, so that the eight loads are in flight together (separate volatile asm
+// statements would be kept in program order with the TMEM stores between them: one L2 round trip each)
+__device__ __forceinline__ void ld_global_128B(const void* p, uint32_t (&r)[32]) {
+  asm volatile(
+      "ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%32];\n\t"
+      "ld.global.nc.v4.u32 {%4, %5, %6, %7}, [%32 + 16];\n\t"
+      "ld.global.nc.v4.u32 {%8, %9, %10, %11}, [%32 + 32];\n\t"
+      "ld.global.nc.v4.u32 {%12, %13, %14, %15}, [%32 + 48];\n\t"
+      "ld.global.nc.v4.u32 {%16, %17, %18, %19}, [%32 + 64];\n\t"
+      "ld.global.nc.v4.u32 {%20, %21, %22, %23}, [%32 + 80];\n\t"
+      "ld.global.nc.v4.u32 {%24, %25, %26, %27}, [%32 + 96];\n\t"
+      "ld.global.nc.v4.u32 {%28, %29, %30, %31}, [%32 + 112];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "l"(p));
 }
 
+// Barriers are per CHUNK (64 cache rows), not per k-block: a tcgen05.commit costs a few hundred cycles of the single MMA
+// thread's time, and with 128x64x16 MMAs (32-64 cycles each) one commit per four MMAs was measured to dominate the
+// kernel (185 us of 266 with the MMAs themselves disabled).  Chunk c uses key stage / label stage / S-P buffer c & 1:
+//   wfull[b], yfull[b]  TMA landed                      sdone[b]  S_c complete: converters read it, producer refills keys
+//   pready[b]           P_c written (8 warps)           ldone[b]  L += P_c Y_c complete: S/P buffer + label stage free
 template <bool EXP>
 __global__ void __launch_bounds__(CF_THREADS, 1)
 cache_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
@@ -64,29 +84,24 @@ cache_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_consta
   uint8_t* sm = smem_raw + (base - raw_addr);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CF_SMEM_BAR);
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t bar_wfull = bar0;                          // [16]
-  const uint32_t bar_wempty = bar0 + 8u * CF_WSTAGES;       // [16]
-  const uint32_t bar_yfull = bar0 + 16u * CF_WSTAGES;       // [3]
-  const uint32_t bar_yempty = bar_yfull + 8u * CF_YSTAGES;  // [3]
-  const uint32_t bar_sready = bar_yempty + 8u * CF_YSTAGES; // [2]  S_j complete in TMEM
-  const uint32_t bar_pready = bar_sready + 16;              // [2]  P_j written (8 warps)
-  const uint32_t bar_sfree = bar_pready + 16;               // [2]  P_j consumed by the L MMA: the buffer may take S_{j+2}
-  const uint32_t bar_fready = bar_sfree + 16;               // F tile of the unit in TMEM (8 warps)
-  const uint32_t bar_ffree = bar_fready + 8;                // every S MMA of the unit done: F may be overwritten
-  const uint32_t bar_lready = bar_ffree + 8;                // L of the unit complete
-  const uint32_t bar_lfree = bar_lready + 8;                // L drained by the epilogue (8 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + CF_SMEM_BAR + 480);
+  const uint32_t bar_wfull = bar0;             // [2]
+  const uint32_t bar_yfull = bar0 + 16;        // [2]
+  const uint32_t bar_sdone = bar0 + 32;        // [2]
+  const uint32_t bar_pready = bar0 + 48;       // [2]
+  const uint32_t bar_ldone = bar0 + 64;        // [2]
+  const uint32_t bar_fready = bar0 + 80;       // F tile of the unit in TMEM (8 warps)
+  const uint32_t bar_lfree = bar0 + 88;        // L drained by the unit's epilogue (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + CF_SMEM_BAR + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW0); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmY0); tma_prefetch_desc(&tmY1); tma_prefetch_desc(&tmY2);
-    for (int s = 0; s < CF_WSTAGES; ++s) { mbar_init(bar_wfull + 8u * s, 1); mbar_init(bar_wempty + 8u * s, 1); }
-    for (int s = 0; s < CF_YSTAGES; ++s) { mbar_init(bar_yfull + 8u * s, 1); mbar_init(bar_yempty + 8u * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_sready + 8u * s, 1); mbar_init(bar_pready + 8u * s, 8); mbar_init(bar_sfree + 8u * s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_wfull + 8u * s, 1); mbar_init(bar_yfull + 8u * s, 1); mbar_init(bar_sdone + 8u * s, 1);
+      mbar_init(bar_pready + 8u * s, 8); mbar_init(bar_ldone + 8u * s, 1);
+    }
     mbar_init(bar_fready, 8);
-    mbar_init(bar_ffree, 1);
-    mbar_init(bar_lready, 1);
     mbar_init(bar_lfree, 8);
     fence_barrier_init();
   }
@@ -110,29 +125,35 @@ cache_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_consta
     x = p / g.nsplit;
     sp = p - x * g.nsplit;
   };
+  // chunk c is the (c >> 1)-th user of buffer c & 1: its barriers complete with parity (c >> 1) & 1
+  auto par = [](long c) { return uint32_t(c >> 1) & 1u; };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int ws = 0, ys = 0;
-      uint32_t wph = 0, yph = 0;
+      long cj = 0;
       for (int i = 0; i < n_local; ++i) {
         int x, sp, tile;
         decode(first + i * stride, x, sp, tile);
         const CUtensorMap* tw = x == 0 ? &tmW0 : (x == 1 ? &tmW1 : &tmW2);
         const CUtensorMap* ty = x == 0 ? &tmY0 : (x == 1 ? &tmY1 : &tmY2);
-        for (int j = 0; j < C; ++j) {
+        for (int j = 0; j < C; ++j, ++cj) {
+          const int b = int(cj & 1);
           const int n0 = (sp * C + j) * CF_CHUNK;
-          for (int kb = 0; kb < CF_KB; ++kb) {
-            mbar_wait(bar_wempty + 8u * ws, wph ^ 1u);
-            mbar_arrive_expect_tx(bar_wfull + 8u * ws, CF_W_BYTES);
-            tma_load_2d(base + ws * CF_W_BYTES, tw, bar_wfull + 8u * ws, kb * 64, n0);
-            if (++ws == CF_WSTAGES) { ws = 0; wph ^= 1u; }
+          if (cj >= 2) mbar_wait(bar_sdone + 8u * b, par(cj - 2));      // S_{c-2} has read key stage b
+          if (g.debug == 5) mbar_arrive(bar_wfull + 8u * b);
+          else {
+            mbar_arrive_expect_tx(bar_wfull + 8u * b, CF_W_BYTES);
+#pragma unroll
+            for (int kb = 0; kb < CF_KB; ++kb)
+              tma_load_2d(base + b * CF_W_BYTES + kb * CF_KB_BYTES, tw, bar_wfull + 8u * b, kb * 64, n0);
           }
-          mbar_wait(bar_yempty + 8u * ys, yph ^ 1u);
-          mbar_arrive_expect_tx(bar_yfull + 8u * ys, uint32_t(g.c_pad) * 128u);
-          tma_load_2d(base + CF_SMEM_Y + ys * CF_Y_BYTES, ty, bar_yfull + 8u * ys, n0, 0);
-          if (++ys == CF_YSTAGES) { ys = 0; yph ^= 1u; }
+          if (cj >= 2) mbar_wait(bar_ldone + 8u * b, par(cj - 2));      // L of chunk c-2 has read label stage b
+          if (g.debug == 5) mbar_arrive(bar_yfull + 8u * b);
+          else {
+            mbar_arrive_expect_tx(bar_yfull + 8u * b, uint32_t(g.c_pad) * 128u);
+            tma_load_2d(base + CF_SMEM_Y + b * CF_Y_BYTES, ty, bar_yfull + 8u * b, n0, 0);
+          }
         }
       }
     }
@@ -141,52 +162,44 @@ cache_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_consta
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(CF_ROWS, CF_CHUNK);
       const uint32_t idesc_l = make_idesc_bf16(CF_ROWS, g.c_pad);
-      int ws = 0, ys = 0;
-      uint32_t wph = 0, yph = 0;
-      long cj = 0;                          // global chunk counter: S/P buffer = cj & 1, its phase = (cj >> 1) & 1
+      long cj = 0;
       for (int i = 0; i < n_local; ++i) {
         mbar_wait(bar_fready, i & 1u);
         tc_fence_after();
         auto issue_l = [&](int j, long c) {
           const int b = int(c & 1);
-          mbar_wait(bar_pready + 8u * b, uint32_t(c >> 1) & 1u);
-          mbar_wait(bar_yfull + 8u * ys, yph);
+          mbar_wait(bar_pready + 8u * b, par(c));
+          mbar_wait(bar_yfull + 8u * b, par(c));
           if (j == 0 && i > 0) mbar_wait(bar_lfree, (i - 1) & 1u);      // previous unit's L drained
           tc_fence_after();
-          const uint32_t ydesc_addr = base + CF_SMEM_Y + ys * CF_Y_BYTES;
+          const uint32_t yaddr = base + CF_SMEM_Y + b * CF_Y_BYTES;
           const uint32_t pbase = tmem + CF_TM_S + uint32_t(b * 64);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            if (g.debug == 2) break;
             // P k-step t: k-values 16t..16t+15 = packed columns {0, 8, 32, 40}[t] of the buffer (each converter thread
             // overlays ITS OWN 32 S columns with its 16 packed P columns)
             const uint32_t pcol = uint32_t((k >> 1) * 32 + (k & 1) * 8);
-            umma_bf16_ts(tmem + CF_TM_L, pbase + pcol, make_sdesc_sw128(ydesc_addr + k * 32), idesc_l, (j > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ts(tmem + CF_TM_L, pbase + pcol, make_sdesc_sw128(yaddr + k * 32), idesc_l, (j > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(bar_yempty + 8u * ys);
-          tc_commit(bar_sfree + 8u * b);
-          if (++ys == CF_YSTAGES) { ys = 0; yph ^= 1u; }
+          tc_commit(bar_ldone + 8u * b);
         };
         for (int j = 0; j < C; ++j, ++cj) {
           const int b = int(cj & 1);
-          if (cj >= 2) mbar_wait(bar_sfree + 8u * b, uint32_t((cj >> 1) - 1) & 1u);   // P_{cj-2} consumed
+          if (cj >= 2) mbar_wait(bar_ldone + 8u * b, par(cj - 2));     // P_{c-2} consumed: buffer b may take S_c
+          mbar_wait(bar_wfull + 8u * b, par(cj));
           tc_fence_after();
-          for (int kb = 0; kb < CF_KB; ++kb) {
-            mbar_wait(bar_wfull + 8u * ws, wph);
-            tc_fence_after();
-            const uint32_t waddr = base + ws * CF_W_BYTES;
+          const uint32_t waddr = base + b * CF_W_BYTES;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ts(tmem + CF_TM_S + uint32_t(b * 64), tmem + CF_TM_F + uint32_t(kb * 32 + k * 8),
-                           make_sdesc_sw128(waddr + k * 32), idesc_s, (kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit(bar_wempty + 8u * ws);
-            if (++ws == CF_WSTAGES) { ws = 0; wph ^= 1u; }
+          for (int kk = 0; kk < CF_KB * 4; ++kk) {
+            if (g.debug == 1) break;
+            umma_bf16_ts(tmem + CF_TM_S + uint32_t(b * 64), tmem + CF_TM_F + uint32_t(kk * 8),
+                         make_sdesc_sw128(waddr + (kk >> 2) * CF_KB_BYTES + (kk & 3) * 32), idesc_s, kk > 0 ? 1u : 0u);
           }
-          tc_commit(bar_sready + 8u * b);
-          if (j == C - 1) tc_commit(bar_ffree);
+          tc_commit(bar_sdone + 8u * b);
           if (j > 0) issue_l(j - 1, cj - 1);       // lags one chunk: the conversion of S_{j-1} ran under the MMAs of S_j
         }
         issue_l(C - 1, cj - 1);
-        tc_commit(bar_lready);
       }
     }
   } else {
@@ -199,30 +212,35 @@ cache_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_consta
     auto load_f = [&](int i) {
       int x, sp, tile;
       decode(first + i * stride, x, sp, tile);
-      if (i > 0) mbar_wait(bar_ffree, (i - 1) & 1u);        // every S MMA of the previous unit has read F
-      tc_fence_after();
       const int row = tile * CF_ROWS + rrow;
       const bool ok = row < g.ktot;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(g.feat + (size_t(x) * g.ktot + (ok ? row : 0)) * CF_K) + half * 512;
-#pragma unroll 4
-      for (int it = 0; it < 16; ++it) {
-        uint32_t v[8];
-        if (ok) ld_global_v4x2(src + it * 32, v);
+#pragma unroll 1
+      for (int it = 0; it < 4; ++it) {
+        if (g.debug == 3) break;
+        uint32_t v[32];
+        if (ok) ld_global_128B(src + it * 128, v);
         else {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = 0u;
+          for (int q = 0; q < 32; ++q) v[q] = 0u;
         }
-        tmem_st_32x32b_x8(tmem + lane_addr + CF_TM_F + uint32_t(half * 128 + it * 8), v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t w8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w8[e] = v[q * 8 + e];
+          tmem_st_32x32b_x8(tmem + lane_addr + CF_TM_F + uint32_t(half * 128 + it * 32 + q * 8), w8);
+        }
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_fready);
     };
-    auto epilogue = [&](int i) {
+    auto epilogue = [&](int i, long c_last) {
       int x, sp, tile;
       decode(first + i * stride, x, sp, tile);
-      mbar_wait(bar_lready, i & 1u);
+      mbar_wait(bar_ldone + 8u * uint32_t(c_last & 1), par(c_last));     // L of the unit's last chunk complete
       tc_fence_after();
       const int row = tile * CF_ROWS + rrow;
       const int cols = g.c_pad / 2;                        // columns of this thread (multiple of 8)
@@ -251,8 +269,14 @@ cache_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_consta
       for (int j = 0; j < C; ++j, ++cj) {
         const int b = int(cj & 1);
         const uint32_t sbuf = tmem + lane_addr + CF_TM_S + uint32_t(b * 64 + half * 32);
-        mbar_wait(bar_sready + 8u * b, uint32_t(cj >> 1) & 1u);
+        mbar_wait(bar_sdone + 8u * b, par(cj));
         tc_fence_after();
+        if (g.debug == 4) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_pready + 8u * b);
+          continue;
+        }
         uint32_t r[32];
         tmem_ld_32x32b_x32(sbuf, r);
         tmem_wait_ld();
@@ -282,10 +306,10 @@ cache_fused_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_pready + 8u * b);
       }
-      // unit boundary: the next unit's F tile first (its S MMAs can start while this unit's L finishes), then this
-      // unit's epilogue
+      // unit boundary: every S MMA of this unit is complete (sdone of its last chunk was observed above), so the F columns
+      // may take the next unit's tile now — its S MMAs then start while this unit's last L MMA and epilogue finish
       if (i + 1 < n_local) load_f(i + 1);
-      epilogue(i);
+      epilogue(i, cj - 1);
     }
   }
 
@@ -360,6 +384,8 @@ int hoigen_score_cache_fused(const hoigen_score_weights* w, const void* pair_fea
   g.c_pad = (C + 15) / 16 * 16;
   g.num_tiles = g.ktot_pad / 128;
   g.beta_log2e = beta * 1.4426950408889634f;
+  g.debug = getenv("HOIGEN_CF_DEBUG") ? atoi(getenv("HOIGEN_CF_DEBUG")) : 0;
+  const int force_split = getenv("HOIGEN_CF_NSPLIT") ? atoi(getenv("HOIGEN_CF_NSPLIT")) : 0;
   // cache split: fewest rounds x (unit cost + per-unit F-tile load), units = 3 * nsplit * tiles over one CTA per SM
   const int chunks = (N + CF_CHUNK - 1) / CF_CHUNK;
   int best = 1;
@@ -372,6 +398,7 @@ int hoigen_score_cache_fused(const hoigen_score_weights* w, const void* pair_fea
     const double cost = double(rounds) * (double(cps) * (1024.0 + 2.0 * g.c_pad) + 3500.0);
     if (cost < best_cost) { best_cost = cost; best = ns; }
   }
+  if (force_split == 1 || force_split == 2 || force_split == 4) best = force_split;
   g.nsplit = best;
   g.chunks_per_split = (chunks + best - 1) / best;
   const CUtensorMap* tw[3];

@@ -4,6 +4,10 @@
 //
 // Reference: CLIP_models_adapter_prior2.py:489-496 (embed + ln_pre), :409-415 (LayerNorm, fp32, eps 1e-5),
 // :183-203 + :51-72 (Adapter.forward / TransformerDecoderLayer.forward_post).
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -65,7 +69,7 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
                     __nv_bfloat16* __restrict__ out_bf16, int rows, const __nv_bfloat16* __restrict__ delta = nullptr,
                     float* __restrict__ stream_out = nullptr, const __nv_bfloat16* __restrict__ delta_b = nullptr,
                     __nv_bfloat16* __restrict__ stream_bf16 = nullptr, const float* __restrict__ col_bias = nullptr,
-                    float2* __restrict__ stats_out = nullptr) {
+                    float2* __restrict__ stats_out = nullptr, int keep_l2 = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;   // one warp per row; rows per CTA = launch-time choice
   if (row >= rows) return;
@@ -83,7 +87,7 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
   } else {
     const float4* src = reinterpret_cast<const float4*>(in + long(row) * WIDTH);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) v[j] = __ldcs(src + lane + 32 * j);   // streamed: the fp32 stream is not re-read before ~100 MB of other traffic
+    for (int j = 0; j < 6; ++j) v[j] = keep_l2 ? src[lane + 32 * j] : __ldcs(src + lane + 32 * j);   // streamed: the fp32 stream is not re-read before ~100 MB of other traffic
     if (delta) {
       const uint2* dsrc = reinterpret_cast<const uint2*>(delta + long(row) * WIDTH);
 #pragma unroll
@@ -110,7 +114,9 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
       }
       float4* dst = reinterpret_cast<float4*>(stream_out + long(row) * WIDTH);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) __stcs(dst + lane + 32 * j, v[j]);   // evict-first: keep L2 for h / delta / qkv, which ARE re-read
+      for (int j = 0; j < 6; ++j) {   // evict-first: keep L2 for h / delta / qkv, which ARE re-read
+        if (keep_l2) dst[lane + 32 * j] = v[j]; else __stcs(dst + lane + 32 * j, v[j]);
+      }
       if (stream_bf16) {   // bf16 copy of the updated stream: the next adapter block's tensor-core operand
         uint2* dstb = reinterpret_cast<uint2*>(stream_bf16 + long(row) * WIDTH);
 #pragma unroll
@@ -154,6 +160,105 @@ layernorm768_kernel(const float* __restrict__ in, const float* __restrict__ cls,
 }
 
 // ------------------------------------------------------------------------------------------------
+// The encoder's residual pass (25 launches per forward): x += delta (+ delta_b) (+ col_bias), write x (fp32) [+ its bf16
+// copy], then LayerNorm -> bf16 h  (STATS: emit (mean, rstd) instead of h).  PERSISTENT and software-pipelined: a fixed grid
+// of resident CTAs (no partial last wave: 1576 CTAs on 148 x 4 slots used to run 2.66 waves as 3), one warp per row, and
+// the loads of the warp's NEXT row are in flight while the current row is reduced, normalised and stored.
+// ------------------------------------------------------------------------------------------------
+struct RowRegs {
+  float4 x[6];
+  uint2 d[6];
+  uint2 e[6];
+};
+
+__device__ __forceinline__ void residual_row_load(RowRegs& r, const float* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
+                                                  const __nv_bfloat16* __restrict__ delta_b, long row, int lane) {
+  const float4* src = reinterpret_cast<const float4*>(x + row * WIDTH);
+  const uint2* d1 = reinterpret_cast<const uint2*>(delta + row * WIDTH);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) r.x[j] = __ldcs(src + lane + 32 * j);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) r.d[j] = __ldg(d1 + lane + 32 * j);
+  if (delta_b) {
+    const uint2* d2 = reinterpret_cast<const uint2*>(delta_b + row * WIDTH);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) r.e[j] = __ldg(d2 + lane + 32 * j);
+  }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(256, 2)
+residual_ln768_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta, const __nv_bfloat16* __restrict__ delta_b,
+                      const float* __restrict__ col_bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ stream_bf16,
+                      float2* __restrict__ stats_out, int rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long stride = long(gridDim.x) * (blockDim.x >> 5);
+  long row = long(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  RowRegs cur, nxt;
+  residual_row_load(cur, x, delta, delta_b, row, lane);
+  for (; row < rows; row += stride) {
+    const long nrow = row + stride;
+    if (nrow < rows) residual_row_load(nxt, x, delta, delta_b, nrow, lane);      // in flight during this row's work
+    float4 v[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      v[j] = cur.x[j];
+      v[j].x += __uint_as_float(cur.d[j].x << 16); v[j].y += __uint_as_float(cur.d[j].x & 0xffff0000u);
+      v[j].z += __uint_as_float(cur.d[j].y << 16); v[j].w += __uint_as_float(cur.d[j].y & 0xffff0000u);
+    }
+    if (delta_b) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        v[j].x += __uint_as_float(cur.e[j].x << 16); v[j].y += __uint_as_float(cur.e[j].x & 0xffff0000u);
+        v[j].z += __uint_as_float(cur.e[j].y << 16); v[j].w += __uint_as_float(cur.e[j].y & 0xffff0000u);
+      }
+    }
+    if (col_bias) {   // bias row of the GEMM that produced delta (kept out of that GEMM's epilogue); L1-resident
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(col_bias) + lane + 32 * j);
+        v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(x + row * WIDTH);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) __stcs(dst + lane + 32 * j, v[j]);   // evict-first: keep L2 for h / delta / qkv, which ARE re-read
+    if (stream_bf16) {   // bf16 copy of the updated stream: the next adapter block's tensor-core operand
+      uint2* dstb = reinterpret_cast<uint2*>(stream_bf16 + row * WIDTH);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) dstb[lane + 32 * j] = make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = warp_sum(s) * (1.0f / WIDTH);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / WIDTH) + 1e-5f);
+    if (STATS) {
+      if (lane == 0) stats_out[row] = make_float2(mean, rstd);
+    } else {
+      const float4* g4 = reinterpret_cast<const float4*>(gamma);
+      const float4* b4 = reinterpret_cast<const float4*>(beta);
+      uint2* oh = reinterpret_cast<uint2*>(out_bf16 + row * WIDTH);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float4 g = __ldg(g4 + lane + 32 * j), bb = __ldg(b4 + lane + 32 * j);
+        oh[lane + 32 * j] = make_uint2(pack_bf16x2((v[j].x - mean) * rstd * g.x + bb.x, (v[j].y - mean) * rstd * g.y + bb.y),
+                                       pack_bf16x2((v[j].z - mean) * rstd * g.z + bb.z, (v[j].w - mean) * rstd * g.w + bb.w));
+      }
+    }
+    cur = nxt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Adapter K/V of the prior tokens for every layer:  KV[l][tok][0:64] = Wk_l p + bk_l, [64:128] = Wv_l p + bv_l
 // (rows 64..191 of multihead_attn.in_proj_weight, C:63-66).  grid = (ceil(tokens/16), layers), 128 threads.
 // ------------------------------------------------------------------------------------------------
@@ -184,6 +289,12 @@ adapter_kv_kernel(const float* __restrict__ prior, const float* __restrict__ in_
 #pragma unroll
   for (int r = 0; r < 16; ++r)
     if (t0 + r < tokens) kv[(long(l) * tokens + t0 + r) * 128 + o] = acc[r];
+}
+
+// experiment switch (HOIGEN_LN_KEEP_L2=1): default caching of the fp32 stream in the residual passes instead of streaming it
+static int ln_keep_l2() {
+  static const int v = getenv("HOIGEN_LN_KEEP_L2") ? atoi(getenv("HOIGEN_LN_KEEP_L2")) : 0;
+  return v;
 }
 
 }  // namespace hoigen
@@ -232,11 +343,19 @@ int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2
   HOIGEN_CHECK_ARG(x && delta_bf16 && gamma && beta && out_bf16 && rows > 0, "add_layernorm768: bad arguments");
   KernelScope ks("add_layernorm768", reinterpret_cast<cudaStream_t>(stream), 0,
                  double(rows) * WIDTH * (4 + 2 + 4 + 2 + (delta2_bf16 ? 2 : 0) + (x_bf16 ? 2 : 0)));
-  constexpr int rpc = 8;   // 2 / 4 rows per CTA (small enough to sit next to a resident GEMM CTA) measured the same step time
-  layernorm768_kernel<false><<<(rows + rpc - 1) / rpc, rpc * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, nullptr, nullptr, gamma, beta, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows,
-      reinterpret_cast<const __nv_bfloat16*>(delta_bf16), x, reinterpret_cast<const __nv_bfloat16*>(delta2_bf16),
-      reinterpret_cast<__nv_bfloat16*>(x_bf16), col_bias);
+  static const bool legacy = getenv("HOIGEN_LN_LEGACY") != nullptr;      // A/B switch: the one-wave-per-8-rows kernel
+  if (legacy) {
+    constexpr int rpc = 8;
+    layernorm768_kernel<false><<<(rows + rpc - 1) / rpc, rpc * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, nullptr, nullptr, gamma, beta, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows,
+        reinterpret_cast<const __nv_bfloat16*>(delta_bf16), x, reinterpret_cast<const __nv_bfloat16*>(delta2_bf16),
+        reinterpret_cast<__nv_bfloat16*>(x_bf16), col_bias, nullptr, ln_keep_l2());
+  } else {
+    const int grid = std::min((rows + 7) / 8, 2 * num_sms());
+    residual_ln768_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, reinterpret_cast<const __nv_bfloat16*>(delta_bf16), reinterpret_cast<const __nv_bfloat16*>(delta2_bf16), col_bias, gamma,
+        beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), reinterpret_cast<__nv_bfloat16*>(x_bf16), nullptr, rows);
+  }
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
@@ -247,11 +366,10 @@ int hoigen_add_rowstats768(float* x, const void* delta_bf16, const void* delta2_
   HOIGEN_CHECK_ARG(x && delta_bf16 && x_bf16 && stats && rows > 0, "add_rowstats768: bad arguments");
   KernelScope ks("add_rowstats768", reinterpret_cast<cudaStream_t>(stream), 0,
                  double(rows) * WIDTH * (4 + 2 + 4 + 2 + (delta2_bf16 ? 2 : 0)) + double(rows) * 8);
-  constexpr int rpc = 8;
-  layernorm768_kernel<false, true><<<(rows + rpc - 1) / rpc, rpc * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rows, reinterpret_cast<const __nv_bfloat16*>(delta_bf16), x,
-      reinterpret_cast<const __nv_bfloat16*>(delta2_bf16), reinterpret_cast<__nv_bfloat16*>(x_bf16), col_bias,
-      reinterpret_cast<float2*>(stats));
+  const int grid = std::min((rows + 7) / 8, 2 * num_sms());
+  residual_ln768_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<const __nv_bfloat16*>(delta_bf16), reinterpret_cast<const __nv_bfloat16*>(delta2_bf16), col_bias, nullptr,
+      nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(x_bf16), reinterpret_cast<float2*>(stats), rows);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }

@@ -126,16 +126,19 @@ __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const 
   float v[CW];
 #pragma unroll
   for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
-  if (has_ln) {   // rstd * (x W'^T - mean * colsum): s_cs holds colsum here
-    const float nm = -ln_mean;
+  if (has_ln) {
+    // rstd * (x W'^T - mean * colsum) + bias' = fma(rstd, acc, fma(-rstd * mean, colsum, bias')): two FMAs per element
+    // (s_cs holds colsum here)
+    const float nmr = -ln_mean * ln_rstd;
 #pragma unroll
     for (int j = 0; j < CW; j += 4) {
       const float4 c = *reinterpret_cast<const float4*>(s_cs + j);
-      v[j] = ln_rstd * fmaf(nm, c.x, v[j]); v[j + 1] = ln_rstd * fmaf(nm, c.y, v[j + 1]);
-      v[j + 2] = ln_rstd * fmaf(nm, c.z, v[j + 2]); v[j + 3] = ln_rstd * fmaf(nm, c.w, v[j + 3]);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_bias) b = *reinterpret_cast<const float4*>(s_bias + j);
+      v[j] = fmaf(ln_rstd, v[j], fmaf(nmr, c.x, b.x)); v[j + 1] = fmaf(ln_rstd, v[j + 1], fmaf(nmr, c.y, b.y));
+      v[j + 2] = fmaf(ln_rstd, v[j + 2], fmaf(nmr, c.z, b.z)); v[j + 3] = fmaf(ln_rstd, v[j + 3], fmaf(nmr, c.w, b.w));
     }
-  }
-  if (has_bias) {
+  } else if (has_bias) {
 #pragma unroll
     for (int j = 0; j < CW; j += 4) {
       const float4 b = *reinterpret_cast<const float4*>(s_bias + j);

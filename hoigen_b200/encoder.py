@@ -115,8 +115,11 @@ class VisionTransformer(nn.Module):
         self.transformer = Transformer(width, layers, use_adapter, adapter_layers, adapter_num_layers)
         self.ln_post = _ln_params(width)
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
-        # LayerNorm folded into the QKV / c_fc GEMM epilogues (default); False = stand-alone LayerNorm passes writing `h`
-        self.fold_layernorm = os.environ.get("HOIGEN_NO_LN_FOLD") is None
+        # LayerNorm folded into the QKV / c_fc GEMM epilogues (north_star item 1; `True` or HOIGEN_LN_FOLD=1) instead of
+        # stand-alone LayerNorm passes writing `h`.  Same results (tests), measured on B200 (tools/ln_fold_probe.py): the
+        # fold's two extra FMAs + colsum reads per output lengthen the epilogue-bound K = 768 GEMMs by 2.1-2.2 us each
+        # (+52 us per step) while the residual pass gets 1.1 us shorter (-26 us per step) => off by default.
+        self.fold_layernorm = os.environ.get("HOIGEN_LN_FOLD") is not None
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_struct = None
         self._ws_cache: Dict[Tuple[int, int], Tuple[Dict[str, torch.Tensor], object]] = {}   # (batch, stream) -> buffers

@@ -688,3 +688,25 @@ def test_exp_affinity_matches_oracle(cuda_device):
         scale = max(scale, o_int["logits"][b].abs().max().item())
     print(f"exp affinity: logits max-abs vs oracle {worst:.3e} (|logit| max {scale:.3f})")
     assert worst <= 1e-2 * max(1.0, scale), worst
+
+
+def test_layernorm_folded_encoder_matches_reference_golden(cuda_device):
+    """VisionTransformer.fold_layernorm = True (LayerNorm folded into the QKV / c_fc GEMM epilogues, north_star item 1; off by
+    default for speed, see encoder.py): same detections as the reference, logits inside the same 1e-2 bar."""
+    c = CASES["hico117_n4096_b4"]
+    gold = np.load("tests/golden/hico117_n4096_b4.npz")
+    m, enc, head = _build_case(c, cuda_device)
+    vt = m.clip_head.image_encoder
+    vt.fold_layernorm = True
+    vt.invalidate_packed()
+    imgs, props, dino = inputs_for(c)
+    dets, inter = m.forward_from_proposals(imgs.to(cuda_device), _props_to(props, cuda_device), dino.to(cuda_device),
+                                           return_intermediates=True)
+    assert vt._packed_struct.qkv_wf and vt._packed_struct.fc_colsum        # the folded weights were packed and used
+    worst = 0.0
+    for b, d in enumerate(dets):
+        for k in ("pairing", "labels", "objects"):
+            assert np.array_equal(d[k].cpu().numpy(), gold[f"{k}_{b}"]), k
+        worst = max(worst, float(np.abs(inter["logits"][b].cpu().numpy() - gold[f"logits_{b}"]).max()))
+    print(f"LayerNorm-folded encoder: logits max-abs err vs reference {worst:.3e}")
+    assert worst <= LOGIT_TOL, worst
