@@ -93,8 +93,8 @@ def workload_config(args, world, w):
         "batches_in_flight": (f"{getattr(args, 'streams', 1)} (consecutive steps alternate over {getattr(args, 'streams', 1)} CUDA streams and "
                               "overlap on the GPU; kernel_breakdown / roofline are single-stream per-launch times)"),
         "collective": ("none (single GPU)" if world == 1 else
-                       f"NCCL all-gather of the detections in the compact wire format, one chunk every {args.gather_every} steps on a "
-                       "side stream, drained inside each timed region"),
+                       "all ranks receive all detections: per step a compact wire record (9 B/triplet) pushed into every peer's buffer over "
+                       "NVLink peer memory (copy engines), one barrier + unpack per sweep, inside each timed region"),
     }
 
 
@@ -417,16 +417,22 @@ def run_b200(args, rank, world, local_rank):
             bx, sc, lb = dev_packed[r]
             return model.launch_packed(dev_imgs[r], bx, sc, lb, n_list, nh_list, dino_features_for(r, st))
 
-    # The path's one collective (N > 1): every rank ends up with every rank's detections.  The sweep's detections travel in
-    # the compact wire format (9 B per triplet instead of 36), one fixed-capacity chunk every `--gather-every` steps on a
-    # side stream, no host synchronisation inside the loop; drained (headers read, records widened back to int64) inside
-    # the timed region.
-    exchange = SweepExchange(world, B, w["K"] * max_row_len * B, n_per * B, dev, chunk_steps=args.gather_every) if world > 1 else None
+    # The path's one exchange (N > 1): every rank ends up with every rank's detections.  Each step's detections are packed
+    # on a side stream into the compact wire record (9 B per triplet instead of 36) and pushed into every peer's receive
+    # buffer over NVLink peer memory (copy engines, no SM, no rank waits for another); no host synchronisation inside the
+    # loop; drained (one barrier, headers read, records widened back to int64) inside the timed region.
+    exchange = (SweepExchange(world, B, w["K"] * max_row_len * B, n_per * B, dev, max_steps=max(args.steps, args.gather_every))
+                if world > 1 else None)
+
+    def exchange_add(packed, pend):
+        if exchange.full:                  # sweeps longer than the exchanger's capacity (the sustained block): drain first
+            exchange.finish()
+        exchange.add(packed, pend)
 
     def finish_resident(pend):
         dets = model.finish(pend)          # the path's device->host read (triplet offsets) + detection views
         if exchange is not None:
-            exchange.add(dets.packed, pend)
+            exchange_add(dets.packed, pend)
         return dets
 
     def drain_exchanges():
@@ -505,7 +511,7 @@ def run_b200(args, rank, world, local_rank):
         dets = model.finish(pend)
         pk = dets.packed
         if exchange is not None:
-            exchange.add(pk, pend)
+            exchange_add(pk, pend)
         m = pk.scores.numel()
         ho = host_out[i % 2]
         if ho["keep"] is not None:
@@ -573,7 +579,6 @@ def run_b200(args, rank, world, local_rank):
     sustained = None
     if args.sustain_s > 0:
         n_sus = max(args.steps, int(math.ceil(args.sustain_s * 1e3 / ms_step)))
-        n_sus = (n_sus + args.gather_every - 1) // args.gather_every * args.gather_every
         clocks.active = True
         s0, s1, _ = timed_resident(0, n_sus)
         barrier()
@@ -740,6 +745,10 @@ def run_b200(args, rank, world, local_rank):
         "folded_cache_variant": folded,
         "full_with_dino_r50": full_dino,
     }
+    if exchange is not None:
+        line["detection_exchange"] = {"transport": exchange.transport, "record_capacity_bytes": exchange.cap,
+                                      "bytes_per_triplet": 9, "sweep_capacity_steps": exchange.max_steps,
+                                      "why_not_p2p": getattr(exchange, "why_not_p2p", None)}
     print(json.dumps(line))
     out_dir = ROOT / "gpurun_out"
     if out_dir.exists():
@@ -775,8 +784,8 @@ def main():
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams that consecutive steps alternate over: 2 (default) = two batches overlap on the GPU, "
                          "1 = strictly one batch at a time")
-    ap.add_argument("--gather-every", type=int, default=4,
-                    help="N>1 only: steps per exchanged chunk of detections (one non-blocking all-gather per chunk on a side stream)")
+    ap.add_argument("--gather-every", type=int, default=32,
+                    help="N>1 only: steps a sweep of the detection exchange holds at most before it is drained (barrier + unpack)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.rotate <= 0:

@@ -354,146 +354,170 @@ def unpack_wire_torch(record: torch.Tensor, max_images: int, size):
 class SweepExchange:
     """All ranks end up with every rank's detections of a sweep (an evaluation pass over a dataset shard).
 
-    `add(packed, pend)` after every finished step: the step's detections are packed into the compact wire record ON THE
-    DEVICE (hoigen_pack_wire reads the forward's own offsets — nothing is sized on the host) into the current chunk;
-    every `chunk_steps` steps the chunk is exchanged with ONE fixed-capacity all-gather, enqueued on a side stream so it
-    overlaps the next steps' compute.  No host synchronisation happens until `finish()`, which reads all headers back
-    once, widens every record to the reference's dtypes (hoigen_unpack_wire) and returns [rank][step] PackedDetections.
-    CPU tensors (gloo, the host-logic tests) take the torch forms of the same format."""
+    `add(packed)` after every finished step packs the step's detections into the compact wire record ON THE DEVICE, on a
+    side stream (hoigen_pack_wire reads the forward's own device-side offsets).  Transport of the records:
 
-    def __init__(self, world: int, max_images: int, max_triplets: int, max_boxes: int, device, chunk_steps: int = 4,
-                 group=None):
-        self.world, self.max_images, self.chunk_steps, self.group = world, max_images, max(1, chunk_steps), group
+      "p2p"         (CUDA, world > 1, default when torch's symmetric memory can be set up): every rank owns a receive
+                    buffer [rank][slot] mapped into all peers (NVLink / NVSwitch peer memory); a record is PUSHED straight
+                    into every peer's buffer with copy-engine peer copies — no SM is used, no rank waits for another, so
+                    the exchange overlaps the next steps' compute without disturbing it (an NCCL all-gather kernel per
+                    chunk was measured to DOUBLE the step time at N = 2: its CTAs hold SMs while they spin for the peer,
+                    which breaks the co-residency the persistent GEMMs are scheduled for).  `finish()` = one barrier.
+      "collective"  ONE all-gather of the sweep's records at `finish()` (NCCL; gloo in the CPU tests), after the compute.
+
+    No host synchronisation happens until `finish()`, which reads all headers back once, widens every record to the
+    reference's dtypes (hoigen_unpack_wire) and returns [rank][step] PackedDetections.  A sweep holds at most `max_steps`
+    steps (`full` tells when to `finish()`); every rank must add the same number of steps per sweep."""
+
+    def __init__(self, world: int, max_images: int, max_triplets: int, max_boxes: int, device, max_steps: int = 32,
+                 group=None, transport: str = "auto"):
+        self.world, self.max_images, self.max_steps, self.group = world, max_images, max(1, max_steps), group
         self.dev = torch.device(device)
         self.cap = wire_record_bytes(max_images, max_triplets, max_boxes)
         self.hdr_bytes = (4 + 2 * (max_images + 1)) * 4
         self.cuda = self.dev.type == "cuda"
         self.side = torch.cuda.Stream(device=self.dev) if self.cuda else None
+        self.rank = dist.get_rank(group) if (world > 1 and dist.is_initialized()) else 0
+        self.transport, self.symm = "collective", None
+        nbytes = world * self.max_steps * self.cap
+        if self.cuda and world > 1 and transport in ("auto", "p2p"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                self.recv = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.dev)
+                self.symm = symm_mem.rendezvous(self.recv, grp.group_name if hasattr(grp, "group_name") else grp)
+                self.peers = [self.symm.get_buffer(r, (nbytes,), torch.uint8) for r in range(world)]
+                self.transport = "p2p"
+            except Exception as e:          # no peer mapping on this box / build: the collective form still works
+                if transport == "p2p":
+                    raise
+                self.symm, self.why_not_p2p = None, f"{type(e).__name__}: {e}"
+        if self.transport == "collective":
+            self.recv = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        # this rank's records of the sweep (p2p: the own slice of the receive buffer)
+        self.mine = (self.recv[self.rank * self.max_steps * self.cap: (self.rank + 1) * self.max_steps * self.cap]
+                     if self.transport == "p2p" else torch.empty(self.max_steps * self.cap, dtype=torch.uint8, device=self.dev))
         self._reset()
 
     def _reset(self):
-        self.chunks = []        # [(gathered (world*steps*cap,), n_steps, work)]
-        self.cur, self.cur_n = None, 0
-        self.keep = []          # the steps' own tensors: alive until the records have been built
+        self.n = 0
+        self.keep = []          # the steps' own tensors: alive until their records have been built
         self.size = None
 
-    def _new_chunk(self):
-        buf = torch.empty(self.chunk_steps * self.cap, dtype=torch.uint8, device=self.dev)
-        buf.view(self.chunk_steps, self.cap)[:, : self.hdr_bytes].zero_()        # unused slots read as "no record"
-        return buf
+    @property
+    def full(self) -> bool:
+        return self.n >= self.max_steps
 
     def add(self, packed, pend=None) -> None:
+        if self.full:
+            raise RuntimeError(f"SweepExchange holds {self.max_steps} steps per sweep: call finish() first")
         self.size = packed.size
-        if self.cuda:
-            from . import _cabi
-            done = getattr(packed, "done", None)
-            with torch.cuda.stream(self.side):
-                if done is not None:
-                    self.side.wait_event(done)
-                else:
-                    self.side.wait_stream(torch.cuda.current_stream(self.dev))
-                if self.cur is None:
-                    self.cur, self.cur_n = self._new_chunk(), 0
-                rec = self.cur[self.cur_n * self.cap: (self.cur_n + 1) * self.cap]
-                img_off = packed.img_off_dev if pend is None else pend.img_off       # device-side int32 offsets of the forward
-                box_off = packed.box_off_dev if pend is None else pend.d_box_off
-                _cabi.call("hoigen_pack_wire", packed.scores.data_ptr(), packed.labels.data_ptr(), packed.objects.data_ptr(),
-                           packed.pairing.data_ptr(), packed.boxes.data_ptr(), img_off.data_ptr(), box_off.data_ptr(),
-                           packed.num_images, self.max_images, self.cap, rec.data_ptr())
-                self.keep.append((packed, pend))
-                self.cur_n += 1
-                if self.cur_n == self.chunk_steps:
-                    self._flush()
-        else:
-            if self.cur is None:
-                self.cur, self.cur_n = self._new_chunk(), 0
-            pack_wire_torch(packed, self.max_images, self.cap, self.cur[self.cur_n * self.cap: (self.cur_n + 1) * self.cap])
-            self.cur_n += 1
-            if self.cur_n == self.chunk_steps:
-                self._flush()
-
-    def _flush(self):
-        """Exchange the current chunk (whole capacity: sizes are not known on the host, and need not be)."""
-        gathered = torch.empty(self.world * self.chunk_steps * self.cap, dtype=torch.uint8, device=self.dev)
-        if self.world > 1:
-            work = dist.all_gather_into_tensor(gathered, self.cur, group=self.group, async_op=True)
-        else:
-            gathered.copy_(self.cur)
-            work = None
-        self.chunks.append((gathered, self.cur, work))
-        self.cur, self.cur_n = None, 0
+        rec = self.mine[self.n * self.cap: (self.n + 1) * self.cap]
+        if not self.cuda:
+            rec[: self.hdr_bytes].zero_()
+            pack_wire_torch(packed, self.max_images, self.cap, rec)
+            self.n += 1
+            return
+        from . import _cabi
+        done = getattr(packed, "done", None)
+        with torch.cuda.stream(self.side):
+            if done is not None:
+                self.side.wait_event(done)
+            else:
+                self.side.wait_stream(torch.cuda.current_stream(self.dev))
+            img_off = packed.img_off_dev if pend is None else pend.img_off       # device-side int32 offsets of the forward
+            box_off = packed.box_off_dev if pend is None else pend.d_box_off
+            _cabi.call("hoigen_pack_wire", packed.scores.data_ptr(), packed.labels.data_ptr(), packed.objects.data_ptr(),
+                       packed.pairing.data_ptr(), packed.boxes.data_ptr(), img_off.data_ptr(), box_off.data_ptr(),
+                       packed.num_images, self.max_images, self.cap, rec.data_ptr())
+            if self.transport == "p2p":
+                # the record's size is known on the host (the forward's offsets came back with finish()): push exactly
+                # that many bytes into slot [rank][n] of every peer's receive buffer — copy engines over NVLink, no SMs
+                nb = min(self.cap, _align(wire_layout(self.max_images, packed.scores.numel(), packed.boxes.shape[0])["end"], 16))
+                off = (self.rank * self.max_steps + self.n) * self.cap
+                for r in range(self.world):
+                    if r != self.rank:
+                        self.peers[r][off: off + nb].copy_(rec[:nb], non_blocking=True)
+        self.keep.append((packed, pend))
+        self.n += 1
 
     def finish(self):
         """-> [rank][step] PackedDetections of everything added since the last finish()."""
         from .detector import PackedDetections
-        if self.cur is not None:
-            if self.cuda:
-                with torch.cuda.stream(self.side):
-                    self._flush()
-            else:
-                self._flush()
-        if not self.chunks:
-            return [[] for _ in range(self.world)]
-        S, W, cap, hb = self.chunk_steps, self.world, self.cap, self.hdr_bytes
+        W, S, cap, hb, n = self.world, self.max_steps, self.cap, self.hdr_bytes, self.n
         out = [[] for _ in range(W)]
+        if n == 0:
+            return out
         if not self.cuda:
-            for gathered, _, work in self.chunks:
-                if work is not None:
-                    work.wait()
-                g = gathered.view(W, S, cap)
-                for r in range(W):
-                    for s in range(S):
-                        if int(g[r, s, :4].view(torch.int32)[0]) & 0xFFFFFFFF == WIRE_MAGIC:
-                            out[r].append(unpack_wire_torch(g[r, s], self.max_images, self.size))
+            if W > 1:
+                gathered = torch.empty(W * n * cap, dtype=torch.uint8)
+                dist.all_gather_into_tensor(gathered, self.mine[: n * cap].contiguous(), group=self.group)
+                g = gathered.view(W, n, cap)
+            else:
+                g = self.mine[: n * cap].view(1, n, cap)
+            for r in range(W):
+                for s in range(n):
+                    out[r].append(unpack_wire_torch(g[r, s], self.max_images, self.size))
             self._reset()
             return out
         from . import _cabi
         with torch.cuda.stream(self.side):
-            for _, _, work in self.chunks:
-                if work is not None:
-                    work.wait()                       # stream-level: the side stream waits for NCCL's
+            if self.transport == "p2p":
+                self.symm.barrier()                    # every rank's pushes (stream-ordered before its barrier) have landed
+                g = self.recv.view(W, S, cap)
+            elif W > 1:
+                gathered = torch.empty(W * n * cap, dtype=torch.uint8, device=self.dev)
+                dist.all_gather_into_tensor(gathered, self.mine[: n * cap], group=self.group)
+                g = gathered.view(W, n, cap)
+            else:
+                g = self.mine.view(1, S, cap)
             # ONE read-back: every record's header
-            hdrs = torch.cat([g.view(W * S, cap)[:, :hb] for g, _, _ in self.chunks]).contiguous()
+            hdrs = g[:, :n, :hb].contiguous()
             host = torch.empty(hdrs.shape, dtype=torch.uint8).pin_memory()
             host.copy_(hdrs, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
         ev.synchronize()
-        H = host.view(torch.int32).view(len(self.chunks), W, S, -1)
-        recs = []            # (chunk, rank, slot, nimg, m, nbox, toff, boff)
+        H = host.view(torch.int32).view(W, n, -1)
         mi = self.max_images
-        for c in range(len(self.chunks)):
-            for r in range(W):
-                for s in range(S):
-                    h = H[c, r, s]
-                    if int(h[0]) & 0xFFFFFFFF != WIRE_MAGIC:
-                        continue
-                    nimg, m, nbox = int(h[1]), int(h[2]), int(h[3])
-                    if m < 0:
-                        raise ValueError(f"rank {r}: a step's detections did not fit the record capacity ({cap} bytes)")
-                    recs.append((c, r, s, nimg, m, nbox, h[4: 4 + nimg + 1].tolist(), h[4 + mi + 1: 4 + mi + 1 + nimg + 1].tolist()))
-        m_tot, b_tot = sum(x[4] for x in recs), sum(x[5] for x in recs)
+        recs = []            # (rank, slot, nimg, m, nbox, toff, boff)
+        for r in range(W):
+            for s in range(n):
+                h = H[r, s]
+                if int(h[0]) & 0xFFFFFFFF != WIRE_MAGIC:
+                    raise ValueError(f"rank {r} slot {s}: no record arrived (ranks must add the same number of steps per sweep)")
+                nimg, m, nbox = int(h[1]), int(h[2]), int(h[3])
+                if m < 0:
+                    raise ValueError(f"rank {r}: a step's detections did not fit the record capacity ({cap} bytes)")
+                recs.append((r, s, nimg, m, nbox, h[4: 4 + nimg + 1].tolist(), h[4 + mi + 1: 4 + mi + 1 + nimg + 1].tolist()))
+        m_tot, b_tot = sum(x[3] for x in recs), sum(x[4] for x in recs)
+        rows = g.shape[1]                                         # slots per rank in the buffer being unpacked
         with torch.cuda.stream(self.side):
             scores = torch.empty(max(m_tot, 1), dtype=torch.float32, device=self.dev)
             labels = torch.empty(max(m_tot, 1), dtype=torch.int64, device=self.dev)
             objects = torch.empty(max(m_tot, 1), dtype=torch.int64, device=self.dev)
             pairing = torch.empty(max(2 * m_tot, 2), dtype=torch.int64, device=self.dev)
             boxes = torch.empty(max(b_tot, 1), 4, dtype=torch.float32, device=self.dev)
-            bases = torch.full((len(self.chunks), W * S, 2), -1, dtype=torch.int64)
+            bases = torch.full((W, rows, 2), -1, dtype=torch.int64)
             tb, bb, place = 0, 0, []
-            for (c, r, s, nimg, m, nbox, toff, boff) in recs:
-                bases[c, r * S + s, 0], bases[c, r * S + s, 1] = tb, bb
+            for (r, s, nimg, m, nbox, toff, boff) in recs:
+                bases[r, s, 0], bases[r, s, 1] = tb, bb
                 place.append((tb, bb))
                 tb += m
                 bb += nbox
             bases_d = bases.pin_memory().to(self.dev, non_blocking=True)
-            for c, (gathered, _, _) in enumerate(self.chunks):
-                _cabi.call("hoigen_unpack_wire", gathered.data_ptr(), W * S, cap, mi, bases_d[c].data_ptr(), scores.data_ptr(),
+            base_ptr = g.data_ptr()
+            for r in range(W):                                    # one launch per rank: its `rows` slots are contiguous
+                _cabi.call("hoigen_unpack_wire", base_ptr + r * rows * cap, rows, cap, mi, bases_d[r].data_ptr(), scores.data_ptr(),
                            labels.data_ptr(), objects.data_ptr(), pairing.data_ptr(), boxes.data_ptr())
+            if self.transport == "p2p":
+                # headers cleared + a second barrier: no peer may push the next sweep's records while this one is being read
+                self.recv.view(W, S, cap)[:, :, :hb].zero_()
+                self.symm.barrier()
             done = torch.cuda.Event()
             done.record()
         torch.cuda.current_stream(self.dev).wait_event(done)
-        for (c, r, s, nimg, m, nbox, toff, boff), (tb, bb) in zip(recs, place):
+        for (r, s, nimg, m, nbox, toff, boff), (tb, bb) in zip(recs, place):
             pk = PackedDetections(scores[tb: tb + m], labels[tb: tb + m], objects[tb: tb + m], pairing[2 * tb: 2 * (tb + m)],
                                   boxes[bb: bb + nbox], toff, boff, self.size)
             pk.done = done

@@ -178,8 +178,8 @@ def _worker_sweep(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        steps = 5                                   # chunk_steps = 2: two full chunks + a partial one
-        ex = SweepExchange(world, 8, 8 * 50, 8 * 9, "cpu", chunk_steps=2)
+        steps = 5
+        ex = SweepExchange(world, 8, 8 * 50, 8 * 9, "cpu", max_steps=6)
         ok = True
         for sweep in range(2):                      # the exchanger is reusable across sweeps
             for s in range(steps):

@@ -648,7 +648,7 @@ def test_wire_format_kernels_match_torch_form(cuda_device):
     from hoigen_b200.gather import wire_layout
     end = wire_layout(8, pk.scores.numel(), pk.boxes.shape[0])["end"]
     assert torch.equal(rec.cpu()[:end], ref[:end])
-    ex = SweepExchange(1, 8, 8 * 36 * 20, 8 * 9, cuda_device, chunk_steps=2)
+    ex = SweepExchange(1, 8, 8 * 36 * 20, 8 * 9, cuda_device, max_steps=5)
     for rep in range(2):
         for d in steps:
             ex.add(d.packed)
@@ -660,7 +660,7 @@ def test_wire_format_kernels_match_torch_form(cuda_device):
             for f in ("scores", "labels", "objects", "pairing", "boxes"):
                 a, b = getattr(g, f), getattr(d.packed, f)
                 assert a.dtype == b.dtype and torch.equal(a, b), (rep, f)
-    tiny = SweepExchange(1, 8, 4, 8 * 9, cuda_device, chunk_steps=1)             # capacity too small: loud at finish()
+    tiny = SweepExchange(1, 8, 4, 8 * 9, cuda_device, max_steps=1)             # capacity too small: loud at finish()
     tiny.add(steps[0].packed)
     with pytest.raises(ValueError):
         tiny.finish()
