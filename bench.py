@@ -562,7 +562,9 @@ def run_b200(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()                           # NVML is initialised here, outside the timed regions
-    run_resident(0, args.warmup)                 # (N > 1: also warms the exchange — NCCL channel setup, staging buffers)
+    run_resident(0, args.warmup)
+    if world > 1:
+        run_resident(0, args.steps)              # a full-length sweep: the exchange's sweep-sized allocations are one-time costs
     barrier()
     _cabi.profile(False)
     clocks.active = True

@@ -397,6 +397,12 @@ class SweepExchange:
         # this rank's records of the sweep (p2p: the own slice of the receive buffer)
         self.mine = (self.recv[self.rank * self.max_steps * self.cap: (self.rank + 1) * self.max_steps * self.cap]
                      if self.transport == "p2p" else torch.empty(self.max_steps * self.cap, dtype=torch.uint8, device=self.dev))
+        # pinned landing / staging buffers for finish(), allocated ONCE (a pinned allocation per call is a cudaHostAlloc: it
+        # synchronises the device and was measured at 10-30 ms for a first-seen size)
+        if self.cuda:
+            self.hdr_host = torch.empty(world, self.max_steps, self.hdr_bytes, dtype=torch.uint8).pin_memory()
+            self.bases_host = torch.empty(world, self.max_steps, 2, dtype=torch.int64).pin_memory()
+            self.bases_dev = torch.empty(world, self.max_steps, 2, dtype=torch.int64, device=self.dev)
         self._reset()
 
     def _reset(self):
@@ -409,6 +415,15 @@ class SweepExchange:
         return self.n >= self.max_steps
 
     def add(self, packed, pend=None) -> None:
+        import os, time
+        t_add = time.perf_counter() if os.environ.get("HOIGEN_GATHER_TRACE") else None
+        try:
+            return self._add(packed, pend)
+        finally:
+            if t_add is not None:
+                self._t_add = getattr(self, "_t_add", 0.0) + time.perf_counter() - t_add
+
+    def _add(self, packed, pend=None) -> None:
         if self.full:
             raise RuntimeError(f"SweepExchange holds {self.max_steps} steps per sweep: call finish() first")
         self.size = packed.size
@@ -443,6 +458,23 @@ class SweepExchange:
 
     def finish(self):
         """-> [rank][step] PackedDetections of everything added since the last finish()."""
+        import os, sys, time
+        if not os.environ.get("HOIGEN_GATHER_TRACE"):
+            return self._finish()
+        if self.cuda:
+            torch.cuda.synchronize(self.dev)
+        t0 = time.perf_counter()
+        n = self.n
+        out = self._finish()
+        if self.cuda:
+            torch.cuda.synchronize(self.dev)
+        if self.rank == 0:
+            print(f"[exchange] finish of {n} steps: {1e3 * (time.perf_counter() - t0):.2f} ms (device idle before it); host time in add() "
+                  f"since the last report {1e3 * getattr(self, '_t_add', 0.0):.2f} ms; transport {self.transport}", file=sys.stderr, flush=True)
+        self._t_add = 0.0
+        return out
+
+    def _finish(self):
         from .detector import PackedDetections
         W, S, cap, hb, n = self.world, self.max_steps, self.cap, self.hdr_bytes, self.n
         out = [[] for _ in range(W)]
@@ -472,24 +504,23 @@ class SweepExchange:
             else:
                 g = self.mine.view(1, S, cap)
             # ONE read-back: every record's header
-            hdrs = g[:, :n, :hb].contiguous()
-            host = torch.empty(hdrs.shape, dtype=torch.uint8).pin_memory()
-            host.copy_(hdrs, non_blocking=True)
+            self.hdr_host[:, :n].copy_(g[:, :n, :hb], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
         ev.synchronize()
-        H = host.view(torch.int32).view(W, n, -1)
+        H = self.hdr_host[:, :n].numpy().view("int32").reshape(W, n, -1)
         mi = self.max_images
+        if (H[:, :, 0] != WIRE_MAGIC).any():
+            r, s = [int(v[0]) for v in (H[:, :, 0] != WIRE_MAGIC).nonzero()]
+            raise ValueError(f"rank {r} slot {s}: no record arrived (ranks must add the same number of steps per sweep)")
+        if (H[:, :, 2] < 0).any():
+            raise ValueError(f"rank {int((H[:, :, 2] < 0).nonzero()[0][0])}: a step's detections did not fit the record capacity ({cap} bytes)")
         recs = []            # (rank, slot, nimg, m, nbox, toff, boff)
         for r in range(W):
             for s in range(n):
                 h = H[r, s]
-                if int(h[0]) & 0xFFFFFFFF != WIRE_MAGIC:
-                    raise ValueError(f"rank {r} slot {s}: no record arrived (ranks must add the same number of steps per sweep)")
-                nimg, m, nbox = int(h[1]), int(h[2]), int(h[3])
-                if m < 0:
-                    raise ValueError(f"rank {r}: a step's detections did not fit the record capacity ({cap} bytes)")
-                recs.append((r, s, nimg, m, nbox, h[4: 4 + nimg + 1].tolist(), h[4 + mi + 1: 4 + mi + 1 + nimg + 1].tolist()))
+                nimg = int(h[1])
+                recs.append((r, s, nimg, int(h[2]), int(h[3]), h[4: 4 + nimg + 1].tolist(), h[4 + mi + 1: 4 + mi + 1 + nimg + 1].tolist()))
         m_tot, b_tot = sum(x[3] for x in recs), sum(x[4] for x in recs)
         rows = g.shape[1]                                         # slots per rank in the buffer being unpacked
         with torch.cuda.stream(self.side):
@@ -498,17 +529,19 @@ class SweepExchange:
             objects = torch.empty(max(m_tot, 1), dtype=torch.int64, device=self.dev)
             pairing = torch.empty(max(2 * m_tot, 2), dtype=torch.int64, device=self.dev)
             boxes = torch.empty(max(b_tot, 1), 4, dtype=torch.float32, device=self.dev)
-            bases = torch.full((W, rows, 2), -1, dtype=torch.int64)
+            bases = self.bases_host
+            bases.fill_(-1)
             tb, bb, place = 0, 0, []
             for (r, s, nimg, m, nbox, toff, boff) in recs:
                 bases[r, s, 0], bases[r, s, 1] = tb, bb
                 place.append((tb, bb))
                 tb += m
                 bb += nbox
-            bases_d = bases.pin_memory().to(self.dev, non_blocking=True)
+            self.bases_dev.copy_(bases, non_blocking=True)
+            bases_d = self.bases_dev
             base_ptr = g.data_ptr()
-            for r in range(W):                                    # one launch per rank: its `rows` slots are contiguous
-                _cabi.call("hoigen_unpack_wire", base_ptr + r * rows * cap, rows, cap, mi, bases_d[r].data_ptr(), scores.data_ptr(),
+            for r in range(W):                                    # one launch per rank: its slots are contiguous
+                _cabi.call("hoigen_unpack_wire", base_ptr + r * rows * cap, min(rows, n), cap, mi, bases_d[r].data_ptr(), scores.data_ptr(),
                            labels.data_ptr(), objects.data_ptr(), pairing.data_ptr(), boxes.data_ptr())
             if self.transport == "p2p":
                 # headers cleared + a second barrier: no peer may push the next sweep's records while this one is being read
