@@ -213,3 +213,64 @@ class DetectionAPMeter:
                    ngt.data_ptr(), thr.data_ptr(), self.num_cls, ap.data_ptr(), max_rec.data_ptr())
         self.ap, self.max_rec = ap, max_rec
         return ap
+
+
+@torch.no_grad()
+def test_hico(net, dataloader, object_n_verb_to_interaction=None, num_gt=None, *, tgt_num_classes: int = 600,
+              min_iou: float = 0.5, to_device=None, launch_ahead: bool = True) -> torch.Tensor:
+    """The reference's evaluation sweep `CustomisedDLE.test_hico` (utils_tip_cache_and_union_finetune.py:348-411) around
+    the accelerated forward: for every batch `(inputs, ..., targets)` of the loader run `net(inputs, targets)`, skip
+    batches without detections (T:371-373), convert (object, verb) -> HOI id, associate with the ground truth and feed
+    `DetectionAPMeter(600, num_gt, '11P')`; returns `meter.eval()` (per-class AP, fp64, on the device).
+
+    Differences from the reference, none of which changes a number: any batch size (the reference is fixed at 1), the
+    detections never leave the GPU (association and AP are the batched kernels above), and when `net` offers
+    `launch(inputs, targets)` / `finish(handle)` (hoigen_b200.detector.UPT: `launch_from_proposals` / `finish` behind a thin
+    adapter) the next batch is enqueued before the previous one is post-processed.
+
+    net: callable `(inputs, targets) -> List[dict] | None` like the reference's detector (U:1543).
+    object_n_verb_to_interaction: `dataset.object_n_verb_to_interaction` for 117-verb models (T:387-388); None when the
+    model's classes already are HOI ids (T:389-390).  num_gt: `dataset.anno_interaction` (HICO-DET) or None (T:361)."""
+    assoc = HOIAssociator(object_n_verb_to_interaction, min_iou=min_iou)
+    meter = DetectionAPMeter(tgt_num_classes, num_gt=num_gt, algorithm="11P")
+    pipelined = launch_ahead and hasattr(net, "launch") and hasattr(net, "finish")
+
+    def consume(outputs, targets):
+        if outputs is None or len(outputs) == 0:      # T:371-373
+            return
+        for scores, interactions, labels in assoc(outputs, targets):
+            meter.append(scores, interactions, labels)
+
+    pending = None
+    for batch in dataloader:
+        inputs, targets = batch[0], batch[-1]
+        if to_device is not None:
+            inputs = to_device(inputs)
+        if pipelined:
+            handle = net.launch(inputs, targets)
+            if pending is not None:
+                consume(net.finish(pending[0]), pending[1])
+            pending = (handle, targets)
+        else:
+            consume(net(inputs, targets), targets)
+    if pending is not None:
+        consume(net.finish(pending[0]), pending[1])
+    return meter.eval()
+
+
+def summarize_map(ap: torch.Tensor, num_anno=None, unseen_hoi_idx: Optional[Sequence[int]] = None) -> dict:
+    """The numbers main_tip_finetune.py:915-948 prints: full mAP, rare (< 10 training annotations) / non-rare, and for the
+    zero-shot settings seen / unseen over `hico_unseen_index[zs_type]`.  Values in percent, like the reference's log."""
+    ap = ap.detach().double().cpu()
+    out = {"full": float(ap.mean() * 100)}
+    if num_anno is not None:
+        na = torch.as_tensor(num_anno)
+        rare, non_rare = torch.nonzero(na < 10).squeeze(1), torch.nonzero(na >= 10).squeeze(1)
+        out["rare"] = float(ap[rare].mean() * 100)
+        out["non_rare"] = float(ap[non_rare].mean() * 100)
+    if unseen_hoi_idx is not None:
+        unseen = sorted(set(int(i) for i in unseen_hoi_idx))
+        seen = [i for i in range(ap.numel()) if i not in set(unseen)]
+        out["unseen"] = float(ap[torch.tensor(unseen)].mean() * 100)
+        out["seen"] = float(ap[torch.tensor(seen)].mean() * 100)
+    return out

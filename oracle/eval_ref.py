@@ -249,3 +249,38 @@ def group_by_class(stream, num_cls: int):
                 lb[c].append(labels[ok][sel].double())
     cat = lambda xs: torch.cat(xs) if xs else torch.zeros(0, dtype=torch.float64)
     return [cat(x) for x in sc], [cat(x) for x in lb]
+
+
+def test_hico_ref(outputs_per_batch, targets_per_batch, conversion: Optional[torch.Tensor], num_gt=None, num_cls: int = 600,
+                  min_iou: float = 0.5):
+    """The sweep of T:348-411 on CPU detections: per batch the per-image association above, the meter's per-class gathering
+    (meters.py:585-604) and its 11-point AP (ap_11point).  -> ap (num_cls,) fp64."""
+    scores = [[] for _ in range(num_cls)]
+    labels = [[] for _ in range(num_cls)]
+    for outputs, targets in zip(outputs_per_batch, targets_per_batch):
+        if outputs is None or len(outputs) == 0:
+            continue
+        for output, target in zip(outputs, targets):
+            s, inter, lab = associate_image(output, target, conversion, min_iou)
+            for c in inter.unique().tolist():
+                if c != c or c < 0 or c >= num_cls:          # NaN / invalid combinations are never gathered
+                    continue
+                sel = inter == c
+                scores[int(c)].append(s[sel])
+                labels[int(c)].append(lab[sel])
+    cat = lambda xs: torch.cat(xs) if xs else torch.zeros(0)
+    return ap_11point([cat(x) for x in scores], [cat(x) for x in labels], num_gt)[0]
+
+
+def summarize_map_ref(ap: torch.Tensor, num_anno, unseen_idx=None) -> dict:
+    """M:915-948."""
+    num_anno = torch.as_tensor(num_anno)
+    rare = torch.nonzero(num_anno < 10).squeeze(1)
+    non_rare = torch.nonzero(num_anno >= 10).squeeze(1)
+    out = {"full": float(ap.mean() * 100), "rare": float(ap[rare].mean() * 100), "non_rare": float(ap[non_rare].mean() * 100)}
+    if unseen_idx is not None:
+        ap_unseen = [v for i, v in enumerate(ap) if i in unseen_idx]
+        ap_seen = [v for i, v in enumerate(ap) if i not in unseen_idx]
+        out["unseen"] = float(torch.as_tensor(ap_unseen).mean() * 100)
+        out["seen"] = float(torch.as_tensor(ap_seen).mean() * 100)
+    return out

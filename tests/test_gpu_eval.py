@@ -125,3 +125,79 @@ def test_ap_meter_edges(cuda_device):
                torch.tensor([1.0, 1.0, 0.0], device=cuda_device))
     with pytest.raises(AssertionError):
         bad.eval()
+
+
+class _LoaderNet:
+    """What main_tip_finetune.py hands to CustomisedDLE.test_hico, reduced to the accelerated path: `net(inputs, targets)`
+    like the reference's detector, plus launch / finish so that evaluate.test_hico can keep a batch in flight."""
+
+    def __init__(self, model, dev):
+        self.model, self.dev = model, dev
+
+    def launch(self, inputs, targets):
+        imgs, props, dino = inputs
+        return self.model.launch_from_proposals(imgs.to(self.dev), [{k: (v.to(self.dev) if torch.is_tensor(v) else v) for k, v in p.items()}
+                                                                    for p in props], dino.to(self.dev))
+
+    def finish(self, handle):
+        return self.model.finish(handle)
+
+    def __call__(self, inputs, targets):
+        return self.finish(self.launch(inputs, targets))
+
+
+def test_sweep_driver_map_matches_reference_loop(cuda_device):
+    """f1 end to end (T:348-411 + M:915-948): a seeded synthetic 'dataset' of 6 batches x 4 images through
+    evaluate.test_hico (forward -> HOIAssociator -> DetectionAPMeter -> per-class AP -> full / rare / non-rare / seen / unseen
+    mAP) against the oracle's restatement of the reference's loop.  (a) On the SAME detections the 600 APs are bit-identical
+    (fp64) whether batches are pipelined or not; (b) against the loop fed with the ORACLE forward's detections (fp32 CPU
+    reference arithmetic) the mAPs agree to a small fraction of a point (the bf16 logits move a few near-tied scores)."""
+    from hoigen_b200 import synthetic as S
+    from hoigen_b200.detector import UPT
+    from hoigen_b200.evaluate import summarize_map, test_hico
+    from oracle import eval_ref as E
+    from oracle import hoi_forward_ref as O
+    onv = _tables()
+    conv = E.conversion_table(onv)
+    enc, head = S.make_encoder_state(0), S.make_head_state(117, 256, seed=2)
+    model = UPT.from_state(enc, head).to(cuda_device)
+    net = _LoaderNet(model, cuda_device)
+    batches = []
+    for i in range(6):
+        B = 4
+        props = S.make_region_props(B, 4, 4, ragged=(i % 2 == 1), seed=900 + 10 * i)
+        if i == 3:
+            for p in props:                       # a batch without any human: the forward returns None (T:371-373)
+                p["labels"] = torch.full_like(p["labels"], 7)
+        batches.append((S.make_images(B, seed=910 + i), props, S.make_dino_features(B, seed=920 + i)))
+    # ground truth derived from a first pass over the data (jittered copies of detected pairs + misses), seeded
+    dets_cpu, oracle_dets, targets = [], [], []
+    for i, inp in enumerate(batches):
+        out = net(inp, None)
+        o_out = O.hoi_forward(inp[0], inp[1], inp[2], enc, head) if out is not None else None
+        if out is None:
+            dets_cpu.append(None); oracle_dets.append(None)
+            targets.append([dict(boxes_h=torch.zeros(0, 4), boxes_o=torch.zeros(0, 4), hoi=torch.zeros(0, dtype=torch.int64),
+                                 size=torch.tensor([224.0, 224.0])) for _ in range(4)])
+            continue
+        cpu = [{k: v.cpu() for k, v in d.items()} for d in out]
+        dets_cpu.append(cpu); oracle_dets.append(o_out)
+        targets.append(E.make_targets(cpu, conv, seed=930 + i, per_image=8))
+    loader = [(inp, tg) for inp, tg in zip(batches, targets)]
+    g = torch.Generator().manual_seed(5)
+    num_anno = torch.randint(1, 40, (600,), generator=g)
+    num_gt = [float(v) for v in (torch.randint(5, 60, (600,), generator=g)).tolist()]
+    uc0 = S.load_object_tables()["hico_unseen_uc0"]
+    ap_pipe = test_hico(net, loader, onv, num_gt=num_gt)
+    ap_seq = test_hico(net, loader, onv, num_gt=num_gt, launch_ahead=False)
+    assert torch.equal(ap_pipe, ap_seq)
+    ref_same = E.test_hico_ref(dets_cpu, targets, conv, num_gt=num_gt)
+    assert torch.equal(ap_pipe.cpu(), ref_same), (ap_pipe.cpu() - ref_same).abs().max()
+    ours = summarize_map(ap_pipe, num_anno, uc0)
+    ref = E.summarize_map_ref(ref_same, num_anno, uc0)
+    assert ours == pytest.approx(ref, abs=1e-9) and ours["full"] > 0.05
+    ref_oracle = E.summarize_map_ref(E.test_hico_ref(oracle_dets, targets, conv, num_gt=num_gt), num_anno, uc0)
+    print("mAP (ours | reference loop on oracle-forward detections):",
+          {k: (round(ours[k], 3), round(ref_oracle[k], 3)) for k in ours})
+    for k in ours:
+        assert abs(ours[k] - ref_oracle[k]) <= 0.25, (k, ours[k], ref_oracle[k])
