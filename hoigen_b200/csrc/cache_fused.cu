@@ -22,6 +22,8 @@
 // Replaces U:1156-1163 (gen_feat cache branches) for C <= 128; wider classifiers (600 HOI triplets) keep the two-GEMM form.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -356,7 +358,7 @@ extern "C" {
 int64_t hoigen_cache_fused_workspace_bytes(int32_t ktot, int32_t num_classes) {
   if (ktot < 0 || num_classes <= 0 || num_classes > 128) return -1;
   const int64_t c_pad = (num_classes + 15) / 16 * 16;
-  const int64_t ktot_pad = (int64_t(ktot) + 127) / 128 * 128;
+  const int64_t ktot_pad = (int64_t(ktot) + 255) / 256 * 256;
   return 3 * 4 /*max nsplit*/ * ktot_pad * c_pad * 4;
 }
 
@@ -374,6 +376,19 @@ int hoigen_score_cache_fused(const hoigen_score_weights* w, const void* pair_fea
   HOIGEN_CHECK_ARG(affinity == 0 || (cache_bias && cache_bias[0] && cache_bias[1] && cache_bias[2]),
                    "score_cache_fused: the exp affinity needs the per-row cache biases");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static const bool one_cta = getenv("HOIGEN_CF_ONE_CTA") != nullptr;     // A/B switch: the one-CTA form below
+  if (!one_cta) {
+    int nsplit = 1, ktot_pad = 0, c_pad = 0;
+    HOIGEN_TRY_RC(launch_cache_fused_pair(w, pair_feat_bf16, cache_bias, ktot, affinity, beta, parts, &nsplit, &ktot_pad, &c_pad, s));
+    const long total = long(ktot) * C;
+    const int blocks = int(std::min<long>(long(num_sms()) * 8, (total + 255) / 256));
+    KernelScope ks("cache_combine", s, 0, double(3 * nsplit) * ktot * C * 4 + double(ktot) * C * 4);
+    cache_combine_kernel<<<blocks, 256, 0, s>>>(parts, nsplit, ktot, ktot_pad, c_pad, C, img_logits, pair_off, batch,
+                                                w->bias_term[0], w->bias_term[1], w->bias_term[2], w->colscale[0],
+                                                w->colscale[1], w->colscale[2], affinity == 0 ? 1 : 0, ld_logits, logits);
+    HOIGEN_CHECK_LAUNCH();
+    return HOIGEN_OK;
+  }
   CacheFusedArgs g;
   g.feat = reinterpret_cast<const __nv_bfloat16*>(pair_feat_bf16);
   for (int x = 0; x < 3; ++x) g.cache_bias[x] = cache_bias ? cache_bias[x] : nullptr;

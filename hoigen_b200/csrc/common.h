@@ -33,6 +33,11 @@ struct StreamKWorkspace {
 };
 StreamKWorkspace get_streamk_workspace(cudaStream_t stream, size_t slot_bytes, int num_flags);
 
+// CTA-pair form of the fused cache kernel (cache_fused2.cu); fills parts [3 * nsplit][ktot_pad][c_pad]
+int launch_cache_fused_pair(const hoigen_score_weights* w, const void* pair_feat_bf16, const float* const* cache_bias, int ktot,
+                            int affinity, float beta, float* parts, int* nsplit_out, int* ktot_pad_out, int* c_pad_out,
+                            cudaStream_t s);
+
 // Counts every kernel launch of this library and, when profiling is enabled (hoigen_profile_enable), brackets
 // the launch with CUDA events on the launching stream. flops / bytes are the ALGORITHMIC work of the launch.
 struct KernelScope {

@@ -186,7 +186,7 @@ def test_sweep_driver_map_matches_reference_loop(cuda_device):
     loader = [(inp, tg) for inp, tg in zip(batches, targets)]
     g = torch.Generator().manual_seed(5)
     num_anno = torch.randint(1, 40, (600,), generator=g)
-    num_gt = [float(v) for v in (torch.randint(5, 60, (600,), generator=g)).tolist()]
+    num_gt = [float(v) for v in (torch.randint(200, 400, (600,), generator=g)).tolist()]
     uc0 = S.load_object_tables()["hico_unseen_uc0"]
     ap_pipe = test_hico(net, loader, onv, num_gt=num_gt)
     ap_seq = test_hico(net, loader, onv, num_gt=num_gt, launch_ahead=False)
