@@ -394,28 +394,15 @@ def run_b200(args, rank, world, local_rank):
     # then overlap the GEMMs of the next instead of leaving most SMs idle
     streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else [torch.cuda.current_stream(dev)]
 
-    # optional stock DINO ResNet-50 (U:1616-1618) on a side stream, for the "full" figure
-    dino_state = {"model": None, "stream": torch.cuda.Stream(device=dev), "autocast": False}
-
-    def dino_features_for(r, compute_stream):
-        if dino_state["model"] is None:
-            return dev_dino[r]
-        ds = dino_state["stream"]
-        with torch.cuda.stream(ds), torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dino_state["autocast"]):
-            x = dev_imgs[r]
-            if dino_state["autocast"]:
-                x = x.contiguous(memory_format=torch.channels_last)
-            f = dino_state["model"](x).float()
-            f = f / f.norm(dim=-1, keepdim=True)                  # U:1618
-        compute_stream.wait_stream(ds)
-        return f
+    # "full" figure: the DINO ResNet-50 branch (U:1616-1618) run by the module itself instead of supplied features
+    dino_state = {"inline": False}
 
     def launch_resident(i):
         r = i % R
         st = streams[i % len(streams)]
         with torch.cuda.stream(st):
             bx, sc, lb = dev_packed[r]
-            return model.launch_packed(dev_imgs[r], bx, sc, lb, n_list, nh_list, dino_features_for(r, st))
+            return model.launch_packed(dev_imgs[r], bx, sc, lb, n_list, nh_list, None if dino_state["inline"] else dev_dino[r])
 
     # The path's one exchange (N > 1): every rank ends up with every rank's detections.  Each step's detections are packed
     # on a side stream into the compact wire record (9 B per triplet instead of 36) and pushed into every peer's receive
@@ -435,9 +422,14 @@ def run_b200(args, rank, world, local_rank):
             exchange_add(dets.packed, pend)
         return dets
 
+    exch_stats = {"finish_ms": []}
+
     def drain_exchanges():
         if exchange is not None:
-            return exchange.finish()
+            t_f = time.perf_counter()
+            out = exchange.finish()
+            exch_stats["finish_ms"].append((time.perf_counter() - t_f) * 1e3)
+            return out
         return None
 
     def run_resident(first, count):
@@ -572,7 +564,15 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     clocks.active = False
     launches = _cabi.launch_count()
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    own_ms = e0.elapsed_time(e1) / args.steps
+    per_rank_ms = None
+    if world > 1:      # every rank's own step time: separates GPU-to-GPU variation from the cost of the exchange
+        t_all = torch.zeros(world, device=dev, dtype=torch.float64)
+        t_all[rank] = own_ms
+        dist.all_reduce(t_all)
+        per_rank_ms = [round(v, 4) for v in t_all.tolist()]
+    timed_finish_ms = exch_stats["finish_ms"][-1] if exch_stats["finish_ms"] else None
+    ms_step = max_over_ranks(own_ms)
     value = world * B / (ms_step * 1e-3)
     triplets = sum(int(d["scores"].numel()) for d in dets[:B])
     clk = clocks.snapshot() if rank == 0 else None
@@ -645,24 +645,28 @@ def run_b200(args, rank, world, local_rank):
         model.invalidate_packed()
         model.pack_weights()
         torch.cuda.synchronize()
-        # ---- "full" step: the stock DINO ResNet-50 (U:1616-1618) run per step on a side stream --------------------------------
+        # ---- "full" step: the DINO ResNet-50 branch (U:1616-1618) run per step by the module (features NOT supplied) --------
         try:
             import torchvision
             r50 = torchvision.models.resnet50(weights=None)
             r50.fc = torch.nn.Identity()
-            r50 = r50.to(dev).eval()
-            full_dino = {"what": "same resident loop, DINO features computed per step by the stock torchvision ResNet-50 "
-                                 "(fc = Identity, random init) + L2 normalise on a side stream (U:1616-1618); cuDNN, outside the four "
-                                 "kernel groups (SURVEY 8 row a8)"}
-            for tag, ac in (("stock_fp32", False), ("bf16_channels_last", True)):
-                dino_state.update(model=(r50.to(memory_format=torch.channels_last) if ac else r50), autocast=ac)
-                fms = quick_resident(args.steps)
-                full_dino[tag] = {"ms_per_step": fms, "value": B / (fms * 1e-3), "unit": UNIT}
-            dino_state["model"] = None
-            del r50
+            model.dino_model = r50.to(dev).eval()
+            dino_state["inline"] = True
+            full_dino = {"what": "same resident loop, but the module runs its DINO branch itself (torchvision ResNet-50, fc = Identity, random "
+                                 "init, + L2 normalise: U:1616-1618) for every step; cuDNN, outside the four kernel groups (SURVEY 8 row a8)"}
+            fms = quick_resident(args.steps)
+            full_dino["stock_fp32"] = {"ms_per_step": fms, "value": B / (fms * 1e-3), "unit": UNIT,
+                                       "note": "the injected module exactly as the reference runs it (fp32, eager)"}
+            model.accelerate_dino()
+            fms = quick_resident(args.steps)
+            full_dino["accelerate_dino"] = {"ms_per_step": fms, "value": B / (fms * 1e-3), "unit": UNIT,
+                                            "note": "UPT.accelerate_dino(): BatchNorms folded, bf16 channels-last, one CUDA graph per batch "
+                                                    "size and stream (hoigen_b200/dino.py); opt-in, bf16-accurate features"}
         except Exception as e:
-            full_dino = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
-            dino_state["model"] = None
+            full_dino = dict(full_dino or {}, unavailable=f"{type(e).__name__}: {e}"[:300])
+        dino_state["inline"] = False
+        object.__setattr__(model, "_fast_dino", None)
+        model.dino_model = None
         torch.cuda.synchronize()
 
     # ---- per-kernel event profile of one step (separate from the timed regions) ---------------------------------------------
@@ -749,6 +753,8 @@ def run_b200(args, rank, world, local_rank):
     }
     if exchange is not None:
         line["detection_exchange"] = {"transport": exchange.transport, "record_capacity_bytes": exchange.cap,
+                                      "per_rank_ms_per_step": per_rank_ms,
+                                      "rank0_host_ms_in_finish_of_timed_sweep": timed_finish_ms,
                                       "bytes_per_triplet": 9, "sweep_capacity_steps": exchange.max_steps,
                                       "why_not_p2p": getattr(exchange, "why_not_p2p", None)}
     print(json.dumps(line))

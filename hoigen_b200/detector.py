@@ -228,6 +228,16 @@ class UPT(nn.Module):
     def invalidate_packed(self) -> None:
         self._packed = None
 
+    def accelerate_dino(self, use_graph: bool = True) -> "UPT":
+        """Opt in to the fast execution of the injected DINO ResNet-50 (hoigen_b200.dino.FastDinoR50: BatchNorms folded, bf16
+        channels-last, one CUDA graph per batch size).  Row a8 of SURVEY.md §8 is outside the parity-gated path; the stock
+        fp32 module stays the default."""
+        from .dino import FastDinoR50
+        if self.dino_model is None:
+            raise ValueError("no dino_model to accelerate")
+        object.__setattr__(self, "_fast_dino", FastDinoR50(self.dino_model, use_graph=use_graph))
+        return self
+
     def _apply(self, fn, *a, **k):
         self.invalidate_packed()
         self._ws = {}
@@ -589,8 +599,11 @@ class UPT(nn.Module):
         if self.dino and dino_image_features is None:
             if self.dino_model is None:
                 raise ValueError("dino=True needs `dino_image_features` or a `dino_model`")
-            dino_image_features = self.dino_model(images_clip)
-            dino_image_features = dino_image_features / dino_image_features.norm(dim=-1, keepdim=True)
+            if getattr(self, "_fast_dino", None) is not None:        # opt-in (accelerate_dino): same module, bf16 / graph execution
+                dino_image_features = self._fast_dino(images_clip)
+            else:
+                dino_image_features = self.dino_model(images_clip)
+                dino_image_features = dino_image_features / dino_image_features.norm(dim=-1, keepdim=True)
         dino_ptr = dino_image_features.float().contiguous() if self.dino else None
 
         # ---- a9: RoIAlign + pair assembly --------------------------------------------------------------------------

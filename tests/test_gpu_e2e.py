@@ -710,3 +710,40 @@ def test_layernorm_folded_encoder_matches_reference_golden(cuda_device):
         worst = max(worst, float(np.abs(inter["logits"][b].cpu().numpy() - gold[f"logits_{b}"]).max()))
     print(f"LayerNorm-folded encoder: logits max-abs err vs reference {worst:.3e}")
     assert worst <= LOGIT_TOL, worst
+
+
+def test_fast_dino_matches_stock_module(cuda_device):
+    """UPT.accelerate_dino() (row a8, opt-in): the injected torchvision ResNet-50 with BatchNorms folded, bf16 channels-last,
+    CUDA-graph replay gives the stock fp32 module's L2-normalised features to bf16 accuracy (cosine > 0.9995), and the
+    detections computed from them keep every index and stay inside the logit bar relative to the stock-module run."""
+    import torchvision
+    from hoigen_b200 import synthetic as S
+    torch.manual_seed(0)
+    r50 = torchvision.models.resnet50(weights=None)
+    r50.fc = torch.nn.Identity()
+    for mod in r50.modules():                       # non-trivial BatchNorm statistics, as in a trained checkpoint
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5); mod.weight.data.uniform_(0.8, 1.2); mod.bias.data.normal_(0, 0.1)
+    r50 = r50.to(cuda_device).eval()
+    m, enc, head = _build(117, 256, cuda_device)
+    m.dino_model = r50
+    B = 4
+    imgs = S.make_images(B, seed=950).to(cuda_device)
+    props = _props_to(S.make_region_props(B, 4, 4, seed=951), cuda_device)
+    with torch.no_grad():
+        ref_feat = r50(imgs)
+        ref_feat = ref_feat / ref_feat.norm(dim=-1, keepdim=True)
+    dets_stock, inter_stock = m.forward_from_proposals(imgs, props, None, return_intermediates=True)
+    m.accelerate_dino()
+    for rep in range(2):                            # second call replays the captured graph
+        fast = m._fast_dino(imgs)
+        cos = (fast * ref_feat).sum(-1)
+        assert cos.min().item() > 0.9995, cos
+    dets_fast, inter_fast = m.forward_from_proposals(imgs, props, None, return_intermediates=True)
+    worst = 0.0
+    for b in range(B):
+        for k in ("pairing", "labels", "objects"):
+            assert torch.equal(dets_fast[b][k], dets_stock[b][k]), k
+        worst = max(worst, (inter_fast["logits"][b] - inter_stock["logits"][b]).abs().max().item())
+    print(f"fast DINO: min cosine {cos.min().item():.6f}, logits max-abs vs stock-module run {worst:.3e}")
+    assert worst <= 2e-3, worst
