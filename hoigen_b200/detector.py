@@ -657,11 +657,13 @@ class UPT(nn.Module):
                            dino_ptr.data_ptr() if dino_ptr is not None else None, d_pair_off.data_ptr(), B, ktot)
         # ---- a11-a12: prior scores + ordered triplet emission ----------------------------------------------------------
         cap = ktot * p["max_row_len"]
-        out_scores = torch.empty(max(cap, 1), device=dev, dtype=torch.float32)
-        out_labels = torch.empty(max(cap, 1), device=dev, dtype=torch.int64)
-        out_objects = torch.empty(max(cap, 1), device=dev, dtype=torch.int64)
-        out_pairing = torch.empty(max(2 * cap, 2), device=dev, dtype=torch.int64)
-        img_off = torch.empty(B + 1, device=dev, dtype=torch.int32)
+        # the caller owns the outputs (fresh memory per forward, as in the reference) — ONE allocation carved into the five
+        # typed arrays: int64 fields first, so every view stays 8-byte aligned
+        cap1 = max(cap, 1)
+        out_raw = torch.empty(4 * cap1 + (cap1 + 1) // 2 + (B + 2) // 2, device=dev, dtype=torch.int64)
+        out_labels, out_objects, out_pairing = out_raw[:cap1], out_raw[cap1: 2 * cap1], out_raw[2 * cap1: 4 * cap1]
+        out_scores = out_raw[4 * cap1: 4 * cap1 + (cap1 + 1) // 2].view(torch.float32)[:cap1]
+        img_off = out_raw[4 * cap1 + (cap1 + 1) // 2:].view(torch.int32)[: B + 1]
         _cabi.call("hoigen_emit_triplets", logits.data_ptr(), Cn, ldl, scores.data_ptr(), labels.data_ptr(), d_box_off.data_ptr(),
                    d_pair_off.data_ptr(), B, ktot, p["table_bits"].data_ptr(), p["table_words"], int(p["table_bits"].shape[0]),
                    float(self.hyper_lambda),
