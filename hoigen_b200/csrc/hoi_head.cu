@@ -5,6 +5,7 @@
 // Reference (U = upt_tip_cache_model_free_finetune_distill3.py):
 //   get_prior U:1445-1495, compute_roi_embeddings U:981-1057 (torchvision.ops.roi_align call sites U:1028-1029),
 //   compute_prior_scores U:806-833, postprocessing U:1408-1427.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -554,9 +555,14 @@ int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int3
   HOIGEN_CHECK_LAUNCH();
   {
     // algorithmic bytes: token map read once + boxes + one fp32 feature row per single / union box
-    KernelScope ks("roi_features", s, 0, double(batch) * 196 * FEAT * 4 + double(ntot + ktot) * (16 + FEAT * 4));
-    roi_features_grouped_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES_V2, s>>>(
-          tokens, roi_weights, box_off, pair_off, ntot, single_feat, union_feat);
+    KernelScope ks("roi_features", s, 2.0 * double(ntot + ktot) * 196 * FEAT, double(batch) * 196 * FEAT * 4 + double(ntot + ktot) * (16 + FEAT * 4));
+    static const bool simt = getenv("HOIGEN_ROI_SIMT") != nullptr;      // A/B switch: the fp32 SIMT form (four boxes per warp)
+    if (simt) {
+      roi_features_grouped_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES_V2, s>>>(
+            tokens, roi_weights, box_off, pair_off, ntot, single_feat, union_feat);
+    } else {
+      HOIGEN_TRY_RC(launch_roi_features_tc(tokens, roi_weights, box_off, pair_off, batch, ntot, single_feat, union_feat, s));
+    }
   }
   HOIGEN_CHECK_LAUNCH();
   if (ktot > 0) {

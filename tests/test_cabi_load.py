@@ -37,6 +37,26 @@ def test_sass_contains_blackwell_instructions():
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path present"
 
 
+def test_tensor_core_kernels_contain_utcmma():
+    """Per kernel: the GEMMs, attention, the adapter block, the fused cache kernel (both forms) and the RoIAlign kernel issue
+    tcgen05.mma (SASS UTCHMMA) themselves."""
+    import shutil
+    import subprocess
+    from hoigen_b200 import _build
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", str(_build.build())], capture_output=True, text=True).stdout
+    counts, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+        elif "UTCHMMA" in line and cur:
+            counts[cur] = counts.get(cur, 0) + 1
+    for kernel in ("gemm2_bf16_kernel", "gemm_bf16_kernel", "attention_kernel", "adapter_tc_kernel", "cache_fused_pair_kernel",
+                   "cache_fused_kernel", "roi_tc_kernel"):
+        assert any(kernel in k and n > 0 for k, n in counts.items()), f"{kernel}: no UTCHMMA in its SASS"
+
+
 def test_no_cpu_fallback_without_cuda():
     import torch
     if torch.cuda.is_available():
