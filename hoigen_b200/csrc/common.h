@@ -38,9 +38,9 @@ int launch_cache_fused_pair(const hoigen_score_weights* w, const void* pair_feat
                             int affinity, float beta, float* parts, int* nsplit_out, int* ktot_pad_out, int* c_pad_out,
                             cudaStream_t s);
 
-// RoIAlign + mean as a 3 x bf16-split tensor-core product (roi_tc.cu); wts = per-axis weights of roi_weights_kernel
-int launch_roi_features_tc(const float* tokens, const float* wts, const int* box_off, const int* pair_off, int batch, int ntot,
-                           float* single_feat, float* union_feat, cudaStream_t s);
+// RoIAlign + mean as a 3 x bf16-split tensor-core product (roi_tc.cu); computes the per-axis weights from the boxes itself
+int launch_roi_features_tc(const float* tokens, const float* boxes, const int* box_off, const int* pair_off, int batch,
+                           float spatial_scale, float* single_feat, float* union_feat, cudaStream_t s);
 
 // Counts every kernel launch of this library and, when profiling is enabled (hoigen_profile_enable), brackets
 // the launch with CUDA events on the launching stream. flops / bytes are the ALGORITHMIC work of the launch.

@@ -10,13 +10,12 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "roi_common.cuh"
 
 namespace hoigen {
 
 constexpr int FEAT = 512;
 constexpr int TOK = 197;
-constexpr int G14 = 14;
-constexpr int POOL = 7;
 
 __device__ __forceinline__ float warp_sum_h(float v) {
 #pragma unroll
@@ -129,24 +128,6 @@ prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ s
 constexpr int ROI_THREADS = 256;
 constexpr int ROI_SLICE = 128;
 constexpr int ROI_SMEM_BYTES = 196 * ROI_SLICE * 4;
-
-__device__ __forceinline__ float axis_weight(int t, float start, float bin, int g) {
-  float w = 0.f;
-  const float gf = float(g);
-  for (int p = 0; p < POOL; ++p) {
-    for (int i = 0; i < g; ++i) {
-      float c = start + float(p) * bin + (float(i) + 0.5f) * bin / gf;
-      if (c < -1.0f || c > float(G14)) continue;
-      c = fmaxf(c, 0.f);
-      int lo = int(c), hi;
-      if (lo >= G14 - 1) { lo = hi = G14 - 1; c = float(lo); } else { hi = lo + 1; }
-      const float l = c - float(lo);
-      if (t == lo) w += 1.0f - l;
-      if (t == hi) w += l;
-    }
-  }
-  return w;
-}
 
 // Per-axis RoIAlign weights of every single / union box, computed ONCE (not once per channel slice): one warp per box,
 // lanes 0..13 -> Wy, lanes 16..29 -> Wx, lane 31 -> 1 / (49 * count).  job index: [0, Ntot) singles, [Ntot, Ntot+Ktot)
@@ -547,22 +528,21 @@ int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int3
   HOIGEN_CHECK_ARG(batch > 0 && ntot > 0 && ktot >= 0, "roi_pair_features: bad sizes");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(roi_features_grouped_kernel), ROI_SMEM_BYTES_V2));
-  {
-    KernelScope ks("roi_weights", s, 0, double(ntot + ktot) * (16 + 128));
-    roi_weights_kernel<<<((ntot + ktot) * 32 + 255) / 256, 256, 0, s>>>(boxes, box_off, pair_off, batch, ntot, ktot,
-                                                                        spatial_scale, roi_weights);
-  }
-  HOIGEN_CHECK_LAUNCH();
-  {
+  static const bool simt = getenv("HOIGEN_ROI_SIMT") != nullptr;      // A/B switch: the fp32 SIMT form (four boxes per warp)
+  if (simt) {
+    {
+      KernelScope ks("roi_weights", s, 0, double(ntot + ktot) * (16 + 128));
+      roi_weights_kernel<<<((ntot + ktot) * 32 + 255) / 256, 256, 0, s>>>(boxes, box_off, pair_off, batch, ntot, ktot,
+                                                                          spatial_scale, roi_weights);
+    }
+    HOIGEN_CHECK_LAUNCH();
+    KernelScope ks("roi_features", s, 2.0 * double(ntot + ktot) * 196 * FEAT, double(batch) * 196 * FEAT * 4 + double(ntot + ktot) * (16 + FEAT * 4));
+    roi_features_grouped_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES_V2, s>>>(
+          tokens, roi_weights, box_off, pair_off, ntot, single_feat, union_feat);
+  } else {
     // algorithmic bytes: token map read once + boxes + one fp32 feature row per single / union box
     KernelScope ks("roi_features", s, 2.0 * double(ntot + ktot) * 196 * FEAT, double(batch) * 196 * FEAT * 4 + double(ntot + ktot) * (16 + FEAT * 4));
-    static const bool simt = getenv("HOIGEN_ROI_SIMT") != nullptr;      // A/B switch: the fp32 SIMT form (four boxes per warp)
-    if (simt) {
-      roi_features_grouped_kernel<<<dim3(batch, FEAT / ROI_SLICE), ROI_THREADS, ROI_SMEM_BYTES_V2, s>>>(
-            tokens, roi_weights, box_off, pair_off, ntot, single_feat, union_feat);
-    } else {
-      HOIGEN_TRY_RC(launch_roi_features_tc(tokens, roi_weights, box_off, pair_off, batch, ntot, single_feat, union_feat, s));
-    }
+    HOIGEN_TRY_RC(launch_roi_features_tc(tokens, boxes, box_off, pair_off, batch, spatial_scale, single_feat, union_feat, s));
   }
   HOIGEN_CHECK_LAUNCH();
   if (ktot > 0) {

@@ -13,11 +13,12 @@
 // with M = channels (two 128-row tiles per CTA), N = the image's jobs (<= 192 per pass, a multiple of 16: no padding to a
 // power of two), K = tokens in chunks of 64.  grid = (image, channel half).  Per token chunk every thread builds the bf16
 // planes straight into 128B-swizzled K-major shared-memory tiles (token planes transposed on the way: a thread owns one
-// channel and packs 8 consecutive tokens into one 16-byte store; weight planes from the per-axis weights of
-// roi_weights_kernel), one thread issues 2 x 6 x 4 UMMA 128 x N x 16, and the epilogue scales by 1 / (49 count) and writes
+// channel and packs 8 consecutive tokens into one 16-byte store; weight planes from the per-axis weights the CTA
+// computes itself from the boxes), one thread issues 2 x 6 x 4 UMMA 128 x N x 16, and the epilogue scales by 1 / (49 count) and writes
 // the feature rows with coalesced 128-byte stores.
 #include "common.h"
 #include "ptx.cuh"
+#include "roi_common.cuh"
 
 namespace hoigen {
 
@@ -48,8 +49,8 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& h, uint4& m, 
 }
 
 __global__ void __launch_bounds__(RT_THREADS, 1)
-roi_tc_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const float* __restrict__ wts /* (Ntot+Ktot, 32) */,
-              const int* __restrict__ box_off, const int* __restrict__ pair_off, int ntot,
+roi_tc_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const float* __restrict__ boxes /* (Ntot, 4) xyxy */,
+              const int* __restrict__ box_off, const int* __restrict__ pair_off, float spatial_scale,
               float* __restrict__ single_feat, float* __restrict__ union_feat) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -88,15 +89,36 @@ roi_tc_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const float* 
   for (int j0 = 0; j0 < njobs; j0 += RT_MAXJOBS) {
     const int nj = min(RT_MAXJOBS, njobs - j0);
     const int NT = (nj + 15) & ~15;                       // MMA N (multiple of 16)
-    // ---- the pass's per-axis weights -> smem (row r: Wy[0..14) at 0, Wx[0..14) at 16, 1 / (49 count) at 31) ----
-    for (int i = threadIdx.x; i < NT * 32; i += RT_THREADS) {
-      const int r = i >> 5, job = j0 + r;
-      float v = 0.f;
-      if (r < nj) {
-        const int gjob = job < n ? bbase + job : ntot + pbase + (job - n);
-        v = __ldg(wts + size_t(gjob) * 32 + (i & 31));
+    // ---- the pass's per-axis RoIAlign weights, computed here from the boxes (row r: Wy[0..14) at 0, Wx[0..14) at 16,
+    //      1 / (49 count) at 31; single boxes first, then the unions min / max of (human x, box y), U:1007-1023) ----
+    //      one owner thread per (row, axis): 2 NT <= 384 tasks in one round of the 512 threads
+    for (int i = threadIdx.x; i < NT * 2; i += RT_THREADS) {
+      const int r = i >> 1, axis = i & 1, job = j0 + r;
+      float* row = s_w + r * 32 + axis * 16;
+      if (r >= nj) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) row[t] = 0.f;
+        continue;
       }
-      s_w[i] = v;
+      float4 bx;
+      if (job < n) {
+        bx = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + job);
+      } else {
+        const int li = job - n;
+        const int px = li / (n - 1), rr = li % (n - 1);
+        const int py = rr < px ? rr : rr + 1;           // row-major enumeration of (x, y != x), x < n_h
+        const float4 bh = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + px);
+        const float4 bo = __ldg(reinterpret_cast<const float4*>(boxes) + bbase + py);
+        bx = make_float4(fminf(bh.x, bo.x), fminf(bh.y, bo.y), fmaxf(bh.z, bo.z), fmaxf(bh.w, bo.w));
+      }
+      // same expressions as roi_axis_entry: extent = (end * scale - 0.5) - (start * scale - 0.5), g = ceil(extent / 7)
+      const float sx = bx.x * spatial_scale - 0.5f, sy = bx.y * spatial_scale - 0.5f;
+      const float rw = (bx.z * spatial_scale - 0.5f) - sx, rh = (bx.w * spatial_scale - 0.5f) - sy;
+      const int gw = int(ceilf(rw / float(POOL))), gh = int(ceilf(rh / float(POOL)));
+      if (axis == 0) axis_weights_row(row, sy, rh / float(POOL), gh);
+      else           axis_weights_row(row, sx, rw / float(POOL), gw);
+      row[14] = 0.f;
+      row[15] = axis ? 1.0f / (float(max(gh * gw, 1)) * float(POOL * POOL)) : 0.f;
     }
     __syncthreads();
     // this thread's 32 tokens of chunk kc -> registers (32 loads in flight per thread; tokens >= 196 are zero)
@@ -209,10 +231,10 @@ roi_tc_kernel(const float* __restrict__ tokens /* (B*197, 512) */, const float* 
   }
 }
 
-int launch_roi_features_tc(const float* tokens, const float* wts, const int* box_off, const int* pair_off, int batch, int ntot,
-                           float* single_feat, float* union_feat, cudaStream_t s) {
+int launch_roi_features_tc(const float* tokens, const float* boxes, const int* box_off, const int* pair_off, int batch,
+                           float spatial_scale, float* single_feat, float* union_feat, cudaStream_t s) {
   HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(roi_tc_kernel), RT_SMEM_BYTES));
-  roi_tc_kernel<<<dim3(batch, 2), RT_THREADS, RT_SMEM_BYTES, s>>>(tokens, wts, box_off, pair_off, ntot, single_feat, union_feat);
+  roi_tc_kernel<<<dim3(batch, 2), RT_THREADS, RT_SMEM_BYTES, s>>>(tokens, boxes, box_off, pair_off, spatial_scale, single_feat, union_feat);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }

@@ -40,6 +40,8 @@ recs = _cabi.profile_read()
 _cabi.profile(False)
 out = []
 for tag in ("roi_weights", "roi_features", "pair_assemble"):
+    if not any(r[0] == tag for r in recs):
+        continue
     ms = sorted(r[1] for r in recs if r[0] == tag)
     out.append(f"{tag} {ms[len(ms) // 2] * 1e3:.1f} us")
 print(f"simt={os.environ.get('HOIGEN_ROI_SIMT', '0')} B={B} boxes={nh}+{no}: " + ", ".join(out))
