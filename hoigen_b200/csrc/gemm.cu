@@ -557,7 +557,11 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;          // 16 KiB: this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * BK * 2;    // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+#ifdef HOIGEN_EXP_OUT_BYTES
+  static constexpr int OUT_BYTES = HOIGEN_EXP_OUT_BYTES;   // experiment only (epilogue disabled): deeper operand ring
+#else
   static constexpr int OUT_BYTES = TMA_OUT ? (BN / 64) * 16384 : 0;
+#endif
   static constexpr int STAGES_FIT = (196608 - OUT_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int ACC_STRIDE = 256;               // TMEM columns between the two accumulator stages
@@ -741,7 +745,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (TMA_OUT) {
         fence_proxy_async_smem();                                  // staging writes -> visible to the TMA engine
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64) {
+        if (threadIdx.x == 64 && g.debug != 4 && g.debug != 5) {   // 5: whole epilogue but no global writes
           const int row0 = m_blk * (2 * BM) + int(rank) * BM;
 #pragma unroll
           for (int pnl = 0; pnl < BN / 64; ++pnl)
