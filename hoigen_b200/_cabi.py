@@ -32,6 +32,19 @@ class GemmParams(C.Structure):
         ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int32),
         ("block_n", C.c_int32), ("split_k", C.c_int32),
         ("act_param", C.c_float), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p),
+        ("conv_taps", C.c_int32), ("conv_cin", C.c_int32), ("halo_h", C.c_int32), ("halo_w", C.c_int32),
+        ("res_bf16", C.c_void_p), ("ld_resb", C.c_int32),
+    ]
+
+
+CONV_OP_GEMM, CONV_OP_STEM_IM2COL, CONV_OP_MAXPOOL, CONV_OP_GATHER_S2, CONV_OP_AVGPOOL_L2NORM = range(5)
+
+
+class ConvOp(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("in_", C.c_void_p), ("out", C.c_void_p),
+        ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("taps", C.c_int32),
+        ("gemm", GemmParams),
     ]
 
 
@@ -199,6 +212,11 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_score_pairs_fp32": [C.POINTER(ScoreWeightsFp32), C.POINTER(ScoreBuffersFp32), _P, _P, _P, _P, _I, _I, _P],
     "hoigen_score_pairs_folded": [C.POINTER(FoldedWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
     "hoigen_ap_11point": [_P, _P, _P, _P, _I, _P, _P, _P],
+    "hoigen_stem_im2col": [_P, _P, _I, _P],
+    "hoigen_maxpool3x3s2_halo": [_P, _P, _I, _I, _I, _I, _P],
+    "hoigen_conv_gather_s2": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "hoigen_avgpool_l2norm": [_P, _P, _I, _I, _I, _I, _P],
+    "hoigen_conv_plan_run": [_P, _I, _P],
     "hoigen_prepare_proposals": [_P, _P, _P, _I, _I, _L, _F, _I, _I, _F, _P, _P, _P, _P, _P],
     "hoigen_associate_pairs": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P],
     "hoigen_pack_wire": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P, _P],
@@ -241,17 +259,22 @@ def call(name: str, *args) -> None:
     check(getattr(lib, name)(*args, stream_ptr()), name)
 
 
-def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act=ACT_NONE, residual=None,
-              out_f32=None, out_bf16=None, block_n: int = 0, split_k: int = 0, simt: bool = False,
-              act_param: float = 0.0, ln_stats=None, ln_colsum=None) -> None:
-    """out = epi(a[M,K] @ w[N,K]^T); see hoigen_gemm_bf16 in include/hoigen_b200.h."""
-    lib = init(a.device)
+def gemm_params(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act=ACT_NONE, residual=None,
+                out_f32=None, out_bf16=None, block_n: int = 0, split_k: int = 0, act_param: float = 0.0, ln_stats=None,
+                ln_colsum=None, conv_taps: int = 0, halo=None, res_bf16=None) -> "GemmParams":
+    """Fill a hoigen_gemm_params from tensors (no launch).  conv_taps = 9: `a` is the (rows, cin) activation matrix with a
+    zero halo, `w` is (N, 9 * cin); halo = (H + 2, W + 2); res_bf16 = bf16 identity added before the activation."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
     N = w.shape[0]
-    assert w.shape[1] == K
     p = GemmParams()
+    if conv_taps == 9:
+        assert w.shape[1] == 9 * K and halo is not None
+        p.conv_taps, p.conv_cin = 9, K
+        K = 9 * K
+    else:
+        assert w.shape[1] == K
     p.a, p.w = a.data_ptr(), w.data_ptr()
     p.M, p.N, p.K = M, N, K
     p.lda, p.ldw = a.stride(0), w.stride(0)
@@ -276,5 +299,17 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act
         assert ln_stats.dtype == torch.float32 and ln_stats.shape == (M, 2) and ln_stats.is_contiguous()
         assert ln_colsum is not None and ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N
         p.ln_stats, p.ln_colsum = ln_stats.data_ptr(), ln_colsum.data_ptr()
+    if halo is not None:
+        p.halo_h, p.halo_w = int(halo[0]), int(halo[1])
+    if res_bf16 is not None:
+        assert res_bf16.dtype == torch.bfloat16 and res_bf16.stride(1) == 1 and res_bf16.shape[0] >= M
+        p.res_bf16, p.ld_resb = res_bf16.data_ptr(), res_bf16.stride(0)
+    return p
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, *, simt: bool = False, **kw) -> None:
+    """out = epi(a[M,K] @ w[N,K]^T); see hoigen_gemm_bf16 in include/hoigen_b200.h."""
+    lib = init(a.device)
+    p = gemm_params(a, w, **kw)
     fn = lib.hoigen_debug_gemm_simt if simt else lib.hoigen_gemm_bf16
     check(fn(C.byref(p), stream_ptr()), "hoigen_gemm_bf16")

@@ -45,6 +45,12 @@ struct GemmArgs {
   // stream x, W = W . diag(gamma); out = rstd[row] * (acc - mean[row] * colsum[col]) + bias'[col], colsum = sum_k W'[col][k]
   // (staged where the column scale would be), bias' = bias + W beta.  ln_stats = (mean, rstd) per row from the residual pass.
   const float2* ln_stats;
+  // convolution forms (hoigen_gemm_params.conv_taps / halo_* / res_bf16)
+  int tap_kb;               // k-blocks per 3x3 tap (0 = plain GEMM): k-block kb reads A columns (kb % tap_kb) * 64 of the
+                            // rows shifted by (t / 3 - 1) * halo_w + (t % 3 - 1), t = kb / tap_kb
+  int halo_h, halo_w;       // rows on the ring of each (halo_h, halo_w) image are written as 0 (halo_w = 0: off)
+  const __nv_bfloat16* res_bf16;   // added before the activation
+  int ld_resb;
   int debug;  // diagnostics only (HOIGEN_GEMM_DEBUG): 1 = TMA loads without MMAs, 2 = MMAs without TMA loads
   // CTA-pair kernel work split (stream-K): work unit = one k-block of one tile; pair p owns units [bound(p), bound(p+1))
   float* sk_ws;     // fp32 partial-accumulator slots, one per (pair, cta rank)
@@ -53,6 +59,24 @@ struct GemmArgs {
   int sk_tiles;     // the LAST sk_tiles tiles are split at k-block granularity; the others are dealt out round-robin
   int split_k;      // one-CTA kernel: every tile's k-range is cut into split_k units (sk_ws slots + sk_flags tile counters)
 };
+
+// A-operand TMA coordinates of k-block kb: plain GEMM (kb * 64, row0) or the row-shifted view of a 3x3 tap
+__device__ __forceinline__ void a_coords(const GemmArgs& g, int kb, int row0, int& col, int& row) {
+  col = kb * BK; row = row0;
+  if (g.tap_kb > 0) {
+    const int t = kb / g.tap_kb;
+    col = (kb - t * g.tap_kb) * BK;
+    row = row0 + (t / 3 - 1) * g.halo_w + (t % 3 - 1);
+  }
+}
+
+// true when output row `row` is a halo pixel of its (halo_h, halo_w) image
+__device__ __forceinline__ bool halo_row(const GemmArgs& g, int row) {
+  if (g.halo_w == 0) return false;
+  const int q = row % (g.halo_h * g.halo_w);
+  const int y = q / g.halo_w, x = q - y * g.halo_w;
+  return x == 0 || x == g.halo_w - 1 || y == 0 || y == g.halo_h - 1;
+}
 
 template <int BN>
 struct GemmCfg {
@@ -115,7 +139,7 @@ __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const 
                                                        bool res_vec, const float* res_row, const float* s_bias,
                                                        const float* s_cs, int row, bool row_ok, int col0,
                                                        uint8_t* out_tile = nullptr, int rrow = 0, int tile_col = 0,
-                                                       float ln_mean = 0.f, float ln_rstd = 1.f) {
+                                                       float ln_mean = 0.f, float ln_rstd = 1.f, bool halo = false) {
   const bool full_chunk = (col0 + CW <= g.N);
   // EPI >= 0: the epilogue recipe is a compile-time constant (act | colscale << 4 | bias << 5 | layernorm << 6), no work
   // for absent terms
@@ -145,9 +169,32 @@ __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const 
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
+  if (EPI < 0 && g.res_bf16 != nullptr && row_ok) {   // Bottleneck identity: added before the activation
+    const __nv_bfloat16* rp = g.res_bf16 + size_t(row) * g.ld_resb + col0;
+    if (full_chunk && (g.ld_resb & 7) == 0) {
+#pragma unroll
+      for (int h = 0; h < CW / 8; ++h) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp) + h);
+        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[8 * h + 2 * e] += __uint_as_float(w4[e] << 16);
+          v[8 * h + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (col0 + j < g.N) v[j] += __bfloat162float(rp[j]);
+    }
+  }
   if (act != HOIGEN_ACT_NONE) {
 #pragma unroll
     for (int j = 0; j < CW; ++j) v[j] = apply_act(v[j], act, g.act_param);
+  }
+  if (EPI < 0 && halo) {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) v[j] = 0.f;
   }
   if (has_cs) {
 #pragma unroll
@@ -226,6 +273,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
     const float2 st = __ldg(g.ln_stats + row);
     ln_mean = st.x; ln_rstd = st.y;
   }
+  const bool halo = EPI < 0 && halo_row(g, row);
   if (res_vec && colbase + CW <= g.N) {
 #pragma unroll
     for (int j = 0; j < CW / 4; ++j) res[0][j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
@@ -259,7 +307,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
       }
     }
     epilogue_process_chunk<EPI>(g, r[c & 1], res[c & 1], res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0,
-                           out_tile, rrow, tile_col0 + c * CW, ln_mean, ln_rstd);
+                           out_tile, rrow, tile_col0 + c * CW, ln_mean, ln_rstd, halo);
     if (!more) break;
   }
   tmem_wait_ld();
@@ -303,7 +351,7 @@ __device__ __forceinline__ void epilogue_from_parts(const GemmArgs& g, int row, 
       ln_mean = st.x; ln_rstd = st.y;
     }
     epilogue_process_chunk<EPI>(g, r, res, res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0, nullptr, 0, 0,
-                                ln_mean, ln_rstd);
+                                ln_mean, ln_rstd, EPI < 0 && halo_row(g, row));
   }
 }
 
@@ -373,7 +421,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t b_dst = a_dst + Cfg::A_BYTES;
           const uint32_t full = bar_full + 8u * stage;
           mbar_arrive_expect_tx(full, Cfg::STAGE_BYTES);
-          tma_load_2d(a_dst, &tmA, full, kb * BK, m_blk * BM);
+          int a_col, a_row;
+          a_coords(g, kb, m_blk * BM, a_col, a_row);
+          tma_load_2d(a_dst, &tmA, full, a_col, a_row);
           tma_load_2d(b_dst, &tmB, full, kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -645,7 +695,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           } else {
             if (rank == 0) mbar_arrive_expect_tx(full, 2 * Cfg::STAGE_BYTES);
             else mbar_arrive_leader(full);
-            tma_load_2d_2sm(a_dst, &tmA, full, kb * BK, m_blk * (2 * BM) + int(rank) * BM);
+            int a_col, a_row;
+            a_coords(g, kb, m_blk * (2 * BM) + int(rank) * BM, a_col, a_row);
+            tma_load_2d_2sm(a_dst, &tmA, full, a_col, a_row);
             tma_load_2d_2sm(b_dst, &tmB, full, kb * BK, n_blk * BN + int(rank) * (BN / 2));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -778,11 +830,23 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ a, const __nv
   const int m = blockIdx.y;
   if (n >= g.N || m >= g.M) return;
   float acc = 0.f;
-  for (int k = 0; k < g.K; ++k)
-    acc = fmaf(__bfloat162float(a[size_t(m) * lda + k]), __bfloat162float(w[size_t(n) * ldw + k]), acc);
+  if (g.tap_kb > 0) {
+    const int cin = g.tap_kb * BK;
+    for (int t = 0; t < 9; ++t) {
+      const long long src = (long long)m + (t / 3 - 1) * g.halo_w + (t % 3 - 1);
+      if (src < 0 || src >= g.M) continue;
+      for (int k = 0; k < cin; ++k)
+        acc = fmaf(__bfloat162float(a[size_t(src) * lda + k]), __bfloat162float(w[size_t(n) * ldw + t * cin + k]), acc);
+    }
+  } else {
+    for (int k = 0; k < g.K; ++k)
+      acc = fmaf(__bfloat162float(a[size_t(m) * lda + k]), __bfloat162float(w[size_t(n) * ldw + k]), acc);
+  }
   if (g.ln_stats) acc = g.ln_stats[m].y * (acc - g.ln_stats[m].x * g.colscale[n]);
   if (g.bias) acc += g.bias[n];
+  if (g.res_bf16) acc += __bfloat162float(g.res_bf16[size_t(m) * g.ld_resb + n]);
   acc = apply_act(acc, g.act, g.act_param);
+  if (halo_row(g, m)) acc = 0.f;
   if (g.colscale && !g.ln_stats) acc *= g.colscale[n];
   if (g.residual) acc += g.residual[size_t(m) * g.ld_res + n];
   if (g.out_f32) g.out_f32[size_t(m) * g.ld_f32 + n] = acc;
@@ -793,7 +857,7 @@ static int validate(const hoigen_gemm_params* p) {
   HOIGEN_CHECK_ARG(p != nullptr, "gemm: null params");
   HOIGEN_CHECK_ARG(p->a && p->w, "gemm: null operand");
   HOIGEN_CHECK_ARG(p->M > 0 && p->N > 0 && p->K > 0, "gemm: bad shape M=%d N=%d K=%d", p->M, p->N, p->K);
-  HOIGEN_CHECK_ARG(p->lda >= p->K && p->ldw >= p->K, "gemm: lda/ldw < K");
+  HOIGEN_CHECK_ARG((p->conv_taps == 9 || p->lda >= p->K) && p->ldw >= p->K, "gemm: lda/ldw < K");
   HOIGEN_CHECK_ARG((p->lda % 8) == 0 && (p->ldw % 8) == 0, "gemm: lda/ldw must be multiples of 8 (got %d, %d)",
                    p->lda, p->ldw);
   HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w) & 15) == 0,
@@ -802,6 +866,12 @@ static int validate(const hoigen_gemm_params* p) {
   HOIGEN_CHECK_ARG(!p->out_f32 || p->ld_f32 >= p->N, "gemm: ld_f32 < N");
   HOIGEN_CHECK_ARG(!p->out_bf16 || p->ld_bf16 >= p->N, "gemm: ld_bf16 < N");
   HOIGEN_CHECK_ARG(!p->residual || p->ld_res >= p->N, "gemm: ld_res < N");
+  HOIGEN_CHECK_ARG(p->conv_taps == 0 || p->conv_taps == 1 || p->conv_taps == 9, "gemm: conv_taps must be 0, 1 or 9 (got %d)", p->conv_taps);
+  HOIGEN_CHECK_ARG(p->conv_taps != 9 || (p->conv_cin > 0 && p->conv_cin % 64 == 0 && p->K == 9 * p->conv_cin && p->halo_w > 0 && p->lda >= p->conv_cin),
+                   "gemm: 3x3 form needs conv_cin %% 64 == 0, K == 9 * conv_cin, halo_w > 0 (cin=%d K=%d)", p->conv_cin, p->K);
+  HOIGEN_CHECK_ARG(p->halo_w == 0 || (p->halo_h >= 3 && p->halo_w >= 3 && p->M % (p->halo_h * p->halo_w) == 0),
+                   "gemm: M must be a whole number of (halo_h, halo_w) images");
+  HOIGEN_CHECK_ARG(!p->res_bf16 || (p->ld_resb >= p->N && !p->ln_stats), "gemm: bad res_bf16 layout");
   HOIGEN_CHECK_ARG(p->act >= 0 && p->act <= 3, "gemm: bad act %d", p->act);
   HOIGEN_CHECK_ARG(!p->ln_stats || (p->ln_colsum && !p->colscale), "gemm: ln_stats needs ln_colsum and excludes colscale");
   HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(p->ln_colsum) & 15) == 0,
@@ -826,6 +896,9 @@ static GemmArgs to_args(const hoigen_gemm_params* p) {
   static const int dbg = getenv("HOIGEN_GEMM_DEBUG") ? atoi(getenv("HOIGEN_GEMM_DEBUG")) : 0;
   g.debug = dbg;
   g.sk_ws = nullptr; g.sk_flags = nullptr; g.sk_snap = 0; g.sk_tiles = 0; g.split_k = 1;
+  g.tap_kb = p->conv_taps == 9 ? p->conv_cin / BK : 0;
+  g.halo_h = p->halo_h; g.halo_w = p->halo_w;
+  g.res_bf16 = reinterpret_cast<const __nv_bfloat16*>(p->res_bf16); g.ld_resb = p->ld_resb;
   return g;
 }
 
@@ -856,7 +929,7 @@ template <int BN>
 static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(gemm_bf16_kernel<BN>), Cfg::SMEM_BYTES));
-  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
+  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
   if (!ta) return HOIGEN_ERR_CUDA;
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN);
   if (!tb) return HOIGEN_ERR_CUDA;
@@ -883,7 +956,7 @@ template <int BN, bool TMA_OUT, int EPI>
 static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream, bool force_split) {
   using Cfg = Gemm2Cfg<BN, TMA_OUT>;
   HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(gemm2_bf16_kernel<BN, TMA_OUT, EPI>), Cfg::SMEM_BYTES));
-  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
+  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
   if (!ta) return HOIGEN_ERR_CUDA;
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN / 2);
   if (!tb) return HOIGEN_ERR_CUDA;
@@ -939,6 +1012,7 @@ static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream, bool f
   static const bool no_tma_out = getenv("HOIGEN_GEMM_NO_TMA_STORE") != nullptr;
   const bool tma_out = !no_tma_out && p->out_bf16 && !p->out_f32 && !p->residual && (p->ld_bf16 % 8) == 0 && (p->N % 8) == 0;
   if (!tma_out) return launch_gemm2_impl<BN, false, -1>(p, stream, force_split);
+  if (p->halo_w > 0 || p->res_bf16) return launch_gemm2_impl<BN, true, -1>(p, stream, force_split);   // convolution epilogues
   // compile-time epilogue recipes of the encoder's bf16-output GEMMs; anything else uses the runtime-flag epilogue
   const bool b = p->bias != nullptr, c = p->colscale != nullptr;
   if (p->ln_stats) {   // LayerNorm-folded QKV / c_fc

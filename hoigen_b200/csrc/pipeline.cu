@@ -11,7 +11,7 @@ namespace hoigen {
 static int gemm(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias, int act,
                 const float* colscale, const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_bf16,
                 int ld_bf16, cudaStream_t s) {
-  hoigen_gemm_params p;
+  hoigen_gemm_params p = {};
   p.a = a; p.w = w; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw;
   p.bias = bias; p.colscale = colscale; p.act = act;
   p.residual = residual; p.ld_res = ld_res;
@@ -28,7 +28,7 @@ static int gemm(const void* a, int lda, const void* w, int ldw, int M, int N, in
 // bf16-output GEMM with the preceding LayerNorm folded into its epilogue (see hoigen_gemm_params.ln_stats)
 static int gemm_ln(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias, int act,
                    const float* ln_stats, const float* ln_colsum, void* out_bf16, int ld_bf16, cudaStream_t s) {
-  hoigen_gemm_params p;
+  hoigen_gemm_params p = {};
   p.a = a; p.w = w; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw;
   p.bias = bias; p.colscale = nullptr; p.act = act;
   p.residual = nullptr; p.ld_res = 0;
@@ -44,7 +44,7 @@ static int gemm_ln(const void* a, int lda, const void* w, int ldw, int M, int N,
 
 static int gemm_exp(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias, float beta,
                     void* out_bf16, int ld_bf16, cudaStream_t s) {
-  hoigen_gemm_params p;
+  hoigen_gemm_params p = {};
   p.a = a; p.w = w; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw;
   p.bias = bias; p.colscale = nullptr; p.act = HOIGEN_ACT_EXP;
   p.residual = nullptr; p.ld_res = 0;

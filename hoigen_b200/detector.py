@@ -228,14 +228,23 @@ class UPT(nn.Module):
     def invalidate_packed(self) -> None:
         self._packed = None
 
-    def accelerate_dino(self, use_graph: bool = True) -> "UPT":
-        """Opt in to the fast execution of the injected DINO ResNet-50 (hoigen_b200.dino.FastDinoR50: BatchNorms folded, bf16
-        channels-last, one CUDA graph per batch size).  Row a8 of SURVEY.md §8 is outside the parity-gated path; the stock
-        fp32 module stays the default."""
-        from .dino import FastDinoR50
+    def accelerate_dino(self, use_graph: bool = True, engine: str = "kernels") -> "UPT":
+        """Opt in to a fast execution of the injected DINO ResNet-50 (row a8 of SURVEY.md §8, U:1616-1618).
+
+        engine = "kernels" (default): hoigen_b200.dino.KernelDinoR50 -- BatchNorms folded, NHWC bf16, every convolution on
+        the repo's tcgen05 GEMM (3x3 as an implicit GEMM), one C call per batch.  engine = "cudnn": FastDinoR50 -- the same
+        folded module left to cuDNN (bf16 channels-last, one CUDA graph per batch size).  Both give the stock fp32 module's
+        features to bf16 accuracy; the stock module stays the default because this row is outside the parity-gated path."""
+        from .dino import FastDinoR50, KernelDinoR50
         if self.dino_model is None:
             raise ValueError("no dino_model to accelerate")
-        object.__setattr__(self, "_fast_dino", FastDinoR50(self.dino_model, use_graph=use_graph))
+        if engine == "kernels":
+            fast = KernelDinoR50(self.dino_model)
+        elif engine == "cudnn":
+            fast = FastDinoR50(self.dino_model, use_graph=use_graph)
+        else:
+            raise ValueError(f"accelerate_dino: engine must be 'kernels' or 'cudnn', got {engine!r}")
+        object.__setattr__(self, "_fast_dino", fast)
         return self
 
     def _apply(self, fn, *a, **k):

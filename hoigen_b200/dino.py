@@ -9,14 +9,24 @@ channels-last tensors, the whole network replayed from ONE CUDA graph per batch 
 is library tuning outside the hand-written kernels, NOT part of the parity-gated path, and OFF unless asked for
 (`UPT.accelerate_dino()`).  Outputs are the L2-normalised fp32 features the scoring stage takes (`dino_image_features`);
 against the stock fp32 module they differ by bf16 rounding (tests/test_gpu_e2e.py::test_fast_dino_*).
+
+`KernelDinoR50` (round 2) is the same network on the repo's OWN kernels: every convolution runs on the tcgen05 GEMM of
+`csrc/gemm.cu` -- 1x1 convolutions are plain GEMMs over NHWC rows, 3x3 / stride-1 convolutions are nine accumulated
+products of row-shifted views of the same activation matrix (an implicit GEMM: the activations carry a one-pixel zero halo,
+so no im2col matrix exists), bias + identity + ReLU + halo zeroing live in the GEMM epilogue -- plus four small row kernels
+(`csrc/conv_rows.cu`: stem im2col, max-pool, the stride-2 gathers, average-pool + L2 norm).  One C call
+(`hoigen_conv_plan_run`) launches the whole 60-step plan.
 """
 from __future__ import annotations
 
 import copy
-from typing import Dict
+import ctypes as C
+from typing import Dict, List
 
 import torch
 from torch import nn
+
+from . import _cabi
 
 
 def _fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
@@ -86,3 +96,132 @@ class FastDinoR50(nn.Module):
         static_in.copy_(images)
         graph.replay()
         return static_out.clone()
+
+
+class KernelDinoR50(nn.Module):
+    """`features = net(images)` -> (B, 2048) fp32, L2-normalised (U:1617-1618), on the hand-written kernels.
+
+    Weights: the BatchNorm-folded convolutions of the given torchvision ResNet-50 (eval), bf16, packed K-major:
+    1x1 -> (Cout, Cin); 3x3 -> (Cout, 9 Cin) with k = (ky * 3 + kx) * Cin + c; stem 7x7 -> (64, 160), k = (ky * 7 + kx) * 3 + c.
+    """
+
+    STEM_K = 160
+
+    def __init__(self, dino_model: nn.Module):
+        super().__init__()
+        dev = next(dino_model.parameters()).device
+        if dev.type != "cuda":
+            raise ValueError("KernelDinoR50 needs the module on a CUDA device")
+        m = fold_batchnorms(dino_model)
+        self.device_ = dev
+        self._keep: List[torch.Tensor] = []
+
+        def pack(conv: nn.Conv2d):
+            w = conv.weight.detach().float()
+            co, ci, kh, kw = w.shape
+            wk = w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+            if kh == 7:
+                wk = torch.nn.functional.pad(wk, (0, self.STEM_K - wk.shape[1]))
+            wk = wk.to(torch.bfloat16).contiguous()
+            b = conv.bias.detach().float().contiguous()
+            self._keep += [wk, b]
+            return wk, b
+
+        self.stem = pack(m.conv1)
+        self.stages = []
+        for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
+            blocks = []
+            for blk in layer:
+                blocks.append(dict(c1=pack(blk.conv1), c2=pack(blk.conv2), c3=pack(blk.conv3),
+                                   ds=pack(blk.downsample[0]) if blk.downsample is not None else None,
+                                   stride=blk.conv2.stride[0]))
+            self.stages.append(blocks)
+        self._plans: Dict[tuple, dict] = {}
+
+    # ---- plan construction: buffers + the op list for one (batch, stream) ----
+    def _build_plan(self, B: int) -> dict:
+        dev = self.device_
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        ops: List[_cabi.ConvOp] = []
+        bufs: List[torch.Tensor] = []
+
+        def new(rows, cols):
+            t = torch.zeros(rows, cols, **bf)
+            bufs.append(t)
+            return t
+
+        def gemm(a, wb, out, *, relu, halo=None, taps=0, res=None):
+            op = _cabi.ConvOp()
+            op.kind = _cabi.CONV_OP_GEMM
+            op.gemm = _cabi.gemm_params(a, wb[0], bias=wb[1], act=_cabi.ACT_RELU if relu else _cabi.ACT_NONE, out_bf16=out,
+                                        conv_taps=taps, halo=halo, res_bf16=res)
+            ops.append(op)
+
+        def rowop(kind, src, dst, h=0, w=0, c=0, taps=0):
+            op = _cabi.ConvOp()
+            op.kind, op.in_, op.out = kind, src.data_ptr() if src is not None else 0, dst.data_ptr()
+            op.batch, op.h, op.w, op.c, op.taps = B, h, w, c, taps
+            ops.append(op)
+
+        stem_rows = new(B * 112 * 112, self.STEM_K)
+        stem_out = new(B * 112 * 112, 64)
+        rowop(_cabi.CONV_OP_STEM_IM2COL, None, stem_rows)
+        gemm(stem_rows, self.stem, stem_out, relu=True)
+        H = 56
+        x = new(B * (H + 2) * (H + 2), 64)
+        rowop(_cabi.CONV_OP_MAXPOOL, stem_out, x, 112, 112, 64)
+        cin = 64
+        for blocks in self.stages:
+            for blk in blocks:
+                width = blk["c1"][0].shape[0]
+                cout = blk["c3"][0].shape[0]
+                halo_in = (H + 2, H + 2)
+                rows_in = B * halo_in[0] * halo_in[1]
+                t1 = new(rows_in, width)
+                gemm(x, blk["c1"], t1, relu=True, halo=halo_in)
+                if blk["stride"] == 2:
+                    Ho = H // 2
+                    halo_out = (Ho + 2, Ho + 2)
+                    rows_out = B * halo_out[0] * halo_out[1]
+                    g2 = new(rows_out, 9 * width)
+                    rowop(_cabi.CONV_OP_GATHER_S2, t1, g2, H, H, width, 9)
+                    t2 = new(rows_out, width)
+                    gemm(g2, blk["c2"], t2, relu=True, halo=halo_out)
+                    gs = new(rows_out, cin)
+                    rowop(_cabi.CONV_OP_GATHER_S2, x, gs, H, H, cin, 1)
+                    sc = new(rows_out, cout)
+                    gemm(gs, blk["ds"], sc, relu=False, halo=halo_out)
+                    H = Ho
+                else:
+                    halo_out, rows_out = halo_in, rows_in
+                    t2 = new(rows_out, width)
+                    gemm(t1, blk["c2"], t2, relu=True, halo=halo_out, taps=9)
+                    if blk["ds"] is not None:
+                        sc = new(rows_out, cout)
+                        gemm(x, blk["ds"], sc, relu=False, halo=halo_out)
+                    else:
+                        sc = x
+                y = new(rows_out, cout)
+                gemm(t2, blk["c3"], y, relu=True, halo=halo_out, res=sc)
+                x, cin = y, cout
+        out = torch.empty(B, cin, device=dev, dtype=torch.float32)
+        op = _cabi.ConvOp()
+        op.kind, op.in_, op.out = _cabi.CONV_OP_AVGPOOL_L2NORM, x.data_ptr(), out.data_ptr()
+        op.batch, op.h, op.w, op.c = B, H, H, cin
+        ops.append(op)
+        arr = (_cabi.ConvOp * len(ops))(*ops)
+        return dict(ops=arr, n=len(ops), bufs=bufs, out=out)
+
+    @torch.no_grad()
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        if images.device != self.device_ or images.dtype != torch.float32 or tuple(images.shape[1:]) != (3, 224, 224):
+            raise ValueError("KernelDinoR50 takes (B, 3, 224, 224) fp32 images on the module's device")
+        images = images.contiguous()
+        lib = _cabi.init(images.device)
+        key = (int(images.shape[0]), torch.cuda.current_stream(images.device).cuda_stream)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = self._build_plan(key[0])
+        plan["ops"][0].in_ = images.data_ptr()
+        _cabi.check(lib.hoigen_conv_plan_run(plan["ops"], plan["n"], _cabi.stream_ptr()), "hoigen_conv_plan_run")
+        return plan["out"].clone()

@@ -57,7 +57,7 @@ HOIGEN_API long long hoigen_profile_read(char* buf, long long cap);
  * Replaces every nn.Linear / F.linear / `@` on the path: conv1-as-GEMM C:491, in_proj/out_proj
  * C:443-445, c_fc/c_proj C:428-432, adapter down/up C:184,201, `@ proj` C:505, and the cache /
  * text GEMMs U:1156-1163.
- *   v = acc (+ bias[n]) ; v = act(v) ; v *= colscale[n] ; v += residual[m,n]
+ *   v = acc (+ bias[n]) (+ res_bf16[m,n]) ; v = act(v) ; v *= colscale[n] ; v += residual[m,n]
  *   then out_f32[m,n] = v and/or out_bf16[m,n] = bf16(v).   residual may alias out_f32.
  * lda/ldw in elements, multiples of 8 (16-byte TMA strides); a, w 16-byte aligned.
  * ---------------------------------------------------------------------------------------------- */
@@ -87,6 +87,20 @@ typedef struct {
    * bias = b + W beta.  NULL = plain GEMM.  Excludes colscale. */
   const float* ln_stats;   /* (M, 2) */
   const float* ln_colsum;  /* (N) */
+  /* Convolutions of the ResNet-50 branch (U:1616-1618: dino_model = torchvision resnet50, eval) on NHWC bf16 activations
+   * stored WITH a one-pixel zero halo: rows = the pixels of (B, halo_h, halo_w) = (B, H + 2, W + 2), columns = channels.
+   *   1x1 convolution = this GEMM as it is.   3x3 / stride 1 / pad 1 (conv_taps = 9) = nine accumulated products of
+   *   ROW-SHIFTED views of the same matrix: a = [M, conv_cin], w = [N, 9 * conv_cin] with k = (ky * 3 + kx) * conv_cin + c,
+   *   K = 9 * conv_cin; tap t reads rows m + (t / 3 - 1) * halo_w + (t % 3 - 1) (rows outside [0, M) read as zero) --
+   *   an implicit GEMM: no im2col matrix exists.
+   * halo_w > 0: output rows on the halo ring are written as 0 (they are the next convolution's zero padding).
+   * res_bf16: bf16 [M, ld_resb] added BEFORE the activation (Bottleneck: relu(conv3 + identity)).
+   * All zero / NULL = plain GEMM. */
+  int32_t conv_taps;       /* 0, 1 or 9 */
+  int32_t conv_cin;        /* multiple of 64 when conv_taps = 9 */
+  int32_t halo_h, halo_w;
+  const void* res_bf16;
+  int32_t ld_resb;
 } hoigen_gemm_params;
 
 HOIGEN_API int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream);
@@ -429,6 +443,45 @@ HOIGEN_API int hoigen_prepare_proposals(const float* scores, const int64_t* labe
                                         int32_t num_queries, int64_t human_idx, float box_score_thresh,
                                         int32_t min_instances, int32_t max_instances, float nms_iou, float* out_boxes,
                                         float* out_scores, int64_t* out_labels, int32_t* counts, hoigen_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a8: the ResNet-50 branch of the forward -- `dino_model(images_clip)` then `/ norm` (U:1616-1618; dino_model is a
+ * torchvision resnet50 with fc = Identity in eval mode, main_tip_finetune.py:393,404-405).  BatchNorms are folded into the
+ * convolutions at pack time; activations are NHWC bf16 with a one-pixel zero halo (rows = pixels of (B, H+2, W+2));
+ * 1x1 convolutions and the 3x3 / stride-1 ones run on hoigen_gemm_bf16 (conv_taps / halo_* / res_bf16 of
+ * hoigen_gemm_params: bias + identity + ReLU + halo zeroing in the epilogue); these are the remaining row kernels and the
+ * runner that executes a packed list of such steps in order on one stream.
+ * ---------------------------------------------------------------------------------------------- */
+/* images (B,3,224,224) fp32 -> rows (B*112*112, 160) bf16: im2col of conv1 (7x7, stride 2, pad 3), column = (ky*7+kx)*3+c,
+ * columns 147..159 zero. */
+HOIGEN_API int hoigen_stem_im2col(const float* images, void* rows_bf16, int32_t batch, hoigen_stream_t stream);
+/* MaxPool2d(3, stride 2, padding 1): in (B,h,w,c) bf16 without halo -> out (B, h/2+2, w/2+2, c) with the zero halo */
+HOIGEN_API int hoigen_maxpool3x3s2_halo(const void* in_bf16, void* out_bf16, int32_t batch, int32_t h, int32_t w, int32_t c,
+                                        hoigen_stream_t stream);
+/* A operand of the stride-2 convolutions: in (B, h+2, w+2, c) -> rows (B*(h/2+2)*(w/2+2), taps*c); taps = 9: 3x3 / pad 1,
+ * column = (ky*3+kx)*c + channel; taps = 1: the 1x1 shortcut.  Rows of the output ring are zeros. */
+HOIGEN_API int hoigen_conv_gather_s2(const void* in_bf16, void* rows_bf16, int32_t batch, int32_t h, int32_t w, int32_t c,
+                                     int32_t taps, hoigen_stream_t stream);
+/* AdaptiveAvgPool2d(1) over the interior of (B, h+2, w+2, c), then x / ||x||_2 (U:1618) -> (B, c) fp32; c % 256 == 0, <= 2048 */
+HOIGEN_API int hoigen_avgpool_l2norm(const void* in_bf16, float* out, int32_t batch, int32_t h, int32_t w, int32_t c,
+                                     hoigen_stream_t stream);
+
+typedef enum {
+  HOIGEN_CONV_OP_GEMM = 0,            /* gemm                                   */
+  HOIGEN_CONV_OP_STEM_IM2COL = 1,     /* in = images, out = rows, batch          */
+  HOIGEN_CONV_OP_MAXPOOL = 2,         /* in, out, batch, h, w, c                 */
+  HOIGEN_CONV_OP_GATHER_S2 = 3,       /* in, out, batch, h, w, c, taps           */
+  HOIGEN_CONV_OP_AVGPOOL_L2NORM = 4   /* in, out (fp32), batch, h, w, c          */
+} hoigen_conv_op_kind;
+typedef struct {
+  int32_t kind;
+  const void* in;
+  void* out;
+  int32_t batch, h, w, c, taps;
+  hoigen_gemm_params gemm;
+} hoigen_conv_op;
+/* Launches ops[0..n_ops) in order on `stream`; stops at the first error. */
+HOIGEN_API int hoigen_conv_plan_run(const hoigen_conv_op* ops, int32_t n_ops, hoigen_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -735,7 +735,7 @@ def test_fast_dino_matches_stock_module(cuda_device):
         ref_feat = ref_feat / ref_feat.norm(dim=-1, keepdim=True)
     dets_stock, inter_stock = m.forward_from_proposals(imgs, props, None, return_intermediates=True)
     logits_stock = [l.clone() for l in inter_stock["logits"]]          # the intermediates are views of reused workspace
-    m.accelerate_dino()
+    m.accelerate_dino(engine="cudnn")
     for rep in range(2):                            # second call replays the captured graph
         fast = m._fast_dino(imgs)
         cos = (fast * ref_feat).sum(-1)
@@ -748,4 +748,56 @@ def test_fast_dino_matches_stock_module(cuda_device):
         worst = max(worst, (inter_fast["logits"][b] - logits_stock[b]).abs().max().item())
     assert worst > 0.0, "the fast branch was not used"
     print(f"fast DINO: min cosine {cos.min().item():.6f}, logits max-abs vs stock-module run {worst:.3e}")
+    assert worst <= 2e-3, worst
+
+
+def _random_r50(device):
+    import torchvision
+    torch.manual_seed(0)
+    r50 = torchvision.models.resnet50(weights=None)
+    r50.fc = torch.nn.Identity()
+    for mod in r50.modules():                       # non-trivial BatchNorm statistics, as in a trained checkpoint
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5); mod.weight.data.uniform_(0.8, 1.2); mod.bias.data.normal_(0, 0.1)
+    return r50.to(device).eval()
+
+
+def test_kernel_dino_matches_stock_module(cuda_device):
+    """Row a8 on the repo's own kernels (UPT.accelerate_dino(engine="kernels") -> dino.KernelDinoR50): every convolution of
+    the injected torchvision ResNet-50 on the tcgen05 GEMM (1x1 = GEMM, 3x3 / stride 1 = nine row-shifted accumulated
+    products over haloed NHWC rows, stride-2 through the gather kernel), max-pool, average-pool + L2 norm.  Against the stock
+    fp32 module (U:1616-1618): cosine > 0.9995 per image (bf16 activations and weights), detections keep every index, logits
+    inside the bar; batch sizes 1 and 5 exercise ragged tile edges."""
+    from hoigen_b200 import synthetic as S
+    r50 = _random_r50(cuda_device)
+    m, enc, head = _build(117, 256, cuda_device)
+    m.dino_model = r50
+    B = 5
+    imgs = S.make_images(B, seed=960).to(cuda_device)
+    props = _props_to(S.make_region_props(B, 4, 4, seed=961), cuda_device)
+    with torch.no_grad():
+        ref_feat = r50(imgs)
+        ref_feat = ref_feat / ref_feat.norm(dim=-1, keepdim=True)
+    dets_stock, inter_stock = m.forward_from_proposals(imgs, props, None, return_intermediates=True)
+    logits_stock = [l.clone() for l in inter_stock["logits"]]
+    m.accelerate_dino(engine="kernels")
+    for rep in range(2):
+        fast = m._fast_dino(imgs)
+        assert fast.shape == ref_feat.shape and fast.dtype == torch.float32
+        assert torch.isfinite(fast).all()
+        cos = (fast * ref_feat).sum(-1)
+        assert cos.min().item() > 0.9995, cos
+        assert ((fast.norm(dim=-1) - 1).abs() < 1e-5).all()
+    one = m._fast_dino(imgs[:1])
+    assert (one * ref_feat[:1]).sum(-1).item() > 0.9995
+    assert (one - fast[:1]).abs().max().item() < 2e-3          # batch-size independent up to tile-order rounding
+    dets_fast, inter_fast = m.forward_from_proposals(imgs, props, None, return_intermediates=True)
+    worst = 0.0
+    for b in range(B):
+        for k in ("pairing", "labels", "objects"):
+            assert torch.equal(dets_fast[b][k], dets_stock[b][k]), k
+        worst = max(worst, (inter_fast["logits"][b] - logits_stock[b]).abs().max().item())
+    assert worst > 0.0, "the kernel branch was not used"
+    print(f"kernel DINO: min cosine {cos.min().item():.6f}, max-abs feature diff {(fast - ref_feat).abs().max().item():.3e}, "
+          f"logits max-abs vs stock-module run {worst:.3e}")
     assert worst <= 2e-3, worst

@@ -615,3 +615,113 @@ def test_cache_fused_kernel(cuda_device, ktot, N, C, affinity):
     err = (got - ref).abs().max().item()
     print(f"fused cache kernel ktot={ktot} N={N} C={C} affinity={affinity}: max-abs err {err:.3e} (|ref| max {ref.abs().max():.2f})")
     assert err < 2e-3 * scale, err
+
+
+def _haloed(x_nchw):
+    """(B, C, H, W) fp32 -> (B * (H + 2) * (W + 2), C) bf16 rows with the one-pixel zero halo."""
+    B, Cc, H, W = x_nchw.shape
+    xp = torch.nn.functional.pad(x_nchw, (1, 1, 1, 1))
+    return xp.permute(0, 2, 3, 1).reshape(B * (H + 2) * (W + 2), Cc).to(torch.bfloat16).contiguous()
+
+
+def _interior(rows, B, H, W):
+    return rows.float().view(B, H + 2, W + 2, -1)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("B,H,cin,cout,block_n", [(3, 14, 64, 64, 0), (2, 28, 128, 128, 0), (5, 7, 512, 512, 0),
+                                                   (9, 14, 256, 256, 2256), (2, 14, 64, 96, 64)])
+def test_gemm_conv3x3_implicit(cuda_device, B, H, cin, cout, block_n):
+    """hoigen_gemm_params.conv_taps = 9: the 3x3 / stride 1 / pad 1 convolution of the ResNet-50 branch (a8) as nine
+    accumulated products of row-shifted views of the haloed NHWC matrix, bias + ReLU + halo zeroing in the epilogue.
+    Against torch conv2d in fp32 on the same bf16-rounded operands (accumulation order differs: <= 2e-2 relative to the
+    output scale before the bf16 store) and against the SIMT form of the same contract."""
+    from hoigen_b200 import _cabi
+    torch.manual_seed(B * 100 + H)
+    x = torch.randn(B, cin, H, H, device=cuda_device)
+    w = torch.randn(cout, cin, 3, 3, device=cuda_device) / (3 * cin ** 0.5)
+    bias = torch.randn(cout, device=cuda_device) * 0.1
+    rows = _haloed(x)
+    wk = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(torch.bfloat16).contiguous()
+    out = torch.full((rows.shape[0], cout), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.gemm_bf16(rows, wk, bias=bias, act=_cabi.ACT_RELU, out_bf16=out, conv_taps=9, halo=(H + 2, H + 2), block_n=block_n)
+    ref = torch.relu(torch.nn.functional.conv2d(_interior(rows, B, H, H), wk.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2),
+                                                bias, padding=1))
+    got = _interior(out, B, H, H)
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err
+    ring = out.float().view(B, H + 2, H + 2, cout)
+    assert ring[:, 0].abs().max() == 0 and ring[:, -1].abs().max() == 0 and ring[:, :, 0].abs().max() == 0 and ring[:, :, -1].abs().max() == 0
+    simt = torch.empty_like(out)
+    _cabi.gemm_bf16(rows, wk, bias=bias, act=_cabi.ACT_RELU, out_bf16=simt, conv_taps=9, halo=(H + 2, H + 2), simt=True)
+    assert (out.float() - simt.float()).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_conv1x1_identity_epilogue(cuda_device):
+    """1x1 convolution = plain GEMM over the haloed rows with the Bottleneck epilogue: relu(acc + bias + identity) with a
+    bf16 identity added BEFORE the activation, halo rows written as zero (pair and one-CTA kernels)."""
+    from hoigen_b200 import _cabi
+    torch.manual_seed(5)
+    B, H, cin, cout = 4, 14, 256, 1024
+    x = torch.randn(B, cin, H, H, device=cuda_device)
+    rows = _haloed(x)
+    w = (torch.randn(cout, cin, device=cuda_device) / cin ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, device=cuda_device) * 0.1
+    ident = (torch.randn(rows.shape[0], cout, device=cuda_device)).to(torch.bfloat16)
+    ref = torch.relu(rows.float() @ w.float().t() + bias + ident.float())
+    mask = torch.zeros(B, H + 2, H + 2, dtype=torch.bool, device=cuda_device)
+    mask[:, 1:-1, 1:-1] = True
+    ref = ref * mask.view(-1, 1)
+    for bn in (0, 2256, 128):
+        out = torch.full((rows.shape[0], cout), 7.0, device=cuda_device, dtype=torch.bfloat16)
+        _cabi.gemm_bf16(rows, w, bias=bias, act=_cabi.ACT_RELU, out_bf16=out, halo=(H + 2, H + 2), res_bf16=ident, block_n=bn)
+        err = (out.float() - ref).abs().max().item()
+        assert err <= 2e-2 * ref.abs().max().item(), (bn, err)
+
+
+def test_conv_row_kernels(cuda_device):
+    """The four row kernels of the ResNet-50 branch against torch: stem im2col (7x7 / s2 / p3 as a GEMM operand), max-pool
+    3x3 / s2 / p1 into the haloed layout, the stride-2 gathers (3x3 and 1x1) and average-pool + L2 norm."""
+    from hoigen_b200 import _cabi
+    import ctypes as C
+    torch.manual_seed(6)
+    lib = _cabi.init(cuda_device)
+    B = 3
+    # stem: im2col rows @ packed weights == conv2d(stride 2, pad 3)
+    img = torch.randn(B, 3, 224, 224, device=cuda_device)
+    rows = torch.empty(B * 112 * 112, 160, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.check(lib.hoigen_stem_im2col(_cabi.ptr(img), _cabi.ptr(rows), B, _cabi.stream_ptr()), "stem_im2col")
+    w = torch.randn(64, 3, 7, 7, device=cuda_device) * 0.05
+    wk = torch.nn.functional.pad(w.permute(0, 2, 3, 1).reshape(64, 147), (0, 13))
+    got = (rows.float() @ wk.t()).view(B, 112, 112, 64).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(img.to(torch.bfloat16).float(), w, stride=2, padding=3)
+    assert (got - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+    assert rows[:, 147:].abs().max() == 0
+    # max-pool
+    a = torch.randn(B, 64, 112, 112, device=cuda_device).to(torch.bfloat16)
+    a_rows = a.permute(0, 2, 3, 1).contiguous()
+    pooled = torch.full((B * 58 * 58, 64), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.check(lib.hoigen_maxpool3x3s2_halo(_cabi.ptr(a_rows), _cabi.ptr(pooled), B, 112, 112, 64, _cabi.stream_ptr()), "maxpool")
+    ref = torch.nn.functional.max_pool2d(a.float(), 3, 2, 1)
+    assert torch.equal(_interior(pooled, B, 56, 56), ref)
+    assert pooled.view(B, 58, 58, 64)[:, 0].abs().max() == 0 and pooled.view(B, 58, 58, 64)[:, :, -1].abs().max() == 0
+    # stride-2 gathers
+    x = torch.randn(B, 128, 28, 28, device=cuda_device)
+    xr = _haloed(x)
+    g9 = torch.full((B * 16 * 16, 9 * 128), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.check(lib.hoigen_conv_gather_s2(_cabi.ptr(xr), _cabi.ptr(g9), B, 28, 28, 128, 9, _cabi.stream_ptr()), "gather9")
+    w3 = torch.randn(32, 128, 3, 3, device=cuda_device) * 0.05
+    got = _interior(g9.float() @ w3.permute(0, 2, 3, 1).reshape(32, -1).t(), B, 14, 14)
+    ref = torch.nn.functional.conv2d(_interior(xr, B, 28, 28), w3, stride=2, padding=1)
+    assert (got - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+    g1 = torch.full((B * 16 * 16, 128), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.check(lib.hoigen_conv_gather_s2(_cabi.ptr(xr), _cabi.ptr(g1), B, 28, 28, 128, 1, _cabi.stream_ptr()), "gather1")
+    assert torch.equal(_interior(g1, B, 14, 14), _interior(xr, B, 28, 28)[:, :, ::2, ::2])
+    assert g1.view(B, 16, 16, 128)[:, 0].abs().max() == 0
+    # average-pool + L2 norm
+    y = torch.randn(B, 2048, 7, 7, device=cuda_device)
+    yr = _haloed(y)
+    feat = torch.empty(B, 2048, device=cuda_device)
+    _cabi.check(lib.hoigen_avgpool_l2norm(_cabi.ptr(yr), _cabi.ptr(feat), B, 7, 7, 2048, _cabi.stream_ptr()), "avgpool")
+    ref = _interior(yr, B, 7, 7).mean(dim=(2, 3))
+    ref = ref / ref.norm(dim=-1, keepdim=True)
+    assert (feat - ref).abs().max().item() <= 1e-6
