@@ -37,7 +37,7 @@ class GemmParams(C.Structure):
     ]
 
 
-CONV_OP_GEMM, CONV_OP_STEM_IM2COL, CONV_OP_MAXPOOL, CONV_OP_GATHER_S2, CONV_OP_AVGPOOL_L2NORM = range(5)
+CONV_OP_GEMM, CONV_OP_STEM_IM2COL, CONV_OP_MAXPOOL, CONV_OP_GATHER_S2, CONV_OP_AVGPOOL_L2NORM, CONV_OP_STEM_CONV = range(6)
 
 
 class ConvOp(C.Structure):
@@ -213,6 +213,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_score_pairs_folded": [C.POINTER(FoldedWeights), C.POINTER(ScoreBuffers), _P, _P, _P, _I, _I, _P],
     "hoigen_ap_11point": [_P, _P, _P, _P, _I, _P, _P, _P],
     "hoigen_stem_im2col": [_P, _P, _I, _P],
+    "hoigen_stem_conv": [_P, _P, _P, _P, _I, _P],
     "hoigen_maxpool3x3s2_halo": [_P, _P, _I, _I, _I, _I, _P],
     "hoigen_conv_gather_s2": [_P, _P, _I, _I, _I, _I, _I, _P],
     "hoigen_avgpool_l2norm": [_P, _P, _I, _I, _I, _I, _P],

@@ -18,35 +18,39 @@ namespace hoigen {
 constexpr int STEM_K = 160;   // 7 * 7 * 3 = 147 taps, zero-padded to a multiple of 8 (16-byte TMA rows)
 
 // images (B, 3, 224, 224) fp32 -> rows (B * 112 * 112, 160) bf16: row = output pixel (b, oy, ox) of the 7x7 / stride 2 /
-// pad 3 stem convolution, column k = (ky * 7 + kx) * 3 + c.  One thread per 8 columns.
-__global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ rows, int batch) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)batch * 112 * 112 * (STEM_K / 8);
-  if (gid >= total) return;
-  const int g8 = int(gid % (STEM_K / 8));
-  const long long pix = gid / (STEM_K / 8);
-  const int ox = int(pix % 112), oy = int((pix / 112) % 112), b = int(pix / (112 * 112));
+// pad 3 stem convolution, column k = (ky * 7 + kx) * 3 + c.  One CTA per (image, pair of output rows): the nine input rows
+// it needs are staged once in shared memory, channel-interleaved and zero-padded ([row][col -3 .. 226][c] bf16), so that the
+// 21 entries (kx, c) of one (pixel, ky) are CONTIGUOUS there; the threads then emit the output as coalesced 16-byte chunks.
+constexpr int STEM_SCOLS = 224 + 6;            // input columns -3 .. 226
+constexpr int STEM_SROW = STEM_SCOLS * 3;      // bf16 elements per staged row
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ rows) {
+  __shared__ __nv_bfloat16 s_in[9 * STEM_SROW];
+  const int b = blockIdx.y, oy0 = blockIdx.x * 2;
   const float* base = img + size_t(b) * 3 * 224 * 224;
-  uint32_t packed[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float v2[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k = g8 * 8 + e * 2 + h;
-      float v = 0.f;
-      if (k < 147) {
-        const int tap = k / 3, c = k - tap * 3;
-        const int ky = tap / 7, kx = tap - ky * 7;
-        const int iy = 2 * oy - 3 + ky, ix = 2 * ox - 3 + kx;
-        if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) v = __ldg(base + (size_t(c) * 224 + iy) * 224 + ix);
-      }
-      v2[h] = v;
-    }
-    const __nv_bfloat162 p = __floats2bfloat162_rn(v2[0], v2[1]);
-    packed[e] = *reinterpret_cast<const uint32_t*>(&p);
+  // stage input rows 2 oy0 - 3 .. 2 oy0 + 5 (coalesced 4-byte reads along x; rows / columns outside the image are zero)
+  for (int i = threadIdx.x; i < 9 * 3 * STEM_SCOLS; i += 256) {
+    const int col = i % STEM_SCOLS, rc = i / STEM_SCOLS;
+    const int c = rc % 3, r = rc / 3;
+    const int iy = 2 * oy0 - 3 + r, ix = col - 3;
+    float v = 0.f;
+    if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) v = __ldg(base + (size_t(c) * 224 + iy) * 224 + ix);
+    s_in[r * STEM_SROW + col * 3 + c] = __float2bfloat16_rn(v);
   }
-  *reinterpret_cast<uint4*>(rows + pix * STEM_K + g8 * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  __syncthreads();
+  __nv_bfloat16* out = rows + (size_t(b) * 112 + oy0) * 112 * STEM_K;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  for (int i = threadIdx.x; i < 2 * 112 * (STEM_K / 8); i += 256) {
+    const int g8 = i % (STEM_K / 8), pix = i / (STEM_K / 8);
+    const int ox = pix % 112, dy = pix / 112;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = g8 * 8 + e;
+      const int ky = k / 21, r = k - ky * 21;
+      v[e] = k < 147 ? s_in[(2 * dy + ky) * STEM_SROW + 6 * ox + r] : zero;
+    }
+    *reinterpret_cast<uint4*>(out + size_t(pix) * STEM_K + g8 * 8) = *reinterpret_cast<const uint4*>(v);
+  }
 }
 
 __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
@@ -164,9 +168,8 @@ using namespace hoigen;
 int hoigen_stem_im2col(const float* images, void* rows_bf16, int32_t batch, hoigen_stream_t stream) {
   HOIGEN_CHECK_ARG(images && rows_bf16 && batch > 0, "stem_im2col: bad arguments");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const long long total = (long long)batch * 112 * 112 * (STEM_K / 8);
   KernelScope ks("stem_im2col", s, 0, double(batch) * (3.0 * 224 * 224 * 4 + 112.0 * 112 * STEM_K * 2));
-  stem_im2col_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(images, reinterpret_cast<__nv_bfloat16*>(rows_bf16), batch);
+  stem_im2col_kernel<<<dim3(56, batch), 256, 0, s>>>(images, reinterpret_cast<__nv_bfloat16*>(rows_bf16));
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
@@ -216,6 +219,9 @@ int hoigen_conv_plan_run(const hoigen_conv_op* ops, int32_t n_ops, hoigen_stream
     switch (o.kind) {
       case HOIGEN_CONV_OP_GEMM: rc = hoigen_gemm_bf16(&o.gemm, stream); break;
       case HOIGEN_CONV_OP_STEM_IM2COL: rc = hoigen_stem_im2col(reinterpret_cast<const float*>(o.in), o.out, o.batch, stream); break;
+      case HOIGEN_CONV_OP_STEM_CONV:
+        rc = hoigen_stem_conv(reinterpret_cast<const float*>(o.in), o.gemm.w, o.gemm.bias, o.out, o.batch, stream);
+        break;
       case HOIGEN_CONV_OP_MAXPOOL: rc = hoigen_maxpool3x3s2_halo(o.in, o.out, o.batch, o.h, o.w, o.c, stream); break;
       case HOIGEN_CONV_OP_GATHER_S2: rc = hoigen_conv_gather_s2(o.in, o.out, o.batch, o.h, o.w, o.c, o.taps, stream); break;
       case HOIGEN_CONV_OP_AVGPOOL_L2NORM:

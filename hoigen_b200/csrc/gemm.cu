@@ -139,10 +139,11 @@ __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const 
                                                        bool res_vec, const float* res_row, const float* s_bias,
                                                        const float* s_cs, int row, bool row_ok, int col0,
                                                        uint8_t* out_tile = nullptr, int rrow = 0, int tile_col = 0,
-                                                       float ln_mean = 0.f, float ln_rstd = 1.f, bool halo = false) {
+                                                       float ln_mean = 0.f, float ln_rstd = 1.f, bool halo = false,
+                                                       const uint4* resb = nullptr /* prefetched bf16 identity, 2 x uint4 */) {
   const bool full_chunk = (col0 + CW <= g.N);
-  // EPI >= 0: the epilogue recipe is a compile-time constant (act | colscale << 4 | bias << 5 | layernorm << 6), no work
-  // for absent terms
+  // EPI >= 0: the epilogue recipe is a compile-time constant (act | colscale << 4 | bias << 5 | layernorm << 6 |
+  // bf16 identity << 7 | halo zeroing << 8), no work for absent terms
   const int act = EPI >= 0 ? (EPI & 15) : g.act;
   const bool has_ln = EPI >= 0 ? ((EPI >> 6) & 1) != 0 : (g.ln_stats != nullptr);
   const bool has_cs = (EPI >= 0 ? ((EPI >> 4) & 1) != 0 : true) && !has_ln;
@@ -169,12 +170,27 @@ __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const 
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
-  if (EPI < 0 && g.res_bf16 != nullptr && row_ok) {   // Bottleneck identity: added before the activation
+  const bool has_resb = EPI >= 0 ? ((EPI >> 7) & 1) != 0 : (g.res_bf16 != nullptr);
+  if (EPI >= 0 && has_resb && out_tile != nullptr) {
+    // identity tile already in the staging buffer (TMA-loaded, same swizzled slots this thread is about to overwrite)
+    const uint8_t* panel = out_tile + (tile_col >> 6) * 16384;
+    const uint32_t ch = uint32_t(tile_col & 63) >> 3;
+#pragma unroll
+    for (int h = 0; h < CW / 8; ++h) {
+      const uint4 q = *reinterpret_cast<const uint4*>(panel + sw128_offset(rrow, ch + h));
+      const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[8 * h + 2 * e] += __uint_as_float(w4[e] << 16);
+        v[8 * h + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+      }
+    }
+  } else if (has_resb && row_ok) {   // Bottleneck identity: added before the activation
     const __nv_bfloat16* rp = g.res_bf16 + size_t(row) * g.ld_resb + col0;
     if (full_chunk && (g.ld_resb & 7) == 0) {
 #pragma unroll
       for (int h = 0; h < CW / 8; ++h) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp) + h);
+        const uint4 q = resb ? resb[h] : __ldg(reinterpret_cast<const uint4*>(rp) + h);
         const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -192,7 +208,7 @@ __device__ __forceinline__ void epilogue_process_chunk(const GemmArgs& g, const 
 #pragma unroll
     for (int j = 0; j < CW; ++j) v[j] = apply_act(v[j], act, g.act_param);
   }
-  if (EPI < 0 && halo) {
+  if ((EPI < 0 || ((EPI >> 8) & 1) != 0) && halo) {
 #pragma unroll
     for (int j = 0; j < CW; ++j) v[j] = 0.f;
   }
@@ -273,7 +289,16 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
     const float2 st = __ldg(g.ln_stats + row);
     ln_mean = st.x; ln_rstd = st.y;
   }
-  const bool halo = EPI < 0 && halo_row(g, row);
+  const bool halo = (EPI < 0 || ((EPI >> 8) & 1) != 0) && halo_row(g, row);
+  // bf16 identity of the convolution epilogues: chunk c + 1's 32 bytes are fetched while chunk c is processed
+  // (compile-time recipes of the TMA-store kernels get the identity tile by TMA into the staging buffer instead: see RES_TMA)
+  const bool resb_vec = (EPI >= 0 ? (((EPI >> 7) & 1) != 0 && out_tile == nullptr) : g.res_bf16 != nullptr) && row_ok && (g.ld_resb & 7) == 0;
+  const __nv_bfloat16* resb_row = resb_vec ? g.res_bf16 + size_t(row) * g.ld_resb : nullptr;
+  uint4 resb[2][CW / 8];
+  if (resb_vec && colbase + CW <= g.N) {
+#pragma unroll
+    for (int h = 0; h < CW / 8; ++h) resb[0][h] = __ldg(reinterpret_cast<const uint4*>(resb_row + colbase) + h);
+  }
   if (res_vec && colbase + CW <= g.N) {
 #pragma unroll
     for (int j = 0; j < CW / 4; ++j) res[0][j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
@@ -293,6 +318,10 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
         for (int j = 0; j < CW / 4; ++j)
           res[(c + 1) & 1][j] = *reinterpret_cast<const float4*>(res_row + col0 + CW + 4 * j);
       }
+      if (resb_vec && col0 + 2 * CW <= g.N) {
+#pragma unroll
+        for (int h = 0; h < CW / 8; ++h) resb[(c + 1) & 1][h] = __ldg(reinterpret_cast<const uint4*>(resb_row + col0 + CW) + h);
+      }
     }
     if (n_parts > 0) {   // stream-K fix-up: add the other pairs' partial accumulators of this tile (fixed order)
       const float* pp = part + size_t(c) * (BM * CW);
@@ -307,7 +336,8 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
       }
     }
     epilogue_process_chunk<EPI>(g, r[c & 1], res[c & 1], res_vec, res_row, s_bias + c * CW, s_cs + c * CW, row, row_ok, col0,
-                           out_tile, rrow, tile_col0 + c * CW, ln_mean, ln_rstd, halo);
+                           out_tile, rrow, tile_col0 + c * CW, ln_mean, ln_rstd, halo,
+                           (resb_vec && col0 + CW <= g.N) ? resb[c & 1] : nullptr);
     if (!more) break;
   }
   tmem_wait_ld();
@@ -623,7 +653,9 @@ struct Gemm2Cfg {
 template <int BN, bool TMA_OUT, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmC, GemmArgs g) {
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmArgs g) {
+  // convolution recipe with a bf16 identity: its tile is TMA-loaded into the output staging buffer and updated in place
+  constexpr bool RES_TMA = TMA_OUT && EPI >= 0 && ((EPI >> 7) & 1) != 0;
   using Cfg = Gemm2Cfg<BN, TMA_OUT>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -636,6 +668,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t bar_empty = bar_full + 8u * STAGES;
   const uint32_t bar_tfull = bar_full + 16u * STAGES;
   const uint32_t bar_tempty = bar_tfull + 16u;
+  const uint32_t bar_res = bar_full + 208u;   // identity tile landed in the staging buffer (RES_TMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -666,6 +699,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(bar_tfull + 8u * a, 1);
       mbar_init(bar_tempty + 8u * a, 16);
     }
+    if (RES_TMA) mbar_init(bar_res, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -746,6 +780,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // this thread's row inside the warp's first chunk of a slot
     const size_t slot_off = (size_t(half * (BN / 2) / CW) * BM + rrow) * CW;
     int it = 0;
+    int res_it = 0;   // identity tiles loaded so far (bar_res phase)
     PairWork work = work0;
     for (int tile, kb0, kb1; work.next(tile, kb0, kb1); ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -783,10 +818,24 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int colbase = n_blk * BN + half * (BN / 2);
       float* s_bias = reinterpret_cast<float*>(tiles + Cfg::BAR_OFF + 256) + (it & 1) * 2 * BN;
       float* s_cs = s_bias + BN;
-      if (TMA_OUT && threadIdx.x == 64) tma_store_wait_read();   // previous tile's TMA stores have drained the staging tile
+      if (TMA_OUT && threadIdx.x == 64) {
+        tma_store_wait_read();   // previous tile's TMA stores have drained the staging tile
+        if (RES_TMA) {
+          const int row0 = m_blk * (2 * BM) + int(rank) * BM;
+          int panels = 0;
+#pragma unroll
+          for (int pnl = 0; pnl < BN / 64; ++pnl) panels += (n_blk * BN + pnl * 64 < g.N) ? 1 : 0;
+          mbar_arrive_expect_tx(bar_res, uint32_t(panels) * 16384u);
+#pragma unroll
+          for (int pnl = 0; pnl < BN / 64; ++pnl)
+            if (n_blk * BN + pnl * 64 < g.N)
+              tma_load_2d(smem_u32(out_stage) + pnl * 16384, &tmR, bar_res, n_blk * BN + pnl * 64, row0);
+        }
+      }
       epilogue_stage_vectors<BN>(g, n_blk * BN, s_bias, s_cs, threadIdx.x - 64);   // (contains the epilogue-wide barrier)
       epilogue_warp<BN / 2, EPI>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
         mbar_wait(bar_tfull + 8u * acc, acc_phase);
+        if (RES_TMA) mbar_wait(bar_res, uint32_t(res_it) & 1u);
         tc_fence_after();
       }, TMA_OUT ? out_stage : nullptr, rrow, half * (BN / 2),
       n_parts ? g.sk_ws + (size_t(cluster_id + 1) * 2 + rank) * SLOT + slot_off : nullptr,
@@ -809,6 +858,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (n_parts && threadIdx.x == 64)   // every epilogue thread is past its slot reads: re-arm the flags
         for (int q = 1; q <= n_parts; ++q) g.sk_flags[(cluster_id + q) * 2 + int(rank)] = 0;
+      ++res_it;
     }
     if (TMA_OUT && threadIdx.x == 64) tma_store_wait_all();
   }
@@ -1001,7 +1051,12 @@ static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream, b
   cfg.numAttrs = 1;
   KernelScope ks(gemm_tag(p->N, p->K, 2), stream, 2.0 * p->M * p->N * p->K,
                  2.0 * (double(p->M) * p->K + double(p->N) * p->K) + double(p->M) * p->N * ((p->out_f32 ? 4 : 0) + (p->out_bf16 ? 2 : 0) + (p->residual ? 4 : 0)));
-  HOIGEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, TMA_OUT, EPI>, *ta, *tb, *tc, args));
+  const CUtensorMap* tr = tc;   // identity tiles (RES_TMA recipes only)
+  if (TMA_OUT && EPI >= 0 && ((EPI >> 7) & 1) != 0) {
+    tr = get_tmap_2d_bf16(p->res_bf16, uint64_t(p->N), uint64_t(p->M), uint64_t(p->ld_resb) * 2, 64, BM);
+    if (!tr) return HOIGEN_ERR_CUDA;
+  }
+  HOIGEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, TMA_OUT, EPI>, *ta, *tb, *tc, *tr, args));
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
@@ -1012,9 +1067,17 @@ static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream, bool f
   static const bool no_tma_out = getenv("HOIGEN_GEMM_NO_TMA_STORE") != nullptr;
   const bool tma_out = !no_tma_out && p->out_bf16 && !p->out_f32 && !p->residual && (p->ld_bf16 % 8) == 0 && (p->N % 8) == 0;
   if (!tma_out) return launch_gemm2_impl<BN, false, -1>(p, stream, force_split);
-  if (p->halo_w > 0 || p->res_bf16) return launch_gemm2_impl<BN, true, -1>(p, stream, force_split);   // convolution epilogues
+
   // compile-time epilogue recipes of the encoder's bf16-output GEMMs; anything else uses the runtime-flag epilogue
   const bool b = p->bias != nullptr, c = p->colscale != nullptr;
+  if (p->halo_w > 0 || p->res_bf16) {   // convolution epilogues of the ResNet-50 branch (bias folded from the BatchNorm)
+    constexpr int HALO = 1 << 8, RESB = 1 << 7, BIAS = 1 << 5;
+    const bool plain = b && !p->colscale && !p->ln_stats && p->halo_w > 0;
+    if (plain && !p->res_bf16 && p->act == HOIGEN_ACT_RELU) return launch_gemm2_impl<BN, true, HALO | BIAS | HOIGEN_ACT_RELU>(p, stream, force_split);
+    if (plain && !p->res_bf16 && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, HALO | BIAS>(p, stream, force_split);
+    if (plain && p->res_bf16 && p->act == HOIGEN_ACT_RELU && (p->ld_resb % 8) == 0 && (reinterpret_cast<uintptr_t>(p->res_bf16) & 15) == 0) return launch_gemm2_impl<BN, true, HALO | RESB | BIAS | HOIGEN_ACT_RELU>(p, stream, force_split);
+    return launch_gemm2_impl<BN, true, -1>(p, stream, force_split);
+  }
   if (p->ln_stats) {   // LayerNorm-folded QKV / c_fc
     if (b && p->act == HOIGEN_ACT_NONE) return launch_gemm2_impl<BN, true, (1 << 6) | (1 << 5)>(p, stream, force_split);
     if (b && p->act == HOIGEN_ACT_QUICKGELU) return launch_gemm2_impl<BN, true, (1 << 6) | (1 << 5) | HOIGEN_ACT_QUICKGELU>(p, stream, force_split);

@@ -127,7 +127,13 @@ class KernelDinoR50(nn.Module):
             self._keep += [wk, b]
             return wk, b
 
-        self.stem = pack(m.conv1)
+        self.stem = pack(m.conv1)                      # (64, 160): the two-step form (im2col + GEMM), kept for tests / A-B
+        w7 = m.conv1.weight.detach().float()           # (64, 3, 7, 7) -> (64, 192): column = ky * 24 + kx * 3 + c
+        w_runs = torch.zeros(64, 7, 24, device=dev)
+        w_runs[:, :, :21] = w7.permute(0, 2, 3, 1).reshape(64, 7, 21)
+        self.stem_fused = (torch.nn.functional.pad(w_runs.reshape(64, 168), (0, 24)).to(torch.bfloat16).contiguous(), self.stem[1])
+        self._keep.append(self.stem_fused[0])
+        self.fused_stem = True
         self.stages = []
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             blocks = []
@@ -153,8 +159,12 @@ class KernelDinoR50(nn.Module):
         def gemm(a, wb, out, *, relu, halo=None, taps=0, res=None):
             op = _cabi.ConvOp()
             op.kind = _cabi.CONV_OP_GEMM
+            n_out = wb[0].shape[0]
+            # CTA-pair tiles with the TMA-store epilogue whenever the output is wide enough (the tile chooser's cost model
+            # is tuned for K >= 768; these products are short-K and store-bound)
+            bn = 2256 if n_out >= 256 else (2128 if (n_out >= 128 or a.shape[1] != self.STEM_K) else 0)
             op.gemm = _cabi.gemm_params(a, wb[0], bias=wb[1], act=_cabi.ACT_RELU if relu else _cabi.ACT_NONE, out_bf16=out,
-                                        conv_taps=taps, halo=halo, res_bf16=res)
+                                        conv_taps=taps, halo=halo, res_bf16=res, block_n=bn)
             ops.append(op)
 
         def rowop(kind, src, dst, h=0, w=0, c=0, taps=0):
@@ -163,10 +173,16 @@ class KernelDinoR50(nn.Module):
             op.batch, op.h, op.w, op.c, op.taps = B, h, w, c, taps
             ops.append(op)
 
-        stem_rows = new(B * 112 * 112, self.STEM_K)
         stem_out = new(B * 112 * 112, 64)
-        rowop(_cabi.CONV_OP_STEM_IM2COL, None, stem_rows)
-        gemm(stem_rows, self.stem, stem_out, relu=True)
+        if self.fused_stem:
+            op = _cabi.ConvOp()
+            op.kind, op.out, op.batch = _cabi.CONV_OP_STEM_CONV, stem_out.data_ptr(), B
+            op.gemm.w, op.gemm.bias = self.stem_fused[0].data_ptr(), self.stem_fused[1].data_ptr()
+            ops.append(op)
+        else:
+            stem_rows = new(B * 112 * 112, self.STEM_K)
+            rowop(_cabi.CONV_OP_STEM_IM2COL, None, stem_rows)
+            gemm(stem_rows, self.stem, stem_out, relu=True)
         H = 56
         x = new(B * (H + 2) * (H + 2), 64)
         rowop(_cabi.CONV_OP_MAXPOOL, stem_out, x, 112, 112, 64)

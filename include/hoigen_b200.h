@@ -455,6 +455,11 @@ HOIGEN_API int hoigen_prepare_proposals(const float* scores, const int64_t* labe
 /* images (B,3,224,224) fp32 -> rows (B*112*112, 160) bf16: im2col of conv1 (7x7, stride 2, pad 3), column = (ky*7+kx)*3+c,
  * columns 147..159 zero. */
 HOIGEN_API int hoigen_stem_im2col(const float* images, void* rows_bf16, int32_t batch, hoigen_stream_t stream);
+/* The same convolution fused with its BatchNorm-folded bias and ReLU as ONE tensor-core kernel without the im2col matrix:
+ * images (B,3,224,224) fp32 -> out (B*112*112, 64) bf16 NHWC rows.  w: bf16 (64, 192), column = ky*24 + kx*3 + c (each
+ * ky run of 21 taps padded to 24, 168..191 zero); bias (64) fp32. */
+HOIGEN_API int hoigen_stem_conv(const float* images, const void* w_bf16, const float* bias, void* out_bf16, int32_t batch,
+                                hoigen_stream_t stream);
 /* MaxPool2d(3, stride 2, padding 1): in (B,h,w,c) bf16 without halo -> out (B, h/2+2, w/2+2, c) with the zero halo */
 HOIGEN_API int hoigen_maxpool3x3s2_halo(const void* in_bf16, void* out_bf16, int32_t batch, int32_t h, int32_t w, int32_t c,
                                         hoigen_stream_t stream);
@@ -471,7 +476,8 @@ typedef enum {
   HOIGEN_CONV_OP_STEM_IM2COL = 1,     /* in = images, out = rows, batch          */
   HOIGEN_CONV_OP_MAXPOOL = 2,         /* in, out, batch, h, w, c                 */
   HOIGEN_CONV_OP_GATHER_S2 = 3,       /* in, out, batch, h, w, c, taps           */
-  HOIGEN_CONV_OP_AVGPOOL_L2NORM = 4   /* in, out (fp32), batch, h, w, c          */
+  HOIGEN_CONV_OP_AVGPOOL_L2NORM = 4,  /* in, out (fp32), batch, h, w, c          */
+  HOIGEN_CONV_OP_STEM_CONV = 5        /* in = images, out, batch, gemm.w, gemm.bias */
 } hoigen_conv_op_kind;
 typedef struct {
   int32_t kind;

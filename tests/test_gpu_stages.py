@@ -671,7 +671,7 @@ def test_gemm_conv1x1_identity_epilogue(cuda_device):
     mask = torch.zeros(B, H + 2, H + 2, dtype=torch.bool, device=cuda_device)
     mask[:, 1:-1, 1:-1] = True
     ref = ref * mask.view(-1, 1)
-    for bn in (0, 2256, 128):
+    for bn in (0, 2256, 2192, 2128, 128):
         out = torch.full((rows.shape[0], cout), 7.0, device=cuda_device, dtype=torch.bfloat16)
         _cabi.gemm_bf16(rows, w, bias=bias, act=_cabi.ACT_RELU, out_bf16=out, halo=(H + 2, H + 2), res_bf16=ident, block_n=bn)
         err = (out.float() - ref).abs().max().item()
@@ -696,6 +696,18 @@ def test_conv_row_kernels(cuda_device):
     ref = torch.nn.functional.conv2d(img.to(torch.bfloat16).float(), w, stride=2, padding=3)
     assert (got - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
     assert rows[:, 147:].abs().max() == 0
+    # the fused stem kernel: convolution + bias + ReLU without the im2col matrix (weights packed in 24-wide ky runs)
+    bias = torch.randn(64, device=cuda_device) * 0.1
+    w_runs = torch.zeros(64, 7, 24, device=cuda_device)
+    w_runs[:, :, :21] = w.permute(0, 2, 3, 1).reshape(64, 7, 21)
+    w_fused = torch.nn.functional.pad(w_runs.reshape(64, 168), (0, 24)).to(torch.bfloat16).contiguous()
+    for nb in (B, 1):
+        fused = torch.full((nb * 112 * 112, 64), 7.0, device=cuda_device, dtype=torch.bfloat16)
+        _cabi.check(lib.hoigen_stem_conv(_cabi.ptr(img[:nb].contiguous()), _cabi.ptr(w_fused), _cabi.ptr(bias), _cabi.ptr(fused), nb,
+                                         _cabi.stream_ptr()), "stem_conv")
+        ref_f = torch.relu(torch.nn.functional.conv2d(img[:nb].to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, stride=2, padding=3))
+        got_f = fused.float().view(nb, 112, 112, 64).permute(0, 3, 1, 2)
+        assert (got_f - ref_f).abs().max().item() <= 1e-2 * max(1.0, ref_f.abs().max().item()), (got_f - ref_f).abs().max().item()
     # max-pool
     a = torch.randn(B, 64, 112, 112, device=cuda_device).to(torch.bfloat16)
     a_rows = a.permute(0, 2, 3, 1).contiguous()

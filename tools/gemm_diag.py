@@ -5,7 +5,8 @@ if len(sys.argv) > 1:
     import torch
     from hoigen_b200 import _cabi
     dev = torch.device("cuda:0")
-    for (M, N, K, bn) in [(12608, 3072, 768, 2256), (12608, 768, 3072, 2256), (12608, 2304, 768, 2256), (12608, 768, 768, 2256)]:
+    shapes = [(215296, 256, 64, 2256), (16384, 1024, 256, 2256)] if os.environ.get('CONV_SHAPES') else [(12608, 3072, 768, 2256), (12608, 768, 3072, 2256), (12608, 2304, 768, 2256), (12608, 768, 768, 2256)]
+    for (M, N, K, bn) in shapes:
         a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16()
         o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         for _ in range(3): _cabi.gemm_bf16(a, w, out_bf16=o, block_n=bn)
