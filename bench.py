@@ -20,7 +20,8 @@ rows, 4 = V-COCO 24 actions, batch 128, 16h+16o boxes (496 pairs), 5 = 600-tripl
                       oracle/_ref (`kind: "reference"`), else the oracle port (`kind: "port"`)
   gpu_torch_baseline  the UNMODIFIED reference on the same B200, same inputs: fp32 as shipped and under
                       torch.autocast(bf16) (BASELINE configs[1] "vs reference torch path on the same GPU inputs")
-  full_with_dino_r50  the step with the stock torchvision ResNet-50 DINO branch (U:1616-1618) run per step on a side stream
+  full_with_dino_r50  the step with the ResNet-50 DINO branch (U:1616-1618) run per step by the module: stock fp32 torchvision,
+                      the cuDNN bf16 graph, and this repo's own convolution kernels (UPT.accelerate_dino)
 
 `--impl reference` times the reference's CPU implementation of the path with all host threads on the same workload;
 `--impl reference-gpu` is the same-GPU torch comparator as a stand-alone run (what gpu_torch_baseline spawns).
@@ -153,6 +154,24 @@ class ClockSampler:
             except Exception:
                 pass
             time.sleep(self.period)
+
+    def sample_now(self):
+        """One synchronous NVML sample on the calling thread (the queued GPU work is still running): the 20-step window is
+        only ~75 ms long and the sampling thread can be starved of the GIL by the launch loop."""
+        if self.source != "nvml" or not self.active:
+            return
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            self.power.append(float(nv.nvmlDeviceGetPowerUsage(self.h)) / 1e3)
+            bits = int(get_reasons(self.h))
+            for name, _attr, bit in self._REASONS:
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def _loop_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -561,6 +580,8 @@ def run_b200(args, rank, world, local_rank):
     _cabi.profile(False)
     clocks.active = True
     e0, e1, dets = timed_resident(args.warmup, args.steps)
+    if rank == 0:
+        clocks.sample_now()                      # the last steps are still running on the GPU
     barrier()
     clocks.active = False
     launches = _cabi.launch_count()
@@ -583,6 +604,8 @@ def run_b200(args, rank, world, local_rank):
         n_sus = max(args.steps, int(math.ceil(args.sustain_s * 1e3 / ms_step)))
         clocks.active = True
         s0, s1, _ = timed_resident(0, n_sus)
+        if rank == 0:
+            clocks.sample_now()
         barrier()
         clocks.active = False
         sus_ms = max_over_ranks(s0.elapsed_time(s1) / n_sus)
@@ -657,11 +680,18 @@ def run_b200(args, rank, world, local_rank):
             fms = quick_resident(args.steps)
             full_dino["stock_fp32"] = {"ms_per_step": fms, "value": B / (fms * 1e-3), "unit": UNIT,
                                        "note": "the injected module exactly as the reference runs it (fp32, eager)"}
-            model.accelerate_dino()
+            model.accelerate_dino(engine="cudnn")
             fms = quick_resident(args.steps)
-            full_dino["accelerate_dino"] = {"ms_per_step": fms, "value": B / (fms * 1e-3), "unit": UNIT,
-                                            "note": "UPT.accelerate_dino(): BatchNorms folded, bf16 channels-last, one CUDA graph per batch "
-                                                    "size and stream (hoigen_b200/dino.py); opt-in, bf16-accurate features"}
+            full_dino["accelerate_dino_cudnn"] = {"ms_per_step": fms, "value": B / (fms * 1e-3), "unit": UNIT,
+                                                  "note": "UPT.accelerate_dino(engine='cudnn'): BatchNorms folded, bf16 channels-last, one CUDA "
+                                                          "graph per batch size and stream (library tuning; bf16-accurate features)"}
+            model.accelerate_dino(engine="kernels")
+            fms = quick_resident(args.steps)
+            full_dino["accelerate_dino_kernels"] = {"ms_per_step": fms, "value": B / (fms * 1e-3), "unit": UNIT,
+                                                    "note": "UPT.accelerate_dino(engine='kernels'): the branch on this repo's own kernels -- every "
+                                                            "convolution on the tcgen05 GEMM (3x3 as an implicit GEMM over haloed NHWC rows), fused "
+                                                            "tensor-core stem, one C call per batch (hoigen_b200/dino.py KernelDinoR50; opt-in, "
+                                                            "bf16-accurate features)"}
         except Exception as e:
             full_dino = dict(full_dino or {}, unavailable=f"{type(e).__name__}: {e}"[:300])
         dino_state["inline"] = False
