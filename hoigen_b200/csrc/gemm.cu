@@ -28,6 +28,24 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int GEMM2_THREADS = 352; // CTA-pair kernel: + warp 10 = output DMA (TMA stores / identity loads of the staging panels)
+
+// Hand-over of the 64-column staging panels between the epilogue warps and the DMA warp of the CTA-pair kernel:
+// ready[p] completes once per tile when panel p may be written (its previous TMA store has been read out, and -- identity
+// recipes -- the identity tile has landed in it); written[p] when every thread that writes panel p has done so.
+struct PanelSync {
+  uint32_t ready, written;   // smem addresses of the two barrier arrays (8 bytes per panel); 0 = no staging (no-op)
+  uint32_t phase;
+  __device__ __forceinline__ void enter(int p) const {
+    if (ready) mbar_wait(ready + 8u * p, phase);
+  }
+  __device__ __forceinline__ void leave(int p) const {
+    if (ready) {
+      fence_proxy_async_smem();          // this thread's staging writes -> visible to the TMA engine
+      mbar_arrive(written + 8u * p);
+    }
+  }
+};
 
 struct GemmArgs {
   int M, N, K;
@@ -277,7 +295,7 @@ template <int COLS, int EPI, typename WaitFn>
 __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int colbase, uint32_t t_addr, const float* s_bias,
                                               const float* s_cs, WaitFn wait_acc, uint8_t* out_tile = nullptr, int rrow = 0,
                                               int tile_col0 = 0, const float* part = nullptr, int n_parts = 0,
-                                              size_t part_stride = 0) {
+                                              size_t part_stride = 0, PanelSync ps = PanelSync{0, 0, 0}) {
   constexpr int CHUNKS = COLS / CW;
   const bool row_ok = row < g.M;
   const bool res_vec = g.residual && row_ok && (g.ld_res & 3) == 0;
@@ -304,11 +322,23 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
     for (int j = 0; j < CW / 4; ++j) res[0][j] = *reinterpret_cast<const float4*>(res_row + colbase + 4 * j);
   }
   wait_acc();
-  if (colbase >= g.N || g.debug == 4) return;  // warp-uniform: nothing to do for this half
+  if (g.debug == 4) return;
+  const int last_panel = (tile_col0 + COLS - 1) >> 6;
+  if (colbase >= g.N) {  // warp-uniform: nothing to compute for this half; its panels are handed over untouched
+    for (int p = tile_col0 >> 6; p <= last_panel; ++p) { ps.enter(p); ps.leave(p); }
+    return;
+  }
+  int cur_panel = -1;
   tmem_ld_32x32b_x16(t_addr, r[0]);
 #pragma unroll
   for (int c = 0; c < CHUNKS; ++c) {
     const int col0 = colbase + c * CW;
+    const int pc = (tile_col0 + c * CW) >> 6;
+    if (pc != cur_panel) {               // first chunk of a staging panel: the previous one is complete, this one must be free
+      if (cur_panel >= 0) ps.leave(cur_panel);
+      ps.enter(pc);
+      cur_panel = pc;
+    }
     tmem_wait_ld();   // chunk c is in registers
     const bool more = (c + 1 < CHUNKS) && (col0 + CW < g.N);
     if (more) {
@@ -341,6 +371,8 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs& g, int row, int co
     if (!more) break;
   }
   tmem_wait_ld();
+  ps.leave(cur_panel);
+  for (int p = cur_panel + 1; p <= last_panel; ++p) { ps.enter(p); ps.leave(p); }   // panels past the matrix edge
 }
 
 // Split-K finisher: the accumulator of a tile is the sum of its n_parts partial slots (fixed order -> bit-reproducible),
@@ -647,11 +679,12 @@ struct Gemm2Cfg {
   static constexpr int ACC_STRIDE = 256;               // TMEM columns between the two accumulator stages
   static constexpr int TMEM_COLS = 512;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES + OUT_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 4 * BN * 4;
+  static constexpr int BAR_BYTES = 384;                // mbarriers + TMEM slot, then the bias / column-scale staging
+  static constexpr int SMEM_BYTES = BAR_OFF + 1024 + BAR_BYTES + 4 * BN * 4;
 };
 
 template <int BN, bool TMA_OUT, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmArgs g) {
   // convolution recipe with a bf16 identity: its tile is TMA-loaded into the output staging buffer and updated in place
@@ -668,7 +701,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t bar_empty = bar_full + 8u * STAGES;
   const uint32_t bar_tfull = bar_full + 16u * STAGES;
   const uint32_t bar_tempty = bar_tfull + 16u;
-  const uint32_t bar_res = bar_full + 208u;   // identity tile landed in the staging buffer (RES_TMA)
+  const uint32_t bar_ready = bar_full + 256u;     // [BN / 64] staging panel may be written   (PanelSync)
+  const uint32_t bar_written = bar_full + 288u;   // [BN / 64] staging panel has been written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -699,7 +733,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(bar_tfull + 8u * a, 1);
       mbar_init(bar_tempty + 8u * a, 16);
     }
-    if (RES_TMA) mbar_init(bar_res, 1);
+    if (TMA_OUT) {
+      // threads writing staging panel p: 128 per column half that reaches into it
+      for (int p = 0; p < BN / 64; ++p) {
+        int halves = 0;
+        for (int h = 0; h < 2; ++h) halves += ((h * (BN / 2)) >> 6) <= p && p <= ((h * (BN / 2) + BN / 2 - 1) >> 6) ? 1 : 0;
+        mbar_init(bar_ready + 8u * p, 1);
+        mbar_init(bar_written + 8u * p, 128u * halves);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -771,7 +813,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_commit_2sm(bar_tfull + 8u * acc);       // accumulator halves complete in BOTH CTAs
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ===================== epilogue warps (both CTAs: own 128 rows) =====================
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -780,7 +822,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // this thread's row inside the warp's first chunk of a slot
     const size_t slot_off = (size_t(half * (BN / 2) / CW) * BM + rrow) * CW;
     int it = 0;
-    int res_it = 0;   // identity tiles loaded so far (bar_res phase)
+    int res_it = 0;   // tiles this thread has run the epilogue of (phase of the staging-panel barriers)
     PairWork work = work0;
     for (int tile, kb0, kb1; work.next(tile, kb0, kb1); ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -816,51 +858,77 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       const int row = m_blk * (2 * BM) + int(rank) * BM + rrow;
       const int colbase = n_blk * BN + half * (BN / 2);
-      float* s_bias = reinterpret_cast<float*>(tiles + Cfg::BAR_OFF + 256) + (it & 1) * 2 * BN;
+      float* s_bias = reinterpret_cast<float*>(tiles + Cfg::BAR_OFF + Cfg::BAR_BYTES) + (it & 1) * 2 * BN;
       float* s_cs = s_bias + BN;
-      if (TMA_OUT && threadIdx.x == 64) {
-        tma_store_wait_read();   // previous tile's TMA stores have drained the staging tile
-        if (RES_TMA) {
-          const int row0 = m_blk * (2 * BM) + int(rank) * BM;
-          int panels = 0;
-#pragma unroll
-          for (int pnl = 0; pnl < BN / 64; ++pnl) panels += (n_blk * BN + pnl * 64 < g.N) ? 1 : 0;
-          mbar_arrive_expect_tx(bar_res, uint32_t(panels) * 16384u);
-#pragma unroll
-          for (int pnl = 0; pnl < BN / 64; ++pnl)
-            if (n_blk * BN + pnl * 64 < g.N)
-              tma_load_2d(smem_u32(out_stage) + pnl * 16384, &tmR, bar_res, n_blk * BN + pnl * 64, row0);
-        }
-      }
       epilogue_stage_vectors<BN>(g, n_blk * BN, s_bias, s_cs, threadIdx.x - 64);   // (contains the epilogue-wide barrier)
       epilogue_warp<BN / 2, EPI>(g, row, colbase, t_addr, s_bias + half * (BN / 2), s_cs + half * (BN / 2), [&]() {
         mbar_wait(bar_tfull + 8u * acc, acc_phase);
-        if (RES_TMA) mbar_wait(bar_res, uint32_t(res_it) & 1u);
         tc_fence_after();
       }, TMA_OUT ? out_stage : nullptr, rrow, half * (BN / 2),
       n_parts ? g.sk_ws + (size_t(cluster_id + 1) * 2 + rank) * SLOT + slot_off : nullptr,
-      (g.debug == 6 || g.debug == 7) ? 0 : n_parts, 2 * SLOT);
+      (g.debug == 6 || g.debug == 7) ? 0 : n_parts, 2 * SLOT,
+      TMA_OUT ? PanelSync{bar_ready, bar_written, uint32_t(res_it) & 1u} : PanelSync{0, 0, 0});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * acc);   // TMEM drained: the next-but-one tile's MMAs may start
-      if (TMA_OUT) {
-        fence_proxy_async_smem();                                  // staging writes -> visible to the TMA engine
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64 && g.debug != 4 && g.debug != 5) {   // 5: whole epilogue but no global writes
-          const int row0 = m_blk * (2 * BM) + int(rank) * BM;
-#pragma unroll
-          for (int pnl = 0; pnl < BN / 64; ++pnl)
-            if (n_blk * BN + pnl * 64 < g.N) tma_store_2d(&tmC, smem_u32(out_stage) + pnl * 16384, n_blk * BN + pnl * 64, row0);
-          tma_store_commit();
-        }
-      } else if (n_parts) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
+      if (n_parts) asm volatile("bar.sync 1, 256;" ::: "memory");
       if (n_parts && threadIdx.x == 64)   // every epilogue thread is past its slot reads: re-arm the flags
         for (int q = 1; q <= n_parts; ++q) g.sk_flags[(cluster_id + q) * 2 + int(rank)] = 0;
       ++res_it;
     }
-    if (TMA_OUT && threadIdx.x == 64) tma_store_wait_all();
+  } else if (TMA_OUT && warp == 10 && lane == 0 && g.debug != 4) {
+    // ===================== output DMA (both CTAs: own staging panels) =====================
+    // Per finished tile: as each 64-column panel is handed over, TMA-store it; then, as each store has been read out of
+    // shared memory, hand the panel back for the next tile -- after TMA-loading that tile's bf16 identity into it for the
+    // convolution recipes (the epilogue then updates the panel in place).  The epilogue warps never wait for a store.
+    constexpr int NP = BN / 64;
+    // panels in the order they are completed: with four, the two column halves finish their first panels together
+    constexpr int ORDER[4] = {0, NP == 4 ? 2 : 1, NP == 4 ? 1 : 2, 3};
+    PairWork work = work0;
+    int tile = 0, kb0 = 0, kb1 = 0;
+    auto next_tile = [&]() {             // tiles this pair runs the epilogue of (stream-K contributions have none)
+      while (work.next(tile, kb0, kb1))
+        if (kb0 == 0) return true;
+      return false;
+    };
+    auto hand_back = [&](int p) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      if (RES_TMA && n_blk * BN + p * 64 < g.N) {
+        mbar_arrive_expect_tx(bar_ready + 8u * p, 16384u);
+        tma_load_2d(smem_u32(out_stage) + p * 16384, &tmR, bar_ready + 8u * p, n_blk * BN + p * 64,
+                    m_blk * (2 * BM) + int(rank) * BM);
+      } else {
+        mbar_arrive(bar_ready + 8u * p);
+      }
+    };
+    bool have = next_tile();
+    if (have)
+      for (int p = 0; p < NP; ++p) hand_back(p);
+    for (uint32_t n_ep = 0; have; ++n_ep) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row0 = m_blk * (2 * BM) + int(rank) * BM;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const int p = ORDER[j];
+        mbar_wait(bar_written + 8u * p, n_ep & 1u);
+        if (n_blk * BN + p * 64 < g.N && g.debug != 5)   // 5: whole epilogue but no global writes
+          tma_store_2d(&tmC, smem_u32(out_stage) + p * 16384, n_blk * BN + p * 64, row0);
+        tma_store_commit();                              // one bulk group per panel, empty or not
+      }
+      have = next_tile();
+      if (have) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          // groups complete in order: at most NP - 1 - j younger ones pending <=> the store of ORDER[j] has been read out
+          if (NP - 1 - j == 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+          else if (NP - 1 - j == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          else if (NP - 1 - j == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          hand_back(ORDER[j]);
+        }
+      }
+    }
+    tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -1039,7 +1107,7 @@ static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream, b
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(GEMM2_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
