@@ -233,7 +233,9 @@ HOIGEN_API int hoigen_prior_tokens(const float* boxes, const float* scores, cons
                                    float* prior, uint8_t* mask, hoigen_stream_t stream);
 /* compute_roi_embeddings geometry U:981-1057: RoIAlign(7x7, sampling_ratio=-1, aligned=True)+mean of every single
  * box and every union box on the 14x14 token grid (torchvision.ops.roi_align call sites U:1028-1029), then
- * f_H = single[x]/|.|, f_O = single[y]/|.|, f_U = union/|.|  -> pair_feat [3][Ktot][512] (H,O,U) bf16 (+fp32). */
+ * f_H = single[x]/|.|, f_O = single[y]/|.|, f_U = union/|.|  -> pair_feat [3][Ktot][512] (H,O,U) bf16 (+fp32).
+ * RoIAlign + mean runs as one fp32-accurate tensor-core product per image (3 x bf16-split operands, roi_tc.cu; <= 32 boxes
+ * per image); roi_weights is scratch for the fp32 SIMT form (HOIGEN_ROI_SIMT=1) and otherwise untouched. */
 HOIGEN_API int hoigen_roi_pair_features(const float* tokens, const float* boxes, const int32_t* box_off,
                                         const int32_t* pair_off, int32_t batch, int32_t ntot, int32_t ktot,
                                         float spatial_scale, float* roi_weights /* workspace (ntot+ktot, 32) */,
