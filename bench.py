@@ -93,6 +93,8 @@ def workload_config(args, world, w):
                          "reports the step with the stock R50 run per step",
         "batches_in_flight": (f"{getattr(args, 'streams', 1)} (consecutive steps alternate over {getattr(args, 'streams', 1)} CUDA streams and "
                               "overlap on the GPU; kernel_breakdown / roofline are single-stream per-launch times)"),
+        "launch_ahead": (f"{getattr(args, 'ahead', 1)} steps are enqueued ahead of the one being finished (every step is launched and "
+                         "finished inside its timed region)"),
         "collective": ("none (single GPU)" if world == 1 else
                        "all ranks receive all detections: per step a compact wire record (9 B/triplet) pushed into every peer's buffer over "
                        "NVLink peer memory (copy engines), one barrier + unpack per sweep, inside each timed region"),
@@ -452,18 +454,19 @@ def run_b200(args, rank, world, local_rank):
         return None
 
     def run_resident(first, count):
-        """`count` complete steps; step i+1 is enqueued before step i is waited for, so the host's per-step work (layout,
-        launches, result views) overlaps the GPU instead of leaving it idle.  Every step is launched AND finished here."""
+        """`count` complete steps; steps i+1 .. i+A (--ahead, default 1) are enqueued before step i is waited for, so the
+        host's per-step work (layout, launches, result views) overlaps the GPU.  Every step is launched AND finished here."""
         trace = os.environ.get("HOIGEN_BENCH_TRACE")
-        pend = launch_resident(first)
+        A = max(1, args.ahead)
+        queue = [launch_resident(first + j) for j in range(min(A, count))]
         dets = None
         for i in range(count):
             ta = time.perf_counter()
-            nxt = launch_resident(first + i + 1) if i + 1 < count else None
+            if i + A < count:
+                queue.append(launch_resident(first + i + A))
             tb = time.perf_counter()
-            dets = finish_resident(pend)
-            pend = nxt
-            if nxt is None:
+            dets = finish_resident(queue.pop(0))
+            if i + 1 == count:
                 drain_exchanges()
             if trace:
                 print(f"[trace] step {first + i}: launch {1e3 * (tb - ta):.2f} ms, finish {1e3 * (time.perf_counter() - tb):.2f} ms",
@@ -483,7 +486,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- end-to-end step: HOST (pinned) inputs -> device -> detections -> HOST, H2D of step i+1 overlapped with step i --
     copy_stream = torch.cuda.Stream(device=dev)
-    NSLOT = 3   # input slots: one being computed on, one launched ahead, one being uploaded
+    NSLOT = max(1, args.ahead) + 2   # input slots: one being computed on, --ahead launched ahead, one being uploaded
     dev_in = [dict(imgs=torch.empty_like(dev_imgs[0]), boxes=torch.empty(B * n_per, 4, device=dev),
                    scores=torch.empty(B * n_per, device=dev), labels=torch.empty(B * n_per, dtype=torch.int64, device=dev),
                    dino=torch.empty_like(dev_dino[0]), ev=torch.cuda.Event(), free=None) for _ in range(NSLOT)]
@@ -537,25 +540,26 @@ def run_b200(args, rank, world, local_rank):
         ho["keep"] = dets                                # keeps the device tensors alive until the copy is done
         return m
 
-    def run_host(first, count, pend):
-        """`count` end-to-end steps starting at step `first` (already uploaded and launched as `pend`).  Per step: one
-        upload (two steps ahead), one launch (one step ahead), one finish + D2H.  Returns the next pending step."""
+    def run_host(first, count, queue):
+        """`count` end-to-end steps starting at step `first`; `queue` holds the already launched steps first .. first+A-1
+        (A = --ahead).  Per step: one upload (A + 2 steps ahead), one launch (A steps ahead), one finish + D2H.  Returns
+        the queue of still-pending steps."""
         m = 0
+        A = max(1, args.ahead)
         trace = os.environ.get("HOIGEN_BENCH_TRACE")
         for i in range(first, first + count):
             ta = time.perf_counter()
-            nxt = launch_host(i + 1)
+            queue.append(launch_host(i + A))
             tb = time.perf_counter()
-            m = finish_host(i, pend)
+            m = finish_host(i, queue.pop(0))
             tc = time.perf_counter()
-            upload(i + 3)                                # its slot was read by step i, which has finished
-            pend = nxt
+            upload(i + A + 2)                            # its slot was read by step i, which has finished
             if trace:
                 ms_ = torch.cuda.memory_stats(dev)
                 print(f"[trace-e2e] step {i}: launch {1e3 * (tb - ta):.2f} ms, finish+d2h {1e3 * (tc - tb):.2f} ms, "
                       f"upload {1e3 * (time.perf_counter() - tc):.2f} ms segs {ms_['segment.all.allocated']} "
                       f"gc {[g['collections'] for g in gc.get_stats()]}", file=sys.stderr, flush=True)
-        return pend, m
+        return queue, m
 
     def barrier():
         if world > 1:
@@ -613,10 +617,10 @@ def run_b200(args, rank, world, local_rank):
                      "unit": UNIT, "clocks": clocks.snapshot() if rank == 0 else None}
 
     # ---- end-to-end timing with host buffers -----------------------------------------------------------------------------
-    for i in range(3):
+    for i in range(max(1, args.ahead) + 2):
         upload(i)
     w_e2e = max(8, args.warmup)
-    pend, m_out = run_host(0, w_e2e, launch_host(0))
+    pend, m_out = run_host(0, w_e2e, [launch_host(j) for j in range(max(1, args.ahead))])
     barrier()
     # The timer starts at a step boundary of the RUNNING pipeline, six untimed steps after that synchronisation: traced
     # (HOIGEN_BENCH_TRACE prints the caching allocator's segment count per step), the allocator grows by two segments on
@@ -643,7 +647,8 @@ def run_b200(args, rank, world, local_rank):
         clocks.snapshot()
     h2d = host_imgs[0].numel() * 4 + sum(t.numel() * t.element_size() for t in host_packed[0]) + host_dino[0].numel() * 4
     d2h = m_out * (4 + 8 + 8 + 16) + (B + 1) * 4
-    model.finish(pend)
+    for p_ in pend:
+        model.finish(p_)
     torch.cuda.synchronize()
 
     def quick_resident(steps):
@@ -819,6 +824,9 @@ def main():
     ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the sustained block in seconds (0 = skip)")
     ap.add_argument("--ref-batch", type=int, default=8, help="--impl reference: images per step (bounded CPU sample)")
     ap.add_argument("--ref-gpu-batch", type=int, default=64, help="--impl reference-gpu: images per step (capped at the config's batch)")
+    ap.add_argument("--ahead", type=int, default=1,
+                    help="steps launched ahead of the one being finished (both loops).  Measured on B200: 1 / 2 / 3 ahead give 3.67 / 3.66 / "
+                         "3.67 ms resident and 3.88 / 4.13 / 4.16 ms end to end (more uploads in flight), so 1 is the default")
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams that consecutive steps alternate over: 2 (default) = two batches overlap on the GPU, "
                          "1 = strictly one batch at a time")

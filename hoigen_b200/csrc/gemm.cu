@@ -1159,7 +1159,9 @@ static int launch_gemm2(const hoigen_gemm_params* p, cudaStream_t stream, bool f
 }
 
 // Pick (cta pair?, BN): fewest (possibly fractional, see stream-K) scheduling rounds x relative tile time. The one-CTA kernel is L2-operand-bound
-// (~87 FLOP per L2 byte at BN = 256) so its tiles are charged 1.35x.
+// (~87 FLOP per L2 byte at BN = 256) and stores through per-thread writes: measured 550-680 TFLOP/s against 900-1060 for the
+// pair kernel on the K = 768 shapes at M = 25 216, so its tiles are charged 1.6x (1.35x let a one-round quantisation
+// advantage pick it for BASELINE config 4).
 static int auto_split_k(int num_tiles, int num_k);
 static void choose_config(int M, int N, int K, int* pair, int* bn) {
   const int sms = num_sms();
@@ -1189,7 +1191,7 @@ static void choose_config(int M, int N, int K, int* pair, int* bn) {
     if (b > 64 && N <= b / 2) continue;
     const int tiles = ((M + BM - 1) / BM) * ((N + b - 1) / b);
     const int rounds = (tiles + sms - 1) / sms;
-    const double cost = rounds * (double(b) * 1.35 + 24.0);
+    const double cost = rounds * (double(b) * 1.6 + 24.0);
     if (cost < best) { best = cost; *pair = 0; *bn = b; }
   }
   if (M > BM) {
