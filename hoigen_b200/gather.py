@@ -351,6 +351,29 @@ def unpack_wire_torch(record: torch.Tensor, max_images: int, size):
     return PackedDetections(scores, labels, objects, pairing, boxes, toff, boff, size)
 
 
+class _SweepRecord:
+    """One (rank, step) record of a finished sweep: PackedDetections whose per-field tensors are views into the sweep-wide
+    output tensors, cut on first access (a sweep at 8 ranks x 32 steps holds 256 records x 5 fields)."""
+
+    def __init__(self, bufs, tb, m, bb, nbox, triplet_off, box_off, size, done):
+        self._bufs, self._tb, self._m, self._bb, self._nbox = bufs, tb, m, bb, nbox
+        self.triplet_off, self.box_off, self.size, self.done = triplet_off, box_off, tuple(size), done
+
+    scores = property(lambda self: self._bufs[0][self._tb: self._tb + self._m])
+    labels = property(lambda self: self._bufs[1][self._tb: self._tb + self._m])
+    objects = property(lambda self: self._bufs[2][self._tb: self._tb + self._m])
+    pairing = property(lambda self: self._bufs[3][2 * self._tb: 2 * (self._tb + self._m)])
+    boxes = property(lambda self: self._bufs[4][self._bb: self._bb + self._nbox])
+
+    @property
+    def num_images(self) -> int:
+        return len(self.triplet_off) - 1
+
+    def image(self, b: int) -> dict:
+        from .detector import PackedDetections
+        return PackedDetections.image(self, b)
+
+
 class SweepExchange:
     """All ranks end up with every rank's detections of a sweep (an evaluation pass over a dataset shard).
 
@@ -515,13 +538,12 @@ class SweepExchange:
             raise ValueError(f"rank {r} slot {s}: no record arrived (ranks must add the same number of steps per sweep)")
         if (H[:, :, 2] < 0).any():
             raise ValueError(f"rank {int((H[:, :, 2] < 0).nonzero()[0][0])}: a step's detections did not fit the record capacity ({cap} bytes)")
-        recs = []            # (rank, slot, nimg, m, nbox, toff, boff)
-        for r in range(W):
-            for s in range(n):
-                h = H[r, s]
-                nimg = int(h[1])
-                recs.append((r, s, nimg, int(h[2]), int(h[3]), h[4: 4 + nimg + 1].tolist(), h[4 + mi + 1: 4 + mi + 1 + nimg + 1].tolist()))
-        m_tot, b_tot = sum(x[3] for x in recs), sum(x[4] for x in recs)
+        # host side of the unpack, vectorised: at 8 ranks x 20 steps a per-record Python loop over tensor slices cost ~3 ms
+        import numpy as np
+        m_arr, nb_arr = H[:, :, 2].astype(np.int64), H[:, :, 3].astype(np.int64)
+        tb_arr = (np.cumsum(m_arr.ravel()) - m_arr.ravel()).reshape(W, n)      # triplet / box base of record (r, s) in the
+        bb_arr = (np.cumsum(nb_arr.ravel()) - nb_arr.ravel()).reshape(W, n)    # sweep-wide output tensors, (rank, step) order
+        m_tot, b_tot = int(m_arr.sum()), int(nb_arr.sum())
         rows = g.shape[1]                                         # slots per rank in the buffer being unpacked
         with torch.cuda.stream(self.side):
             scores = torch.empty(max(m_tot, 1), dtype=torch.float32, device=self.dev)
@@ -529,15 +551,11 @@ class SweepExchange:
             objects = torch.empty(max(m_tot, 1), dtype=torch.int64, device=self.dev)
             pairing = torch.empty(max(2 * m_tot, 2), dtype=torch.int64, device=self.dev)
             boxes = torch.empty(max(b_tot, 1), 4, dtype=torch.float32, device=self.dev)
-            bases = self.bases_host
-            bases.fill_(-1)
-            tb, bb, place = 0, 0, []
-            for (r, s, nimg, m, nbox, toff, boff) in recs:
-                bases[r, s, 0], bases[r, s, 1] = tb, bb
-                place.append((tb, bb))
-                tb += m
-                bb += nbox
-            self.bases_dev.copy_(bases, non_blocking=True)
+            bases_np = self.bases_host.numpy()
+            bases_np[...] = -1
+            bases_np[:, :n, 0] = tb_arr
+            bases_np[:, :n, 1] = bb_arr
+            self.bases_dev.copy_(self.bases_host, non_blocking=True)
             bases_d = self.bases_dev
             base_ptr = g.data_ptr()
             for r in range(W):                                    # one launch per rank: its slots are contiguous
@@ -550,10 +568,14 @@ class SweepExchange:
             done = torch.cuda.Event()
             done.record()
         torch.cuda.current_stream(self.dev).wait_event(done)
-        for (r, s, nimg, m, nbox, toff, boff), (tb, bb) in zip(recs, place):
-            pk = PackedDetections(scores[tb: tb + m], labels[tb: tb + m], objects[tb: tb + m], pairing[2 * tb: 2 * (tb + m)],
-                                  boxes[bb: bb + nbox], toff, boff, self.size)
-            pk.done = done
-            out[r].append(pk)
+        Hl = H.tolist()
+        bufs = (scores, labels, objects, pairing, boxes)
+        for r in range(W):
+            row_out = out[r]
+            for s in range(n):
+                h = Hl[r][s]
+                nimg = h[1]
+                row_out.append(_SweepRecord(bufs, int(tb_arr[r, s]), h[2], int(bb_arr[r, s]), h[3], h[4: 4 + nimg + 1],
+                                            h[4 + mi + 1: 4 + mi + 1 + nimg + 1], self.size, done))
         self._reset()
         return out
