@@ -53,6 +53,39 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   }
 }
 
+// The same im2col for any image size (DETR's backbone runs the identical stem on up to 800 x 1333 inputs): one thread per 8
+// columns of one output pixel of (B, ceil(H / 2), ceil(W / 2)); reads hit L1 / L2 (neighbouring pixels share 5 of 7 columns).
+__global__ void stem_im2col_hw_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ rows, int batch, int H, int W) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)batch * Ho * Wo * (STEM_K / 8);
+  if (gid >= total) return;
+  const int g8 = int(gid % (STEM_K / 8));
+  const long long pix = gid / (STEM_K / 8);
+  const int ox = int(pix % Wo), oy = int((pix / Wo) % Ho), b = int(pix / ((long long)Wo * Ho));
+  const float* base = img + size_t(b) * 3 * H * W;
+  uint32_t packed[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = g8 * 8 + e * 2 + h;
+      float v = 0.f;
+      if (k < 147) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int ky = tap / 7, kx = tap - ky * 7;
+        const int iy = 2 * oy - 3 + ky, ix = 2 * ox - 3 + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(base + (size_t(c) * H + iy) * W + ix);
+      }
+      v2[h] = v;
+    }
+    const __nv_bfloat162 p = __floats2bfloat162_rn(v2[0], v2[1]);
+    packed[e] = *reinterpret_cast<const uint32_t*>(&p);
+  }
+  *reinterpret_cast<uint4*>(rows + pix * STEM_K + g8 * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
 __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   uint4 r;
   const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
@@ -63,11 +96,11 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   return r;
 }
 
-// 3x3 / stride 2 / pad 1 max pooling: in (B, h, w, c) bf16 WITHOUT halo (the stem GEMM's rows) -> out (B, h/2 + 2, w/2 + 2, c)
-// with the zero halo written.  One thread per (output pixel incl. ring, 8 channels).
+// 3x3 / stride 2 / pad 1 max pooling: in (B, h, w, c) bf16 WITHOUT halo (the stem GEMM's rows) -> out (B, ho + 2, wo + 2, c),
+// ho = ceil(h / 2), wo = ceil(w / 2), with the zero halo written.  One thread per (output pixel incl. ring, 8 channels).
 __global__ void maxpool3x3s2_halo_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int batch, int h,
                                          int w, int c) {
-  const int ho = h / 2, wo = w / 2, hp = ho + 2, wp = wo + 2, c8 = c / 8;
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2, hp = ho + 2, wp = wo + 2, c8 = c / 8;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)batch * hp * wp * c8;
   if (gid >= total) return;
@@ -95,12 +128,12 @@ __global__ void maxpool3x3s2_halo_kernel(const __nv_bfloat16* __restrict__ in, _
   *(reinterpret_cast<uint4*>(out + pix * c) + g8) = best;
 }
 
-// Stride-2 gathers: in (B, h + 2, w + 2, c) with halo -> rows (B * (h/2 + 2) * (w/2 + 2), taps * c), the A operand of the
+// Stride-2 gathers: in (B, h + 2, w + 2, c) with halo -> rows (B * (ho + 2) * (wo + 2), taps * c), ho = ceil(h / 2), the A operand of the
 // stride-2 convolutions (taps = 9: 3x3 / pad 1, column = (ky * 3 + kx) * c + channel; taps = 1: the 1x1 down-sampling
 // shortcut).  Ring rows of the output are written as zeros.  One thread per (row, tap, 8 channels).
 __global__ void conv_gather_s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ rows, int batch, int h,
                                       int w, int c, int taps) {
-  const int ho = h / 2, wo = w / 2, hp = ho + 2, wp = wo + 2, c8 = c / 8;
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2, hp = ho + 2, wp = wo + 2, c8 = c / 8;   // odd h: tap row 2 ho = h + 1 is the halo
   const int hin = h + 2, win = w + 2;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)batch * hp * wp * taps * c8;
@@ -174,13 +207,25 @@ int hoigen_stem_im2col(const float* images, void* rows_bf16, int32_t batch, hoig
   return HOIGEN_OK;
 }
 
+int hoigen_stem_im2col_hw(const float* images, void* rows_bf16, int32_t batch, int32_t h, int32_t w, hoigen_stream_t stream) {
+  HOIGEN_CHECK_ARG(images && rows_bf16 && batch > 0 && h > 0 && w > 0, "stem_im2col_hw: bad arguments");
+  if (h == 224 && w == 224) return hoigen_stem_im2col(images, rows_bf16, batch, stream);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)batch * ((h + 1) / 2) * ((w + 1) / 2) * (STEM_K / 8);
+  HOIGEN_CHECK_ARG(total / 256 < 0x7fffffffLL, "stem_im2col_hw: batch too large");
+  KernelScope ks("stem_im2col", s, 0, double(batch) * (3.0 * h * w * 4 + double((h + 1) / 2) * ((w + 1) / 2) * STEM_K * 2));
+  stem_im2col_hw_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(images, reinterpret_cast<__nv_bfloat16*>(rows_bf16), batch, h, w);
+  HOIGEN_CHECK_LAUNCH();
+  return HOIGEN_OK;
+}
+
 int hoigen_maxpool3x3s2_halo(const void* in_bf16, void* out_bf16, int32_t batch, int32_t h, int32_t w, int32_t c,
                              hoigen_stream_t stream) {
-  HOIGEN_CHECK_ARG(in_bf16 && out_bf16 && batch > 0 && h > 0 && w > 0 && (h % 2) == 0 && (w % 2) == 0 && c > 0 && (c % 8) == 0,
+  HOIGEN_CHECK_ARG(in_bf16 && out_bf16 && batch > 0 && h > 0 && w > 0 && c > 0 && (c % 8) == 0,
                    "maxpool3x3s2_halo: bad arguments (h=%d w=%d c=%d)", h, w, c);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const long long total = (long long)batch * (h / 2 + 2) * (w / 2 + 2) * (c / 8);
-  KernelScope ks("maxpool3x3s2", s, 0, double(batch) * c * 2 * (double(h) * w + double(h / 2 + 2) * (w / 2 + 2)));
+  const long long total = (long long)batch * ((h + 1) / 2 + 2) * ((w + 1) / 2 + 2) * (c / 8);
+  KernelScope ks("maxpool3x3s2", s, 0, double(batch) * c * 2 * (double(h) * w + double((h + 1) / 2 + 2) * ((w + 1) / 2 + 2)));
   maxpool3x3s2_halo_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), batch, h, w, c);
   HOIGEN_CHECK_LAUNCH();
@@ -189,11 +234,10 @@ int hoigen_maxpool3x3s2_halo(const void* in_bf16, void* out_bf16, int32_t batch,
 
 int hoigen_conv_gather_s2(const void* in_bf16, void* rows_bf16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t taps,
                           hoigen_stream_t stream) {
-  HOIGEN_CHECK_ARG(in_bf16 && rows_bf16 && batch > 0 && h > 0 && w > 0 && (h % 2) == 0 && (w % 2) == 0 && c > 0 && (c % 8) == 0 &&
-                       (taps == 1 || taps == 9),
+  HOIGEN_CHECK_ARG(in_bf16 && rows_bf16 && batch > 0 && h > 0 && w > 0 && c > 0 && (c % 8) == 0 && (taps == 1 || taps == 9),
                    "conv_gather_s2: bad arguments (h=%d w=%d c=%d taps=%d)", h, w, c, taps);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const long long total = (long long)batch * (h / 2 + 2) * (w / 2 + 2) * taps * (c / 8);
+  const long long total = (long long)batch * ((h + 1) / 2 + 2) * ((w + 1) / 2 + 2) * taps * (c / 8);
   KernelScope ks("conv_gather_s2", s, 0, 2.0 * double(total) * 16);
   conv_gather_s2_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(rows_bf16), batch, h, w, c, taps);
@@ -218,7 +262,10 @@ int hoigen_conv_plan_run(const hoigen_conv_op* ops, int32_t n_ops, hoigen_stream
     int rc = HOIGEN_ERR_INVALID;
     switch (o.kind) {
       case HOIGEN_CONV_OP_GEMM: rc = hoigen_gemm_bf16(&o.gemm, stream); break;
-      case HOIGEN_CONV_OP_STEM_IM2COL: rc = hoigen_stem_im2col(reinterpret_cast<const float*>(o.in), o.out, o.batch, stream); break;
+      case HOIGEN_CONV_OP_STEM_IM2COL:
+        rc = (o.h > 0 && o.w > 0) ? hoigen_stem_im2col_hw(reinterpret_cast<const float*>(o.in), o.out, o.batch, o.h, o.w, stream)
+                                  : hoigen_stem_im2col(reinterpret_cast<const float*>(o.in), o.out, o.batch, stream);
+        break;
       case HOIGEN_CONV_OP_STEM_CONV:
         rc = hoigen_stem_conv(reinterpret_cast<const float*>(o.in), o.gemm.w, o.gemm.bias, o.out, o.batch, stream);
         break;

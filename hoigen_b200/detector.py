@@ -247,6 +247,16 @@ class UPT(nn.Module):
         object.__setattr__(self, "_fast_dino", fast)
         return self
 
+    def accelerate_detr_backbone(self) -> "UPT":
+        """Opt in: run the injected DETR detector's ResNet-50 backbone body (U:1594, detr/models/backbone.py:72-73; FrozenBatchNorm,
+        layer4 only) on this repo's convolution kernels (hoigen_b200.dino.KernelDetrBackboneBody; bf16 activations).  The
+        position encoding, the transformer and the heads stay the injected stock modules."""
+        from .dino import KernelDetrBackboneBody
+        backbone = self.detector.backbone[0]
+        if not isinstance(backbone.body, KernelDetrBackboneBody):
+            backbone.body = KernelDetrBackboneBody(backbone.body)
+        return self
+
     def _apply(self, fn, *a, **k):
         self.invalidate_packed()
         self._ws = {}

@@ -29,11 +29,11 @@ from torch import nn
 from . import _cabi
 
 
-def _fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
+def _fold_bn(conv: nn.Conv2d, bn: nn.Module) -> nn.Conv2d:
     """conv -> bn (eval) == conv' with w' = w * gamma / sqrt(var + eps), b' = beta + (b - mean) * gamma / sqrt(var + eps)."""
     w = conv.weight.detach().float()
     b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
-    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + getattr(bn, "eps", 1e-5))   # DETR's FrozenBatchNorm2d: 1e-5
     fused = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation,
                       conv.groups, bias=True).to(w.device)
     fused.weight.data = w * scale[:, None, None, None]
@@ -98,21 +98,23 @@ class FastDinoR50(nn.Module):
         return static_out.clone()
 
 
-class KernelDinoR50(nn.Module):
-    """`features = net(images)` -> (B, 2048) fp32, L2-normalised (U:1617-1618), on the hand-written kernels.
+class KernelResNet50(nn.Module):
+    """A torchvision ResNet-50 (eval; BatchNorm2d or DETR's FrozenBatchNorm2d) executed on the repo's kernels for any image
+    size: `rows, (h, w) = net.features(images)` gives layer4 as haloed NHWC bf16 rows of (B, h + 2, w + 2, 2048).
 
-    Weights: the BatchNorm-folded convolutions of the given torchvision ResNet-50 (eval), bf16, packed K-major:
-    1x1 -> (Cout, Cin); 3x3 -> (Cout, 9 Cin) with k = (ky * 3 + kx) * Cin + c; stem 7x7 -> (64, 160), k = (ky * 7 + kx) * 3 + c.
+    Weights: the BatchNorm-folded convolutions, bf16, packed K-major: 1x1 -> (Cout, Cin); 3x3 -> (Cout, 9 Cin) with
+    k = (ky * 3 + kx) * Cin + c; stem 7x7 -> (64, 160), k = (ky * 7 + kx) * 3 + c (im2col form) and (64, 192),
+    k = ky * 24 + kx * 3 + c (fused 224 x 224 stem kernel).
     """
 
     STEM_K = 160
 
-    def __init__(self, dino_model: nn.Module):
+    def __init__(self, resnet: nn.Module):
         super().__init__()
-        dev = next(dino_model.parameters()).device
+        dev = next(iter(resnet.parameters())).device
         if dev.type != "cuda":
-            raise ValueError("KernelDinoR50 needs the module on a CUDA device")
-        m = fold_batchnorms(dino_model)
+            raise ValueError("KernelResNet50 needs the module on a CUDA device")
+        m = fold_batchnorms(resnet)
         self.device_ = dev
         self._keep: List[torch.Tensor] = []
 
@@ -127,25 +129,27 @@ class KernelDinoR50(nn.Module):
             self._keep += [wk, b]
             return wk, b
 
-        self.stem = pack(m.conv1)                      # (64, 160): the two-step form (im2col + GEMM), kept for tests / A-B
+        self.stem = pack(m.conv1)                      # (64, 160): the two-step form (im2col + GEMM), any image size
         w7 = m.conv1.weight.detach().float()           # (64, 3, 7, 7) -> (64, 192): column = ky * 24 + kx * 3 + c
         w_runs = torch.zeros(64, 7, 24, device=dev)
         w_runs[:, :, :21] = w7.permute(0, 2, 3, 1).reshape(64, 7, 21)
         self.stem_fused = (torch.nn.functional.pad(w_runs.reshape(64, 168), (0, 24)).to(torch.bfloat16).contiguous(), self.stem[1])
         self._keep.append(self.stem_fused[0])
-        self.fused_stem = True
+        self.fused_stem = True                         # 224 x 224 inputs only
         self.stages = []
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             blocks = []
             for blk in layer:
+                if blk.conv2.dilation[0] != 1 or blk.conv1.stride[0] != 1:
+                    raise NotImplementedError("KernelResNet50: dilated / stride-on-conv1 bottlenecks are not supported")
                 blocks.append(dict(c1=pack(blk.conv1), c2=pack(blk.conv2), c3=pack(blk.conv3),
                                    ds=pack(blk.downsample[0]) if blk.downsample is not None else None,
                                    stride=blk.conv2.stride[0]))
             self.stages.append(blocks)
         self._plans: Dict[tuple, dict] = {}
 
-    # ---- plan construction: buffers + the op list for one (batch, stream) ----
-    def _build_plan(self, B: int) -> dict:
+    # ---- plan construction: buffers + the op list for one (batch, image size, head, stream) ----
+    def _build_plan(self, B: int, Hi: int, Wi: int, head: str) -> dict:
         dev = self.device_
         bf = dict(device=dev, dtype=torch.bfloat16)
         ops: List[_cabi.ConvOp] = []
@@ -173,41 +177,43 @@ class KernelDinoR50(nn.Module):
             op.batch, op.h, op.w, op.c, op.taps = B, h, w, c, taps
             ops.append(op)
 
-        stem_out = new(B * 112 * 112, 64)
-        if self.fused_stem:
+        half = lambda v: (v + 1) // 2
+        H1, W1 = half(Hi), half(Wi)                    # stem output
+        stem_out = new(B * H1 * W1, 64)
+        if self.fused_stem and (Hi, Wi) == (224, 224):
             op = _cabi.ConvOp()
             op.kind, op.out, op.batch = _cabi.CONV_OP_STEM_CONV, stem_out.data_ptr(), B
             op.gemm.w, op.gemm.bias = self.stem_fused[0].data_ptr(), self.stem_fused[1].data_ptr()
             ops.append(op)
         else:
-            stem_rows = new(B * 112 * 112, self.STEM_K)
-            rowop(_cabi.CONV_OP_STEM_IM2COL, None, stem_rows)
+            stem_rows = new(B * H1 * W1, self.STEM_K)
+            rowop(_cabi.CONV_OP_STEM_IM2COL, None, stem_rows, Hi, Wi)
             gemm(stem_rows, self.stem, stem_out, relu=True)
-        H = 56
-        x = new(B * (H + 2) * (H + 2), 64)
-        rowop(_cabi.CONV_OP_MAXPOOL, stem_out, x, 112, 112, 64)
+        H, W = half(H1), half(W1)                      # after the max-pool
+        x = new(B * (H + 2) * (W + 2), 64)
+        rowop(_cabi.CONV_OP_MAXPOOL, stem_out, x, H1, W1, 64)
         cin = 64
         for blocks in self.stages:
             for blk in blocks:
                 width = blk["c1"][0].shape[0]
                 cout = blk["c3"][0].shape[0]
-                halo_in = (H + 2, H + 2)
+                halo_in = (H + 2, W + 2)
                 rows_in = B * halo_in[0] * halo_in[1]
                 t1 = new(rows_in, width)
                 gemm(x, blk["c1"], t1, relu=True, halo=halo_in)
                 if blk["stride"] == 2:
-                    Ho = H // 2
-                    halo_out = (Ho + 2, Ho + 2)
+                    Ho, Wo = half(H), half(W)
+                    halo_out = (Ho + 2, Wo + 2)
                     rows_out = B * halo_out[0] * halo_out[1]
                     g2 = new(rows_out, 9 * width)
-                    rowop(_cabi.CONV_OP_GATHER_S2, t1, g2, H, H, width, 9)
+                    rowop(_cabi.CONV_OP_GATHER_S2, t1, g2, H, W, width, 9)
                     t2 = new(rows_out, width)
                     gemm(g2, blk["c2"], t2, relu=True, halo=halo_out)
                     gs = new(rows_out, cin)
-                    rowop(_cabi.CONV_OP_GATHER_S2, x, gs, H, H, cin, 1)
+                    rowop(_cabi.CONV_OP_GATHER_S2, x, gs, H, W, cin, 1)
                     sc = new(rows_out, cout)
                     gemm(gs, blk["ds"], sc, relu=False, halo=halo_out)
-                    H = Ho
+                    H, W = Ho, Wo
                 else:
                     halo_out, rows_out = halo_in, rows_in
                     t2 = new(rows_out, width)
@@ -220,24 +226,69 @@ class KernelDinoR50(nn.Module):
                 y = new(rows_out, cout)
                 gemm(t2, blk["c3"], y, relu=True, halo=halo_out, res=sc)
                 x, cin = y, cout
-        out = torch.empty(B, cin, device=dev, dtype=torch.float32)
-        op = _cabi.ConvOp()
-        op.kind, op.in_, op.out = _cabi.CONV_OP_AVGPOOL_L2NORM, x.data_ptr(), out.data_ptr()
-        op.batch, op.h, op.w, op.c = B, H, H, cin
-        ops.append(op)
+        out = None
+        if head == "dino":
+            out = torch.empty(B, cin, device=dev, dtype=torch.float32)
+            op = _cabi.ConvOp()
+            op.kind, op.in_, op.out = _cabi.CONV_OP_AVGPOOL_L2NORM, x.data_ptr(), out.data_ptr()
+            op.batch, op.h, op.w, op.c = B, H, W, cin
+            ops.append(op)
         arr = (_cabi.ConvOp * len(ops))(*ops)
-        return dict(ops=arr, n=len(ops), bufs=bufs, out=out)
+        return dict(ops=arr, n=len(ops), bufs=bufs, out=out, rows=x, hw=(H, W), channels=cin)
+
+    def _run(self, images: torch.Tensor, head: str) -> dict:
+        if images.device != self.device_ or images.dtype != torch.float32 or images.dim() != 4 or images.shape[1] != 3:
+            raise ValueError("KernelResNet50 takes (B, 3, H, W) fp32 images on the module's device")
+        images = images.contiguous()
+        lib = _cabi.init(images.device)
+        key = (int(images.shape[0]), int(images.shape[2]), int(images.shape[3]), head,
+               torch.cuda.current_stream(images.device).cuda_stream)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 8:                  # DETR batches change size: keep the activation sets bounded
+                self._plans.clear()
+            plan = self._plans[key] = self._build_plan(key[0], key[1], key[2], head)
+        plan["ops"][0].in_ = images.data_ptr()
+        _cabi.check(lib.hoigen_conv_plan_run(plan["ops"], plan["n"], _cabi.stream_ptr()), "hoigen_conv_plan_run")
+        return plan
+
+    @torch.no_grad()
+    def features(self, images: torch.Tensor):
+        """-> (rows, (h, w)): layer4 as haloed NHWC bf16 rows of (B, h + 2, w + 2, 2048), a workspace view valid until the
+        next call with the same batch / image size on this stream."""
+        plan = self._run(images, "features")
+        return plan["rows"], plan["hw"]
+
+    @torch.no_grad()
+    def features_nchw(self, images: torch.Tensor) -> torch.Tensor:
+        """-> layer4 (B, 2048, h, w) fp32, what `IntermediateLayerGetter(resnet, {'layer4': '0'})` returns."""
+        rows, (h, w) = self.features(images)
+        B = images.shape[0]
+        return rows.view(B, h + 2, w + 2, -1)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().contiguous()
+
+
+class KernelDinoR50(KernelResNet50):
+    """`features = net(images)` -> (B, 2048) fp32, L2-normalised (U:1617-1618), on the hand-written kernels."""
+
+    def __init__(self, dino_model: nn.Module):
+        super().__init__(dino_model)
 
     @torch.no_grad()
     def forward(self, images: torch.Tensor) -> torch.Tensor:
-        if images.device != self.device_ or images.dtype != torch.float32 or tuple(images.shape[1:]) != (3, 224, 224):
+        if tuple(images.shape[1:]) != (3, 224, 224):
             raise ValueError("KernelDinoR50 takes (B, 3, 224, 224) fp32 images on the module's device")
-        images = images.contiguous()
-        lib = _cabi.init(images.device)
-        key = (int(images.shape[0]), torch.cuda.current_stream(images.device).cuda_stream)
-        plan = self._plans.get(key)
-        if plan is None:
-            plan = self._plans[key] = self._build_plan(key[0])
-        plan["ops"][0].in_ = images.data_ptr()
-        _cabi.check(lib.hoigen_conv_plan_run(plan["ops"], plan["n"], _cabi.stream_ptr()), "hoigen_conv_plan_run")
-        return plan["out"].clone()
+        return self._run(images, "dino")["out"].clone()
+
+
+class KernelDetrBackboneBody(nn.Module):
+    """Drop-in for `detector.backbone[0].body` (torchvision IntermediateLayerGetter over a FrozenBatchNorm ResNet-50 returning
+    {'0': layer4}; detr/models/backbone.py:69,72-73, call site U:1594): the same feature map from the repo's kernels."""
+
+    def __init__(self, body: nn.Module):
+        super().__init__()
+        self.net = KernelResNet50(body)
+
+    @torch.no_grad()
+    def forward(self, images: torch.Tensor):
+        from collections import OrderedDict
+        return OrderedDict([("0", self.net.features_nchw(images.float()))])

@@ -457,15 +457,19 @@ HOIGEN_API int hoigen_prepare_proposals(const float* scores, const int64_t* labe
 /* images (B,3,224,224) fp32 -> rows (B*112*112, 160) bf16: im2col of conv1 (7x7, stride 2, pad 3), column = (ky*7+kx)*3+c,
  * columns 147..159 zero. */
 HOIGEN_API int hoigen_stem_im2col(const float* images, void* rows_bf16, int32_t batch, hoigen_stream_t stream);
+/* The same im2col for (B,3,h,w) images of any size -> rows (B*ceil(h/2)*ceil(w/2), 160): the stem of DETR's ResNet-50 backbone
+ * (detr/models/backbone.py:83-91, U:1594) is the same convolution on larger, padded images. */
+HOIGEN_API int hoigen_stem_im2col_hw(const float* images, void* rows_bf16, int32_t batch, int32_t h, int32_t w,
+                                     hoigen_stream_t stream);
 /* The same convolution fused with its BatchNorm-folded bias and ReLU as ONE tensor-core kernel without the im2col matrix:
  * images (B,3,224,224) fp32 -> out (B*112*112, 64) bf16 NHWC rows.  w: bf16 (64, 192), column = ky*24 + kx*3 + c (each
  * ky run of 21 taps padded to 24, 168..191 zero); bias (64) fp32. */
 HOIGEN_API int hoigen_stem_conv(const float* images, const void* w_bf16, const float* bias, void* out_bf16, int32_t batch,
                                 hoigen_stream_t stream);
-/* MaxPool2d(3, stride 2, padding 1): in (B,h,w,c) bf16 without halo -> out (B, h/2+2, w/2+2, c) with the zero halo */
+/* MaxPool2d(3, stride 2, padding 1): in (B,h,w,c) bf16 without halo -> out (B, ceil(h/2)+2, ceil(w/2)+2, c) with the zero halo */
 HOIGEN_API int hoigen_maxpool3x3s2_halo(const void* in_bf16, void* out_bf16, int32_t batch, int32_t h, int32_t w, int32_t c,
                                         hoigen_stream_t stream);
-/* A operand of the stride-2 convolutions: in (B, h+2, w+2, c) -> rows (B*(h/2+2)*(w/2+2), taps*c); taps = 9: 3x3 / pad 1,
+/* A operand of the stride-2 convolutions: in (B, h+2, w+2, c) -> rows (B*(ceil(h/2)+2)*(ceil(w/2)+2), taps*c); taps = 9: 3x3 / pad 1,
  * column = (ky*3+kx)*c + channel; taps = 1: the 1x1 shortcut.  Rows of the output ring are zeros. */
 HOIGEN_API int hoigen_conv_gather_s2(const void* in_bf16, void* rows_bf16, int32_t batch, int32_t h, int32_t w, int32_t c,
                                      int32_t taps, hoigen_stream_t stream);
@@ -475,7 +479,7 @@ HOIGEN_API int hoigen_avgpool_l2norm(const void* in_bf16, float* out, int32_t ba
 
 typedef enum {
   HOIGEN_CONV_OP_GEMM = 0,            /* gemm                                   */
-  HOIGEN_CONV_OP_STEM_IM2COL = 1,     /* in = images, out = rows, batch          */
+  HOIGEN_CONV_OP_STEM_IM2COL = 1,     /* in = images, out = rows, batch, (h, w: image size, 0 = 224) */
   HOIGEN_CONV_OP_MAXPOOL = 2,         /* in, out, batch, h, w, c                 */
   HOIGEN_CONV_OP_GATHER_S2 = 3,       /* in, out, batch, h, w, c, taps           */
   HOIGEN_CONV_OP_AVGPOOL_L2NORM = 4,  /* in, out (fp32), batch, h, w, c          */
