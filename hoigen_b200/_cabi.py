@@ -219,6 +219,8 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_conv_gather_s2": [_P, _P, _I, _I, _I, _I, _I, _P],
     "hoigen_avgpool_l2norm": [_P, _P, _I, _I, _I, _I, _P],
     "hoigen_conv_plan_run": [_P, _I, _P],
+    "hoigen_add_layernorm256": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
+    "hoigen_attention_heads32": [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _F, _P],
     "hoigen_prepare_proposals": [_P, _P, _P, _I, _I, _L, _F, _I, _I, _F, _P, _P, _P, _P, _P],
     "hoigen_associate_pairs": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P],
     "hoigen_pack_wire": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P, _P],

@@ -257,6 +257,16 @@ class UPT(nn.Module):
             backbone.body = KernelDetrBackboneBody(backbone.body)
         return self
 
+    def accelerate_detr(self) -> "UPT":
+        """Opt in: run the whole injected DETR detector of the proposal stage (U:1594-1599: ResNet-50 backbone body, position
+        encoding, input projection, 6 + 6-layer transformer, class / box heads) on this repo's kernels
+        (hoigen_b200.detr.KernelDetr: bf16 operands, fp32 residual stream; only the last decoder layer is produced, which is
+        all the forward reads).  The stock fp32 modules stay the default: bf16 scores can move proposals that sit next to the
+        0.2 score / 0.5 NMS thresholds."""
+        from .detr import KernelDetr
+        object.__setattr__(self, "_fast_detr", KernelDetr(self.detector))
+        return self
+
     def _apply(self, fn, *a, **k):
         self.invalidate_packed()
         self._ws = {}
@@ -757,11 +767,15 @@ class UPT(nn.Module):
             raise ValueError("UPT.forward needs the injected `detector` and `postprocessor` (U:303-304); "
                              "use forward_from_proposals for precomputed region proposals")
         nested = nested_tensor_from_tensor_list(images_orig)
-        features, pos = self.detector.backbone(nested)
-        src, mask = features[-1].decompose()
-        hs, _ = self.detector.transformer(self.detector.input_proj(src), mask, self.detector.query_embed.weight, pos[-1])
-        outputs_class = self.detector.class_embed(hs)
-        outputs_coord = self.detector.bbox_embed(hs).sigmoid()
+        if getattr(self, "_fast_detr", None) is not None:          # opt-in (accelerate_detr): the same detector on the repo's kernels
+            logits, coords = self._fast_detr(nested.tensors, nested.mask)
+            outputs_class, outputs_coord = logits[None], coords[None]
+        else:
+            features, pos = self.detector.backbone(nested)
+            src, mask = features[-1].decompose()
+            hs, _ = self.detector.transformer(self.detector.input_proj(src), mask, self.detector.query_embed.weight, pos[-1])
+            outputs_class = self.detector.class_embed(hs)
+            outputs_coord = self.detector.bbox_embed(hs).sigmoid()
         if self.dataset == "vcoco" and outputs_class.shape[-1] == 92:                 # U:1600-1602
             outputs_class = outputs_class[..., self.reserve_indices.to(outputs_class.device)]
             assert outputs_class.shape[-1] == 81, "reserved shape NOT match 81"

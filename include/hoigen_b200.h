@@ -495,6 +495,23 @@ typedef struct {
 /* Launches ops[0..n_ops) in order on `stream`; stops at the first error. */
 HOIGEN_API int hoigen_conv_plan_run(const hoigen_conv_op* ops, int32_t n_ops, hoigen_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * f3, second half: the DETR transformer behind U:1596 (detr/models/transformer.py; d_model 256, 8 heads of 32, post-norm).
+ * Every nn.Linear is hoigen_gemm_bf16; these are the two row kernels between them.
+ * ---------------------------------------------------------------------------------------------- */
+/* x (rows,256) fp32 in place:  x += delta (bf16, may be NULL) ; x = LayerNorm(x) * gamma + beta (eps 1e-5; gamma = beta = NULL:
+ * no normalisation) -- `src = norm(src + dropout(src2))` of forward_post (transformer.py:143-149, 200-208).  Side outputs for the
+ * next products: x_bf16 = bf16(x) and xpos_bf16 = bf16(x + pos[row % pos_rows]) = `with_pos_embed` (transformer.py:124-125); either may be NULL. */
+HOIGEN_API int hoigen_add_layernorm256(float* x, const void* delta_bf16, const float* gamma, const float* beta, const float* pos,
+                                       int32_t pos_rows, void* x_bf16, void* xpos_bf16, int32_t rows, hoigen_stream_t stream);
+/* nn.MultiheadAttention's core for head_dim 32: out[b, i, h*32:(h+1)*32] = softmax_j(q_i . k_j * scale  [-inf where
+ * key_mask[b, j] != 0]) v_j, per image b and head h.  q (batch*lq, ldq), k / v (batch*lk, ldk / ldv), out (batch*lq, ldo): bf16 rows,
+ * head h in columns [32 h, 32 h + 32); pitches in elements (multiples of 8).  key_mask (batch, lk) uint8 or NULL
+ * (key_padding_mask, transformer.py:139,193). */
+HOIGEN_API int hoigen_attention_heads32(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                                        void* out, int32_t ldo, const uint8_t* key_mask, int32_t batch, int32_t lq, int32_t lk,
+                                        int32_t heads, float scale, hoigen_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
