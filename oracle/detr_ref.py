@@ -81,11 +81,30 @@ class _Transformer(nn.Module):
         self.encoder = _Stack([EncoderLayer(d, heads, ff) for _ in range(enc)])
         self.decoder = _Stack([DecoderLayer(d, heads, ff) for _ in range(dec)], nn.LayerNorm(d))
 
+    def forward(self, src, mask, query_embed, pos_embed):
+        """transformer.py:46-60 (only the last decoder layer is returned, stacked as one: all U:1604 reads)."""
+        bs, c, h, w = src.shape
+        x = src.flatten(2).permute(2, 0, 1)
+        pos = pos_embed.flatten(2).permute(2, 0, 1)
+        qpos = query_embed.unsqueeze(1).repeat(1, bs, 1)
+        kpm = mask.flatten(1)
+        for layer in self.encoder.layers:
+            x = layer(x, kpm, pos)
+        tgt = torch.zeros_like(qpos)
+        for layer in self.decoder.layers:
+            tgt = layer(tgt, x, kpm, pos, qpos)
+        return self.decoder.norm(tgt).transpose(0, 1)[None], x.permute(1, 2, 0).view(bs, c, h, w)
+
 
 class _MLP(nn.Module):
     def __init__(self, d):
         super().__init__()
         self.layers = nn.ModuleList([nn.Linear(d, d), nn.Linear(d, d), nn.Linear(d, 4)])
+
+    def forward(self, x):
+        for i, lin in enumerate(self.layers):
+            x = F.relu(lin(x)) if i < 2 else lin(x)
+        return x
 
 
 class DetrRef(nn.Module):

@@ -139,3 +139,64 @@ def test_detr_full_detector_matches_stock_modules(cuda_device):
     el, eb = (logits - ref_logits).abs().max().item(), (boxes - ref_boxes).abs().max().item()
     print(f"full DETR on kernels vs stock fp32: logits max-abs {el:.3e} (|ref| <= {ref_logits.abs().max().item():.2f}), boxes {eb:.3e}")
     assert el < 1e-1 and eb < 1e-2, (el, eb)
+
+
+def test_upt_forward_with_accelerated_detr(cuda_device):
+    """UPT.forward (U:1543-1664) with `accelerate_detr()`: the padded NestedTensor batch goes through KernelDetr instead of
+    detector.backbone / transformer / heads; what reaches the post-processor (pred_logits, pred_boxes of the last decoder layer)
+    matches the stock fp32 modules' run of the same forward, and the detections come out through the normal path."""
+    import torchvision
+    from torchvision.models._utils import IntermediateLayerGetter
+    from torchvision.ops.misc import FrozenBatchNorm2d
+    from hoigen_b200 import synthetic as S
+    from hoigen_b200.detector import _NestedTensor
+    from hoigen_b200.detr import sine_position_embedding
+    from test_gpu_e2e import _build
+    m, enc, head = _build(117, 256, cuda_device)
+    torch.manual_seed(6)
+    det = _seeded_detr(cuda_device)
+    r50 = torchvision.models.resnet50(weights=None, norm_layer=FrozenBatchNorm2d)
+
+    class BackboneBase(torch.nn.Module):                         # detr/models/backbone.py:60-80
+        def __init__(self):
+            super().__init__()
+            self.body = IntermediateLayerGetter(r50, return_layers={"layer4": "0"})
+
+        def forward(self, nested):
+            x = self.body(nested.tensors)["0"]
+            mk = torch.nn.functional.interpolate(nested.mask[None].float(), size=x.shape[-2:]).to(torch.bool)[0]
+            return {"0": _NestedTensor(x, mk)}
+
+    class Joiner(torch.nn.Sequential):                           # detr/models/backbone.py:94-107
+        def forward(self, nested):
+            xs = self[0](nested)
+            out = list(xs.values())
+            return out, [sine_position_embedding(x.mask).permute(0, 3, 1, 2) for x in out]
+
+    det.backbone = Joiner(BackboneBase(), torch.nn.Identity()).to(cuda_device).eval()
+    gold = np.load("tests/golden/proposals.npz")
+    results = [dict(scores=torch.from_numpy(gold[f"in_scores_{b}"]).to(cuda_device), labels=torch.from_numpy(gold[f"in_labels_{b}"]).to(cuda_device),
+                    boxes=torch.from_numpy(gold[f"in_boxes_{b}"]).to(cuda_device)) for b in range(2)]
+    seen = []
+
+    class PP(torch.nn.Module):
+        def forward(self, outputs, sizes):
+            seen.append({k: v.clone() for k, v in outputs.items()})
+            return results
+
+    m.detector, m.postprocessor = det, PP()
+    imgs = S.make_images(2, seed=7).to(cuda_device)
+    dino = S.make_dino_features(2).to(cuda_device)
+    m.dino_model = lambda x: dino
+    batch = [(torch.randn(3, 200, 264, device=cuda_device), imgs[0]), (torch.randn(3, 168, 224, device=cuda_device), imgs[1])]
+    dets_stock = m(batch)
+    m.accelerate_detr()
+    dets_fast = m(batch)
+    assert len(seen) == 2 and seen[0]["pred_logits"].shape == seen[1]["pred_logits"].shape == (2, 100, 92)
+    el = (seen[0]["pred_logits"] - seen[1]["pred_logits"]).abs().max().item()
+    eb = (seen[0]["pred_boxes"] - seen[1]["pred_boxes"]).abs().max().item()
+    print(f"UPT.forward, accelerated DETR vs stock: pred_logits max-abs {el:.3e}, pred_boxes {eb:.3e}")
+    assert 0 < el < 1e-1 and eb < 1e-2, (el, eb)
+    for a, b in zip(dets_stock, dets_fast):                       # same (stubbed) proposals -> identical detections
+        for k in ("pairing", "labels", "objects", "scores"):
+            assert torch.equal(a[k], b[k]), k
