@@ -215,6 +215,7 @@ _SIGNATURES: dict[str, list] = {
     "hoigen_stem_im2col": [_P, _P, _I, _P],
     "hoigen_stem_im2col_hw": [_P, _P, _I, _I, _I, _P],
     "hoigen_stem_conv": [_P, _P, _P, _P, _I, _P],
+    "hoigen_stem_conv_hw": [_P, _P, _P, _P, _I, _I, _I, _P],
     "hoigen_maxpool3x3s2_halo": [_P, _P, _I, _I, _I, _I, _P],
     "hoigen_conv_gather_s2": [_P, _P, _I, _I, _I, _I, _I, _P],
     "hoigen_avgpool_l2norm": [_P, _P, _I, _I, _I, _I, _P],

@@ -267,7 +267,8 @@ int hoigen_conv_plan_run(const hoigen_conv_op* ops, int32_t n_ops, hoigen_stream
                                   : hoigen_stem_im2col(reinterpret_cast<const float*>(o.in), o.out, o.batch, stream);
         break;
       case HOIGEN_CONV_OP_STEM_CONV:
-        rc = hoigen_stem_conv(reinterpret_cast<const float*>(o.in), o.gemm.w, o.gemm.bias, o.out, o.batch, stream);
+        rc = hoigen_stem_conv_hw(reinterpret_cast<const float*>(o.in), o.gemm.w, o.gemm.bias, o.out, o.batch, o.h > 0 ? o.h : 224,
+                                 o.w > 0 ? o.w : 224, stream);
         break;
       case HOIGEN_CONV_OP_MAXPOOL: rc = hoigen_maxpool3x3s2_halo(o.in, o.out, o.batch, o.h, o.w, o.c, stream); break;
       case HOIGEN_CONV_OP_GATHER_S2: rc = hoigen_conv_gather_s2(o.in, o.out, o.batch, o.h, o.w, o.c, o.taps, stream); break;

@@ -17,7 +17,7 @@ namespace hoigen {
 
 constexpr int DM = 256;        // d_model
 constexpr int DH = 32;         // head dimension
-constexpr int ATT_Q = 128;     // queries per CTA
+constexpr int ATT_Q = 128;     // queries per CTA (one per thread)
 constexpr int ATT_K = 64;      // keys per shared-memory tile
 
 __global__ void __launch_bounds__(256) add_layernorm256_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
@@ -88,49 +88,41 @@ __global__ void __launch_bounds__(256) add_layernorm256_kernel(float* __restrict
   }
 }
 
-// Two queries per thread (rows t and t + 64 of the CTA's 128), 128 queries of one (image, head) per CTA; keys / values stream
-// through shared memory 64 at a time as fp32; the scores of 8 keys are formed, the running maximum / sum / output rescaled once
-// per 8 (online softmax).  All lanes of a warp read the same key / value element, so every shared-memory read is a broadcast,
-// and each one feeds both of the thread's queries (with one query per thread the kernel was bound by those reads: 16 LDS.128
-// per 64 FMAs).
-constexpr int ATT_THREADS = ATT_Q / 2;
-
-__global__ void __launch_bounds__(ATT_THREADS) attention_heads32_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
-                                                                         const __nv_bfloat16* __restrict__ k, int ldk,
-                                                                         const __nv_bfloat16* __restrict__ v, int ldv,
-                                                                         __nv_bfloat16* __restrict__ out, int ldo,
-                                                                         const uint8_t* __restrict__ key_mask, int lq, int lk,
-                                                                         float scale_log2e) {
+// One thread per query, 128 queries of one (image, head) per CTA; keys / values stream through shared memory 64 at a time as
+// fp32; the scores of 8 keys are formed, the running maximum / sum / output rescaled once per 8 (online softmax).  All lanes of
+// a warp read the same key / value element, so every shared-memory read is a broadcast.
+__global__ void __launch_bounds__(ATT_Q) attention_heads32_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
+                                                                   const __nv_bfloat16* __restrict__ k, int ldk,
+                                                                   const __nv_bfloat16* __restrict__ v, int ldv,
+                                                                   __nv_bfloat16* __restrict__ out, int ldo,
+                                                                   const uint8_t* __restrict__ key_mask, int lq, int lk, float scale_log2e) {
   __shared__ __align__(16) float s_k[ATT_K][DH];
   __shared__ __align__(16) float s_v[ATT_K][DH];
   __shared__ float s_bias[ATT_K];          // 0 or -inf (masked / past the end)
   const int b = blockIdx.z, h = blockIdx.y;
-  int qi[2];
-  bool q_ok[2];
-  float qr[2][DH], o[2][DH];
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    qi[u] = blockIdx.x * ATT_Q + u * ATT_THREADS + threadIdx.x;
-    q_ok[u] = qi[u] < lq;
-    const __nv_bfloat16* qp = q + (size_t(b) * lq + (q_ok[u] ? qi[u] : 0)) * ldq + h * DH;
+  const int qi = blockIdx.x * ATT_Q + threadIdx.x;
+  const bool q_ok = qi < lq;
+  float qr[DH], o[DH];
+  {
+    const __nv_bfloat16* qp = q + (size_t(b) * lq + (q_ok ? qi : 0)) * ldq + h * DH;
 #pragma unroll
     for (int c = 0; c < DH / 8; ++c) {
       const uint4 w = __ldg(reinterpret_cast<const uint4*>(qp) + c);
       const uint32_t w4[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        qr[u][c * 8 + 2 * e] = __uint_as_float(w4[e] << 16) * scale_log2e;
-        qr[u][c * 8 + 2 * e + 1] = __uint_as_float(w4[e] & 0xffff0000u) * scale_log2e;
+        qr[c * 8 + 2 * e] = __uint_as_float(w4[e] << 16) * scale_log2e;
+        qr[c * 8 + 2 * e + 1] = __uint_as_float(w4[e] & 0xffff0000u) * scale_log2e;
       }
     }
-#pragma unroll
-    for (int d = 0; d < DH; ++d) o[u][d] = 0.f;
   }
-  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+#pragma unroll
+  for (int d = 0; d < DH; ++d) o[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
   for (int k0 = 0; k0 < lk; k0 += ATT_K) {
     __syncthreads();                       // the previous tile has been consumed
     // ---- stage 64 keys / values of this head: 64 rows x 4 chunks of 8 bf16 each for K and for V = 512 chunk loads ----
-    for (int i = threadIdx.x; i < ATT_K * (DH / 8) * 2; i += ATT_THREADS) {
+    for (int i = threadIdx.x; i < ATT_K * (DH / 8) * 2; i += ATT_Q) {
       const int which = i / (ATT_K * (DH / 8)), r = (i / (DH / 8)) % ATT_K, c = i % (DH / 8);
       const int kj = k0 + r;
       uint4 w = make_uint4(0, 0, 0, 0);
@@ -146,73 +138,60 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_heads32_kernel(const __
         dst[2 * e + 1] = __uint_as_float(w4[e] & 0xffff0000u);
       }
     }
-    {
-      const int kj = k0 + threadIdx.x;     // ATT_THREADS == ATT_K
+    if (threadIdx.x < ATT_K) {
+      const int kj = k0 + threadIdx.x;
       const bool dead = kj >= lk || (key_mask != nullptr && key_mask[size_t(b) * lk + kj] != 0);
       s_bias[threadIdx.x] = dead ? -INFINITY : 0.f;
     }
     __syncthreads();
 #pragma unroll 1
     for (int j0 = 0; j0 < ATT_K; j0 += 8) {
-      float s[2][8];
-      float cmax[2] = {-INFINITY, -INFINITY};
+      float s[8];
+      float cmax = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float a0 = 0.f, a1 = 0.f;
+        float acc = 0.f;
 #pragma unroll
         for (int d4 = 0; d4 < DH / 4; ++d4) {
           const float4 kk = *reinterpret_cast<const float4*>(&s_k[j0 + j][d4 * 4]);
-          a0 = fmaf(qr[0][d4 * 4], kk.x, a0); a0 = fmaf(qr[0][d4 * 4 + 1], kk.y, a0);
-          a0 = fmaf(qr[0][d4 * 4 + 2], kk.z, a0); a0 = fmaf(qr[0][d4 * 4 + 3], kk.w, a0);
-          a1 = fmaf(qr[1][d4 * 4], kk.x, a1); a1 = fmaf(qr[1][d4 * 4 + 1], kk.y, a1);
-          a1 = fmaf(qr[1][d4 * 4 + 2], kk.z, a1); a1 = fmaf(qr[1][d4 * 4 + 3], kk.w, a1);
+          acc = fmaf(qr[d4 * 4], kk.x, acc); acc = fmaf(qr[d4 * 4 + 1], kk.y, acc);
+          acc = fmaf(qr[d4 * 4 + 2], kk.z, acc); acc = fmaf(qr[d4 * 4 + 3], kk.w, acc);
         }
-        const float bias = s_bias[j0 + j];
-        s[0][j] = a0 + bias; s[1][j] = a1 + bias;
-        cmax[0] = fmaxf(cmax[0], s[0][j]); cmax[1] = fmaxf(cmax[1], s[1][j]);
+        s[j] = acc + s_bias[j0 + j];
+        cmax = fmaxf(cmax, s[j]);
       }
-      if (cmax[0] == -INFINITY && cmax[1] == -INFINITY) continue;   // (the mask does not depend on the query: all 8 keys dead)
-      float p[2][8];
+      if (cmax == -INFINITY) continue;     // (warp-uniform: the mask does not depend on the query)
+      const float m_new = fmaxf(m, cmax);
+      const float corr = exp2f(m - m_new); // m = -inf on the first live chunk: exp2(-inf) = 0
+      m = m_new;
+      l *= corr;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float m_new = fmaxf(m[u], cmax[u]);
-        const float corr = exp2f(m[u] - m_new);   // m = -inf on the first live chunk: exp2(-inf) = 0
-        m[u] = m_new;
-        l[u] *= corr;
-#pragma unroll
-        for (int d = 0; d < DH; ++d) o[u][d] *= corr;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { p[u][j] = exp2f(s[u][j] - m_new); l[u] += p[u][j]; }
-      }
+      for (int d = 0; d < DH; ++d) o[d] *= corr;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        const float p = exp2f(s[j] - m);
+        l += p;
 #pragma unroll
         for (int d4 = 0; d4 < DH / 4; ++d4) {
           const float4 vv = *reinterpret_cast<const float4*>(&s_v[j0 + j][d4 * 4]);
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            o[u][d4 * 4] = fmaf(p[u][j], vv.x, o[u][d4 * 4]); o[u][d4 * 4 + 1] = fmaf(p[u][j], vv.y, o[u][d4 * 4 + 1]);
-            o[u][d4 * 4 + 2] = fmaf(p[u][j], vv.z, o[u][d4 * 4 + 2]); o[u][d4 * 4 + 3] = fmaf(p[u][j], vv.w, o[u][d4 * 4 + 3]);
-          }
+          o[d4 * 4] = fmaf(p, vv.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p, vv.y, o[d4 * 4 + 1]);
+          o[d4 * 4 + 2] = fmaf(p, vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p, vv.w, o[d4 * 4 + 3]);
         }
       }
     }
   }
+  if (!q_ok) return;
+  const float inv = l > 0.f ? 1.0f / l : 0.f;   // every key masked: zeros (torch gives NaN; DETR never masks a whole row)
+  __nv_bfloat16* op = out + (size_t(b) * lq + qi) * ldo + h * DH;
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    if (!q_ok[u]) continue;
-    const float inv = l[u] > 0.f ? 1.0f / l[u] : 0.f;   // every key masked: zeros (torch gives NaN; DETR never masks a whole row)
-    __nv_bfloat16* op = out + (size_t(b) * lq + qi[u]) * ldo + h * DH;
+  for (int c = 0; c < DH / 8; ++c) {
+    uint32_t p[4];
 #pragma unroll
-    for (int c = 0; c < DH / 8; ++c) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(o[u][c * 8 + 2 * e] * inv, o[u][c * 8 + 2 * e + 1] * inv);
-        pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      }
-      *(reinterpret_cast<uint4*>(op) + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(o[c * 8 + 2 * e] * inv, o[c * 8 + 2 * e + 1] * inv);
+      p[e] = *reinterpret_cast<const uint32_t*>(&hh);
     }
+    *(reinterpret_cast<uint4*>(op) + c) = make_uint4(p[0], p[1], p[2], p[3]);
   }
 }
 
@@ -249,7 +228,7 @@ int hoigen_attention_heads32(const void* q, int32_t ldq, const void* k, int32_t 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   KernelScope ks("attention_heads32", s, 4.0 * batch * heads * double(lq) * lk * DH,
                  2.0 * batch * heads * DH * (2.0 * lq + 2.0 * lk * ((lq + ATT_Q - 1) / ATT_Q)));
-  attention_heads32_kernel<<<dim3((lq + ATT_Q - 1) / ATT_Q, heads, batch), ATT_THREADS, 0, s>>>(
+  attention_heads32_kernel<<<dim3((lq + ATT_Q - 1) / ATT_Q, heads, batch), ATT_Q, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(k), ldk,
       reinterpret_cast<const __nv_bfloat16*>(v), ldv, reinterpret_cast<__nv_bfloat16*>(out), ldo, key_mask, lq, lk,
       scale * 1.4426950408889634f);

@@ -135,7 +135,7 @@ class KernelResNet50(nn.Module):
         w_runs[:, :, :21] = w7.permute(0, 2, 3, 1).reshape(64, 7, 21)
         self.stem_fused = (torch.nn.functional.pad(w_runs.reshape(64, 168), (0, 24)).to(torch.bfloat16).contiguous(), self.stem[1])
         self._keep.append(self.stem_fused[0])
-        self.fused_stem = True                         # 224 x 224 inputs only
+        self.fused_stem = True                         # False: the two-step form (im2col + GEMM)
         self.stages = []
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             blocks = []
@@ -180,9 +180,9 @@ class KernelResNet50(nn.Module):
         half = lambda v: (v + 1) // 2
         H1, W1 = half(Hi), half(Wi)                    # stem output
         stem_out = new(B * H1 * W1, 64)
-        if self.fused_stem and (Hi, Wi) == (224, 224):
+        if self.fused_stem:
             op = _cabi.ConvOp()
-            op.kind, op.out, op.batch = _cabi.CONV_OP_STEM_CONV, stem_out.data_ptr(), B
+            op.kind, op.out, op.batch, op.h, op.w = _cabi.CONV_OP_STEM_CONV, stem_out.data_ptr(), B, Hi, Wi
             op.gemm.w, op.gemm.bias = self.stem_fused[0].data_ptr(), self.stem_fused[1].data_ptr()
             ops.append(op)
         else:

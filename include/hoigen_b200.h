@@ -466,6 +466,9 @@ HOIGEN_API int hoigen_stem_im2col_hw(const float* images, void* rows_bf16, int32
  * ky run of 21 taps padded to 24, 168..191 zero); bias (64) fp32. */
 HOIGEN_API int hoigen_stem_conv(const float* images, const void* w_bf16, const float* bias, void* out_bf16, int32_t batch,
                                 hoigen_stream_t stream);
+/* The same kernel for (B,3,h,w) images of any size -> out (B*ceil(h/2)*ceil(w/2), 64)  (DETR's backbone stem, U:1594). */
+HOIGEN_API int hoigen_stem_conv_hw(const float* images, const void* w_bf16, const float* bias, void* out_bf16, int32_t batch,
+                                   int32_t h, int32_t w, hoigen_stream_t stream);
 /* MaxPool2d(3, stride 2, padding 1): in (B,h,w,c) bf16 without halo -> out (B, ceil(h/2)+2, ceil(w/2)+2, c) with the zero halo */
 HOIGEN_API int hoigen_maxpool3x3s2_halo(const void* in_bf16, void* out_bf16, int32_t batch, int32_t h, int32_t w, int32_t c,
                                         hoigen_stream_t stream);
@@ -483,7 +486,7 @@ typedef enum {
   HOIGEN_CONV_OP_MAXPOOL = 2,         /* in, out, batch, h, w, c                 */
   HOIGEN_CONV_OP_GATHER_S2 = 3,       /* in, out, batch, h, w, c, taps           */
   HOIGEN_CONV_OP_AVGPOOL_L2NORM = 4,  /* in, out (fp32), batch, h, w, c          */
-  HOIGEN_CONV_OP_STEM_CONV = 5        /* in = images, out, batch, gemm.w, gemm.bias */
+  HOIGEN_CONV_OP_STEM_CONV = 5        /* in = images, out, batch, gemm.w, gemm.bias, (h, w: image size, 0 = 224) */
 } hoigen_conv_op_kind;
 typedef struct {
   int32_t kind;

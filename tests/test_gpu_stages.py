@@ -708,6 +708,22 @@ def test_conv_row_kernels(cuda_device):
         ref_f = torch.relu(torch.nn.functional.conv2d(img[:nb].to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, stride=2, padding=3))
         got_f = fused.float().view(nb, 112, 112, 64).permute(0, 3, 1, 2)
         assert (got_f - ref_f).abs().max().item() <= 1e-2 * max(1.0, ref_f.abs().max().item()), (got_f - ref_f).abs().max().item()
+    # the same kernel at other image sizes (DETR's padded batches: odd, wider than one 128-pixel block, taller than a row group)
+    for (hh, ww) in ((97, 130), (250, 333), (64, 700)):
+        im = torch.randn(2, 3, hh, ww, device=cuda_device)
+        ho, wo = (hh + 1) // 2, (ww + 1) // 2
+        fused = torch.full((2 * ho * wo, 64), 7.0, device=cuda_device, dtype=torch.bfloat16)
+        _cabi.check(lib.hoigen_stem_conv_hw(_cabi.ptr(im), _cabi.ptr(w_fused), _cabi.ptr(bias), _cabi.ptr(fused), 2, hh, ww,
+                                            _cabi.stream_ptr()), "stem_conv_hw")
+        ref_f = torch.relu(torch.nn.functional.conv2d(im.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, stride=2, padding=3))
+        got_f = fused.float().view(2, ho, wo, 64).permute(0, 3, 1, 2)
+        assert got_f.shape == ref_f.shape
+        assert (got_f - ref_f).abs().max().item() <= 1e-2 * max(1.0, ref_f.abs().max().item()), ((hh, ww), (got_f - ref_f).abs().max().item())
+        rows_hw = torch.empty(2 * ho * wo, 160, device=cuda_device, dtype=torch.bfloat16)          # and the general im2col form
+        _cabi.check(lib.hoigen_stem_im2col_hw(_cabi.ptr(im), _cabi.ptr(rows_hw), 2, hh, ww, _cabi.stream_ptr()), "stem_im2col_hw")
+        got_i = (rows_hw.float() @ wk.t()).view(2, ho, wo, 64).permute(0, 3, 1, 2)
+        ref_i = torch.nn.functional.conv2d(im.to(torch.bfloat16).float(), w, stride=2, padding=3)
+        assert (got_i - ref_i).abs().max().item() <= 1e-3 * max(1.0, ref_i.abs().max().item())
     # max-pool
     a = torch.randn(B, 64, 112, 112, device=cuda_device).to(torch.bfloat16)
     a_rows = a.permute(0, 2, 3, 1).contiguous()
