@@ -11,7 +11,10 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "common.h"
+#include "ptx.cuh"
 
 namespace hoigen {
 
@@ -195,6 +198,183 @@ __global__ void __launch_bounds__(ATT_Q) attention_heads32_kernel(const __nv_bfl
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// The same attention on the tensor cores: one CTA = 128 queries of one (image, head), keys in blocks of 128.
+//   S = Q K^T      UMMA 128 x 128 x 16, two k-steps (head_dim 32), operands staged by the threads into 128B-swizzled tiles
+//   softmax        thread = query row: S row read from TMEM, online max / sum, P = exp2(.) written as bf16 into the A tile of
+//   O_blk = P V    UMMA 128 x 64 x 16, eight k-steps, V consumed MN-major straight from its key rows (rows padded to 64 columns);
+//                  the block's 128 x 32 result is read back and accumulated in registers with the running rescale
+// The next block's key / value rows are fetched into registers while the current block is being processed.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int AT2_THREADS = 128;
+constexpr int AT2_KB = 128;                 // keys per block
+constexpr int AT2_Q = 0;                    // 16 KiB  Q tile   [128 rows x 128 B], 64 B of each row used
+constexpr int AT2_K = 16384;                // 16 KiB  K tile   [128 keys x 128 B]
+constexpr int AT2_V = 32768;                // 16 KiB  V tile   [128 keys x 128 B], columns 32..63 zero
+constexpr int AT2_P = 49152;                // 32 KiB  P tile   [128 rows x 128 keys] as two 64-key k-blocks
+constexpr int AT2_BIAS = 81920;             // 128 floats
+constexpr int AT2_BAR = AT2_BIAS + 512;
+constexpr int AT2_SMEM_BYTES = AT2_BAR + 64 + 1024;
+
+__global__ void __launch_bounds__(AT2_THREADS) attention_heads32_tc_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
+                                                                            const __nv_bfloat16* __restrict__ k, int ldk,
+                                                                            const __nv_bfloat16* __restrict__ v, int ldv,
+                                                                            __nv_bfloat16* __restrict__ out, int ldo,
+                                                                            const uint8_t* __restrict__ key_mask, int lq, int lk,
+                                                                            float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  float* s_bias = reinterpret_cast<float*>(sm + AT2_BIAS);
+  const uint32_t bar = base + AT2_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + AT2_BAR + 16);
+  const int t = threadIdx.x, warp = t >> 5;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int qi = blockIdx.x * 128 + t;
+
+  if (t == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 128);
+    tmem_relinquish();
+  }
+  // Q row -> A tile (this thread's row, four 16-byte chunks); the V tile's unused upper half is zeroed once
+  {
+    const __nv_bfloat16* qp = q + (size_t(b) * lq + (qi < lq ? qi : 0)) * ldq + h * DH;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(sm + AT2_Q + sw128_offset(uint32_t(t), uint32_t(c))) = __ldg(reinterpret_cast<const uint4*>(qp) + c);
+#pragma unroll
+    for (int c = 4; c < 8; ++c) *reinterpret_cast<uint4*>(sm + AT2_V + sw128_offset(uint32_t(t), uint32_t(c))) = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_row = tmem + (uint32_t(warp * 32) << 16);
+
+  float o[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) o[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  uint32_t phase = 0;
+
+  // this thread's key / value row of a block -> registers
+  uint4 kr[4], vr[4];
+  bool dead = true;
+  auto fetch = [&](int k0) {
+    const int kj = k0 + t;
+    dead = kj >= lk || (key_mask != nullptr && key_mask[size_t(b) * lk + kj] != 0);
+    if (kj < lk) {
+      const uint4* kp = reinterpret_cast<const uint4*>(k + (size_t(b) * lk + kj) * ldk + h * DH);
+      const uint4* vp = reinterpret_cast<const uint4*>(v + (size_t(b) * lk + kj) * ldv + h * DH);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { kr[c] = __ldg(kp + c); vr[c] = __ldg(vp + c); }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { kr[c] = make_uint4(0, 0, 0, 0); vr[c] = make_uint4(0, 0, 0, 0); }
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < lk; k0 += AT2_KB) {
+    // ---- stage this block's rows (the previous block's MMAs have completed: both were waited for below) ----
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      *reinterpret_cast<uint4*>(sm + AT2_K + sw128_offset(uint32_t(t), uint32_t(c))) = kr[c];
+      *reinterpret_cast<uint4*>(sm + AT2_V + sw128_offset(uint32_t(t), uint32_t(c))) = vr[c];
+    }
+    s_bias[t] = dead ? -INFINITY : 0.f;
+    if (k0 + AT2_KB < lk) fetch(k0 + AT2_KB);          // in flight during the MMAs and the softmax
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks)
+        umma_bf16_ss(tmem, make_sdesc_sw128(base + AT2_Q + ks * 32), make_sdesc_sw128(base + AT2_K + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
+      tc_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    // ---- online softmax of this row over the block's 128 keys; P -> A tile of the second product ----
+    float bmax = -INFINITY;
+    uint32_t r[32];
+#pragma unroll 1
+    for (int c4 = 0; c4 < 4; ++c4) {                   // pass 1: the block maximum
+      tmem_ld_32x32b_x32(t_row + uint32_t(c4 * 32), r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bmax = fmaxf(bmax, fmaf(__uint_as_float(r[j]), scale_log2e, s_bias[c4 * 32 + j]));
+    }
+    const float m_new = fmaxf(m, bmax);
+    const bool live = m_new != -INFINITY;              // false only while every key so far is masked
+    const float corr = live ? exp2f(m - m_new) : 1.f;
+    m = m_new;
+    l *= corr;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] *= corr;
+#pragma unroll 1
+    for (int c4 = 0; c4 < 4; ++c4) {                   // pass 2: probabilities
+      tmem_ld_32x32b_x32(t_row + uint32_t(c4 * 32), r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = g * 8 + 2 * e;
+          const float p0 = live ? exp2f(fmaf(__uint_as_float(r[j]), scale_log2e, s_bias[c4 * 32 + j]) - m_new) : 0.f;
+          const float p1 = live ? exp2f(fmaf(__uint_as_float(r[j + 1]), scale_log2e, s_bias[c4 * 32 + j + 1]) - m_new) : 0.f;
+          l += p0 + p1;
+          pk[e] = pack_bf16x2(p0, p1);
+        }
+        const int chunk = c4 * 4 + g;                  // 16-byte chunk (8 keys) of this row: k-block chunk / 8
+        *reinterpret_cast<uint4*>(sm + AT2_P + (chunk >> 3) * 16384 + sw128_offset(uint32_t(t), uint32_t(chunk & 7))) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, /*a_mn_major=*/0, /*b_mn_major=*/1);
+#pragma unroll
+      for (int ks = 0; ks < AT2_KB / 16; ++ks)
+        umma_bf16_ss(tmem, make_sdesc_sw128(base + AT2_P + (ks >> 2) * 16384 + (ks & 3) * 32),
+                     make_sdesc_sw128(base + AT2_V + ks * 2048), idesc_o, ks > 0 ? 1u : 0u);
+      tc_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    tmem_ld_32x32b_x32(t_row, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] += __uint_as_float(r[d]);
+    tc_fence_before();
+  }
+  if (qi < lq) {
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    __nv_bfloat16* op = out + (size_t(b) * lq + qi) * ldo + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 8; ++c)
+      *(reinterpret_cast<uint4*>(op) + c) = make_uint4(pack_bf16x2(o[c * 8] * inv, o[c * 8 + 1] * inv), pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv),
+                                                       pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv), pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv));
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
 }  // namespace hoigen
 
 extern "C" {
@@ -228,6 +408,16 @@ int hoigen_attention_heads32(const void* q, int32_t ldq, const void* k, int32_t 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   KernelScope ks("attention_heads32", s, 4.0 * batch * heads * double(lq) * lk * DH,
                  2.0 * batch * heads * DH * (2.0 * lq + 2.0 * lk * ((lq + ATT_Q - 1) / ATT_Q)));
+  static const bool simt = getenv("HOIGEN_ATT32_SIMT") != nullptr;      // A/B switch: the fp32 SIMT form
+  if (!simt) {
+    HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(attention_heads32_tc_kernel), AT2_SMEM_BYTES));
+    attention_heads32_tc_kernel<<<dim3((lq + 127) / 128, heads, batch), AT2_THREADS, AT2_SMEM_BYTES, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(k), ldk,
+        reinterpret_cast<const __nv_bfloat16*>(v), ldv, reinterpret_cast<__nv_bfloat16*>(out), ldo, key_mask, lq, lk,
+        scale * 1.4426950408889634f);
+    HOIGEN_CHECK_LAUNCH();
+    return HOIGEN_OK;
+  }
   attention_heads32_kernel<<<dim3((lq + ATT_Q - 1) / ATT_Q, heads, batch), ATT_Q, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(k), ldk,
       reinterpret_cast<const __nv_bfloat16*>(v), ldv, reinterpret_cast<__nv_bfloat16*>(out), ldo, key_mask, lq, lk,
