@@ -510,7 +510,8 @@ HOIGEN_API int hoigen_add_layernorm256(float* x, const void* delta_bf16, const f
 /* nn.MultiheadAttention's core for head_dim 32: out[b, i, h*32:(h+1)*32] = softmax_j(q_i . k_j * scale  [-inf where
  * key_mask[b, j] != 0]) v_j, per image b and head h.  q (batch*lq, ldq), k / v (batch*lk, ldk / ldv), out (batch*lq, ldo): bf16 rows,
  * head h in columns [32 h, 32 h + 32); pitches in elements (multiples of 8).  key_mask (batch, lk) uint8 or NULL
- * (key_padding_mask, transformer.py:139,193). */
+ * (key_padding_mask, transformer.py:139,193).  Online-softmax tcgen05 kernel (S = Q K^T in TMEM, P V with V read MN-major from its
+ * key rows); HOIGEN_ATT32_SIMT=1 selects the fp32 SIMT form. */
 HOIGEN_API int hoigen_attention_heads32(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                                         void* out, int32_t ldo, const uint8_t* key_mask, int32_t batch, int32_t lq, int32_t lk,
                                         int32_t heads, float scale, hoigen_stream_t stream);

@@ -38,8 +38,8 @@ def test_sass_contains_blackwell_instructions():
 
 
 def test_tensor_core_kernels_contain_utcmma():
-    """Per kernel: the GEMMs, attention, the adapter block, the fused cache kernel (both forms), the RoIAlign kernel and the
-    ResNet-50 stem convolution issue tcgen05.mma (SASS UTCHMMA) themselves."""
+    """Per kernel: the GEMMs, attention, the adapter block, the fused cache kernel (both forms), the RoIAlign kernel, the
+    ResNet-50 stem convolution and DETR's attention issue tcgen05.mma (SASS UTCHMMA) themselves."""
     import shutil
     import subprocess
     from hoigen_b200 import _build
@@ -53,7 +53,7 @@ def test_tensor_core_kernels_contain_utcmma():
         elif "UTCHMMA" in line and cur:
             counts[cur] = counts.get(cur, 0) + 1
     for kernel in ("gemm2_bf16_kernel", "gemm_bf16_kernel", "attention_kernel", "adapter_tc_kernel", "cache_fused_pair_kernel",
-                   "cache_fused_kernel", "roi_tc_kernel", "stem_conv_kernel"):
+                   "cache_fused_kernel", "roi_tc_kernel", "stem_conv_kernel", "attention_heads32_tc_kernel"):
         assert any(kernel in k and n > 0 for k, n in counts.items()), f"{kernel}: no UTCHMMA in its SASS"
 
 
