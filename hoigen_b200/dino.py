@@ -155,10 +155,22 @@ class KernelResNet50(nn.Module):
         ops: List[_cabi.ConvOp] = []
         bufs: List[torch.Tensor] = []
 
+        pool: Dict[tuple, list] = {}
+
         def new(rows, cols):
+            # every buffer is written in full by its producer (halo rows included) and the plan runs in order on one stream,
+            # so a buffer whose last reader has been enqueued can back a later tensor of the same shape
+            free_list = pool.get((rows, cols))
+            if free_list:
+                return free_list.pop()
             t = torch.zeros(rows, cols, **bf)
             bufs.append(t)
             return t
+
+        def release(*ts):
+            for t in ts:
+                if t is not None:
+                    pool.setdefault((t.shape[0], t.shape[1]), []).append(t)
 
         def gemm(a, wb, out, *, relu, halo=None, taps=0, res=None):
             op = _cabi.ConvOp()
@@ -189,9 +201,11 @@ class KernelResNet50(nn.Module):
             stem_rows = new(B * H1 * W1, self.STEM_K)
             rowop(_cabi.CONV_OP_STEM_IM2COL, None, stem_rows, Hi, Wi)
             gemm(stem_rows, self.stem, stem_out, relu=True)
+            release(stem_rows)
         H, W = half(H1), half(W1)                      # after the max-pool
         x = new(B * (H + 2) * (W + 2), 64)
         rowop(_cabi.CONV_OP_MAXPOOL, stem_out, x, H1, W1, 64)
+        release(stem_out)
         cin = 64
         for blocks in self.stages:
             for blk in blocks:
@@ -209,10 +223,12 @@ class KernelResNet50(nn.Module):
                     rowop(_cabi.CONV_OP_GATHER_S2, t1, g2, H, W, width, 9)
                     t2 = new(rows_out, width)
                     gemm(g2, blk["c2"], t2, relu=True, halo=halo_out)
+                    release(g2)
                     gs = new(rows_out, cin)
                     rowop(_cabi.CONV_OP_GATHER_S2, x, gs, H, W, cin, 1)
                     sc = new(rows_out, cout)
                     gemm(gs, blk["ds"], sc, relu=False, halo=halo_out)
+                    release(gs)
                     H, W = Ho, Wo
                 else:
                     halo_out, rows_out = halo_in, rows_in
@@ -225,6 +241,7 @@ class KernelResNet50(nn.Module):
                         sc = x
                 y = new(rows_out, cout)
                 gemm(t2, blk["c3"], y, relu=True, halo=halo_out, res=sc)
+                release(t1, t2, x, sc if sc is not x else None)
                 x, cin = y, cout
         out = None
         if head == "dino":
