@@ -201,18 +201,25 @@ __global__ void __launch_bounds__(ATT_Q) attention_heads32_kernel(const __nv_bfl
 // ---------------------------------------------------------------------------------------------------------------------------
 // The same attention on the tensor cores: one CTA = 128 queries of one (image, head), keys in blocks of 128.
 //   S = Q K^T      UMMA 128 x 128 x 16, two k-steps (head_dim 32), operands staged by the threads into 128B-swizzled tiles
-//   softmax        thread = query row: S row read from TMEM, online max / sum, P = exp2(.) written as bf16 into the A tile of
-//   O_blk = P V    UMMA 128 x 64 x 16, eight k-steps, V consumed MN-major straight from its key rows (rows padded to 64 columns);
-//                  the block's 128 x 32 result is read back and accumulated in registers with the running rescale
+//   softmax        thread = query row: S row read from TMEM, online max / sum, P = exp2(.) written back as packed bf16 OVER the
+//                  row's own S columns (tcgen05.st; 128 keys = 64 columns), so P never passes through shared memory
+//   O_blk = P V    UMMA 128 x 64 x 16 with A = P from TMEM, eight k-steps, V consumed MN-major straight from its key rows (rows
+//                  padded to 64 columns); the block's 128 x 32 result is read back and accumulated in registers with the
+//                  running rescale
 // The next block's key / value rows are fetched into registers while the current block is being processed.
 // ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_fast(float x) {   // MUFU.EX2 without exp2f's range fix-up (ex2(-inf) = 0, no denormal care needed)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int AT2_THREADS = 128;
 constexpr int AT2_KB = 128;                 // keys per block
 constexpr int AT2_Q = 0;                    // 16 KiB  Q tile   [128 rows x 128 B], 64 B of each row used
 constexpr int AT2_K = 16384;                // 16 KiB  K tile   [128 keys x 128 B]
 constexpr int AT2_V = 32768;                // 16 KiB  V tile   [128 keys x 128 B], columns 32..63 zero
-constexpr int AT2_P = 49152;                // 32 KiB  P tile   [128 rows x 128 keys] as two 64-key k-blocks
-constexpr int AT2_BIAS = 81920;             // 128 floats
+constexpr int AT2_BIAS = 49152;             // 128 floats   (P never touches shared memory: it overlays S in TMEM)
 constexpr int AT2_BAR = AT2_BIAS + 512;
 constexpr int AT2_SMEM_BYTES = AT2_BAR + 64 + 1024;
 
@@ -320,26 +327,24 @@ __global__ void __launch_bounds__(AT2_THREADS) attention_heads32_tc_kernel(const
 #pragma unroll
     for (int d = 0; d < DH; ++d) o[d] *= corr;
 #pragma unroll 1
-    for (int c4 = 0; c4 < 4; ++c4) {                   // pass 2: probabilities
-      tmem_ld_32x32b_x32(t_row + uint32_t(c4 * 32), r);
+    for (int c4 = 0; c4 < 4; ++c4) {                   // pass 2: probabilities; P chunk c4 (columns 16 c4 ..) lies inside S chunks
+      tmem_ld_32x32b_x32(t_row + uint32_t(c4 * 32), r);   // <= c4 of this row, all of which are in registers or consumed by now
       tmem_wait_ld();
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t pk[4];
+      for (int g = 0; g < 2; ++g) {
+        uint32_t pk[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = g * 8 + 2 * e;
-          const float p0 = live ? exp2f(fmaf(__uint_as_float(r[j]), scale_log2e, s_bias[c4 * 32 + j]) - m_new) : 0.f;
-          const float p1 = live ? exp2f(fmaf(__uint_as_float(r[j + 1]), scale_log2e, s_bias[c4 * 32 + j + 1]) - m_new) : 0.f;
+        for (int e = 0; e < 8; ++e) {
+          const int j = g * 16 + 2 * e;
+          const float p0 = live ? ex2_fast(fmaf(__uint_as_float(r[j]), scale_log2e, s_bias[c4 * 32 + j]) - m_new) : 0.f;
+          const float p1 = live ? ex2_fast(fmaf(__uint_as_float(r[j + 1]), scale_log2e, s_bias[c4 * 32 + j + 1]) - m_new) : 0.f;
           l += p0 + p1;
           pk[e] = pack_bf16x2(p0, p1);
         }
-        const int chunk = c4 * 4 + g;                  // 16-byte chunk (8 keys) of this row: k-block chunk / 8
-        *reinterpret_cast<uint4*>(sm + AT2_P + (chunk >> 3) * 16384 + sw128_offset(uint32_t(t), uint32_t(chunk & 7))) =
-            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        tmem_st_32x32b_x8(t_row + uint32_t(c4 * 16 + g * 8), pk);   // keys 32 c4 + 16 g .. + 15 -> 8 packed columns
       }
     }
-    fence_proxy_async_smem();
+    tmem_wait_st();
     tc_fence_before();
     __syncthreads();
     if (t == 0) {
@@ -347,14 +352,13 @@ __global__ void __launch_bounds__(AT2_THREADS) attention_heads32_tc_kernel(const
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, /*a_mn_major=*/0, /*b_mn_major=*/1);
 #pragma unroll
       for (int ks = 0; ks < AT2_KB / 16; ++ks)
-        umma_bf16_ss(tmem, make_sdesc_sw128(base + AT2_P + (ks >> 2) * 16384 + (ks & 3) * 32),
-                     make_sdesc_sw128(base + AT2_V + ks * 2048), idesc_o, ks > 0 ? 1u : 0u);
+        umma_bf16_ts(tmem + 64u, tmem + uint32_t(ks * 8), make_sdesc_sw128(base + AT2_V + ks * 2048), idesc_o, ks > 0 ? 1u : 0u);
       tc_commit(bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1u;
     tc_fence_after();
-    tmem_ld_32x32b_x32(t_row, r);
+    tmem_ld_32x32b_x32(t_row + 64u, r);
     tmem_wait_ld();
 #pragma unroll
     for (int d = 0; d < DH; ++d) o[d] += __uint_as_float(r[d]);
