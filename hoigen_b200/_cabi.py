@@ -34,6 +34,7 @@ class GemmParams(C.Structure):
         ("act_param", C.c_float), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("conv_taps", C.c_int32), ("conv_cin", C.c_int32), ("halo_h", C.c_int32), ("halo_w", C.c_int32),
         ("res_bf16", C.c_void_p), ("ld_resb", C.c_int32),
+        ("a2", C.c_void_p), ("lda2", C.c_int32), ("k2", C.c_int32),
     ]
 
 
@@ -266,7 +267,7 @@ def call(name: str, *args) -> None:
 
 def gemm_params(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act=ACT_NONE, residual=None,
                 out_f32=None, out_bf16=None, block_n: int = 0, split_k: int = 0, act_param: float = 0.0, ln_stats=None,
-                ln_colsum=None, conv_taps: int = 0, halo=None, res_bf16=None) -> "GemmParams":
+                ln_colsum=None, conv_taps: int = 0, halo=None, res_bf16=None, a2=None) -> "GemmParams":
     """Fill a hoigen_gemm_params from tensors (no launch).  conv_taps = 9: `a` is the (rows, cin) activation matrix with a
     zero halo, `w` is (N, 9 * cin); halo = (H + 2, W + 2); res_bf16 = bf16 identity added before the activation."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -278,6 +279,11 @@ def gemm_params(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, a
         assert w.shape[1] == 9 * K and halo is not None
         p.conv_taps, p.conv_cin = 9, K
         K = 9 * K
+    elif a2 is not None:        # second A source: w = [W1 | W2] along K
+        assert a2.dtype == torch.bfloat16 and a2.dim() == 2 and a2.stride(1) == 1 and a2.shape[0] == M
+        assert w.shape[1] == K + a2.shape[1] and K % 64 == 0
+        p.a2, p.lda2, p.k2 = a2.data_ptr(), a2.stride(0), a2.shape[1]
+        K = K + a2.shape[1]
     else:
         assert w.shape[1] == K
     p.a, p.w = a.data_ptr(), w.data_ptr()

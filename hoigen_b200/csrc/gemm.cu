@@ -69,6 +69,9 @@ struct GemmArgs {
   int halo_h, halo_w;       // rows on the ring of each (halo_h, halo_w) image are written as 0 (halo_w = 0: off)
   const __nv_bfloat16* res_bf16;   // added before the activation
   int ld_resb;
+  int a2_kb0;               // CTA-pair kernel: k-blocks >= a2_kb0 load their A tile from the second source (tmR); 0 = off
+  const __nv_bfloat16* a2;  // (SIMT cross-check only)
+  int lda2;
   int debug;  // diagnostics only (HOIGEN_GEMM_DEBUG): 1 = TMA loads without MMAs, 2 = MMAs without TMA loads
   // CTA-pair kernel work split (stream-K): work unit = one k-block of one tile; pair p owns units [bound(p), bound(p+1))
   float* sk_ws;     // fp32 partial-accumulator slots, one per (pair, cta rank)
@@ -773,7 +776,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             else mbar_arrive_leader(full);
             int a_col, a_row;
             a_coords(g, kb, m_blk * (2 * BM) + int(rank) * BM, a_col, a_row);
-            tma_load_2d_2sm(a_dst, &tmA, full, a_col, a_row);
+            if (g.a2_kb0 > 0 && kb >= g.a2_kb0) tma_load_2d_2sm(a_dst, &tmR, full, (kb - g.a2_kb0) * BK, a_row);   // second A source
+            else tma_load_2d_2sm(a_dst, &tmA, full, a_col, a_row);
             tma_load_2d_2sm(b_dst, &tmB, full, kb * BK, n_blk * BN + int(rank) * (BN / 2));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -957,8 +961,11 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ a, const __nv
         acc = fmaf(__bfloat162float(a[size_t(src) * lda + k]), __bfloat162float(w[size_t(n) * ldw + t * cin + k]), acc);
     }
   } else {
-    for (int k = 0; k < g.K; ++k)
+    const int k1 = g.a2_kb0 > 0 ? g.a2_kb0 * BK : g.K;
+    for (int k = 0; k < k1; ++k)
       acc = fmaf(__bfloat162float(a[size_t(m) * lda + k]), __bfloat162float(w[size_t(n) * ldw + k]), acc);
+    for (int k = k1; k < g.K; ++k)
+      acc = fmaf(__bfloat162float(g.a2[size_t(m) * g.lda2 + k - k1]), __bfloat162float(w[size_t(n) * ldw + k]), acc);
   }
   if (g.ln_stats) acc = g.ln_stats[m].y * (acc - g.ln_stats[m].x * g.colscale[n]);
   if (g.bias) acc += g.bias[n];
@@ -975,7 +982,7 @@ static int validate(const hoigen_gemm_params* p) {
   HOIGEN_CHECK_ARG(p != nullptr, "gemm: null params");
   HOIGEN_CHECK_ARG(p->a && p->w, "gemm: null operand");
   HOIGEN_CHECK_ARG(p->M > 0 && p->N > 0 && p->K > 0, "gemm: bad shape M=%d N=%d K=%d", p->M, p->N, p->K);
-  HOIGEN_CHECK_ARG((p->conv_taps == 9 || p->lda >= p->K) && p->ldw >= p->K, "gemm: lda/ldw < K");
+  HOIGEN_CHECK_ARG((p->conv_taps == 9 || p->lda >= (p->a2 ? p->K - p->k2 : p->K)) && p->ldw >= p->K, "gemm: lda/ldw < K");
   HOIGEN_CHECK_ARG((p->lda % 8) == 0 && (p->ldw % 8) == 0, "gemm: lda/ldw must be multiples of 8 (got %d, %d)",
                    p->lda, p->ldw);
   HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w) & 15) == 0,
@@ -990,6 +997,10 @@ static int validate(const hoigen_gemm_params* p) {
   HOIGEN_CHECK_ARG(p->halo_w == 0 || (p->halo_h >= 3 && p->halo_w >= 3 && p->M % (p->halo_h * p->halo_w) == 0),
                    "gemm: M must be a whole number of (halo_h, halo_w) images");
   HOIGEN_CHECK_ARG(!p->res_bf16 || (p->ld_resb >= p->N && !p->ln_stats), "gemm: bad res_bf16 layout");
+  HOIGEN_CHECK_ARG(!p->a2 || (p->k2 > 0 && p->k2 < p->K && (p->K - p->k2) % 64 == 0 && p->lda2 >= p->k2 && (p->lda2 % 8) == 0 &&
+                              (reinterpret_cast<uintptr_t>(p->a2) & 15) == 0 && !p->res_bf16 && p->conv_taps != 9 &&
+                              (p->block_n == 0 || p->block_n > 2000) && p->M > 128),
+                   "gemm: second A source needs K - k2 %% 64 == 0, CTA-pair tiles, no res_bf16 / 3x3 form (K=%d k2=%d)", p->K, p->k2);
   HOIGEN_CHECK_ARG(p->act >= 0 && p->act <= 3, "gemm: bad act %d", p->act);
   HOIGEN_CHECK_ARG(!p->ln_stats || (p->ln_colsum && !p->colscale), "gemm: ln_stats needs ln_colsum and excludes colscale");
   HOIGEN_CHECK_ARG((reinterpret_cast<uintptr_t>(p->ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(p->ln_colsum) & 15) == 0,
@@ -1017,6 +1028,8 @@ static GemmArgs to_args(const hoigen_gemm_params* p) {
   g.tap_kb = p->conv_taps == 9 ? p->conv_cin / BK : 0;
   g.halo_h = p->halo_h; g.halo_w = p->halo_w;
   g.res_bf16 = reinterpret_cast<const __nv_bfloat16*>(p->res_bf16); g.ld_resb = p->ld_resb;
+  g.a2_kb0 = p->a2 ? (p->K - p->k2) / BK : 0;
+  g.a2 = reinterpret_cast<const __nv_bfloat16*>(p->a2); g.lda2 = p->lda2;
   return g;
 }
 
@@ -1047,7 +1060,7 @@ template <int BN>
 static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(gemm_bf16_kernel<BN>), Cfg::SMEM_BYTES));
-  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
+  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : (p->a2 ? p->K - p->k2 : p->K)), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
   if (!ta) return HOIGEN_ERR_CUDA;
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN);
   if (!tb) return HOIGEN_ERR_CUDA;
@@ -1074,7 +1087,7 @@ template <int BN, bool TMA_OUT, int EPI>
 static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream, bool force_split) {
   using Cfg = Gemm2Cfg<BN, TMA_OUT>;
   HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(gemm2_bf16_kernel<BN, TMA_OUT, EPI>), Cfg::SMEM_BYTES));
-  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : p->K), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
+  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : (p->a2 ? p->K - p->k2 : p->K)), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
   if (!ta) return HOIGEN_ERR_CUDA;
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN / 2);
   if (!tb) return HOIGEN_ERR_CUDA;
@@ -1119,8 +1132,11 @@ static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream, b
   cfg.numAttrs = 1;
   KernelScope ks(gemm_tag(p->N, p->K, 2), stream, 2.0 * p->M * p->N * p->K,
                  2.0 * (double(p->M) * p->K + double(p->N) * p->K) + double(p->M) * p->N * ((p->out_f32 ? 4 : 0) + (p->out_bf16 ? 2 : 0) + (p->residual ? 4 : 0)));
-  const CUtensorMap* tr = tc;   // identity tiles (RES_TMA recipes only)
-  if (TMA_OUT && EPI >= 0 && ((EPI >> 7) & 1) != 0) {
+  const CUtensorMap* tr = tc;   // identity tiles (RES_TMA recipes) or the second A source
+  if (p->a2) {
+    tr = get_tmap_2d_bf16(p->a2, uint64_t(p->k2), uint64_t(p->M), uint64_t(p->lda2) * 2, BK, BM);
+    if (!tr) return HOIGEN_ERR_CUDA;
+  } else if (TMA_OUT && EPI >= 0 && ((EPI >> 7) & 1) != 0) {
     tr = get_tmap_2d_bf16(p->res_bf16, uint64_t(p->N), uint64_t(p->M), uint64_t(p->ld_resb) * 2, 64, BM);
     if (!tr) return HOIGEN_ERR_CUDA;
   }
@@ -1223,8 +1239,10 @@ int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream) {
   int bn = p->block_n, pair = 0;
   const bool force_split = bn >= 10000;   // testing: +10000 forces the stream-K split whatever K is
   if (force_split) bn -= 10000;
-  if (bn == 0) choose_config(p->M, p->N, p->K, &pair, &bn);
-  else if (bn > 2000) { pair = 1; bn -= 2000; }
+  if (bn == 0) {
+    choose_config(p->M, p->N, p->K, &pair, &bn);
+    if (p->a2 && !pair) { pair = 1; bn = p->N > 128 ? 256 : 128; }   // the second A source exists in the CTA-pair kernel only
+  } else if (bn > 2000) { pair = 1; bn -= 2000; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pair) {
     switch (bn) {

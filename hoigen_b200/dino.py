@@ -136,15 +136,21 @@ class KernelResNet50(nn.Module):
         self.stem_fused = (torch.nn.functional.pad(w_runs.reshape(64, 168), (0, 24)).to(torch.bfloat16).contiguous(), self.stem[1])
         self._keep.append(self.stem_fused[0])
         self.fused_stem = True                         # False: the two-step form (im2col + GEMM)
+        self.merge_downsample = True                   # False: downsample as its own GEMM + bf16 identity epilogue
         self.stages = []
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             blocks = []
             for blk in layer:
                 if blk.conv2.dilation[0] != 1 or blk.conv1.stride[0] != 1:
                     raise NotImplementedError("KernelResNet50: dilated / stride-on-conv1 bottlenecks are not supported")
-                blocks.append(dict(c1=pack(blk.conv1), c2=pack(blk.conv2), c3=pack(blk.conv3),
-                                   ds=pack(blk.downsample[0]) if blk.downsample is not None else None,
-                                   stride=blk.conv2.stride[0]))
+                d = dict(c1=pack(blk.conv1), c2=pack(blk.conv2), c3=pack(blk.conv3),
+                         ds=pack(blk.downsample[0]) if blk.downsample is not None else None,
+                         stride=blk.conv2.stride[0], c3ds=None)
+                if d["ds"] is not None:
+                    # conv3(t) + downsample(x) as ONE product: [t | x] . [W3 | Wds]^T + (b3 + bds)  (hoigen_gemm_params.a2)
+                    d["c3ds"] = (torch.cat([d["c3"][0], d["ds"][0]], dim=1).contiguous(), (d["c3"][1] + d["ds"][1]).contiguous())
+                    self._keep += list(d["c3ds"])
+                blocks.append(d)
             self.stages.append(blocks)
         self._plans: Dict[tuple, dict] = {}
 
@@ -172,7 +178,7 @@ class KernelResNet50(nn.Module):
                 if t is not None:
                     pool.setdefault((t.shape[0], t.shape[1]), []).append(t)
 
-        def gemm(a, wb, out, *, relu, halo=None, taps=0, res=None):
+        def gemm(a, wb, out, *, relu, halo=None, taps=0, res=None, a2=None):
             op = _cabi.ConvOp()
             op.kind = _cabi.CONV_OP_GEMM
             n_out = wb[0].shape[0]
@@ -180,7 +186,7 @@ class KernelResNet50(nn.Module):
             # is tuned for K >= 768; these products are short-K and store-bound)
             bn = 2256 if n_out >= 256 else (2128 if (n_out >= 128 or a.shape[1] != self.STEM_K) else 0)
             op.gemm = _cabi.gemm_params(a, wb[0], bias=wb[1], act=_cabi.ACT_RELU if relu else _cabi.ACT_NONE, out_bf16=out,
-                                        conv_taps=taps, halo=halo, res_bf16=res, block_n=bn)
+                                        conv_taps=taps, halo=halo, res_bf16=res, block_n=bn, a2=a2)
             ops.append(op)
 
         def rowop(kind, src, dst, h=0, w=0, c=0, taps=0):
@@ -224,24 +230,35 @@ class KernelResNet50(nn.Module):
                     t2 = new(rows_out, width)
                     gemm(g2, blk["c2"], t2, relu=True, halo=halo_out)
                     release(g2)
+                    merged = self.merge_downsample and rows_out > 128
                     gs = new(rows_out, cin)
                     rowop(_cabi.CONV_OP_GATHER_S2, x, gs, H, W, cin, 1)
-                    sc = new(rows_out, cout)
-                    gemm(gs, blk["ds"], sc, relu=False, halo=halo_out)
-                    release(gs)
+                    if merged:
+                        sc, x2 = None, gs
+                    else:
+                        sc = new(rows_out, cout)
+                        gemm(gs, blk["ds"], sc, relu=False, halo=halo_out)
+                        release(gs)
                     H, W = Ho, Wo
                 else:
                     halo_out, rows_out = halo_in, rows_in
+                    merged = self.merge_downsample and blk["ds"] is not None and rows_out > 128
                     t2 = new(rows_out, width)
                     gemm(t1, blk["c2"], t2, relu=True, halo=halo_out, taps=9)
-                    if blk["ds"] is not None:
+                    if merged:
+                        sc, x2 = None, x
+                    elif blk["ds"] is not None:
                         sc = new(rows_out, cout)
                         gemm(x, blk["ds"], sc, relu=False, halo=halo_out)
                     else:
                         sc = x
                 y = new(rows_out, cout)
-                gemm(t2, blk["c3"], y, relu=True, halo=halo_out, res=sc)
-                release(t1, t2, x, sc if sc is not x else None)
+                if merged:
+                    gemm(t2, blk["c3ds"], y, relu=True, halo=halo_out, a2=x2)
+                    release(t1, t2, x, x2 if x2 is not x else None)
+                else:
+                    gemm(t2, blk["c3"], y, relu=True, halo=halo_out, res=sc)
+                    release(t1, t2, x, sc if sc is not x else None)
                 x, cin = y, cout
         out = None
         if head == "dino":

@@ -101,6 +101,11 @@ typedef struct {
   int32_t halo_h, halo_w;
   const void* res_bf16;
   int32_t ld_resb;
+  /* Second A source (CTA-pair tiles only): columns [K - k2, K) of the product come from a2 [M, lda2] instead of a -- one GEMM for
+   * `conv3(t) + downsample(x)` of a Bottleneck's first block (w = [W3 | Wds] along K, bias = b3 + bds).  K - k2 must be a multiple
+   * of 64; excludes res_bf16 and conv_taps = 9.  NULL = off. */
+  const void* a2;
+  int32_t lda2, k2;
 } hoigen_gemm_params;
 
 HOIGEN_API int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream);

@@ -678,6 +678,40 @@ def test_gemm_conv1x1_identity_epilogue(cuda_device):
         assert err <= 2e-2 * ref.abs().max().item(), (bn, err)
 
 
+@pytest.mark.parametrize("B,H,k1,k2,cout,bn", [(4, 14, 64, 64, 256, 0), (3, 14, 256, 512, 1024, 2256), (2, 7, 512, 1024, 2048, 2192),
+                                                (1, 10, 64, 96, 64, 0), (5, 28, 128, 256, 512, 2128)])
+def test_gemm_second_a_source(cuda_device, B, H, k1, k2, cout, bn):
+    """hoigen_gemm_params.a2: relu([t | x] . [W3 | Wds]^T + bias) with t and x in separate buffers -- conv3 + downsample of a
+    Bottleneck's first block as one product (CTA-pair kernel; k-blocks past K - k2 load their A tile from the second
+    source).  Against fp32 torch on the same bf16 operands and against the SIMT form of the same contract."""
+    from hoigen_b200 import _cabi
+    torch.manual_seed(B * 10 + H)
+    rows = B * (H + 2) * (H + 2)
+    t = torch.randn(rows, k1, device=cuda_device).to(torch.bfloat16)
+    xbuf = torch.randn(rows, k2 + 8, device=cuda_device).to(torch.bfloat16)
+    x = xbuf[:, :k2]                                   # row stride != width
+    w = (torch.randn(cout, k1 + k2, device=cuda_device) / (k1 + k2) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, device=cuda_device) * 0.1
+    ref = torch.relu(t.float() @ w[:, :k1].float().t() + x.float() @ w[:, k1:].float().t() + bias)
+    mask = torch.zeros(B, H + 2, H + 2, dtype=torch.bool, device=cuda_device)
+    mask[:, 1:-1, 1:-1] = True
+    ref = ref * mask.view(-1, 1)
+    out = torch.full((rows, cout), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.gemm_bf16(t, w, bias=bias, act=_cabi.ACT_RELU, out_bf16=out, halo=(H + 2, H + 2), a2=x, block_n=bn)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), err
+    simt = torch.empty_like(out)
+    _cabi.gemm_bf16(t, w, bias=bias, act=_cabi.ACT_RELU, out_bf16=simt, halo=(H + 2, H + 2), a2=x, simt=True)
+    assert (out.float() - simt.float()).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    # fp32 output through the runtime-flag epilogue, no halo
+    o32 = torch.empty(rows, cout, device=cuda_device)
+    _cabi.gemm_bf16(t, w, bias=bias, out_f32=o32, a2=x, block_n=bn)
+    ref32 = t.float() @ w[:, :k1].float().t() + x.float() @ w[:, k1:].float().t() + bias
+    assert (o32 - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
+    with pytest.raises(_cabi.HoigenError):             # one-CTA tiles have no second source
+        _cabi.gemm_bf16(t, w, bias=bias, out_f32=o32, a2=x, block_n=128)
+
+
 def test_conv_row_kernels(cuda_device):
     """The four row kernels of the ResNet-50 branch against torch: stem im2col (7x7 / s2 / p3 as a GEMM operand), max-pool
     3x3 / s2 / p1 into the haloed layout, the stride-2 gathers (3x3 and 1x1) and average-pool + L2 norm."""

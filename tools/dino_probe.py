@@ -39,6 +39,12 @@ with torch.no_grad():
     t_cudnn = timeit(lambda: fast(imgs))
     kern = KernelDinoR50(r50)
     t_kern = timeit(lambda: kern(imgs))
+    split = KernelDinoR50(r50)
+    split.merge_downsample = False                     # A/B: downsample as its own GEMM + identity epilogue
+    t_split = timeit(lambda: split(imgs))
+    print(f"conv3 + downsample merged {t_kern:.3f} ms, separate {t_split:.3f} ms, max-abs feature difference "
+          f"{(kern(imgs) - split(imgs)).abs().max().item():.3e}")
+    del split
     ref = r50(imgs)
     ref = ref / ref.norm(dim=-1, keepdim=True)
     cos = (kern(imgs) * ref).sum(-1).min().item()
