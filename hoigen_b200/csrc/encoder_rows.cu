@@ -171,12 +171,41 @@ struct RowRegs {
   uint2 e[6];
 };
 
+// How the fp32 stream is cached by the residual pass (HOIGEN_X_L2, A/B in profiles/r02_ab_notes.md):
+//   0 = streaming (ld/st .cs, evict-first; the default)   1 = default caching   2 = L2 evict_last policy on the stream's
+//   loads and stores.  Measured: all three within noise (3.74-3.76 ms/step); a persisting access-policy window over x on
+//   the launching stream (82.9 MB carve-out) was WORSE (3.97 ms/step, pass 25 -> 29.6 us) and is not kept.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_f4_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_f4_hint(float4* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void residual_row_load(RowRegs& r, const float* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
-                                                  const __nv_bfloat16* __restrict__ delta_b, long row, int lane) {
+                                                  const __nv_bfloat16* __restrict__ delta_b, long row, int lane, int xmode,
+                                                  uint64_t pol) {
   const float4* src = reinterpret_cast<const float4*>(x + row * WIDTH);
   const uint2* d1 = reinterpret_cast<const uint2*>(delta + row * WIDTH);
+  if (xmode == 0) {
 #pragma unroll
-  for (int j = 0; j < 6; ++j) r.x[j] = __ldcs(src + lane + 32 * j);
+    for (int j = 0; j < 6; ++j) r.x[j] = __ldcs(src + lane + 32 * j);
+  } else if (xmode == 2) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) r.x[j] = ld_f4_hint(src + lane + 32 * j, pol);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) r.x[j] = src[lane + 32 * j];
+  }
 #pragma unroll
   for (int j = 0; j < 6; ++j) r.d[j] = __ldg(d1 + lane + 32 * j);
   if (delta_b) {
@@ -191,16 +220,17 @@ __global__ void __launch_bounds__(256, 2)
 residual_ln768_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta, const __nv_bfloat16* __restrict__ delta_b,
                       const float* __restrict__ col_bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                       __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ stream_bf16,
-                      float2* __restrict__ stats_out, int rows) {
+                      float2* __restrict__ stats_out, int rows, int xmode) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long stride = long(gridDim.x) * (blockDim.x >> 5);
   long row = long(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
+  const uint64_t pol = xmode == 2 ? l2_policy_evict_last() : 0;
   RowRegs cur, nxt;
-  residual_row_load(cur, x, delta, delta_b, row, lane);
+  residual_row_load(cur, x, delta, delta_b, row, lane, xmode, pol);
   for (; row < rows; row += stride) {
     const long nrow = row + stride;
-    if (nrow < rows) residual_row_load(nxt, x, delta, delta_b, nrow, lane);      // in flight during this row's work
+    if (nrow < rows) residual_row_load(nxt, x, delta, delta_b, nrow, lane, xmode, pol);      // in flight during this row's work
     float4 v[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -223,8 +253,16 @@ residual_ln768_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ d
       }
     }
     float4* dst = reinterpret_cast<float4*>(x + row * WIDTH);
+    if (xmode == 0) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) __stcs(dst + lane + 32 * j, v[j]);   // evict-first: keep L2 for h / delta / qkv, which ARE re-read
+      for (int j = 0; j < 6; ++j) __stcs(dst + lane + 32 * j, v[j]);   // evict-first: keep L2 for h / delta / qkv, which ARE re-read
+    } else if (xmode == 2) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) st_f4_hint(dst + lane + 32 * j, v[j], pol);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) dst[lane + 32 * j] = v[j];
+    }
     if (stream_bf16) {   // bf16 copy of the updated stream: the next adapter block's tensor-core operand
       uint2* dstb = reinterpret_cast<uint2*>(stream_bf16 + row * WIDTH);
 #pragma unroll
@@ -292,6 +330,10 @@ adapter_kv_kernel(const float* __restrict__ prior, const float* __restrict__ in_
 }
 
 // experiment switch (HOIGEN_LN_KEEP_L2=1): default caching of the fp32 stream in the residual passes instead of streaming it
+static int residual_x_l2_mode() {
+  static const int v = getenv("HOIGEN_X_L2") ? atoi(getenv("HOIGEN_X_L2")) : 0;
+  return v;
+}
 static int ln_keep_l2() {
   static const int v = getenv("HOIGEN_LN_KEEP_L2") ? atoi(getenv("HOIGEN_LN_KEEP_L2")) : 0;
   return v;
@@ -354,7 +396,7 @@ int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2
     const int grid = std::min((rows + 7) / 8, 2 * num_sms());
     residual_ln768_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         x, reinterpret_cast<const __nv_bfloat16*>(delta_bf16), reinterpret_cast<const __nv_bfloat16*>(delta2_bf16), col_bias, gamma,
-        beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), reinterpret_cast<__nv_bfloat16*>(x_bf16), nullptr, rows);
+        beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), reinterpret_cast<__nv_bfloat16*>(x_bf16), nullptr, rows, residual_x_l2_mode());
   }
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
@@ -369,7 +411,7 @@ int hoigen_add_rowstats768(float* x, const void* delta_bf16, const void* delta2_
   const int grid = std::min((rows + 7) / 8, 2 * num_sms());
   residual_ln768_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, reinterpret_cast<const __nv_bfloat16*>(delta_bf16), reinterpret_cast<const __nv_bfloat16*>(delta2_bf16), col_bias, nullptr,
-      nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(x_bf16), reinterpret_cast<float2*>(stats), rows);
+      nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(x_bf16), reinterpret_cast<float2*>(stats), rows, residual_x_l2_mode());
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
 }
