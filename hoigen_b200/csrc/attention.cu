@@ -51,7 +51,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+#ifndef HOIGEN_ATT_REGCAP_THREADS
+#define HOIGEN_ATT_REGCAP_THREADS ATT_THREADS     // 448: <= 144 registers (see HOIGEN_GEMM2_REGCAP_THREADS in gemm.cu)
+#endif
+__global__ void __launch_bounds__(HOIGEN_ATT_REGCAP_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ /* box 64 x 128 x 1 */,
                  const __grid_constant__ CUtensorMap tmKV /* box 64 x 208 x 1 */,
                  const __grid_constant__ CUtensorMap tmO /* box 64 x 128 x 1 on the (B,197,768) output */,

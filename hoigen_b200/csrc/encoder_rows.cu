@@ -215,8 +215,11 @@ __device__ __forceinline__ void residual_row_load(RowRegs& r, const float* __res
   }
 }
 
+#ifndef HOIGEN_LN_THREADS
+#define HOIGEN_LN_THREADS 256       // 128: a CTA is 16 Ki registers and fits beside a register-capped GEMM / attention CTA
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(HOIGEN_LN_THREADS, 512 / HOIGEN_LN_THREADS)
 residual_ln768_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta, const __nv_bfloat16* __restrict__ delta_b,
                       const float* __restrict__ col_bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                       __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ stream_bf16,
@@ -393,8 +396,9 @@ int hoigen_add_layernorm768(float* x, const void* delta_bf16, const void* delta2
         reinterpret_cast<const __nv_bfloat16*>(delta_bf16), x, reinterpret_cast<const __nv_bfloat16*>(delta2_bf16),
         reinterpret_cast<__nv_bfloat16*>(x_bf16), col_bias, nullptr, ln_keep_l2());
   } else {
-    const int grid = std::min((rows + 7) / 8, 2 * num_sms());
-    residual_ln768_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    constexpr int wpc = HOIGEN_LN_THREADS / 32;
+    const int grid = std::min((rows + wpc - 1) / wpc, (16 / wpc) * num_sms());
+    residual_ln768_kernel<false><<<grid, HOIGEN_LN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         x, reinterpret_cast<const __nv_bfloat16*>(delta_bf16), reinterpret_cast<const __nv_bfloat16*>(delta2_bf16), col_bias, gamma,
         beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), reinterpret_cast<__nv_bfloat16*>(x_bf16), nullptr, rows, residual_x_l2_mode());
   }
@@ -408,8 +412,9 @@ int hoigen_add_rowstats768(float* x, const void* delta_bf16, const void* delta2_
   HOIGEN_CHECK_ARG(x && delta_bf16 && x_bf16 && stats && rows > 0, "add_rowstats768: bad arguments");
   KernelScope ks("add_rowstats768", reinterpret_cast<cudaStream_t>(stream), 0,
                  double(rows) * WIDTH * (4 + 2 + 4 + 2 + (delta2_bf16 ? 2 : 0)) + double(rows) * 8);
-  const int grid = std::min((rows + 7) / 8, 2 * num_sms());
-  residual_ln768_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  constexpr int wpc = HOIGEN_LN_THREADS / 32;
+  const int grid = std::min((rows + wpc - 1) / wpc, (16 / wpc) * num_sms());
+  residual_ln768_kernel<true><<<grid, HOIGEN_LN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, reinterpret_cast<const __nv_bfloat16*>(delta_bf16), reinterpret_cast<const __nv_bfloat16*>(delta2_bf16), col_bias, nullptr,
       nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(x_bf16), reinterpret_cast<float2*>(stats), rows, residual_x_l2_mode());
   HOIGEN_CHECK_LAUNCH();

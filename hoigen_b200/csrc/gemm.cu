@@ -687,7 +687,13 @@ struct Gemm2Cfg {
 };
 
 template <int BN, bool TMA_OUT, int EPI>
-__global__ void __launch_bounds__(GEMM2_THREADS, 1)
+// HOIGEN_GEMM2_REGCAP_THREADS (512) declares a larger thread bound than the 352 the kernel is launched with: the compiler then
+// keeps it within 64 Ki / 512 = 128 registers (no spills in the encoder's recipes), so that a 128-thread CTA of the HBM-bound
+// residual + LayerNorm pass of the OTHER batch in flight fits on the same SM (352 x 128 + 128 x 128 <= 64 Ki registers).
+#ifndef HOIGEN_GEMM2_REGCAP_THREADS
+#define HOIGEN_GEMM2_REGCAP_THREADS GEMM2_THREADS
+#endif
+__global__ void __launch_bounds__(HOIGEN_GEMM2_REGCAP_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmArgs g) {
   // convolution recipe with a bf16 identity: its tile is TMA-loaded into the output staging buffer and updated in place
