@@ -25,94 +25,179 @@ __device__ __forceinline__ float warp_sum_h(float v) {
 
 // ------------------------------------------------------------------------------------------------
 // prior tokens: [score, box/(w,h,w,h), object_embedding[label]] (517) -> 128 -> 128 -> 64 (ReLU between)
-// one block per (image, 4 tokens), 128 threads; thread o owns output feature o of those tokens.
+// one block per (image, 8 tokens), 256 threads; thread (o, half) owns output feature o of four of those tokens.
 // Padding tokens (t >= n_b) are MLP(0) constants and mask = 1 (U:1448-1450, 1469, 1495).
-// weights are passed TRANSPOSED (in, out) so that the per-thread reads are coalesced.
+// Weights are passed TRANSPOSED (in, out) and stream through a three-stage cp.async ring of 32-row chunks (16 KiB): the
+// chunk loads of the whole three-layer chain stay two ahead of the FMAs, so the kernel runs at its weight-stream rate
+// instead of one exposed L2 round trip per chunk (41 -> ~10 us at B = 64).  Every output element is still the k-ascending
+// fmaf chain  acc = fmaf(w[k][o], x[t][k], acc)  from the bias: results are bit-identical to the first form.
 // ------------------------------------------------------------------------------------------------
 constexpr int PRIOR_IN = 517;
 constexpr int PRIOR_MAXTOK = 32;
-constexpr int PRIOR_TPB = 4;  // tokens per block
+constexpr int PRIOR_TPB = 8;            // tokens per block
+constexpr int PRIOR_LDX = 520;          // row pitch of the staged inputs (16-byte aligned rows)
+constexpr int PRIOR_CHUNK = 32;         // weight rows per ring stage
+constexpr int PRIOR_STAGES = 3;
+constexpr int PRIOR_SMEM_BYTES = (PRIOR_TPB * PRIOR_LDX + 2 * PRIOR_TPB * 128 + PRIOR_STAGES * PRIOR_CHUNK * 128) * 4;
 
-// y[t][o] (+)= sum_k x[t][k] * Wt[k][o] for PRIOR_TPB tokens; Wt (K x NOUT, row-major) is streamed through shared
-// memory in 64-row chunks with coalesced, fully independent loads (the per-thread dependent LDG chain was pure latency).
-template <int NOUT>
-__device__ __forceinline__ void prior_layer(const float* __restrict__ wt, int K, const float* __restrict__ x, int ldx,
-                                            float* __restrict__ wchunk, float (&acc)[4], int o) {
-  for (int k0 = 0; k0 < K; k0 += 64) {
-    const int kn = min(64, K - k0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < kn * NOUT / 4; i += 128)
-      reinterpret_cast<float4*>(wchunk)[i] = __ldg(reinterpret_cast<const float4*>(wt + size_t(k0) * NOUT) + i);
-    __syncthreads();
-    if (o < NOUT) {
-#pragma unroll 8
-      for (int k = 0; k < kn; ++k) {
-        const float w = wchunk[k * NOUT + o];
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// One weight chunk of the chain: layer L (0, 1, 2), rows [k0, k0 + kn) of its (K x NOUT) transposed matrix.
+struct PriorChunk {
+  const float* src;   // first row of the chunk
+  int kn;             // rows (<= 32)
+  int nout;           // 128 or 64
+};
+
+// acc[t] = fmaf(w[k][o], x[t][k], acc[t]) for k ascending over one chunk (TOK tokens of this thread); full chunks have a
+// compile-time trip count so that the next quads' shared-memory loads are in flight under the current quad's FMAs
+template <int NOUT, int TOK>
+__device__ __forceinline__ void prior_chunk_fma(const float* __restrict__ ws, const float* __restrict__ x, int ldx, int kn, int o,
+                                                float (&acc)[TOK]) {
+  auto quad = [&](int k) {
+    const float wa = ws[k * NOUT + o], wb = ws[(k + 1) * NOUT + o], wc = ws[(k + 2) * NOUT + o], wd = ws[(k + 3) * NOUT + o];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) acc[t] = fmaf(w, x[t * ldx + k0 + k], acc[t]);
-      }
+    for (int t = 0; t < TOK; ++t) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + t * ldx + k);    // broadcast
+      acc[t] = fmaf(wa, xv.x, acc[t]);
+      acc[t] = fmaf(wb, xv.y, acc[t]);
+      acc[t] = fmaf(wc, xv.z, acc[t]);
+      acc[t] = fmaf(wd, xv.w, acc[t]);
+    }
+  };
+  if (kn == PRIOR_CHUNK) {
+#pragma unroll
+    for (int k = 0; k < PRIOR_CHUNK; k += 4) quad(k);
+  } else {
+    const int k4 = kn & ~3;
+    for (int k = 0; k < k4; k += 4) quad(k);
+    for (int k = k4; k < kn; ++k) {
+      const float w = ws[k * NOUT + o];
+#pragma unroll
+      for (int t = 0; t < TOK; ++t) acc[t] = fmaf(w, x[t * ldx + k], acc[t]);
     }
   }
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int PRIOR_THREADS = 256;      // thread = (output feature o, token half): 8 warps per CTA to cover the LDS latency
+constexpr int PRIOR_TPT = PRIOR_TPB / 2;   // tokens per thread
+
+__global__ void __launch_bounds__(PRIOR_THREADS)
 prior_tokens_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ labels,
                     const int* __restrict__ box_off, const float* __restrict__ obj_emb, const float* __restrict__ w0t,
                     const float* __restrict__ b0, const float* __restrict__ w1t, const float* __restrict__ b1,
                     const float* __restrict__ w2t, const float* __restrict__ b2, float img_w, float img_h, int n_max,
                     int num_objects, float* __restrict__ prior, uint8_t* __restrict__ mask) {
-  __shared__ float xin[PRIOR_TPB][520];
-  __shared__ float h1[PRIOR_TPB][128];
-  __shared__ float h2[PRIOR_TPB][128];
-  __shared__ __align__(16) float wchunk[64 * 128];
-  static_assert(PRIOR_TPB == 4, "prior_layer is written for 4 tokens per block");
+  extern __shared__ __align__(16) float prior_smem[];
+  float* xin = prior_smem;                                   // [8][520]
+  float* h1 = xin + PRIOR_TPB * PRIOR_LDX;                   // [8][128]
+  float* h2 = h1 + PRIOR_TPB * 128;                          // [8][128]
+  float* ring = h2 + PRIOR_TPB * 128;                        // [3][32 x 128]
+  constexpr int C0 = (PRIOR_IN + PRIOR_CHUNK - 1) / PRIOR_CHUNK;   // 17 chunks of layer 0
+  constexpr int C1 = 128 / PRIOR_CHUNK;                            // 4 of layer 1, 4 of layer 2
+  constexpr int NCHUNK = C0 + 2 * C1;
   const int b = blockIdx.x;
   const int tbase = blockIdx.y * PRIOR_TPB;
-  const int o = threadIdx.x;
+  const int o = threadIdx.x & 127, th = threadIdx.x >> 7;     // tokens [4 th, 4 th + 4) of the block
   const int base = box_off[b];
   const int n = box_off[b + 1] - base;
-  for (int i = threadIdx.x; i < PRIOR_TPB * 520; i += 128) {
-    const int t = tbase + i / 520, c = i % 520;
-    float v = 0.f;
-    if (t < n && c < PRIOR_IN) {
-      if (c == 0) v = scores[base + t];
-      else if (c < 5) v = boxes[(base + t) * 4 + (c - 1)] / ((c & 1) ? img_w : img_h);  // x1/w, y1/h, x2/w, y2/h
-      else {   // a label outside the embedding table reads nothing (the host surface validates / the reference would raise)
-        const int64_t lb = labels[base + t];
-        v = (lb >= 0 && lb < num_objects) ? __ldg(obj_emb + lb * FEAT + (c - 5)) : 0.f;
-      }
+
+  auto chunk_of = [&](int c) {
+    PriorChunk ch;
+    if (c < C0) { ch.src = w0t + size_t(c) * PRIOR_CHUNK * 128; ch.kn = min(PRIOR_CHUNK, PRIOR_IN - c * PRIOR_CHUNK); ch.nout = 128; }
+    else if (c < C0 + C1) { ch.src = w1t + size_t(c - C0) * PRIOR_CHUNK * 128; ch.kn = PRIOR_CHUNK; ch.nout = 128; }
+    else { ch.src = w2t + size_t(c - C0 - C1) * PRIOR_CHUNK * 64; ch.kn = PRIOR_CHUNK; ch.nout = 64; }
+    return ch;
+  };
+  auto issue = [&](int c) {     // chunk c -> ring stage c % 3 (16-byte pieces, coalesced); one commit group per call
+    if (c < NCHUNK) {
+      const PriorChunk ch = chunk_of(c);
+      float* dst = ring + (c % PRIOR_STAGES) * PRIOR_CHUNK * 128;
+      const int pieces = ch.kn * ch.nout / 4;
+      for (int i = threadIdx.x; i < pieces; i += PRIOR_THREADS) cp_async16(dst + 4 * i, ch.src + 4 * i);
     }
-    xin[i / 520][c] = v;
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+
+  // staged inputs of the block's tokens (zero rows for padding tokens).  The embedding gather depends on the label load:
+  // one owner thread per token fetches the label (and writes the five scalar columns), then every thread issues its eight
+  // INDEPENDENT 16-byte row loads at once -- the element-per-iteration form paid one exposed round trip per iteration.
+  __shared__ int s_label[PRIOR_TPB];
+  if (threadIdx.x < PRIOR_TPB) {
+    const int t = tbase + threadIdx.x;
+    float* row = xin + threadIdx.x * PRIOR_LDX;
+    int lab = -1;
+    float sc = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+    if (t < n) {
+      const int64_t lb = labels[base + t];   // a label outside the embedding table reads nothing (the host surface validates)
+      lab = (lb >= 0 && lb < num_objects) ? int(lb) : -1;
+      const float* bx = boxes + size_t(base + t) * 4;
+      sc = scores[base + t];
+      x1 = bx[0] / img_w; y1 = bx[1] / img_h; x2 = bx[2] / img_w; y2 = bx[3] / img_h;
+    }
+    s_label[threadIdx.x] = lab;
+    row[0] = sc; row[1] = x1; row[2] = y1; row[3] = x2; row[4] = y2;
+    row[PRIOR_IN] = 0.f; row[PRIOR_IN + 1] = 0.f; row[PRIOR_IN + 2] = 0.f;
+    if (t < n_max) mask[b * n_max + t] = t < n ? 0 : 1;
   }
-  if (threadIdx.x < PRIOR_TPB && tbase + threadIdx.x < n_max)
-    mask[b * n_max + tbase + threadIdx.x] = (tbase + threadIdx.x) < n ? 0 : 1;
-  float acc[4];
+  __syncthreads();
+  {
+    float4 v[PRIOR_TPT];
+#pragma unroll
+    for (int t = 0; t < PRIOR_TPT; ++t) {          // token 4 th + t, floats [4 o, 4 o + 4) of its embedding row
+      const int lab = s_label[th * PRIOR_TPT + t];
+      v[t] = lab >= 0 ? __ldg(reinterpret_cast<const float4*>(obj_emb + size_t(lab) * FEAT) + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int t = 0; t < PRIOR_TPT; ++t) {
+      float* dst = xin + (th * PRIOR_TPT + t) * PRIOR_LDX + 5 + 4 * o;
+      dst[0] = v[t].x; dst[1] = v[t].y; dst[2] = v[t].z; dst[3] = v[t].w;
+    }
+  }
+
+  float acc[PRIOR_TPT];
   {
     const float bias = b0[o];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) acc[t] = bias;
-    prior_layer<128>(w0t, PRIOR_IN, &xin[0][0], 520, wchunk, acc, o);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) h1[t][o] = fmaxf(acc[t], 0.f);
+    for (int t = 0; t < PRIOR_TPT; ++t) acc[t] = bias;
   }
-  {
-    const float bias = b1[o];
+  const int t0 = th * PRIOR_TPT;
+  for (int c = 0; c < NCHUNK; ++c) {
+    issue(c + 2);
+    cp_async_wait<2>();        // this thread's pieces of chunk c have landed ...
+    __syncthreads();           // ... and everyone's (also orders the staged inputs / previous layer's activations)
+    const PriorChunk ch = chunk_of(c);
+    const float* ws = ring + (c % PRIOR_STAGES) * PRIOR_CHUNK * 128;
+    if (c < C0) prior_chunk_fma<128, PRIOR_TPT>(ws, xin + t0 * PRIOR_LDX + c * PRIOR_CHUNK, PRIOR_LDX, ch.kn, o, acc);
+    else if (c < C0 + C1) prior_chunk_fma<128, PRIOR_TPT>(ws, h1 + t0 * 128 + (c - C0) * PRIOR_CHUNK, 128, ch.kn, o, acc);
+    else if (o < 64) prior_chunk_fma<64, PRIOR_TPT>(ws, h2 + t0 * 128 + (c - C0 - C1) * PRIOR_CHUNK, 128, ch.kn, o, acc);
+    // layer boundaries: activations out, next layer's bias in
+    if (c == C0 - 1) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) acc[t] = bias;
-    prior_layer<128>(w1t, 128, &h1[0][0], 128, wchunk, acc, o);
+      for (int t = 0; t < PRIOR_TPT; ++t) h1[(t0 + t) * 128 + o] = fmaxf(acc[t], 0.f);
+      const float bias = b1[o];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) h2[t][o] = fmaxf(acc[t], 0.f);
-  }
-  {
-    const float bias = o < 64 ? b2[o] : 0.f;
+      for (int t = 0; t < PRIOR_TPT; ++t) acc[t] = bias;
+    } else if (c == C0 + C1 - 1) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) acc[t] = bias;
-    prior_layer<64>(w2t, 128, &h2[0][0], 128, wchunk, acc, o);
-    if (o < 64) {
+      for (int t = 0; t < PRIOR_TPT; ++t) h2[(t0 + t) * 128 + o] = fmaxf(acc[t], 0.f);
+      const float bias = o < 64 ? b2[o] : 0.f;
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (tbase + t < n_max) prior[(size_t(b) * n_max + tbase + t) * 64 + o] = acc[t];
+      for (int t = 0; t < PRIOR_TPT; ++t) acc[t] = bias;
     }
+    __syncthreads();           // the stage is refilled by the next iteration's issue
+  }
+  if (o < 64) {
+#pragma unroll
+    for (int t = 0; t < PRIOR_TPT; ++t)
+      if (tbase + t0 + t < n_max) prior[(size_t(b) * n_max + tbase + t0 + t) * 64 + o] = acc[t];
   }
 }
 
@@ -512,7 +597,10 @@ int hoigen_prior_tokens(const float* boxes, const float* scores, const int64_t* 
   HOIGEN_CHECK_ARG(num_objects > 0, "prior_tokens: num_objects (rows of object_embedding) must be positive");
   KernelScope ks("prior_tokens", reinterpret_cast<cudaStream_t>(stream), 2.0 * batch * n_max * (517 * 128 + 128 * 128 + 128 * 64),
                  double(batch) * n_max * (517 + 64) * 4);
-  prior_tokens_kernel<<<dim3(batch, (n_max + PRIOR_TPB - 1) / PRIOR_TPB), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(prior_tokens_kernel), PRIOR_SMEM_BYTES));
+  HOIGEN_CHECK_ARG(((reinterpret_cast<uintptr_t>(w0t) | reinterpret_cast<uintptr_t>(w1t) | reinterpret_cast<uintptr_t>(w2t)) & 15) == 0,
+                   "prior_tokens: the transposed weight matrices must be 16-byte aligned");
+  prior_tokens_kernel<<<dim3(batch, (n_max + PRIOR_TPB - 1) / PRIOR_TPB), PRIOR_THREADS, PRIOR_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
       boxes, scores, labels, box_off, obj_emb, w0t, b0, w1t, b1, w2t, b2, img_w, img_h, n_max, num_objects, prior, mask);
   HOIGEN_CHECK_LAUNCH();
   return HOIGEN_OK;
