@@ -35,6 +35,7 @@ class GemmParams(C.Structure):
         ("conv_taps", C.c_int32), ("conv_cin", C.c_int32), ("halo_h", C.c_int32), ("halo_w", C.c_int32),
         ("res_bf16", C.c_void_p), ("ld_resb", C.c_int32),
         ("a2", C.c_void_p), ("lda2", C.c_int32), ("k2", C.c_int32),
+        ("conv_stride", C.c_int32),
     ]
 
 
@@ -267,9 +268,11 @@ def call(name: str, *args) -> None:
 
 def gemm_params(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, act=ACT_NONE, residual=None,
                 out_f32=None, out_bf16=None, block_n: int = 0, split_k: int = 0, act_param: float = 0.0, ln_stats=None,
-                ln_colsum=None, conv_taps: int = 0, halo=None, res_bf16=None, a2=None) -> "GemmParams":
+                ln_colsum=None, conv_taps: int = 0, halo=None, res_bf16=None, a2=None, conv_stride: int = 1) -> "GemmParams":
     """Fill a hoigen_gemm_params from tensors (no launch).  conv_taps = 9: `a` is the (rows, cin) activation matrix with a
-    zero halo, `w` is (N, 9 * cin); halo = (H + 2, W + 2); res_bf16 = bf16 identity added before the activation."""
+    zero halo, `w` is (N, 9 * cin); halo = (H + 2, W + 2); res_bf16 = bf16 identity added before the activation.
+    conv_stride = 2: `a` is the (4 * rows_out, cin) four-phase split of the input (hoigen_conv_gather_s2, taps = 4) and halo the
+    OUTPUT's (Ho + 2, Wo + 2)."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
@@ -279,6 +282,10 @@ def gemm_params(a: torch.Tensor, w: torch.Tensor, *, bias=None, colscale=None, a
         assert w.shape[1] == 9 * K and halo is not None
         p.conv_taps, p.conv_cin = 9, K
         K = 9 * K
+        if conv_stride == 2:
+            assert M % 4 == 0
+            M //= 4
+            p.conv_stride = 2
     elif a2 is not None:        # second A source: w = [W1 | W2] along K
         assert a2.dtype == torch.bfloat16 and a2.dim() == 2 and a2.stride(1) == 1 and a2.shape[0] == M
         assert w.shape[1] == K + a2.shape[1] and K % 64 == 0

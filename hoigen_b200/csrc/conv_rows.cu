@@ -131,6 +131,28 @@ __global__ void maxpool3x3s2_halo_kernel(const __nv_bfloat16* __restrict__ in, _
 // Stride-2 gathers: in (B, h + 2, w + 2, c) with halo -> rows (B * (ho + 2) * (wo + 2), taps * c), ho = ceil(h / 2), the A operand of the
 // stride-2 convolutions (taps = 9: 3x3 / pad 1, column = (ky * 3 + kx) * c + channel; taps = 1: the 1x1 down-sampling
 // shortcut).  Ring rows of the output are written as zeros.  One thread per (row, tap, 8 channels).
+// taps = 4: the FOUR-PHASE split for the implicit stride-2 3x3 convolution (hoigen_gemm_params.conv_stride = 2):
+// rows [p][B * (ho + 2) * (wo + 2)][c], p = 2 py + px, holding in[2 y' + py][2 x' + px] at haloed position (y' + 1, x' + 1) and
+// zero where that source pixel does not exist -- 4/9 of the bytes of the nine-tap gather, written and read.
+__global__ void conv_phase_split_s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ rows, int batch, int h,
+                                           int w, int c) {
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2, hp = ho + 2, wp = wo + 2, c8 = c / 8;
+  const int hin = h + 2, win = w + 2;
+  const long long per_phase = (long long)batch * hp * wp;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= 4 * per_phase * c8) return;
+  const int g8 = int(gid % c8);
+  const long long r = gid / c8;                   // row of the [4 * per_phase, c] matrix
+  const int ph = int(r / per_phase);
+  const long long pix = r - ph * per_phase;
+  const int X = int(pix % wp), Y = int((pix / wp) % hp), b = int(pix / ((long long)wp * hp));
+  const int iy = 2 * (Y - 1) + (ph >> 1), ix = 2 * (X - 1) + (ph & 1);       // unpadded source pixel
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+    v = __ldg(reinterpret_cast<const uint4*>(in + ((size_t(b) * hin + iy + 1) * win + ix + 1) * c) + g8);
+  *(reinterpret_cast<uint4*>(rows + r * c) + g8) = v;
+}
+
 __global__ void conv_gather_s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ rows, int batch, int h,
                                       int w, int c, int taps) {
   const int ho = (h + 1) / 2, wo = (w + 1) / 2, hp = ho + 2, wp = wo + 2, c8 = c / 8;   // odd h: tap row 2 ho = h + 1 is the halo
@@ -234,9 +256,17 @@ int hoigen_maxpool3x3s2_halo(const void* in_bf16, void* out_bf16, int32_t batch,
 
 int hoigen_conv_gather_s2(const void* in_bf16, void* rows_bf16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t taps,
                           hoigen_stream_t stream) {
-  HOIGEN_CHECK_ARG(in_bf16 && rows_bf16 && batch > 0 && h > 0 && w > 0 && c > 0 && (c % 8) == 0 && (taps == 1 || taps == 9),
+  HOIGEN_CHECK_ARG(in_bf16 && rows_bf16 && batch > 0 && h > 0 && w > 0 && c > 0 && (c % 8) == 0 && (taps == 1 || taps == 9 || taps == 4),
                    "conv_gather_s2: bad arguments (h=%d w=%d c=%d taps=%d)", h, w, c, taps);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (taps == 4) {
+    const long long total4 = 4LL * batch * ((h + 1) / 2 + 2) * ((w + 1) / 2 + 2) * (c / 8);
+    KernelScope ks4("conv_phase_split_s2", s, 0, 2.0 * double(total4) * 16);
+    conv_phase_split_s2_kernel<<<unsigned((total4 + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(rows_bf16), batch, h, w, c);
+    HOIGEN_CHECK_LAUNCH();
+    return HOIGEN_OK;
+  }
   const long long total = (long long)batch * ((h + 1) / 2 + 2) * ((w + 1) / 2 + 2) * taps * (c / 8);
   KernelScope ks("conv_gather_s2", s, 0, 2.0 * double(total) * 16);
   conv_gather_s2_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(

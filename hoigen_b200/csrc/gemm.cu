@@ -66,6 +66,7 @@ struct GemmArgs {
   // convolution forms (hoigen_gemm_params.conv_taps / halo_* / res_bf16)
   int tap_kb;               // k-blocks per 3x3 tap (0 = plain GEMM): k-block kb reads A columns (kb % tap_kb) * 64 of the
                             // rows shifted by (t / 3 - 1) * halo_w + (t % 3 - 1), t = kb / tap_kb
+  int phase_rows;           // stride-2 form (conv_stride = 2): rows per input phase block (= M); 0 = stride 1
   int halo_h, halo_w;       // rows on the ring of each (halo_h, halo_w) image are written as 0 (halo_w = 0: off)
   const __nv_bfloat16* res_bf16;   // added before the activation
   int ld_resb;
@@ -87,7 +88,9 @@ __device__ __forceinline__ void a_coords(const GemmArgs& g, int kb, int row0, in
   if (g.tap_kb > 0) {
     const int t = kb / g.tap_kb;
     col = (kb - t * g.tap_kb) * BK;
-    row = row0 + (t / 3 - 1) * g.halo_w + (t % 3 - 1);
+    const int ky = t / 3, kx = t - ky * 3;
+    if (g.phase_rows > 0) row = row0 + ((ky != 1) * 2 + (kx != 1)) * g.phase_rows - (ky == 0) * g.halo_w - (kx == 0);
+    else row = row0 + (ky - 1) * g.halo_w + (kx - 1);
   }
 }
 
@@ -961,8 +964,11 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ a, const __nv
   if (g.tap_kb > 0) {
     const int cin = g.tap_kb * BK;
     for (int t = 0; t < 9; ++t) {
-      const long long src = (long long)m + (t / 3 - 1) * g.halo_w + (t % 3 - 1);
-      if (src < 0 || src >= g.M) continue;
+      const int ky = t / 3, kx = t % 3;
+      const long long src = g.phase_rows > 0
+                                ? (long long)m + (long long)((ky != 1) * 2 + (kx != 1)) * g.phase_rows - (ky == 0) * g.halo_w - (kx == 0)
+                                : (long long)m + (ky - 1) * g.halo_w + (kx - 1);
+      if (src < 0 || src >= (g.phase_rows > 0 ? 4LL * g.M : (long long)g.M)) continue;
       for (int k = 0; k < cin; ++k)
         acc = fmaf(__bfloat162float(a[size_t(src) * lda + k]), __bfloat162float(w[size_t(n) * ldw + t * cin + k]), acc);
     }
@@ -998,6 +1004,8 @@ static int validate(const hoigen_gemm_params* p) {
   HOIGEN_CHECK_ARG(!p->out_bf16 || p->ld_bf16 >= p->N, "gemm: ld_bf16 < N");
   HOIGEN_CHECK_ARG(!p->residual || p->ld_res >= p->N, "gemm: ld_res < N");
   HOIGEN_CHECK_ARG(p->conv_taps == 0 || p->conv_taps == 1 || p->conv_taps == 9, "gemm: conv_taps must be 0, 1 or 9 (got %d)", p->conv_taps);
+  HOIGEN_CHECK_ARG(p->conv_stride == 0 || p->conv_stride == 1 || (p->conv_stride == 2 && p->conv_taps == 9 && p->M <= (1 << 28)),
+                   "gemm: conv_stride must be 0 / 1, or 2 together with conv_taps = 9 (got %d)", p->conv_stride);
   HOIGEN_CHECK_ARG(p->conv_taps != 9 || (p->conv_cin > 0 && p->conv_cin % 64 == 0 && p->K == 9 * p->conv_cin && p->halo_w > 0 && p->lda >= p->conv_cin),
                    "gemm: 3x3 form needs conv_cin %% 64 == 0, K == 9 * conv_cin, halo_w > 0 (cin=%d K=%d)", p->conv_cin, p->K);
   HOIGEN_CHECK_ARG(p->halo_w == 0 || (p->halo_h >= 3 && p->halo_w >= 3 && p->M % (p->halo_h * p->halo_w) == 0),
@@ -1032,6 +1040,7 @@ static GemmArgs to_args(const hoigen_gemm_params* p) {
   g.debug = dbg;
   g.sk_ws = nullptr; g.sk_flags = nullptr; g.sk_snap = 0; g.sk_tiles = 0; g.split_k = 1;
   g.tap_kb = p->conv_taps == 9 ? p->conv_cin / BK : 0;
+  g.phase_rows = (p->conv_taps == 9 && p->conv_stride == 2) ? p->M : 0;
   g.halo_h = p->halo_h; g.halo_w = p->halo_w;
   g.res_bf16 = reinterpret_cast<const __nv_bfloat16*>(p->res_bf16); g.ld_resb = p->ld_resb;
   g.a2_kb0 = p->a2 ? (p->K - p->k2) / BK : 0;
@@ -1066,7 +1075,7 @@ template <int BN>
 static int launch_gemm(const hoigen_gemm_params* p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(gemm_bf16_kernel<BN>), Cfg::SMEM_BYTES));
-  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : (p->a2 ? p->K - p->k2 : p->K)), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
+  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : (p->a2 ? p->K - p->k2 : p->K)), uint64_t(p->M) * (p->conv_taps == 9 && p->conv_stride == 2 ? 4 : 1), uint64_t(p->lda) * 2, BK, BM);
   if (!ta) return HOIGEN_ERR_CUDA;
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN);
   if (!tb) return HOIGEN_ERR_CUDA;
@@ -1093,7 +1102,7 @@ template <int BN, bool TMA_OUT, int EPI>
 static int launch_gemm2_impl(const hoigen_gemm_params* p, cudaStream_t stream, bool force_split) {
   using Cfg = Gemm2Cfg<BN, TMA_OUT>;
   HOIGEN_TRY_RC(set_max_dynamic_smem(reinterpret_cast<const void*>(gemm2_bf16_kernel<BN, TMA_OUT, EPI>), Cfg::SMEM_BYTES));
-  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : (p->a2 ? p->K - p->k2 : p->K)), uint64_t(p->M), uint64_t(p->lda) * 2, BK, BM);
+  const CUtensorMap* ta = get_tmap_2d_bf16(p->a, uint64_t(p->conv_taps == 9 ? p->conv_cin : (p->a2 ? p->K - p->k2 : p->K)), uint64_t(p->M) * (p->conv_taps == 9 && p->conv_stride == 2 ? 4 : 1), uint64_t(p->lda) * 2, BK, BM);
   if (!ta) return HOIGEN_ERR_CUDA;
   const CUtensorMap* tb = get_tmap_2d_bf16(p->w, uint64_t(p->K), uint64_t(p->N), uint64_t(p->ldw) * 2, BK, BN / 2);
   if (!tb) return HOIGEN_ERR_CUDA;

@@ -137,6 +137,7 @@ class KernelResNet50(nn.Module):
         self._keep.append(self.stem_fused[0])
         self.fused_stem = True                         # False: the two-step form (im2col + GEMM)
         self.merge_downsample = True                   # False: downsample as its own GEMM + bf16 identity epilogue
+        self.implicit_stride2 = True                   # False: stride-2 3x3 convolutions through the nine-tap gather (im2col)
         self.stages = []
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             blocks = []
@@ -178,7 +179,7 @@ class KernelResNet50(nn.Module):
                 if t is not None:
                     pool.setdefault((t.shape[0], t.shape[1]), []).append(t)
 
-        def gemm(a, wb, out, *, relu, halo=None, taps=0, res=None, a2=None):
+        def gemm(a, wb, out, *, relu, halo=None, taps=0, res=None, a2=None, stride=1):
             op = _cabi.ConvOp()
             op.kind = _cabi.CONV_OP_GEMM
             n_out = wb[0].shape[0]
@@ -186,7 +187,7 @@ class KernelResNet50(nn.Module):
             # is tuned for K >= 768; these products are short-K and store-bound)
             bn = 2256 if n_out >= 256 else (2128 if (n_out >= 128 or a.shape[1] != self.STEM_K) else 0)
             op.gemm = _cabi.gemm_params(a, wb[0], bias=wb[1], act=_cabi.ACT_RELU if relu else _cabi.ACT_NONE, out_bf16=out,
-                                        conv_taps=taps, halo=halo, res_bf16=res, block_n=bn, a2=a2)
+                                        conv_taps=taps, halo=halo, res_bf16=res, block_n=bn, a2=a2, conv_stride=stride)
             ops.append(op)
 
         def rowop(kind, src, dst, h=0, w=0, c=0, taps=0):
@@ -225,10 +226,16 @@ class KernelResNet50(nn.Module):
                     Ho, Wo = half(H), half(W)
                     halo_out = (Ho + 2, Wo + 2)
                     rows_out = B * halo_out[0] * halo_out[1]
-                    g2 = new(rows_out, 9 * width)
-                    rowop(_cabi.CONV_OP_GATHER_S2, t1, g2, H, W, width, 9)
                     t2 = new(rows_out, width)
-                    gemm(g2, blk["c2"], t2, relu=True, halo=halo_out)
+                    if self.implicit_stride2 and width % 64 == 0:
+                        # four-phase split of t1 in the output's haloed geometry: every tap is a row shift of one phase block
+                        g2 = new(4 * rows_out, width)
+                        rowop(_cabi.CONV_OP_GATHER_S2, t1, g2, H, W, width, 4)
+                        gemm(g2, blk["c2"], t2, relu=True, halo=halo_out, taps=9, stride=2)
+                    else:
+                        g2 = new(rows_out, 9 * width)
+                        rowop(_cabi.CONV_OP_GATHER_S2, t1, g2, H, W, width, 9)
+                        gemm(g2, blk["c2"], t2, relu=True, halo=halo_out)
                     release(g2)
                     merged = self.merge_downsample and rows_out > 128
                     gs = new(rows_out, cin)

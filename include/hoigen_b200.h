@@ -106,6 +106,12 @@ typedef struct {
    * of 64; excludes res_bf16 and conv_taps = 9.  NULL = off. */
   const void* a2;
   int32_t lda2, k2;
+  /* conv_taps = 9 with conv_stride = 2: the 3x3 / stride 2 / pad 1 convolution as an implicit GEMM.  `a` holds the FOUR PHASES of
+   * the input, [4][M, lda]: phase (py, px) = 2 py + px is the image in[2 y' + py][2 x' + px] laid out in the OUTPUT's haloed
+   * geometry (halo_h, halo_w), zero where the source pixel does not exist (hoigen_conv_gather_s2 with taps = 4).  Tap (ky, kx) of
+   * output row q then reads phase (ky != 1, kx != 1) at row q - (ky == 0) halo_w - (kx == 0): a constant row shift per tap,
+   * as in the stride-1 form.  0 / 1 = stride 1. */
+  int32_t conv_stride;
 } hoigen_gemm_params;
 
 HOIGEN_API int hoigen_gemm_bf16(const hoigen_gemm_params* p, hoigen_stream_t stream);
@@ -478,7 +484,8 @@ HOIGEN_API int hoigen_stem_conv_hw(const float* images, const void* w_bf16, cons
 HOIGEN_API int hoigen_maxpool3x3s2_halo(const void* in_bf16, void* out_bf16, int32_t batch, int32_t h, int32_t w, int32_t c,
                                         hoigen_stream_t stream);
 /* A operand of the stride-2 convolutions: in (B, h+2, w+2, c) -> rows (B*(ceil(h/2)+2)*(ceil(w/2)+2), taps*c); taps = 9: 3x3 / pad 1,
- * column = (ky*3+kx)*c + channel; taps = 1: the 1x1 shortcut.  Rows of the output ring are zeros. */
+ * column = (ky*3+kx)*c + channel; taps = 1: the 1x1 shortcut.  Rows of the output ring are zeros.
+ * taps = 4: the four-phase split [4][B*(ceil(h/2)+2)*(ceil(w/2)+2)][c] that hoigen_gemm_params.conv_stride = 2 consumes. */
 HOIGEN_API int hoigen_conv_gather_s2(const void* in_bf16, void* rows_bf16, int32_t batch, int32_t h, int32_t w, int32_t c,
                                      int32_t taps, hoigen_stream_t stream);
 /* AdaptiveAvgPool2d(1) over the interior of (B, h+2, w+2, c), then x / ||x||_2 (U:1618) -> (B, c) fp32; c % 256 == 0, <= 2048 */

@@ -656,6 +656,51 @@ def test_gemm_conv3x3_implicit(cuda_device, B, H, cin, cout, block_n):
     assert (out.float() - simt.float()).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout,block_n", [(3, 14, 14, 64, 64, 0), (2, 28, 28, 128, 128, 2256), (4, 7, 9, 256, 256, 0),
+                                                     (2, 13, 20, 128, 96, 2128), (1, 56, 56, 128, 128, 128)])
+def test_gemm_conv3x3_stride2_implicit(cuda_device, B, H, W, cin, cout, block_n):
+    """hoigen_gemm_params.conv_stride = 2: the 3x3 / stride 2 / pad 1 convolution (first block of ResNet stages 2-4) as nine
+    accumulated products of row-shifted views of the FOUR-PHASE split of the input (hoigen_conv_gather_s2, taps = 4), odd sizes
+    included.  Against torch conv2d in fp32 on the same bf16 operands, against the SIMT form of the same contract, and against
+    the nine-tap gather + plain GEMM it replaces (same products, same fp32 accumulator: equal up to summation order)."""
+    from hoigen_b200 import _cabi
+    _cabi.init(cuda_device)
+    torch.manual_seed(B * 100 + H + W)
+    x = torch.randn(B, cin, H, W, device=cuda_device)
+    w = torch.randn(cout, cin, 3, 3, device=cuda_device) / (3 * cin ** 0.5)
+    bias = torch.randn(cout, device=cuda_device) * 0.1
+    rows = _haloed(x)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    rows_out = B * (Ho + 2) * (Wo + 2)
+    wk = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(torch.bfloat16).contiguous()
+    phases = torch.full((4 * rows_out, cin), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.call("hoigen_conv_gather_s2", rows.data_ptr(), phases.data_ptr(), B, H, W, cin, 4)
+    xin = rows.float().view(B, H + 2, W + 2, cin)[:, 1:-1, 1:-1]
+    for ph in range(4):                                   # the split itself: exact copies, zero halo / missing pixels
+        want = torch.zeros(B, Ho + 2, Wo + 2, cin, device=cuda_device)
+        sub = xin[:, (ph >> 1)::2, (ph & 1)::2]
+        want[:, 1:1 + sub.shape[1], 1:1 + sub.shape[2]] = sub
+        assert torch.equal(phases[ph * rows_out:(ph + 1) * rows_out].float().view(B, Ho + 2, Wo + 2, cin), want), ph
+    out = torch.full((rows_out, cout), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.gemm_bf16(phases, wk, bias=bias, act=_cabi.ACT_RELU, out_bf16=out, conv_taps=9, conv_stride=2, halo=(Ho + 2, Wo + 2),
+                    block_n=block_n)
+    ref = torch.relu(torch.nn.functional.conv2d(xin.permute(0, 3, 1, 2), wk.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2), bias,
+                                                stride=2, padding=1))
+    got = out.float().view(B, Ho + 2, Wo + 2, cout)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+    scale = max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() <= 2e-2 * scale
+    ring = out.float().view(B, Ho + 2, Wo + 2, cout)
+    assert ring[:, 0].abs().max() == 0 and ring[:, -1].abs().max() == 0 and ring[:, :, 0].abs().max() == 0 and ring[:, :, -1].abs().max() == 0
+    simt = torch.empty_like(out)
+    _cabi.gemm_bf16(phases, wk, bias=bias, act=_cabi.ACT_RELU, out_bf16=simt, conv_taps=9, conv_stride=2, halo=(Ho + 2, Wo + 2), simt=True)
+    assert (out.float() - simt.float()).abs().max().item() <= 2e-2 * scale
+    g9 = torch.empty(rows_out, 9 * cin, device=cuda_device, dtype=torch.bfloat16)
+    _cabi.call("hoigen_conv_gather_s2", rows.data_ptr(), g9.data_ptr(), B, H, W, cin, 9)
+    old = torch.empty_like(out)
+    _cabi.gemm_bf16(g9, wk, bias=bias, act=_cabi.ACT_RELU, out_bf16=old, halo=(Ho + 2, Wo + 2), block_n=block_n)
+    assert (out.float() - old.float()).abs().max().item() <= 1e-2 * scale
+
+
 def test_gemm_conv1x1_identity_epilogue(cuda_device):
     """1x1 convolution = plain GEMM over the haloed rows with the Bottleneck epilogue: relu(acc + bias + identity) with a
     bf16 identity added BEFORE the activation, halo rows written as zero (pair and one-CTA kernels)."""

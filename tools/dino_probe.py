@@ -45,6 +45,12 @@ with torch.no_grad():
     print(f"conv3 + downsample merged {t_kern:.3f} ms, separate {t_split:.3f} ms, max-abs feature difference "
           f"{(kern(imgs) - split(imgs)).abs().max().item():.3e}")
     del split
+    im2col = KernelDinoR50(r50)
+    im2col.implicit_stride2 = False                    # A/B: stride-2 3x3 convolutions through the nine-tap gather
+    t_g9 = timeit(lambda: im2col(imgs))
+    print(f"stride-2 3x3 as implicit GEMM over the four-phase split {t_kern:.3f} ms, nine-tap gather + GEMM {t_g9:.3f} ms, "
+          f"max-abs feature difference {(kern(imgs) - im2col(imgs)).abs().max().item():.3e}")
+    del im2col
     ref = r50(imgs)
     ref = ref / ref.norm(dim=-1, keepdim=True)
     cos = (kern(imgs) * ref).sum(-1).min().item()
