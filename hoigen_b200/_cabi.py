@@ -14,6 +14,7 @@ import torch
 from ._build import LIB_PATH
 
 ACT_NONE, ACT_QUICKGELU, ACT_RELU, ACT_EXP = 0, 1, 2, 3
+ABI_VERSION = 2          # HOIGEN_ABI_VERSION of include/hoigen_b200.h that the ctypes mirrors below follow
 
 
 class HoigenError(RuntimeError):
@@ -70,6 +71,9 @@ def load() -> C.CDLL:
             "hoigen_b200 has no CPU / PyTorch fallback.")
     lib = C.CDLL(str(path))
     lib.hoigen_abi_version.restype = C.c_int
+    if lib.hoigen_abi_version() != ABI_VERSION:     # a stale build would read the parameter structs with another layout
+        raise HoigenError(f"{path} has ABI version {lib.hoigen_abi_version()}, this package expects {ABI_VERSION}: rebuild it "
+                          "(python -m hoigen_b200._build --force)")
     lib.hoigen_last_error.restype = C.c_char_p
     lib.hoigen_init.argtypes = [C.c_int]
     for name, sig in _SIGNATURES.items():

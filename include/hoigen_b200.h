@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HOIGEN_ABI_VERSION 1
+#define HOIGEN_ABI_VERSION 2   /* 2: hoigen_gemm_params gained a2 / lda2 / k2 / conv_stride */
 #define HOIGEN_API __attribute__((visibility("default")))
 
 typedef void* hoigen_stream_t; /* cudaStream_t */

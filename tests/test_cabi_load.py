@@ -21,7 +21,7 @@ def test_library_builds_and_exports_all_declared_symbols():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_cabi.EXPORTED_SYMBOLS) == declared, "ctypes bindings and header disagree"
-    assert lib.hoigen_abi_version() == 1
+    assert lib.hoigen_abi_version() == _cabi.ABI_VERSION == 2
 
 
 def test_sass_contains_blackwell_instructions():
